@@ -1,0 +1,137 @@
+"""Generate golden vectors by running the UNMODIFIED reference in the build container.
+
+    python tests/golden/make_golden.py        # needs /root/reference; writes tests/golden/*.npz
+
+The reference ships no tests or fixtures, so these files are what pins the oracle
+(and through it the CUDA path).  Inputs are regenerated from seeds by ``oracle/`` generators; each fixture
+also stores input checksums so drift in the generators is detected, and small inputs are stored verbatim.
+"""
+import contextlib
+import copy
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_shims                                   # noqa: E402
+from oracle import mpn_oracle as mo                # noqa: E402
+from oracle import postproc_oracle as po           # noqa: E402
+
+MPN_CASES = {
+    # name: (N, C, graph seed, weight seed, L, n_cls, node_in_dim, node_fc_dims, planted, affine_jitter)
+    "mpn_shipped_L1": (48, 4, 11, 1, 1, 1, 2048, (1024, 512, 128), False, True),
+    "mpn_shipped_L1_planted": (60, 4, 12, 2, 1, 1, 2048, (1024, 512, 128), True, False),
+    "mpn_small_L4_cls2": (40, 4, 13, 3, 4, 2, 64, (48, 40), True, True),
+    "mpn_small_L0": (24, 3, 14, 4, 0, 1, 64, (48,), False, True),
+    "mpn_small_L3_cls3_c5": (55, 5, 15, 5, 3, 3, 96, (64, 48, 40), True, True),
+}
+
+POST_CASES = {
+    # name: (N, C, seed, flip_on, flip_off, single_dir)
+    "post_n40_c4": (40, 4, 101, 0.04, 0.04, 0.02),
+    "post_n64_c4": (64, 4, 102, 0.06, 0.03, 0.03),
+    "post_n90_c5": (90, 5, 103, 0.05, 0.05, 0.02),
+    "post_n120_c4_noisy": (120, 4, 104, 0.10, 0.05, 0.05),
+    "post_n36_c3": (36, 3, 105, 0.08, 0.02, 0.04),
+    "post_n50_c4_clean": (50, 4, 106, 0.0, 0.0, 0.0),
+}
+
+
+def run_mpn_case(MOTMPNet, name, spec):
+    N, C, gseed, wseed, L, n_cls, din, fcd, planted, jitter = spec
+    params = mo.shipped_model_params(L, n_cls, din, fcd)
+    x, edge_index, cam, ident = mo.synth_graph(N, C, gseed, D=din, planted=planted)
+    sd = mo.init_weights(params, "resnet101", wseed, affine_jitter=jitter)
+    torch.manual_seed(0)
+    model = MOTMPNet(copy.deepcopy(params), None, "resnet101").eval()
+    assert list(model.state_dict().keys()) == list(sd.keys()), "oracle key layout differs from the reference"
+    for k, v in model.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        # edge features exactly as inference.py:453-456
+        F = torch.nn.functional
+        d = F.pairwise_distance(x[edge_index[0]], x[edge_index[1]]).view(-1, 1)
+        c = 1 - F.cosine_similarity(x[edge_index[0]], x[edge_index[1]]).view(-1, 1)
+        edge_attr = torch.cat((d, c), dim=1)
+        Data = sys.modules["torch_geometric.data"].Data
+        data = Data(x=x, edge_index=edge_index, edge_attr=edge_attr)
+        out, h = model(data)
+        logits = [t.numpy() for t in out["classified_edges"]]
+        prob = torch.softmax(out["classified_edges"][-1], dim=1).numpy()       # inference.py:475-479
+        pred = torch.argmax(out["classified_edges"][-1], dim=1).numpy()
+        m64 = copy.deepcopy(model).double()
+        out64, h64 = m64(Data(x=x.double(), edge_index=edge_index, edge_attr=edge_attr.double()))
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        spec=np.array([N, C, gseed, wseed, L, n_cls, din, int(planted), int(jitter)], dtype=np.int64),
+        fc_dims=np.array(fcd, dtype=np.int64),
+        x_checksum=np.array([x.double().sum().item(), x.double().abs().sum().item()]),
+        w_checksum=np.array([sum(v.double().sum().item() for v in sd.values())]),
+        edge_index=edge_index.numpy().astype(np.int32),
+        edge_attr=edge_attr.numpy(),
+        h=h.numpy(), prob=prob, pred=pred,
+        n_logits=np.array([len(logits)]),
+        **{f"logits{i}": l for i, l in enumerate(logits)},
+        **{f"logits64_{i}": t.numpy() for i, t in enumerate(out64["classified_edges"])},
+        h64=h64.numpy(),
+    )
+    print(name, "E=%d" % edge_index.shape[1], "max|logit|=%.3f" % np.abs(logits[-1]).max(),
+          "active=%d" % int(pred.sum()))
+
+
+def run_post_case(ref_utils, ref_inference, name, spec):
+    import networkx as nx
+    N, C, seed, f_on, f_off, sdir = spec
+    src, dst, prob1, pred, cam = po.planted_prediction_graph(N, C, seed, flip_on=f_on, flip_off=f_off,
+                                                             single_dir=sdir, dense=True)
+    Data = sys.modules["torch_geometric.data"].Data
+    edge_index = torch.from_numpy(np.stack([src, dst]))
+    data = Data(x=torch.zeros(N, 1), edge_index=edge_index)
+    edge_list = edge_index.numpy()
+    preds_prob = torch.from_numpy(np.stack([1 - prob1, prob1], axis=1))
+    out = {}
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        predictions = torch.from_numpy(pred.copy())
+        act_list = [(edge_list[0][p], edge_list[1][p]) for p in torch.where(predictions == 1)[0]]
+        ID0, _ = ref_utils.compute_SCC_and_Clusters(nx.DiGraph(act_list), N)
+        out["labels_initial"] = ID0.numpy()
+        for tag, cfg in (("full", (True, True, True)), ("cut_only", (True, False, False)),
+                         ("prune_only", (False, True, False)), ("split_only", (False, False, True)),
+                         ("cut_prune", (True, True, False))):
+            predictions = torch.from_numpy(pred.copy())
+            act_list = [(edge_list[0][p], edge_list[1][p]) for p in torch.where(predictions == 1)[0]]
+            CONFIG = {"CUTTING": cfg[0], "PRUNING": cfg[1], "SPLITTING": cfg[2]}
+            ID, P = ref_inference.post_processing(C, ID0.clone(), act_list, predictions, edge_list, CONFIG, data, preds_prob)
+            out["labels_" + tag] = ID.numpy()
+            out["pred_" + tag] = P.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"),
+                        spec=np.array([N, C, seed], dtype=np.int64), src=src.astype(np.int32), dst=dst.astype(np.int32),
+                        prob1=prob1, pred=pred.astype(np.int8), **out)
+    print(name, "E=%d active %d -> %d, clusters %d" % (src.size, pred.sum(), out["pred_full"].sum(),
+                                                       out["labels_full"].max() + 1))
+
+
+def main():
+    if not ref_shims.reference_available():
+        raise SystemExit("reference not found at %s" % ref_shims.REFERENCE_ROOT)
+    MOTMPNet, ref_utils, ref_inference, _ = ref_shims.load_reference()
+    only = set(sys.argv[1:])
+    for name, spec in MPN_CASES.items():
+        if not only or name in only:
+            run_mpn_case(MOTMPNet, name, spec)
+    for name, spec in POST_CASES.items():
+        if not only or name in only:
+            run_post_case(ref_utils, ref_inference, name, spec)
+
+
+if __name__ == "__main__":
+    main()
