@@ -1,0 +1,18 @@
+"""B200-native tracklet-graph message passing (drop-in for models/mpn.py + the post-processing of inference.py).
+
+Public surface (same names as the reference where one exists):
+    MOTMPNet                     models/mpn.py:144
+    edge_features                inference.py:453-456
+    post_processing              inference.py:70
+    pruning, splitting, remove_edges_single_direction, compute_SCC_and_Clusters      utils.py
+    ShardedMPN                   row-block sharded forward across the GPUs of one box (new)
+"""
+from . import _lib
+from .edge_features import edge_features
+from .graph import TrackletGraph, graph_for
+from .mpn import MOTMPNet
+from .postprocess import (compute_SCC_and_Clusters, post_processing, pruning, remove_edges_single_direction,
+                          splitting)
+
+__all__ = ["MOTMPNet", "edge_features", "post_processing", "pruning", "splitting", "remove_edges_single_direction",
+           "compute_SCC_and_Clusters", "TrackletGraph", "graph_for", "_lib"]

@@ -1,0 +1,176 @@
+// K1: initial edge features (inference.py:453-456)
+//   edge_attr[e] = [ ||x_r - x_c + eps||_2 , 1 - cos(x_r, x_c) ],  eps = 1e-6 (F.pairwise_distance), cos eps = 1e-8
+// via the Gram matrix G = X X^T:
+//   ||a - b + eps||^2 = |a|^2 + |b|^2 - 2 a.b + 2 eps (sum a - sum b) + D eps^2
+//   cos = a.b / max(|a||b|, 1e-8)
+// The reference gathers two [E,D] copies (8 KB per edge each); here the only per-edge traffic is one
+// Gram read and one 8-byte write.  Pairs whose squared distance cancels badly (near-duplicate embeddings,
+// d^2 < 1% of |a|^2+|b|^2) are recomputed directly from the rows, exactly as the reference sums them.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mpn {
+
+constexpr float PAIRWISE_EPS = 1e-6f;
+constexpr float COSINE_EPS = 1e-8f;
+constexpr float REFINE_FRACTION = 1e-2f;
+
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, int n, int D, double* __restrict__ sq,
+                                                        double* __restrict__ sx) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = gwarp; r < n; r += nwarps) {
+    const float* p = x + (size_t)r * D;
+    double s = 0.0, q = 0.0;
+    for (int k = lane; k < D; k += 32) {
+      const double v = p[k];
+      s += v;
+      q += v * v;
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) { sq[r] = q; sx[r] = s; }
+  }
+}
+
+// one warp per task (a run of edges of one row): coalesced Gram reads when the row's columns are consecutive
+__global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_graph g, int r0, int r1, const float* __restrict__ G,
+                                                                  const double* __restrict__ sq, const double* __restrict__ sx,
+                                                                  int D, float2* __restrict__ edge_attr,
+                                                                  int* __restrict__ refine_list, int* __restrict__ refine_count) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int t0 = g.taskptr[r0], t1 = g.taskptr[r1];
+  const double eps = (double)PAIRWISE_EPS;
+  for (int t = t0 + gwarp; t < t1; t += nwarps) {
+    const int row = g.task_row[t];
+    const int beg = g.rowptr[row] + (t - g.taskptr[row]) * g.chunk;
+    const int end = min(beg + g.chunk, g.rowptr[row + 1]);
+    const int grow = row + g.row_offset;
+    const double sa = sq[grow], xa = sx[grow];
+    const float* Grow = G + (size_t)(row - r0) * g.n_cols;
+    for (int e = beg + lane; e < end; e += 32) {
+      const int c = g.col[e];
+      const double gij = Grow[c];
+      const double sb = sq[c];
+      double d2 = sa + sb - 2.0 * gij + 2.0 * eps * (xa - sx[c]) + D * eps * eps;
+      if (d2 < (double)REFINE_FRACTION * (sa + sb)) {
+        const int slot = atomicAdd(refine_count, 1);
+        refine_list[slot] = e;
+      }
+      if (d2 < 0.0) d2 = 0.0;
+      const double denom = fmax(sqrt(sa) * sqrt(sb), (double)COSINE_EPS);
+      edge_attr[e] = make_float2((float)sqrt(d2), (float)(1.0 - gij / denom));
+    }
+  }
+}
+
+// direct recomputation for the flagged pairs (one warp per pair), fp32 elementwise like ATen
+__global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_graph g, const float* __restrict__ x, int D,
+                                                                  const int* __restrict__ refine_list,
+                                                                  const int* __restrict__ refine_count,
+                                                                  float2* __restrict__ edge_attr) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n = *refine_count;
+  for (int i = gwarp; i < n; i += nwarps) {
+    const int e = refine_list[i];
+    int lo = 0, hi = g.n_nodes;                       // row = last r with rowptr[r] <= e
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (g.rowptr[mid] <= e) lo = mid; else hi = mid;
+    }
+    const float* a = x + (size_t)(lo + g.row_offset) * D;
+    const float* b = x + (size_t)g.col[e] * D;
+    double d2 = 0.0, ab = 0.0, aa = 0.0, bb = 0.0;
+    for (int k = lane; k < D; k += 32) {
+      const float av = a[k], bv = b[k];
+      const float df = av - bv + PAIRWISE_EPS;
+      d2 += (double)df * df;
+      ab += (double)av * bv;
+      aa += (double)av * av;
+      bb += (double)bv * bv;
+    }
+    d2 = warp_sum(d2); ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
+    if (lane == 0) {
+      const double denom = fmax(sqrt(aa) * sqrt(bb), (double)COSINE_EPS);
+      edge_attr[e] = make_float2((float)sqrt(d2), (float)(1.0 - ab / denom));
+    }
+  }
+}
+
+struct EfLayout {
+  double *sq, *sx;
+  float* G;
+  int *refine_list, *refine_count;
+  void* gemm_ws;
+  size_t gemm_ws_bytes;
+  int rows_per_block;
+  size_t total;
+};
+
+static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) {
+  EfLayout L;
+  Arena a(ws, ws_bytes);
+  L.sq = a.take<double>(g->n_cols);
+  L.sx = a.take<double>(g->n_cols);
+  const size_t budget = (size_t)2 << 30;
+  size_t rows = budget / ((size_t)g->n_cols * sizeof(float));
+  if (rows < 128) rows = 128;
+  if (rows > (size_t)g->n_nodes) rows = g->n_nodes;
+  L.rows_per_block = (int)rows;
+  L.G = a.take<float>(rows * (size_t)g->n_cols);
+  L.refine_list = a.take<int>((size_t)(g->n_edges > 0 ? g->n_edges : 1));
+  L.refine_count = a.take<int>(1);
+  L.gemm_ws_bytes = gemm_tc_workspace_bytes((int)rows, g->n_cols, D);
+  L.gemm_ws = L.gemm_ws_bytes ? (void*)a.take<char>(L.gemm_ws_bytes) : nullptr;
+  L.total = a.off;
+  return L;
+}
+
+}  // namespace mpn
+
+using namespace mpn;
+
+extern "C" {
+
+size_t mpn_edge_features_workspace_bytes(const mpn_graph* g, int32_t D) {
+  if (!g || D <= 0) return 0;
+  return ef_layout(g, D, nullptr, 0).total + 256;
+}
+
+int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge_attr, int use_tc, void* ws, size_t ws_bytes,
+                      void* stream) {
+  MPN_REQUIRE(g && x && D > 0 && ws, "edge_features: NULL argument");
+  MPN_REQUIRE(edge_attr || g->n_edges == 0, "edge_features: NULL output");
+  MPN_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  EfLayout L = ef_layout(g, D, ws, ws_bytes);
+  if (L.total > ws_bytes) {
+    set_error("edge_features workspace too small: need %zu bytes, have %zu", L.total, ws_bytes);
+    return MPN_ERR_WORKSPACE;
+  }
+  if (g->n_edges == 0) return MPN_OK;
+  row_stats_kernel<<<min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st>>>(x, g->n_cols, D, L.sq, L.sx);
+  MPN_LAUNCH_OK();
+  MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, sizeof(int), st));
+  for (int r0 = 0; r0 < g->n_nodes; r0 += L.rows_per_block) {
+    const int r1 = min(r0 + L.rows_per_block, g->n_nodes);
+    const float* Ablk = x + (size_t)(g->row_offset + r0) * D;
+    if (use_tc && gemm_tc_supported(r1 - r0, g->n_cols, D))
+      MPN_TRY(gemm_nt_tc(Ablk, x, nullptr, L.G, r1 - r0, g->n_cols, D, L.gemm_ws, L.gemm_ws_bytes, st));
+    else
+      MPN_TRY(gemm_nt_simt(Ablk, x, nullptr, nullptr, nullptr, L.G, r1 - r0, g->n_cols, D, st));
+    edge_feature_gather_kernel<<<kNumSMs * 8, 256, 0, st>>>(*g, r0, r1, L.G, L.sq, L.sx, D, (float2*)edge_attr,
+                                                           L.refine_list, L.refine_count);
+    MPN_LAUNCH_OK();
+  }
+  edge_feature_refine_kernel<<<kNumSMs * 4, 256, 0, st>>>(*g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+}  // extern "C"

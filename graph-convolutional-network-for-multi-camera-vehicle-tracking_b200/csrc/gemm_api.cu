@@ -1,0 +1,22 @@
+// C ABI of the GEMM building block (tests + roofline bench).
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace mpn;
+
+extern "C" {
+
+size_t mpn_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int impl) {
+  return impl == 1 ? gemm_tc_workspace_bytes(M, N, K) + 256 : 256;
+}
+
+int mpn_gemm_nt(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K, int impl,
+                void* ws, size_t ws_bytes, void* stream) {
+  MPN_REQUIRE(A && B && C, "gemm: NULL argument");
+  if (impl == 0) return gemm_nt_simt(A, B, bias, nullptr, nullptr, C, M, N, K, (cudaStream_t)stream);
+  MPN_REQUIRE(impl == 1, "gemm: impl must be 0 (simt) or 1 (tcgen05)");
+  MPN_REQUIRE(gemm_tc_supported(M, N, K), "gemm: shape %d x %d x %d not supported by the tcgen05 kernel", M, N, K);
+  return gemm_nt_tc(A, B, bias, C, M, N, K, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

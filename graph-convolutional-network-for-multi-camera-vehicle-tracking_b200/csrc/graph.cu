@@ -1,0 +1,147 @@
+// K0: int32 CSR + task tables from the reference's edge_index (models/mpn.py:44 `row, col = edge_index`).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace mpn {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// One pass over the edges: narrow to int32, validate ordering / ranges, emit row boundaries.
+template <typename IdxT>
+__global__ void __launch_bounds__(256) csr_scan_edges(const IdxT* __restrict__ row, const IdxT* __restrict__ col,
+                                                      long long E, int n_rows, int n_cols, int row_offset,
+                                                      int* __restrict__ rowptr, int* __restrict__ col32,
+                                                      int* __restrict__ flags) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    long long r = (long long)row[e] - row_offset, c = (long long)col[e];
+    if (r < 0 || r >= n_rows || c < 0 || c >= n_cols) { bad |= 2; continue; }
+    col32[e] = (int)c;
+    long long pr = -1, pc = -1;
+    if (e > 0) {
+      pr = (long long)row[e - 1] - row_offset;
+      pc = (long long)col[e - 1];
+      if (pr > r || (pr == r && pc >= c)) bad |= 1;
+      if (pr < 0 || pr >= n_rows) pr = r;          // reported via the other thread's range check
+    }
+    for (long long q = pr + 1; q <= r; ++q) rowptr[q] = (int)e;      // rows (pr, r] start at e
+    if (e == E - 1)
+      for (long long q = r + 1; q <= n_rows; ++q) rowptr[q] = (int)E;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+__global__ void csr_empty(int n_rows, int* rowptr) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_rows; i += gridDim.x * blockDim.x) rowptr[i] = 0;
+}
+
+// Single-block exclusive scan of ceil(deg/chunk) -> taskptr, n_tasks.  n_rows <= a few million.
+__global__ void __launch_bounds__(1024) task_scan(const int* __restrict__ rowptr, int n_rows, int chunk,
+                                                  int* __restrict__ taskptr, int* __restrict__ n_tasks) {
+  __shared__ int strip_sum[1024];
+  const int t = threadIdx.x;
+  const int per = (n_rows + 1023) / 1024;
+  const int lo = min(t * per, n_rows), hi = min(lo + per, n_rows);
+  int s = 0;
+  for (int r = lo; r < hi; ++r) s += (rowptr[r + 1] - rowptr[r] + chunk - 1) / chunk;
+  strip_sum[t] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {          // Hillis-Steele inclusive scan
+    int v = (t >= off) ? strip_sum[t - off] : 0;
+    __syncthreads();
+    strip_sum[t] += v;
+    __syncthreads();
+  }
+  int run = (t == 0) ? 0 : strip_sum[t - 1];
+  for (int r = lo; r < hi; ++r) {
+    taskptr[r] = run;
+    run += (rowptr[r + 1] - rowptr[r] + chunk - 1) / chunk;
+  }
+  if (t == 1023) {
+    taskptr[n_rows] = strip_sum[1023];
+    *n_tasks = strip_sum[1023];
+  }
+}
+
+__global__ void task_fill(const int* __restrict__ taskptr, int n_rows, int max_tasks, int* __restrict__ task_row) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
+    for (int t = taskptr[r]; t < taskptr[r + 1] && t < max_tasks; ++t) task_row[t] = r;
+}
+
+template <typename IdxT>
+static int graph_build_impl(mpn_graph* g, const IdxT* row, const IdxT* col, cudaStream_t st) {
+  MPN_REQUIRE(g != nullptr, "graph is NULL");
+  MPN_REQUIRE(g->n_nodes > 0 && g->n_cols > 0 && g->n_edges >= 0, "bad graph sizes");
+  MPN_REQUIRE(g->n_edges < (1ll << 31), "n_edges must be < 2^31 per shard");
+  MPN_REQUIRE(g->chunk >= 32 && g->chunk <= 4096 && (g->chunk & (g->chunk - 1)) == 0, "chunk must be a power of two in [32,4096]");
+  MPN_REQUIRE(g->max_tasks >= g->n_edges / g->chunk + g->n_nodes, "max_tasks too small (need E/chunk + N)");
+  MPN_REQUIRE(g->rowptr && g->taskptr && g->task_row && g->n_tasks && (g->col || g->n_edges == 0), "graph table pointer is NULL");
+  int* flags = g->n_tasks;                        // reused as the flag word until task_scan overwrites it
+  MPN_CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(int), st));
+  if (g->n_edges == 0) {
+    csr_empty<<<div_up(g->n_nodes + 1, 256), 256, 0, st>>>(g->n_nodes, g->rowptr);
+  } else {
+    int grid = (int)min((long long)kNumSMs * 16, (long long)div_up(g->n_edges, 256));
+    csr_scan_edges<IdxT><<<grid, 256, 0, st>>>(row, col, g->n_edges, g->n_nodes, g->n_cols, g->row_offset,
+                                               g->rowptr, g->col, flags);
+  }
+  MPN_LAUNCH_OK();
+  int h_flags = 0;
+  MPN_CUDA_OK(cudaMemcpyAsync(&h_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MPN_CUDA_OK(cudaStreamSynchronize(st));
+  if (h_flags & 2) {
+    set_error("edge_index has node ids outside [row_offset, row_offset+n_nodes) x [0, n_cols)");
+    return MPN_ERR_INVALID;
+  }
+  if (h_flags & 1) {
+    set_error("edge_index is not strictly (row, col)-sorted (unsorted or duplicate edges)");
+    return MPN_ERR_UNSORTED;
+  }
+  task_scan<<<1, 1024, 0, st>>>(g->rowptr, g->n_nodes, g->chunk, g->taskptr, g->n_tasks);
+  MPN_LAUNCH_OK();
+  task_fill<<<min(kNumSMs * 8, div_up(g->n_nodes, 256)), 256, 0, st>>>(g->taskptr, g->n_nodes, g->max_tasks, g->task_row);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+}  // namespace mpn
+
+extern "C" {
+
+int mpn_abi_version(void) { return MPN_B200_ABI_VERSION; }
+const char* mpn_last_error(void) { return mpn::g_err; }
+
+int mpn_check_device(int dev) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || dev < 0 || dev >= n) {
+    mpn::set_error("no CUDA device %d (device count %d): the MPN path has no CPU fallback", dev, n);
+    cudaGetLastError();
+    return MPN_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess || p.major != 10) {
+    mpn::set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, p.major, p.minor);
+    return MPN_ERR_NO_DEVICE;
+  }
+  return MPN_OK;
+}
+
+int mpn_graph_build(mpn_graph* g, const int64_t* edge_index_dev, void* stream) {
+  if (!g) { mpn::set_error("graph is NULL"); return MPN_ERR_INVALID; }
+  return mpn::graph_build_impl<long long>(g, (const long long*)edge_index_dev,
+                                          (const long long*)edge_index_dev + g->n_edges, (cudaStream_t)stream);
+}
+
+int mpn_graph_build_i32(mpn_graph* g, const int32_t* row_dev, const int32_t* col_dev, void* stream) {
+  return mpn::graph_build_impl<int>(g, row_dev, col_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,19 @@
+// Internal (non-ABI) declarations shared between the translation units of libmpn_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mpn {
+
+// gemm_simt.cu
+int gemm_nt_simt(const float* A, const float* B, const float* bias, const float* a_scale, const float* a_shift,
+                 float* C, int M, int N, int K, cudaStream_t st);
+
+// gemm_tc.cu  (tcgen05 3xTF32; operands are pre-split hi/lo planes)
+size_t gemm_tc_workspace_bytes(int M, int N, int K);
+int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
+               void* workspace, size_t workspace_bytes, cudaStream_t st);
+bool gemm_tc_supported(int M, int N, int K);
+
+}  // namespace mpn

@@ -1,0 +1,869 @@
+// MOTMPNet.forward (models/mpn.py:250-299) as HBM-bound edge sweeps + small node kernels.
+//
+// Algebra (exact up to fp32 re-association):
+//   edge update  y  = W_e[68->4]·[h_r;h_c;e] + b = Ps[row] + Pd[col] + We·e      (models/mpn.py:48,68-69)
+//                e' = relu(BN(y))                       BN over all E edges        (models/mlp.py:16)
+//   node update  z  = W_n[36->32]·[h_r;e'] + b = A[row] + Wn·e'                    (models/mpn.py:97-98)
+//                h' = segment_sum_row(relu(BN(z)))      BN over all E edges        (models/mpn.py:99,202)
+// BatchNorm uses batch statistics, so every BN is a global reduction followed by a second sweep.
+// Moments are accumulated in fp64, block partials are reduced in a fixed order (deterministic).
+#include <new>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mpn {
+
+// ------------------------------------------------------------------------------------------------
+// folded constants living in device memory (floats)
+// ------------------------------------------------------------------------------------------------
+enum {
+  FC_ENC1_W = 0,     // [4][2]  s1 * W1
+  FC_ENC1_C = 8,     // [4]     s1 * b1 + t1
+  FC_ENC2_W = 12,    // [4][4]  s2 * W2
+  FC_ENC2_C = 28,    // [4]
+  FC_EDGE_WE = 32,   // [4][4]  W_edge[:, 64:68]
+  FC_BN3_S = 48,     // [4]     edge-model BN scale of the most recent finalised step
+  FC_BN3_T = 52,     // [4]
+  FC_NODE_WE = 64,   // [32][4] s4 * W_node[:, 32:36]
+  FC_BN4_S = 192,    // [32]
+  FC_BN4_T = 224,    // [32]
+  FC_CLS_W = 256,    // [2][4]
+  FC_CLS_B = 264,    // [2]
+  FC_TOTAL = 272
+};
+
+constexpr int SUMS = MPN_SUMS_DOUBLES;     // 96 doubles per partial row
+constexpr int SWEEP_THREADS = 256;
+constexpr int SWEEP_BLOCKS_PER_SM = 4;
+constexpr int SWEEP_GRID = kNumSMs * SWEEP_BLOCKS_PER_SM;
+constexpr float BN_EPS = 1e-5f;
+
+struct EdgeConsts {           // staged in shared memory by every sweep
+  float v[FC_TOTAL];
+};
+
+__device__ __forceinline__ void load_consts(EdgeConsts& sc, const float* __restrict__ consts) {
+  for (int i = threadIdx.x; i < FC_TOTAL; i += blockDim.x) sc.v[i] = consts[i];
+  __syncthreads();
+}
+
+// encoder edge MLP with folded BatchNorm: 2 -> 4 -> 4, ReLU after each (models/mpn.py:128-142)
+__device__ __forceinline__ void enc_layer1(const EdgeConsts& sc, float2 ea, float (&a1)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    a1[j] = fmaxf(fmaf(sc.v[FC_ENC1_W + 2 * j], ea.x, fmaf(sc.v[FC_ENC1_W + 2 * j + 1], ea.y, sc.v[FC_ENC1_C + j])), 0.f);
+}
+__device__ __forceinline__ void enc_layer2_pre(const float* __restrict__ w2 /*[4][4]*/, const float* __restrict__ c2,
+                                               const float (&a1)[4], float (&u)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float s = c2[j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s = fmaf(w2[4 * j + k], a1[k], s);
+    u[j] = s;
+  }
+}
+__device__ __forceinline__ void enc_full(const EdgeConsts& sc, float2 ea, float (&e0)[4]) {
+  float a1[4];
+  enc_layer1(sc, ea, a1);
+  enc_layer2_pre(&sc.v[FC_ENC2_W], &sc.v[FC_ENC2_C], a1, e0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) e0[j] = fmaxf(e0[j], 0.f);
+}
+// y = Ps[row] + Pd[col] + We·e_in
+__device__ __forceinline__ void edge_pre(const EdgeConsts& sc, const float4 ps, const float4 pd, const float (&ein)[4], float (&y)[4]) {
+  const float p[4] = {ps.x + pd.x, ps.y + pd.y, ps.z + pd.z, ps.w + pd.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float s = p[j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s = fmaf(sc.v[FC_EDGE_WE + 4 * j + k], ein[k], s);
+    y[j] = s;
+  }
+}
+__device__ __forceinline__ void bn3_relu(const EdgeConsts& sc, const float (&y)[4], float (&e)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) e[j] = fmaxf(fmaf(sc.v[FC_BN3_S + j], y[j], sc.v[FC_BN3_T + j]), 0.f);
+}
+
+struct TaskRange {
+  int row, beg, end;
+};
+__device__ __forceinline__ TaskRange task_range(const mpn_graph& g, int t) {
+  TaskRange r;
+  r.row = g.task_row[t];
+  const int rb = g.rowptr[r.row];
+  r.beg = rb + (t - g.taskptr[r.row]) * g.chunk;
+  r.end = min(r.beg + g.chunk, g.rowptr[r.row + 1]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat sweeps over edge_attr for the two encoder BatchNorms
+// ------------------------------------------------------------------------------------------------
+// STAGE 0: sums of (a, b, aa, ab, bb);  STAGE 1: sums of u[4], u^2[4] with u = W2·relu(BN1(W1·ea+b1)) + b2
+template <int STAGE>
+__global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_kernel(const float2* __restrict__ edge_attr, long long E,
+                                                                    const float* __restrict__ consts,
+                                                                    const float* __restrict__ small,
+                                                                    double* __restrict__ partials) {
+  __shared__ EdgeConsts sc;
+  __shared__ double red[(SWEEP_THREADS / 32) * 8];
+  __shared__ float w2raw[20];
+  load_consts(sc, consts);
+  if (STAGE == 1) {
+    if (threadIdx.x < 16) w2raw[threadIdx.x] = small[MPN_W_ENC2_W + threadIdx.x];
+    else if (threadIdx.x < 20) w2raw[threadIdx.x] = small[MPN_W_ENC2_B + threadIdx.x - 16];
+    __syncthreads();
+  }
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    const float2 ea = ldg_stream2(edge_attr + e);
+    if (STAGE == 0) {
+      const double a = ea.x, b = ea.y;
+      acc[0] += a; acc[1] += b; acc[2] += a * a; acc[3] += a * b; acc[4] += b * b;
+    } else {
+      float a1[4], u[4];
+      enc_layer1(sc, ea, a1);
+      enc_layer2_pre(w2raw, w2raw + 16, a1, u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const double d = u[j]; acc[j] += d; acc[4 + j] += d * d; }
+    }
+  }
+  block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SA: moments of the edge-update pre-activation y (and optionally materialise y)
+//   SRC 0: e_in = encoder(edge_attr[e])            (step 1)
+//   SRC 1: e_in = relu(BN3_prev(ybuf[e]))          (step >= 2; ybuf updated in place)
+// ------------------------------------------------------------------------------------------------
+template <int SRC, bool WRITE_Y>
+__global__ void __launch_bounds__(SWEEP_THREADS) edge_moments_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
+                                                                     const float4* __restrict__ Ps, const float4* __restrict__ Pd,
+                                                                     float4* __restrict__ ybuf, const float* __restrict__ consts,
+                                                                     double* __restrict__ partials) {
+  __shared__ EdgeConsts sc;
+  __shared__ double red[(SWEEP_THREADS / 32) * 8];
+  load_consts(sc, consts);
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * SWEEP_THREADS) >> 5;
+  const int n_tasks = *g.n_tasks;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = gwarp; t < n_tasks; t += nwarps) {
+    const TaskRange tr = task_range(g, t);
+    const float4 ps = Ps[tr.row];
+    for (int e = tr.beg + lane; e < tr.end; e += 32) {
+      const int c = ldg_stream_i32(g.col + e);
+      const float4 pd = __ldg(Pd + c);
+      float ein[4], y[4];
+      if (SRC == 0) {
+        enc_full(sc, ldg_stream2(edge_attr + e), ein);
+      } else {
+        const float4 yp = ybuf[e];
+        const float ypv[4] = {yp.x, yp.y, yp.z, yp.w};
+        bn3_relu(sc, ypv, ein);
+      }
+      edge_pre(sc, ps, pd, ein, y);
+      if (WRITE_Y) ybuf[e] = make_float4(y[0], y[1], y[2], y[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const double d = y[j]; acc[j] += d; acc[4 + j] += d * d; }
+    }
+  }
+  block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SB: e' = relu(BN3(y)); per-task S1 = sum e' (for the closed-form node-BN moments), global T2 = sum e' e'^T
+//   YSRC 0: recompute y from (edge_attr, col, Ps, Pd);  YSRC 1: read y from ybuf
+// ------------------------------------------------------------------------------------------------
+template <int YSRC>
+__device__ __forceinline__ void load_eprime(const EdgeConsts& sc, const mpn_graph& g, int e, const float4 ps,
+                                            const float2* __restrict__ edge_attr, const float4* __restrict__ Pd,
+                                            const float4* __restrict__ ybuf, float (&ep)[4]) {
+  float y[4];
+  if (YSRC == 0) {
+    const int c = ldg_stream_i32(g.col + e);
+    const float4 pd = __ldg(Pd + c);
+    float ein[4];
+    enc_full(sc, ldg_stream2(edge_attr + e), ein);
+    edge_pre(sc, ps, pd, ein, y);
+  } else {
+    const float4 yy = ldg_stream4(ybuf + e);
+    y[0] = yy.x; y[1] = yy.y; y[2] = yy.z; y[3] = yy.w;
+  }
+  bn3_relu(sc, y, ep);
+}
+
+template <int YSRC>
+__global__ void __launch_bounds__(SWEEP_THREADS) node_moments_sweep_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
+                                                                           const float4* __restrict__ Ps, const float4* __restrict__ Pd,
+                                                                           const float4* __restrict__ ybuf, const float* __restrict__ consts,
+                                                                           float4* __restrict__ s1_task, double* __restrict__ partials) {
+  __shared__ EdgeConsts sc;
+  __shared__ double red[(SWEEP_THREADS / 32) * 10];
+  load_consts(sc, consts);
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * SWEEP_THREADS) >> 5;
+  const int n_tasks = *g.n_tasks;
+  double t2[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = gwarp; t < n_tasks; t += nwarps) {
+    const TaskRange tr = task_range(g, t);
+    const float4 ps = (YSRC == 0) ? Ps[tr.row] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f};
+    float q[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int e = tr.beg + lane; e < tr.end; e += 32) {
+      float ep[4];
+      load_eprime<YSRC>(sc, g, e, ps, edge_attr, Pd, ybuf, ep);
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        s1[a] += ep[a];
+#pragma unroll
+        for (int b = a; b < 4; ++b) { q[idx] = fmaf(ep[a], ep[b], q[idx]); ++idx; }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) s1[a] = warp_sum(s1[a]);
+    if (lane == 0) s1_task[t] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t2[i] += (double)q[i];      // <= chunk/32 fp32 terms per lane, then fp64
+  }
+  block_sum_doubles<10, SWEEP_THREADS>(t2, red, partials + (size_t)blockIdx.x * SUMS + 64);
+}
+
+// per-node part of the closed-form node-BN moments:
+//   m1[c] = sum_n deg_n A[n,c] + w_c·S1_n ;  m2[c] = sum_n deg_n A[n,c]^2 + 2 A[n,c] (w_c·S1_n)     (w_c = W_node[c, 32:36])
+constexpr int NM_THREADS = 256;
+constexpr int NM_GRID = kNumSMs * 2;
+__global__ void __launch_bounds__(NM_THREADS) node_moments_node_kernel(const mpn_graph g, const float* __restrict__ A,
+                                                                       const float4* __restrict__ s1_task,
+                                                                       const float* __restrict__ small,
+                                                                       double* __restrict__ partials) {
+  __shared__ double red[NM_THREADS / 32][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = (blockIdx.x * NM_THREADS + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * NM_THREADS) >> 5;
+  float w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = small[MPN_W_NODE_W + lane * 36 + 32 + k];
+  double m1 = 0.0, m2 = 0.0;
+  for (int n = gwarp; n < g.n_nodes; n += nwarps) {
+    const int deg = g.rowptr[n + 1] - g.rowptr[n];
+    if (deg == 0) continue;
+    double s[4] = {0, 0, 0, 0};
+    for (int t = g.taskptr[n]; t < g.taskptr[n + 1]; ++t) {
+      const float4 v = s1_task[t];
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+    const double a = A[(size_t)n * MPN_DH + lane];
+    const double qd = w[0] * s[0] + w[1] * s[1] + w[2] * s[2] + w[3] * s[3];
+    m1 += deg * a + qd;
+    m2 += deg * a * a + 2.0 * a * qd;
+  }
+  red[warp][lane] = m1;
+  red[warp][32 + lane] = m2;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    double s = 0.0;
+    for (int wv = 0; wv < NM_THREADS / 32; ++wv) s += red[wv][threadIdx.x];
+    partials[(size_t)blockIdx.x * SUMS + threadIdx.x] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SC: apply.  messages m = relu(BN4(A[row] + Wn·e')), per-task segment sums, logits, decisions.
+// Lane = edge; 32 fp32 accumulators per lane; a 31-shuffle transpose-reduce per task leaves channel c's
+// sum in lane c (deterministic: fixed shuffle tree, fixed task order in node_finalize).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float transpose_reduce32(float (&acc)[32], int lane) {
+  // after step with offset o the live values per lane halve; lane keeps the half selected by bit o of lane
+#pragma unroll
+  for (int o = 16, n = 16; o > 0; o >>= 1, n >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < n) {
+        const float send = upper ? acc[i] : acc[i + n];
+        const float keep = upper ? acc[i + n] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+  }
+  return acc[0];
+}
+
+template <int YSRC, bool CLASSIFY>
+__global__ void __launch_bounds__(SWEEP_THREADS) apply_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
+                                                              const float4* __restrict__ Ps, const float4* __restrict__ Pd,
+                                                              const float4* __restrict__ ybuf, const float* __restrict__ A,
+                                                              const float* __restrict__ consts, float* __restrict__ msg_task,
+                                                              float2* __restrict__ logits, uint8_t* __restrict__ pred,
+                                                              float* __restrict__ prob1) {
+  __shared__ EdgeConsts sc;
+  load_consts(sc, consts);
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * SWEEP_THREADS) >> 5;
+  const int n_tasks = *g.n_tasks;
+  for (int t = gwarp; t < n_tasks; t += nwarps) {
+    const TaskRange tr = task_range(g, t);
+    const float4 ps = (YSRC == 0) ? Ps[tr.row] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // folded A'[c] = s4[c]*A[row,c] + t4[c]; lane c computes it, every lane needs all 32
+    const float a_mine = fmaf(sc.v[FC_BN4_S + lane], A[(size_t)tr.row * MPN_DH + lane], sc.v[FC_BN4_T + lane]);
+    float ap[32], acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { ap[c] = __shfl_sync(0xffffffffu, a_mine, c); acc[c] = 0.f; }
+    for (int e = tr.beg + lane; e < tr.end; e += 32) {
+      float ep[4];
+      load_eprime<YSRC>(sc, g, e, ps, edge_attr, Pd, ybuf, ep);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float4 w = *reinterpret_cast<const float4*>(&sc.v[FC_NODE_WE + 4 * c]);
+        float z = fmaf(w.x, ep[0], ap[c]);
+        z = fmaf(w.y, ep[1], z);
+        z = fmaf(w.z, ep[2], z);
+        z = fmaf(w.w, ep[3], z);
+        acc[c] += fmaxf(z, 0.f);
+      }
+      if (CLASSIFY) {
+        float l0 = sc.v[FC_CLS_B + 0], l1 = sc.v[FC_CLS_B + 1];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          l0 = fmaf(sc.v[FC_CLS_W + k], ep[k], l0);
+          l1 = fmaf(sc.v[FC_CLS_W + 4 + k], ep[k], l1);
+        }
+        logits[e] = make_float2(l0, l1);
+        if (pred) pred[e] = (l1 > l0) ? 1 : 0;                  // argmax, tie -> class 0 (inference.py:479)
+        if (prob1) {
+          const float m = fmaxf(l0, l1);
+          const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+          prob1[e] = e1 / (e0 + e1);                           // softmax(dim=1)[:,1] (inference.py:475-477)
+        }
+      }
+    }
+    const float total = transpose_reduce32(acc, lane);
+    msg_task[(size_t)t * MPN_DH + lane] = total;
+  }
+}
+
+// L == 0 special case (models/mpn.py:295-297): classify the encoder output directly
+__global__ void __launch_bounds__(SWEEP_THREADS) classify_encoded_kernel(const float2* __restrict__ edge_attr, long long E,
+                                                                         const float* __restrict__ consts,
+                                                                         float2* __restrict__ logits, uint8_t* __restrict__ pred,
+                                                                         float* __restrict__ prob1) {
+  __shared__ EdgeConsts sc;
+  load_consts(sc, consts);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    float ep[4];
+    enc_full(sc, ldg_stream2(edge_attr + e), ep);
+    float l0 = sc.v[FC_CLS_B + 0], l1 = sc.v[FC_CLS_B + 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      l0 = fmaf(sc.v[FC_CLS_W + k], ep[k], l0);
+      l1 = fmaf(sc.v[FC_CLS_W + 4 + k], ep[k], l1);
+    }
+    logits[e] = make_float2(l0, l1);
+    if (pred) pred[e] = (l1 > l0) ? 1 : 0;
+    if (prob1) {
+      const float m = fmaxf(l0, l1);
+      const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+      prob1[e] = e1 / (e0 + e1);
+    }
+  }
+}
+
+__global__ void decide_kernel(const float2* __restrict__ logits, long long E, uint8_t* __restrict__ pred, float* __restrict__ prob1) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    const float2 l = logits[e];
+    if (pred) pred[e] = (l.y > l.x) ? 1 : 0;
+    if (prob1) {
+      const float m = fmaxf(l.x, l.y);
+      const float e0 = expf(l.x - m), e1 = expf(l.y - m);
+      prob1[e] = e1 / (e0 + e1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: fixed-order reduction of block partials -> sums; sums -> folded constants
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) finalize_kernel(int stage, const double* __restrict__ partials, int n_partials,
+                                                       const double* __restrict__ partials2, int n_partials2,
+                                                       double* __restrict__ sums, int do_reduce, int do_consts,
+                                                       float* __restrict__ consts, const float* __restrict__ small,
+                                                       double n_total) {
+  const int k = threadIdx.x;
+  if (do_reduce && k < SUMS) {
+    double s = 0.0;
+    if (stage == MPN_STAGE_NODE) {
+      if (k < 64) for (int p = 0; p < n_partials2; ++p) s += partials2[(size_t)p * SUMS + k];
+      else if (k < 74) for (int p = 0; p < n_partials; ++p) s += partials[(size_t)p * SUMS + k];
+    } else if (k < 8) {
+      for (int p = 0; p < n_partials; ++p) s += partials[(size_t)p * SUMS + k];
+    }
+    sums[k] = s;
+  }
+  __syncthreads();
+  if (!do_consts) return;
+  const double inv_n = 1.0 / n_total;
+  if (stage == MPN_STAGE_ENC0) {
+    // static constants
+    if (k < 16) consts[FC_EDGE_WE + k] = small[MPN_W_EDGE_W + (k >> 2) * 68 + 64 + (k & 3)];
+    if (k < 8) consts[FC_CLS_W + k] = small[MPN_W_CLS_W + k];
+    if (k < 2) consts[FC_CLS_B + k] = small[MPN_W_CLS_B + k];
+    if (k < 4) {
+      const double ma = sums[0] * inv_n, mb = sums[1] * inv_n;
+      const double caa = sums[2] * inv_n - ma * ma, cab = sums[3] * inv_n - ma * mb, cbb = sums[4] * inv_n - mb * mb;
+      const double w0 = small[MPN_W_ENC1_W + 2 * k], w1 = small[MPN_W_ENC1_W + 2 * k + 1], b = small[MPN_W_ENC1_B + k];
+      const double mean = w0 * ma + w1 * mb + b;
+      double var = w0 * w0 * caa + 2.0 * w0 * w1 * cab + w1 * w1 * cbb;
+      if (var < 0.0) var = 0.0;
+      const double s = (double)small[MPN_W_ENC1_G + k] / sqrt(var + (double)BN_EPS);
+      const double t = (double)small[MPN_W_ENC1_BETA + k] - s * mean;
+      consts[FC_ENC1_W + 2 * k] = (float)(s * w0);
+      consts[FC_ENC1_W + 2 * k + 1] = (float)(s * w1);
+      consts[FC_ENC1_C + k] = (float)(s * b + t);
+    }
+  } else if (stage == MPN_STAGE_ENC1 || stage == MPN_STAGE_EDGE) {
+    if (k < 4) {
+      const double mean = sums[k] * inv_n;
+      double var = sums[4 + k] * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const int G = (stage == MPN_STAGE_ENC1) ? MPN_W_ENC2_G : MPN_W_EDGE_G;
+      const int B = (stage == MPN_STAGE_ENC1) ? MPN_W_ENC2_BETA : MPN_W_EDGE_BETA;
+      const double s = (double)small[G + k] / sqrt(var + (double)BN_EPS);
+      const double t = (double)small[B + k] - s * mean;
+      if (stage == MPN_STAGE_ENC1) {
+        for (int j = 0; j < 4; ++j) consts[FC_ENC2_W + 4 * k + j] = (float)(s * small[MPN_W_ENC2_W + 4 * k + j]);
+        consts[FC_ENC2_C + k] = (float)(s * small[MPN_W_ENC2_B + k] + t);
+      } else {
+        consts[FC_BN3_S + k] = (float)s;
+        consts[FC_BN3_T + k] = (float)t;
+      }
+    }
+  } else if (stage == MPN_STAGE_NODE) {
+    if (k < 32) {
+      double w[4];
+      for (int j = 0; j < 4; ++j) w[j] = small[MPN_W_NODE_W + k * 36 + 32 + j];
+      double quad = 0.0;
+      int idx = 0;
+      for (int a = 0; a < 4; ++a)
+        for (int b = a; b < 4; ++b) quad += (a == b ? 1.0 : 2.0) * w[a] * w[b] * sums[64 + idx++];
+      const double mean = sums[k] * inv_n;
+      double var = (sums[32 + k] + quad) * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double s = (double)small[MPN_W_NODE_G + k] / sqrt(var + (double)BN_EPS);
+      const double t = (double)small[MPN_W_NODE_BETA + k] - s * mean;
+      consts[FC_BN4_S + k] = (float)s;
+      consts[FC_BN4_T + k] = (float)t;
+      for (int j = 0; j < 4; ++j) consts[FC_NODE_WE + 4 * k + j] = (float)(s * w[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// node encoder pieces: column statistics of a [M, Nc] activation, BN+ReLU apply
+// ------------------------------------------------------------------------------------------------
+constexpr int CS_ROWSPLIT_MAX = 64;
+__global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ Y, int M, int Nc, int rows_per_split,
+                                                       double* __restrict__ part /*[splits][Nc][2]*/) {
+  __shared__ double ssum[8][33], ssq[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(r0 + rows_per_split, M);
+  double s = 0.0, q = 0.0;
+  if (col < Nc)
+    for (int r = r0 + ry; r < r1; r += 8) {
+      const double v = Y[(size_t)r * Nc + col];
+      s += v;
+      q += v * v;
+    }
+  ssum[ry][cx] = s;
+  ssq[ry][cx] = q;
+  __syncthreads();
+  if (ry == 0 && col < Nc) {
+    for (int i = 1; i < 8; ++i) { s += ssum[i][cx]; q += ssq[i][cx]; }
+    part[((size_t)blockIdx.y * Nc + col) * 2 + 0] = s;
+    part[((size_t)blockIdx.y * Nc + col) * 2 + 1] = q;
+  }
+}
+
+__global__ void colstats_finalize_kernel(const double* __restrict__ part, int splits, int Nc, int M,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ scale, float* __restrict__ shift) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= Nc) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < splits; ++i) {
+    s += part[((size_t)i * Nc + col) * 2 + 0];
+    q += part[((size_t)i * Nc + col) * 2 + 1];
+  }
+  const double mean = s / M;
+  double var = q / M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double sc = (double)gamma[col] / sqrt(var + (double)BN_EPS);
+  scale[col] = (float)sc;
+  shift[col] = (float)((double)beta[col] - sc * mean);
+}
+
+__global__ void bn_relu_apply_kernel(const float* __restrict__ Y, long long total, int Nc, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % Nc);
+    out[i] = fmaxf(fmaf(Y[i], scale[c], shift[c]), 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-step node tables:  Ps = h·Ws^T + b_e, Pd = h·Wd^T, A = h·Wh^T + b_n
+// ------------------------------------------------------------------------------------------------
+constexpr int NT_NODES = 64, NT_THREADS = 256, NT_OUT = 40;
+__global__ void __launch_bounds__(NT_THREADS) node_tables_kernel(const float* __restrict__ h_full, int n_cols, int row_offset,
+                                                                 int n_rows, const float* __restrict__ small,
+                                                                 float* __restrict__ Ps, float* __restrict__ Pd,
+                                                                 float* __restrict__ A) {
+  __shared__ float hs[NT_NODES][33];
+  __shared__ float ws[NT_OUT][33];
+  __shared__ float bs[NT_OUT];
+  const int n0 = blockIdx.x * NT_NODES;
+  for (int i = threadIdx.x; i < NT_NODES * 32; i += NT_THREADS) {
+    const int n = n0 + (i >> 5);
+    hs[i >> 5][i & 31] = (n < n_cols) ? h_full[(size_t)n * 32 + (i & 31)] : 0.f;
+  }
+  for (int i = threadIdx.x; i < NT_OUT * 32; i += NT_THREADS) {
+    const int o = i >> 5, c = i & 31;
+    float v;
+    if (o < 4) v = small[MPN_W_EDGE_W + o * 68 + c];                 // Ws: columns 0..31 of the 68-wide weight
+    else if (o < 8) v = small[MPN_W_EDGE_W + (o - 4) * 68 + 32 + c]; // Wd: columns 32..63
+    else v = small[MPN_W_NODE_W + (o - 8) * 36 + c];                 // Wh: columns 0..31 of the 36-wide weight
+    ws[o][c] = v;
+  }
+  if (threadIdx.x < NT_OUT) {
+    const int o = threadIdx.x;
+    bs[o] = (o < 4) ? small[MPN_W_EDGE_B + o] : (o < 8 ? 0.f : small[MPN_W_NODE_B + o - 8]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NT_NODES * NT_OUT; i += NT_THREADS) {
+    const int ln = i / NT_OUT, o = i % NT_OUT;
+    const int n = n0 + ln;
+    if (n >= n_cols) continue;
+    float s = bs[o];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) s = fmaf(ws[o][c], hs[ln][c], s);
+    const int lr = n - row_offset;
+    if (o >= 4 && o < 8) Pd[(size_t)n * 4 + (o - 4)] = s;
+    else if (lr >= 0 && lr < n_rows) {
+      if (o < 4) Ps[(size_t)lr * 4 + o] = s;
+      else A[(size_t)lr * 32 + (o - 8)] = s;
+    }
+  }
+}
+
+// h'[row] = sum over the row's tasks of msg_task (fixed order)  — the deterministic segment sum of models/mpn.py:202
+__global__ void __launch_bounds__(256) node_finalize_kernel(const mpn_graph g, const float* __restrict__ msg_task,
+                                                            float* __restrict__ h_full) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = gwarp; n < g.n_nodes; n += nwarps) {
+    float s = 0.f;
+    for (int t = g.taskptr[n]; t < g.taskptr[n + 1]; ++t) s += msg_task[(size_t)t * MPN_DH + lane];
+    h_full[(size_t)(g.row_offset + n) * MPN_DH + lane] = s;
+  }
+}
+
+}  // namespace mpn
+
+// ================================================================================================
+// plan + C ABI
+// ================================================================================================
+using namespace mpn;
+
+struct mpn_fwd_plan {
+  mpn_graph g;
+  mpn_weights w;
+  int L, n_cls, use_tc, max_dim;
+  long long total_edges;
+  float *act0, *act1, *colscale, *colshift;
+  double* colpart;
+  float *h_full, *Ps, *Pd, *A, *consts, *s1_task, *msg_task, *ybuf;
+  double *partials, *partials2, *sums;
+  void* gemm_ws;
+  size_t gemm_ws_bytes;
+};
+
+static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need) {
+  Arena a(ws, ws_bytes);
+  const mpn_graph& g = p.g;
+  int max_dim = 0;
+  for (int i = 1; i <= p.w.n_node_layers; ++i) max_dim = p.w.node_dims[i] > max_dim ? p.w.node_dims[i] : max_dim;
+  p.max_dim = max_dim;
+  p.act0 = a.take<float>((size_t)g.n_cols * max_dim);
+  p.act1 = a.take<float>((size_t)g.n_cols * max_dim);
+  p.colscale = a.take<float>(max_dim > 0 ? max_dim : 1);
+  p.colshift = a.take<float>(max_dim > 0 ? max_dim : 1);
+  p.colpart = a.take<double>((size_t)CS_ROWSPLIT_MAX * (max_dim > 0 ? max_dim : 1) * 2);
+  p.h_full = a.take<float>((size_t)g.n_cols * MPN_DH);
+  p.Ps = a.take<float>((size_t)g.n_nodes * 4);
+  p.Pd = a.take<float>((size_t)g.n_cols * 4);
+  p.A = a.take<float>((size_t)g.n_nodes * MPN_DH);
+  p.consts = a.take<float>(FC_TOTAL);
+  p.s1_task = a.take<float>((size_t)g.max_tasks * 4);
+  p.msg_task = a.take<float>((size_t)g.max_tasks * MPN_DH);
+  p.partials = a.take<double>((size_t)SWEEP_GRID * SUMS);
+  p.partials2 = a.take<double>((size_t)NM_GRID * SUMS);
+  p.sums = a.take<double>(SUMS);
+  p.ybuf = (p.L > 1) ? a.take<float>((size_t)g.n_edges * 4) : nullptr;
+  size_t gw = 0;
+  if (p.use_tc) {
+    int prev = p.w.node_dims[0];
+    for (int i = 0; i < p.w.n_node_layers; ++i) {
+      size_t b = gemm_tc_workspace_bytes(g.n_cols, p.w.node_dims[i + 1], prev);
+      gw = b > gw ? b : gw;
+      prev = p.w.node_dims[i + 1];
+    }
+  }
+  p.gemm_ws_bytes = gw;
+  p.gemm_ws = gw ? (void*)a.take<char>(gw) : nullptr;
+  if (need) *need = a.off;
+  if (!a.ok()) {
+    set_error("forward workspace too small: need %zu bytes, have %zu", a.off, ws_bytes);
+    return MPN_ERR_WORKSPACE;
+  }
+  return MPN_OK;
+}
+
+static int check_weights(const mpn_weights* w) {
+  MPN_REQUIRE(w != nullptr, "weights is NULL");
+  MPN_REQUIRE(w->n_node_layers >= 1 && w->n_node_layers <= MPN_MAX_NODE_LAYERS, "n_node_layers must be in [1,%d]", MPN_MAX_NODE_LAYERS);
+  MPN_REQUIRE(w->node_dims[w->n_node_layers] == MPN_DH, "node_out_dim must be %d (got %d)", MPN_DH, w->node_dims[w->n_node_layers]);
+  for (int i = 0; i < w->n_node_layers; ++i)
+    MPN_REQUIRE(w->node_w[i] && w->node_b[i] && w->node_gamma[i] && w->node_beta[i] && w->node_dims[i] > 0, "node layer %d has NULL tensors", i);
+  MPN_REQUIRE(w->small != nullptr, "small weight block is NULL");
+  return MPN_OK;
+}
+
+extern "C" {
+
+size_t mpn_forward_workspace_bytes(const mpn_graph* g, const mpn_weights* w, int32_t num_enc_steps) {
+  if (!g || !w) return 0;
+  mpn_fwd_plan p;
+  memset(&p, 0, sizeof(p));
+  p.g = *g; p.w = *w; p.L = num_enc_steps; p.use_tc = 1;
+  size_t need = 0;
+  plan_layout(p, nullptr, 0, &need);
+  return need + 256;
+}
+
+int mpn_plan_create(mpn_fwd_plan** plan_out, const mpn_graph* g, const mpn_weights* w, int32_t L, int32_t n_cls,
+                    int64_t total_edges, int use_tc, void* ws, size_t ws_bytes) {
+  MPN_REQUIRE(plan_out && g && ws, "plan_create: NULL argument");
+  MPN_TRY(check_weights(w));
+  MPN_REQUIRE(L >= 0 && n_cls >= 0 && n_cls <= (L > 0 ? L : 1), "need 0 <= num_class_steps <= max(num_enc_steps,1)");
+  MPN_REQUIRE(total_edges >= g->n_edges, "total_edges smaller than this shard's edges");
+  MPN_REQUIRE(total_edges > 1, "BatchNorm over edges needs more than 1 edge (reference raises ValueError)");
+  MPN_REQUIRE(g->n_cols > 1, "BatchNorm over nodes needs more than 1 node (reference raises ValueError)");
+  MPN_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  mpn_fwd_plan* p = new (std::nothrow) mpn_fwd_plan;
+  MPN_REQUIRE(p != nullptr, "out of host memory");
+  memset(p, 0, sizeof(*p));
+  p->g = *g; p->w = *w; p->L = L; p->n_cls = n_cls; p->use_tc = use_tc; p->total_edges = total_edges;
+  int rc = plan_layout(*p, ws, ws_bytes, nullptr);
+  if (rc != MPN_OK) { delete p; return rc; }
+  *plan_out = p;
+  return MPN_OK;
+}
+
+void mpn_plan_destroy(mpn_fwd_plan* plan) { delete plan; }
+double* mpn_plan_sums(mpn_fwd_plan* plan) { return plan ? plan->sums : nullptr; }
+float* mpn_plan_h_full(mpn_fwd_plan* plan) { return plan ? plan->h_full : nullptr; }
+
+int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
+  MPN_REQUIRE(p && x, "node_encoder: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = p->g.n_cols;
+  const float* in = x;
+  float* bufs[2] = {p->act0, p->act1};
+  const float *sc = nullptr, *sh = nullptr;
+  for (int l = 0; l < p->w.n_node_layers; ++l) {
+    const int K = p->w.node_dims[l], Nc = p->w.node_dims[l + 1];
+    float* out = bufs[l & 1];
+    bool done = false;
+    if (p->use_tc && gemm_tc_supported(M, Nc, K)) {
+      // the TMA-fed tensor-core path needs materialised (BN+ReLU applied) inputs: apply in place
+      if (sc) {
+        bn_relu_apply_kernel<<<kNumSMs * 4, 256, 0, st>>>(in, (long long)M * K, K, sc, sh, (float*)in);
+        MPN_LAUNCH_OK();
+      }
+      MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st));
+      done = true;
+    }
+    if (!done) MPN_TRY(gemm_nt_simt(in, p->w.node_w[l], p->w.node_b[l], sc, sh, out, M, Nc, K, st));
+    int splits = div_up(M, 256);
+    splits = splits > CS_ROWSPLIT_MAX ? CS_ROWSPLIT_MAX : splits;
+    const int rps = div_up(M, splits);
+    colstats_kernel<<<dim3(div_up(Nc, 32), splits), 256, 0, st>>>(out, M, Nc, rps, p->colpart);
+    MPN_LAUNCH_OK();
+    colstats_finalize_kernel<<<div_up(Nc, 128), 128, 0, st>>>(p->colpart, splits, Nc, M, p->w.node_gamma[l], p->w.node_beta[l],
+                                                              p->colscale, p->colshift);
+    MPN_LAUNCH_OK();
+    in = out;
+    sc = p->colscale;
+    sh = p->colshift;
+  }
+  bn_relu_apply_kernel<<<min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st>>>(in, (long long)M * MPN_DH, MPN_DH, sc, sh, p->h_full);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+int mpn_plan_node_tables(mpn_fwd_plan* p, int32_t step, void* stream) {
+  MPN_REQUIRE(p, "node_tables: NULL plan");
+  (void)step;
+  node_tables_kernel<<<div_up(p->g.n_cols, NT_NODES), NT_THREADS, 0, (cudaStream_t)stream>>>(
+      p->h_full, p->g.n_cols, p->g.row_offset, p->g.n_nodes, p->w.small, p->Ps, p->Pd, p->A);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* edge_attr, float* logits_out,
+                   uint8_t* pred_out, float* prob1_out, void* stream) {
+  MPN_REQUIRE(p && edge_attr, "sweep: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mpn_graph& g = p->g;
+  const float2* ea = (const float2*)edge_attr;
+  const bool stored = p->L > 1;           // y materialised in ybuf for multi-step runs
+  const int flat_grid = (int)min((long long)SWEEP_GRID, (long long)div_up(g.n_edges > 0 ? g.n_edges : 1, SWEEP_THREADS));
+  switch (stage) {
+    case MPN_STAGE_ENC0:
+      MPN_CUDA_OK(cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st));
+      enc_moments_kernel<0><<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, p->w.small, p->partials);
+      break;
+    case MPN_STAGE_ENC1:
+      enc_moments_kernel<1><<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, p->w.small, p->partials);
+      break;
+    case MPN_STAGE_EDGE:
+      if (step == 1) {
+        if (stored) edge_moments_kernel<0, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (float4*)p->ybuf, p->consts, p->partials);
+        else edge_moments_kernel<0, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, nullptr, p->consts, p->partials);
+      } else {
+        edge_moments_kernel<1, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (float4*)p->ybuf, p->consts, p->partials);
+      }
+      break;
+    case MPN_STAGE_NODE:
+      if (stored) node_moments_sweep_kernel<1><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (const float4*)p->ybuf, p->consts, (float4*)p->s1_task, p->partials);
+      else node_moments_sweep_kernel<0><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, nullptr, p->consts, (float4*)p->s1_task, p->partials);
+      MPN_LAUNCH_OK();
+      node_moments_node_kernel<<<NM_GRID, NM_THREADS, 0, st>>>(g, p->A, (const float4*)p->s1_task, p->w.small, p->partials2);
+      break;
+    case MPN_STAGE_APPLY: {
+      const bool classify = logits_out != nullptr;
+      float2* lg = (float2*)logits_out;
+      if (p->L == 0) {
+        MPN_REQUIRE(classify, "L == 0 needs a logits buffer");
+        classify_encoded_kernel<<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, lg, pred_out, prob1_out);
+        break;
+      }
+#define MPN_APPLY(YS, CL) apply_kernel<YS, CL><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (const float4*)p->ybuf, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+      if (stored) { if (classify) MPN_APPLY(1, true); else MPN_APPLY(1, false); }
+      else        { if (classify) MPN_APPLY(0, true); else MPN_APPLY(0, false); }
+#undef MPN_APPLY
+      break;
+    }
+    default:
+      MPN_REQUIRE(false, "unknown stage %d", stage);
+  }
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+int mpn_plan_finalize(mpn_fwd_plan* p, int32_t step, int32_t stage, void* stream) {
+  MPN_REQUIRE(p, "finalize: NULL plan");
+  (void)step;
+  // sums already reduced (and possibly all-reduced by the host): constants only
+  finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(stage, nullptr, 0, nullptr, 0, p->sums, 0, 1, p->consts, p->w.small,
+                                                       (double)p->total_edges);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+// reduce this rank's block partials into the sums vector (phase API: host all-reduces it afterwards)
+int mpn_plan_reduce(mpn_fwd_plan* p, int32_t stage, int with_consts, void* stream) {
+  MPN_REQUIRE(p, "reduce: NULL plan");
+  finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(stage, p->partials, SWEEP_GRID, p->partials2, NM_GRID, p->sums, 1,
+                                                       with_consts, p->consts, p->w.small, (double)p->total_edges);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+int mpn_plan_node_finalize(mpn_fwd_plan* p, int32_t step, void* stream) {
+  MPN_REQUIRE(p, "node_finalize: NULL plan");
+  (void)step;
+  node_finalize_kernel<<<min(kNumSMs * 8, div_up((long long)p->g.n_nodes * 32, 256)), 256, 0, (cudaStream_t)stream>>>(p->g, p->msg_task, p->h_full);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const float* edge_attr, int32_t L, int32_t n_cls,
+                float* logits_out, float* h_out, uint8_t* pred_out, float* prob1_out, int use_tc, void* ws, size_t ws_bytes,
+                void* stream) {
+  MPN_REQUIRE(g && x && edge_attr && logits_out, "forward: NULL argument");
+  MPN_REQUIRE(g->row_offset == 0 && g->n_cols == g->n_nodes, "mpn_forward runs an unsharded graph; use the plan API for row blocks");
+  cudaStream_t st = (cudaStream_t)stream;
+  mpn_fwd_plan* p = nullptr;
+  MPN_TRY(mpn_plan_create(&p, g, w, L, n_cls, g->n_edges, use_tc, ws, ws_bytes));
+  int rc = MPN_OK;
+  const size_t lstride = (size_t)g->n_edges * 2;
+#define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
+  STEP_TRY(mpn_plan_node_encoder(p, x, st));
+  STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
+  STEP_TRY(mpn_plan_reduce(p, MPN_STAGE_ENC0, 1, st));
+  STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
+  STEP_TRY(mpn_plan_reduce(p, MPN_STAGE_ENC1, 1, st));
+  if (L == 0) {
+    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_APPLY, edge_attr, logits_out, pred_out, prob1_out, st));
+  }
+  {
+    const int first_class_step = L - n_cls + 1;
+    int k = 0;
+    for (int step = 1; step <= L; ++step) {
+      STEP_TRY(mpn_plan_node_tables(p, step, st));
+      STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_EDGE, edge_attr, nullptr, nullptr, nullptr, st));
+      STEP_TRY(mpn_plan_reduce(p, MPN_STAGE_EDGE, 1, st));
+      STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_NODE, edge_attr, nullptr, nullptr, nullptr, st));
+      STEP_TRY(mpn_plan_reduce(p, MPN_STAGE_NODE, 1, st));
+      const bool cls = step >= first_class_step;
+      const bool last = step == L;
+      STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_APPLY, edge_attr, cls ? logits_out + lstride * k : nullptr,
+                              (cls && last) ? pred_out : nullptr, (cls && last) ? prob1_out : nullptr, st));
+      if (cls) ++k;
+      STEP_TRY(mpn_plan_node_finalize(p, step, st));
+    }
+  }
+  if (h_out) {
+    cudaError_t e = cudaMemcpyAsync(h_out, p->h_full, sizeof(float) * (size_t)g->n_nodes * MPN_DH, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_error("h copy failed: %s", cudaGetErrorString(e)); rc = MPN_ERR_CUDA; }
+  }
+#undef STEP_TRY
+done:
+  mpn_plan_destroy(p);
+  return rc;
+}
+
+int mpn_decide(const float* logits, int64_t E, uint8_t* pred, float* prob1, void* stream) {
+  MPN_REQUIRE(logits || E == 0, "decide: NULL logits");
+  if (E == 0) return MPN_OK;
+  decide_kernel<<<(int)min((long long)kNumSMs * 8, (long long)div_up(E, 256)), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)logits, E, pred, prob1);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+}  // extern "C"

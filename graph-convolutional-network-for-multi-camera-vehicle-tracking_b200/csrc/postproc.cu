@@ -1,0 +1,707 @@
+// K5: CUTTING / PRUNING / SPLITTING and strongly-connected-component labelling on the GPU.
+// Reference: inference.post_processing (inference.py:70-169) and utils.py:30-52, 54-123, 125-142, 144-339.
+//
+// All stages work on an order-preserving compaction of the active edges (A << E): one pass over the
+// 1-byte activity flags, then every fixed-point round touches only A entries plus O(N) node arrays.
+// Integer / index results are bit-exact by construction: counts use integer atomics, arg-min uses a
+// packed (prob bits, edge id) 64-bit atomicMin (ties -> lowest edge id, as torch.argmin over ascending
+// candidates, utils.py:288-289), components use min-id union-find.
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mpn {
+
+constexpr int EPB = 4096;            // edges per compaction block (256 threads x 16 flags)
+constexpr unsigned int HASH_EMPTY = 0xFFFFFFFFu;
+
+struct PostCtx {
+  mpn_graph g;
+  cudaStream_t st;
+  int n_blocks;
+  // device
+  int *blockoff, *a_eid, *a_src, *a_dst, *a_rev;
+  int *fo, *fi, *label, *size, *od_src, *od_dst, *counters;      // counters[8]
+  unsigned long long *mo, *mi;
+  unsigned int *mbits, *hash;
+  int hash_cap;
+  size_t total;
+  // host
+  int n_active;
+};
+
+static void post_layout(PostCtx& c, void* ws, size_t ws_bytes) {
+  Arena a(ws, ws_bytes);
+  const size_t E = (size_t)(c.g.n_edges > 0 ? c.g.n_edges : 1), N = (size_t)c.g.n_nodes;
+  c.n_blocks = div_up((long long)E, EPB);
+  c.blockoff = a.take<int>(c.n_blocks + 1);
+  c.a_eid = a.take<int>(E);
+  c.a_src = a.take<int>(E);
+  c.a_dst = a.take<int>(E);
+  c.a_rev = a.take<int>(E);
+  c.od_src = a.take<int>(E);
+  c.od_dst = a.take<int>(E);
+  c.fo = a.take<int>(N);
+  c.fi = a.take<int>(N);
+  c.label = a.take<int>(N);
+  c.size = a.take<int>(N);
+  c.mo = a.take<unsigned long long>(N);
+  c.mi = a.take<unsigned long long>(N);
+  c.mbits = a.take<unsigned int>(N);
+  int cap = 1024;
+  while ((size_t)cap < N) cap <<= 1;
+  c.hash_cap = cap;
+  c.hash = a.take<unsigned int>(cap);
+  c.counters = a.take<int>(8);
+  c.total = a.off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// order-preserving compaction of active edges
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) count_active_kernel(const uint8_t* __restrict__ act, long long E, int* __restrict__ blockcnt) {
+  __shared__ int wsum[8];
+  const long long base = (long long)blockIdx.x * EPB + (long long)threadIdx.x * 16;
+  int cnt = 0;
+  if (base + 16 <= E && (((uintptr_t)act) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(act + base);
+    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) cnt += ((w[i] >> (8 * b)) & 0xFFu) != 0;
+  } else {
+    for (int i = 0; i < 16; ++i)
+      if (base + i < E) cnt += act[base + i] != 0;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int i = 0; i < 8; ++i) s += wsum[i];
+    blockcnt[blockIdx.x] = s;
+  }
+}
+
+// single-block exclusive scan (in place) + total
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(int* __restrict__ v, int n, int* __restrict__ total) {
+  __shared__ int strip[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(t * per, n), hi = min(lo + per, n);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += v[i];
+  strip[t] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    int x = (t >= off) ? strip[t - off] : 0;
+    __syncthreads();
+    strip[t] += x;
+    __syncthreads();
+  }
+  int run = (t == 0) ? 0 : strip[t - 1];
+  for (int i = lo; i < hi; ++i) { const int x = v[i]; v[i] = run; run += x; }
+  if (t == 1023) { v[n] = strip[1023]; *total = strip[1023]; }
+}
+
+__device__ __forceinline__ int find_row(const int* __restrict__ rowptr, int n_rows, int e) {
+  int lo = 0, hi = n_rows;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (rowptr[mid] <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// index of edge (u -> v) or -1; columns are sorted within a row
+__device__ __forceinline__ int find_edge(const mpn_graph& g, int u, int v) {
+  int lo = g.rowptr[u], hi = g.rowptr[u + 1];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int c = g.col[mid];
+    if (c == v) return mid;
+    if (c < v) lo = mid + 1; else hi = mid;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(256) write_active_kernel(const mpn_graph g, const uint8_t* __restrict__ act,
+                                                           const int* __restrict__ blockoff, int* __restrict__ a_eid,
+                                                           int* __restrict__ a_src, int* __restrict__ a_dst, int* __restrict__ a_rev) {
+  __shared__ int tsum[256];
+  const long long E = g.n_edges;
+  const long long base = (long long)blockIdx.x * EPB + (long long)threadIdx.x * 16;
+  unsigned int mask = 0;
+  for (int i = 0; i < 16; ++i)
+    if (base + i < E && act[base + i] != 0) mask |= 1u << i;
+  const int cnt = __popc(mask);
+  tsum[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    int x = (threadIdx.x >= off) ? tsum[threadIdx.x - off] : 0;
+    __syncthreads();
+    tsum[threadIdx.x] += x;
+    __syncthreads();
+  }
+  int pos = blockoff[blockIdx.x] + tsum[threadIdx.x] - cnt;
+  while (mask) {
+    const int i = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int e = (int)(base + i);
+    const int u = find_row(g.rowptr, g.n_nodes, e);
+    const int v = g.col[e];
+    a_eid[pos] = e;
+    a_src[pos] = u;
+    a_dst[pos] = v;
+    a_rev[pos] = find_edge(g, v, u);
+    ++pos;
+  }
+}
+
+static int build_active_list(PostCtx& c, const uint8_t* act) {
+  if (c.g.n_edges == 0) { c.n_active = 0; return MPN_OK; }
+  count_active_kernel<<<c.n_blocks, 256, 0, c.st>>>(act, c.g.n_edges, c.blockoff);
+  MPN_LAUNCH_OK();
+  scan_blocks_kernel<<<1, 1024, 0, c.st>>>(c.blockoff, c.n_blocks, c.counters);
+  MPN_LAUNCH_OK();
+  write_active_kernel<<<c.n_blocks, 256, 0, c.st>>>(c.g, act, c.blockoff, c.a_eid, c.a_src, c.a_dst, c.a_rev);
+  MPN_LAUNCH_OK();
+  MPN_CUDA_OK(cudaMemcpyAsync(&c.n_active, c.counters, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  return MPN_OK;
+}
+
+static inline int list_grid(int n) { return std::max(1, std::min(kNumSMs * 8, div_up(n, 256))); }
+
+// ------------------------------------------------------------------------------------------------
+// CUT (utils.py:125-142): an active edge survives only if its reverse is active
+// ------------------------------------------------------------------------------------------------
+__global__ void cut_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_rev, uint8_t* __restrict__ act) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    const int e = a_eid[i];
+    if (!act[e]) continue;
+    const int r = a_rev[i];
+    // race-free in place: act[e] is only read by the thread owning rev(e), which exists only while act[rev(e)] == 1,
+    // and in that case act[e] is not cleared here
+    if (r < 0 || !act[r]) act[e] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PRUNE (utils.py:161-188, 277-317)
+// ------------------------------------------------------------------------------------------------
+__global__ void flow_count_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const int* __restrict__ a_dst,
+                                  const uint8_t* __restrict__ act, int* __restrict__ fo, int* __restrict__ fi) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    if (!act[a_eid[i]]) continue;
+    atomicAdd(&fo[a_src[i]], 1);
+    atomicAdd(&fi[a_dst[i]], 1);
+  }
+}
+__global__ void prune_pick_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const int* __restrict__ a_dst,
+                                  const uint8_t* __restrict__ act, const float* __restrict__ prob, int pstride, int limit,
+                                  const int* __restrict__ fo, const int* __restrict__ fi, unsigned long long* __restrict__ mo,
+                                  unsigned long long* __restrict__ mi, int* __restrict__ any_violation) {
+  bool viol = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    const int e = a_eid[i];
+    if (!act[e]) continue;
+    const int u = a_src[i], v = a_dst[i];
+    const bool bo = fo[u] > limit, bi = fi[v] > limit;
+    if (!(bo || bi)) continue;
+    viol = true;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(prob[(size_t)e * pstride]) << 32) | (unsigned int)e;
+    if (bo) atomicMin(&mo[u], key);
+    if (bi) atomicMin(&mi[v], key);
+  }
+  if (viol) *any_violation = 1;
+}
+__global__ void prune_remove_kernel(int N, const unsigned long long* __restrict__ mo, const unsigned long long* __restrict__ mi,
+                                    uint8_t* __restrict__ act) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    const unsigned long long a = mo[n], b = mi[n];
+    if (a != ~0ull) act[(unsigned int)(a & 0xFFFFFFFFull)] = 0;
+    if (b != ~0ull) act[(unsigned int)(b & 0xFFFFFFFFull)] = 0;
+  }
+}
+
+static int prune_stage(PostCtx& c, uint8_t* act, const float* prob, int pstride, int num_cameras, int* changed, int* rounds) {
+  const int A = c.n_active, N = c.g.n_nodes;
+  *changed = 0;
+  *rounds = 0;
+  if (A == 0) return MPN_OK;
+  for (;;) {
+    MPN_CUDA_OK(cudaMemsetAsync(c.fo, 0, sizeof(int) * N, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(c.fi, 0, sizeof(int) * N, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(c.mo, 0xFF, sizeof(unsigned long long) * N, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(c.mi, 0xFF, sizeof(unsigned long long) * N, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(c.counters + 1, 0, sizeof(int), c.st));
+    flow_count_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, c.fo, c.fi);
+    MPN_LAUNCH_OK();
+    prune_pick_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, prob, pstride, num_cameras - 1, c.fo,
+                                                      c.fi, c.mo, c.mi, c.counters + 1);
+    MPN_LAUNCH_OK();
+    int viol = 0;
+    MPN_CUDA_OK(cudaMemcpyAsync(&viol, c.counters + 1, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+    if (!viol) break;
+    *changed = 1;
+    ++*rounds;
+    prune_remove_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.mo, c.mi, act);
+    MPN_LAUNCH_OK();
+  }
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SCC: min-id union-find over mutual edges, then (rarely) a host Tarjan on the condensed digraph of the
+// remaining one-directional edges.  Every mutual-edge component lies inside one SCC, so the condensation
+// is exact.  label[n] = smallest node id of n's SCC.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int* __restrict__ parent, int x) {
+  int p = parent[x];
+  while (p != x) {
+    const int gp = parent[p];
+    if (gp != p) parent[x] = gp;          // path halving (benign race: only ever points closer to the root)
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+__device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }      // hook the larger root under the smaller one
+    if (atomicCAS(&parent[a], a, b) == a) return;
+  }
+}
+__global__ void iota_kernel(int N, int* __restrict__ v) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) v[n] = n;
+}
+__global__ void union_mutual_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const int* __restrict__ a_dst,
+                                    const int* __restrict__ a_rev, const uint8_t* __restrict__ act, int* __restrict__ parent) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    if (!act[a_eid[i]]) continue;
+    const int u = a_src[i], v = a_dst[i];
+    if (u >= v) continue;                               // the (v,u) twin handles u > v
+    const int r = a_rev[i];
+    if (r >= 0 && act[r]) uf_union(parent, u, v);
+  }
+}
+__global__ void flatten_kernel(int N, int* __restrict__ parent, int* __restrict__ n_roots) {
+  int roots = 0;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    int x = n;
+    while (parent[x] != x) x = parent[x];
+    roots += (x == n);
+    // safe without a second buffer: roots never change in this kernel and only non-root entries are rewritten to roots
+    if (x != n) parent[n] = x;
+  }
+  if (n_roots) {
+    roots = __reduce_add_sync(0xffffffffu, roots);
+    if ((threadIdx.x & 31) == 0 && roots) atomicAdd(n_roots, roots);
+  }
+}
+__global__ void one_dir_edges_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const int* __restrict__ a_dst,
+                                     const int* __restrict__ a_rev, const uint8_t* __restrict__ act, const int* __restrict__ label,
+                                     int* __restrict__ od_src, int* __restrict__ od_dst, int* __restrict__ od_count) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    if (!act[a_eid[i]]) continue;
+    const int r = a_rev[i];
+    if (r >= 0 && act[r]) continue;
+    const int lu = label[a_src[i]], lv = label[a_dst[i]];
+    if (lu == lv) continue;
+    const int slot = atomicAdd(od_count, 1);
+    od_src[slot] = lu;
+    od_dst[slot] = lv;
+  }
+}
+__global__ void hook_pairs_kernel(int n, const int* __restrict__ from, const int* __restrict__ to, int* __restrict__ parent) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) parent[from[i]] = to[i];
+}
+
+// iterative Tarjan on a small digraph given as edge arrays over arbitrary ids; returns (id -> min id of its SCC) for
+// every id that belongs to an SCC with more than one member
+static void host_condensed_scc(const std::vector<int>& s, const std::vector<int>& d, std::vector<int>& from, std::vector<int>& to) {
+  std::unordered_map<int, int> idx;
+  std::vector<int> ids;
+  auto get = [&](int v) {
+    auto it = idx.find(v);
+    if (it != idx.end()) return it->second;
+    const int k = (int)ids.size();
+    idx.emplace(v, k);
+    ids.push_back(v);
+    return k;
+  };
+  const size_t m = s.size();
+  std::vector<int> us(m), vs(m);
+  for (size_t i = 0; i < m; ++i) { us[i] = get(s[i]); vs[i] = get(d[i]); }
+  const int n = (int)ids.size();
+  std::vector<int> ptr(n + 1, 0), adj(m);
+  for (size_t i = 0; i < m; ++i) ptr[us[i] + 1]++;
+  for (int i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
+  {
+    std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+    for (size_t i = 0; i < m; ++i) adj[cur[us[i]]++] = vs[i];
+  }
+  std::vector<int> index(n, -1), low(n, 0), cursor(n, 0), stack, call;
+  std::vector<char> on(n, 0);
+  int counter = 0;
+  for (int root = 0; root < n; ++root) {
+    if (index[root] >= 0) continue;
+    call.push_back(root);
+    while (!call.empty()) {
+      const int v = call.back();
+      if (index[v] < 0) { index[v] = low[v] = counter++; stack.push_back(v); on[v] = 1; cursor[v] = ptr[v]; }
+      bool descended = false;
+      while (cursor[v] < ptr[v + 1]) {
+        const int w = adj[cursor[v]++];
+        if (index[w] < 0) { call.push_back(w); descended = true; break; }
+        if (on[w]) low[v] = std::min(low[v], index[w]);
+      }
+      if (descended) continue;
+      call.pop_back();
+      if (!call.empty()) low[call.back()] = std::min(low[call.back()], low[v]);
+      if (low[v] == index[v]) {
+        std::vector<int> comp;
+        for (;;) {
+          const int w = stack.back();
+          stack.pop_back();
+          on[w] = 0;
+          comp.push_back(w);
+          if (w == v) break;
+        }
+        if (comp.size() > 1) {
+          int mn = ids[comp[0]];
+          for (int w : comp) mn = std::min(mn, ids[w]);
+          for (int w : comp)
+            if (ids[w] != mn) { from.push_back(ids[w]); to.push_back(mn); }
+        }
+      }
+    }
+  }
+}
+
+// labels into c.label; n_components optional
+static int scc_stage(PostCtx& c, const uint8_t* act, int* n_components) {
+  const int A = c.n_active, N = c.g.n_nodes;
+  iota_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label);
+  MPN_LAUNCH_OK();
+  if (A > 0) {
+    union_mutual_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, c.a_rev, act, c.label);
+    MPN_LAUNCH_OK();
+  }
+  MPN_CUDA_OK(cudaMemsetAsync(c.counters + 2, 0, 2 * sizeof(int), c.st));
+  flatten_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, c.counters + 2);
+  MPN_LAUNCH_OK();
+  if (A > 0) {
+    one_dir_edges_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, c.a_rev, act, c.label, c.od_src, c.od_dst,
+                                                         c.counters + 3);
+    MPN_LAUNCH_OK();
+  }
+  int h[2] = {0, 0};
+  MPN_CUDA_OK(cudaMemcpyAsync(h, c.counters + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  int n_comp = h[0];
+  const int n_od = h[1];
+  if (n_od > 0) {
+    std::vector<int> s(n_od), d(n_od), from, to;
+    MPN_CUDA_OK(cudaMemcpyAsync(s.data(), c.od_src, sizeof(int) * n_od, cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaMemcpyAsync(d.data(), c.od_dst, sizeof(int) * n_od, cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+    host_condensed_scc(s, d, from, to);
+    if (!from.empty()) {
+      const int k = (int)from.size();
+      // reuse od buffers for the (root -> new root) pairs
+      MPN_CUDA_OK(cudaMemcpyAsync(c.od_src, from.data(), sizeof(int) * k, cudaMemcpyHostToDevice, c.st));
+      MPN_CUDA_OK(cudaMemcpyAsync(c.od_dst, to.data(), sizeof(int) * k, cudaMemcpyHostToDevice, c.st));
+      hook_pairs_kernel<<<list_grid(k), 256, 0, c.st>>>(k, c.od_src, c.od_dst, c.label);
+      MPN_LAUNCH_OK();
+      flatten_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, nullptr);
+      MPN_LAUNCH_OK();
+      MPN_CUDA_OK(cudaStreamSynchronize(c.st));      // host vectors must outlive the copies
+      n_comp -= k;
+    }
+  }
+  if (n_components) *n_components = n_comp;
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SPLIT (utils.py:54-123) as parallel rounds: every oversized SCC contributes the minimum probability among the
+// active edges touching it (either endpoint, utils.py:71); every edge whose probability equals one of those
+// values is deactivated (global float equality, utils.py:96-98); repeat until no SCC has more than C nodes.
+// ------------------------------------------------------------------------------------------------
+__global__ void comp_size_kernel(int N, const int* __restrict__ label, int* __restrict__ size) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) atomicAdd(&size[label[n]], 1);
+}
+__global__ void split_min_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const int* __restrict__ a_dst,
+                                 const uint8_t* __restrict__ act, const float* __restrict__ prob, int pstride,
+                                 const int* __restrict__ label, const int* __restrict__ size, int limit,
+                                 unsigned int* __restrict__ mbits) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    const int e = a_eid[i];
+    if (!act[e]) continue;
+    const int lu = label[a_src[i]], lv = label[a_dst[i]];
+    const unsigned int pb = __float_as_uint(prob[(size_t)e * pstride]);
+    if (size[lu] > limit) atomicMin(&mbits[lu], pb);
+    if (lv != lu && size[lv] > limit) atomicMin(&mbits[lv], pb);
+  }
+}
+__device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__global__ void split_collect_kernel(int N, const int* __restrict__ label, const int* __restrict__ size, int limit,
+                                     const unsigned int* __restrict__ mbits, unsigned int* __restrict__ hash, int cap,
+                                     int* __restrict__ n_big) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    if (label[n] != n || size[n] <= limit) continue;
+    atomicAdd(n_big, 1);
+    const unsigned int key = mbits[n];
+    if (key == HASH_EMPTY) continue;
+    unsigned int slot = hash_u32(key) & (cap - 1);
+    for (;;) {
+      const unsigned int old = atomicCAS(&hash[slot], HASH_EMPTY, key);
+      if (old == HASH_EMPTY || old == key) break;
+      slot = (slot + 1) & (cap - 1);
+    }
+  }
+}
+__global__ void split_remove_kernel(int A, const int* __restrict__ a_eid, uint8_t* __restrict__ act, const float* __restrict__ prob,
+                                    int pstride, const unsigned int* __restrict__ hash, int cap) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    const int e = a_eid[i];
+    if (!act[e]) continue;
+    const unsigned int key = __float_as_uint(prob[(size_t)e * pstride]);
+    unsigned int slot = hash_u32(key) & (cap - 1);
+    for (;;) {
+      const unsigned int v = hash[slot];
+      if (v == key) { act[e] = 0; break; }
+      if (v == HASH_EMPTY) break;
+      slot = (slot + 1) & (cap - 1);
+    }
+  }
+}
+
+static int split_stage(PostCtx& c, uint8_t* act, const float* prob, int pstride, int num_cameras, int* rounds) {
+  const int A = c.n_active, N = c.g.n_nodes;
+  *rounds = 0;
+  if (A == 0) return MPN_OK;
+  for (;;) {
+    MPN_TRY(scc_stage(c, act, nullptr));
+    MPN_CUDA_OK(cudaMemsetAsync(c.size, 0, sizeof(int) * N, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(c.mbits, 0xFF, sizeof(unsigned int) * N, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(c.hash, 0xFF, sizeof(unsigned int) * c.hash_cap, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(c.counters + 4, 0, sizeof(int), c.st));
+    comp_size_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, c.size);
+    MPN_LAUNCH_OK();
+    split_min_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, prob, pstride, c.label, c.size, num_cameras, c.mbits);
+    MPN_LAUNCH_OK();
+    split_collect_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, c.size, num_cameras, c.mbits, c.hash, c.hash_cap, c.counters + 4);
+    MPN_LAUNCH_OK();
+    int n_big = 0;
+    MPN_CUDA_OK(cudaMemcpyAsync(&n_big, c.counters + 4, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+    if (n_big == 0) break;
+    ++*rounds;
+    split_remove_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, act, prob, pstride, c.hash, c.hash_cap);
+    MPN_LAUNCH_OK();
+    if (*rounds > A + 1) { set_error("split did not converge"); return MPN_ERR_INVALID; }
+  }
+  return MPN_OK;
+}
+
+static int post_begin(PostCtx& c, const mpn_graph* g, const uint8_t* act, void* ws, size_t ws_bytes, void* stream) {
+  MPN_REQUIRE(g && ws, "post: NULL argument");
+  MPN_REQUIRE(act || g->n_edges == 0, "post: NULL activity flags");
+  MPN_REQUIRE(g->row_offset == 0 && g->n_cols == g->n_nodes, "post-processing runs on an unsharded graph (replicas only)");
+  MPN_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  c.g = *g;
+  c.st = (cudaStream_t)stream;
+  post_layout(c, ws, ws_bytes);
+  if (c.total > ws_bytes) {
+    set_error("post workspace too small: need %zu bytes, have %zu", c.total, ws_bytes);
+    return MPN_ERR_WORKSPACE;
+  }
+  return build_active_list(c, act);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reference label numbering on the host (utils.py:30-52 + networkx SCC emission order)
+// ------------------------------------------------------------------------------------------------
+static void labels_reference(const int* src, const int* dst, long long m, int n_nodes, long long* labels, int* n_comp) {
+  std::vector<int> order;                 // nodes in first-appearance order (u then v per edge): DiGraph insertion order
+  std::vector<int> pos(n_nodes, -1);
+  for (long long i = 0; i < m; ++i) {
+    if (pos[src[i]] < 0) { pos[src[i]] = (int)order.size(); order.push_back(src[i]); }
+    if (pos[dst[i]] < 0) { pos[dst[i]] = (int)order.size(); order.push_back(dst[i]); }
+  }
+  std::vector<long long> ptr(n_nodes + 1, 0);
+  for (long long i = 0; i < m; ++i) ptr[src[i] + 1]++;
+  for (int i = 0; i < n_nodes; ++i) ptr[i + 1] += ptr[i];
+  std::vector<int> adj(m);
+  {
+    std::vector<long long> cur(ptr.begin(), ptr.end() - 1);
+    for (long long i = 0; i < m; ++i) adj[cur[src[i]]++] = dst[i];       // successor order = edge insertion order
+  }
+  std::vector<int> preorder(n_nodes, 0), lowlink(n_nodes, 0);
+  std::vector<char> found(n_nodes, 0);
+  std::vector<long long> cursor(ptr.begin(), ptr.end() - 1);
+  std::vector<int> queue, scc_queue;
+  std::vector<std::vector<int>> sccs;
+  int counter = 0;
+  for (int source : order) {
+    if (found[source]) continue;
+    queue.assign(1, source);
+    while (!queue.empty()) {
+      const int v = queue.back();
+      if (preorder[v] == 0) preorder[v] = ++counter;
+      bool done = true;
+      while (cursor[v] < ptr[v + 1]) {
+        const int w = adj[cursor[v]++];
+        if (preorder[w] == 0) { queue.push_back(w); done = false; break; }
+      }
+      if (!done) continue;
+      lowlink[v] = preorder[v];
+      for (long long k = ptr[v]; k < ptr[v + 1]; ++k) {
+        const int w = adj[k];
+        if (!found[w]) lowlink[v] = std::min(lowlink[v], preorder[w] > preorder[v] ? lowlink[w] : preorder[w]);
+      }
+      queue.pop_back();
+      if (lowlink[v] == preorder[v]) {
+        std::vector<int> scc(1, v);
+        while (!scc_queue.empty() && preorder[scc_queue.back()] > preorder[v]) { scc.push_back(scc_queue.back()); scc_queue.pop_back(); }
+        for (int w : scc) found[w] = 1;
+        sccs.push_back(std::move(scc));
+      } else {
+        scc_queue.push_back(v);
+      }
+    }
+  }
+  std::stable_sort(sccs.begin(), sccs.end(), [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() < b.size(); });
+  for (int i = 0; i < n_nodes; ++i) labels[i] = -1;
+  long long k = 0;
+  for (const auto& s : sccs) { for (int v : s) labels[v] = k; ++k; }
+  for (int i = 0; i < n_nodes; ++i) if (labels[i] < 0) labels[i] = k++;
+  *n_comp = (int)k;
+}
+
+}  // namespace mpn
+
+using namespace mpn;
+
+extern "C" {
+
+size_t mpn_post_workspace_bytes(const mpn_graph* g) {
+  if (!g) return 0;
+  PostCtx c;
+  c.g = *g;
+  post_layout(c, nullptr, 0);
+  return c.total + 256;
+}
+
+int mpn_cut(const mpn_graph* g, uint8_t* act, void* ws, size_t ws_bytes, void* stream) {
+  PostCtx c;
+  MPN_TRY(post_begin(c, g, act, ws, ws_bytes, stream));
+  if (c.n_active == 0) return MPN_OK;
+  cut_kernel<<<list_grid(c.n_active), 256, 0, c.st>>>(c.n_active, c.a_eid, c.a_rev, act);
+  MPN_LAUNCH_OK();
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  return MPN_OK;
+}
+
+int mpn_prune(const mpn_graph* g, uint8_t* act, const float* prob1, int32_t pstride, int32_t num_cameras, int32_t* changed,
+              int32_t* rounds, void* ws, size_t ws_bytes, void* stream) {
+  PostCtx c;
+  MPN_REQUIRE(prob1 && pstride >= 1 && num_cameras >= 1, "prune: bad arguments");
+  MPN_TRY(post_begin(c, g, act, ws, ws_bytes, stream));
+  int ch = 0, r = 0;
+  MPN_TRY(prune_stage(c, act, prob1, pstride, num_cameras, &ch, &r));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  if (changed) *changed = ch;
+  if (rounds) *rounds = r;
+  return MPN_OK;
+}
+
+int mpn_split(const mpn_graph* g, uint8_t* act, const float* prob1, int32_t pstride, int32_t num_cameras, int32_t* rounds,
+              void* ws, size_t ws_bytes, void* stream) {
+  PostCtx c;
+  MPN_REQUIRE(prob1 && pstride >= 1 && num_cameras >= 1, "split: bad arguments");
+  MPN_TRY(post_begin(c, g, act, ws, ws_bytes, stream));
+  int r = 0;
+  MPN_TRY(split_stage(c, act, prob1, pstride, num_cameras, &r));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  if (rounds) *rounds = r;
+  return MPN_OK;
+}
+
+int mpn_scc_labels(const mpn_graph* g, const uint8_t* act, int32_t* labels, int32_t* n_components, void* ws, size_t ws_bytes,
+                   void* stream) {
+  PostCtx c;
+  MPN_REQUIRE(labels, "scc_labels: NULL output");
+  MPN_TRY(post_begin(c, g, act, ws, ws_bytes, stream));
+  int nc = 0;
+  MPN_TRY(scc_stage(c, act, &nc));
+  MPN_CUDA_OK(cudaMemcpyAsync(labels, c.label, sizeof(int) * g->n_nodes, cudaMemcpyDeviceToDevice, c.st));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  if (n_components) *n_components = nc;
+  return MPN_OK;
+}
+
+int mpn_post_processing(const mpn_graph* g, uint8_t* act, const float* prob1, int32_t pstride, int32_t num_cameras, int32_t flags,
+                        int32_t* labels, int32_t* n_components, int32_t* prune_changed, void* ws, size_t ws_bytes, void* stream) {
+  PostCtx c;
+  MPN_REQUIRE(prob1 && pstride >= 1 && num_cameras >= 1, "post_processing: bad arguments");
+  MPN_TRY(post_begin(c, g, act, ws, ws_bytes, stream));
+  int ch = 0, r = 0;
+  if ((flags & MPN_POST_CUT) && c.n_active) {
+    cut_kernel<<<list_grid(c.n_active), 256, 0, c.st>>>(c.n_active, c.a_eid, c.a_rev, act);
+    MPN_LAUNCH_OK();
+  }
+  if (flags & MPN_POST_PRUNE) MPN_TRY(prune_stage(c, act, prob1, pstride, num_cameras, &ch, &r));
+  if ((flags & MPN_POST_CUT) && c.n_active) {
+    cut_kernel<<<list_grid(c.n_active), 256, 0, c.st>>>(c.n_active, c.a_eid, c.a_rev, act);
+    MPN_LAUNCH_OK();
+  }
+  if (flags & MPN_POST_SPLIT) MPN_TRY(split_stage(c, act, prob1, pstride, num_cameras, &r));
+  int nc = 0;
+  MPN_TRY(scc_stage(c, act, &nc));
+  if (labels) MPN_CUDA_OK(cudaMemcpyAsync(labels, c.label, sizeof(int) * g->n_nodes, cudaMemcpyDeviceToDevice, c.st));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  if (n_components) *n_components = nc;
+  if (prune_changed) *prune_changed = ch;
+  return MPN_OK;
+}
+
+int mpn_active_edges(const mpn_graph* g, const uint8_t* act, int32_t* src_out, int32_t* dst_out, int64_t capacity,
+                     int64_t* n_active, void* ws, size_t ws_bytes, void* stream) {
+  PostCtx c;
+  MPN_TRY(post_begin(c, g, act, ws, ws_bytes, stream));
+  if (n_active) *n_active = c.n_active;
+  MPN_REQUIRE(c.n_active <= capacity, "active_edges: capacity %lld < %d active edges", (long long)capacity, c.n_active);
+  if (c.n_active) {
+    MPN_REQUIRE(src_out && dst_out, "active_edges: NULL output");
+    MPN_CUDA_OK(cudaMemcpyAsync(src_out, c.a_src, sizeof(int) * c.n_active, cudaMemcpyDeviceToDevice, c.st));
+    MPN_CUDA_OK(cudaMemcpyAsync(dst_out, c.a_dst, sizeof(int) * c.n_active, cudaMemcpyDeviceToDevice, c.st));
+    MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  }
+  return MPN_OK;
+}
+
+int mpn_labels_reference_host(const int32_t* src, const int32_t* dst, int64_t n_active, int32_t n_nodes, int64_t* labels_out,
+                              int32_t* n_components) {
+  MPN_REQUIRE(labels_out && n_nodes > 0 && n_active >= 0 && (n_active == 0 || (src && dst)), "labels_reference_host: bad arguments");
+  for (int64_t i = 0; i < n_active; ++i)
+    MPN_REQUIRE(src[i] >= 0 && src[i] < n_nodes && dst[i] >= 0 && dst[i] < n_nodes, "labels_reference_host: node id out of range");
+  int nc = 0;
+  labels_reference(src, dst, n_active, n_nodes, (long long*)labels_out, &nc);
+  if (n_components) *n_components = nc;
+  return MPN_OK;
+}
+
+}  // extern "C"

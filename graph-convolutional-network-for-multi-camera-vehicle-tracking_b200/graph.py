@@ -1,0 +1,107 @@
+"""Device-side graph tables (int32 CSR + task table) for a tracklet graph.
+
+The reference indexes node features with ``row, col = edge_index`` (models/mpn.py:44,82) on the int64
+[2,E] tensor built by ``torch.cartesian_prod`` per camera (inference.py:407-413).  The kernels use an int32
+CSR over ``row`` (the node at which messages are aggregated, models/mpn.py:97-99) plus a table of *tasks*
+(runs of at most ``chunk`` edges of one row) that warps iterate over.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_WORKSPACES = {}
+
+
+def workspace(kind: str, device: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only uint8 scratch buffer per (kind, device); torch owns the memory, the C ABI only borrows it."""
+    key = (kind, device.index)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _WORKSPACES.pop(key, None)
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def current_stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def choose_chunk(n_edges: int) -> int:
+    """Edges per task: aim for >= 4 tasks per resident warp slot of a 148-SM part, within [32, 1024]."""
+    target = max(1, n_edges // (148 * 32 * 4))
+    chunk = 32
+    while chunk * 2 <= target and chunk < 1024:
+        chunk *= 2
+    return chunk
+
+
+class TrackletGraph:
+    """CSR + task tables on the device.  ``perm`` is None when the caller's edge order is already (row, col)-sorted,
+    otherwise ``sorted_edge = original_edge[perm]``."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, chunk: int = None, row_offset: int = 0,
+                 n_rows: int = None):
+        if not edge_index.is_cuda:
+            raise RuntimeError("TrackletGraph needs a CUDA edge_index: the B200 path has no CPU fallback")
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError("edge_index must have shape [2, E]")
+        dev = edge_index.device
+        _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        self.device = dev
+        self.n_cols = int(num_nodes)
+        self.n_nodes = int(n_rows if n_rows is not None else num_nodes)
+        self.row_offset = int(row_offset)
+        self.n_edges = int(edge_index.shape[1])
+        self.chunk = int(chunk or choose_chunk(self.n_edges))
+        self.max_tasks = self.n_edges // self.chunk + self.n_nodes
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(self.n_nodes + 1, **i32)
+        self.col = torch.empty(max(self.n_edges, 1), **i32)
+        self.taskptr = torch.empty(self.n_nodes + 1, **i32)
+        self.task_row = torch.empty(max(self.max_tasks, 1), **i32)
+        self.n_tasks = torch.zeros(1, **i32)
+        self.perm = None
+        self.struct = _lib.MpnGraph(self.n_nodes, self.n_cols, self.row_offset, self.chunk, self.n_edges, self.max_tasks, 0,
+                                    self.rowptr.data_ptr(), self.col.data_ptr(), self.taskptr.data_ptr(),
+                                    self.task_row.data_ptr(), self.n_tasks.data_ptr())
+        ei = edge_index
+        if ei.dtype != torch.int64:
+            ei = ei.long()
+        ei = ei.contiguous()
+        stream = current_stream_ptr(dev)
+        with torch.cuda.device(dev):
+            try:
+                _lib.check(_lib.lib().mpn_graph_build(C.byref(self.struct), ei.data_ptr(), stream))
+            except _lib.UnsortedEdgeIndex:
+                # training-style graphs (train.py:295-302) are not row-sorted: sort once, remember the permutation
+                key = ei[0] * self.n_cols + ei[1]
+                skey, perm = torch.sort(key, stable=True)
+                if self.n_edges > 1 and bool((skey[1:] == skey[:-1]).any()):
+                    raise ValueError("edge_index contains duplicate edges")
+                self.perm = perm
+                ei = ei[:, perm].contiguous()
+                _lib.check(_lib.lib().mpn_graph_build(C.byref(self.struct), ei.data_ptr(), stream))
+        self._keepalive = ei
+
+    @property
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def graph_for(data, edge_index: torch.Tensor, num_nodes: int) -> TrackletGraph:
+    """Graph tables cached on the data object (one graph per batch in the reference driver, inference.py:375)."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes))
+    cached = getattr(data, "_mpn_b200_graph", None) if data is not None else None
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    g = TrackletGraph(edge_index, num_nodes)
+    if data is not None:
+        try:
+            object.__setattr__(data, "_mpn_b200_graph", (key, g))
+        except Exception:
+            pass
+    return g

@@ -1,0 +1,231 @@
+"""Drop-in ``MOTMPNet`` for the reference's tracklet-graph message-passing network.
+
+Same constructor (``MOTMPNet(model_params, bb_encoder=None, arch)``, models/mpn.py:154), same ``state_dict``
+keys and shapes (so ``utils.load_pretrained_weights`` works unchanged, utils.py:482-531) and the same
+``forward(data) -> ({'classified_edges': [...]}, latent_node_feats)`` contract (models/mpn.py:250-299).
+The parameters live in ordinary ``nn.Linear`` / ``nn.BatchNorm1d`` modules arranged exactly as the reference's
+``nn.Sequential`` numbers them (models/mlp.py:11-30); the computation is done by libmpn_b200's sm_100a kernels.
+There is no PyTorch/CPU fallback for ``forward``.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+from .graph import current_stream_ptr, graph_for, workspace
+
+USE_TENSOR_CORES = True
+
+
+class MLP(nn.Module):
+    """Parameter container with the reference layout: [Linear, BatchNorm1d, ReLU, Dropout] per hidden width
+    (BN/ReLU/Dropout omitted for width 1; bare Linear stack for classifiers) — models/mlp.py:4-33."""
+
+    def __init__(self, input_dim, fc_dims, dropout_p=0.4, use_batchnorm=False, is_classifier=False):
+        super().__init__()
+        assert isinstance(fc_dims, (list, tuple)), \
+            'fc_dims must be either a list or a tuple, but got {}'.format(type(fc_dims))
+        mods, self.blocks = [], []
+        for width in fc_dims:
+            lin_pos, bn_pos = len(mods), None
+            mods.append(nn.Linear(input_dim, width))
+            if not is_classifier and width != 1:
+                if use_batchnorm:
+                    bn_pos = len(mods)
+                    mods.append(nn.BatchNorm1d(width, track_running_stats=False))
+                mods.append(nn.ReLU(inplace=True))
+                if dropout_p is not None:
+                    mods.append(nn.Dropout(p=dropout_p))
+            self.blocks.append((lin_pos, bn_pos))
+            input_dim = width
+        self.fc_layers = nn.Sequential(*mods)
+
+    def forward(self, input):
+        raise RuntimeError("the B200 MLP modules only hold parameters; call MOTMPNet.forward (CUDA kernels)")
+
+
+class MLPGraphIndependent(nn.Module):
+    """Encoder / classifier container (models/mpn.py:103-142)."""
+
+    def __init__(self, edge_in_dim=None, node_in_dim=None, edge_out_dim=None, node_out_dim=None, node_fc_dims=None,
+                 edge_fc_dims=None, dropout_p=None, use_batchnorm=None, is_classifier=False):
+        super().__init__()
+        self.node_mlp = None if node_in_dim is None else MLP(node_in_dim, list(node_fc_dims) + [node_out_dim],
+                                                             dropout_p, use_batchnorm, is_classifier)
+        self.edge_mlp = None if edge_in_dim is None else MLP(edge_in_dim, list(edge_fc_dims) + [edge_out_dim],
+                                                             dropout_p, use_batchnorm, is_classifier)
+
+
+class EdgeModel(nn.Module):
+    def __init__(self, edge_mlp):
+        super().__init__()
+        self.edge_mlp = edge_mlp
+
+
+class NodeModel(nn.Module):
+    def __init__(self, node_mlp, node_agg_fn):
+        super().__init__()
+        self.node_mlp = node_mlp
+        self.node_agg_fn = node_agg_fn
+
+
+class MetaLayer(nn.Module):
+    def __init__(self, edge_model=None, node_model=None):
+        super().__init__()
+        self.edge_model = edge_model
+        self.node_model = node_model
+
+
+def _unsupported(what):
+    return NotImplementedError("libmpn_b200 does not implement %s (supported family: the shipped configuration "
+                               "config/config_training.yaml:68-111 with any node-encoder widths, any num_enc_steps / "
+                               "num_class_steps); there is no PyTorch fallback" % what)
+
+
+class MOTMPNet(nn.Module):
+    def __init__(self, model_params, bb_encoder=None, arch=None):
+        super().__init__()
+        self.node_cnn = bb_encoder
+        self.model_params = model_params
+        # the reference merges the node-encoder dict into the edge-encoder dict in place (models/mpn.py:167-170)
+        edges_params = model_params['encoder_feats_dict']['edges']
+        nodes_params = model_params['encoder_feats_dict']['nodes'][arch]
+        edges_params.update(nodes_params)
+        enc = edges_params
+        cls = model_params['classifier_feats_dict']
+        self.encoder = MLPGraphIndependent(**enc)
+        self.classifier = MLPGraphIndependent(**cls)
+
+        agg = model_params['node_agg_fn']
+        assert agg.lower() in ('mean', 'max', 'sum'), "node_agg_fn can only be 'max', 'mean' or 'sum'."
+        self.reattach_initial_nodes = model_params['reattach_initial_nodes']
+        self.reattach_initial_edges = model_params['reattach_initial_edges']
+        edge_factor = 2 if self.reattach_initial_edges else 1
+        node_factor = 2 if self.reattach_initial_nodes else 1
+        edge_in = node_factor * 2 * enc['node_out_dim'] + edge_factor * enc['edge_out_dim']
+        node_in = node_factor * enc['node_out_dim'] + enc['edge_out_dim']
+        em, nm = model_params['edge_model_feats_dict'], model_params['node_model_feats_dict']
+        self.MPNet = MetaLayer(
+            edge_model=EdgeModel(MLP(edge_in, em['fc_dims'], em['dropout_p'], em['use_batchnorm'])),
+            node_model=NodeModel(MLP(node_in, nm['fc_dims'], nm['dropout_p'], nm['use_batchnorm']), agg))
+        self.num_enc_steps = model_params['num_enc_steps']
+        self.num_class_steps = model_params['num_class_steps']
+
+        # ---- what the kernels support; checked once here so forward() fails early and loudly ----
+        if agg != 'sum':
+            raise _unsupported("node_agg_fn=%r" % agg)
+        if self.reattach_initial_nodes or self.reattach_initial_edges:
+            raise _unsupported("reattach_initial_nodes/edges=True")
+        if not (enc['edge_in_dim'] == 2 and list(enc['edge_fc_dims']) == [4] and enc['edge_out_dim'] == 4):
+            raise _unsupported("an edge encoder other than 2->[4]->4")
+        if enc['node_out_dim'] != _lib.MPN_DH or len(enc['node_fc_dims']) + 1 > _lib.MPN_MAX_NODE_LAYERS:
+            raise _unsupported("node_out_dim != 32 or more than 8 node-encoder layers")
+        if not (enc['use_batchnorm'] and em['use_batchnorm'] and nm['use_batchnorm']):
+            raise _unsupported("use_batchnorm=False")
+        if list(em['fc_dims']) != [4] or list(nm['fc_dims']) != [32]:
+            raise _unsupported("edge_model fc_dims != [4] or node_model fc_dims != [32]")
+        if not (cls['edge_in_dim'] == 4 and list(cls['edge_fc_dims']) == [] and cls['edge_out_dim'] == 2
+                and cls.get('is_classifier', False)):
+            raise _unsupported("a classifier other than Linear 4->2")
+        if any(w == 1 for w in list(enc['node_fc_dims'])):
+            raise _unsupported("node encoder widths of 1")
+        self._packed = None          # (version key, small block tensor, MpnWeights struct, keepalive list)
+        self.fuse_decisions = False  # when True forward also stores self.last_pred (uint8) / self.last_prob1 (fp32)
+        self.last_pred = self.last_prob1 = None
+
+    # ------------------------------------------------------------------------------------------
+    def _weights(self, device):
+        params = list(self.parameters())
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[2]
+        for p in params:
+            if p.device != device or p.dtype != torch.float32:
+                raise RuntimeError("all MOTMPNet parameters must be fp32 on %s (got %s %s)" % (device, p.dtype, p.device))
+        W = _lib.MpnWeights()
+        keep = []
+        nmlp = self.encoder.node_mlp
+        W.n_node_layers = len(nmlp.blocks)
+        for i, (lin, bn) in enumerate(nmlp.blocks):
+            l, b = nmlp.fc_layers[lin], nmlp.fc_layers[bn]
+            if i == 0:
+                W.node_dims[0] = l.in_features
+            W.node_dims[i + 1] = l.out_features
+            ts = [l.weight.detach().contiguous(), l.bias.detach().contiguous(), b.weight.detach().contiguous(),
+                  b.bias.detach().contiguous()]
+            keep += ts
+            W.node_w[i], W.node_b[i], W.node_gamma[i], W.node_beta[i] = (t.data_ptr() for t in ts)
+        small = torch.zeros(_lib.W_SMALL_FLOATS, dtype=torch.float32, device=device)
+
+        def put(off, t):
+            small[off:off + t.numel()] = t.detach().reshape(-1)
+
+        e = self.encoder.edge_mlp
+        (l1, b1), (l2, b2) = e.blocks
+        put(_lib.W_ENC1_W, e.fc_layers[l1].weight); put(_lib.W_ENC1_B, e.fc_layers[l1].bias)
+        put(_lib.W_ENC1_G, e.fc_layers[b1].weight); put(_lib.W_ENC1_BETA, e.fc_layers[b1].bias)
+        put(_lib.W_ENC2_W, e.fc_layers[l2].weight); put(_lib.W_ENC2_B, e.fc_layers[l2].bias)
+        put(_lib.W_ENC2_G, e.fc_layers[b2].weight); put(_lib.W_ENC2_BETA, e.fc_layers[b2].bias)
+        m = self.MPNet.edge_model.edge_mlp
+        (l, b), = m.blocks
+        put(_lib.W_EDGE_W, m.fc_layers[l].weight); put(_lib.W_EDGE_B, m.fc_layers[l].bias)
+        put(_lib.W_EDGE_G, m.fc_layers[b].weight); put(_lib.W_EDGE_BETA, m.fc_layers[b].bias)
+        m = self.MPNet.node_model.node_mlp
+        (l, b), = m.blocks
+        put(_lib.W_NODE_W, m.fc_layers[l].weight); put(_lib.W_NODE_B, m.fc_layers[l].bias)
+        put(_lib.W_NODE_G, m.fc_layers[b].weight); put(_lib.W_NODE_BETA, m.fc_layers[b].bias)
+        c = self.classifier.edge_mlp
+        (l, _), = c.blocks
+        put(_lib.W_CLS_W, c.fc_layers[l].weight); put(_lib.W_CLS_B, c.fc_layers[l].bias)
+        W.small = small.data_ptr()
+        self._packed = (key, small, W, keep)
+        return W
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, data):
+        """data.x [N,D] fp32, data.edge_index [2,E] int64, data.edge_attr [E,2] fp32, all on one CUDA device.
+        Returns ({'classified_edges': [logits [E,2], ...]}, latent_node_feats [N,32]) as models/mpn.py:299."""
+        x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
+        if not (x.is_cuda and edge_index.is_cuda and edge_attr.is_cuda):
+            raise RuntimeError("MOTMPNet.forward needs CUDA tensors: the B200 path has no CPU fallback")
+        if self.training:
+            raise _unsupported("training mode (dropout active / autograd); call .eval() as main.py:98 does")
+        dev = x.device
+        x = x.contiguous().float()
+        g = graph_for(data, edge_index, x.shape[0])
+        ea = edge_attr.contiguous().float()
+        if g.perm is not None:
+            ea = ea[g.perm].contiguous()
+        W = self._weights(dev)
+        if x.shape[1] != W.node_dims[0]:
+            raise ValueError("data.x has %d features, the node encoder expects %d" % (x.shape[1], W.node_dims[0]))
+        if ea.shape != (g.n_edges, 2):
+            raise ValueError("data.edge_attr must be [E,2]")
+        L, n_cls = int(self.num_enc_steps), int(self.num_class_steps)
+        n_out = 1 if L == 0 else n_cls
+        logits = torch.empty(max(n_out, 1), g.n_edges, 2, dtype=torch.float32, device=dev)
+        h = torch.empty(g.n_nodes, _lib.MPN_DH, dtype=torch.float32, device=dev)
+        pred = prob1 = None
+        if self.fuse_decisions and n_out > 0:
+            pred = torch.empty(g.n_edges, dtype=torch.uint8, device=dev)
+            prob1 = torch.empty(g.n_edges, dtype=torch.float32, device=dev)
+        lib = _lib.lib()
+        need = lib.mpn_forward_workspace_bytes(g.ref, C.byref(W), L)
+        ws = workspace("forward", dev, need)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mpn_forward(g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, logits.data_ptr(),
+                                       h.data_ptr(), pred.data_ptr() if pred is not None else None,
+                                       prob1.data_ptr() if prob1 is not None else None, int(bool(USE_TENSOR_CORES)),
+                                       ws.data_ptr(), ws.numel(), current_stream_ptr(dev)))
+        if g.perm is not None:                       # back to the caller's edge order
+            inv = torch.empty_like(logits)
+            inv[:, g.perm] = logits
+            logits = inv
+            if pred is not None:
+                p2, q2 = torch.empty_like(pred), torch.empty_like(prob1)
+                p2[g.perm], q2[g.perm] = pred, prob1
+                pred, prob1 = p2, q2
+        self.last_pred, self.last_prob1 = pred, prob1
+        return {'classified_edges': [logits[i] for i in range(n_out)]}, h

@@ -1,0 +1,226 @@
+/*
+ * mpn_b200.h — C ABI of the B200-native tracklet-graph message-passing path.
+ *
+ * Drop-in boundary for the reference's hot path.  The reference has no FFI layer (it is pure
+ * Python on ATen / torch_scatter / networkx); each entry point below names the reference code it
+ * replaces (paths relative to the upstream repository root).  The Python host in
+ * graph-convolutional-network-for-multi-camera-vehicle-tracking_b200/ binds these with ctypes and
+ * mirrors the reference classes/functions (MOTMPNet, post_processing, pruning, splitting, ...).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `dev` pointer is CUDA device memory owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.  Functions documented as
+ *     "synchronises" wait for the stream internally because they return host-side results;
+ *   - workspaces are caller-allocated device memory; the *_workspace_bytes functions size them;
+ *   - return value: 0 = ok, otherwise an MPN_ERR_* code; mpn_last_error() gives a thread-local message;
+ *   - floating point is IEEE fp32 with fp64 accumulation of all BatchNorm moments; indices int32 on
+ *     device (edge ids < 2^31 per shard), int64 accepted at the boundary as the reference delivers them.
+ */
+#ifndef MPN_B200_H
+#define MPN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPN_B200_ABI_VERSION 1
+
+enum {
+  MPN_OK = 0,
+  MPN_ERR_INVALID = 1,      /* bad argument / unsupported configuration */
+  MPN_ERR_CUDA = 2,         /* a CUDA runtime call or kernel launch failed */
+  MPN_ERR_UNSORTED = 3,     /* edge_index is not lexicographically (row, col) sorted */
+  MPN_ERR_WORKSPACE = 4,    /* workspace too small */
+  MPN_ERR_NO_DEVICE = 5     /* no sm_100 device / kernels not loadable */
+};
+
+/* fixed widths of the supported model family (config/config_training.yaml:68-111) */
+#define MPN_DE 4            /* edge embedding width  (encoder edge_out_dim, edge_model fc_dims[-1]) */
+#define MPN_DH 32           /* node embedding width  (encoder node_out_dim, node_model fc_dims[-1]) */
+#define MPN_MAX_NODE_LAYERS 8
+
+int mpn_abi_version(void);
+const char* mpn_last_error(void);
+/* 0 if device `dev` exists and is sm_100; error otherwise.  Never falls back to CPU. */
+int mpn_check_device(int dev);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph tables (K0).  Replaces the implicit `row, col = edge_index` indexing of
+ * models/mpn.py:44,82 and the tuple-list scans of utils.py:125-142 with an int32 CSR.
+ * `edge_index` is the reference layout: int64 [2,E] row-major (row = edge_index[0], aggregated-at node).
+ * Must be lexicographically sorted by (row, col) and free of duplicates — true for inference graphs
+ * (inference.py:407-413); MPN_ERR_UNSORTED otherwise (the Python host then sorts and permutes).
+ * A task is a run of <= `chunk` consecutive edges of one row; max_tasks = E / chunk + N.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mpn_graph {
+  int32_t n_nodes;          /* nodes whose rows this table holds (all nodes of the graph, or a row block) */
+  int32_t n_cols;           /* size of the column (neighbour) id space: total nodes of the graph */
+  int32_t row_offset;       /* global id of local row 0 (0 for an unsharded graph) */
+  int32_t chunk;            /* edges per task (power of two, 32..4096) */
+  int64_t n_edges;
+  int32_t max_tasks;        /* capacity of task_row / task_beg */
+  int32_t reserved;
+  int32_t* rowptr;          /* dev [n_nodes+1]  */
+  int32_t* col;             /* dev [n_edges]    global column ids */
+  int32_t* taskptr;         /* dev [n_nodes+1]  first task of each row */
+  int32_t* task_row;        /* dev [max_tasks]  local row of each task */
+  int32_t* n_tasks;         /* dev [1]          */
+} mpn_graph;
+
+/* Fills the tables of `g` (pointers and sizes pre-set by the caller).  Synchronises (reads the sorted flag). */
+int mpn_graph_build(mpn_graph* g, const int64_t* edge_index_dev, void* stream);
+/* Same from int32 row/col arrays already split (used for row-block shards). */
+int mpn_graph_build_i32(mpn_graph* g, const int32_t* row_dev, const int32_t* col_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Edge features (K1).  Replaces inference.py:453-456:
+ *   edge_attr[e] = [ ||x_r - x_c + 1e-6||_2 , 1 - cos(x_r, x_c) ]
+ * computed from the Gram matrix X X^T (fp32-accurate: 3xTF32 tensor-core GEMM, or the fp32 SIMT GEMM
+ * when `use_tensor_cores` is 0) with the distance epilogue applied per edge; the [E,D] gathers of the
+ * reference are never materialised.  x: dev [n_cols, D] fp32 row-major.  edge_attr: dev [E,2].
+ * ---------------------------------------------------------------------------------------------- */
+size_t mpn_edge_features_workspace_bytes(const mpn_graph* g, int32_t D);
+int mpn_edge_features(const mpn_graph* g, const float* x_dev, int32_t D, float* edge_attr_dev,
+                      int use_tensor_cores, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MPN weights.  Same tensors, names and shapes as the reference state_dict (models/mpn.py:166-247,
+ * models/mlp.py:11-30); `small` is one packed fp32 block (offsets below) so the sweeps stage it once.
+ * ---------------------------------------------------------------------------------------------- */
+enum {                                   /* offsets (in floats) inside mpn_weights.small */
+  MPN_W_ENC1_W = 0,                      /* encoder.edge_mlp.fc_layers.0.weight [4,2]  */
+  MPN_W_ENC1_B = 8,                      /* ...0.bias [4] */
+  MPN_W_ENC1_G = 12,                     /* ...1.weight (BN gamma) [4] */
+  MPN_W_ENC1_BETA = 16,                  /* ...1.bias   (BN beta)  [4] */
+  MPN_W_ENC2_W = 20,                     /* encoder.edge_mlp.fc_layers.4.weight [4,4]  */
+  MPN_W_ENC2_B = 36,
+  MPN_W_ENC2_G = 40,
+  MPN_W_ENC2_BETA = 44,
+  MPN_W_EDGE_W = 48,                     /* MPNet.edge_model.edge_mlp.fc_layers.0.weight [4,68] = [h_row|h_col|e] */
+  MPN_W_EDGE_B = 320,
+  MPN_W_EDGE_G = 324,
+  MPN_W_EDGE_BETA = 328,
+  MPN_W_NODE_W = 332,                    /* MPNet.node_model.node_mlp.fc_layers.0.weight [32,36] = [h_row|e] */
+  MPN_W_NODE_B = 1484,
+  MPN_W_NODE_G = 1516,
+  MPN_W_NODE_BETA = 1548,
+  MPN_W_CLS_W = 1580,                    /* classifier.edge_mlp.fc_layers.0.weight [2,4] */
+  MPN_W_CLS_B = 1588,
+  MPN_W_SMALL_FLOATS = 1592
+};
+
+typedef struct mpn_weights {
+  int32_t n_node_layers;                          /* encoder.node_mlp: number of Linear+BN+ReLU blocks */
+  int32_t node_dims[MPN_MAX_NODE_LAYERS + 1];     /* in, hidden..., out (out must equal MPN_DH) */
+  const float* node_w[MPN_MAX_NODE_LAYERS];       /* dev [out,in] row-major (nn.Linear.weight) */
+  const float* node_b[MPN_MAX_NODE_LAYERS];       /* dev [out] */
+  const float* node_gamma[MPN_MAX_NODE_LAYERS];   /* dev [out] BatchNorm weight */
+  const float* node_beta[MPN_MAX_NODE_LAYERS];    /* dev [out] BatchNorm bias */
+  const float* small;                             /* dev [MPN_W_SMALL_FLOATS] */
+} mpn_weights;
+
+/* ------------------------------------------------------------------------------------------------
+ * Forward (K1b-K4).  Replaces MOTMPNet.forward (models/mpn.py:250-299) for the supported family:
+ * encoder (MLPGraphIndependent, mpn.py:128-142), `num_enc_steps` x MetaLayer (mpn.py:32-54: EdgeModel
+ * mpn.py:67-69, NodeModel mpn.py:97-99 with scatter_add mpn.py:202) and the edge classifier on the last
+ * `num_class_steps` steps (mpn.py:277,290-297).  BatchNorm uses batch statistics (models/mlp.py:16).
+ *   x          dev [n_cols, node_dims[0]]
+ *   edge_attr  dev [E,2]
+ *   logits_out dev [n_out, E, 2], n_out = max(num_class_steps,1) if L==0 else num_class_steps
+ *   h_out      dev [n_nodes, 32]   latent node features after the last step
+ *   pred_out   dev [E] uint8 or NULL: argmax of the LAST logits (ties -> 0)      (inference.py:479)
+ *   prob1_out  dev [E] fp32  or NULL: softmax(last logits)[:,1]                  (inference.py:475-477)
+ * ---------------------------------------------------------------------------------------------- */
+size_t mpn_forward_workspace_bytes(const mpn_graph* g, const mpn_weights* w, int32_t num_enc_steps);
+int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x_dev, const float* edge_attr_dev,
+                int32_t num_enc_steps, int32_t num_class_steps, float* logits_out_dev, float* h_out_dev,
+                uint8_t* pred_out_dev, float* prob1_out_dev, int use_tensor_cores,
+                void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Phase-level entry points of the same forward, for row-block sharded execution where the host inserts
+ * the collectives (all-reduce of BatchNorm moment sums, all-gather of h) between phases.  See DESIGN.md. */
+typedef struct mpn_fwd_plan mpn_fwd_plan;       /* opaque; lives inside the caller's workspace */
+enum { MPN_SUMS_DOUBLES = 96 };                 /* size of the moment-sum vector exchanged between ranks */
+enum {                                          /* sweep / stage ids */
+  MPN_STAGE_ENC0 = 0,     /* moments of edge_attr                      -> BN of encoder layer 1 */
+  MPN_STAGE_ENC1 = 1,     /* moments of encoder layer 2 pre-activation -> BN of encoder layer 2 */
+  MPN_STAGE_EDGE = 2,     /* moments of the edge-update pre-activation y -> BN of edge model     */
+  MPN_STAGE_NODE = 3,     /* moments of the node-update pre-activation z -> BN of node model     */
+  MPN_STAGE_APPLY = 4     /* apply: messages, segment sum, logits, decisions                     */
+};
+int mpn_plan_create(mpn_fwd_plan** plan_out, const mpn_graph* g, const mpn_weights* w, int32_t num_enc_steps,
+                    int32_t num_class_steps, int64_t total_edges, int use_tensor_cores,
+                    void* workspace_dev, size_t workspace_bytes);
+void mpn_plan_destroy(mpn_fwd_plan* plan);
+/* node encoder over all n_cols nodes (replicated on every rank); h0 -> plan-internal buffer [n_cols,32] */
+int mpn_plan_node_encoder(mpn_fwd_plan* plan, const float* x_dev, void* stream);
+/* per-step node tables from the plan's full h buffer (after the host has all-gathered it) */
+int mpn_plan_node_tables(mpn_fwd_plan* plan, int32_t step, void* stream);
+/* run the sweep of `stage` for `step` (1-based); leaves local moment sums in plan sums buffer */
+int mpn_plan_sweep(mpn_fwd_plan* plan, int32_t step, int32_t stage, const float* edge_attr_dev,
+                   float* logits_out_dev, uint8_t* pred_out_dev, float* prob1_out_dev, void* stream);
+/* device pointer to the MPN_SUMS_DOUBLES fp64 sums of the last sweep (all-reduce this across ranks) */
+double* mpn_plan_sums(mpn_fwd_plan* plan);
+/* reduce this rank's block partials of the last sweep into the sums vector (fixed order); with_consts != 0
+ * also folds the constants right away (single-GPU shortcut for reduce + finalize) */
+int mpn_plan_reduce(mpn_fwd_plan* plan, int32_t stage, int with_consts, void* stream);
+/* turn (all-reduced) sums into folded BatchNorm constants for the next sweep */
+int mpn_plan_finalize(mpn_fwd_plan* plan, int32_t step, int32_t stage, void* stream);
+/* after MPN_STAGE_APPLY: reduce task partials into h rows of this shard; returns device pointers */
+int mpn_plan_node_finalize(mpn_fwd_plan* plan, int32_t step, void* stream);
+float* mpn_plan_h_full(mpn_fwd_plan* plan);     /* dev [n_cols,32]: row block [row_offset, +n_nodes) is this rank's */
+
+/* ------------------------------------------------------------------------------------------------
+ * Decisions.  Replaces inference.py:475-479 when the caller owns the logits.
+ * ---------------------------------------------------------------------------------------------- */
+int mpn_decide(const float* logits_dev, int64_t n_edges, uint8_t* pred_out_dev, float* prob1_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Post-processing (K5).  `act` is dev uint8 [E] (1 = active edge), updated in place; `prob1` dev fp32
+ * with element stride `prob_stride` (2 when pointing at column 1 of the caller's [E,2] softmax).
+ * All of these synchronise the stream (they iterate to a fixed point with host-visible flags).
+ *   mpn_cut     remove_edges_single_direction      utils.py:125-142
+ *   mpn_prune   pruning                            utils.py:144-339 (live 161-188,277-317); *changed_host = 0
+ *               is the reference's "return []" case
+ *   mpn_split   splitting                          utils.py:54-123
+ *   mpn_scc_labels  partition of compute_SCC_and_Clusters (utils.py:30-52); labels_dev[n] = smallest node
+ *               id of n's strongly connected component ("canonical" numbering)
+ *   mpn_post_processing  inference.post_processing inference.py:70-169 (CUT, PRUNE, CUT, SPLIT)
+ * ---------------------------------------------------------------------------------------------- */
+enum { MPN_POST_CUT = 1, MPN_POST_PRUNE = 2, MPN_POST_SPLIT = 4 };
+size_t mpn_post_workspace_bytes(const mpn_graph* g);
+int mpn_cut(const mpn_graph* g, uint8_t* act_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+int mpn_prune(const mpn_graph* g, uint8_t* act_dev, const float* prob1_dev, int32_t prob_stride, int32_t num_cameras,
+              int32_t* changed_host, int32_t* rounds_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+int mpn_split(const mpn_graph* g, uint8_t* act_dev, const float* prob1_dev, int32_t prob_stride, int32_t num_cameras,
+              int32_t* rounds_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+int mpn_scc_labels(const mpn_graph* g, const uint8_t* act_dev, int32_t* labels_dev, int32_t* n_components_host,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
+int mpn_post_processing(const mpn_graph* g, uint8_t* act_dev, const float* prob1_dev, int32_t prob_stride,
+                        int32_t num_cameras, int32_t flags, int32_t* labels_dev, int32_t* n_components_host,
+                        int32_t* prune_changed_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Active edges in edge order as (src, dst) int32 pairs, for the reference label numbering.
+ * n_active_host receives the count; src_out/dst_out dev [capacity].  Synchronises. */
+int mpn_active_edges(const mpn_graph* g, const uint8_t* act_dev, int32_t* src_out_dev, int32_t* dst_out_dev,
+                     int64_t capacity, int64_t* n_active_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Host-side (CPU, sequential by nature): label integers exactly as compute_SCC_and_Clusters (utils.py:30-52)
+ * assigns them — networkx SCC emission order, stable sort by size, isolated nodes last.  HOST pointers. */
+int mpn_labels_reference_host(const int32_t* src_host, const int32_t* dst_host, int64_t n_active, int32_t n_nodes,
+                              int64_t* labels_out_host, int32_t* n_components_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM building block (exported for tests and for the roofline bench):
+ *   C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]), fp32 in / fp32 out, row-major, "NT".
+ *   impl: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 (TMA + TMEM).
+ * ---------------------------------------------------------------------------------------------- */
+size_t mpn_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int impl);
+int mpn_gemm_nt(const float* A_dev, const float* B_dev, const float* bias_dev, float* C_dev,
+                int32_t M, int32_t N, int32_t K, int impl, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPN_B200_H */

@@ -1,0 +1,41 @@
+import glob
+import os
+
+import numpy as np
+import torch
+
+from oracle import mpn_oracle as mo
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MPN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "mpn_*.npz")))
+POST_FILES = sorted(glob.glob(os.path.join(GOLDEN, "post_*.npz")))
+
+
+class Data:
+    """Stand-in for torch_geometric.data.Data (inference.py:458): attribute bag with num_nodes."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def num_nodes(self):
+        return self.x.size(0)
+
+
+def ids(files):
+    return [os.path.basename(p)[:-4] for p in files]
+
+
+def load_mpn_case(path):
+    g = np.load(path)
+    N, C, gseed, wseed, L, n_cls, din, planted, jitter = [int(v) for v in g["spec"]]
+    fcd = tuple(int(v) for v in g["fc_dims"])
+    params = mo.shipped_model_params(L, n_cls, din, fcd)
+    x, edge_index, cam, _ = mo.synth_graph(N, C, gseed, D=din, planted=bool(planted))
+    sd = mo.init_weights(params, "resnet101", wseed, affine_jitter=bool(jitter))
+    return g, params, sd, x, edge_index, C
+
+
+def same_partition(a, b):
+    a, b = np.asarray(a).tolist(), np.asarray(b).tolist()
+    return len(set(zip(a, b))) == len(set(a)) == len(set(b))

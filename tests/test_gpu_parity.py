@@ -1,0 +1,257 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden outputs.  B200 only."""
+import copy
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpn_oracle as mo
+from oracle import postproc_oracle as po
+from tests._util import Data, MPN_FILES, POST_FILES, ids, load_mpn_case, same_partition
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def m():
+    import gcn_mtmc_b200 as mod
+    mod._lib.require_device(0)
+    return mod
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+# ---------------------------------------------------------------------------------------------- graph tables
+def test_graph_tables_match_numpy(m):
+    x, ei, cam, _ = mo.synth_graph(90, 5, 3, D=8)
+    g = m.TrackletGraph(ei.to(dev()), 90, chunk=32)
+    row, col = ei[0].numpy(), ei[1].numpy()
+    rowptr = np.searchsorted(row, np.arange(91))
+    assert np.array_equal(g.rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(g.col.cpu().numpy()[:row.size], col)
+    deg = np.diff(rowptr)
+    nt = (deg + 31) // 32
+    assert int(g.n_tasks.item()) == nt.sum()
+    assert np.array_equal(g.taskptr.cpu().numpy(), np.r_[0, np.cumsum(nt)])
+    assert np.array_equal(g.task_row.cpu().numpy()[:nt.sum()], np.repeat(np.arange(90), nt))
+    assert g.perm is None
+
+
+def test_graph_unsorted_and_invalid(m):
+    x, ei, cam, _ = mo.synth_graph(40, 4, 5, D=8)
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(0))
+    g = m.TrackletGraph(ei[:, perm].to(dev()), 40)
+    assert g.perm is not None
+    assert torch.equal(ei[:, perm][:, g.perm.cpu()], ei)
+    with pytest.raises(ValueError):
+        m.TrackletGraph(torch.cat([ei, ei[:, :3]], dim=1).to(dev()), 40)          # duplicates
+    bad = ei.clone(); bad[1, 7] = 99
+    with pytest.raises(m._lib.MpnError):
+        m.TrackletGraph(bad.to(dev()), 40)                                         # node id out of range
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("shape", [(300, 1024, 2048), (257, 130, 96), (64, 32, 128), (1000, 512, 1024), (33, 7, 50)])
+def test_gemm_simt_matches_fp64(m, shape):
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    ref = (A.double() @ B.double().t() + bias.double())
+    Ad, Bd, bd = A.to(dev()), B.to(dev()), bias.to(dev())
+    Cd = torch.empty(M, N, device=dev())
+    ws = torch.empty(4096, dtype=torch.uint8, device=dev())
+    m._lib.check(m._lib.lib().mpn_gemm_nt(Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), Cd.data_ptr(), M, N, K, 0,
+                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    err = (Cd.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-6 * K ** 0.5 * 4, err            # fp32 accumulation bound (values ~N(0,1))
+
+
+# ---------------------------------------------------------------------------------------------- edge features
+@pytest.mark.parametrize("path", MPN_FILES, ids=ids(MPN_FILES))
+def test_edge_features_match_reference_golden(m, path):
+    g, params, sd, x, ei, _ = load_mpn_case(path)
+    out = m.edge_features(x.to(dev()), ei.to(dev()), use_tensor_cores=False).cpu().numpy()
+    assert np.allclose(out, g["edge_attr"], rtol=3e-6, atol=3e-6)
+
+
+def test_edge_features_near_duplicates_and_unsorted(m):
+    x, ei, cam, ident = mo.synth_graph(64, 4, 21, D=256, planted=True, noise=1e-3)     # near-duplicate embeddings
+    ref = mo.edge_features(x, ei, dtype=torch.float64).numpy()
+    out = m.edge_features(x.to(dev()), ei.to(dev()), use_tensor_cores=False).cpu().numpy()
+    assert np.allclose(out, ref, rtol=2e-5, atol=1e-6)
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(1))
+    out_p = m.edge_features(x.to(dev()), ei[:, perm].to(dev()), use_tensor_cores=False).cpu().numpy()
+    assert np.array_equal(out_p, out[perm.numpy()])
+
+
+# ---------------------------------------------------------------------------------------------- forward
+def run_forward(m, params, sd, x, ei, ea, fuse=False):
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev()).eval()
+    net.fuse_decisions = fuse
+    data = Data(x=x.to(dev()), edge_index=ei.to(dev()), edge_attr=ea.to(dev()))
+    out, h = net(data)
+    torch.cuda.synchronize()
+    return out["classified_edges"], h, net
+
+
+@pytest.mark.parametrize("path", MPN_FILES, ids=ids(MPN_FILES))
+def test_forward_matches_reference_golden(m, path):
+    g, params, sd, x, ei, _ = load_mpn_case(path)
+    ea = torch.from_numpy(g["edge_attr"])
+    outs, h, net = run_forward(m, params, sd, x, ei, ea, fuse=True)
+    assert len(outs) == int(g["n_logits"][0])
+    for i, o in enumerate(outs):
+        ref = g[f"logits{i}"]
+        tol = 1e-4 * np.abs(ref).max()                   # north_star tolerance: 1e-4 relative (to max |logit|)
+        assert np.abs(o.cpu().numpy() - ref).max() <= tol, (i, np.abs(o.cpu().numpy() - ref).max(), tol)
+    assert np.abs(h.cpu().numpy() - g["h"]).max() <= 1e-4 * max(1.0, np.abs(g["h"]).max())
+    last = g[f"logits{len(outs) - 1}"]
+    margin = np.abs(last[:, 1] - last[:, 0])
+    pred = net.last_pred.cpu().numpy()
+    assert not np.any((pred != g["pred"]) & (margin > 1e-4))      # decisions identical outside the 1e-4 band
+    assert np.abs(net.last_prob1.cpu().numpy() - g["prob"][:, 1]).max() <= 2e-5
+
+
+def test_forward_s02_shape_vs_oracle_and_deterministic(m):
+    params = mo.shipped_model_params(1, 1)
+    x, ei, cam, _ = mo.synth_graph(300, 4, 0, planted=True)
+    sd = mo.init_weights(params, "resnet101", 7)
+    ea = mo.edge_features(x, ei)
+    ref, href = mo.mpn_forward(sd, params, "resnet101", x, ei, ea)
+    ref64, _ = mo.mpn_forward(sd, params, "resnet101", x, ei, ea, dtype=torch.float64)
+    outs, h, net = run_forward(m, params, sd, x, ei, ea)
+    o = outs[0].cpu()
+    scale = ref64[0].abs().max().item()
+    err = (o.double() - ref64[0]).abs().max().item()
+    err_ref = (ref[0].double() - ref64[0]).abs().max().item()
+    assert err <= max(1e-4 * scale, err_ref), (err, err_ref)
+    assert (h.cpu() - href).abs().max().item() <= 1e-4 * max(1.0, href.abs().max().item())
+    outs2, h2, _ = run_forward(m, params, sd, x, ei, ea)
+    assert torch.equal(outs2[0].cpu(), o) and torch.equal(h2.cpu(), h.cpu())        # bit-reproducible
+
+
+def test_forward_multi_step_unsorted_edges(m):
+    params = mo.shipped_model_params(3, 2, 64, (48, 40))
+    x, ei, cam, _ = mo.synth_graph(80, 4, 31, D=64, planted=True)
+    sd = mo.init_weights(params, "resnet101", 9)
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(2))
+    ei_p = ei[:, perm]
+    ea_p = mo.edge_features(x, ei_p)
+    ref, href = mo.mpn_forward(sd, params, "resnet101", x, ei_p, ea_p, dtype=torch.float64)
+    outs, h, _ = run_forward(m, params, sd, x, ei_p, ea_p)
+    for o, r in zip(outs, ref):
+        assert (o.cpu().double() - r).abs().max().item() <= 1e-4 * r.abs().max().item()
+    assert (h.cpu().double() - href).abs().max().item() <= 1e-4 * max(1.0, href.abs().max().item())
+
+
+def test_forward_rejects_cpu_and_training(m):
+    params = mo.shipped_model_params(1, 1, 64, (48,))
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    x, ei, _, _ = mo.synth_graph(20, 2, 1, D=64)
+    with pytest.raises(RuntimeError):
+        net.eval()(Data(x=x, edge_index=ei, edge_attr=torch.zeros(ei.shape[1], 2)))
+    net = net.to(dev()).train()
+    with pytest.raises(NotImplementedError):
+        net(Data(x=x.to(dev()), edge_index=ei.to(dev()), edge_attr=torch.zeros(ei.shape[1], 2, device=dev())))
+
+
+def test_decide_kernel(m):
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(10001, 2, generator=g)
+    logits[5] = torch.tensor([0.25, 0.25])                                # tie -> class 0
+    prob, pred = mo.decide(logits)
+    ld = logits.to(dev())
+    p8 = torch.empty(10001, dtype=torch.uint8, device=dev())
+    p1 = torch.empty(10001, device=dev())
+    m._lib.check(m._lib.lib().mpn_decide(ld.data_ptr(), 10001, p8.data_ptr(), p1.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+    assert np.array_equal(p8.cpu().numpy(), pred.numpy().astype(np.uint8))
+    assert (p1.cpu() - prob[:, 1]).abs().max().item() <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- post-processing
+CONFIGS = (("full", (True, True, True)), ("cut_only", (True, False, False)), ("prune_only", (False, True, False)),
+           ("split_only", (False, False, True)), ("cut_prune", (True, True, False)))
+
+
+@pytest.mark.parametrize("path", POST_FILES, ids=ids(POST_FILES))
+def test_post_processing_matches_reference_golden(m, path):
+    g = np.load(path)
+    N, Cn, _ = [int(v) for v in g["spec"]]
+    ei = torch.from_numpy(np.stack([g["src"], g["dst"]]).astype(np.int64)).to(dev())
+    data = Data(x=torch.zeros(N, 1, device=dev()), edge_index=ei)
+    prob1 = torch.from_numpy(g["prob1"])
+    preds_prob = torch.stack([1 - prob1, prob1], dim=1).to(dev())
+    for tag, cfg in CONFIGS:
+        pred = torch.from_numpy(g["pred"].astype(np.int64)).to(dev())
+        CONFIG = {"CUTTING": cfg[0], "PRUNING": str(cfg[1]), "SPLITTING": cfg[2]}       # one flag as a CLI string
+        ID, P = m.post_processing(Cn, None, None, pred, None, CONFIG, data, preds_prob)
+        assert ID.dtype == torch.int64 and not ID.is_cuda and P.is_cuda and P.dtype == torch.int64
+        assert np.array_equal(P.cpu().numpy(), g["pred_" + tag]), tag           # bit-exact decisions
+        assert np.array_equal(ID.numpy(), g["labels_" + tag]), tag              # bit-exact label integers
+        pred = torch.from_numpy(g["pred"].astype(np.int64)).to(dev())
+        IDc, Pc = m.post_processing(Cn, None, None, pred, None, dict(CONFIG), data, preds_prob, numbering="canonical")
+        assert np.array_equal(Pc.cpu().numpy(), g["pred_" + tag])
+        assert same_partition(IDc.numpy(), g["labels_" + tag])
+    lab0, _ = m.compute_SCC_and_Clusters(list(zip(g["src"][g["pred"] != 0].tolist(), g["dst"][g["pred"] != 0].tolist())), N)
+    assert np.array_equal(lab0.numpy(), g["labels_initial"])
+
+
+def test_stage_functions_mirror_reference_contracts(m):
+    g = np.load(POST_FILES[0])
+    N, Cn, _ = [int(v) for v in g["spec"]]
+    src, dst = g["src"].astype(np.int64), g["dst"].astype(np.int64)
+    ei = torch.from_numpy(np.stack([src, dst])).to(dev())
+    data = Data(x=torch.zeros(N, 1, device=dev()), edge_index=ei)
+    pred = torch.from_numpy(g["pred"].astype(np.int64)).to(dev())
+    prob1 = torch.from_numpy(g["prob1"]).to(dev())
+    new_pred, act_list = m.remove_edges_single_direction(None, pred, None, data=data)
+    cut = po.cut_sequential(src, dst, g["pred"].astype(np.int64))
+    assert np.array_equal(new_pred.cpu().numpy(), cut) and new_pred.data_ptr() != pred.data_ptr()
+    assert act_list == [(int(src[e]), int(dst[e])) for e in np.flatnonzero(cut)]
+    r = m.pruning(data, new_pred, prob1, None, Cn)
+    ref = po.prune_sequential(src, dst, cut, g["prob1"], Cn, N)
+    assert (r == [] and ref is None) or np.array_equal(r.cpu().numpy(), ref)
+    assert m.pruning(data, torch.zeros_like(pred), prob1, None, Cn) == []            # nothing violated -> []
+    p2 = pred.clone()
+    out = m.splitting(None, p2, prob1, None, data, None, Cn)
+    assert out.data_ptr() == p2.data_ptr()                                         # mutated in place
+    assert np.array_equal(p2.cpu().numpy(), po.split_sequential(src, dst, g["pred"].astype(np.int64), g["prob1"], Cn, N))
+
+
+@pytest.mark.parametrize("n_nodes,cams,seed", [(3000, 6, 1), (20000, 8, 2)])
+def test_post_processing_sparse_large_vs_oracle_rounds(m, n_nodes, cams, seed):
+    src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, cams, seed, n_extra_per_node=6.0, flip_on=0.05,
+                                                          flip_off=0.03, single_dir=0.05)
+    lab_ref, act_ref = po.post_processing_rounds(src, dst, pred, prob, cams, n_nodes, numbering="reference")
+    ei = torch.from_numpy(np.stack([src, dst])).to(dev())
+    data = Data(x=torch.zeros(n_nodes, 1, device=dev()), edge_index=ei)
+    p = torch.from_numpy(prob).to(dev())
+    ID, P = m.post_processing(cams, None, None, torch.from_numpy(pred).to(dev()), None,
+                              {"CUTTING": True, "PRUNING": True, "SPLITTING": True}, data, p)
+    assert np.array_equal(P.cpu().numpy(), act_ref)
+    assert np.array_equal(ID.numpy(), lab_ref)
+    assert np.bincount(ID.numpy()).max() <= cams                                    # size-independent property
+
+
+def test_scc_with_one_directional_cycles(m):
+    # 3-cycle of one-directional edges between mutual-edge pairs: SCC must merge them (condensation path)
+    src = np.array([0, 1, 2, 3, 4, 5, 1, 3, 5, 6, 7], dtype=np.int64)
+    dst = np.array([1, 0, 3, 2, 5, 4, 2, 4, 0, 7, 8], dtype=np.int64)
+    order = np.lexsort((dst, src))
+    src, dst = src[order], dst[order]
+    ei = torch.from_numpy(np.stack([src, dst])).to(dev())
+    data = Data(x=torch.zeros(10, 1, device=dev()), edge_index=ei)
+    pred = torch.ones(src.size, dtype=torch.int64, device=dev())
+    prob = torch.linspace(0.6, 0.9, src.size).to(dev())
+    ID, P = m.post_processing(8, None, None, pred, None, {"CUTTING": False, "PRUNING": True, "SPLITTING": True}, data, prob)
+    ref, _ = po.scc_labels_reference(src, dst, np.ones(src.size), 10)
+    assert np.array_equal(ID.numpy(), ref)
+    IDc, _ = m.post_processing(8, None, None, pred, None, {"CUTTING": False, "PRUNING": True, "SPLITTING": True}, data, prob,
+                               numbering="canonical")
+    assert IDc.numpy().tolist() == [0, 0, 0, 0, 0, 0, 6, 7, 8, 9]

@@ -1,0 +1,80 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol; host logic that needs no GPU."""
+import copy
+import os
+import re
+
+import pytest
+import torch
+
+import gcn_mtmc_b200 as m
+from oracle import mpn_oracle as mo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = m._lib.lib()
+    header = open(os.path.join(ROOT, "include", "mpn_b200.h")).read()
+    declared = set(re.findall(r"\b(mpn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mpn_graph", "mpn_weights", "mpn_fwd_plan"}
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), "symbol %s declared in include/mpn_b200.h is not exported" % name
+    assert set(m._lib.EXPORTED_SYMBOLS) == declared
+    assert lib.mpn_abi_version() == 1
+
+
+def test_no_device_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(m._lib.MpnError):
+        m._lib.require_device(0)
+    net = m.MOTMPNet(copy.deepcopy(mo.shipped_model_params(1, 1, 64, (48,))), None, "resnet101").eval()
+    x, ei, _, _ = mo.synth_graph(20, 2, 1, D=64)
+
+    class D:
+        pass
+    d = D(); d.x, d.edge_index, d.edge_attr = x, ei, torch.zeros(ei.shape[1], 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(d)
+
+
+def test_state_dict_layout_matches_reference_names():
+    p = mo.shipped_model_params()
+    net = m.MOTMPNet(copy.deepcopy(p), None, "resnet101")
+    sd = mo.init_weights(p, "resnet101", 0)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    assert sum(v.numel() for v in net.state_dict().values()) == 2697750
+    # the constructor mutates the params dict exactly like the reference (models/mpn.py:169)
+    q = mo.shipped_model_params()
+    m.MOTMPNet(q, None, "resnet101")
+    assert "node_in_dim" in q["encoder_feats_dict"]["edges"]
+
+
+def test_unsupported_configs_raise():
+    p = mo.shipped_model_params()
+    p["node_agg_fn"] = "max"
+    with pytest.raises(NotImplementedError):
+        m.MOTMPNet(p, None, "resnet101")
+    p = mo.shipped_model_params()
+    p["reattach_initial_edges"] = True
+    with pytest.raises(NotImplementedError):
+        m.MOTMPNet(p, None, "resnet101")
+
+
+def test_host_reference_numbering_matches_oracle():
+    import numpy as np
+    from oracle import postproc_oracle as po
+    rng = np.random.default_rng(3)
+    for _ in range(30):
+        n = int(rng.integers(4, 60))
+        k = int(rng.integers(0, 5 * n))
+        s, d = rng.integers(0, n, k), rng.integers(0, n, k)
+        keep = s != d
+        key = np.unique(s[keep] * n + d[keep])
+        key = key[rng.permutation(key.size)]
+        s, d = key // n, key % n
+        ref, nref = po.scc_labels_reference(s, d, np.ones(s.size), n)
+        lab, nc = m.compute_SCC_and_Clusters(list(zip(s.tolist(), d.tolist())), n)
+        assert nc == nref and np.array_equal(lab.numpy(), ref)
