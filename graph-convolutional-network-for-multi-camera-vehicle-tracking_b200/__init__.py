@@ -11,8 +11,10 @@ from . import _lib
 from .edge_features import edge_features
 from .graph import TrackletGraph, graph_for
 from .mpn import MOTMPNet
+from .sharded import CudaPhases, ShardedMPN, partition_rows, shard_edges, sharded_forward
 from .postprocess import (compute_SCC_and_Clusters, post_processing, pruning, remove_edges_single_direction,
                           splitting)
 
 __all__ = ["MOTMPNet", "edge_features", "post_processing", "pruning", "splitting", "remove_edges_single_direction",
-           "compute_SCC_and_Clusters", "TrackletGraph", "graph_for", "_lib"]
+           "compute_SCC_and_Clusters", "TrackletGraph", "graph_for", "ShardedMPN", "CudaPhases", "sharded_forward", "partition_rows",
+           "shard_edges", "_lib"]

@@ -12,6 +12,7 @@ namespace mpn {
 constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 void set_error(const char* fmt, ...);
+extern unsigned long long g_kernel_launches;   // kernels launched by this library (bench.py's gpu_launches)
 
 #define MPN_CUDA_OK(expr)                                                                      \
   do {                                                                                         \
@@ -24,6 +25,7 @@ void set_error(const char* fmt, ...);
 
 #define MPN_LAUNCH_OK()                                                                        \
   do {                                                                                         \
+    ++mpn::g_kernel_launches;                                                                  \
     cudaError_t _e = cudaGetLastError();                                                       \
     if (_e != cudaSuccess) {                                                                   \
       mpn::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

@@ -1,11 +1,12 @@
 // K1: initial edge features (inference.py:453-456)
 //   edge_attr[e] = [ ||x_r - x_c + eps||_2 , 1 - cos(x_r, x_c) ],  eps = 1e-6 (F.pairwise_distance), cos eps = 1e-8
-// via the Gram matrix G = X X^T:
-//   ||a - b + eps||^2 = |a|^2 + |b|^2 - 2 a.b + 2 eps (sum a - sum b) + D eps^2
-//   cos = a.b / max(|a||b|, 1e-8)
-// The reference gathers two [E,D] copies (8 KB per edge each); here the only per-edge traffic is one
-// Gram read and one 8-byte write.  Pairs whose squared distance cancels badly (near-duplicate embeddings,
-// d^2 < 1% of |a|^2+|b|^2) are recomputed directly from the rows, exactly as the reference sums them.
+// via the Gram matrix of the CENTRED features x' = x - mean_row(x)  (distances are translation invariant, and ReID
+// embeddings share a large common component that would otherwise dominate the cancellation):
+//   ||a - b + eps||^2 = |a'|^2 + |b'|^2 - 2 a'.b' + 2 eps (sum a' - sum b') + D eps^2
+//   a.b = a'.b' + mu.a' + mu.b' + |mu|^2 ,   cos = a.b / max(|a||b|, 1e-8)
+// The reference gathers two [E,D] copies (8 KB per edge each); here the only per-edge traffic is one Gram read and
+// one 8-byte write.  Pairs whose squared distance still cancels (d^2 < 25% of |a'|^2+|b'|^2: same-identity pairs)
+// are recomputed directly from the rows, exactly as the reference sums them.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -13,31 +14,57 @@ namespace mpn {
 
 constexpr float PAIRWISE_EPS = 1e-6f;
 constexpr float COSINE_EPS = 1e-8f;
-constexpr float REFINE_FRACTION = 1e-2f;
+constexpr float REFINE_FRACTION = 0.25f;
 
-__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, int n, int D, double* __restrict__ sq,
-                                                        double* __restrict__ sx) {
+// column means of x [n, D] (fp64 accumulation): grid over 32-column tiles
+__global__ void __launch_bounds__(256) col_mean_kernel(const float* __restrict__ x, int n, int D, float* __restrict__ mu) {
+  __shared__ double ssum[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  double s = 0.0;
+  if (col < D)
+    for (int r = ry; r < n; r += 8) s += x[(size_t)r * D + col];
+  ssum[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && col < D) {
+    for (int i = 1; i < 8; ++i) s += ssum[i][cx];
+    mu[col] = (float)(s / n);
+  }
+}
+
+// xc = x - mu; per-row fp64 statistics of the centred row: st[r] = {|a'|^2, sum a', mu.a', |a|^2}
+__global__ void __launch_bounds__(256) center_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu, int n, int D,
+                                                          float* __restrict__ xc, double* __restrict__ st) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int r = gwarp; r < n; r += nwarps) {
     const float* p = x + (size_t)r * D;
-    double s = 0.0, q = 0.0;
+    float* q = xc + (size_t)r * D;
+    double sq = 0.0, sx = 0.0, md = 0.0, mm = 0.0;
     for (int k = lane; k < D; k += 32) {
-      const double v = p[k];
-      s += v;
-      q += v * v;
+      const float m = mu[k];
+      const float c = p[k] - m;
+      q[k] = c;
+      sq += (double)c * c;
+      sx += (double)c;
+      md += (double)m * c;
+      mm += (double)m * m;
     }
-    s = warp_sum(s);
-    q = warp_sum(q);
-    if (lane == 0) { sq[r] = q; sx[r] = s; }
+    sq = warp_sum(sq); sx = warp_sum(sx); md = warp_sum(md); mm = warp_sum(mm);
+    if (lane == 0) {
+      st[4 * (size_t)r + 0] = sq;
+      st[4 * (size_t)r + 1] = sx;
+      st[4 * (size_t)r + 2] = md + 0.5 * mm;          // a.b = g' + (mu.a' + |mu|^2/2) + (mu.b' + |mu|^2/2)
+      st[4 * (size_t)r + 3] = sq + 2.0 * md + mm;     // |a|^2
+    }
   }
 }
 
 // one warp per task (a run of edges of one row): coalesced Gram reads when the row's columns are consecutive
 __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_graph g, int r0, int r1, const float* __restrict__ G,
-                                                                  const double* __restrict__ sq, const double* __restrict__ sx,
-                                                                  int D, float2* __restrict__ edge_attr,
+                                                                  const double* __restrict__ st, int D,
+                                                                  float2* __restrict__ edge_attr,
                                                                   int* __restrict__ refine_list, int* __restrict__ refine_count) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -48,21 +75,22 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
     const int row = g.task_row[t];
     const int beg = g.rowptr[row] + (t - g.taskptr[row]) * g.chunk;
     const int end = min(beg + g.chunk, g.rowptr[row + 1]);
-    const int grow = row + g.row_offset;
-    const double sa = sq[grow], xa = sx[grow];
+    const size_t grow = (size_t)(row + g.row_offset);
+    const double sa = st[4 * grow], xa = st[4 * grow + 1], ma = st[4 * grow + 2], na = st[4 * grow + 3];
     const float* Grow = G + (size_t)(row - r0) * g.n_cols;
     for (int e = beg + lane; e < end; e += 32) {
-      const int c = g.col[e];
+      const size_t c = (size_t)g.col[e];
       const double gij = Grow[c];
-      const double sb = sq[c];
-      double d2 = sa + sb - 2.0 * gij + 2.0 * eps * (xa - sx[c]) + D * eps * eps;
+      const double sb = st[4 * c], xb = st[4 * c + 1], mb = st[4 * c + 2], nb = st[4 * c + 3];
+      double d2 = sa + sb - 2.0 * gij + 2.0 * eps * (xa - xb) + D * eps * eps;
       if (d2 < (double)REFINE_FRACTION * (sa + sb)) {
         const int slot = atomicAdd(refine_count, 1);
         refine_list[slot] = e;
       }
       if (d2 < 0.0) d2 = 0.0;
-      const double denom = fmax(sqrt(sa) * sqrt(sb), (double)COSINE_EPS);
-      edge_attr[e] = make_float2((float)sqrt(d2), (float)(1.0 - gij / denom));
+      const double ab = gij + ma + mb;
+      const double denom = fmax(sqrt(na) * sqrt(nb), (double)COSINE_EPS);
+      edge_attr[e] = make_float2((float)sqrt(d2), (float)(1.0 - ab / denom));
     }
   }
 }
@@ -103,7 +131,8 @@ __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_grap
 }
 
 struct EfLayout {
-  double *sq, *sx;
+  double* st;
+  float *mu, *xc;
   float* G;
   int *refine_list, *refine_count;
   void* gemm_ws;
@@ -115,8 +144,9 @@ struct EfLayout {
 static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) {
   EfLayout L;
   Arena a(ws, ws_bytes);
-  L.sq = a.take<double>(g->n_cols);
-  L.sx = a.take<double>(g->n_cols);
+  L.st = a.take<double>((size_t)g->n_cols * 4);
+  L.mu = a.take<float>(D);
+  L.xc = a.take<float>((size_t)g->n_cols * D);
   const size_t budget = (size_t)2 << 30;
   size_t rows = budget / ((size_t)g->n_cols * sizeof(float));
   if (rows < 128) rows = 128;
@@ -154,17 +184,19 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
     return MPN_ERR_WORKSPACE;
   }
   if (g->n_edges == 0) return MPN_OK;
-  row_stats_kernel<<<min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st>>>(x, g->n_cols, D, L.sq, L.sx);
+  col_mean_kernel<<<div_up(D, 32), 256, 0, st>>>(x, g->n_cols, D, L.mu);
+  MPN_LAUNCH_OK();
+  center_rows_kernel<<<min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st>>>(x, L.mu, g->n_cols, D, L.xc, L.st);
   MPN_LAUNCH_OK();
   MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, sizeof(int), st));
   for (int r0 = 0; r0 < g->n_nodes; r0 += L.rows_per_block) {
     const int r1 = min(r0 + L.rows_per_block, g->n_nodes);
-    const float* Ablk = x + (size_t)(g->row_offset + r0) * D;
+    const float* Ablk = L.xc + (size_t)(g->row_offset + r0) * D;
     if (use_tc && gemm_tc_supported(r1 - r0, g->n_cols, D))
-      MPN_TRY(gemm_nt_tc(Ablk, x, nullptr, L.G, r1 - r0, g->n_cols, D, L.gemm_ws, L.gemm_ws_bytes, st));
+      MPN_TRY(gemm_nt_tc(Ablk, L.xc, nullptr, L.G, r1 - r0, g->n_cols, D, L.gemm_ws, L.gemm_ws_bytes, st));
     else
-      MPN_TRY(gemm_nt_simt(Ablk, x, nullptr, nullptr, nullptr, L.G, r1 - r0, g->n_cols, D, st));
-    edge_feature_gather_kernel<<<kNumSMs * 8, 256, 0, st>>>(*g, r0, r1, L.G, L.sq, L.sx, D, (float2*)edge_attr,
+      MPN_TRY(gemm_nt_simt(Ablk, L.xc, nullptr, nullptr, nullptr, L.G, r1 - r0, g->n_cols, D, st));
+    edge_feature_gather_kernel<<<kNumSMs * 8, 256, 0, st>>>(*g, r0, r1, L.G, L.st, D, (float2*)edge_attr,
                                                            L.refine_list, L.refine_count);
     MPN_LAUNCH_OK();
   }

@@ -6,6 +6,7 @@
 namespace mpn {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_kernel_launches = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -118,6 +119,7 @@ extern "C" {
 
 int mpn_abi_version(void) { return MPN_B200_ABI_VERSION; }
 const char* mpn_last_error(void) { return mpn::g_err; }
+uint64_t mpn_kernel_launches(void) { return mpn::g_kernel_launches; }
 
 int mpn_check_device(int dev) {
   int n = 0;

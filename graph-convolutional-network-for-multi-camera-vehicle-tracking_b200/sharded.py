@@ -1,0 +1,199 @@
+"""Row-block sharded MPN forward across the GPUs of one box (new; the reference is single-GPU, main.py:7).
+
+Edges are sharded by the node at which messages are aggregated (``row = edge_index[0]``, models/mpn.py:97-99), so the
+segment sums stay local.  Every BatchNorm over edges becomes an all-reduce of a 96-double moment vector; every
+message-passing step after the first needs one all-gather of the updated node embeddings h [N,32].  ``x``, the weights
+and the node encoder are replicated (cheaper than communicating).
+
+The schedule (``sharded_forward``) is written against two small interfaces so it can be exercised on CPU with gloo:
+``phases`` (the per-rank compute: CUDA plan API here, an oracle-backed fake in tests/) and ``comm`` (collectives).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .graph import TrackletGraph, current_stream_ptr, workspace
+
+
+def partition_rows(rowptr: torch.Tensor, world: int):
+    """Contiguous row blocks balanced by out-degree.  rowptr: int tensor [N+1] (CPU).  Returns list of (n0, n1)."""
+    rp = rowptr.to(torch.int64).cpu()
+    n = rp.numel() - 1
+    total = int(rp[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r // world
+        idx = int(torch.searchsorted(rp, torch.tensor(target), right=False))
+        idx = min(max(idx, bounds[-1]), n)
+        bounds.append(idx)
+    bounds.append(n)
+    return [(bounds[i], bounds[i + 1]) for i in range(world)]
+
+
+def shard_edges(edge_index: torch.Tensor, n0: int, n1: int):
+    """Slice [e0, e1) of a row-sorted edge_index whose rows fall in [n0, n1)."""
+    row = edge_index[0].contiguous()
+    lo = int(torch.searchsorted(row, torch.tensor(n0, device=row.device, dtype=row.dtype), right=False))
+    hi = int(torch.searchsorted(row, torch.tensor(n1, device=row.device, dtype=row.dtype), right=False))
+    return lo, hi
+
+
+class TorchComm:
+    """torch.distributed collectives (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def all_gather_rows(self, full, blocks):
+        """full: [N, W]; this rank's block is already written; fill the others."""
+        if self.world == 1:
+            return
+        sizes = {b[1] - b[0] for b in blocks}
+        n0, n1 = blocks[self.rank]
+        if len(sizes) == 1 and blocks[-1][1] == full.shape[0]:
+            self.dist.all_gather_into_tensor(full, full[n0:n1].clone(), group=self.group)
+        else:                                       # ragged blocks: zero the rest and sum (x + 0 is exact)
+            full[:n0].zero_()
+            full[n1:].zero_()
+            self.dist.all_reduce(full, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+def sharded_forward(phases, comm, num_enc_steps: int, num_class_steps: int, blocks):
+    """The phase/collective schedule of one forward.  Returns the number of classified steps."""
+    L, n_cls = int(num_enc_steps), int(num_class_steps)
+    phases.node_encoder()
+    for stage in (_lib.STAGE_ENC0, _lib.STAGE_ENC1):
+        phases.sweep(0, stage)
+        phases.reduce(stage)
+        comm.all_reduce_sum(phases.sums())
+        phases.finalize(0, stage)
+    k = 0
+    if L == 0:
+        phases.sweep(0, _lib.STAGE_APPLY, out_index=0, last=True)
+        return 1
+    first_class_step = L - n_cls + 1
+    for step in range(1, L + 1):
+        if step > 1:
+            comm.all_gather_rows(phases.h_full(), blocks)
+        phases.node_tables(step)
+        for stage in (_lib.STAGE_EDGE, _lib.STAGE_NODE):
+            phases.sweep(step, stage)
+            phases.reduce(stage)
+            comm.all_reduce_sum(phases.sums())
+            phases.finalize(step, stage)
+        cls = step >= first_class_step
+        phases.sweep(step, _lib.STAGE_APPLY, out_index=k if cls else None, last=(step == L))
+        k += int(cls)
+        phases.node_finalize(step)
+    return k
+
+
+class CudaPhases:
+    """Per-rank compute through the plan API of libmpn_b200 (include/mpn_b200.h)."""
+
+    def __init__(self, graph: TrackletGraph, weights, x, edge_attr, L, n_cls, total_edges, logits, pred=None, prob1=None,
+                 use_tensor_cores=True, ws_kind="forward_plan"):
+        self.lib = _lib.lib()
+        self.g, self.x, self.ea = graph, x, edge_attr
+        self.dev = x.device
+        self.logits, self.pred, self.prob1 = logits, pred, prob1
+        need = self.lib.mpn_forward_workspace_bytes(graph.ref, C.byref(weights), L)
+        self.ws = workspace(ws_kind, self.dev, need)
+        self.plan = C.c_void_p()
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.mpn_plan_create(C.byref(self.plan), graph.ref, C.byref(weights), L, n_cls, int(total_edges),
+                                                int(bool(use_tensor_cores)), self.ws.data_ptr(), self.ws.numel()))
+        self._weights = weights
+        sums_off = self.lib.mpn_plan_sums(self.plan) - self.ws.data_ptr()
+        self._sums = self.ws[sums_off:sums_off + _lib.MPN_SUMS_DOUBLES * 8].view(torch.float64)
+        h_off = self.lib.mpn_plan_h_full(self.plan) - self.ws.data_ptr()
+        self._h = self.ws[h_off:h_off + graph.n_cols * _lib.MPN_DH * 4].view(torch.float32).view(graph.n_cols, _lib.MPN_DH)
+
+    def close(self):
+        if self.plan:
+            self.lib.mpn_plan_destroy(self.plan)
+            self.plan = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return current_stream_ptr(self.dev)
+
+    def node_encoder(self):
+        _lib.check(self.lib.mpn_plan_node_encoder(self.plan, self.x.data_ptr(), self.stream))
+
+    def node_tables(self, step):
+        _lib.check(self.lib.mpn_plan_node_tables(self.plan, step, self.stream))
+
+    def sweep(self, step, stage, out_index=None, last=False):
+        lg = pr = pb = None
+        if stage == _lib.STAGE_APPLY and out_index is not None:
+            lg = self.logits[out_index].data_ptr()
+            if last:
+                pr = self.pred.data_ptr() if self.pred is not None else None
+                pb = self.prob1.data_ptr() if self.prob1 is not None else None
+        _lib.check(self.lib.mpn_plan_sweep(self.plan, step, stage, self.ea.data_ptr(), lg, pr, pb, self.stream))
+
+    def reduce(self, stage, with_consts=False):
+        _lib.check(self.lib.mpn_plan_reduce(self.plan, stage, int(with_consts), self.stream))
+
+    def finalize(self, step, stage):
+        _lib.check(self.lib.mpn_plan_finalize(self.plan, step, stage, self.stream))
+
+    def node_finalize(self, step):
+        _lib.check(self.lib.mpn_plan_node_finalize(self.plan, step, self.stream))
+
+    def sums(self):
+        return self._sums
+
+    def h_full(self):
+        return self._h
+
+
+class ShardedMPN:
+    """Row-block sharded forward.  Each rank passes its own shard (``edge_index`` rows inside its block, global ids)
+    plus the replicated ``x``; outputs stay sharded (logits of the local edges, h of the local rows)."""
+
+    def __init__(self, model, group=None):
+        self.model = model
+        self.comm = TorchComm(group)
+
+    @torch.no_grad()
+    def forward(self, x, local_edge_index, local_edge_attr, blocks, fuse_decisions=False, graph=None):
+        from .mpn import USE_TENSOR_CORES
+        m, comm = self.model, self.comm
+        dev = x.device
+        n0, n1 = blocks[comm.rank]
+        g = graph if graph is not None else TrackletGraph(local_edge_index, x.shape[0], row_offset=n0, n_rows=n1 - n0)
+        if g.perm is not None:
+            raise ValueError("sharded forward needs (row, col)-sorted local edges")
+        W = m._weights(dev)
+        L, n_cls = int(m.num_enc_steps), int(m.num_class_steps)
+        n_out = 1 if L == 0 else n_cls
+        tot = torch.tensor([g.n_edges], dtype=torch.float64, device=dev)
+        comm.all_reduce_sum(tot)
+        logits = torch.empty(max(n_out, 1), g.n_edges, 2, dtype=torch.float32, device=dev)
+        pred = torch.empty(g.n_edges, dtype=torch.uint8, device=dev) if fuse_decisions else None
+        prob1 = torch.empty(g.n_edges, dtype=torch.float32, device=dev) if fuse_decisions else None
+        with torch.cuda.device(dev):
+            ph = CudaPhases(g, W, x.contiguous().float(), local_edge_attr.contiguous().float(), L, n_cls, int(tot.item()),
+                            logits, pred, prob1, USE_TENSOR_CORES)
+            try:
+                sharded_forward(ph, comm, L, n_cls, blocks)
+                h_local = ph.h_full()[n0:n1].clone()
+            finally:
+                ph.close()
+        return {'classified_edges': [logits[i] for i in range(n_out)]}, h_local, pred, prob1

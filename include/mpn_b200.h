@@ -44,6 +44,8 @@ enum {
 
 int mpn_abi_version(void);
 const char* mpn_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (monotonic) */
+uint64_t mpn_kernel_launches(void);
 /* 0 if device `dev` exists and is sm_100; error otherwise.  Never falls back to CPU. */
 int mpn_check_device(int dev);
 

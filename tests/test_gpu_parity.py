@@ -66,7 +66,7 @@ def test_gemm_simt_matches_fp64(m, shape):
     m._lib.check(m._lib.lib().mpn_gemm_nt(Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), Cd.data_ptr(), M, N, K, 0,
                                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
     err = (Cd.cpu().double() - ref).abs().max().item()
-    assert err <= 2e-6 * K ** 0.5 * 4, err            # fp32 accumulation bound (values ~N(0,1))
+    assert err <= 5e-7 * K, err                        # fp32 accumulation: ~eps*K typical, max over M*N entries (values ~N(0,1))
 
 
 # ---------------------------------------------------------------------------------------------- edge features
