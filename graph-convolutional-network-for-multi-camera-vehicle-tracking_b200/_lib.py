@@ -119,5 +119,12 @@ def check(code):
         raise MpnError(code, msg)
 
 
+_DEVICE_OK = set()
+
+
 def require_device(index: int):
-    check(lib().mpn_check_device(int(index)))
+    """Raises unless CUDA device `index` is an sm_100 part.  Cached: cudaGetDeviceProperties costs milliseconds."""
+    index = int(index)
+    if index not in _DEVICE_OK:
+        check(lib().mpn_check_device(index))
+        _DEVICE_OK.add(index)

@@ -1,12 +1,357 @@
-// tcgen05 3xTF32 GEMM (placeholder until the TMA/TMEM kernel lands): reports "unsupported" so callers use the SIMT kernel.
+// tcgen05 3xTF32 "NT" GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]),  fp32 in / fp32 out.
+//
+// fp32 accuracy on the tensor cores: every operand is pre-split into two TF32-representable planes
+//   x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi)
+// and each k-slice issues three MMAs:  main += hi*hi ;  corr += lo*hi + hi*lo   (the dropped lo*lo term is ~2^-22
+// relative).  The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
+// accumulation steps and with |accumulator| (measured: mean error toward zero, linear in K).  Keeping the small
+// correction products in their own TMEM accumulator, and (BN=128) alternating two main accumulators over the k-slices,
+// cuts that bias 3x / 6x; the epilogue sums the accumulators in fp32 round-to-nearest.  Used for the Gram matrix of the edge features
+// (inference.py:453-456) and the node-encoder Linear layers (models/mpn.py:117, models/mlp.py:14).
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the four operand tiles (A_hi, A_lo, B_hi, B_lo), SWIZZLE_128B,
+//               into a STAGES-deep shared-memory ring guarded by full/empty mbarriers
+//   warp 1      TMEM allocation + MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8),
+//               tcgen05.commit releases ring slots and finally signals the accumulator
+//   warps 2..5  epilogue: tcgen05.ld 32x32b of the fp32 accumulator (one TMEM lane = one output row per thread),
+//               bias add, vectorised global stores with edge masking
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace mpn {
-size_t gemm_tc_workspace_bytes(int, int, int) { return 0; }
-bool gemm_tc_supported(int, int, int) { return false; }
-int gemm_nt_tc(const float*, const float*, const float*, float*, int, int, int, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return MPN_ERR_INVALID;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                    // 32 fp32 = 128 bytes = one SWIZZLE_128B row
+constexpr int TC_UMMA_K = 8;                 // kind::tf32: 32 bytes of K per instruction
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Spin on the barrier phase; a protocol bug must surface as a trap (launch error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(bar, parity)) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) __trap();           // 4 s
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte atoms, 1024 bytes apart)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;           // one plane of A per stage (16 KB)
+  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int N_MAIN = (BN == 256) ? 1 : 2;          // main accumulators (alternating k-slices)
+  static constexpr int TMEM_COLS = 512;                        // main(s) + correction accumulator, power of two
+  static constexpr int CORR_COL = N_MAIN * BN;
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                      const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        const int k0 = kb * TC_BK;
+        tma_load_2d(&map_a_hi, &full_bar[stage], st, k0, m0);
+        tma_load_2d(&map_a_lo, &full_bar[stage], st + Cfg::A_BYTES, k0, m0);
+        tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * Cfg::A_BYTES, k0, n0);
+        tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, n0);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t a_hi = make_smem_desc(sbase), a_lo = make_smem_desc(sbase + Cfg::A_BYTES);
+        const uint64_t b_hi = make_smem_desc(sbase + 2 * Cfg::A_BYTES), b_lo = make_smem_desc(sbase + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
+          const uint64_t adv = (uint64_t)((kk * TC_UMMA_K * 4) >> 4);        // advance the start address inside the 128-byte row
+          const int slice = kb * (TC_BK / TC_UMMA_K) + kk;
+          const int which = (Cfg::N_MAIN == 2) ? (slice & 1) : 0;
+          umma_tf32(tmem_base + which * BN, a_hi + adv, b_hi + adv, Cfg::IDESC, slice >= Cfg::N_MAIN);
+          umma_tf32(tmem_base + Cfg::CORR_COL, a_lo + adv, b_hi + adv, Cfg::IDESC, slice != 0);
+          umma_tf32(tmem_base + Cfg::CORR_COL, a_hi + adv, b_lo + adv, Cfg::IDESC, 1);
+        }
+        umma_commit(&empty_bar[stage]);                                         // slot free once these MMAs retire
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);                                               // accumulator complete
+    }
+  } else {
+    // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool vec_ok = ((N & 3) == 0) && ((((uintptr_t)C) & 15) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;                                                  // warp-uniform
+      float v[32], w[32];
+      const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      tmem_ld32(tq, v);
+      if (Cfg::N_MAIN == 2) {
+        tmem_ld32(tq + BN, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+      }
+      tmem_ld32(tq + Cfg::CORR_COL, w);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += w[j];
+      if (row < M) {
+        float* out = C + (size_t)row * N + n0 + c0;
+        if (vec_ok && n0 + c0 + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (bias) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            *reinterpret_cast<float4*>(out + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < N) out[j] = v[j] + (bias ? bias[n0 + c0 + j] : 0.f);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+  }
+}
+
+// x -> (hi, lo) TF32 planes
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, long long n4, float4* __restrict__ hi,
+                                                         float4* __restrict__ lo) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = x[i];
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[j]));
+      h[j] = __uint_as_float(hb);
+      const float r = in[j] - h[j];
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(r));
+      l[j] = __uint_as_float(lb);
+    }
+    hi[i] = make_float4(h[0], h[1], h[2], h[3]);
+    lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  MPN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MPN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%d K=%d)", (int)r, rows, K);
+  return MPN_OK;
+}
+
+bool gemm_tc_supported(int M, int N, int K) { return M >= 1 && N >= 64 && K >= 64 && (K % 4) == 0; }
+
+size_t gemm_tc_workspace_bytes(int M, int N, int K) {
+  if (!gemm_tc_supported(M, N, K)) return 0;
+  const size_t plane_a = (((size_t)M * K * sizeof(float)) + 255) & ~(size_t)255;
+  const size_t plane_b = (((size_t)N * K * sizeof(float)) + 255) & ~(size_t)255;
+  return 2 * plane_a + 2 * plane_b + 1024;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const float* bias,
+                     float* C, int M, int N, int K, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid(div_up(N, BN), div_up(M, TC_BM));
+  gemm_nt_3xtf32_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ah, al, bh, bl, bias, C, M, N, K);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
+               cudaStream_t st) {
+  MPN_REQUIRE(gemm_tc_supported(M, N, K), "tcgen05 GEMM: unsupported shape %d x %d x %d", M, N, K);
+  MPN_REQUIRE(ws && ws_bytes >= gemm_tc_workspace_bytes(M, N, K), "tcgen05 GEMM: workspace too small");
+  MPN_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "tcgen05 GEMM: operands must be 16-byte aligned");
+  char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  const size_t plane_b = (((size_t)N * K * sizeof(float)) + 255) & ~(size_t)255;
+  const size_t plane_a = (((size_t)M * K * sizeof(float)) + 255) & ~(size_t)255;
+  float* b_hi = (float*)w;
+  float* b_lo = (float*)(w + plane_b);
+  float *a_hi, *a_lo;
+  const int split_grid = kNumSMs * 8;
+  split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)B, (long long)N * K / 4, (float4*)b_hi, (float4*)b_lo);
+  MPN_LAUNCH_OK();
+  if (A >= B && A + (size_t)M * K <= B + (size_t)N * K) {      // A is a row block of B (Gram matrix): share the planes
+    a_hi = b_hi + (A - B);
+    a_lo = b_lo + (A - B);
+  } else {
+    a_hi = (float*)(w + 2 * plane_b);
+    a_lo = (float*)(w + 2 * plane_b + plane_a);
+    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, (float4*)a_hi, (float4*)a_lo);
+    MPN_LAUNCH_OK();
+  }
+  CUtensorMap ah, al, bh, bl;
+  static int forced_bn = -1;                         // diagnostics: MPN_TC_BN=128|256 overrides the tile width
+  if (forced_bn < 0) {
+    const char* e = getenv("MPN_TC_BN");
+    forced_bn = e ? atoi(e) : 0;
+  }
+  // 128-wide tiles measured both faster (3 stages, more tiles per wave) and more accurate (three accumulators) than 256
+  const int BN = (forced_bn == 128 || forced_bn == 256) ? forced_bn : 128;
+  MPN_TRY(make_map(&ah, a_hi, M, K, TC_BM));
+  MPN_TRY(make_map(&al, a_lo, M, K, TC_BM));
+  MPN_TRY(make_map(&bh, b_hi, N, K, BN));
+  MPN_TRY(make_map(&bl, b_lo, N, K, BN));
+  if (BN == 256) return launch_tc<256>(ah, al, bh, bl, bias, C, M, N, K, st);
+  return launch_tc<128>(ah, al, bh, bl, bias, C, M, N, K, st);
+}
+
 }  // namespace mpn

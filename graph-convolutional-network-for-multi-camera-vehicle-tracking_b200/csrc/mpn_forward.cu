@@ -394,21 +394,30 @@ __global__ void decide_kernel(const float2* __restrict__ logits, long long E, ui
 // ------------------------------------------------------------------------------------------------
 // finalize: fixed-order reduction of block partials -> sums; sums -> folded constants
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) finalize_kernel(int stage, const double* __restrict__ partials, int n_partials,
+constexpr int FIN_THREADS = 1024;
+__global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(int stage, const double* __restrict__ partials, int n_partials,
                                                        const double* __restrict__ partials2, int n_partials2,
                                                        double* __restrict__ sums, int do_reduce, int do_consts,
                                                        float* __restrict__ consts, const float* __restrict__ small,
                                                        double n_total) {
   const int k = threadIdx.x;
-  if (do_reduce && k < SUMS) {
-    double s = 0.0;
-    if (stage == MPN_STAGE_NODE) {
-      if (k < 64) for (int p = 0; p < n_partials2; ++p) s += partials2[(size_t)p * SUMS + k];
-      else if (k < 74) for (int p = 0; p < n_partials; ++p) s += partials[(size_t)p * SUMS + k];
-    } else if (k < 8) {
-      for (int p = 0; p < n_partials; ++p) s += partials[(size_t)p * SUMS + k];
+  if (do_reduce) {
+    // one warp per column: lanes stride over the partial rows in a fixed pattern, then a fixed shuffle tree
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int col = warp; col < SUMS; col += FIN_THREADS / 32) {
+      const double* src = partials;
+      int n = n_partials;
+      bool live = col < 8;
+      if (stage == MPN_STAGE_NODE) {
+        live = col < 74;
+        if (col < 64) { src = partials2; n = n_partials2; }
+      }
+      double s = 0.0;
+      if (live)
+        for (int p = lane; p < n; p += 32) s += src[(size_t)p * SUMS + col];
+      s = warp_sum(s);
+      if (lane == 0) sums[col] = s;
     }
-    sums[k] = s;
   }
   __syncthreads();
   if (!do_consts) return;
@@ -788,7 +797,7 @@ int mpn_plan_finalize(mpn_fwd_plan* p, int32_t step, int32_t stage, void* stream
   MPN_REQUIRE(p, "finalize: NULL plan");
   (void)step;
   // sums already reduced (and possibly all-reduced by the host): constants only
-  finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(stage, nullptr, 0, nullptr, 0, p->sums, 0, 1, p->consts, p->w.small,
+  finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(stage, nullptr, 0, nullptr, 0, p->sums, 0, 1, p->consts, p->w.small,
                                                        (double)p->total_edges);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -797,7 +806,7 @@ int mpn_plan_finalize(mpn_fwd_plan* p, int32_t step, int32_t stage, void* stream
 // reduce this rank's block partials into the sums vector (phase API: host all-reduces it afterwards)
 int mpn_plan_reduce(mpn_fwd_plan* p, int32_t stage, int with_consts, void* stream) {
   MPN_REQUIRE(p, "reduce: NULL plan");
-  finalize_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(stage, p->partials, SWEEP_GRID, p->partials2, NM_GRID, p->sums, 1,
+  finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(stage, p->partials, SWEEP_GRID, p->partials2, NM_GRID, p->sums, 1,
                                                        with_consts, p->consts, p->w.small, (double)p->total_edges);
   MPN_LAUNCH_OK();
   return MPN_OK;

@@ -69,6 +69,41 @@ def test_gemm_simt_matches_fp64(m, shape):
     assert err <= 5e-7 * K, err                        # fp32 accumulation: ~eps*K typical, max over M*N entries (values ~N(0,1))
 
 
+@pytest.mark.parametrize("shape", [(300, 1024, 2048), (257, 130, 96), (128, 256, 64), (1000, 512, 1024), (4096, 128, 512),
+                                   (77, 64, 2048), (1024, 1024, 2048)])
+def test_gemm_tcgen05_3xtf32_matches_fp64(m, shape):
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A, B, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    ref = (A.double() @ B.double().t() + bias.double())
+    Ad, Bd, bd = A.to(dev()), B.to(dev()), bias.to(dev())
+    Cd = torch.full((M, N), float("nan"), device=dev())
+    L = m._lib.lib()
+    ws = torch.empty(L.mpn_gemm_nt_workspace_bytes(M, N, K, 1), dtype=torch.uint8, device=dev())
+    m._lib.check(L.mpn_gemm_nt(Ad.data_ptr(), Bd.data_ptr(), bd.data_ptr(), Cd.data_ptr(), M, N, K, 1,
+                               ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    err = (Cd.cpu().double() - ref).abs().max().item()
+    # 3xTF32 products are fp32-accurate; the tensor core's truncating accumulate adds a bias ~3e-7*K (measured)
+    assert err <= 6e-7 * K, err
+
+
+def test_gemm_tcgen05_gram_aliasing(m):
+    """A given as a row block of B (the Gram-matrix call of the edge features) shares the split planes."""
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(640, 256, generator=g)
+    Xd = X.to(dev())
+    r0, r1 = 128, 448
+    Cd = torch.empty(r1 - r0, 640, device=dev())
+    L = m._lib.lib()
+    ws = torch.empty(L.mpn_gemm_nt_workspace_bytes(r1 - r0, 640, 256, 1), dtype=torch.uint8, device=dev())
+    m._lib.check(L.mpn_gemm_nt(Xd[r0:].data_ptr(), Xd.data_ptr(), None, Cd.data_ptr(), r1 - r0, 640, 256, 1,
+                               ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    ref = X[r0:r1].double() @ X.double().t()
+    # coherent sums (|x|^2 on the aliased diagonal) see the largest truncation bias: ~1e-6 relative to |a||b| = K
+    assert (Cd.cpu().double() - ref).abs().max().item() <= 2e-6 * 256
+
+
 # ---------------------------------------------------------------------------------------------- edge features
 @pytest.mark.parametrize("path", MPN_FILES, ids=ids(MPN_FILES))
 def test_edge_features_match_reference_golden(m, path):
