@@ -66,33 +66,71 @@ class TorchComm:
             self.dist.all_reduce(full, op=self.dist.ReduceOp.SUM, group=self.group)
 
 
-def sharded_forward(phases, comm, num_enc_steps: int, num_class_steps: int, blocks):
-    """The phase/collective schedule of one forward.  Returns the number of classified steps."""
+def _combine_sums(shards, comm):
+    """Global BatchNorm moment sums: add the shards of this process, then all-reduce across processes."""
+    if len(shards) == 1:
+        comm.all_reduce_sum(shards[0].sums())
+        return
+    total = torch.stack([p.sums() for p in shards]).sum(dim=0)
+    comm.all_reduce_sum(total)
+    for p in shards:
+        p.sums().copy_(total)
+
+
+def _exchange_h(shards, comm, blocks):
+    """Every shard needs h of ALL nodes for the next step's Pd table: the one all-gather per step."""
+    if len(shards) == 1:
+        comm.all_gather_rows(shards[0].h_full(), blocks)
+        return
+    assert comm.world == 1, "several local shards per process are only supported in a single process"
+    for s, src in enumerate(shards):
+        n0, n1 = blocks[s]
+        for t, dst in enumerate(shards):
+            if t != s:
+                dst.h_full()[n0:n1].copy_(src.h_full()[n0:n1])
+
+
+def sharded_forward(shards, comm, num_enc_steps: int, num_class_steps: int, blocks):
+    """The phase/collective schedule of one forward over row-block shards.
+
+    ``shards``: one phases object per row block held by this process (normally one; several emulate a multi-GPU run
+    inside one process, which is how the 1-GPU and CPU tests cover the N>1 path).  Returns the number of classified steps.
+    """
+    if not isinstance(shards, (list, tuple)):
+        shards = [shards]
     L, n_cls = int(num_enc_steps), int(num_class_steps)
-    phases.node_encoder()
+    for p in shards:
+        p.node_encoder()
     for stage in (_lib.STAGE_ENC0, _lib.STAGE_ENC1):
-        phases.sweep(0, stage)
-        phases.reduce(stage)
-        comm.all_reduce_sum(phases.sums())
-        phases.finalize(0, stage)
+        for p in shards:
+            p.sweep(0, stage)
+            p.reduce(stage)
+        _combine_sums(shards, comm)
+        for p in shards:
+            p.finalize(0, stage)
     k = 0
     if L == 0:
-        phases.sweep(0, _lib.STAGE_APPLY, out_index=0, last=True)
+        for p in shards:
+            p.sweep(0, _lib.STAGE_APPLY, out_index=0, last=True)
         return 1
     first_class_step = L - n_cls + 1
     for step in range(1, L + 1):
         if step > 1:
-            comm.all_gather_rows(phases.h_full(), blocks)
-        phases.node_tables(step)
+            _exchange_h(shards, comm, blocks)
+        for p in shards:
+            p.node_tables(step)
         for stage in (_lib.STAGE_EDGE, _lib.STAGE_NODE):
-            phases.sweep(step, stage)
-            phases.reduce(stage)
-            comm.all_reduce_sum(phases.sums())
-            phases.finalize(step, stage)
+            for p in shards:
+                p.sweep(step, stage)
+                p.reduce(stage)
+            _combine_sums(shards, comm)
+            for p in shards:
+                p.finalize(step, stage)
         cls = step >= first_class_step
-        phases.sweep(step, _lib.STAGE_APPLY, out_index=k if cls else None, last=(step == L))
+        for p in shards:
+            p.sweep(step, _lib.STAGE_APPLY, out_index=k if cls else None, last=(step == L))
+            p.node_finalize(step)
         k += int(cls)
-        phases.node_finalize(step)
     return k
 
 

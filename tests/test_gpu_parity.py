@@ -184,6 +184,53 @@ def test_forward_multi_step_unsorted_edges(m):
     assert (h.cpu().double() - href).abs().max().item() <= 1e-4 * max(1.0, href.abs().max().item())
 
 
+class _NoComm:
+    world, rank = 1, 0
+
+    def all_reduce_sum(self, t):
+        pass
+
+    def all_gather_rows(self, full, blocks):
+        pass
+
+
+@pytest.mark.parametrize("L,n_cls,world", [(1, 1, 2), (3, 2, 3), (0, 1, 2)])
+def test_sharded_cuda_shards_in_one_process(m, L, n_cls, world):
+    """The N>1 path on one GPU: G row-block shards run phase by phase in one process (no concurrent waiting kernels)."""
+    params = mo.shipped_model_params(L, n_cls, 64, (48, 40))
+    x, ei, cam, _ = mo.synth_graph(90, 3, 41, D=64, planted=True)
+    sd = mo.init_weights(params, "resnet101", 13)
+    ea = mo.edge_features(x, ei)
+    ref, href = mo.mpn_forward(sd, params, "resnet101", x, ei, ea, dtype=torch.float64)
+    outs, h, net = run_forward(m, params, sd, x, ei, ea)
+    N, E = x.shape[0], ei.shape[1]
+    rowptr = torch.searchsorted(ei[0].contiguous(), torch.arange(N + 1))
+    blocks = m.partition_rows(rowptr, world)
+    n_out = 1 if L == 0 else n_cls
+    xd, W = x.to(dev()), net._weights(dev())
+    shards, spans, keep = [], [], []
+    for i, (n0, n1) in enumerate(blocks):
+        lo, hi = m.shard_edges(ei, n0, n1)
+        g = m.TrackletGraph(ei[:, lo:hi].to(dev()), N, row_offset=n0, n_rows=n1 - n0)
+        logits = torch.empty(max(n_out, 1), hi - lo, 2, device=dev())
+        ph = m.CudaPhases(g, W, xd, ea[lo:hi].to(dev()).contiguous(), L, n_cls, E, logits, None, None, False, ws_kind="shard%d" % i)
+        shards.append(ph); spans.append((lo, hi)); keep.append((g, logits))
+    m.sharded_forward(shards, _NoComm(), L, n_cls, blocks)
+    torch.cuda.synchronize()
+    for i in range(n_out):
+        got = torch.cat([k[1][i] for k in keep]).cpu()
+        assert (got.double() - ref[i]).abs().max().item() <= 1e-4 * ref[i].abs().max().item()
+        assert (got - outs[i].cpu()).abs().max().item() <= 2e-6            # same kernels, only the reduction order differs
+    hs = torch.cat([p.h_full()[b[0]:b[1]] for p, b in zip(shards, blocks)]).cpu()
+    assert (hs.double() - href).abs().max().item() <= 1e-4 * max(1.0, href.abs().max().item())
+    # sharded edge features: each shard computes its row block of the Gram matrix
+    for (lo, hi), (g, _) in zip(spans, keep):
+        ef = m.edge_features(xd, None, graph=g, use_tensor_cores=False).cpu()
+        assert np.allclose(ef.numpy(), ea[lo:hi].numpy(), rtol=3e-6, atol=3e-6)
+    for p in shards:
+        p.close()
+
+
 def test_forward_rejects_cpu_and_training(m):
     params = mo.shipped_model_params(1, 1, 64, (48,))
     net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")

@@ -1,0 +1,93 @@
+"""N>1 path on CPU: row-block partitioning + the collective schedule, with gloo (world_size 2) and in-process shards."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import gcn_mtmc_b200 as m
+from oracle import mpn_oracle as mo
+from tests.fake_phases import FakePhases
+
+
+def _case(L, n_cls, N=36, C=3, D=48):
+    params = mo.shipped_model_params(L, n_cls, D, (40,))
+    x, ei, cam, _ = mo.synth_graph(N, C, 5, D=D, planted=True)
+    sd = mo.init_weights(params, "resnet101", 11)
+    ea = mo.edge_features(x, ei)
+    ref, href = mo.mpn_forward(sd, params, "resnet101", x, ei, ea, dtype=torch.float64)
+    return params, sd, x, ei, ea, ref, href
+
+
+def _blocks(ei, N, world):
+    rowptr = torch.searchsorted(ei[0].contiguous(), torch.arange(N + 1))
+    return m.partition_rows(rowptr, world)
+
+
+class NoComm:
+    world, rank = 1, 0
+
+    def all_reduce_sum(self, t):
+        pass
+
+    def all_gather_rows(self, full, blocks):
+        pass
+
+
+@pytest.mark.parametrize("L,n_cls,world", [(1, 1, 1), (1, 1, 3), (3, 2, 2), (4, 4, 4), (0, 1, 2)])
+def test_inprocess_shards_match_oracle(L, n_cls, world):
+    params, sd, x, ei, ea, ref, href = _case(L, n_cls)
+    N = x.shape[0]
+    blocks = _blocks(ei, N, world)
+    assert blocks[0][0] == 0 and blocks[-1][1] == N and all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+    n_out = 1 if L == 0 else n_cls
+    shards, spans = [], []
+    for (n0, n1) in blocks:
+        lo, hi = m.shard_edges(ei, n0, n1)
+        spans.append((lo, hi))
+        shards.append(FakePhases(sd, params, x, ei[:, lo:hi], ea[lo:hi], n0, n1, ei.shape[1], n_out))
+    assert spans[0][0] == 0 and spans[-1][1] == ei.shape[1]
+    k = m.sharded_forward(shards, NoComm(), L, n_cls, blocks)
+    assert k == n_out
+    for i in range(n_out):
+        got = torch.cat([s.logits[i] for s in shards])
+        assert (got - ref[i]).abs().max().item() <= 1e-9
+    h = torch.cat([s.h_full()[b[0]:b[1]] for s, b in zip(shards, blocks)])
+    assert (h - href).abs().max().item() <= 1e-9
+
+
+def _worker(rank, world, port, L, n_cls, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        params, sd, x, ei, ea, ref, href = _case(L, n_cls)
+        blocks = _blocks(ei, x.shape[0], world)
+        n0, n1 = blocks[rank]
+        lo, hi = m.shard_edges(ei, n0, n1)
+        tot = torch.tensor([hi - lo], dtype=torch.float64)
+        dist.all_reduce(tot)
+        assert int(tot.item()) == ei.shape[1]
+        ph = FakePhases(sd, params, x, ei[:, lo:hi], ea[lo:hi], n0, n1, int(tot.item()), n_cls)
+        m.sharded_forward(ph, m.sharded.TorchComm(), L, n_cls, blocks)
+        err = max((ph.logits[i] - ref[i][lo:hi]).abs().max().item() for i in range(n_cls))
+        herr = (ph.h_full()[n0:n1] - href[n0:n1]).abs().max().item()
+        q.put((rank, err, herr))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("L,n_cls", [(1, 1), (3, 2)])
+def test_gloo_world2_matches_oracle(L, n_cls):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, L, n_cls, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=5) for _ in range(2))
+    assert [r[0] for r in res] == [0, 1]
+    assert all(r[1] <= 1e-9 and r[2] <= 1e-9 for r in res), res
