@@ -16,23 +16,33 @@ constexpr float PAIRWISE_EPS = 1e-6f;
 constexpr float COSINE_EPS = 1e-8f;
 constexpr float REFINE_FRACTION = 0.25f;
 
-// column means of x [n, D] (fp64 accumulation): grid over 32-column tiles
-__global__ void __launch_bounds__(256) col_mean_kernel(const float* __restrict__ x, int n, int D, float* __restrict__ mu) {
+// column means of x [n, D] (fp64 accumulation): grid (32-column tiles, row splits) -> partials -> fixed-order finalize
+constexpr int CM_SPLITS = 32;
+__global__ void __launch_bounds__(256) col_mean_partial_kernel(const float* __restrict__ x, int n, int D, int rows_per_split,
+                                                               double* __restrict__ part /*[CM_SPLITS][D]*/) {
   __shared__ double ssum[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(r0 + rows_per_split, n);
   double s = 0.0;
   if (col < D)
-    for (int r = ry; r < n; r += 8) s += x[(size_t)r * D + col];
+    for (int r = r0 + ry; r < r1; r += 8) s += x[(size_t)r * D + col];
   ssum[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && col < D) {
     for (int i = 1; i < 8; ++i) s += ssum[i][cx];
-    mu[col] = (float)(s / n);
+    part[(size_t)blockIdx.y * D + col] = s;
   }
 }
+__global__ void col_mean_finalize_kernel(const double* __restrict__ part, int n, int D, float* __restrict__ mu) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= D) return;
+  double s = 0.0;
+  for (int i = 0; i < CM_SPLITS; ++i) s += part[(size_t)i * D + col];
+  mu[col] = (float)(s / n);
+}
 
-// xc = x - mu; per-row fp64 statistics of the centred row: st[r] = {|a'|^2, sum a', mu.a', |a|^2}
+// xc = x - mu; per-row fp64 statistics of the centred row: st[r] = {|a'|^2, sum a', mu.a' + |mu|^2/2, |a|}
 __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu, int n, int D,
                                                           float* __restrict__ xc, double* __restrict__ st) {
   const int lane = threadIdx.x & 31;
@@ -56,7 +66,7 @@ __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restric
       st[4 * (size_t)r + 0] = sq;
       st[4 * (size_t)r + 1] = sx;
       st[4 * (size_t)r + 2] = md + 0.5 * mm;          // a.b = g' + (mu.a' + |mu|^2/2) + (mu.b' + |mu|^2/2)
-      st[4 * (size_t)r + 3] = sq + 2.0 * md + mm;     // |a|^2
+      st[4 * (size_t)r + 3] = sqrt(fmax(sq + 2.0 * md + mm, 0.0));     // |a|
     }
   }
 }
@@ -89,8 +99,8 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
       }
       if (d2 < 0.0) d2 = 0.0;
       const double ab = gij + ma + mb;
-      const double denom = fmax(sqrt(na) * sqrt(nb), (double)COSINE_EPS);
-      edge_attr[e] = make_float2((float)sqrt(d2), (float)(1.0 - ab / denom));
+      const float denom = fmaxf((float)(na * nb), COSINE_EPS);
+      edge_attr[e] = make_float2(sqrtf((float)d2), 1.0f - (float)ab / denom);
     }
   }
 }
@@ -133,6 +143,7 @@ __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_grap
 struct EfLayout {
   double* st;
   float *mu, *xc;
+  double* mu_part;
   float* G;
   int *refine_list, *refine_count;
   void* gemm_ws;
@@ -146,6 +157,7 @@ static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) 
   Arena a(ws, ws_bytes);
   L.st = a.take<double>((size_t)g->n_cols * 4);
   L.mu = a.take<float>(D);
+  L.mu_part = a.take<double>((size_t)CM_SPLITS * D);
   L.xc = a.take<float>((size_t)g->n_cols * D);
   const size_t budget = (size_t)2 << 30;
   size_t rows = budget / ((size_t)g->n_cols * sizeof(float));
@@ -184,7 +196,9 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
     return MPN_ERR_WORKSPACE;
   }
   if (g->n_edges == 0) return MPN_OK;
-  col_mean_kernel<<<div_up(D, 32), 256, 0, st>>>(x, g->n_cols, D, L.mu);
+  col_mean_partial_kernel<<<dim3(div_up(D, 32), CM_SPLITS), 256, 0, st>>>(x, g->n_cols, D, div_up(g->n_cols, CM_SPLITS), L.mu_part);
+  MPN_LAUNCH_OK();
+  col_mean_finalize_kernel<<<div_up(D, 128), 128, 0, st>>>(L.mu_part, g->n_cols, D, L.mu);
   MPN_LAUNCH_OK();
   center_rows_kernel<<<min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st>>>(x, L.mu, g->n_cols, D, L.xc, L.st);
   MPN_LAUNCH_OK();

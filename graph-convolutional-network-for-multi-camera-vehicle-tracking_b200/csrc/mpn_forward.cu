@@ -136,15 +136,50 @@ __global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_kernel(const float2
 }
 
 // ------------------------------------------------------------------------------------------------
+// Edge sweeps.  One warp per task (<= chunk consecutive edges of one row), lane = edge.  Every lane handles U edges per
+// iteration and issues all of their loads (col, edge_attr | y) before the dependent Pd[col] gathers and the math: the
+// sweeps are latency-bound on the col -> Pd[col] chain otherwise (ncu: long_scoreboard 14-17 warps per issue).
+// Out-of-range lanes read a clamped (valid) edge and are masked out of every sum / store.
+// ------------------------------------------------------------------------------------------------
+template <int U>
+struct EdgeLoad {
+  int e[U];
+  bool ok[U];
+  float2 ea[U];
+  float4 pd[U];
+  float4 y[U];
+};
+
+// YSRC 0: (edge_attr, col, Pd) -> y recomputed;  YSRC 1: y read from ybuf.  NEED_PD: SA with SRC 1 needs Pd AND ybuf.
+template <int U, bool LOAD_EA, bool LOAD_PD, bool LOAD_Y>
+__device__ __forceinline__ void load_edges(EdgeLoad<U>& L, const mpn_graph& g, int base, int end, int lane,
+                                           const float2* __restrict__ edge_attr, const float4* __restrict__ Pd,
+                                           const float4* __restrict__ ybuf) {
+  int c[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int e = base + 32 * j + lane;
+    L.ok[j] = e < end;
+    L.e[j] = L.ok[j] ? e : end - 1;
+    if (LOAD_PD) c[j] = ldg_stream_i32(g.col + L.e[j]);
+    if (LOAD_EA) L.ea[j] = ldg_stream2(edge_attr + L.e[j]);
+    if (LOAD_Y) L.y[j] = ybuf[L.e[j]];
+  }
+  if (LOAD_PD) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) L.pd[j] = __ldg(Pd + c[j]);
+  }
+}
+
 // SA: moments of the edge-update pre-activation y (and optionally materialise y)
 //   SRC 0: e_in = encoder(edge_attr[e])            (step 1)
 //   SRC 1: e_in = relu(BN3_prev(ybuf[e]))          (step >= 2; ybuf updated in place)
-// ------------------------------------------------------------------------------------------------
 template <int SRC, bool WRITE_Y>
-__global__ void __launch_bounds__(SWEEP_THREADS) edge_moments_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
+__global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                                      const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                                      float4* __restrict__ ybuf, const float* __restrict__ consts,
                                                                      double* __restrict__ partials) {
+  constexpr int U = 4;
   __shared__ EdgeConsts sc;
   __shared__ double red[(SWEEP_THREADS / 32) * 8];
   load_consts(sc, consts);
@@ -156,53 +191,52 @@ __global__ void __launch_bounds__(SWEEP_THREADS) edge_moments_kernel(const mpn_g
   for (int t = gwarp; t < n_tasks; t += nwarps) {
     const TaskRange tr = task_range(g, t);
     const float4 ps = Ps[tr.row];
-    for (int e = tr.beg + lane; e < tr.end; e += 32) {
-      const int c = ldg_stream_i32(g.col + e);
-      const float4 pd = __ldg(Pd + c);
-      float ein[4], y[4];
-      if (SRC == 0) {
-        enc_full(sc, ldg_stream2(edge_attr + e), ein);
-      } else {
-        const float4 yp = ybuf[e];
-        const float ypv[4] = {yp.x, yp.y, yp.z, yp.w};
-        bn3_relu(sc, ypv, ein);
-      }
-      edge_pre(sc, ps, pd, ein, y);
-      if (WRITE_Y) ybuf[e] = make_float4(y[0], y[1], y[2], y[3]);
+    for (int base = tr.beg; base < tr.end; base += 32 * U) {
+      EdgeLoad<U> L;
+      load_edges<U, SRC == 0, true, SRC == 1>(L, g, base, tr.end, lane, edge_attr, Pd, ybuf);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const double d = y[j]; acc[j] += d; acc[4 + j] += d * d; }
+      for (int j = 0; j < U; ++j) {
+        float ein[4], y[4];
+        if (SRC == 0) {
+          enc_full(sc, L.ea[j], ein);
+        } else {
+          const float ypv[4] = {L.y[j].x, L.y[j].y, L.y[j].z, L.y[j].w};
+          bn3_relu(sc, ypv, ein);
+        }
+        edge_pre(sc, ps, L.pd[j], ein, y);
+        if (L.ok[j]) {
+          if (WRITE_Y) ybuf[L.e[j]] = make_float4(y[0], y[1], y[2], y[3]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const double d = y[k]; acc[k] += d; acc[4 + k] += d * d; }
+        }
+      }
     }
   }
   block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
 }
 
-// ------------------------------------------------------------------------------------------------
-// SB: e' = relu(BN3(y)); per-task S1 = sum e' (for the closed-form node-BN moments), global T2 = sum e' e'^T
-//   YSRC 0: recompute y from (edge_attr, col, Ps, Pd);  YSRC 1: read y from ybuf
-// ------------------------------------------------------------------------------------------------
+// e' = relu(BN3(y)) for one loaded edge
 template <int YSRC>
-__device__ __forceinline__ void load_eprime(const EdgeConsts& sc, const mpn_graph& g, int e, const float4 ps,
-                                            const float2* __restrict__ edge_attr, const float4* __restrict__ Pd,
-                                            const float4* __restrict__ ybuf, float (&ep)[4]) {
+__device__ __forceinline__ void eprime_of(const EdgeConsts& sc, const float4 ps, const float2 ea, const float4 pd, const float4 yv,
+                                          float (&ep)[4]) {
   float y[4];
   if (YSRC == 0) {
-    const int c = ldg_stream_i32(g.col + e);
-    const float4 pd = __ldg(Pd + c);
     float ein[4];
-    enc_full(sc, ldg_stream2(edge_attr + e), ein);
+    enc_full(sc, ea, ein);
     edge_pre(sc, ps, pd, ein, y);
   } else {
-    const float4 yy = ldg_stream4(ybuf + e);
-    y[0] = yy.x; y[1] = yy.y; y[2] = yy.z; y[3] = yy.w;
+    y[0] = yv.x; y[1] = yv.y; y[2] = yv.z; y[3] = yv.w;
   }
   bn3_relu(sc, y, ep);
 }
 
+// SB: per-task S1 = sum e' (for the closed-form node-BN moments), global T2 = sum e' e'^T
 template <int YSRC>
-__global__ void __launch_bounds__(SWEEP_THREADS) node_moments_sweep_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
+__global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                                            const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                                            const float4* __restrict__ ybuf, const float* __restrict__ consts,
                                                                            float4* __restrict__ s1_task, double* __restrict__ partials) {
+  constexpr int U = 4;
   __shared__ EdgeConsts sc;
   __shared__ double red[(SWEEP_THREADS / 32) * 10];
   load_consts(sc, consts);
@@ -216,15 +250,21 @@ __global__ void __launch_bounds__(SWEEP_THREADS) node_moments_sweep_kernel(const
     const float4 ps = (YSRC == 0) ? Ps[tr.row] : make_float4(0.f, 0.f, 0.f, 0.f);
     float s1[4] = {0.f, 0.f, 0.f, 0.f};
     float q[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int e = tr.beg + lane; e < tr.end; e += 32) {
-      float ep[4];
-      load_eprime<YSRC>(sc, g, e, ps, edge_attr, Pd, ybuf, ep);
-      int idx = 0;
+    for (int base = tr.beg; base < tr.end; base += 32 * U) {
+      EdgeLoad<U> L;
+      load_edges<U, YSRC == 0, YSRC == 0, YSRC == 1>(L, g, base, tr.end, lane, edge_attr, Pd, ybuf);
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        s1[a] += ep[a];
+      for (int j = 0; j < U; ++j) {
+        float ep[4];
+        eprime_of<YSRC>(sc, ps, L.ea[j], L.pd[j], L.y[j], ep);
+        if (!L.ok[j]) { ep[0] = ep[1] = ep[2] = ep[3] = 0.f; }
+        int idx = 0;
 #pragma unroll
-        for (int b = a; b < 4; ++b) { q[idx] = fmaf(ep[a], ep[b], q[idx]); ++idx; }
+        for (int a = 0; a < 4; ++a) {
+          s1[a] += ep[a];
+#pragma unroll
+          for (int b = a; b < 4; ++b) { q[idx] = fmaf(ep[a], ep[b], q[idx]); ++idx; }
+        }
       }
     }
 #pragma unroll
@@ -277,11 +317,14 @@ __global__ void __launch_bounds__(NM_THREADS) node_moments_node_kernel(const mpn
 
 // ------------------------------------------------------------------------------------------------
 // SC: apply.  messages m = relu(BN4(A[row] + Wn·e')), per-task segment sums, logits, decisions.
-// Lane = edge; 32 fp32 accumulators per lane; a 31-shuffle transpose-reduce per task leaves channel c's
-// sum in lane c (deterministic: fixed shuffle tree, fixed task order in node_finalize).
+// Lane = edge, two edges per lane per iteration (the folded weights are read once from shared memory for both), the
+// loads of the NEXT iteration are issued before the math of the current one.  The 32-channel message is computed on
+// packed channel pairs with fma.rn.f32x2 / add.f32x2 (sm_100 packed fp32).  32 fp32 accumulators per lane; a 31-shuffle
+// transpose-reduce per task leaves channel c's sum in lane c (deterministic: fixed shuffle tree, fixed task order in
+// node_finalize).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float transpose_reduce32(float (&acc)[32], int lane) {
-  // after step with offset o the live values per lane halve; lane keeps the half selected by bit o of lane
+  // after the step with offset o the live values per lane halve; the lane keeps the half selected by bit o of its id
 #pragma unroll
   for (int o = 16, n = 16; o > 0; o >>= 1, n >>= 1) {
     const bool upper = (lane & o) != 0;
@@ -297,15 +340,65 @@ __device__ __forceinline__ float transpose_reduce32(float (&acc)[32], int lane) 
   return acc[0];
 }
 
+typedef unsigned long long f32x2;        // two packed fp32 in one 64-bit register
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 relu2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return pack2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+}
+
+template <bool CLASSIFY>
+__device__ __forceinline__ void classify_store(const EdgeConsts& sc, const float (&ep)[4], int e, float2* __restrict__ logits,
+                                               uint8_t* __restrict__ pred, float* __restrict__ prob1) {
+  if (!CLASSIFY) return;
+  float l0 = sc.v[FC_CLS_B + 0], l1 = sc.v[FC_CLS_B + 1];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    l0 = fmaf(sc.v[FC_CLS_W + k], ep[k], l0);
+    l1 = fmaf(sc.v[FC_CLS_W + 4 + k], ep[k], l1);
+  }
+  logits[e] = make_float2(l0, l1);
+  if (pred) pred[e] = (l1 > l0) ? 1 : 0;                  // argmax, tie -> class 0 (inference.py:479)
+  if (prob1) {
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+    prob1[e] = e1 / (e0 + e1);                           // softmax(dim=1)[:,1] (inference.py:475-477)
+  }
+}
+
 template <int YSRC, bool CLASSIFY>
-__global__ void __launch_bounds__(SWEEP_THREADS) apply_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
+__global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                               const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                               const float4* __restrict__ ybuf, const float* __restrict__ A,
                                                               const float* __restrict__ consts, float* __restrict__ msg_task,
                                                               float2* __restrict__ logits, uint8_t* __restrict__ pred,
                                                               float* __restrict__ prob1) {
+  constexpr int U = 2;
   __shared__ EdgeConsts sc;
+  __shared__ __align__(16) f32x2 w2s[16][4];                  // folded node weights as channel pairs: (w[2p][k], w[2p+1][k])
   load_consts(sc, consts);
+  if (threadIdx.x < 64) {
+    const int p = threadIdx.x >> 2, k = threadIdx.x & 3;
+    w2s[p][k] = pack2(sc.v[FC_NODE_WE + 4 * (2 * p) + k], sc.v[FC_NODE_WE + 4 * (2 * p + 1) + k]);
+  }
+  __syncthreads();
+  const uint32_t w2_addr = (uint32_t)__cvta_generic_to_shared(&w2s[0][0]);
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * SWEEP_THREADS) >> 5;
@@ -313,40 +406,58 @@ __global__ void __launch_bounds__(SWEEP_THREADS) apply_kernel(const mpn_graph g,
   for (int t = gwarp; t < n_tasks; t += nwarps) {
     const TaskRange tr = task_range(g, t);
     const float4 ps = (YSRC == 0) ? Ps[tr.row] : make_float4(0.f, 0.f, 0.f, 0.f);
-    // folded A'[c] = s4[c]*A[row,c] + t4[c]; lane c computes it, every lane needs all 32
+    // folded A'[c] = s4[c]*A[row,c] + t4[c]; lane c computes it, every lane needs all 32 (as 16 packed pairs)
     const float a_mine = fmaf(sc.v[FC_BN4_S + lane], A[(size_t)tr.row * MPN_DH + lane], sc.v[FC_BN4_T + lane]);
-    float ap[32], acc[32];
+    f32x2 ap[16], acc[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) { ap[c] = __shfl_sync(0xffffffffu, a_mine, c); acc[c] = 0.f; }
-    for (int e = tr.beg + lane; e < tr.end; e += 32) {
-      float ep[4];
-      load_eprime<YSRC>(sc, g, e, ps, edge_attr, Pd, ybuf, ep);
+    for (int p = 0; p < 16; ++p) {
+      ap[p] = pack2(__shfl_sync(0xffffffffu, a_mine, 2 * p), __shfl_sync(0xffffffffu, a_mine, 2 * p + 1));
+      acc[p] = 0ull;
+    }
+    EdgeLoad<U> cur, nxt;
+    load_edges<U, YSRC == 0, YSRC == 0, YSRC == 1>(cur, g, tr.beg, tr.end, lane, edge_attr, Pd, ybuf);
+    for (int base = tr.beg; base < tr.end; base += 32 * U) {
+      const int nbase = base + 32 * U;
+      if (nbase < tr.end) load_edges<U, YSRC == 0, YSRC == 0, YSRC == 1>(nxt, g, nbase, tr.end, lane, edge_attr, Pd, ybuf);
+      float ep[U][4];
+      f32x2 ed[U][4];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float4 w = *reinterpret_cast<const float4*>(&sc.v[FC_NODE_WE + 4 * c]);
-        float z = fmaf(w.x, ep[0], ap[c]);
-        z = fmaf(w.y, ep[1], z);
-        z = fmaf(w.z, ep[2], z);
-        z = fmaf(w.w, ep[3], z);
-        acc[c] += fmaxf(z, 0.f);
+      for (int j = 0; j < U; ++j) {
+        eprime_of<YSRC>(sc, ps, cur.ea[j], cur.pd[j], cur.y[j], ep[j]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ed[j][k] = pack2(ep[j][k], ep[j][k]);
       }
-      if (CLASSIFY) {
-        float l0 = sc.v[FC_CLS_B + 0], l1 = sc.v[FC_CLS_B + 1];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          l0 = fmaf(sc.v[FC_CLS_W + k], ep[k], l0);
-          l1 = fmaf(sc.v[FC_CLS_W + 4 + k], ep[k], l1);
+      for (int p = 0; p < 16; ++p) {
+        // volatile: keep the 32 weight loads inside the loop (hoisting them costs 128 registers and spills)
+        ulonglong2 wa, wb;
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(wa.x), "=l"(wa.y) : "r"(w2_addr + p * 32));
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(wb.x), "=l"(wb.y) : "r"(w2_addr + p * 32 + 16));
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          f32x2 z = fma2(wa.x, ed[j][0], ap[p]);
+          z = fma2(wa.y, ed[j][1], z);
+          z = fma2(wb.x, ed[j][2], z);
+          z = fma2(wb.y, ed[j][3], z);
+          z = relu2(z);
+          if (cur.ok[j]) acc[p] = add2(acc[p], z);
         }
-        logits[e] = make_float2(l0, l1);
-        if (pred) pred[e] = (l1 > l0) ? 1 : 0;                  // argmax, tie -> class 0 (inference.py:479)
-        if (prob1) {
-          const float m = fmaxf(l0, l1);
-          const float e0 = expf(l0 - m), e1 = expf(l1 - m);
-          prob1[e] = e1 / (e0 + e1);                           // softmax(dim=1)[:,1] (inference.py:475-477)
-        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if (cur.ok[j]) classify_store<CLASSIFY>(sc, ep[j], cur.e[j], logits, pred, prob1);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {                       // rotate only the fields this variant loads
+        cur.e[j] = nxt.e[j];
+        cur.ok[j] = nxt.ok[j];
+        if (YSRC == 0) { cur.ea[j] = nxt.ea[j]; cur.pd[j] = nxt.pd[j]; }
+        else cur.y[j] = nxt.y[j];
       }
     }
-    const float total = transpose_reduce32(acc, lane);
+    float accf[32];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) unpack2(acc[p], accf[2 * p], accf[2 * p + 1]);
+    const float total = transpose_reduce32(accf, lane);
     msg_task[(size_t)t * MPN_DH + lane] = total;
   }
 }
