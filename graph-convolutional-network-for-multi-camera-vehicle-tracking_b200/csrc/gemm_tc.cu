@@ -115,7 +115,8 @@ struct TcCfg {
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 };
 
-template <int BN>
+// SYM: C = A A^T (A == B, M == N): only tiles on or above the diagonal are computed, the epilogue also writes the mirror.
+template <int BN, bool SYM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -131,6 +132,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int num_kb = (K + TC_BK - 1) / TC_BK;
+  if (SYM && n0 + BN <= m0) return;                      // strictly below the diagonal: produced by the mirror store
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -231,6 +233,13 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             if (n0 + c0 + j < N) out[j] = v[j] + (bias ? bias[n0 + c0 + j] : 0.f);
         }
       }
+      if (SYM && row < M) {                               // mirror: C[col][row]; lanes hold consecutive rows -> coalesced
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col < N && col >= m0 + TC_BM) C[(size_t)col * N + row] = v[j];
+        }
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -241,13 +250,22 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   }
 }
 
-// x -> (hi, lo) TF32 planes
-__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, long long n4, float4* __restrict__ hi,
-                                                         float4* __restrict__ lo) {
+// x -> (hi, lo) TF32 planes.  Optional fused input transform f(x)[m,k] = relu(x*scale[k] + shift[k]): the BatchNorm+ReLU of
+// the previous encoder layer (models/mlp.py:14-19), so the activation is never re-written in fp32.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, long long n4, int K, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, float4* __restrict__ hi, float4* __restrict__ lo) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = x[i];
-    const float in[4] = {v.x, v.y, v.z, v.w};
+    float in[4] = {v.x, v.y, v.z, v.w};
+    if (scale != nullptr) {
+      const int k = (int)((i * 4) % K);                 // K % 4 == 0: the four lanes stay inside one row
+      const float4 sc = *reinterpret_cast<const float4*>(scale + k), sh = *reinterpret_cast<const float4*>(shift + k);
+      in[0] = fmaxf(fmaf(in[0], sc.x, sh.x), 0.f);
+      in[1] = fmaxf(fmaf(in[1], sc.y, sh.y), 0.f);
+      in[2] = fmaxf(fmaf(in[2], sc.z, sh.z), 0.f);
+      in[3] = fmaxf(fmaf(in[3], sc.w, sh.w), 0.f);
+    }
     float h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -301,22 +319,22 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K) {
   return 2 * plane_a + 2 * plane_b + 1024;
 }
 
-template <int BN>
+template <int BN, bool SYM>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const float* bias,
                      float* C, int M, int N, int K, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+    MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
     configured = true;
   }
   dim3 grid(div_up(N, BN), div_up(M, TC_BM));
-  gemm_nt_3xtf32_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ah, al, bh, bl, bias, C, M, N, K);
+  gemm_nt_3xtf32_kernel<BN, SYM><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ah, al, bh, bl, bias, C, M, N, K);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
 
 int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-               cudaStream_t st) {
+               cudaStream_t st, const float* a_scale, const float* a_shift) {
   MPN_REQUIRE(gemm_tc_supported(M, N, K), "tcgen05 GEMM: unsupported shape %d x %d x %d", M, N, K);
   MPN_REQUIRE(ws && ws_bytes >= gemm_tc_workspace_bytes(M, N, K), "tcgen05 GEMM: workspace too small");
   MPN_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "tcgen05 GEMM: operands must be 16-byte aligned");
@@ -327,15 +345,15 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
   float* b_lo = (float*)(w + plane_b);
   float *a_hi, *a_lo;
   const int split_grid = kNumSMs * 8;
-  split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)B, (long long)N * K / 4, (float4*)b_hi, (float4*)b_lo);
+  split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)B, (long long)N * K / 4, K, nullptr, nullptr, (float4*)b_hi, (float4*)b_lo);
   MPN_LAUNCH_OK();
-  if (A >= B && A + (size_t)M * K <= B + (size_t)N * K) {      // A is a row block of B (Gram matrix): share the planes
+  if (a_scale == nullptr && A >= B && A + (size_t)M * K <= B + (size_t)N * K) {      // A is a row block of B (Gram matrix): share the planes
     a_hi = b_hi + (A - B);
     a_lo = b_lo + (A - B);
   } else {
     a_hi = (float*)(w + 2 * plane_b);
     a_lo = (float*)(w + 2 * plane_b + plane_a);
-    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, (float4*)a_hi, (float4*)a_lo);
+    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, K, a_scale, a_shift, (float4*)a_hi, (float4*)a_lo);
     MPN_LAUNCH_OK();
   }
   CUtensorMap ah, al, bh, bl;
@@ -350,8 +368,10 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
   MPN_TRY(make_map(&al, a_lo, M, K, TC_BM));
   MPN_TRY(make_map(&bh, b_hi, N, K, BN));
   MPN_TRY(make_map(&bl, b_lo, N, K, BN));
-  if (BN == 256) return launch_tc<256>(ah, al, bh, bl, bias, C, M, N, K, st);
-  return launch_tc<128>(ah, al, bh, bl, bias, C, M, N, K, st);
+  const bool sym = (A == B) && (M == N) && bias == nullptr;     // Gram matrix: half the tiles
+  if (BN == 256) return launch_tc<256, false>(ah, al, bh, bl, bias, C, M, N, K, st);
+  if (sym) return launch_tc<128, true>(ah, al, bh, bl, bias, C, M, N, K, st);
+  return launch_tc<128, false>(ah, al, bh, bl, bias, C, M, N, K, st);
 }
 
 }  // namespace mpn

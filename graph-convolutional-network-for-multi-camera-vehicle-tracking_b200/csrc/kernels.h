@@ -12,8 +12,10 @@ int gemm_nt_simt(const float* A, const float* B, const float* bias, const float*
 
 // gemm_tc.cu  (tcgen05 3xTF32; operands are pre-split hi/lo planes)
 size_t gemm_tc_workspace_bytes(int M, int N, int K);
+// a_scale/a_shift (optional, [K]): A is read as relu(A*scale + shift) while it is split (fused BatchNorm+ReLU)
 int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
-               void* workspace, size_t workspace_bytes, cudaStream_t st);
+               void* workspace, size_t workspace_bytes, cudaStream_t st, const float* a_scale = nullptr,
+               const float* a_shift = nullptr);
 bool gemm_tc_supported(int M, int N, int K);
 
 }  // namespace mpn

@@ -100,6 +100,129 @@ __device__ __forceinline__ TaskRange task_range(const mpn_graph& g, int t) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// finalize: fixed-order reduction of block partials -> sums; sums -> folded constants.  Runs either as its own
+// one-block kernel (sharded runs: the host all-reduces the sums in between) or inside the LAST block of the sweep that
+// produced the partials (single-GPU: saves a launch per BatchNorm).  Partials written by other blocks of the same kernel
+// are read with ld.global.cg (L2), never through the non-coherent path.
+// ------------------------------------------------------------------------------------------------
+struct FinArgs {
+  int stage;
+  const double* partials;
+  int n_partials;
+  const double* partials2;
+  int n_partials2;
+  double* sums;
+  float* consts;
+  const float* small;
+  double n_total;
+  unsigned int* counter;      // != nullptr: fuse into the producing kernel's last block
+};
+
+__device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, int do_consts) {
+  const int stage = f.stage;
+  double* sums = f.sums;
+  float* consts = f.consts;
+  const float* small = f.small;
+  const int k = threadIdx.x;
+  if (do_reduce) {
+    // one warp per column: lanes stride over the partial rows in a fixed pattern, then a fixed shuffle tree
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_partials = f.n_partials, n_partials2 = f.n_partials2;
+    const double* partials = f.partials;
+    const double* partials2 = f.partials2;
+    for (int col = warp; col < SUMS; col += (int)(blockDim.x >> 5)) {
+      const double* src = partials;
+      int n = n_partials;
+      bool live = col < 8;
+      if (stage == MPN_STAGE_NODE) {
+        live = col < 74;
+        if (col < 64) { src = partials2; n = n_partials2; }
+      }
+      double s = 0.0;
+      if (live)
+        for (int p = lane; p < n; p += 32) s += __ldcg(src + (size_t)p * SUMS + col);
+      s = warp_sum(s);
+      if (lane == 0) sums[col] = s;
+    }
+  }
+  __syncthreads();
+  if (!do_consts) return;
+  const double inv_n = 1.0 / f.n_total;
+  if (stage == MPN_STAGE_ENC0) {
+    // static constants
+    if (k < 16) consts[FC_EDGE_WE + k] = small[MPN_W_EDGE_W + (k >> 2) * 68 + 64 + (k & 3)];
+    if (k < 8) consts[FC_CLS_W + k] = small[MPN_W_CLS_W + k];
+    if (k < 2) consts[FC_CLS_B + k] = small[MPN_W_CLS_B + k];
+    if (k < 4) {
+      const double ma = sums[0] * inv_n, mb = sums[1] * inv_n;
+      const double caa = sums[2] * inv_n - ma * ma, cab = sums[3] * inv_n - ma * mb, cbb = sums[4] * inv_n - mb * mb;
+      const double w0 = small[MPN_W_ENC1_W + 2 * k], w1 = small[MPN_W_ENC1_W + 2 * k + 1], b = small[MPN_W_ENC1_B + k];
+      const double mean = w0 * ma + w1 * mb + b;
+      double var = w0 * w0 * caa + 2.0 * w0 * w1 * cab + w1 * w1 * cbb;
+      if (var < 0.0) var = 0.0;
+      const double s = (double)small[MPN_W_ENC1_G + k] / sqrt(var + (double)BN_EPS);
+      const double t = (double)small[MPN_W_ENC1_BETA + k] - s * mean;
+      consts[FC_ENC1_W + 2 * k] = (float)(s * w0);
+      consts[FC_ENC1_W + 2 * k + 1] = (float)(s * w1);
+      consts[FC_ENC1_C + k] = (float)(s * b + t);
+    }
+  } else if (stage == MPN_STAGE_ENC1 || stage == MPN_STAGE_EDGE) {
+    if (k < 4) {
+      const double mean = sums[k] * inv_n;
+      double var = sums[4 + k] * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const int G = (stage == MPN_STAGE_ENC1) ? MPN_W_ENC2_G : MPN_W_EDGE_G;
+      const int B = (stage == MPN_STAGE_ENC1) ? MPN_W_ENC2_BETA : MPN_W_EDGE_BETA;
+      const double s = (double)small[G + k] / sqrt(var + (double)BN_EPS);
+      const double t = (double)small[B + k] - s * mean;
+      if (stage == MPN_STAGE_ENC1) {
+        for (int j = 0; j < 4; ++j) consts[FC_ENC2_W + 4 * k + j] = (float)(s * small[MPN_W_ENC2_W + 4 * k + j]);
+        consts[FC_ENC2_C + k] = (float)(s * small[MPN_W_ENC2_B + k] + t);
+      } else {
+        consts[FC_BN3_S + k] = (float)s;
+        consts[FC_BN3_T + k] = (float)t;
+      }
+    }
+  } else if (stage == MPN_STAGE_NODE) {
+    if (k < 32) {
+      double w[4];
+      for (int j = 0; j < 4; ++j) w[j] = small[MPN_W_NODE_W + k * 36 + 32 + j];
+      double quad = 0.0;
+      int idx = 0;
+      for (int a = 0; a < 4; ++a)
+        for (int b = a; b < 4; ++b) quad += (a == b ? 1.0 : 2.0) * w[a] * w[b] * sums[64 + idx++];
+      const double mean = sums[k] * inv_n;
+      double var = (sums[32 + k] + quad) * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double s = (double)small[MPN_W_NODE_G + k] / sqrt(var + (double)BN_EPS);
+      const double t = (double)small[MPN_W_NODE_BETA + k] - s * mean;
+      consts[FC_BN4_S + k] = (float)s;
+      consts[FC_BN4_T + k] = (float)t;
+      for (int j = 0; j < 4; ++j) consts[FC_NODE_WE + 4 * k + j] = (float)(s * w[j]);
+    }
+  }
+}
+
+constexpr int FIN_THREADS = 1024;
+__global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinArgs f, int do_reduce, int do_consts) {
+  finalize_body(f, do_reduce, do_consts);
+}
+
+// called by every block at the end of a sweep kernel, after its partial row has been written
+__device__ __forceinline__ void finalize_in_last_block(const FinArgs& f) {
+  if (f.counter == nullptr) return;
+  __shared__ unsigned int s_ticket;
+  __threadfence();                                   // publish this block's partials
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(f.counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  finalize_body(f, 1, 1);
+  if (threadIdx.x == 0) *f.counter = 0u;             // ready for the next sweep
+}
+
+// ------------------------------------------------------------------------------------------------
 // flat sweeps over edge_attr for the two encoder BatchNorms
 // ------------------------------------------------------------------------------------------------
 // STAGE 0: sums of (a, b, aa, ab, bb);  STAGE 1: sums of u[4], u^2[4] with u = W2·relu(BN1(W1·ea+b1)) + b2
@@ -107,7 +230,7 @@ template <int STAGE>
 __global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_kernel(const float2* __restrict__ edge_attr, long long E,
                                                                     const float* __restrict__ consts,
                                                                     const float* __restrict__ small,
-                                                                    double* __restrict__ partials) {
+                                                                    double* __restrict__ partials, const FinArgs fin) {
   __shared__ EdgeConsts sc;
   __shared__ double red[(SWEEP_THREADS / 32) * 8];
   __shared__ float w2raw[20];
@@ -118,21 +241,35 @@ __global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_kernel(const float2
     __syncthreads();
   }
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  constexpr int U = 4;                                  // independent loads in flight per thread
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
-    const float2 ea = ldg_stream2(edge_attr + e);
-    if (STAGE == 0) {
-      const double a = ea.x, b = ea.y;
-      acc[0] += a; acc[1] += b; acc[2] += a * a; acc[3] += a * b; acc[4] += b * b;
-    } else {
-      float a1[4], u[4];
-      enc_layer1(sc, ea, a1);
-      enc_layer2_pre(w2raw, w2raw + 16, a1, u);
+  for (long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; e0 < E; e0 += stride * U) {
+    float2 eav[U];
+    bool ok[U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const double d = u[j]; acc[j] += d; acc[4 + j] += d * d; }
+    for (int j = 0; j < U; ++j) {
+      const long long e = e0 + stride * j;
+      ok[j] = e < E;
+      eav[j] = ldg_stream2(edge_attr + (ok[j] ? e : E - 1));
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (!ok[j]) continue;
+      const float2 ea = eav[j];
+      if (STAGE == 0) {
+        const double a = ea.x, b = ea.y;
+        acc[0] += a; acc[1] += b; acc[2] += a * a; acc[3] += a * b; acc[4] += b * b;
+      } else {
+        float a1[4], u[4];
+        enc_layer1(sc, ea, a1);
+        enc_layer2_pre(w2raw, w2raw + 16, a1, u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const double d = u[k]; acc[k] += d; acc[4 + k] += d * d; }
+      }
     }
   }
   block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
+  finalize_in_last_block(fin);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -178,7 +315,7 @@ template <int SRC, bool WRITE_Y>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                                      const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                                      float4* __restrict__ ybuf, const float* __restrict__ consts,
-                                                                     double* __restrict__ partials) {
+                                                                     double* __restrict__ partials, const FinArgs fin) {
   constexpr int U = 4;
   __shared__ EdgeConsts sc;
   __shared__ double red[(SWEEP_THREADS / 32) * 8];
@@ -213,6 +350,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mp
     }
   }
   block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
+  finalize_in_last_block(fin);
 }
 
 // e' = relu(BN3(y)) for one loaded edge
@@ -283,7 +421,7 @@ constexpr int NM_GRID = kNumSMs * 2;
 __global__ void __launch_bounds__(NM_THREADS) node_moments_node_kernel(const mpn_graph g, const float* __restrict__ A,
                                                                        const float4* __restrict__ s1_task,
                                                                        const float* __restrict__ small,
-                                                                       double* __restrict__ partials) {
+                                                                       double* __restrict__ partials, const FinArgs fin) {
   __shared__ double red[NM_THREADS / 32][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = (blockIdx.x * NM_THREADS + threadIdx.x) >> 5;
@@ -313,6 +451,7 @@ __global__ void __launch_bounds__(NM_THREADS) node_moments_node_kernel(const mpn
     for (int wv = 0; wv < NM_THREADS / 32; ++wv) s += red[wv][threadIdx.x];
     partials[(size_t)blockIdx.x * SUMS + threadIdx.x] = s;
   }
+  finalize_in_last_block(fin);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -363,6 +502,9 @@ __device__ __forceinline__ f32x2 relu2(f32x2 v) {
   return pack2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
 }
 
+// softmax([l0,l1])[1] (inference.py:475-477) = 1 / (1 + exp(l0 - l1)): one exp, same value up to rounding
+__device__ __forceinline__ float softmax1(float l0, float l1) { return 1.0f / (1.0f + expf(l0 - l1)); }
+
 template <bool CLASSIFY>
 __device__ __forceinline__ void classify_store(const EdgeConsts& sc, const float (&ep)[4], int e, float2* __restrict__ logits,
                                                uint8_t* __restrict__ pred, float* __restrict__ prob1) {
@@ -375,11 +517,7 @@ __device__ __forceinline__ void classify_store(const EdgeConsts& sc, const float
   }
   logits[e] = make_float2(l0, l1);
   if (pred) pred[e] = (l1 > l0) ? 1 : 0;                  // argmax, tie -> class 0 (inference.py:479)
-  if (prob1) {
-    const float m = fmaxf(l0, l1);
-    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
-    prob1[e] = e1 / (e0 + e1);                           // softmax(dim=1)[:,1] (inference.py:475-477)
-  }
+  if (prob1) prob1[e] = softmax1(l0, l1);
 }
 
 template <int YSRC, bool CLASSIFY>
@@ -481,11 +619,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) classify_encoded_kernel(const f
     }
     logits[e] = make_float2(l0, l1);
     if (pred) pred[e] = (l1 > l0) ? 1 : 0;
-    if (prob1) {
-      const float m = fmaxf(l0, l1);
-      const float e0 = expf(l0 - m), e1 = expf(l1 - m);
-      prob1[e] = e1 / (e0 + e1);
-    }
+    if (prob1) prob1[e] = softmax1(l0, l1);
   }
 }
 
@@ -494,100 +628,13 @@ __global__ void decide_kernel(const float2* __restrict__ logits, long long E, ui
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     const float2 l = logits[e];
     if (pred) pred[e] = (l.y > l.x) ? 1 : 0;
-    if (prob1) {
-      const float m = fmaxf(l.x, l.y);
-      const float e0 = expf(l.x - m), e1 = expf(l.y - m);
-      prob1[e] = e1 / (e0 + e1);
-    }
+    if (prob1) prob1[e] = softmax1(l.x, l.y);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // finalize: fixed-order reduction of block partials -> sums; sums -> folded constants
 // ------------------------------------------------------------------------------------------------
-constexpr int FIN_THREADS = 1024;
-__global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(int stage, const double* __restrict__ partials, int n_partials,
-                                                       const double* __restrict__ partials2, int n_partials2,
-                                                       double* __restrict__ sums, int do_reduce, int do_consts,
-                                                       float* __restrict__ consts, const float* __restrict__ small,
-                                                       double n_total) {
-  const int k = threadIdx.x;
-  if (do_reduce) {
-    // one warp per column: lanes stride over the partial rows in a fixed pattern, then a fixed shuffle tree
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int col = warp; col < SUMS; col += FIN_THREADS / 32) {
-      const double* src = partials;
-      int n = n_partials;
-      bool live = col < 8;
-      if (stage == MPN_STAGE_NODE) {
-        live = col < 74;
-        if (col < 64) { src = partials2; n = n_partials2; }
-      }
-      double s = 0.0;
-      if (live)
-        for (int p = lane; p < n; p += 32) s += src[(size_t)p * SUMS + col];
-      s = warp_sum(s);
-      if (lane == 0) sums[col] = s;
-    }
-  }
-  __syncthreads();
-  if (!do_consts) return;
-  const double inv_n = 1.0 / n_total;
-  if (stage == MPN_STAGE_ENC0) {
-    // static constants
-    if (k < 16) consts[FC_EDGE_WE + k] = small[MPN_W_EDGE_W + (k >> 2) * 68 + 64 + (k & 3)];
-    if (k < 8) consts[FC_CLS_W + k] = small[MPN_W_CLS_W + k];
-    if (k < 2) consts[FC_CLS_B + k] = small[MPN_W_CLS_B + k];
-    if (k < 4) {
-      const double ma = sums[0] * inv_n, mb = sums[1] * inv_n;
-      const double caa = sums[2] * inv_n - ma * ma, cab = sums[3] * inv_n - ma * mb, cbb = sums[4] * inv_n - mb * mb;
-      const double w0 = small[MPN_W_ENC1_W + 2 * k], w1 = small[MPN_W_ENC1_W + 2 * k + 1], b = small[MPN_W_ENC1_B + k];
-      const double mean = w0 * ma + w1 * mb + b;
-      double var = w0 * w0 * caa + 2.0 * w0 * w1 * cab + w1 * w1 * cbb;
-      if (var < 0.0) var = 0.0;
-      const double s = (double)small[MPN_W_ENC1_G + k] / sqrt(var + (double)BN_EPS);
-      const double t = (double)small[MPN_W_ENC1_BETA + k] - s * mean;
-      consts[FC_ENC1_W + 2 * k] = (float)(s * w0);
-      consts[FC_ENC1_W + 2 * k + 1] = (float)(s * w1);
-      consts[FC_ENC1_C + k] = (float)(s * b + t);
-    }
-  } else if (stage == MPN_STAGE_ENC1 || stage == MPN_STAGE_EDGE) {
-    if (k < 4) {
-      const double mean = sums[k] * inv_n;
-      double var = sums[4 + k] * inv_n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const int G = (stage == MPN_STAGE_ENC1) ? MPN_W_ENC2_G : MPN_W_EDGE_G;
-      const int B = (stage == MPN_STAGE_ENC1) ? MPN_W_ENC2_BETA : MPN_W_EDGE_BETA;
-      const double s = (double)small[G + k] / sqrt(var + (double)BN_EPS);
-      const double t = (double)small[B + k] - s * mean;
-      if (stage == MPN_STAGE_ENC1) {
-        for (int j = 0; j < 4; ++j) consts[FC_ENC2_W + 4 * k + j] = (float)(s * small[MPN_W_ENC2_W + 4 * k + j]);
-        consts[FC_ENC2_C + k] = (float)(s * small[MPN_W_ENC2_B + k] + t);
-      } else {
-        consts[FC_BN3_S + k] = (float)s;
-        consts[FC_BN3_T + k] = (float)t;
-      }
-    }
-  } else if (stage == MPN_STAGE_NODE) {
-    if (k < 32) {
-      double w[4];
-      for (int j = 0; j < 4; ++j) w[j] = small[MPN_W_NODE_W + k * 36 + 32 + j];
-      double quad = 0.0;
-      int idx = 0;
-      for (int a = 0; a < 4; ++a)
-        for (int b = a; b < 4; ++b) quad += (a == b ? 1.0 : 2.0) * w[a] * w[b] * sums[64 + idx++];
-      const double mean = sums[k] * inv_n;
-      double var = (sums[32 + k] + quad) * inv_n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const double s = (double)small[MPN_W_NODE_G + k] / sqrt(var + (double)BN_EPS);
-      const double t = (double)small[MPN_W_NODE_BETA + k] - s * mean;
-      consts[FC_BN4_S + k] = (float)s;
-      consts[FC_BN4_T + k] = (float)t;
-      for (int j = 0; j < 4; ++j) consts[FC_NODE_WE + 4 * k + j] = (float)(s * w[j]);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // node encoder pieces: column statistics of a [M, Nc] activation, BN+ReLU apply
 // ------------------------------------------------------------------------------------------------
@@ -716,6 +763,8 @@ struct mpn_fwd_plan {
   double* colpart;
   float *h_full, *Ps, *Pd, *A, *consts, *s1_task, *msg_task, *ybuf;
   double *partials, *partials2, *sums;
+  unsigned int* fin_counter;
+  int fuse_fin;               // single-GPU: the last block of each moment sweep folds the constants itself
   void* gemm_ws;
   size_t gemm_ws_bytes;
 };
@@ -741,6 +790,7 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.partials = a.take<double>((size_t)SWEEP_GRID * SUMS);
   p.partials2 = a.take<double>((size_t)NM_GRID * SUMS);
   p.sums = a.take<double>(SUMS);
+  p.fin_counter = a.take<unsigned int>(1);
   p.ybuf = (p.L > 1) ? a.take<float>((size_t)g.n_edges * 4) : nullptr;
   size_t gw = 0;
   if (p.use_tc) {
@@ -806,6 +856,21 @@ void mpn_plan_destroy(mpn_fwd_plan* plan) { delete plan; }
 double* mpn_plan_sums(mpn_fwd_plan* plan) { return plan ? plan->sums : nullptr; }
 float* mpn_plan_h_full(mpn_fwd_plan* plan) { return plan ? plan->h_full : nullptr; }
 
+static FinArgs make_fin(const mpn_fwd_plan* p, int stage, bool fused) {
+  FinArgs f;
+  f.stage = stage;
+  f.partials = p->partials;
+  f.n_partials = SWEEP_GRID;
+  f.partials2 = p->partials2;
+  f.n_partials2 = NM_GRID;
+  f.sums = p->sums;
+  f.consts = p->consts;
+  f.small = p->w.small;
+  f.n_total = (double)p->total_edges;
+  f.counter = fused ? p->fin_counter : nullptr;
+  return f;
+}
+
 int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
   MPN_REQUIRE(p && x, "node_encoder: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -818,12 +883,8 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
     float* out = bufs[l & 1];
     bool done = false;
     if (p->use_tc && gemm_tc_supported(M, Nc, K)) {
-      // the TMA-fed tensor-core path needs materialised (BN+ReLU applied) inputs: apply in place
-      if (sc) {
-        bn_relu_apply_kernel<<<kNumSMs * 4, 256, 0, st>>>(in, (long long)M * K, K, sc, sh, (float*)in);
-        MPN_LAUNCH_OK();
-      }
-      MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st));
+      // tensor-core path: BatchNorm+ReLU of the previous layer is applied while the operand is split into TF32 planes
+      MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh));
       done = true;
     }
     if (!done) MPN_TRY(gemm_nt_simt(in, p->w.node_w[l], p->w.node_b[l], sc, sh, out, M, Nc, K, st));
@@ -860,28 +921,30 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
   const mpn_graph& g = p->g;
   const float2* ea = (const float2*)edge_attr;
   const bool stored = p->L > 1;           // y materialised in ybuf for multi-step runs
+  const bool fused = p->fuse_fin != 0;
   const int flat_grid = (int)min((long long)SWEEP_GRID, (long long)div_up(g.n_edges > 0 ? g.n_edges : 1, SWEEP_THREADS));
   switch (stage) {
     case MPN_STAGE_ENC0:
       MPN_CUDA_OK(cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st));
-      enc_moments_kernel<0><<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, p->w.small, p->partials);
+      MPN_CUDA_OK(cudaMemsetAsync(p->fin_counter, 0, sizeof(unsigned int), st));
+      enc_moments_kernel<0><<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused));
       break;
     case MPN_STAGE_ENC1:
-      enc_moments_kernel<1><<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, p->w.small, p->partials);
+      enc_moments_kernel<1><<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused));
       break;
     case MPN_STAGE_EDGE:
       if (step == 1) {
-        if (stored) edge_moments_kernel<0, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (float4*)p->ybuf, p->consts, p->partials);
-        else edge_moments_kernel<0, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, nullptr, p->consts, p->partials);
+        if (stored) edge_moments_kernel<0, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (float4*)p->ybuf, p->consts, p->partials, make_fin(p, stage, fused));
+        else edge_moments_kernel<0, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, nullptr, p->consts, p->partials, make_fin(p, stage, fused));
       } else {
-        edge_moments_kernel<1, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (float4*)p->ybuf, p->consts, p->partials);
+        edge_moments_kernel<1, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (float4*)p->ybuf, p->consts, p->partials, make_fin(p, stage, fused));
       }
       break;
     case MPN_STAGE_NODE:
       if (stored) node_moments_sweep_kernel<1><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (const float4*)p->ybuf, p->consts, (float4*)p->s1_task, p->partials);
       else node_moments_sweep_kernel<0><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, nullptr, p->consts, (float4*)p->s1_task, p->partials);
       MPN_LAUNCH_OK();
-      node_moments_node_kernel<<<NM_GRID, NM_THREADS, 0, st>>>(g, p->A, (const float4*)p->s1_task, p->w.small, p->partials2);
+      node_moments_node_kernel<<<NM_GRID, NM_THREADS, 0, st>>>(g, p->A, (const float4*)p->s1_task, p->w.small, p->partials2, make_fin(p, stage, fused));
       break;
     case MPN_STAGE_APPLY: {
       const bool classify = logits_out != nullptr;
@@ -908,8 +971,7 @@ int mpn_plan_finalize(mpn_fwd_plan* p, int32_t step, int32_t stage, void* stream
   MPN_REQUIRE(p, "finalize: NULL plan");
   (void)step;
   // sums already reduced (and possibly all-reduced by the host): constants only
-  finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(stage, nullptr, 0, nullptr, 0, p->sums, 0, 1, p->consts, p->w.small,
-                                                       (double)p->total_edges);
+  finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(make_fin(p, stage, false), 0, 1);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -917,8 +979,7 @@ int mpn_plan_finalize(mpn_fwd_plan* p, int32_t step, int32_t stage, void* stream
 // reduce this rank's block partials into the sums vector (phase API: host all-reduces it afterwards)
 int mpn_plan_reduce(mpn_fwd_plan* p, int32_t stage, int with_consts, void* stream) {
   MPN_REQUIRE(p, "reduce: NULL plan");
-  finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(stage, p->partials, SWEEP_GRID, p->partials2, NM_GRID, p->sums, 1,
-                                                       with_consts, p->consts, p->w.small, (double)p->total_edges);
+  finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(make_fin(p, stage, false), 1, with_consts);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -929,6 +990,26 @@ int mpn_plan_node_finalize(mpn_fwd_plan* p, int32_t step, void* stream) {
   node_finalize_kernel<<<min(kNumSMs * 8, div_up((long long)p->g.n_nodes * 32, 256)), 256, 0, (cudaStream_t)stream>>>(p->g, p->msg_task, p->h_full);
   MPN_LAUNCH_OK();
   return MPN_OK;
+}
+
+// per-device side stream + fork/join events (created once, never destroyed)
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+static SideStream* side_stream() {
+  static SideStream table[64];
+  static int state[64];                 // 0 = not tried, 1 = ok, -1 = failed
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (state[dev] == 0) {
+    SideStream& s = table[dev];
+    const bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+    state[dev] = ok ? 1 : -1;
+  }
+  return state[dev] == 1 ? &table[dev] : nullptr;
 }
 
 int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const float* edge_attr, int32_t L, int32_t n_cls,
@@ -942,11 +1023,17 @@ int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const 
   int rc = MPN_OK;
   const size_t lstride = (size_t)g->n_edges * 2;
 #define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
-  STEP_TRY(mpn_plan_node_encoder(p, x, st));
-  STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
-  STEP_TRY(mpn_plan_reduce(p, MPN_STAGE_ENC0, 1, st));
-  STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
-  STEP_TRY(mpn_plan_reduce(p, MPN_STAGE_ENC1, 1, st));
+  p->fuse_fin = 1;
+  {
+    // the node encoder (tensor-core GEMM chain) does not depend on the edge-encoder sweeps: run it on a side stream
+    SideStream* ss = side_stream();
+    const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
+    STEP_TRY(mpn_plan_node_encoder(p, x, fork ? ss->stream : st));
+    if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
+    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
+    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
+    if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
+  }
   if (L == 0) {
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_APPLY, edge_attr, logits_out, pred_out, prob1_out, st));
   }
@@ -956,9 +1043,7 @@ int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const 
     for (int step = 1; step <= L; ++step) {
       STEP_TRY(mpn_plan_node_tables(p, step, st));
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_EDGE, edge_attr, nullptr, nullptr, nullptr, st));
-      STEP_TRY(mpn_plan_reduce(p, MPN_STAGE_EDGE, 1, st));
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_NODE, edge_attr, nullptr, nullptr, nullptr, st));
-      STEP_TRY(mpn_plan_reduce(p, MPN_STAGE_NODE, 1, st));
       const bool cls = step >= first_class_step;
       const bool last = step == L;
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_APPLY, edge_attr, cls ? logits_out + lstride * k : nullptr,
