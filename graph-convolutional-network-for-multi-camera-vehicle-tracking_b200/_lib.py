@@ -34,7 +34,8 @@ class MpnWeights(C.Structure):
     _fields_ = [("n_node_layers", C.c_int32), ("node_dims", C.c_int32 * (MPN_MAX_NODE_LAYERS + 1)),
                 ("node_w", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_b", C.c_void_p * MPN_MAX_NODE_LAYERS),
                 ("node_gamma", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_beta", C.c_void_p * MPN_MAX_NODE_LAYERS),
-                ("small", C.c_void_p)]
+                ("small", C.c_void_p),
+                ("node_w_hi", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_w_lo", C.c_void_p * MPN_MAX_NODE_LAYERS)]
 
 
 class MpnError(RuntimeError):
@@ -73,6 +74,7 @@ _PROTOS = {
     "mpn_plan_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "mpn_plan_node_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "mpn_plan_h_full": (C.c_void_p, [C.c_void_p]),
+    "mpn_split_tf32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_decide": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_post_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph)]),
     "mpn_cut": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

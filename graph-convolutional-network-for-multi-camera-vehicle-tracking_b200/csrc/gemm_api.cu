@@ -19,4 +19,8 @@ int mpn_gemm_nt(const float* A, const float* B, const float* bias, float* C, int
   return gemm_nt_tc(A, B, bias, C, M, N, K, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int mpn_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream) {
+  return split_tf32(x, (long long)n, hi, lo, (cudaStream_t)stream);
+}
+
 }  // extern "C"

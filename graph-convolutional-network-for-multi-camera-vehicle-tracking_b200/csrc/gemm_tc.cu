@@ -310,6 +310,14 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int K, int bo
   return MPN_OK;
 }
 
+int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t st) {
+  MPN_REQUIRE(x && hi && lo && n > 0 && (n % 4) == 0, "split_tf32: bad arguments (n must be a positive multiple of 4)");
+  MPN_REQUIRE((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "split_tf32: pointers must be 16-byte aligned");
+  split_tf32_kernel<<<(int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256), 256, 0, st>>>((const float4*)x, n / 4, 4, nullptr, nullptr, (float4*)hi, (float4*)lo);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
 bool gemm_tc_supported(int M, int N, int K) { return M >= 1 && N >= 64 && K >= 64 && (K % 4) == 0; }
 
 size_t gemm_tc_workspace_bytes(int M, int N, int K) {
@@ -334,7 +342,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
 }
 
 int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-               cudaStream_t st, const float* a_scale, const float* a_shift) {
+               cudaStream_t st, const float* a_scale, const float* a_shift, const float* b_hi_cached, const float* b_lo_cached) {
   MPN_REQUIRE(gemm_tc_supported(M, N, K), "tcgen05 GEMM: unsupported shape %d x %d x %d", M, N, K);
   MPN_REQUIRE(ws && ws_bytes >= gemm_tc_workspace_bytes(M, N, K), "tcgen05 GEMM: workspace too small");
   MPN_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "tcgen05 GEMM: operands must be 16-byte aligned");
@@ -345,8 +353,13 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
   float* b_lo = (float*)(w + plane_b);
   float *a_hi, *a_lo;
   const int split_grid = kNumSMs * 8;
-  split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)B, (long long)N * K / 4, K, nullptr, nullptr, (float4*)b_hi, (float4*)b_lo);
-  MPN_LAUNCH_OK();
+  if (b_hi_cached && b_lo_cached) {                  // weights: planes made once by mpn_split_tf32
+    b_hi = (float*)b_hi_cached;
+    b_lo = (float*)b_lo_cached;
+  } else {
+    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)B, (long long)N * K / 4, K, nullptr, nullptr, (float4*)b_hi, (float4*)b_lo);
+    MPN_LAUNCH_OK();
+  }
   if (a_scale == nullptr && A >= B && A + (size_t)M * K <= B + (size_t)N * K) {      // A is a row block of B (Gram matrix): share the planes
     a_hi = b_hi + (A - B);
     a_lo = b_lo + (A - B);

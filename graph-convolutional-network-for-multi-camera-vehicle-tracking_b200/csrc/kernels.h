@@ -15,7 +15,8 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K);
 // a_scale/a_shift (optional, [K]): A is read as relu(A*scale + shift) while it is split (fused BatchNorm+ReLU)
 int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
                void* workspace, size_t workspace_bytes, cudaStream_t st, const float* a_scale = nullptr,
-               const float* a_shift = nullptr);
+               const float* a_shift = nullptr, const float* b_hi_cached = nullptr, const float* b_lo_cached = nullptr);
+int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t st);
 bool gemm_tc_supported(int M, int N, int K);
 
 }  // namespace mpn

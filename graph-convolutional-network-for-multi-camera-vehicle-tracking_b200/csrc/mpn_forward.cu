@@ -639,9 +639,14 @@ __global__ void decide_kernel(const float2* __restrict__ logits, long long E, ui
 // node encoder pieces: column statistics of a [M, Nc] activation, BN+ReLU apply
 // ------------------------------------------------------------------------------------------------
 constexpr int CS_ROWSPLIT_MAX = 64;
+// grid (32-column tiles, row splits): fp64 partial sums per split; the LAST split block of a column tile (ticket counter)
+// adds the partials in split order and folds them into the BatchNorm scale/shift of that tile's columns.
 __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ Y, int M, int Nc, int rows_per_split,
-                                                       double* __restrict__ part /*[splits][Nc][2]*/) {
+                                                       double* __restrict__ part /*[splits][Nc][2]*/, unsigned int* __restrict__ tile_counter,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float* __restrict__ scale, float* __restrict__ shift) {
   __shared__ double ssum[8][33], ssq[8][33];
+  __shared__ unsigned int s_ticket;
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
   const int r0 = blockIdx.y * rows_per_split, r1 = min(r0 + rows_per_split, M);
@@ -660,24 +665,26 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
     part[((size_t)blockIdx.y * Nc + col) * 2 + 0] = s;
     part[((size_t)blockIdx.y * Nc + col) * 2 + 1] = q;
   }
-}
-
-__global__ void colstats_finalize_kernel(const double* __restrict__ part, int splits, int Nc, int M,
-                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                         float* __restrict__ scale, float* __restrict__ shift) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= Nc) return;
-  double s = 0.0, q = 0.0;
-  for (int i = 0; i < splits; ++i) {
-    s += part[((size_t)i * Nc + col) * 2 + 0];
-    q += part[((size_t)i * Nc + col) * 2 + 1];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tile_counter[blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  __threadfence();
+  if (ry == 0 && col < Nc) {
+    double ts = 0.0, tq = 0.0;
+    for (int i = 0; i < (int)gridDim.y; ++i) {
+      ts += __ldcg(&part[((size_t)i * Nc + col) * 2 + 0]);
+      tq += __ldcg(&part[((size_t)i * Nc + col) * 2 + 1]);
+    }
+    const double mean = ts / M;
+    double var = tq / M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double sc = (double)gamma[col] / sqrt(var + (double)BN_EPS);
+    scale[col] = (float)sc;
+    shift[col] = (float)((double)beta[col] - sc * mean);
   }
-  const double mean = s / M;
-  double var = q / M - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const double sc = (double)gamma[col] / sqrt(var + (double)BN_EPS);
-  scale[col] = (float)sc;
-  shift[col] = (float)((double)beta[col] - sc * mean);
+  if (threadIdx.x == 0) tile_counter[blockIdx.x] = 0u;
 }
 
 __global__ void bn_relu_apply_kernel(const float* __restrict__ Y, long long total, int Nc, const float* __restrict__ scale,
@@ -764,6 +771,7 @@ struct mpn_fwd_plan {
   float *h_full, *Ps, *Pd, *A, *consts, *s1_task, *msg_task, *ybuf;
   double *partials, *partials2, *sums;
   unsigned int* fin_counter;
+  unsigned int* col_counter;   // [max_dim/32 + 1] ticket counters of the column-statistics tiles
   int fuse_fin;               // single-GPU: the last block of each moment sweep folds the constants itself
   void* gemm_ws;
   size_t gemm_ws_bytes;
@@ -791,6 +799,7 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.partials2 = a.take<double>((size_t)NM_GRID * SUMS);
   p.sums = a.take<double>(SUMS);
   p.fin_counter = a.take<unsigned int>(1);
+  p.col_counter = a.take<unsigned int>((size_t)(max_dim > 0 ? max_dim : 1) / 32 + 1);
   p.ybuf = (p.L > 1) ? a.take<float>((size_t)g.n_edges * 4) : nullptr;
   size_t gw = 0;
   if (p.use_tc) {
@@ -875,6 +884,7 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
   MPN_REQUIRE(p && x, "node_encoder: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int M = p->g.n_cols;
+  MPN_CUDA_OK(cudaMemsetAsync(p->col_counter, 0, sizeof(unsigned int) * ((size_t)p->max_dim / 32 + 1), st));
   const float* in = x;
   float* bufs[2] = {p->act0, p->act1};
   const float *sc = nullptr, *sh = nullptr;
@@ -884,17 +894,16 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
     bool done = false;
     if (p->use_tc && gemm_tc_supported(M, Nc, K)) {
       // tensor-core path: BatchNorm+ReLU of the previous layer is applied while the operand is split into TF32 planes
-      MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh));
+      MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh,
+                         p->w.node_w_hi[l], p->w.node_w_lo[l]));
       done = true;
     }
     if (!done) MPN_TRY(gemm_nt_simt(in, p->w.node_w[l], p->w.node_b[l], sc, sh, out, M, Nc, K, st));
     int splits = div_up(M, 256);
     splits = splits > CS_ROWSPLIT_MAX ? CS_ROWSPLIT_MAX : splits;
     const int rps = div_up(M, splits);
-    colstats_kernel<<<dim3(div_up(Nc, 32), splits), 256, 0, st>>>(out, M, Nc, rps, p->colpart);
-    MPN_LAUNCH_OK();
-    colstats_finalize_kernel<<<div_up(Nc, 128), 128, 0, st>>>(p->colpart, splits, Nc, M, p->w.node_gamma[l], p->w.node_beta[l],
-                                                              p->colscale, p->colshift);
+    colstats_kernel<<<dim3(div_up(Nc, 32), splits), 256, 0, st>>>(out, M, Nc, rps, p->colpart, p->col_counter, p->w.node_gamma[l],
+                                                                  p->w.node_beta[l], p->colscale, p->colshift);
     MPN_LAUNCH_OK();
     in = out;
     sc = p->colscale;

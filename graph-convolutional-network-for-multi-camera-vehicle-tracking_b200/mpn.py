@@ -18,6 +18,73 @@ from .graph import current_stream_ptr, graph_for, workspace
 USE_TENSOR_CORES = True
 
 
+class _GraphedForward:
+    """One captured CUDA graph of ``mpn_forward`` for a fixed (N, E, weights) signature.
+
+    Inputs are staged into static buffers (skipped when the caller passes the same tensors again), the graph is
+    replayed with a single launch, outputs are cloned so the caller still receives fresh tensors like the reference.
+    """
+
+    def __init__(self, W, g, x, ea, L, n_cls, n_out, fused):
+        from .graph import TrackletGraph
+        dev = x.device
+        self.W, self.L, self.n_cls = W, L, n_cls
+        self.x, self.ea = torch.empty_like(x), torch.empty_like(ea)
+        # static graph tables with the same sizes as the caller's
+        self.g = object.__new__(TrackletGraph)
+        for name in ("device", "n_cols", "n_nodes", "row_offset", "n_edges", "chunk", "max_tasks"):
+            setattr(self.g, name, getattr(g, name))
+        self.g.perm = None
+        self.tables = ("rowptr", "col", "taskptr", "task_row", "n_tasks")
+        for name in self.tables:
+            setattr(self.g, name, torch.empty_like(getattr(g, name)))
+        self.g.struct = _lib.MpnGraph(g.n_nodes, g.n_cols, g.row_offset, g.chunk, g.n_edges, g.max_tasks, 0,
+                                      self.g.rowptr.data_ptr(), self.g.col.data_ptr(), self.g.taskptr.data_ptr(),
+                                      self.g.task_row.data_ptr(), self.g.n_tasks.data_ptr())
+        self.logits = torch.empty(n_out, g.n_edges, 2, dtype=torch.float32, device=dev)
+        self.h = torch.empty(g.n_nodes, _lib.MPN_DH, dtype=torch.float32, device=dev)
+        self.pred = torch.empty(g.n_edges, dtype=torch.uint8, device=dev) if fused else None
+        self.prob1 = torch.empty(g.n_edges, dtype=torch.float32, device=dev) if fused else None
+        lib = _lib.lib()
+        need = lib.mpn_forward_workspace_bytes(self.g.ref, C.byref(W), L)
+        self.ws = torch.empty(need + 4096, dtype=torch.uint8, device=dev)      # private: lives as long as the graph
+        self._last = (None, None, None)
+        self._stage(g, x, ea)
+
+        def launch():
+            _lib.check(lib.mpn_forward(self.g.ref, C.byref(W), self.x.data_ptr(), self.ea.data_ptr(), L, n_cls,
+                                       self.logits.data_ptr(), self.h.data_ptr(),
+                                       self.pred.data_ptr() if fused else None, self.prob1.data_ptr() if fused else None,
+                                       int(bool(USE_TENSOR_CORES)), self.ws.data_ptr(), self.ws.numel(),
+                                       current_stream_ptr(dev)))
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                                       # warm-up outside capture (lazy inits)
+                launch()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                launch()
+
+    def _stage(self, g, x, ea):
+        lg, lx, le = self._last
+        if lg is not g:
+            for name in self.tables:
+                getattr(self.g, name).copy_(getattr(g, name), non_blocking=True)
+        if lx is None or lx[0] is not x or lx[1] != x._version:
+            self.x.copy_(x, non_blocking=True)
+        if le is None or le[0] is not ea or le[1] != ea._version:
+            self.ea.copy_(ea, non_blocking=True)
+        self._last = (g, (x, x._version), (ea, ea._version))
+
+    def run(self, g, x, ea):
+        self._stage(g, x, ea)
+        self.graph.replay()
+        return (self.logits.clone(), self.h.clone(), self.pred.clone() if self.pred is not None else None,
+                self.prob1.clone() if self.prob1 is not None else None)
+
+
 class MLP(nn.Module):
     """Parameter container with the reference layout: [Linear, BatchNorm1d, ReLU, Dropout] per hidden width
     (BN/ReLU/Dropout omitted for width 1; bare Linear stack for classifiers) — models/mlp.py:4-33."""
@@ -131,6 +198,10 @@ class MOTMPNet(nn.Module):
         if any(w == 1 for w in list(enc['node_fc_dims'])):
             raise _unsupported("node encoder widths of 1")
         self._packed = None          # (version key, small block tensor, MpnWeights struct, keepalive list)
+        # small graphs are launch-bound (~30 dependent kernels): replay the forward as one CUDA graph
+        self.use_cuda_graph = True
+        self.cuda_graph_max_edges = 1 << 21
+        self._graphs = {}            # (device, N, E, D, L, n_cls, fused, weights key) -> _GraphedForward
         self.fuse_decisions = False  # when True forward also stores self.last_pred (uint8) / self.last_prob1 (fp32)
         self.last_pred = self.last_prob1 = None
 
@@ -156,6 +227,14 @@ class MOTMPNet(nn.Module):
                   b.bias.detach().contiguous()]
             keep += ts
             W.node_w[i], W.node_b[i], W.node_gamma[i], W.node_beta[i] = (t.data_ptr() for t in ts)
+            if ts[0].numel() % 4 == 0:
+                # TF32 hi/lo planes of the weight, made once per weight version (operands of the 3xTF32 GEMM)
+                hi, lo = torch.empty_like(ts[0]), torch.empty_like(ts[0])
+                with torch.cuda.device(device):
+                    _lib.check(_lib.lib().mpn_split_tf32(ts[0].data_ptr(), ts[0].numel(), hi.data_ptr(), lo.data_ptr(),
+                                                         current_stream_ptr(device)))
+                keep += [hi, lo]
+                W.node_w_hi[i], W.node_w_lo[i] = hi.data_ptr(), lo.data_ptr()
         small = torch.zeros(_lib.W_SMALL_FLOATS, dtype=torch.float32, device=device)
 
         def put(off, t):
@@ -205,20 +284,28 @@ class MOTMPNet(nn.Module):
             raise ValueError("data.edge_attr must be [E,2]")
         L, n_cls = int(self.num_enc_steps), int(self.num_class_steps)
         n_out = 1 if L == 0 else n_cls
-        logits = torch.empty(max(n_out, 1), g.n_edges, 2, dtype=torch.float32, device=dev)
-        h = torch.empty(g.n_nodes, _lib.MPN_DH, dtype=torch.float32, device=dev)
-        pred = prob1 = None
-        if self.fuse_decisions and n_out > 0:
-            pred = torch.empty(g.n_edges, dtype=torch.uint8, device=dev)
-            prob1 = torch.empty(g.n_edges, dtype=torch.float32, device=dev)
-        lib = _lib.lib()
-        need = lib.mpn_forward_workspace_bytes(g.ref, C.byref(W), L)
-        ws = workspace("forward", dev, need)
-        with torch.cuda.device(dev):
-            _lib.check(lib.mpn_forward(g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, logits.data_ptr(),
-                                       h.data_ptr(), pred.data_ptr() if pred is not None else None,
-                                       prob1.data_ptr() if prob1 is not None else None, int(bool(USE_TENSOR_CORES)),
-                                       ws.data_ptr(), ws.numel(), current_stream_ptr(dev)))
+        fused = bool(self.fuse_decisions) and n_out > 0
+        if self.use_cuda_graph and g.n_edges <= self.cuda_graph_max_edges and g.n_edges > 1:
+            key = (dev.index, g.n_nodes, g.n_edges, x.shape[1], L, n_cls, bool(self.fuse_decisions), self._packed[0])
+            ent = self._graphs.get(key)
+            if ent is None:
+                if len(self._graphs) >= 8:
+                    self._graphs.pop(next(iter(self._graphs)))
+                ent = self._graphs[key] = _GraphedForward(W, g, x, ea, L, n_cls, max(n_out, 1), fused)
+            logits, h, pred, prob1 = ent.run(g, x, ea)
+        else:
+            logits = torch.empty(max(n_out, 1), g.n_edges, 2, dtype=torch.float32, device=dev)
+            h = torch.empty(g.n_nodes, _lib.MPN_DH, dtype=torch.float32, device=dev)
+            pred = torch.empty(g.n_edges, dtype=torch.uint8, device=dev) if fused else None
+            prob1 = torch.empty(g.n_edges, dtype=torch.float32, device=dev) if fused else None
+            lib = _lib.lib()
+            need = lib.mpn_forward_workspace_bytes(g.ref, C.byref(W), L)
+            ws = workspace("forward", dev, need)
+            with torch.cuda.device(dev):
+                _lib.check(lib.mpn_forward(g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, logits.data_ptr(),
+                                           h.data_ptr(), pred.data_ptr() if pred is not None else None,
+                                           prob1.data_ptr() if prob1 is not None else None, int(bool(USE_TENSOR_CORES)),
+                                           ws.data_ptr(), ws.numel(), current_stream_ptr(dev)))
         if g.perm is not None:                       # back to the caller's edge order
             inv = torch.empty_like(logits)
             inv[:, g.perm] = logits

@@ -122,7 +122,14 @@ typedef struct mpn_weights {
   const float* node_gamma[MPN_MAX_NODE_LAYERS];   /* dev [out] BatchNorm weight */
   const float* node_beta[MPN_MAX_NODE_LAYERS];    /* dev [out] BatchNorm bias */
   const float* small;                             /* dev [MPN_W_SMALL_FLOATS] */
+  /* optional cache: TF32 hi/lo planes of node_w[i] made by mpn_split_tf32 (NULL -> split on every forward) */
+  const float* node_w_hi[MPN_MAX_NODE_LAYERS];
+  const float* node_w_lo[MPN_MAX_NODE_LAYERS];
 } mpn_weights;
+
+/* x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi): the operand planes of the 3xTF32 tensor-core GEMM.
+ * n must be a multiple of 4, pointers 16-byte aligned. */
+int mpn_split_tf32(const float* x_dev, int64_t n, float* hi_dev, float* lo_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Forward (K1b-K4).  Replaces MOTMPNet.forward (models/mpn.py:250-299) for the supported family:

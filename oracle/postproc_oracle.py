@@ -316,13 +316,15 @@ def planted_prediction_graph(n_nodes: int, num_cameras: int, seed: int, n_extra_
         order = np.argsort(ident, kind="stable")
         grp = ident[order]
         starts = np.flatnonzero(np.r_[True, grp[1:] != grp[:-1]])
-        ends = np.r_[starts[1:], grp.size]
+        sizes = np.diff(np.r_[starts, grp.size])
         ps, pd = [], []
-        for a, b in zip(starts, ends):
-            mem = order[a:b]
-            if mem.size > 1:
-                i, j = np.nonzero(~np.eye(mem.size, dtype=bool))
-                ps.append(mem[i]); pd.append(mem[j])
+        for k in range(2, int(sizes.max()) + 1 if sizes.size else 2):       # vectorised per cluster size (<= num_cameras)
+            st = starts[sizes == k]
+            if st.size == 0:
+                continue
+            mem = order[st[:, None] + np.arange(k)[None, :]]                # [n_clusters_of_size_k, k]
+            i, j = np.nonzero(~np.eye(k, dtype=bool))
+            ps.append(mem[:, i].ravel()); pd.append(mem[:, j].ravel())
         n_extra = int(n_nodes * n_extra_per_node / 2)
         u = rng.integers(0, n_nodes, n_extra); v = rng.integers(0, n_nodes, n_extra)
         ok = cam[u] != cam[v]
