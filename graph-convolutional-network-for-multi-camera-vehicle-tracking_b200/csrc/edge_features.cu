@@ -88,19 +88,39 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
     const size_t grow = (size_t)(row + g.row_offset);
     const double sa = st[4 * grow], xa = st[4 * grow + 1], ma = st[4 * grow + 2], na = st[4 * grow + 3];
     const float* Grow = G + (size_t)(row - r0) * g.n_cols;
-    for (int e = beg + lane; e < end; e += 32) {
-      const size_t c = (size_t)g.col[e];
-      const double gij = Grow[c];
-      const double sb = st[4 * c], xb = st[4 * c + 1], mb = st[4 * c + 2], nb = st[4 * c + 3];
-      double d2 = sa + sb - 2.0 * gij + 2.0 * eps * (xa - xb) + D * eps * eps;
-      if (d2 < (double)REFINE_FRACTION * (sa + sb)) {
-        const int slot = atomicAdd(refine_count, 1);
-        refine_list[slot] = e;
+    constexpr int U = 4;                                   // independent col -> (G, st) gathers in flight per lane
+    for (int base = beg; base < end; base += 32 * U) {
+      int c[U];
+      bool ok[U];
+      float gv[U];
+      double sb[U], xb[U], mb[U], nb[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int e = base + 32 * j + lane;
+        ok[j] = e < end;
+        c[j] = g.col[ok[j] ? e : end - 1];
       }
-      if (d2 < 0.0) d2 = 0.0;
-      const double ab = gij + ma + mb;
-      const float denom = fmaxf((float)(na * nb), COSINE_EPS);
-      edge_attr[e] = make_float2(sqrtf((float)d2), 1.0f - (float)ab / denom);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        gv[j] = Grow[c[j]];
+        const double4 s4 = *reinterpret_cast<const double4*>(st + 4 * (size_t)c[j]);
+        sb[j] = s4.x; xb[j] = s4.y; mb[j] = s4.z; nb[j] = s4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (!ok[j]) continue;
+        const int e = base + 32 * j + lane;
+        const double gij = gv[j];
+        double d2 = sa + sb[j] - 2.0 * gij + 2.0 * eps * (xa - xb[j]) + D * eps * eps;
+        if (d2 < (double)REFINE_FRACTION * (sa + sb[j])) {
+          const int slot = atomicAdd(refine_count, 1);
+          refine_list[slot] = e;
+        }
+        if (d2 < 0.0) d2 = 0.0;
+        const double ab = gij + ma + mb[j];
+        const float denom = fmaxf((float)(na * nb[j]), COSINE_EPS);
+        edge_attr[e] = make_float2(sqrtf((float)d2), 1.0f - (float)ab / denom);
+      }
     }
   }
 }

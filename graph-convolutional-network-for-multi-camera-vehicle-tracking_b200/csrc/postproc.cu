@@ -7,6 +7,8 @@
 // packed (prob bits, edge id) 64-bit atomicMin (ties -> lowest edge id, as torch.argmin over ascending
 // candidates, utils.py:288-289), components use min-id union-find.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <unordered_map>
 #include <vector>
 
@@ -24,6 +26,7 @@ struct PostCtx {
   // device
   int *blockoff, *a_eid, *a_src, *a_dst, *a_rev;
   int *fo, *fi, *label, *size, *od_src, *od_dst, *counters;      // counters[8]
+  int *dirty_nodes, *dirty_edges;                                // SPLIT: nodes of oversized clusters, active-list entries touching them
   unsigned long long *mo, *mi;
   unsigned int *mbits, *hash;
   int hash_cap;
@@ -43,6 +46,8 @@ static void post_layout(PostCtx& c, void* ws, size_t ws_bytes) {
   c.a_rev = a.take<int>(E);
   c.od_src = a.take<int>(E);
   c.od_dst = a.take<int>(E);
+  c.dirty_nodes = a.take<int>(N);
+  c.dirty_edges = a.take<int>(E);
   c.fo = a.take<int>(N);
   c.fi = a.take<int>(N);
   c.label = a.take<int>(N);
@@ -488,30 +493,199 @@ __global__ void split_remove_kernel(int A, const int* __restrict__ a_eid, uint8_
   }
 }
 
+// ---- list-restricted variants: after the first round only the nodes of oversized clusters ("dirty") and the active
+// edges touching them can change the outcome, so every later round works on those two lists only.
+__global__ void mark_dirty_nodes_kernel(int N, const int* __restrict__ label, const int* __restrict__ size, int limit,
+                                        int* __restrict__ list, int* __restrict__ count) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
+    if (size[label[n]] > limit) list[atomicAdd(count, 1)] = n;
+}
+__global__ void mark_dirty_edges_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const int* __restrict__ a_dst,
+                                        const uint8_t* __restrict__ act, const int* __restrict__ label, const int* __restrict__ size,
+                                        int limit, int* __restrict__ list, int* __restrict__ count) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    if (!act[a_eid[i]]) continue;
+    if (size[label[a_src[i]]] > limit || size[label[a_dst[i]]] > limit) list[atomicAdd(count, 1)] = i;
+  }
+}
+__global__ void reset_nodes_kernel(int n_list, const int* __restrict__ list, int* __restrict__ label, int* __restrict__ size,
+                                   unsigned int* __restrict__ mbits, int what) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_list; k += gridDim.x * blockDim.x) {
+    const int n = list[k];
+    if (what & 1) label[n] = n;
+    if (what & 2) size[n] = 0;
+    if (what & 4) mbits[n] = HASH_EMPTY;
+  }
+}
+__global__ void union_mutual_list_kernel(int n_list, const int* __restrict__ list, const int* __restrict__ a_eid,
+                                         const int* __restrict__ a_src, const int* __restrict__ a_dst, const int* __restrict__ a_rev,
+                                         const uint8_t* __restrict__ act, int* __restrict__ parent) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_list; k += gridDim.x * blockDim.x) {
+    const int i = list[k];
+    if (!act[a_eid[i]]) continue;
+    const int u = a_src[i], v = a_dst[i];
+    if (u >= v) continue;
+    const int r = a_rev[i];
+    if (r >= 0 && act[r]) uf_union(parent, u, v);
+  }
+}
+__global__ void flatten_list_kernel(int n_list, const int* __restrict__ list, int* __restrict__ parent) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_list; k += gridDim.x * blockDim.x) {
+    const int n = list[k];
+    int x = n;
+    while (parent[x] != x) x = parent[x];
+    if (x != n) parent[n] = x;
+  }
+}
+__global__ void one_dir_edges_list_kernel(int n_list, const int* __restrict__ list, const int* __restrict__ a_eid,
+                                          const int* __restrict__ a_src, const int* __restrict__ a_dst, const int* __restrict__ a_rev,
+                                          const uint8_t* __restrict__ act, const int* __restrict__ label, const int* __restrict__ is_dirty_size,
+                                          int limit_unused, int* __restrict__ od_src, int* __restrict__ od_dst, int* __restrict__ od_count) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_list; k += gridDim.x * blockDim.x) {
+    const int i = list[k];
+    if (!act[a_eid[i]]) continue;
+    const int r = a_rev[i];
+    if (r >= 0 && act[r]) continue;
+    const int lu = label[a_src[i]], lv = label[a_dst[i]];
+    if (lu == lv) continue;
+    const int slot = atomicAdd(od_count, 1);
+    od_src[slot] = lu;
+    od_dst[slot] = lv;
+  }
+}
+__global__ void comp_size_list_kernel(int n_list, const int* __restrict__ list, const int* __restrict__ label, int* __restrict__ size) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_list; k += gridDim.x * blockDim.x) atomicAdd(&size[label[list[k]]], 1);
+}
+__global__ void split_min_list_kernel(int n_list, const int* __restrict__ list, const int* __restrict__ a_eid, const int* __restrict__ a_src,
+                                      const int* __restrict__ a_dst, const uint8_t* __restrict__ act, const float* __restrict__ prob,
+                                      int pstride, const int* __restrict__ label, const int* __restrict__ size, int limit,
+                                      unsigned int* __restrict__ mbits) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_list; k += gridDim.x * blockDim.x) {
+    const int i = list[k];
+    const int e = a_eid[i];
+    if (!act[e]) continue;
+    const int lu = label[a_src[i]], lv = label[a_dst[i]];
+    const unsigned int pb = __float_as_uint(prob[(size_t)e * pstride]);
+    if (size[lu] > limit) atomicMin(&mbits[lu], pb);
+    if (lv != lu && size[lv] > limit) atomicMin(&mbits[lv], pb);
+  }
+}
+__global__ void split_collect_list_kernel(int n_list, const int* __restrict__ list, const int* __restrict__ label,
+                                          const int* __restrict__ size, int limit, const unsigned int* __restrict__ mbits,
+                                          unsigned int* __restrict__ hash, int cap, int* __restrict__ n_big) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_list; k += gridDim.x * blockDim.x) {
+    const int n = list[k];
+    if (label[n] != n || size[n] <= limit) continue;
+    atomicAdd(n_big, 1);
+    const unsigned int key = mbits[n];
+    if (key == HASH_EMPTY) continue;
+    unsigned int slot = hash_u32(key) & (cap - 1);
+    for (;;) {
+      const unsigned int old = atomicCAS(&hash[slot], HASH_EMPTY, key);
+      if (old == HASH_EMPTY || old == key) break;
+      slot = (slot + 1) & (cap - 1);
+    }
+  }
+}
+
+// SCC restricted to the dirty lists (labels of clean nodes are left alone; they cannot become oversized)
+static int scc_dirty(PostCtx& c, const uint8_t* act, int Dn, int De) {
+  reset_nodes_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.label, c.size, c.mbits, 1);
+  MPN_LAUNCH_OK();
+  MPN_CUDA_OK(cudaMemsetAsync(c.counters + 3, 0, sizeof(int), c.st));
+  if (De > 0) {
+    union_mutual_list_kernel<<<list_grid(De), 256, 0, c.st>>>(De, c.dirty_edges, c.a_eid, c.a_src, c.a_dst, c.a_rev, act, c.label);
+    MPN_LAUNCH_OK();
+  }
+  flatten_list_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.label);
+  MPN_LAUNCH_OK();
+  if (De > 0) {
+    one_dir_edges_list_kernel<<<list_grid(De), 256, 0, c.st>>>(De, c.dirty_edges, c.a_eid, c.a_src, c.a_dst, c.a_rev, act, c.label, c.size,
+                                                             0, c.od_src, c.od_dst, c.counters + 3);
+    MPN_LAUNCH_OK();
+  }
+  int n_od = 0;
+  MPN_CUDA_OK(cudaMemcpyAsync(&n_od, c.counters + 3, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  static const bool dbg = getenv("MPN_POST_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "[scc_dirty] one-directional inter-component edges: %d\n", n_od);
+  if (n_od > 0) {
+    std::vector<int> s(n_od), d(n_od), from, to;
+    MPN_CUDA_OK(cudaMemcpyAsync(s.data(), c.od_src, sizeof(int) * n_od, cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaMemcpyAsync(d.data(), c.od_dst, sizeof(int) * n_od, cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+    host_condensed_scc(s, d, from, to);
+    if (!from.empty()) {
+      const int k = (int)from.size();
+      MPN_CUDA_OK(cudaMemcpyAsync(c.od_src, from.data(), sizeof(int) * k, cudaMemcpyHostToDevice, c.st));
+      MPN_CUDA_OK(cudaMemcpyAsync(c.od_dst, to.data(), sizeof(int) * k, cudaMemcpyHostToDevice, c.st));
+      hook_pairs_kernel<<<list_grid(k), 256, 0, c.st>>>(k, c.od_src, c.od_dst, c.label);
+      MPN_LAUNCH_OK();
+      flatten_list_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.label);
+      MPN_LAUNCH_OK();
+      MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+    }
+  }
+  return MPN_OK;
+}
+
 static int split_stage(PostCtx& c, uint8_t* act, const float* prob, int pstride, int num_cameras, int* rounds) {
   const int A = c.n_active, N = c.g.n_nodes;
   *rounds = 0;
   if (A == 0) return MPN_OK;
+  // round 0 on the whole graph: components, sizes, dirty lists
+  MPN_TRY(scc_stage(c, act, nullptr));
+  MPN_CUDA_OK(cudaMemsetAsync(c.size, 0, sizeof(int) * N, c.st));
+  MPN_CUDA_OK(cudaMemsetAsync(c.counters + 5, 0, 2 * sizeof(int), c.st));
+  comp_size_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, c.size);
+  MPN_LAUNCH_OK();
+  mark_dirty_nodes_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, c.size, num_cameras, c.dirty_nodes, c.counters + 5);
+  MPN_LAUNCH_OK();
+  mark_dirty_edges_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, c.label, c.size, num_cameras, c.dirty_edges,
+                                                         c.counters + 6);
+  MPN_LAUNCH_OK();
+  int h[2] = {0, 0};
+  MPN_CUDA_OK(cudaMemcpyAsync(h, c.counters + 5, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  const int Dn = h[0], De = h[1];
+  static const bool dbg = getenv("MPN_POST_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "[split] A=%d N=%d dirty nodes=%d dirty edges=%d\n", A, N, Dn, De);
+  if (Dn == 0) return MPN_OK;
+  auto t_prev = std::chrono::steady_clock::now();
   for (;;) {
-    MPN_TRY(scc_stage(c, act, nullptr));
-    MPN_CUDA_OK(cudaMemsetAsync(c.size, 0, sizeof(int) * N, c.st));
-    MPN_CUDA_OK(cudaMemsetAsync(c.mbits, 0xFF, sizeof(unsigned int) * N, c.st));
+    if (dbg) {
+      auto t_now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[split] round %d: previous round took %.1f us\n", *rounds, std::chrono::duration<double, std::micro>(t_now - t_prev).count());
+      t_prev = t_now;
+    }
+    // per-cluster minimum probability over the active edges touching each oversized cluster
+    reset_nodes_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.label, c.size, c.mbits, 4);
+    MPN_LAUNCH_OK();
     MPN_CUDA_OK(cudaMemsetAsync(c.hash, 0xFF, sizeof(unsigned int) * c.hash_cap, c.st));
     MPN_CUDA_OK(cudaMemsetAsync(c.counters + 4, 0, sizeof(int), c.st));
-    comp_size_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, c.size);
-    MPN_LAUNCH_OK();
-    split_min_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, prob, pstride, c.label, c.size, num_cameras, c.mbits);
-    MPN_LAUNCH_OK();
-    split_collect_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, c.size, num_cameras, c.mbits, c.hash, c.hash_cap, c.counters + 4);
+    if (De > 0) {
+      split_min_list_kernel<<<list_grid(De), 256, 0, c.st>>>(De, c.dirty_edges, c.a_eid, c.a_src, c.a_dst, act, prob, pstride, c.label,
+                                                           c.size, num_cameras, c.mbits);
+      MPN_LAUNCH_OK();
+    }
+    split_collect_list_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.label, c.size, num_cameras, c.mbits, c.hash,
+                                                              c.hash_cap, c.counters + 4);
     MPN_LAUNCH_OK();
     int n_big = 0;
     MPN_CUDA_OK(cudaMemcpyAsync(&n_big, c.counters + 4, sizeof(int), cudaMemcpyDeviceToHost, c.st));
     MPN_CUDA_OK(cudaStreamSynchronize(c.st));
     if (n_big == 0) break;
     ++*rounds;
+    if (*rounds > A + 1) { set_error("split did not converge"); return MPN_ERR_INVALID; }
+    // every edge anywhere whose probability equals one of the minima (utils.py:96-98)
     split_remove_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, act, prob, pstride, c.hash, c.hash_cap);
     MPN_LAUNCH_OK();
-    if (*rounds > A + 1) { set_error("split did not converge"); return MPN_ERR_INVALID; }
+    // recompute components and sizes of the dirty part only
+    MPN_TRY(scc_dirty(c, act, Dn, De));
+    reset_nodes_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.label, c.size, c.mbits, 2);
+    MPN_LAUNCH_OK();
+    comp_size_list_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.label, c.size);
+    MPN_LAUNCH_OK();
   }
   return MPN_OK;
 }
