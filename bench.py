@@ -256,7 +256,7 @@ def run_ours(args):
         if world == 1:
             g = m.TrackletGraph(ei, n_nodes)                                   # K0
             batch.x, batch.edge_index = x, ei
-            batch._mpn_b200_graph = ((ei.data_ptr(), tuple(ei.shape), ei._version, n_nodes), g)
+            batch._mpn_b200_graph = ((ei.data_ptr(), tuple(ei.shape), ei._version, n_nodes, None), g)
             batch.edge_attr = m.edge_features(x, ei, graph=g)                  # K1
             out, h = net(batch)                                                # K1b..K4 (+ fused decisions)
             return net.last_pred

@@ -27,7 +27,8 @@ class MpnGraph(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_cols", C.c_int32), ("row_offset", C.c_int32), ("chunk", C.c_int32),
                 ("n_edges", C.c_int64), ("max_tasks", C.c_int32), ("reserved", C.c_int32),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("taskptr", C.c_void_p), ("task_row", C.c_void_p),
-                ("n_tasks", C.c_void_p)]
+                ("n_tasks", C.c_void_p), ("n_graphs", C.c_int32), ("reserved2", C.c_int32),
+                ("node_gid", C.c_void_p), ("graph_nptr", C.c_void_p)]
 
 
 class MpnWeights(C.Structure):
@@ -107,7 +108,7 @@ def lib():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.mpn_abi_version() != 1:
+        if l.mpn_abi_version() != 2:
             raise ImportError("libmpn_b200.so ABI version mismatch")
         _lib = l
     return _lib

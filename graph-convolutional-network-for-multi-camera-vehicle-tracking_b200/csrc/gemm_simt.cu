@@ -29,8 +29,8 @@ __device__ __forceinline__ float4 load4(const float* __restrict__ base, int r, i
 template <bool ALIGNED>
 __global__ void __launch_bounds__(GT) gemm_nt_simt_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                           const float* __restrict__ bias, const float* __restrict__ a_scale,
-                                                          const float* __restrict__ a_shift, float* __restrict__ C,
-                                                          int M, int N, int K) {
+                                                          const float* __restrict__ a_shift, const int* __restrict__ row_gid,
+                                                          float* __restrict__ C, int M, int N, int K) {
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -43,10 +43,13 @@ __global__ void __launch_bounds__(GT) gemm_nt_simt_kernel(const float* __restric
     float4 v = load4<ALIGNED>(A, m0 + lr, M, k0 + lk, K, K);
     if (a_scale != nullptr) {
       const int k = k0 + lk;
-      if (k + 0 < K) v.x = fmaxf(fmaf(v.x, a_scale[k + 0], a_shift[k + 0]), 0.f);
-      if (k + 1 < K) v.y = fmaxf(fmaf(v.y, a_scale[k + 1], a_shift[k + 1]), 0.f);
-      if (k + 2 < K) v.z = fmaxf(fmaf(v.z, a_scale[k + 2], a_shift[k + 2]), 0.f);
-      if (k + 3 < K) v.w = fmaxf(fmaf(v.w, a_scale[k + 3], a_shift[k + 3]), 0.f);
+      const int m = min(m0 + lr, M - 1);
+      const float* sc = a_scale + (row_gid ? (size_t)row_gid[m] * K : 0);     // per-graph BatchNorm (batched graphs)
+      const float* sh = a_shift + (row_gid ? (size_t)row_gid[m] * K : 0);
+      if (k + 0 < K) v.x = fmaxf(fmaf(v.x, sc[k + 0], sh[k + 0]), 0.f);
+      if (k + 1 < K) v.y = fmaxf(fmaf(v.y, sc[k + 1], sh[k + 1]), 0.f);
+      if (k + 2 < K) v.z = fmaxf(fmaf(v.z, sc[k + 2], sh[k + 2]), 0.f);
+      if (k + 3 < K) v.w = fmaxf(fmaf(v.w, sc[k + 3], sh[k + 3]), 0.f);
       if (m0 + lr >= M) v = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     return v;
@@ -90,14 +93,14 @@ __global__ void __launch_bounds__(GT) gemm_nt_simt_kernel(const float* __restric
 }
 
 int gemm_nt_simt(const float* A, const float* B, const float* bias, const float* a_scale, const float* a_shift, float* C,
-                 int M, int N, int K, cudaStream_t st) {
+                 int M, int N, int K, cudaStream_t st, const int* row_gid) {
   MPN_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %d x %d x %d", M, N, K);
   dim3 grid(div_up(N, BN), div_up(M, BM));
   const bool aligned = (K % 4 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
   if (aligned)
-    gemm_nt_simt_kernel<true><<<grid, GT, 0, st>>>(A, B, bias, a_scale, a_shift, C, M, N, K);
+    gemm_nt_simt_kernel<true><<<grid, GT, 0, st>>>(A, B, bias, a_scale, a_shift, row_gid, C, M, N, K);
   else
-    gemm_nt_simt_kernel<false><<<grid, GT, 0, st>>>(A, B, bias, a_scale, a_shift, C, M, N, K);
+    gemm_nt_simt_kernel<false><<<grid, GT, 0, st>>>(A, B, bias, a_scale, a_shift, row_gid, C, M, N, K);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }

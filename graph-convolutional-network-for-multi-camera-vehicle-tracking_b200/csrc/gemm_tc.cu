@@ -253,14 +253,16 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
 // x -> (hi, lo) TF32 planes.  Optional fused input transform f(x)[m,k] = relu(x*scale[k] + shift[k]): the BatchNorm+ReLU of
 // the previous encoder layer (models/mlp.py:14-19), so the activation is never re-written in fp32.
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, long long n4, int K, const float* __restrict__ scale,
-                                                         const float* __restrict__ shift, float4* __restrict__ hi, float4* __restrict__ lo) {
+                                                         const float* __restrict__ shift, const int* __restrict__ row_gid,
+                                                         float4* __restrict__ hi, float4* __restrict__ lo) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = x[i];
     float in[4] = {v.x, v.y, v.z, v.w};
     if (scale != nullptr) {
       const int k = (int)((i * 4) % K);                 // K % 4 == 0: the four lanes stay inside one row
-      const float4 sc = *reinterpret_cast<const float4*>(scale + k), sh = *reinterpret_cast<const float4*>(shift + k);
+      const size_t o = (row_gid ? (size_t)row_gid[(i * 4) / K] * K : 0) + k;          // per-graph BatchNorm (batched graphs)
+      const float4 sc = *reinterpret_cast<const float4*>(scale + o), sh = *reinterpret_cast<const float4*>(shift + o);
       in[0] = fmaxf(fmaf(in[0], sc.x, sh.x), 0.f);
       in[1] = fmaxf(fmaf(in[1], sc.y, sh.y), 0.f);
       in[2] = fmaxf(fmaf(in[2], sc.z, sh.z), 0.f);
@@ -313,7 +315,7 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int K, int bo
 int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t st) {
   MPN_REQUIRE(x && hi && lo && n > 0 && (n % 4) == 0, "split_tf32: bad arguments (n must be a positive multiple of 4)");
   MPN_REQUIRE((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "split_tf32: pointers must be 16-byte aligned");
-  split_tf32_kernel<<<(int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256), 256, 0, st>>>((const float4*)x, n / 4, 4, nullptr, nullptr, (float4*)hi, (float4*)lo);
+  split_tf32_kernel<<<(int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256), 256, 0, st>>>((const float4*)x, n / 4, 4, nullptr, nullptr, nullptr, (float4*)hi, (float4*)lo);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -342,7 +344,8 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
 }
 
 int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-               cudaStream_t st, const float* a_scale, const float* a_shift, const float* b_hi_cached, const float* b_lo_cached) {
+               cudaStream_t st, const float* a_scale, const float* a_shift, const float* b_hi_cached, const float* b_lo_cached,
+               const int* row_gid) {
   MPN_REQUIRE(gemm_tc_supported(M, N, K), "tcgen05 GEMM: unsupported shape %d x %d x %d", M, N, K);
   MPN_REQUIRE(ws && ws_bytes >= gemm_tc_workspace_bytes(M, N, K), "tcgen05 GEMM: workspace too small");
   MPN_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "tcgen05 GEMM: operands must be 16-byte aligned");
@@ -357,7 +360,7 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
     b_hi = (float*)b_hi_cached;
     b_lo = (float*)b_lo_cached;
   } else {
-    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)B, (long long)N * K / 4, K, nullptr, nullptr, (float4*)b_hi, (float4*)b_lo);
+    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)B, (long long)N * K / 4, K, nullptr, nullptr, nullptr, (float4*)b_hi, (float4*)b_lo);
     MPN_LAUNCH_OK();
   }
   if (a_scale == nullptr && A >= B && A + (size_t)M * K <= B + (size_t)N * K) {      // A is a row block of B (Gram matrix): share the planes
@@ -366,7 +369,7 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
   } else {
     a_hi = (float*)(w + 2 * plane_b);
     a_lo = (float*)(w + 2 * plane_b + plane_a);
-    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, K, a_scale, a_shift, (float4*)a_hi, (float4*)a_lo);
+    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, K, a_scale, a_shift, row_gid, (float4*)a_hi, (float4*)a_lo);
     MPN_LAUNCH_OK();
   }
   CUtensorMap ah, al, bh, bl;

@@ -8,14 +8,15 @@ namespace mpn {
 
 // gemm_simt.cu
 int gemm_nt_simt(const float* A, const float* B, const float* bias, const float* a_scale, const float* a_shift,
-                 float* C, int M, int N, int K, cudaStream_t st);
+                 float* C, int M, int N, int K, cudaStream_t st, const int* row_gid = nullptr);
 
 // gemm_tc.cu  (tcgen05 3xTF32; operands are pre-split hi/lo planes)
 size_t gemm_tc_workspace_bytes(int M, int N, int K);
 // a_scale/a_shift (optional, [K]): A is read as relu(A*scale + shift) while it is split (fused BatchNorm+ReLU)
 int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
                void* workspace, size_t workspace_bytes, cudaStream_t st, const float* a_scale = nullptr,
-               const float* a_shift = nullptr, const float* b_hi_cached = nullptr, const float* b_lo_cached = nullptr);
+               const float* a_shift = nullptr, const float* b_hi_cached = nullptr, const float* b_lo_cached = nullptr,
+               const int* row_gid = nullptr);   // row_gid: a_scale/a_shift are [n_graphs][K] tables indexed by the row's graph
 int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t st);
 bool gemm_tc_supported(int M, int N, int K);
 

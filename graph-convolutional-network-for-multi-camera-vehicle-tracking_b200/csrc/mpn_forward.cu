@@ -48,6 +48,14 @@ __device__ __forceinline__ void load_consts(EdgeConsts& sc, const float* __restr
   __syncthreads();
 }
 
+// batched graphs: every graph has its own folded constants; a warp re-stages them when its task moves to another graph
+constexpr int TASK_PART = 16;                  // doubles per task in the per-task moment partials (batched mode)
+__device__ __forceinline__ void warp_load_consts(EdgeConsts& sc, const float* __restrict__ consts_g, int lane) {
+  __syncwarp();
+  for (int i = lane; i < FC_TOTAL; i += 32) sc.v[i] = consts_g[i];
+  __syncwarp();
+}
+
 // encoder edge MLP with folded BatchNorm: 2 -> 4 -> 4, ReLU after each (models/mpn.py:128-142)
 __device__ __forceinline__ void enc_layer1(const EdgeConsts& sc, float2 ea, float (&a1)[4]) {
 #pragma unroll
@@ -311,22 +319,30 @@ __device__ __forceinline__ void load_edges(EdgeLoad<U>& L, const mpn_graph& g, i
 // SA: moments of the edge-update pre-activation y (and optionally materialise y)
 //   SRC 0: e_in = encoder(edge_attr[e])            (step 1)
 //   SRC 1: e_in = relu(BN3_prev(ybuf[e]))          (step >= 2; ybuf updated in place)
-template <int SRC, bool WRITE_Y>
+template <int SRC, bool WRITE_Y, bool BATCHED>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                                      const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                                      float4* __restrict__ ybuf, const float* __restrict__ consts,
                                                                      double* __restrict__ partials, const FinArgs fin) {
   constexpr int U = 4;
-  __shared__ EdgeConsts sc;
+  __shared__ EdgeConsts scs[BATCHED ? SWEEP_THREADS / 32 : 1];
   __shared__ double red[(SWEEP_THREADS / 32) * 8];
-  load_consts(sc, consts);
   const int lane = threadIdx.x & 31;
+  EdgeConsts& sc = scs[BATCHED ? (threadIdx.x >> 5) : 0];
+  if (!BATCHED) load_consts(sc, consts);
   const int gwarp = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * SWEEP_THREADS) >> 5;
   const int n_tasks = *g.n_tasks;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int cur_gid = -1;
   for (int t = gwarp; t < n_tasks; t += nwarps) {
     const TaskRange tr = task_range(g, t);
+    if (BATCHED) {
+      const int gid = g.node_gid[tr.row];
+      if (gid != cur_gid) { warp_load_consts(sc, consts + (size_t)gid * FC_TOTAL, lane); cur_gid = gid; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+    }
     const float4 ps = Ps[tr.row];
     for (int base = tr.beg; base < tr.end; base += 32 * U) {
       EdgeLoad<U> L;
@@ -348,9 +364,18 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mp
         }
       }
     }
+    if (BATCHED) {                                         // per-task partial, reduced per graph in fixed task order
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) partials[(size_t)t * TASK_PART + k] = v;
+      }
+    }
   }
-  block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
-  finalize_in_last_block(fin);
+  if (!BATCHED) {
+    block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
+    finalize_in_last_block(fin);
+  }
 }
 
 // e' = relu(BN3(y)) for one loaded edge
@@ -369,22 +394,28 @@ __device__ __forceinline__ void eprime_of(const EdgeConsts& sc, const float4 ps,
 }
 
 // SB: per-task S1 = sum e' (for the closed-form node-BN moments), global T2 = sum e' e'^T
-template <int YSRC>
+template <int YSRC, bool BATCHED>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                                            const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                                            const float4* __restrict__ ybuf, const float* __restrict__ consts,
                                                                            float4* __restrict__ s1_task, double* __restrict__ partials) {
   constexpr int U = 4;
-  __shared__ EdgeConsts sc;
+  __shared__ EdgeConsts scs[BATCHED ? SWEEP_THREADS / 32 : 1];
   __shared__ double red[(SWEEP_THREADS / 32) * 10];
-  load_consts(sc, consts);
   const int lane = threadIdx.x & 31;
+  EdgeConsts& sc = scs[BATCHED ? (threadIdx.x >> 5) : 0];
+  if (!BATCHED) load_consts(sc, consts);
   const int gwarp = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * SWEEP_THREADS) >> 5;
   const int n_tasks = *g.n_tasks;
   double t2[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int cur_gid = -1;
   for (int t = gwarp; t < n_tasks; t += nwarps) {
     const TaskRange tr = task_range(g, t);
+    if (BATCHED) {
+      const int gid = g.node_gid[tr.row];
+      if (gid != cur_gid) { warp_load_consts(sc, consts + (size_t)gid * FC_TOTAL, lane); cur_gid = gid; }
+    }
     const float4 ps = (YSRC == 0) ? Ps[tr.row] : make_float4(0.f, 0.f, 0.f, 0.f);
     float s1[4] = {0.f, 0.f, 0.f, 0.f};
     float q[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -409,9 +440,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
     for (int a = 0; a < 4; ++a) s1[a] = warp_sum(s1[a]);
     if (lane == 0) s1_task[t] = make_float4(s1[0], s1[1], s1[2], s1[3]);
 #pragma unroll
-    for (int i = 0; i < 10; ++i) t2[i] += (double)q[i];      // <= chunk/32 fp32 terms per lane, then fp64
+    for (int i = 0; i < 10; ++i) {
+      if (BATCHED) {
+        const double v = warp_sum((double)q[i]);
+        if (lane == 0) partials[(size_t)t * TASK_PART + i] = v;
+      } else {
+        t2[i] += (double)q[i];                              // <= chunk/32 fp32 terms per lane, then fp64
+      }
+    }
   }
-  block_sum_doubles<10, SWEEP_THREADS>(t2, red, partials + (size_t)blockIdx.x * SUMS + 64);
+  if (!BATCHED) block_sum_doubles<10, SWEEP_THREADS>(t2, red, partials + (size_t)blockIdx.x * SUMS + 64);
 }
 
 // per-node part of the closed-form node-BN moments:
@@ -520,7 +558,7 @@ __device__ __forceinline__ void classify_store(const EdgeConsts& sc, const float
   if (prob1) prob1[e] = softmax1(l0, l1);
 }
 
-template <int YSRC, bool CLASSIFY>
+template <int YSRC, bool CLASSIFY, bool BATCHED>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                               const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                               const float4* __restrict__ ybuf, const float* __restrict__ A,
@@ -528,21 +566,40 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph
                                                               float2* __restrict__ logits, uint8_t* __restrict__ pred,
                                                               float* __restrict__ prob1) {
   constexpr int U = 2;
-  __shared__ EdgeConsts sc;
-  __shared__ __align__(16) f32x2 w2s[16][4];                  // folded node weights as channel pairs: (w[2p][k], w[2p+1][k])
-  load_consts(sc, consts);
-  if (threadIdx.x < 64) {
-    const int p = threadIdx.x >> 2, k = threadIdx.x & 3;
-    w2s[p][k] = pack2(sc.v[FC_NODE_WE + 4 * (2 * p) + k], sc.v[FC_NODE_WE + 4 * (2 * p + 1) + k]);
-  }
-  __syncthreads();
-  const uint32_t w2_addr = (uint32_t)__cvta_generic_to_shared(&w2s[0][0]);
+  constexpr int NW = BATCHED ? SWEEP_THREADS / 32 : 1;
+  __shared__ EdgeConsts scs[NW];
+  __shared__ __align__(16) f32x2 w2s_all[NW][16][4];          // folded node weights as channel pairs: (w[2p][k], w[2p+1][k])
   const int lane = threadIdx.x & 31;
+  EdgeConsts& sc = scs[BATCHED ? (threadIdx.x >> 5) : 0];
+  f32x2 (*w2s)[4] = w2s_all[BATCHED ? (threadIdx.x >> 5) : 0];
+  if (!BATCHED) {
+    load_consts(sc, consts);
+    if (threadIdx.x < 64) {
+      const int p = threadIdx.x >> 2, k = threadIdx.x & 3;
+      w2s[p][k] = pack2(sc.v[FC_NODE_WE + 4 * (2 * p) + k], sc.v[FC_NODE_WE + 4 * (2 * p + 1) + k]);
+    }
+    __syncthreads();
+  }
+  const uint32_t w2_addr = (uint32_t)__cvta_generic_to_shared(&w2s[0][0]);
   const int gwarp = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * SWEEP_THREADS) >> 5;
   const int n_tasks = *g.n_tasks;
+  int cur_gid = -1;
   for (int t = gwarp; t < n_tasks; t += nwarps) {
     const TaskRange tr = task_range(g, t);
+    if (BATCHED) {
+      const int gid = g.node_gid[tr.row];
+      if (gid != cur_gid) {
+        warp_load_consts(sc, consts + (size_t)gid * FC_TOTAL, lane);
+#pragma unroll
+        for (int i = lane; i < 64; i += 32) {
+          const int p = i >> 2, k = i & 3;
+          w2s[p][k] = pack2(sc.v[FC_NODE_WE + 4 * (2 * p) + k], sc.v[FC_NODE_WE + 4 * (2 * p + 1) + k]);
+        }
+        __syncwarp();
+        cur_gid = gid;
+      }
+    }
     const float4 ps = (YSRC == 0) ? Ps[tr.row] : make_float4(0.f, 0.f, 0.f, 0.f);
     // folded A'[c] = s4[c]*A[row,c] + t4[c]; lane c computes it, every lane needs all 32 (as 16 packed pairs)
     const float a_mine = fmaf(sc.v[FC_BN4_S + lane], A[(size_t)tr.row * MPN_DH + lane], sc.v[FC_BN4_T + lane]);
@@ -597,6 +654,139 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph
     for (int p = 0; p < 16; ++p) unpack2(acc[p], accf[2 * p], accf[2 * p + 1]);
     const float total = transpose_reduce32(accf, lane);
     msg_task[(size_t)t * MPN_DH + lane] = total;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched small graphs (BASELINE configs[2]): one launch over all graphs, BatchNorm statistics per graph.
+// Moment sweeps write one partial per task; a block per graph adds its tasks in task order (deterministic) and folds
+// that graph's constants.  Graphs are contiguous in node, task and edge order.
+// ------------------------------------------------------------------------------------------------
+template <int STAGE>
+__global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_task_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
+                                                                         const float* __restrict__ consts, const float* __restrict__ small,
+                                                                         double* __restrict__ task_part) {
+  __shared__ EdgeConsts scs[SWEEP_THREADS / 32];
+  __shared__ float w2raw[20];
+  if (threadIdx.x < 16) w2raw[threadIdx.x] = small[MPN_W_ENC2_W + threadIdx.x];
+  else if (threadIdx.x < 20) w2raw[threadIdx.x] = small[MPN_W_ENC2_B + threadIdx.x - 16];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  EdgeConsts& sc = scs[threadIdx.x >> 5];
+  const int gwarp = (blockIdx.x * SWEEP_THREADS + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * SWEEP_THREADS) >> 5;
+  const int n_tasks = *g.n_tasks;
+  int cur_gid = -1;
+  for (int t = gwarp; t < n_tasks; t += nwarps) {
+    const TaskRange tr = task_range(g, t);
+    if (STAGE == 1) {
+      const int gid = g.node_gid[tr.row];
+      if (gid != cur_gid) { warp_load_consts(sc, consts + (size_t)gid * FC_TOTAL, lane); cur_gid = gid; }
+    }
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int e = tr.beg + lane; e < tr.end; e += 32) {
+      const float2 ea = ldg_stream2(edge_attr + e);
+      if (STAGE == 0) {
+        const double a = ea.x, b = ea.y;
+        acc[0] += a; acc[1] += b; acc[2] += a * a; acc[3] += a * b; acc[4] += b * b;
+      } else {
+        float a1[4], u[4];
+        enc_layer1(sc, ea, a1);
+        enc_layer2_pre(w2raw, w2raw + 16, a1, u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const double d = u[k]; acc[k] += d; acc[4 + k] += d * d; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double v = warp_sum(acc[k]);
+      if (lane == 0) task_part[(size_t)t * TASK_PART + k] = v;
+    }
+  }
+}
+
+// one block (128 threads) per graph: task partials -> sums[g] -> consts[g]
+__global__ void __launch_bounds__(128) graph_finalize_kernel(int stage, const mpn_graph g, const double* __restrict__ task_part,
+                                                             const float* __restrict__ A, const float4* __restrict__ s1_task,
+                                                             const float* __restrict__ small, double* __restrict__ sums_all,
+                                                             float* __restrict__ consts_all) {
+  __shared__ double red[4][64];
+  const int gi = blockIdx.x;
+  const int n0 = g.graph_nptr[gi], n1 = g.graph_nptr[gi + 1];
+  const int t0 = g.taskptr[n0], t1 = g.taskptr[n1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sums = sums_all + (size_t)gi * SUMS;
+  const int ncols = (stage == MPN_STAGE_NODE) ? 10 : 8;
+  const int cbase = (stage == MPN_STAGE_NODE) ? 64 : 0;
+  for (int col = warp; col < ncols; col += 4) {                 // warp per column, lanes stride the graph's tasks
+    double v = 0.0;
+    for (int t = t0 + lane; t < t1; t += 32) v += task_part[(size_t)t * TASK_PART + col];
+    v = warp_sum(v);
+    if (lane == 0) sums[cbase + col] = v;
+  }
+  if (stage == MPN_STAGE_NODE) {                                // closed-form per-node part (lane = channel)
+    float w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = small[MPN_W_NODE_W + lane * 36 + 32 + k];
+    double m1 = 0.0, m2 = 0.0;
+    for (int n = n0 + warp; n < n1; n += 4) {
+      const int deg = g.rowptr[n + 1] - g.rowptr[n];
+      if (deg == 0) continue;
+      double sv[4] = {0, 0, 0, 0};
+      for (int t = g.taskptr[n]; t < g.taskptr[n + 1]; ++t) {
+        const float4 v = s1_task[t];
+        sv[0] += v.x; sv[1] += v.y; sv[2] += v.z; sv[3] += v.w;
+      }
+      const double a = A[(size_t)n * MPN_DH + lane];
+      const double qd = w[0] * sv[0] + w[1] * sv[1] + w[2] * sv[2] + w[3] * sv[3];
+      m1 += deg * a + qd;
+      m2 += deg * a * a + 2.0 * a * qd;
+    }
+    red[warp][lane] = m1;
+    red[warp][32 + lane] = m2;
+    __syncthreads();
+    if (threadIdx.x < 64) sums[threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+  }
+  __syncthreads();
+  FinArgs f;
+  f.stage = stage;
+  f.partials = nullptr; f.n_partials = 0; f.partials2 = nullptr; f.n_partials2 = 0;
+  f.sums = sums;
+  f.consts = consts_all + (size_t)gi * FC_TOTAL;
+  f.small = small;
+  f.n_total = (double)(g.rowptr[n1] - g.rowptr[n0]);
+  f.counter = nullptr;
+  finalize_body(f, 0, 1);
+}
+
+// per-graph column statistics of the node-encoder activations: grid (32-column tiles, graphs) -> scale/shift [G][Nc]
+__global__ void __launch_bounds__(256) colstats_graph_kernel(const float* __restrict__ Y, int Nc, const int* __restrict__ graph_nptr,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double ssum[8][33], ssq[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const int gi = blockIdx.y;
+  const int r0 = graph_nptr[gi], r1 = graph_nptr[gi + 1];
+  double s = 0.0, q = 0.0;
+  if (col < Nc)
+    for (int r = r0 + ry; r < r1; r += 8) {
+      const double v = Y[(size_t)r * Nc + col];
+      s += v;
+      q += v * v;
+    }
+  ssum[ry][cx] = s;
+  ssq[ry][cx] = q;
+  __syncthreads();
+  if (ry == 0 && col < Nc) {
+    for (int i = 1; i < 8; ++i) { s += ssum[i][cx]; q += ssq[i][cx]; }
+    const int M = r1 - r0;
+    const double mean = s / M;
+    double var = q / M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double sc = (double)gamma[col] / sqrt(var + (double)BN_EPS);
+    scale[(size_t)gi * Nc + col] = (float)sc;
+    shift[(size_t)gi * Nc + col] = (float)((double)beta[col] - sc * mean);
   }
 }
 
@@ -688,11 +878,12 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
 }
 
 __global__ void bn_relu_apply_kernel(const float* __restrict__ Y, long long total, int Nc, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, float* __restrict__ out) {
+                                     const float* __restrict__ shift, const int* __restrict__ row_gid, float* __restrict__ out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int c = (int)(i % Nc);
-    out[i] = fmaxf(fmaf(Y[i], scale[c], shift[c]), 0.f);
+    const size_t o = row_gid ? (size_t)row_gid[i / Nc] * Nc + c : (size_t)c;
+    out[i] = fmaxf(fmaf(Y[i], scale[o], shift[o]), 0.f);
   }
 }
 
@@ -773,6 +964,8 @@ struct mpn_fwd_plan {
   unsigned int* fin_counter;
   unsigned int* col_counter;   // [max_dim/32 + 1] ticket counters of the column-statistics tiles
   int fuse_fin;               // single-GPU: the last block of each moment sweep folds the constants itself
+  int n_graphs;               // > 1: batched small graphs, BatchNorm statistics per graph
+  double* task_part;          // [max_tasks][TASK_PART] per-task moment partials (batched)
   void* gemm_ws;
   size_t gemm_ws_bytes;
 };
@@ -785,19 +978,22 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.max_dim = max_dim;
   p.act0 = a.take<float>((size_t)g.n_cols * max_dim);
   p.act1 = a.take<float>((size_t)g.n_cols * max_dim);
-  p.colscale = a.take<float>(max_dim > 0 ? max_dim : 1);
-  p.colshift = a.take<float>(max_dim > 0 ? max_dim : 1);
+  const size_t G = (g.n_graphs > 1 && g.node_gid && g.graph_nptr) ? (size_t)g.n_graphs : 1;
+  p.n_graphs = (int)G;
+  p.colscale = a.take<float>(G * (max_dim > 0 ? max_dim : 1));      // [G][Nc] tables when batched
+  p.colshift = a.take<float>(G * (max_dim > 0 ? max_dim : 1));
   p.colpart = a.take<double>((size_t)CS_ROWSPLIT_MAX * (max_dim > 0 ? max_dim : 1) * 2);
   p.h_full = a.take<float>((size_t)g.n_cols * MPN_DH);
   p.Ps = a.take<float>((size_t)g.n_nodes * 4);
   p.Pd = a.take<float>((size_t)g.n_cols * 4);
   p.A = a.take<float>((size_t)g.n_nodes * MPN_DH);
-  p.consts = a.take<float>(FC_TOTAL);
+  p.consts = a.take<float>(G * FC_TOTAL);
+  p.task_part = (G > 1) ? a.take<double>((size_t)g.max_tasks * TASK_PART) : nullptr;
   p.s1_task = a.take<float>((size_t)g.max_tasks * 4);
   p.msg_task = a.take<float>((size_t)g.max_tasks * MPN_DH);
   p.partials = a.take<double>((size_t)SWEEP_GRID * SUMS);
   p.partials2 = a.take<double>((size_t)NM_GRID * SUMS);
-  p.sums = a.take<double>(SUMS);
+  p.sums = a.take<double>(G * SUMS);
   p.fin_counter = a.take<unsigned int>(1);
   p.col_counter = a.take<unsigned int>((size_t)(max_dim > 0 ? max_dim : 1) / 32 + 1);
   p.ybuf = (p.L > 1) ? a.take<float>((size_t)g.n_edges * 4) : nullptr;
@@ -884,6 +1080,7 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
   MPN_REQUIRE(p && x, "node_encoder: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int M = p->g.n_cols;
+  const bool batched = p->n_graphs > 1;
   MPN_CUDA_OK(cudaMemsetAsync(p->col_counter, 0, sizeof(unsigned int) * ((size_t)p->max_dim / 32 + 1), st));
   const float* in = x;
   float* bufs[2] = {p->act0, p->act1};
@@ -892,24 +1089,30 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
     const int K = p->w.node_dims[l], Nc = p->w.node_dims[l + 1];
     float* out = bufs[l & 1];
     bool done = false;
+    const int* gid = batched ? p->g.node_gid : nullptr;        // per-graph BatchNorm tables [G][K] when batched
     if (p->use_tc && gemm_tc_supported(M, Nc, K)) {
       // tensor-core path: BatchNorm+ReLU of the previous layer is applied while the operand is split into TF32 planes
       MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh,
-                         p->w.node_w_hi[l], p->w.node_w_lo[l]));
+                         p->w.node_w_hi[l], p->w.node_w_lo[l], gid));
       done = true;
     }
-    if (!done) MPN_TRY(gemm_nt_simt(in, p->w.node_w[l], p->w.node_b[l], sc, sh, out, M, Nc, K, st));
-    int splits = div_up(M, 256);
-    splits = splits > CS_ROWSPLIT_MAX ? CS_ROWSPLIT_MAX : splits;
-    const int rps = div_up(M, splits);
-    colstats_kernel<<<dim3(div_up(Nc, 32), splits), 256, 0, st>>>(out, M, Nc, rps, p->colpart, p->col_counter, p->w.node_gamma[l],
-                                                                  p->w.node_beta[l], p->colscale, p->colshift);
+    if (!done) MPN_TRY(gemm_nt_simt(in, p->w.node_w[l], p->w.node_b[l], sc, sh, out, M, Nc, K, st, gid));
+    if (batched) {
+      colstats_graph_kernel<<<dim3(div_up(Nc, 32), p->n_graphs), 256, 0, st>>>(out, Nc, p->g.graph_nptr, p->w.node_gamma[l],
+                                                                              p->w.node_beta[l], p->colscale, p->colshift);
+    } else {
+      int splits = div_up(M, 256);
+      splits = splits > CS_ROWSPLIT_MAX ? CS_ROWSPLIT_MAX : splits;
+      const int rps = div_up(M, splits);
+      colstats_kernel<<<dim3(div_up(Nc, 32), splits), 256, 0, st>>>(out, M, Nc, rps, p->colpart, p->col_counter, p->w.node_gamma[l],
+                                                                    p->w.node_beta[l], p->colscale, p->colshift);
+    }
     MPN_LAUNCH_OK();
     in = out;
     sc = p->colscale;
     sh = p->colshift;
   }
-  bn_relu_apply_kernel<<<min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st>>>(in, (long long)M * MPN_DH, MPN_DH, sc, sh, p->h_full);
+  bn_relu_apply_kernel<<<min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st>>>(in, (long long)M * MPN_DH, MPN_DH, sc, sh, batched ? p->g.node_gid : nullptr, p->h_full);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -932,6 +1135,51 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
   const bool stored = p->L > 1;           // y materialised in ybuf for multi-step runs
   const bool fused = p->fuse_fin != 0;
   const int flat_grid = (int)min((long long)SWEEP_GRID, (long long)div_up(g.n_edges > 0 ? g.n_edges : 1, SWEEP_THREADS));
+  const bool batched = p->n_graphs > 1;
+  const float4 *Ps4 = (const float4*)p->Ps, *Pd4 = (const float4*)p->Pd;
+  float4* yb = (float4*)p->ybuf;
+  if (batched) {
+    // per-graph statistics: task-partial moments, then one block per graph reduces + folds (graph_finalize_kernel)
+    double* tp = p->task_part;
+    switch (stage) {
+      case MPN_STAGE_ENC0:
+        enc_moments_task_kernel<0><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, p->consts, p->w.small, tp);
+        break;
+      case MPN_STAGE_ENC1:
+        enc_moments_task_kernel<1><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, p->consts, p->w.small, tp);
+        break;
+      case MPN_STAGE_EDGE:
+        if (step == 1) {
+          if (stored) edge_moments_kernel<0, true, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
+          else edge_moments_kernel<0, false, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, tp, make_fin(p, stage, false));
+        } else {
+          edge_moments_kernel<1, true, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
+        }
+        break;
+      case MPN_STAGE_NODE:
+        if (stored) node_moments_sweep_kernel<1, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, tp);
+        else node_moments_sweep_kernel<0, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, tp);
+        break;
+      case MPN_STAGE_APPLY: {
+        const bool classify = logits_out != nullptr;
+        float2* lg = (float2*)logits_out;
+        MPN_REQUIRE(p->L > 0, "batched graphs need num_enc_steps >= 1");
+#define MPN_APPLY_B(YS, CL) apply_kernel<YS, CL, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+        if (stored) { if (classify) MPN_APPLY_B(1, true); else MPN_APPLY_B(1, false); }
+        else        { if (classify) MPN_APPLY_B(0, true); else MPN_APPLY_B(0, false); }
+#undef MPN_APPLY_B
+        break;
+      }
+      default:
+        MPN_REQUIRE(false, "unknown stage %d", stage);
+    }
+    MPN_LAUNCH_OK();
+    if (stage != MPN_STAGE_APPLY) {
+      graph_finalize_kernel<<<p->n_graphs, 128, 0, st>>>(stage, g, tp, p->A, (const float4*)p->s1_task, p->w.small, p->sums, p->consts);
+      MPN_LAUNCH_OK();
+    }
+    return MPN_OK;
+  }
   switch (stage) {
     case MPN_STAGE_ENC0:
       MPN_CUDA_OK(cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st));
@@ -943,15 +1191,15 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
       break;
     case MPN_STAGE_EDGE:
       if (step == 1) {
-        if (stored) edge_moments_kernel<0, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (float4*)p->ybuf, p->consts, p->partials, make_fin(p, stage, fused));
-        else edge_moments_kernel<0, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, nullptr, p->consts, p->partials, make_fin(p, stage, fused));
+        if (stored) edge_moments_kernel<0, true, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
+        else edge_moments_kernel<0, false, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, p->partials, make_fin(p, stage, fused));
       } else {
-        edge_moments_kernel<1, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (float4*)p->ybuf, p->consts, p->partials, make_fin(p, stage, fused));
+        edge_moments_kernel<1, true, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
       }
       break;
     case MPN_STAGE_NODE:
-      if (stored) node_moments_sweep_kernel<1><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (const float4*)p->ybuf, p->consts, (float4*)p->s1_task, p->partials);
-      else node_moments_sweep_kernel<0><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, nullptr, p->consts, (float4*)p->s1_task, p->partials);
+      if (stored) node_moments_sweep_kernel<1, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, p->partials);
+      else node_moments_sweep_kernel<0, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, p->partials);
       MPN_LAUNCH_OK();
       node_moments_node_kernel<<<NM_GRID, NM_THREADS, 0, st>>>(g, p->A, (const float4*)p->s1_task, p->w.small, p->partials2, make_fin(p, stage, fused));
       break;
@@ -963,7 +1211,7 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
         classify_encoded_kernel<<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, lg, pred_out, prob1_out);
         break;
       }
-#define MPN_APPLY(YS, CL) apply_kernel<YS, CL><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, (const float4*)p->Ps, (const float4*)p->Pd, (const float4*)p->ybuf, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_APPLY(YS, CL) apply_kernel<YS, CL, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
       if (stored) { if (classify) MPN_APPLY(1, true); else MPN_APPLY(1, false); }
       else        { if (classify) MPN_APPLY(0, true); else MPN_APPLY(0, false); }
 #undef MPN_APPLY
@@ -979,6 +1227,7 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
 int mpn_plan_finalize(mpn_fwd_plan* p, int32_t step, int32_t stage, void* stream) {
   MPN_REQUIRE(p, "finalize: NULL plan");
   (void)step;
+  if (p->n_graphs > 1) return MPN_OK;     // batched: graph_finalize_kernel already ran after the sweep
   // sums already reduced (and possibly all-reduced by the host): constants only
   finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(make_fin(p, stage, false), 0, 1);
   MPN_LAUNCH_OK();
@@ -988,6 +1237,7 @@ int mpn_plan_finalize(mpn_fwd_plan* p, int32_t step, int32_t stage, void* stream
 // reduce this rank's block partials into the sums vector (phase API: host all-reduces it afterwards)
 int mpn_plan_reduce(mpn_fwd_plan* p, int32_t stage, int with_consts, void* stream) {
   MPN_REQUIRE(p, "reduce: NULL plan");
+  if (p->n_graphs > 1) return MPN_OK;     // batched: graph_finalize_kernel already ran after the sweep
   finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(make_fin(p, stage, false), 1, with_consts);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -1032,7 +1282,7 @@ int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const 
   int rc = MPN_OK;
   const size_t lstride = (size_t)g->n_edges * 2;
 #define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
-  p->fuse_fin = 1;
+  p->fuse_fin = (p->n_graphs > 1) ? 0 : 1;
   {
     // the node encoder (tensor-core GEMM chain) does not depend on the edge-encoder sweeps: run it on a side stream
     SideStream* ss = side_stream();

@@ -44,7 +44,7 @@ class TrackletGraph:
     otherwise ``sorted_edge = original_edge[perm]``."""
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int, chunk: int = None, row_offset: int = 0,
-                 n_rows: int = None):
+                 n_rows: int = None, ptr: torch.Tensor = None):
         if not edge_index.is_cuda:
             raise RuntimeError("TrackletGraph needs a CUDA edge_index: the B200 path has no CPU fallback")
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
@@ -65,9 +65,30 @@ class TrackletGraph:
         self.task_row = torch.empty(max(self.max_tasks, 1), **i32)
         self.n_tasks = torch.zeros(1, **i32)
         self.perm = None
+        # batched small graphs: ptr = node offsets [G+1] (PyG ``Batch.ptr``); BatchNorm statistics are then per graph
+        self.n_graphs, self.node_gid, self.graph_nptr = 1, None, None
+        if ptr is not None and ptr.numel() > 2:
+            if row_offset != 0 or self.n_nodes != self.n_cols:
+                raise ValueError("batched graphs cannot be row-sharded")
+            nptr = ptr.to(device=dev, dtype=torch.int64).contiguous()
+            if int(nptr[0]) != 0 or int(nptr[-1]) != self.n_nodes or bool((nptr[1:] <= nptr[:-1]).any()):
+                raise ValueError("ptr must be strictly increasing from 0 to num_nodes")
+            self.n_graphs = nptr.numel() - 1
+            self.node_gid = torch.repeat_interleave(torch.arange(self.n_graphs, device=dev, dtype=torch.int32),
+                                                    (nptr[1:] - nptr[:-1])).contiguous()
+            self.graph_nptr = nptr.to(torch.int32).contiguous()
+            row_g, col_g = self.node_gid[edge_index[0].long()], self.node_gid[edge_index[1].long()]
+            if bool((row_g != col_g).any()):
+                raise ValueError("batched graphs must be block-diagonal: an edge connects two different graphs")
+            e_per_graph = torch.bincount(row_g.long(), minlength=self.n_graphs)
+            if int(e_per_graph.min()) < 2 or int((nptr[1:] - nptr[:-1]).min()) < 2:
+                raise ValueError("every graph of a batch needs at least 2 nodes and 2 edges (BatchNorm over one value "
+                                 "raises in the reference)")
         self.struct = _lib.MpnGraph(self.n_nodes, self.n_cols, self.row_offset, self.chunk, self.n_edges, self.max_tasks, 0,
                                     self.rowptr.data_ptr(), self.col.data_ptr(), self.taskptr.data_ptr(),
-                                    self.task_row.data_ptr(), self.n_tasks.data_ptr())
+                                    self.task_row.data_ptr(), self.n_tasks.data_ptr(), self.n_graphs, 0,
+                                    self.node_gid.data_ptr() if self.node_gid is not None else None,
+                                    self.graph_nptr.data_ptr() if self.graph_nptr is not None else None)
         ei = edge_index
         if ei.dtype != torch.int64:
             ei = ei.long()
@@ -94,11 +115,13 @@ class TrackletGraph:
 
 def graph_for(data, edge_index: torch.Tensor, num_nodes: int) -> TrackletGraph:
     """Graph tables cached on the data object (one graph per batch in the reference driver, inference.py:375)."""
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes))
+    ptr = getattr(data, "ptr", None) if data is not None else None
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes),
+           None if ptr is None else (ptr.data_ptr(), ptr._version))
     cached = getattr(data, "_mpn_b200_graph", None) if data is not None else None
     if cached is not None and cached[0] == key:
         return cached[1]
-    g = TrackletGraph(edge_index, num_nodes)
+    g = TrackletGraph(edge_index, num_nodes, ptr=ptr)
     if data is not None:
         try:
             object.__setattr__(data, "_mpn_b200_graph", (key, g))

@@ -38,9 +38,15 @@ class _GraphedForward:
         self.tables = ("rowptr", "col", "taskptr", "task_row", "n_tasks")
         for name in self.tables:
             setattr(self.g, name, torch.empty_like(getattr(g, name)))
+        self.g.n_graphs, self.g.node_gid, self.g.graph_nptr = g.n_graphs, None, None
+        if g.n_graphs > 1:
+            self.tables = self.tables + ("node_gid", "graph_nptr")
+            self.g.node_gid, self.g.graph_nptr = torch.empty_like(g.node_gid), torch.empty_like(g.graph_nptr)
         self.g.struct = _lib.MpnGraph(g.n_nodes, g.n_cols, g.row_offset, g.chunk, g.n_edges, g.max_tasks, 0,
                                       self.g.rowptr.data_ptr(), self.g.col.data_ptr(), self.g.taskptr.data_ptr(),
-                                      self.g.task_row.data_ptr(), self.g.n_tasks.data_ptr())
+                                      self.g.task_row.data_ptr(), self.g.n_tasks.data_ptr(), g.n_graphs, 0,
+                                      self.g.node_gid.data_ptr() if g.n_graphs > 1 else None,
+                                      self.g.graph_nptr.data_ptr() if g.n_graphs > 1 else None)
         self.logits = torch.empty(n_out, g.n_edges, 2, dtype=torch.float32, device=dev)
         self.h = torch.empty(g.n_nodes, _lib.MPN_DH, dtype=torch.float32, device=dev)
         self.pred = torch.empty(g.n_edges, dtype=torch.uint8, device=dev) if fused else None
@@ -286,7 +292,7 @@ class MOTMPNet(nn.Module):
         n_out = 1 if L == 0 else n_cls
         fused = bool(self.fuse_decisions) and n_out > 0
         if self.use_cuda_graph and g.n_edges <= self.cuda_graph_max_edges and g.n_edges > 1:
-            key = (dev.index, g.n_nodes, g.n_edges, x.shape[1], L, n_cls, bool(self.fuse_decisions), self._packed[0])
+            key = (dev.index, g.n_nodes, g.n_edges, g.n_graphs, x.shape[1], L, n_cls, bool(self.fuse_decisions), self._packed[0])
             ent = self._graphs.get(key)
             if ent is None:
                 if len(self._graphs) >= 8:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPN_B200_ABI_VERSION 1
+#define MPN_B200_ABI_VERSION 2
 
 enum {
   MPN_OK = 0,
@@ -70,6 +70,13 @@ typedef struct mpn_graph {
   int32_t* taskptr;         /* dev [n_nodes+1]  first task of each row */
   int32_t* task_row;        /* dev [max_tasks]  local row of each task */
   int32_t* n_tasks;         /* dev [1]          */
+  /* batched small graphs (block-diagonal edge set, nodes of a graph contiguous): BatchNorm statistics are taken
+   * per graph, exactly as if each graph had been passed to the reference on its own (inference.py:375,469).
+   * n_graphs <= 1 (or NULL pointers): one graph. */
+  int32_t n_graphs;
+  int32_t reserved2;
+  int32_t* node_gid;        /* dev [n_nodes]     graph id of each node            */
+  int32_t* graph_nptr;      /* dev [n_graphs+1]  first node of each graph         */
 } mpn_graph;
 
 /* Fills the tables of `g` (pointers and sizes pre-set by the caller).  Synchronises (reads the sorted flag). */

@@ -231,6 +231,54 @@ def test_sharded_cuda_shards_in_one_process(m, L, n_cls, world):
         p.close()
 
 
+def _packed_batch(sizes, cams, D, seed):
+    """PyG-style packing of several graphs: x concatenated, edge_index offset, ptr = node offsets."""
+    xs, eis, ptr = [], [], [0]
+    for i, (n, c) in enumerate(zip(sizes, cams)):
+        x, ei, _, _ = mo.synth_graph(n, c, seed + i, D=D, planted=(i % 2 == 0))
+        xs.append(x); eis.append(ei + ptr[-1]); ptr.append(ptr[-1] + n)
+    return torch.cat(xs), torch.cat(eis, dim=1), torch.tensor(ptr, dtype=torch.int64), xs, eis
+
+
+@pytest.mark.parametrize("L,n_cls", [(1, 1), (3, 2)])
+def test_batched_graphs_per_graph_batchnorm(m, L, n_cls):
+    """BASELINE configs[2]: many small graphs in one launch; statistics per graph == one reference forward per graph."""
+    params = mo.shipped_model_params(L, n_cls, 64, (48, 40))
+    sd = mo.init_weights(params, "resnet101", 17)
+    sizes, cams = [40, 64, 30, 90, 52, 36], [4, 4, 3, 5, 4, 2]
+    x, ei, ptr, xs, eis = _packed_batch(sizes, cams, 64, 300)
+    ea = mo.edge_features(x, ei)
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev()).eval()
+    net.fuse_decisions = True
+    data = Data(x=x.to(dev()), edge_index=ei.to(dev()), edge_attr=ea.to(dev()), ptr=ptr.to(dev()))
+    out, h = net(data)
+    torch.cuda.synchronize()
+    e0 = 0
+    for gi, (xg, eig) in enumerate(zip(xs, eis)):
+        n0, n1 = int(ptr[gi]), int(ptr[gi + 1])
+        eg = eig.shape[1]
+        ref, href = mo.mpn_forward(sd, params, "resnet101", xg, eig - n0, ea[e0:e0 + eg], dtype=torch.float64)
+        for i in range(n_cls):
+            got = out["classified_edges"][i][e0:e0 + eg].cpu().double()
+            assert (got - ref[i]).abs().max().item() <= 1e-4 * ref[i].abs().max().item(), (gi, i)
+        assert (h[n0:n1].cpu().double() - href).abs().max().item() <= 1e-4 * max(1.0, href.abs().max().item()), gi
+        margin = (ref[-1][:, 1] - ref[-1][:, 0]).abs()
+        bad = (net.last_pred[e0:e0 + eg].cpu().long() != ref[-1].argmax(1)) & (margin > 1e-4)
+        assert not bool(bad.any())
+        e0 += eg
+    # a batch of one graph takes the single-graph path and must agree with it bit for bit
+    d1 = Data(x=xs[0].to(dev()), edge_index=(eis[0] - 0).to(dev()), edge_attr=ea[:eis[0].shape[1]].to(dev()),
+              ptr=torch.tensor([0, sizes[0]], device=dev()))
+    d2 = Data(x=xs[0].to(dev()), edge_index=(eis[0] - 0).to(dev()), edge_attr=ea[:eis[0].shape[1]].to(dev()))
+    o1, _ = net(d1); o2, _ = net(d2)
+    assert torch.equal(o1["classified_edges"][-1], o2["classified_edges"][-1])
+    with pytest.raises(ValueError):                                      # an edge between two graphs
+        bad_ei = ei.clone(); bad_ei[1, 0] = int(ptr[2])
+        m.TrackletGraph(bad_ei.to(dev()), x.shape[0], ptr=ptr.to(dev()))
+
+
 def test_forward_rejects_cpu_and_training(m):
     params = mo.shipped_model_params(1, 1, 64, (48,))
     net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")

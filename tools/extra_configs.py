@@ -20,7 +20,7 @@ def c1(reps=300):
 
     def full():
         g = m.TrackletGraph(ei, 300)
-        b._mpn_b200_graph = ((ei.data_ptr(), tuple(ei.shape), ei._version, 300), g)
+        b._mpn_b200_graph = ((ei.data_ptr(), tuple(ei.shape), ei._version, 300, None), g)
         b.edge_attr = m.edge_features(x, ei, graph=g)
         net(b)
 

@@ -24,6 +24,6 @@ timed("require_device", lambda: m._lib.require_device(0))
 g = timed("TrackletGraph", lambda: m.TrackletGraph(ei, N))
 ea = timed("edge_features", lambda: m.edge_features(x, ei, graph=g))
 b.edge_attr = ea
-b._mpn_b200_graph = ((ei.data_ptr(), tuple(ei.shape), ei._version, N), g)
+b._mpn_b200_graph = ((ei.data_ptr(), tuple(ei.shape), ei._version, N, None), g)
 timed("forward", lambda: net(b))
 timed("weights()", lambda: net._weights(dev))
