@@ -27,7 +27,7 @@ class MpnGraph(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_cols", C.c_int32), ("row_offset", C.c_int32), ("chunk", C.c_int32),
                 ("n_edges", C.c_int64), ("max_tasks", C.c_int32), ("reserved", C.c_int32),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("taskptr", C.c_void_p), ("task_row", C.c_void_p),
-                ("n_tasks", C.c_void_p), ("n_graphs", C.c_int32), ("reserved2", C.c_int32),
+                ("n_tasks", C.c_void_p), ("n_graphs", C.c_int32), ("max_graph_nodes", C.c_int32),
                 ("node_gid", C.c_void_p), ("graph_nptr", C.c_void_p)]
 
 

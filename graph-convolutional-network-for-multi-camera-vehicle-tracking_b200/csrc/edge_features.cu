@@ -71,8 +71,43 @@ __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restric
   }
 }
 
+// batched graphs: offsets of the per-graph ng x ng Gram blocks (single thread; G <= 65535)
+__global__ void gram_offsets_kernel(const int* __restrict__ graph_nptr, int n_graphs, long long* __restrict__ g_off) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  long long run = 0;
+  for (int i = 0; i < n_graphs; ++i) {
+    g_off[i] = run;
+    const long long ng = graph_nptr[i + 1] - graph_nptr[i];
+    run += ng * ng;
+  }
+  g_off[n_graphs] = run;
+}
+
+// fp32 fallback for the block-diagonal Gram (tests / shapes the tensor-core kernel does not take): one warp per row
+__global__ void __launch_bounds__(256) gram_blockdiag_simt_kernel(const float* __restrict__ X, int N, int K, const int* __restrict__ node_gid,
+                                                                  const int* __restrict__ graph_nptr, const long long* __restrict__ g_off,
+                                                                  float* __restrict__ Gbuf) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = gwarp; r < N; r += nwarps) {
+    const int gi = node_gid[r];
+    const int base = graph_nptr[gi], ng = graph_nptr[gi + 1] - base;
+    float* out = Gbuf + g_off[gi] + (size_t)(r - base) * ng;
+    const float* a = X + (size_t)r * K;
+    for (int c = 0; c < ng; ++c) {
+      const float* b = X + (size_t)(base + c) * K;
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s = fmaf(a[k], b[k], s);
+      s = warp_sum(s);
+      if (lane == 0) out[c] = s;
+    }
+  }
+}
+
 // one warp per task (a run of edges of one row): coalesced Gram reads when the row's columns are consecutive
 __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_graph g, int r0, int r1, const float* __restrict__ G,
+                                                                  const long long* __restrict__ g_off,
                                                                   const double* __restrict__ st, int D,
                                                                   float2* __restrict__ edge_attr,
                                                                   int* __restrict__ refine_list, int* __restrict__ refine_count) {
@@ -88,6 +123,13 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
     const size_t grow = (size_t)(row + g.row_offset);
     const double sa = st[4 * grow], xa = st[4 * grow + 1], ma = st[4 * grow + 2], na = st[4 * grow + 3];
     const float* Grow = G + (size_t)(row - r0) * g.n_cols;
+    int cshift = 0;
+    if (g_off != nullptr) {                               // batched: this row's block-diagonal Gram block
+      const int gi = g.node_gid[row];
+      const int base = g.graph_nptr[gi], ng = g.graph_nptr[gi + 1] - base;
+      Grow = G + g_off[gi] + (size_t)(row - base) * ng;
+      cshift = base;
+    }
     constexpr int U = 4;                                   // independent col -> (G, st) gathers in flight per lane
     for (int base = beg; base < end; base += 32 * U) {
       int c[U];
@@ -102,7 +144,7 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
       }
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        gv[j] = Grow[c[j]];
+        gv[j] = Grow[c[j] - cshift];
         const double4 s4 = *reinterpret_cast<const double4*>(st + 4 * (size_t)c[j]);
         sb[j] = s4.x; xb[j] = s4.y; mb[j] = s4.z; nb[j] = s4.w;
       }
@@ -166,6 +208,7 @@ struct EfLayout {
   double* mu_part;
   float* G;
   int *refine_list, *refine_count;
+  long long* g_off;
   void* gemm_ws;
   size_t gemm_ws_bytes;
   int rows_per_block;
@@ -179,15 +222,18 @@ static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) 
   L.mu = a.take<float>(D);
   L.mu_part = a.take<double>((size_t)CM_SPLITS * D);
   L.xc = a.take<float>((size_t)g->n_cols * D);
+  const bool batched = g->n_graphs > 1 && g->node_gid && g->graph_nptr;
   const size_t budget = (size_t)2 << 30;
   size_t rows = budget / ((size_t)g->n_cols * sizeof(float));
   if (rows < 128) rows = 128;
   if (rows > (size_t)g->n_nodes) rows = g->n_nodes;
   L.rows_per_block = (int)rows;
-  L.G = a.take<float>(rows * (size_t)g->n_cols);
+  // batched: block-diagonal Gram, sum of ng^2 <= max_graph_nodes * N entries
+  L.G = a.take<float>(batched ? (size_t)g->max_graph_nodes * g->n_cols : rows * (size_t)g->n_cols);
+  L.g_off = a.take<long long>((size_t)(batched ? g->n_graphs : 0) + 1);
   L.refine_list = a.take<int>((size_t)(g->n_edges > 0 ? g->n_edges : 1));
   L.refine_count = a.take<int>(1);
-  L.gemm_ws_bytes = gemm_tc_workspace_bytes((int)rows, g->n_cols, D);
+  L.gemm_ws_bytes = batched ? gemm_tc_workspace_bytes(1, g->n_cols, D) : gemm_tc_workspace_bytes((int)rows, g->n_cols, D);
   L.gemm_ws = L.gemm_ws_bytes ? (void*)a.take<char>(L.gemm_ws_bytes) : nullptr;
   L.total = a.off;
   return L;
@@ -223,6 +269,25 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
   center_rows_kernel<<<min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st>>>(x, L.mu, g->n_cols, D, L.xc, L.st);
   MPN_LAUNCH_OK();
   MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, sizeof(int), st));
+  if (g->n_graphs > 1 && g->node_gid && g->graph_nptr) {
+    // batched small graphs: block-diagonal Gram (one ng x ng block per graph), same epilogue
+    MPN_REQUIRE(g->row_offset == 0 && g->n_cols == g->n_nodes && g->max_graph_nodes > 0, "batched edge features: bad graph");
+    gram_offsets_kernel<<<1, 32, 0, st>>>(g->graph_nptr, g->n_graphs, L.g_off);
+    MPN_LAUNCH_OK();
+    if (use_tc && gemm_tc_supported(g->n_cols, 64, D) && g->n_graphs <= 65535) {
+      MPN_TRY(gram_blockdiag_tc(L.xc, g->n_cols, D, g->graph_nptr, L.g_off, g->n_graphs, g->max_graph_nodes, L.G, L.gemm_ws,
+                                L.gemm_ws_bytes, st));
+    } else {
+      gram_blockdiag_simt_kernel<<<kNumSMs * 8, 256, 0, st>>>(L.xc, g->n_cols, D, g->node_gid, g->graph_nptr, L.g_off, L.G);
+      MPN_LAUNCH_OK();
+    }
+    edge_feature_gather_kernel<<<kNumSMs * 8, 256, 0, st>>>(*g, 0, g->n_nodes, L.G, L.g_off, L.st, D, (float2*)edge_attr, L.refine_list,
+                                                           L.refine_count);
+    MPN_LAUNCH_OK();
+    edge_feature_refine_kernel<<<kNumSMs * 4, 256, 0, st>>>(*g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
   for (int r0 = 0; r0 < g->n_nodes; r0 += L.rows_per_block) {
     const int r1 = min(r0 + L.rows_per_block, g->n_nodes);
     const float* Ablk = L.xc + (size_t)(g->row_offset + r0) * D;
@@ -230,7 +295,7 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
       MPN_TRY(gemm_nt_tc(Ablk, L.xc, nullptr, L.G, r1 - r0, g->n_cols, D, L.gemm_ws, L.gemm_ws_bytes, st));
     else
       MPN_TRY(gemm_nt_simt(Ablk, L.xc, nullptr, nullptr, nullptr, L.G, r1 - r0, g->n_cols, D, st));
-    edge_feature_gather_kernel<<<kNumSMs * 8, 256, 0, st>>>(*g, r0, r1, L.G, L.st, D, (float2*)edge_attr,
+    edge_feature_gather_kernel<<<kNumSMs * 8, 256, 0, st>>>(*g, r0, r1, L.G, nullptr, L.st, D, (float2*)edge_attr,
                                                            L.refine_list, L.refine_count);
     MPN_LAUNCH_OK();
   }

@@ -120,7 +120,8 @@ template <int BN, bool SYM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                      const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K) {
+                      const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
+                      const int* __restrict__ graph_nptr, const long long* __restrict__ g_off) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -130,9 +131,20 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;     // output-local tile origin
+  int tm0 = m0, tn0 = n0;                                // TMA row coordinates of the A / B tiles
   const int num_kb = (K + TC_BK - 1) / TC_BK;
   if (SYM && n0 + BN <= m0) return;                      // strictly below the diagonal: produced by the mirror store
+  if (graph_nptr != nullptr) {
+    // block-diagonal Gram (batched graphs): blockIdx.z = graph; its rows [base, base+ng) form an ng x ng block of C
+    const int base = graph_nptr[blockIdx.z];
+    const int ng = graph_nptr[blockIdx.z + 1] - base;
+    if (m0 >= ng || n0 >= ng) return;
+    tm0 = base + m0;
+    tn0 = base + n0;
+    M = N = ng;
+    C += g_off[blockIdx.z];
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -162,10 +174,10 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         const int k0 = kb * TC_BK;
-        tma_load_2d(&map_a_hi, &full_bar[stage], st, k0, m0);
-        tma_load_2d(&map_a_lo, &full_bar[stage], st + Cfg::A_BYTES, k0, m0);
-        tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * Cfg::A_BYTES, k0, n0);
-        tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, n0);
+        tma_load_2d(&map_a_hi, &full_bar[stage], st, k0, tm0);
+        tma_load_2d(&map_a_lo, &full_bar[stage], st + Cfg::A_BYTES, k0, tm0);
+        tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * Cfg::A_BYTES, k0, tn0);
+        tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, tn0);
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -331,14 +343,16 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K) {
 
 template <int BN, bool SYM>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const float* bias,
-                     float* C, int M, int N, int K, cudaStream_t st) {
+                     float* C, int M, int N, int K, cudaStream_t st, const int* graph_nptr = nullptr, const long long* g_off = nullptr,
+                     int n_graphs = 1, int max_ng = 0) {
   static bool configured = false;
   if (!configured) {
     MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
     configured = true;
   }
   dim3 grid(div_up(N, BN), div_up(M, TC_BM));
-  gemm_nt_3xtf32_kernel<BN, SYM><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ah, al, bh, bl, bias, C, M, N, K);
+  if (graph_nptr) grid = dim3(div_up(max_ng, BN), div_up(max_ng, TC_BM), n_graphs);
+  gemm_nt_3xtf32_kernel<BN, SYM><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ah, al, bh, bl, bias, C, M, N, K, graph_nptr, g_off);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -388,6 +402,24 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
   if (BN == 256) return launch_tc<256, false>(ah, al, bh, bl, bias, C, M, N, K, st);
   if (sym) return launch_tc<128, true>(ah, al, bh, bl, bias, C, M, N, K, st);
   return launch_tc<128, false>(ah, al, bh, bl, bias, C, M, N, K, st);
+}
+
+// Block-diagonal Gram matrix of a batch of graphs: for graph i with rows [nptr[i], nptr[i+1]) the ng x ng block
+// X_i X_i^T is written (row-major, ld = ng) at Gbuf + g_off[i].  Symmetric tiles only.
+int gram_blockdiag_tc(const float* X, int N, int K, const int* graph_nptr, const long long* g_off, int n_graphs, int max_ng,
+                      float* Gbuf, void* ws, size_t ws_bytes, cudaStream_t st) {
+  MPN_REQUIRE(gemm_tc_supported(N, 64, K), "block-diagonal tcgen05 Gram: unsupported K=%d", K);
+  MPN_REQUIRE(n_graphs >= 1 && n_graphs <= 65535, "block-diagonal Gram: at most 65535 graphs per launch");
+  const size_t plane = (((size_t)N * K * sizeof(float)) + 255) & ~(size_t)255;
+  MPN_REQUIRE(ws && ws_bytes >= 2 * plane + 256, "block-diagonal Gram: workspace too small");
+  char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  float *hi = (float*)w, *lo = (float*)(w + plane);
+  split_tf32_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)X, (long long)N * K / 4, K, nullptr, nullptr, nullptr, (float4*)hi, (float4*)lo);
+  MPN_LAUNCH_OK();
+  CUtensorMap mh, ml;
+  MPN_TRY(make_map(&mh, hi, N, K, TC_BM));
+  MPN_TRY(make_map(&ml, lo, N, K, TC_BM));
+  return launch_tc<128, true>(mh, ml, mh, ml, nullptr, Gbuf, N, N, K, st, graph_nptr, g_off, n_graphs, max_ng);
 }
 
 }  // namespace mpn

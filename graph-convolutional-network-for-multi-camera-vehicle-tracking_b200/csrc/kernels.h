@@ -19,5 +19,7 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
                const int* row_gid = nullptr);   // row_gid: a_scale/a_shift are [n_graphs][K] tables indexed by the row's graph
 int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t st);
 bool gemm_tc_supported(int M, int N, int K);
+int gram_blockdiag_tc(const float* X, int N, int K, const int* graph_nptr, const long long* g_off, int n_graphs, int max_ng,
+                      float* Gbuf, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace mpn

@@ -66,7 +66,7 @@ class TrackletGraph:
         self.n_tasks = torch.zeros(1, **i32)
         self.perm = None
         # batched small graphs: ptr = node offsets [G+1] (PyG ``Batch.ptr``); BatchNorm statistics are then per graph
-        self.n_graphs, self.node_gid, self.graph_nptr = 1, None, None
+        self.n_graphs, self.node_gid, self.graph_nptr, self.max_graph_nodes = 1, None, None, 0
         if ptr is not None and ptr.numel() > 2:
             if row_offset != 0 or self.n_nodes != self.n_cols:
                 raise ValueError("batched graphs cannot be row-sharded")
@@ -81,12 +81,13 @@ class TrackletGraph:
             if bool((row_g != col_g).any()):
                 raise ValueError("batched graphs must be block-diagonal: an edge connects two different graphs")
             e_per_graph = torch.bincount(row_g.long(), minlength=self.n_graphs)
+            self.max_graph_nodes = int((nptr[1:] - nptr[:-1]).max())
             if int(e_per_graph.min()) < 2 or int((nptr[1:] - nptr[:-1]).min()) < 2:
                 raise ValueError("every graph of a batch needs at least 2 nodes and 2 edges (BatchNorm over one value "
                                  "raises in the reference)")
         self.struct = _lib.MpnGraph(self.n_nodes, self.n_cols, self.row_offset, self.chunk, self.n_edges, self.max_tasks, 0,
                                     self.rowptr.data_ptr(), self.col.data_ptr(), self.taskptr.data_ptr(),
-                                    self.task_row.data_ptr(), self.n_tasks.data_ptr(), self.n_graphs, 0,
+                                    self.task_row.data_ptr(), self.n_tasks.data_ptr(), self.n_graphs, self.max_graph_nodes,
                                     self.node_gid.data_ptr() if self.node_gid is not None else None,
                                     self.graph_nptr.data_ptr() if self.graph_nptr is not None else None)
         ei = edge_index

@@ -38,13 +38,13 @@ class _GraphedForward:
         self.tables = ("rowptr", "col", "taskptr", "task_row", "n_tasks")
         for name in self.tables:
             setattr(self.g, name, torch.empty_like(getattr(g, name)))
-        self.g.n_graphs, self.g.node_gid, self.g.graph_nptr = g.n_graphs, None, None
+        self.g.n_graphs, self.g.node_gid, self.g.graph_nptr, self.g.max_graph_nodes = g.n_graphs, None, None, g.max_graph_nodes
         if g.n_graphs > 1:
             self.tables = self.tables + ("node_gid", "graph_nptr")
             self.g.node_gid, self.g.graph_nptr = torch.empty_like(g.node_gid), torch.empty_like(g.graph_nptr)
         self.g.struct = _lib.MpnGraph(g.n_nodes, g.n_cols, g.row_offset, g.chunk, g.n_edges, g.max_tasks, 0,
                                       self.g.rowptr.data_ptr(), self.g.col.data_ptr(), self.g.taskptr.data_ptr(),
-                                      self.g.task_row.data_ptr(), self.g.n_tasks.data_ptr(), g.n_graphs, 0,
+                                      self.g.task_row.data_ptr(), self.g.n_tasks.data_ptr(), g.n_graphs, g.max_graph_nodes,
                                       self.g.node_gid.data_ptr() if g.n_graphs > 1 else None,
                                       self.g.graph_nptr.data_ptr() if g.n_graphs > 1 else None)
         self.logits = torch.empty(n_out, g.n_edges, 2, dtype=torch.float32, device=dev)

@@ -74,7 +74,7 @@ typedef struct mpn_graph {
    * per graph, exactly as if each graph had been passed to the reference on its own (inference.py:375,469).
    * n_graphs <= 1 (or NULL pointers): one graph. */
   int32_t n_graphs;
-  int32_t reserved2;
+  int32_t max_graph_nodes;  /* largest graph of the batch (sizes the block-diagonal Gram tiles) */
   int32_t* node_gid;        /* dev [n_nodes]     graph id of each node            */
   int32_t* graph_nptr;      /* dev [n_graphs+1]  first node of each graph         */
 } mpn_graph;

@@ -240,6 +240,16 @@ def _packed_batch(sizes, cams, D, seed):
     return torch.cat(xs), torch.cat(eis, dim=1), torch.tensor(ptr, dtype=torch.int64), xs, eis
 
 
+@pytest.mark.parametrize("D,tc", [(256, True), (2048, True), (48, True), (64, False)])
+def test_batched_edge_features_block_diagonal(m, D, tc):
+    sizes, cams = [40, 150, 30, 290, 52, 131], [4, 4, 3, 5, 4, 2]         # graphs larger than one 128-row tile included
+    x, ei, ptr, xs, eis = _packed_batch(sizes, cams, D, 500)
+    ref = mo.edge_features(x, ei, dtype=torch.float64).numpy()
+    g = m.TrackletGraph(ei.to(dev()), x.shape[0], ptr=ptr.to(dev()))
+    out = m.edge_features(x.to(dev()), None, graph=g, use_tensor_cores=tc).cpu().numpy()
+    assert np.allclose(out, ref, rtol=1e-5, atol=2e-6)
+
+
 @pytest.mark.parametrize("L,n_cls", [(1, 1), (3, 2)])
 def test_batched_graphs_per_graph_batchnorm(m, L, n_cls):
     """BASELINE configs[2]: many small graphs in one launch; statistics per graph == one reference forward per graph."""
