@@ -296,30 +296,56 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = E_total / (ms_per_step * 1e-3)
 
-    # ---- e2e: public API with HOST buffers (pinned), copies inside the timed region
+    # ---- e2e: public API with HOST buffers (pinned), copies inside the timed region.
+    # Primary: what the reference driver holds on the host before it builds the graph (inference.py:383-414): the node
+    # features and the per-node camera ids; the graph tables are built on the device (TrackletGraph.from_cameras, row f1).
+    # Secondary ("int64_edge_index"): the caller ships the reference's int64 edge_index [2,E] over PCIe as well.
     hx = x.cpu().pin_memory()
     hei = ei.cpu().pin_memory()
     hpred = torch.empty(E_local, dtype=torch.uint8).pin_memory()
     dx, dei = torch.empty_like(x), torch.empty_like(ei)
-    e2e_ms = 0.0
+    cam_host = (torch.arange(n_nodes) * CAMS // n_nodes).numpy()
     n_e2e = max(2, min(args.steps, 5))
-    for i in range(n_e2e + 1):
-        flush.fill_(i & 0xFF)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+
+    def e2e_loop(fn):
+        tot_ms = 0.0
+        for i in range(n_e2e + 1):
+            flush.fill_(i & 0xFF)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pred = fn()
+            hpred.copy_(pred, non_blocking=True)
+            b.record()
+            barrier()
+            ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if i > 0:
+                tot_ms += float(ms.item()) / n_e2e
+        return tot_ms
+
+    def e2e_edge_index():
         dx.copy_(hx, non_blocking=True)
         dei.copy_(hei, non_blocking=True)
-        pred = step(dx, dei)                # the step runs on the freshly copied device buffers
-        hpred.copy_(pred, non_blocking=True)
-        b.record()
-        barrier()
-        ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        if i > 0:
-            e2e_ms += float(ms.item()) / n_e2e
-    h2d = hx.numel() * 4 + hei.numel() * 8
+        return step(dx, dei)
+
+    def e2e_cameras():
+        dx.copy_(hx, non_blocking=True)
+        g = m.TrackletGraph.from_cameras(cam_host, dev)                    # K0 from camera ids, on the device
+        batch.x, batch.mpn_graph = dx, g
+        batch.edge_attr = m.edge_features(dx, None, graph=g)
+        net(batch)
+        return net.last_pred
+
+    e2e_ei_ms = e2e_loop(e2e_edge_index)
+    if world == 1:
+        e2e_ms = e2e_loop(e2e_cameras)
+        batch.mpn_graph = None
+        h2d = hx.numel() * 4 + cam_host.size * 8
+    else:
+        e2e_ms = e2e_ei_ms
+        h2d = hx.numel() * 4 + hei.numel() * 8
     d2h = hpred.numel()
 
     line = None
@@ -333,7 +359,11 @@ def run_ours(args):
                            "l2": "256 MiB flush between timed iterations; inputs (edge_index 235 MB) exceed L2",
                            "timing": "CUDA events per step on the launching stream, max over ranks, summed over steps"},
                 "e2e": {"value": E_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms},
+                        "ms_per_step": e2e_ms,
+                        "inputs": "host node features [N,2048] f32 + camera ids (graph tables built on the device)" if world == 1
+                                  else "host node features + int64 edge_index shard",
+                        "int64_edge_index": {"value": E_total / (e2e_ei_ms * 1e-3), "ms_per_step": e2e_ei_ms,
+                                             "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8}},
                 "gpu_launches": int(launches), "clocks": clk}
     if world == 1:
         ph = time_phases(m, net, x, ei)

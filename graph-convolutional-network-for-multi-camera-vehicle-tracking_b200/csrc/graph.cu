@@ -113,9 +113,85 @@ static int graph_build_impl(mpn_graph* g, const IdxT* row, const IdxT* col, cuda
   return MPN_OK;
 }
 
+struct CamLayout {
+  int n_cams;
+  int ptr[MPN_MAX_CAMERAS + 1];            // first node of each camera
+  long long ebase[MPN_MAX_CAMERAS + 1];    // first edge of each camera's row block
+};
+
+// dense cross-camera graph straight from the camera layout: row r (camera k) lists every node outside [ptr[k], ptr[k+1])
+__global__ void __launch_bounds__(256) cross_camera_kernel(const CamLayout L, int n_nodes, long long E, int* __restrict__ rowptr,
+                                                           int* __restrict__ col32, long long* __restrict__ edge_index_out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long r = tid; r <= n_nodes; r += stride) {            // rowptr
+    int k = 0;
+    while (k + 1 < L.n_cams && r >= L.ptr[k + 1]) ++k;
+    const long long deg = n_nodes - (L.ptr[k + 1] - L.ptr[k]);
+    rowptr[r] = (r == n_nodes) ? (int)E : (int)(L.ebase[k] + (r - L.ptr[k]) * deg);
+  }
+  for (long long e = tid; e < E; e += stride) {
+    int k = 0;
+    while (k + 1 < L.n_cams && e >= L.ebase[k + 1]) ++k;
+    const int lo = L.ptr[k], nk = L.ptr[k + 1] - lo;
+    const long long deg = n_nodes - nk;
+    const long long off = e - L.ebase[k];
+    const int row = lo + (int)(off / deg);
+    const int idx = (int)(off % deg);
+    const int c = idx < lo ? idx : idx + nk;
+    col32[e] = c;
+    if (edge_index_out) { edge_index_out[e] = row; edge_index_out[E + e] = c; }
+  }
+}
+
 }  // namespace mpn
 
 extern "C" {
+
+int64_t mpn_cross_camera_edges(const int32_t* cam_ptr, int32_t n_cams) {
+  if (!cam_ptr || n_cams < 1) return -1;
+  const long long n = cam_ptr[n_cams];
+  long long e = 0;
+  for (int k = 0; k < n_cams; ++k) {
+    const long long nk = cam_ptr[k + 1] - cam_ptr[k];
+    if (nk < 0) return -1;
+    e += nk * (n - nk);
+  }
+  return e;
+}
+
+int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n_cams, int64_t* edge_index_out, void* stream) {
+  using namespace mpn;
+  MPN_REQUIRE(g && cam_ptr, "cross_camera: NULL argument");
+  MPN_REQUIRE(n_cams >= 1 && n_cams <= MPN_MAX_CAMERAS, "cross_camera: n_cams must be in [1,%d]", MPN_MAX_CAMERAS);
+  MPN_REQUIRE(cam_ptr[0] == 0 && cam_ptr[n_cams] == g->n_nodes && g->n_cols == g->n_nodes && g->row_offset == 0,
+              "cross_camera: cam_ptr must run from 0 to n_nodes of an unsharded graph");
+  const long long E = mpn_cross_camera_edges(cam_ptr, n_cams);
+  MPN_REQUIRE(E >= 0 && E == g->n_edges, "cross_camera: g->n_edges (%lld) must be %lld", (long long)g->n_edges, E);
+  MPN_REQUIRE(E < (1ll << 31), "n_edges must be < 2^31");
+  MPN_REQUIRE(g->chunk >= 32 && g->chunk <= 4096 && (g->chunk & (g->chunk - 1)) == 0, "chunk must be a power of two in [32,4096]");
+  MPN_REQUIRE(g->max_tasks >= g->n_edges / g->chunk + g->n_nodes, "max_tasks too small (need E/chunk + N)");
+  MPN_REQUIRE(g->rowptr && g->taskptr && g->task_row && g->n_tasks && (g->col || E == 0), "graph table pointer is NULL");
+  CamLayout L;
+  L.n_cams = n_cams;
+  long long run = 0;
+  for (int k = 0; k <= n_cams; ++k) {
+    L.ptr[k] = cam_ptr[k];
+    L.ebase[k] = run;
+    if (k < n_cams) run += (long long)(cam_ptr[k + 1] - cam_ptr[k]) * (g->n_nodes - (cam_ptr[k + 1] - cam_ptr[k]));
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long work = E > g->n_nodes ? E : g->n_nodes + 1;
+  cross_camera_kernel<<<(int)min((long long)kNumSMs * 16, (work + 255) / 256), 256, 0, st>>>(L, g->n_nodes, E, g->rowptr, g->col,
+                                                                                          (long long*)edge_index_out);
+  MPN_LAUNCH_OK();
+  task_scan<<<1, 1024, 0, st>>>(g->rowptr, g->n_nodes, g->chunk, g->taskptr, g->n_tasks);
+  MPN_LAUNCH_OK();
+  task_fill<<<min(kNumSMs * 8, div_up(g->n_nodes, 256)), 256, 0, st>>>(g->taskptr, g->n_nodes, g->max_tasks, g->task_row);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
 
 int mpn_abi_version(void) { return MPN_B200_ABI_VERSION; }
 const char* mpn_last_error(void) { return mpn::g_err; }

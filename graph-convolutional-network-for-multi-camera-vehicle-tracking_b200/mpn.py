@@ -272,14 +272,17 @@ class MOTMPNet(nn.Module):
     def forward(self, data):
         """data.x [N,D] fp32, data.edge_index [2,E] int64, data.edge_attr [E,2] fp32, all on one CUDA device.
         Returns ({'classified_edges': [logits [E,2], ...]}, latent_node_feats [N,32]) as models/mpn.py:299."""
-        x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
-        if not (x.is_cuda and edge_index.is_cuda and edge_attr.is_cuda):
+        x, edge_attr = data.x, data.edge_attr
+        # data.mpn_graph: tables built on the device by TrackletGraph.from_cameras (no int64 edge_index needed)
+        pre = getattr(data, "mpn_graph", None)
+        edge_index = None if pre is not None else data.edge_index
+        if not (x.is_cuda and edge_attr.is_cuda and (edge_index is None or edge_index.is_cuda)):
             raise RuntimeError("MOTMPNet.forward needs CUDA tensors: the B200 path has no CPU fallback")
         if self.training:
             raise _unsupported("training mode (dropout active / autograd); call .eval() as main.py:98 does")
         dev = x.device
         x = x.contiguous().float()
-        g = graph_for(data, edge_index, x.shape[0])
+        g = pre if pre is not None else graph_for(data, edge_index, x.shape[0])
         ea = edge_attr.contiguous().float()
         if g.perm is not None:
             ea = ea[g.perm].contiguous()

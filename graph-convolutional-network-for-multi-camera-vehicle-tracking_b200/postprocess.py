@@ -27,7 +27,8 @@ class _Post:
         if not predictions.is_cuda:
             raise RuntimeError("post-processing needs CUDA tensors: the B200 path has no CPU fallback")
         self.dev = predictions.device
-        self.g = graph_for(data, data.edge_index, int(data.num_nodes))
+        pre = getattr(data, "mpn_graph", None)
+        self.g = pre if pre is not None else graph_for(data, data.edge_index, int(data.num_nodes))
         self.lib = _lib.lib()
         act = (predictions.reshape(-1) != 0).to(torch.uint8)
         self.act = act[self.g.perm].contiguous() if self.g.perm is not None else act.contiguous()

@@ -84,6 +84,16 @@ int mpn_graph_build(mpn_graph* g, const int64_t* edge_index_dev, void* stream);
 /* Same from int32 row/col arrays already split (used for row-block shards). */
 int mpn_graph_build_i32(mpn_graph* g, const int32_t* row_dev, const int32_t* col_dev, void* stream);
 
+/* Graph construction on the device.  Replaces inference.py:407-414: for every camera
+ * ascending, cartesian_prod(nodes in the camera, nodes not in it).  Nodes must be grouped by camera (dataset.py:279-281);
+ * cam_ptr_host[k] = first node of camera k, cam_ptr_host[n_cams] = n_nodes (HOST array, n_cams <= 64).  Fills the tables
+ * of `g` (g->n_edges must equal sum_k n_k (N - n_k)) directly from the camera layout: the int64 edge_index (16 B/edge) is
+ * never read, and only written when edge_index_out_dev != NULL ([2,E] int64, reference layout).  Does not synchronise. */
+#define MPN_MAX_CAMERAS 64
+int64_t mpn_cross_camera_edges(const int32_t* cam_ptr_host, int32_t n_cams);
+int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr_host, int32_t n_cams, int64_t* edge_index_out_dev,
+                                 void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Edge features (K1).  Replaces inference.py:453-456:
  *   edge_attr[e] = [ ||x_r - x_c + 1e-6||_2 , 1 - cos(x_r, x_c) ]

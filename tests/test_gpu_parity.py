@@ -40,6 +40,38 @@ def test_graph_tables_match_numpy(m):
     assert g.perm is None
 
 
+def test_graph_from_cameras_matches_edge_index_path(m):
+    """Row f1: tables built on the device from camera ids == tables built from the reference's int64 edge_index."""
+    cam = torch.tensor([0] * 31 + [2] * 17 + [3] * 40 + [7] * 25)            # ragged cameras, non-contiguous ids
+    ei = mo.cross_camera_edge_index(cam)
+    g1 = m.TrackletGraph(ei.to(dev()), cam.numel(), chunk=64)
+    g2 = m.TrackletGraph.from_cameras(cam, dev(), chunk=64, materialize_edge_index=True)
+    torch.cuda.synchronize()
+    assert g2.n_edges == ei.shape[1]
+    assert torch.equal(g2.edge_index.cpu(), ei)
+    for name in ("rowptr", "taskptr", "n_tasks"):
+        assert torch.equal(getattr(g1, name), getattr(g2, name)), name
+    assert torch.equal(g1.col[:g1.n_edges], g2.col[:g2.n_edges])
+    nt = int(g1.n_tasks.item())
+    assert torch.equal(g1.task_row[:nt], g2.task_row[:nt])
+    with pytest.raises(ValueError):
+        m.TrackletGraph.from_cameras(torch.tensor([0, 1, 0, 1]), dev())
+    # forward through data.mpn_graph (no edge_index on the data object)
+    params = mo.shipped_model_params(1, 1, 64, (48,))
+    sd = mo.init_weights(params, "resnet101", 3)
+    x = torch.nn.functional.normalize(torch.randn(cam.numel(), 64, generator=torch.Generator().manual_seed(0)), dim=0)
+    ea = mo.edge_features(x, ei)
+    ref, _ = mo.mpn_forward(sd, params, "resnet101", x, ei, ea, dtype=torch.float64)
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev()).eval()
+    g3 = m.TrackletGraph.from_cameras(cam, dev())
+    ea_dev = m.edge_features(x.to(dev()), None, graph=g3, use_tensor_cores=False)
+    assert np.allclose(ea_dev.cpu().numpy(), ea.numpy(), rtol=3e-6, atol=3e-6)
+    out, _ = net(Data(x=x.to(dev()), edge_attr=ea_dev, mpn_graph=g3))
+    assert (out["classified_edges"][0].cpu().double() - ref[0]).abs().max().item() <= 1e-4 * ref[0].abs().max().item()
+
+
 def test_graph_unsorted_and_invalid(m):
     x, ei, cam, _ = mo.synth_graph(40, 4, 5, D=8)
     perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(0))
