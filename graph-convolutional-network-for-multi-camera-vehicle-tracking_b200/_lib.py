@@ -39,6 +39,15 @@ class MpnWeights(C.Structure):
                 ("node_w_hi", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_w_lo", C.c_void_p * MPN_MAX_NODE_LAYERS)]
 
 
+MPN_MAX_PEERS = 16
+
+
+class MpnPeerCtx(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("sums", C.c_void_p * MPN_MAX_PEERS),
+                ("flags", C.c_void_p * MPN_MAX_PEERS), ("h", C.c_void_p * MPN_MAX_PEERS),
+                ("seq_moments", C.c_uint64), ("seq_h", C.c_uint64)]
+
+
 class MpnError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("libmpn_b200 error %d: %s" % (code, message))
@@ -78,6 +87,9 @@ _PROTOS = {
     "mpn_plan_node_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "mpn_plan_h_full": (C.c_void_p, [C.c_void_p]),
     "mpn_split_tf32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpn_forward_sharded": (C.c_int, [C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(MpnPeerCtx),
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_decide": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_post_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph)]),
     "mpn_cut": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -216,6 +216,70 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinArgs f, 
   finalize_body(f, do_reduce, do_consts);
 }
 
+// ---- collectives fused over NVLink peer memory (sharded runs) ---------------------------------------------------
+constexpr int KPEERS = MPN_MAX_PEERS;
+struct PeerArgs {
+  int rank, world;
+  double* sums[KPEERS];
+  unsigned long long* flags[KPEERS];
+  float* h[KPEERS];
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// wait until *p >= seq; a protocol bug or a dead peer must surface as a trap, never as a hung GPU
+__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long seq) {
+  if (ld_acquire_sys(p) >= seq) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (ld_acquire_sys(p) < seq) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) __trap();
+  }
+}
+
+// moment all-reduce + constant folding in one kernel: local partials -> my slot -> flag; wait for every rank; add the
+// slots in rank order (the same order on every rank => bit-identical totals); fold.
+__global__ void __launch_bounds__(1024) finalize_peer_kernel(const FinArgs f, const PeerArgs P, unsigned long long seq) {
+  finalize_body(f, 1, 0);                                   // local block partials -> f.sums
+  __syncthreads();
+  const int k = threadIdx.x;
+  const int slot = (int)(seq & 1ull);
+  if (k < SUMS) P.sums[P.rank][slot * SUMS + k] = f.sums[k];
+  __threadfence_system();
+  __syncthreads();
+  if (k == 0) st_release_sys(P.flags[P.rank], seq);
+  if (k < P.world) wait_flag(P.flags[k], seq);
+  __syncthreads();
+  if (k < SUMS) {
+    double t = 0.0;
+    for (int r = 0; r < P.world; ++r) {
+      double v;
+      asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(P.sums[r] + slot * SUMS + k));
+      t += v;
+    }
+    f.sums[k] = t;
+  }
+  __syncthreads();
+  finalize_body(f, 0, 1);
+}
+
+// h all-gather: publish / wait on the second flag word
+__global__ void peer_publish_h_kernel(const PeerArgs P, unsigned long long seq) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(P.flags[P.rank] + 1, seq);
+  }
+}
+__global__ void peer_wait_h_kernel(const PeerArgs P, unsigned long long seq) {
+  if (blockIdx.x == 0 && threadIdx.x < P.world) wait_flag(P.flags[threadIdx.x] + 1, seq);
+}
+
 // called by every block at the end of a sweep kernel, after its partial row has been written
 __device__ __forceinline__ void finalize_in_last_block(const FinArgs& f) {
   if (f.counter == nullptr) return;
@@ -932,16 +996,22 @@ __global__ void __launch_bounds__(NT_THREADS) node_tables_kernel(const float* __
   }
 }
 
-// h'[row] = sum over the row's tasks of msg_task (fixed order)  — the deterministic segment sum of models/mpn.py:202
+// h'[row] = sum over the row's tasks of msg_task (fixed order)  — the deterministic segment sum of models/mpn.py:202.
+// PEERS: the rows are also stored into every other rank's h buffer over NVLink (the per-step all-gather of h).
+template <bool PEERS>
 __global__ void __launch_bounds__(256) node_finalize_kernel(const mpn_graph g, const float* __restrict__ msg_task,
-                                                            float* __restrict__ h_full) {
+                                                            float* __restrict__ h_full, const PeerArgs P) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int n = gwarp; n < g.n_nodes; n += nwarps) {
     float s = 0.f;
     for (int t = g.taskptr[n]; t < g.taskptr[n + 1]; ++t) s += msg_task[(size_t)t * MPN_DH + lane];
-    h_full[(size_t)(g.row_offset + n) * MPN_DH + lane] = s;
+    const size_t o = (size_t)(g.row_offset + n) * MPN_DH + lane;
+    h_full[o] = s;
+    if (PEERS)
+      for (int r = 0; r < P.world; ++r)
+        if (r != P.rank) P.h[r][o] = s;
   }
 }
 
@@ -1246,7 +1316,7 @@ int mpn_plan_reduce(mpn_fwd_plan* p, int32_t stage, int with_consts, void* strea
 int mpn_plan_node_finalize(mpn_fwd_plan* p, int32_t step, void* stream) {
   MPN_REQUIRE(p, "node_finalize: NULL plan");
   (void)step;
-  node_finalize_kernel<<<min(kNumSMs * 8, div_up((long long)p->g.n_nodes * 32, 256)), 256, 0, (cudaStream_t)stream>>>(p->g, p->msg_task, p->h_full);
+  node_finalize_kernel<false><<<min(kNumSMs * 8, div_up((long long)p->g.n_nodes * 32, 256)), 256, 0, (cudaStream_t)stream>>>(p->g, p->msg_task, p->h_full, PeerArgs());
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -1315,6 +1385,86 @@ int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const 
     cudaError_t e = cudaMemcpyAsync(h_out, p->h_full, sizeof(float) * (size_t)g->n_nodes * MPN_DH, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) { set_error("h copy failed: %s", cudaGetErrorString(e)); rc = MPN_ERR_CUDA; }
   }
+#undef STEP_TRY
+done:
+  mpn_plan_destroy(p);
+  return rc;
+}
+
+int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x, const float* edge_attr, int32_t L, int32_t n_cls,
+                        int64_t total_edges, float* logits_out, float* h_out, uint8_t* pred_out, float* prob1_out, int use_tc,
+                        const mpn_peer_ctx* peers, void* ws, size_t ws_bytes, void* stream) {
+  MPN_REQUIRE(g && x && edge_attr && logits_out && peers, "forward_sharded: NULL argument");
+  MPN_REQUIRE(peers->world >= 1 && peers->world <= MPN_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world, "forward_sharded: bad rank/world");
+  MPN_REQUIRE(g->n_graphs <= 1, "forward_sharded: batched graphs cannot be row-sharded");
+  MPN_REQUIRE(L >= 1, "forward_sharded needs num_enc_steps >= 1");
+  PeerArgs P;
+  P.rank = peers->rank;
+  P.world = peers->world;
+  for (int r = 0; r < peers->world; ++r) {
+    MPN_REQUIRE(peers->sums[r] && peers->flags[r] && (L <= 1 || peers->h[r]), "forward_sharded: NULL peer buffer for rank %d", r);
+    P.sums[r] = peers->sums[r];
+    P.flags[r] = (unsigned long long*)peers->flags[r];
+    P.h[r] = peers->h[r];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  mpn_fwd_plan* p = nullptr;
+  MPN_TRY(mpn_plan_create(&p, g, w, L, n_cls, total_edges, use_tc, ws, ws_bytes));
+  if (L > 1) p->h_full = peers->h[peers->rank];            // node tables read the peer-visible buffer
+  p->fuse_fin = 0;
+  int rc = MPN_OK;
+  unsigned long long seq_m = peers->seq_moments, seq_h = peers->seq_h;
+  const size_t lstride = (size_t)g->n_edges * 2;
+#define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
+#define PEER_FINALIZE(stage) do { finalize_peer_kernel<<<1, FIN_THREADS, 0, st>>>(make_fin(p, stage, false), P, ++seq_m); \
+    ++mpn::g_kernel_launches; if (cudaGetLastError() != cudaSuccess) { set_error("finalize_peer launch failed"); rc = MPN_ERR_CUDA; goto done; } } while (0)
+  {
+    SideStream* ss = side_stream();
+    const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
+    STEP_TRY(mpn_plan_node_encoder(p, x, fork ? ss->stream : st));
+    if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
+    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
+    PEER_FINALIZE(MPN_STAGE_ENC0);
+    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
+    PEER_FINALIZE(MPN_STAGE_ENC1);
+    if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
+  }
+  {
+    const int first_class_step = L - n_cls + 1;
+    int k = 0;
+    for (int step = 1; step <= L; ++step) {
+      if (step > 1) {                                       // every rank's rows of h must have landed in my buffer
+        peer_wait_h_kernel<<<1, 32, 0, st>>>(P, seq_h);
+        ++mpn::g_kernel_launches;
+      }
+      STEP_TRY(mpn_plan_node_tables(p, step, st));
+      STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_EDGE, edge_attr, nullptr, nullptr, nullptr, st));
+      PEER_FINALIZE(MPN_STAGE_EDGE);
+      STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_NODE, edge_attr, nullptr, nullptr, nullptr, st));
+      PEER_FINALIZE(MPN_STAGE_NODE);
+      const bool cls = step >= first_class_step;
+      const bool last = step == L;
+      STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_APPLY, edge_attr, cls ? logits_out + lstride * k : nullptr,
+                              (cls && last) ? pred_out : nullptr, (cls && last) ? prob1_out : nullptr, st));
+      if (cls) ++k;
+      const int grid = min(kNumSMs * 8, div_up((long long)g->n_nodes * 32, 256));
+      if (!last) {
+        node_finalize_kernel<true><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P);
+        peer_publish_h_kernel<<<1, 32, 0, st>>>(P, ++seq_h);
+        mpn::g_kernel_launches += 2;
+      } else {
+        node_finalize_kernel<false><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P);
+        ++mpn::g_kernel_launches;
+      }
+      if (cudaGetLastError() != cudaSuccess) { set_error("node_finalize launch failed"); rc = MPN_ERR_CUDA; goto done; }
+    }
+  }
+  if (h_out) {
+    cudaError_t e = cudaMemcpyAsync(h_out, p->h_full + (size_t)g->row_offset * MPN_DH, sizeof(float) * (size_t)g->n_nodes * MPN_DH,
+                                    cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_error("h copy failed: %s", cudaGetErrorString(e)); rc = MPN_ERR_CUDA; }
+  }
+#undef PEER_FINALIZE
 #undef STEP_TRY
 done:
   mpn_plan_destroy(p);

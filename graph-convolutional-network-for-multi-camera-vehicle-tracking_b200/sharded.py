@@ -201,13 +201,86 @@ class CudaPhases:
         return self._h
 
 
+SUMS_BYTES = 2 * _lib.MPN_SUMS_DOUBLES * 8          # two slots of 96 fp64 moment sums
+FLAGS_OFFSET = SUMS_BYTES                            # two uint64 sequence flags
+H_OFFSET = 2048                                      # h buffer [n_cols, 32] fp32 starts here
+
+
+class PeerMemory:
+    """NVLink peer-mapped exchange buffers (torch.distributed._symmetric_memory) for the fused collectives of
+    ``mpn_forward_sharded``: per rank 2 x 96 fp64 moment-sum slots, two sequence flags and an h buffer [n_cols,32]."""
+
+    def __init__(self, n_cols: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        nbytes = H_OFFSET + n_cols * _lib.MPN_DH * 4
+        self.n_cols = n_cols
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)                 # every rank's flags are zero before anyone publishes
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        if self.world > _lib.MPN_MAX_PEERS:
+            raise RuntimeError("at most %d peers" % _lib.MPN_MAX_PEERS)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.seq_moments = 0
+        self.seq_h = 0
+
+    def ctx(self, with_h: bool) -> "_lib.MpnPeerCtx":
+        c = _lib.MpnPeerCtx()
+        c.rank, c.world = self.rank, self.world
+        for r, base in enumerate(self.ptrs):
+            c.sums[r] = base
+            c.flags[r] = base + FLAGS_OFFSET
+            c.h[r] = base + H_OFFSET if with_h else None
+        c.seq_moments, c.seq_h = self.seq_moments, self.seq_h
+        return c
+
+    def advance(self, L: int):
+        self.seq_moments += 2 + 2 * L
+        self.seq_h += max(L - 1, 0)
+
+
 class ShardedMPN:
     """Row-block sharded forward.  Each rank passes its own shard (``edge_index`` rows inside its block, global ids)
-    plus the replicated ``x``; outputs stay sharded (logits of the local edges, h of the local rows)."""
+    plus the replicated ``x``; outputs stay sharded (logits of the local edges, h of the local rows).
 
-    def __init__(self, model, group=None):
+    ``fused=True`` (default): one launch sequence per rank with the collectives inside the kernels over NVLink peer
+    memory (``mpn_forward_sharded``).  If symmetric memory cannot be set up the reason is kept in ``peer_error`` and the
+    NCCL schedule (``sharded_forward``: all-reduce / all-gather between phases) is used instead.
+    """
+
+    def __init__(self, model, group=None, fused: bool = True):
         self.model = model
         self.comm = TorchComm(group)
+        self.fused = fused and self.comm.world > 1
+        self.peers = None
+        self.peer_error = None
+        self._totals = {}
+
+    def _total_edges(self, g, dev):
+        key = id(g)
+        if key not in self._totals:
+            tot = torch.tensor([g.n_edges], dtype=torch.float64, device=dev)
+            self.comm.all_reduce_sum(tot)
+            if len(self._totals) > 16:
+                self._totals.clear()
+            self._totals[key] = (g, int(tot.item()))
+        return self._totals[key][1]
+
+    def _peer_memory(self, n_cols, dev):
+        if self.peers is not None and self.peers.n_cols == n_cols:
+            return self.peers
+        if self.peer_error is not None:
+            return None
+        try:
+            self.peers = PeerMemory(n_cols, dev, self.comm.group)
+        except Exception as e:                          # noqa: BLE001 - any failure -> NCCL schedule, reason recorded
+            self.peer_error = "%s: %s" % (type(e).__name__, e)
+            self.peers = None
+        return self.peers
 
     @torch.no_grad()
     def forward(self, x, local_edge_index, local_edge_attr, blocks, fuse_decisions=False, graph=None):
@@ -221,14 +294,30 @@ class ShardedMPN:
         W = m._weights(dev)
         L, n_cls = int(m.num_enc_steps), int(m.num_class_steps)
         n_out = 1 if L == 0 else n_cls
-        tot = torch.tensor([g.n_edges], dtype=torch.float64, device=dev)
-        comm.all_reduce_sum(tot)
+        total = self._total_edges(g, dev)
+        x = x.contiguous().float()
+        ea = local_edge_attr.contiguous().float()
         logits = torch.empty(max(n_out, 1), g.n_edges, 2, dtype=torch.float32, device=dev)
         pred = torch.empty(g.n_edges, dtype=torch.uint8, device=dev) if fuse_decisions else None
         prob1 = torch.empty(g.n_edges, dtype=torch.float32, device=dev) if fuse_decisions else None
+        peers = self._peer_memory(x.shape[0], dev) if (self.fused and L >= 1) else None
+        if peers is not None:
+            lib = _lib.lib()
+            need = lib.mpn_forward_workspace_bytes(g.ref, C.byref(W), L)
+            ws = workspace("forward_sharded", dev, need)
+            h_local = torch.empty(g.n_nodes, _lib.MPN_DH, dtype=torch.float32, device=dev)
+            ctx = peers.ctx(with_h=L > 1)
+            with torch.cuda.device(dev):
+                _lib.check(lib.mpn_forward_sharded(g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, total,
+                                                   logits.data_ptr(), h_local.data_ptr(),
+                                                   pred.data_ptr() if pred is not None else None,
+                                                   prob1.data_ptr() if prob1 is not None else None,
+                                                   int(bool(USE_TENSOR_CORES)), C.byref(ctx), ws.data_ptr(), ws.numel(),
+                                                   current_stream_ptr(dev)))
+            peers.advance(L)
+            return {'classified_edges': [logits[i] for i in range(n_out)]}, h_local, pred, prob1
         with torch.cuda.device(dev):
-            ph = CudaPhases(g, W, x.contiguous().float(), local_edge_attr.contiguous().float(), L, n_cls, int(tot.item()),
-                            logits, pred, prob1, USE_TENSOR_CORES)
+            ph = CudaPhases(g, W, x, ea, L, n_cls, total, logits, pred, prob1, USE_TENSOR_CORES)
             try:
                 sharded_forward(ph, comm, L, n_cls, blocks)
                 h_local = ph.h_full()[n0:n1].clone()

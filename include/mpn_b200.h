@@ -200,6 +200,31 @@ int mpn_plan_node_finalize(mpn_fwd_plan* plan, int32_t step, void* stream);
 float* mpn_plan_h_full(mpn_fwd_plan* plan);     /* dev [n_cols,32]: row block [row_offset, +n_nodes) is this rank's */
 
 /* ------------------------------------------------------------------------------------------------
+ * Sharded forward with the collectives fused into the kernels over NVLink peer memory (one launch sequence per rank,
+ * no host round trips): every BatchNorm's moment all-reduce happens inside the finalize kernel (each rank publishes its
+ * 96 fp64 sums in a peer-mapped slot, raises a sequence flag with st.release.sys, then adds all ranks' slots in rank
+ * order — bit-identical totals on every rank), and for L > 1 the node-finalize kernel stores its rows of h straight into
+ * every peer's h buffer (the all-gather).  `sums[r]`, `flags[r]`, `h[r]` are rank r's buffers as mapped into THIS
+ * process (e.g. torch.distributed._symmetric_memory); layout per rank: sums = 2 slots x 96 doubles, flags = 2 uint64
+ * (moment sequence, h sequence; zero-initialised, monotonic across calls), h = [n_cols,32] fp32 (may be NULL if L <= 1).
+ * All ranks must call with the same seq_moments / seq_h; the call consumes 2+2L moment and max(L-1,0) h sequence numbers.
+ * Every wait traps after 10 s instead of hanging the GPU.
+ * ---------------------------------------------------------------------------------------------- */
+#define MPN_MAX_PEERS 16
+typedef struct mpn_peer_ctx {
+  int32_t rank, world;
+  double* sums[MPN_MAX_PEERS];
+  uint64_t* flags[MPN_MAX_PEERS];
+  float* h[MPN_MAX_PEERS];
+  uint64_t seq_moments;     /* last moment sequence number already used (this call uses seq_moments+1 ...) */
+  uint64_t seq_h;           /* last h sequence number already used */
+} mpn_peer_ctx;
+int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x_dev, const float* edge_attr_dev,
+                        int32_t num_enc_steps, int32_t num_class_steps, int64_t total_edges, float* logits_out_dev,
+                        float* h_out_dev /* [g->n_nodes,32] local rows */, uint8_t* pred_out_dev, float* prob1_out_dev,
+                        int use_tensor_cores, const mpn_peer_ctx* peers, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Decisions.  Replaces inference.py:475-479 when the caller owns the logits.
  * ---------------------------------------------------------------------------------------------- */
 int mpn_decide(const float* logits_dev, int64_t n_edges, uint8_t* pred_out_dev, float* prob1_out_dev, void* stream);
