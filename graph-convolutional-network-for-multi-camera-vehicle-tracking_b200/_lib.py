@@ -45,7 +45,10 @@ MPN_MAX_PEERS = 16
 class MpnPeerCtx(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("sums", C.c_void_p * MPN_MAX_PEERS),
                 ("flags", C.c_void_p * MPN_MAX_PEERS), ("h", C.c_void_p * MPN_MAX_PEERS),
-                ("seq_moments", C.c_uint64), ("seq_h", C.c_uint64)]
+                ("cstats", C.c_void_p * MPN_MAX_PEERS),
+                ("seq_moments", C.c_uint64), ("seq_h", C.c_uint64), ("seq_c", C.c_uint64),
+                ("shard_node_encoder", C.c_int32), ("reserved", C.c_int32)]
+MPN_PEER_CSTAT_COLS = 1024
 
 
 class MpnError(RuntimeError):
@@ -122,7 +125,7 @@ def lib():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.mpn_abi_version() != 2:
+        if l.mpn_abi_version() != 3:
             raise ImportError("libmpn_b200.so ABI version mismatch")
         _lib = l
     return _lib

@@ -124,6 +124,8 @@ struct FinArgs {
   const float* small;
   double n_total;
   unsigned int* counter;      // != nullptr: fuse into the producing kernel's last block
+  double* n_total_dev;        // != nullptr: total edge count lives on the device (exchanged with the first all-reduce)
+  double local_edges;         // this rank's edge count (sharded runs)
 };
 
 __device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, int do_consts) {
@@ -155,7 +157,7 @@ __device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, i
   }
   __syncthreads();
   if (!do_consts) return;
-  const double inv_n = 1.0 / f.n_total;
+  const double inv_n = 1.0 / (f.n_total_dev ? *f.n_total_dev : f.n_total);
   if (stage == MPN_STAGE_ENC0) {
     // static constants
     if (k < 16) consts[FC_EDGE_WE + k] = small[MPN_W_EDGE_W + (k >> 2) * 68 + 64 + (k & 3)];
@@ -223,6 +225,7 @@ struct PeerArgs {
   double* sums[KPEERS];
   unsigned long long* flags[KPEERS];
   float* h[KPEERS];
+  double* cstats[KPEERS];
 };
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -250,6 +253,9 @@ __global__ void __launch_bounds__(1024) finalize_peer_kernel(const FinArgs f, co
   __syncthreads();
   const int k = threadIdx.x;
   const int slot = (int)(seq & 1ull);
+  // the first all-reduce of a forward also carries the edge counts (last, otherwise unused, slot entry)
+  if (k == SUMS - 1 && f.stage == MPN_STAGE_ENC0 && f.n_total_dev) f.sums[SUMS - 1] = f.local_edges;
+  __syncthreads();
   if (k < SUMS) P.sums[P.rank][slot * SUMS + k] = f.sums[k];
   __threadfence_system();
   __syncthreads();
@@ -264,6 +270,7 @@ __global__ void __launch_bounds__(1024) finalize_peer_kernel(const FinArgs f, co
       t += v;
     }
     f.sums[k] = t;
+    if (k == SUMS - 1 && f.stage == MPN_STAGE_ENC0 && f.n_total_dev) *f.n_total_dev = t;
   }
   __syncthreads();
   finalize_body(f, 0, 1);
@@ -820,6 +827,8 @@ __global__ void __launch_bounds__(128) graph_finalize_kernel(int stage, const mp
   f.small = small;
   f.n_total = (double)(g.rowptr[n1] - g.rowptr[n0]);
   f.counter = nullptr;
+  f.n_total_dev = nullptr;
+  f.local_edges = 0.0;
   finalize_body(f, 0, 1);
 }
 
@@ -919,6 +928,7 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
     part[((size_t)blockIdx.y * Nc + col) * 2 + 0] = s;
     part[((size_t)blockIdx.y * Nc + col) * 2 + 1] = q;
   }
+  if (tile_counter == nullptr) return;                    // partials only (sharded encoder: reduced across ranks next)
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_ticket = atomicAdd(&tile_counter[blockIdx.x], 1u);
@@ -939,6 +949,61 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
     shift[col] = (float)((double)beta[col] - sc * mean);
   }
   if (threadIdx.x == 0) tile_counter[blockIdx.x] = 0u;
+}
+
+// sharded node encoder: column sums of this rank's rows -> my slot -> flag; wait; add all ranks' slots in rank order;
+// fold into the BatchNorm scale/shift over ALL M_total rows.  One block, one thread per column (Nc <= 1024).
+__global__ void __launch_bounds__(1024) colstats_peer_kernel(const double* __restrict__ part, int splits, int Nc, int M_total,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ scale, float* __restrict__ shift,
+                                                             const PeerArgs P, unsigned long long seq) {
+  const int col = threadIdx.x;
+  const int slot = (int)(seq & 1ull);
+  double* mine = P.cstats[P.rank] + (size_t)slot * MPN_PEER_CSTAT_COLS * 2;
+  if (col < Nc) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < splits; ++i) {
+      s += part[((size_t)i * Nc + col) * 2 + 0];
+      q += part[((size_t)i * Nc + col) * 2 + 1];
+    }
+    mine[2 * col] = s;
+    mine[2 * col + 1] = q;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (col == 0) st_release_sys(P.flags[P.rank] + 2, seq);
+  if (col < P.world) wait_flag(P.flags[col] + 2, seq);
+  __syncthreads();
+  if (col < Nc) {
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < P.world; ++r) {
+      const double* src = P.cstats[r] + (size_t)slot * MPN_PEER_CSTAT_COLS * 2 + 2 * col;
+      double a, b;
+      asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(a) : "l"(src));
+      asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(b) : "l"(src + 1));
+      s += a;
+      q += b;
+    }
+    const double mean = s / M_total;
+    double var = q / M_total - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double sc = (double)gamma[col] / sqrt(var + (double)BN_EPS);
+    scale[col] = (float)sc;
+    shift[col] = (float)((double)beta[col] - sc * mean);
+  }
+}
+
+// final BatchNorm+ReLU of the sharded encoder: this rank's rows of h, stored locally and into every peer's h buffer
+__global__ void bn_relu_apply_peer_kernel(const float* __restrict__ Y, int rows, int row_offset, const float* __restrict__ scale,
+                                          const float* __restrict__ shift, const PeerArgs P) {
+  const long long total = (long long)rows * MPN_DH;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % MPN_DH);
+    const float v = fmaxf(fmaf(Y[i], scale[c], shift[c]), 0.f);
+    const size_t o = (size_t)row_offset * MPN_DH + (size_t)i;
+    for (int r = 0; r < P.world; ++r) P.h[r][o] = v;
+  }
 }
 
 __global__ void bn_relu_apply_kernel(const float* __restrict__ Y, long long total, int Nc, const float* __restrict__ scale,
@@ -1035,6 +1100,8 @@ struct mpn_fwd_plan {
   unsigned int* col_counter;   // [max_dim/32 + 1] ticket counters of the column-statistics tiles
   int fuse_fin;               // single-GPU: the last block of each moment sweep folds the constants itself
   int n_graphs;               // > 1: batched small graphs, BatchNorm statistics per graph
+  double* n_total_dev;        // total edge count of the whole (sharded) graph, filled by the first fused all-reduce
+  int n_total_on_device;
   double* task_part;          // [max_tasks][TASK_PART] per-task moment partials (batched)
   void* gemm_ws;
   size_t gemm_ws_bytes;
@@ -1065,6 +1132,7 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.partials2 = a.take<double>((size_t)NM_GRID * SUMS);
   p.sums = a.take<double>(G * SUMS);
   p.fin_counter = a.take<unsigned int>(1);
+  p.n_total_dev = a.take<double>(1);
   p.col_counter = a.take<unsigned int>((size_t)(max_dim > 0 ? max_dim : 1) / 32 + 1);
   p.ybuf = (p.L > 1) ? a.take<float>((size_t)g.n_edges * 4) : nullptr;
   size_t gw = 0;
@@ -1143,6 +1211,8 @@ static FinArgs make_fin(const mpn_fwd_plan* p, int stage, bool fused) {
   f.small = p->w.small;
   f.n_total = (double)p->total_edges;
   f.counter = fused ? p->fin_counter : nullptr;
+  f.n_total_dev = p->n_total_on_device ? p->n_total_dev : nullptr;
+  f.local_edges = (double)p->g.n_edges;
   return f;
 }
 
@@ -1183,6 +1253,40 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
     sh = p->colshift;
   }
   bn_relu_apply_kernel<<<min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st>>>(in, (long long)M * MPN_DH, MPN_DH, sc, sh, batched ? p->g.node_gid : nullptr, p->h_full);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+// node encoder over this rank's row block only; BatchNorm column sums all-reduced through peer memory per layer;
+// the encoded rows land in every rank's h buffer (publish of the h flag is left to the caller)
+static int node_encoder_sharded(mpn_fwd_plan* p, const float* x, const PeerArgs& P, unsigned long long& seq_c, cudaStream_t st) {
+  const int M = p->g.n_nodes, off = p->g.row_offset;
+  const float* in = x + (size_t)off * p->w.node_dims[0];
+  float* bufs[2] = {p->act0, p->act1};
+  const float *sc = nullptr, *sh = nullptr;
+  for (int l = 0; l < p->w.n_node_layers; ++l) {
+    const int K = p->w.node_dims[l], Nc = p->w.node_dims[l + 1];
+    MPN_REQUIRE(Nc <= MPN_PEER_CSTAT_COLS, "sharded node encoder: layer width %d > %d", Nc, MPN_PEER_CSTAT_COLS);
+    float* out = bufs[l & 1];
+    if (p->use_tc && gemm_tc_supported(M, Nc, K))
+      MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh,
+                         p->w.node_w_hi[l], p->w.node_w_lo[l], nullptr));
+    else
+      MPN_TRY(gemm_nt_simt(in, p->w.node_w[l], p->w.node_b[l], sc, sh, out, M, Nc, K, st, nullptr));
+    int splits = div_up(M, 256);
+    splits = splits > CS_ROWSPLIT_MAX ? CS_ROWSPLIT_MAX : splits;
+    const int rps = div_up(M, splits);
+    colstats_kernel<<<dim3(div_up(Nc, 32), splits), 256, 0, st>>>(out, M, Nc, rps, p->colpart, nullptr, p->w.node_gamma[l],
+                                                                  p->w.node_beta[l], p->colscale, p->colshift);
+    MPN_LAUNCH_OK();
+    colstats_peer_kernel<<<1, 1024, 0, st>>>(p->colpart, splits, Nc, p->g.n_cols, p->w.node_gamma[l], p->w.node_beta[l], p->colscale,
+                                            p->colshift, P, ++seq_c);
+    MPN_LAUNCH_OK();
+    in = out;
+    sc = p->colscale;
+    sh = p->colshift;
+  }
+  bn_relu_apply_peer_kernel<<<min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st>>>(in, M, off, sc, sh, P);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -1403,22 +1507,38 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
   P.world = peers->world;
   for (int r = 0; r < peers->world; ++r) {
     MPN_REQUIRE(peers->sums[r] && peers->flags[r] && (L <= 1 || peers->h[r]), "forward_sharded: NULL peer buffer for rank %d", r);
+    MPN_REQUIRE(!peers->shard_node_encoder || (peers->h[r] && peers->cstats[r]), "forward_sharded: sharded encoder needs h and cstats buffers");
     P.sums[r] = peers->sums[r];
     P.flags[r] = (unsigned long long*)peers->flags[r];
     P.h[r] = peers->h[r];
+    P.cstats[r] = peers->cstats[r];
   }
+  const bool shard_enc = peers->shard_node_encoder != 0;
   cudaStream_t st = (cudaStream_t)stream;
   mpn_fwd_plan* p = nullptr;
-  MPN_TRY(mpn_plan_create(&p, g, w, L, n_cls, total_edges, use_tc, ws, ws_bytes));
-  if (L > 1) p->h_full = peers->h[peers->rank];            // node tables read the peer-visible buffer
+  // total_edges <= 0: the ranks' edge counts travel with the first fused all-reduce (no host collective at all)
+  MPN_TRY(mpn_plan_create(&p, g, w, L, n_cls, total_edges > 0 ? total_edges : (int64_t)1 << 40, use_tc, ws, ws_bytes));
+  p->n_total_on_device = total_edges > 0 ? 0 : 1;
+  if (L > 1 || shard_enc) p->h_full = peers->h[peers->rank];            // node tables read the peer-visible buffer
   p->fuse_fin = 0;
   int rc = MPN_OK;
-  unsigned long long seq_m = peers->seq_moments, seq_h = peers->seq_h;
+  unsigned long long seq_m = peers->seq_moments, seq_h = peers->seq_h, seq_c = peers->seq_c;
+  bool h_pending = false;                                   // an h exchange has been published and not yet awaited
   const size_t lstride = (size_t)g->n_edges * 2;
 #define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
 #define PEER_FINALIZE(stage) do { finalize_peer_kernel<<<1, FIN_THREADS, 0, st>>>(make_fin(p, stage, false), P, ++seq_m); \
     ++mpn::g_kernel_launches; if (cudaGetLastError() != cudaSuccess) { set_error("finalize_peer launch failed"); rc = MPN_ERR_CUDA; goto done; } } while (0)
-  {
+  if (shard_enc) {
+    // every rank encodes its own rows; column statistics and the encoded rows travel over NVLink inside the kernels
+    STEP_TRY(node_encoder_sharded(p, x, P, seq_c, st));
+    peer_publish_h_kernel<<<1, 32, 0, st>>>(P, ++seq_h);
+    ++mpn::g_kernel_launches;
+    h_pending = true;
+    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
+    PEER_FINALIZE(MPN_STAGE_ENC0);
+    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
+    PEER_FINALIZE(MPN_STAGE_ENC1);
+  } else {
     SideStream* ss = side_stream();
     const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
     STEP_TRY(mpn_plan_node_encoder(p, x, fork ? ss->stream : st));
@@ -1433,9 +1553,10 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
     const int first_class_step = L - n_cls + 1;
     int k = 0;
     for (int step = 1; step <= L; ++step) {
-      if (step > 1) {                                       // every rank's rows of h must have landed in my buffer
+      if (h_pending) {                                      // every rank's rows of h must have landed in my buffer
         peer_wait_h_kernel<<<1, 32, 0, st>>>(P, seq_h);
         ++mpn::g_kernel_launches;
+        h_pending = false;
       }
       STEP_TRY(mpn_plan_node_tables(p, step, st));
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_EDGE, edge_attr, nullptr, nullptr, nullptr, st));
@@ -1452,6 +1573,7 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
         node_finalize_kernel<true><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P);
         peer_publish_h_kernel<<<1, 32, 0, st>>>(P, ++seq_h);
         mpn::g_kernel_launches += 2;
+        h_pending = true;
       } else {
         node_finalize_kernel<false><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P);
         ++mpn::g_kernel_launches;

@@ -202,8 +202,9 @@ class CudaPhases:
 
 
 SUMS_BYTES = 2 * _lib.MPN_SUMS_DOUBLES * 8          # two slots of 96 fp64 moment sums
-FLAGS_OFFSET = SUMS_BYTES                            # two uint64 sequence flags
-H_OFFSET = 2048                                      # h buffer [n_cols, 32] fp32 starts here
+FLAGS_OFFSET = SUMS_BYTES                            # three uint64 sequence flags (moments, h, column stats)
+CSTATS_OFFSET = 2048                                 # two slots of [1024][2] fp64 column sums (sharded node encoder)
+H_OFFSET = CSTATS_OFFSET + 2 * _lib.MPN_PEER_CSTAT_COLS * 2 * 8        # h buffer [n_cols, 32] fp32 starts here
 
 
 class PeerMemory:
@@ -225,22 +226,24 @@ class PeerMemory:
         if self.world > _lib.MPN_MAX_PEERS:
             raise RuntimeError("at most %d peers" % _lib.MPN_MAX_PEERS)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        self.seq_moments = 0
-        self.seq_h = 0
+        self.seq_moments = self.seq_h = self.seq_c = 0
 
-    def ctx(self, with_h: bool) -> "_lib.MpnPeerCtx":
+    def ctx(self, shard_encoder: bool) -> "_lib.MpnPeerCtx":
         c = _lib.MpnPeerCtx()
         c.rank, c.world = self.rank, self.world
         for r, base in enumerate(self.ptrs):
             c.sums[r] = base
             c.flags[r] = base + FLAGS_OFFSET
-            c.h[r] = base + H_OFFSET if with_h else None
-        c.seq_moments, c.seq_h = self.seq_moments, self.seq_h
+            c.cstats[r] = base + CSTATS_OFFSET
+            c.h[r] = base + H_OFFSET
+        c.seq_moments, c.seq_h, c.seq_c = self.seq_moments, self.seq_h, self.seq_c
+        c.shard_node_encoder = int(shard_encoder)
         return c
 
-    def advance(self, L: int):
+    def advance(self, L: int, shard_encoder: bool, n_layers: int):
         self.seq_moments += 2 + 2 * L
-        self.seq_h += max(L - 1, 0)
+        self.seq_h += max(L - 1, 0) + (1 if shard_encoder else 0)
+        self.seq_c += n_layers if shard_encoder else 0
 
 
 class ShardedMPN:
@@ -252,8 +255,9 @@ class ShardedMPN:
     NCCL schedule (``sharded_forward``: all-reduce / all-gather between phases) is used instead.
     """
 
-    def __init__(self, model, group=None, fused: bool = True):
+    def __init__(self, model, group=None, fused: bool = True, shard_node_encoder: bool = True):
         self.model = model
+        self.shard_node_encoder = shard_node_encoder
         self.comm = TorchComm(group)
         self.fused = fused and self.comm.world > 1
         self.peers = None
@@ -283,7 +287,8 @@ class ShardedMPN:
         return self.peers
 
     @torch.no_grad()
-    def forward(self, x, local_edge_index, local_edge_attr, blocks, fuse_decisions=False, graph=None):
+    def forward(self, x, local_edge_index, local_edge_attr, blocks, fuse_decisions=False, graph=None, total_edges=None):
+        """``total_edges``: number of edges of the WHOLE graph if the caller knows it (saves one all-reduce + host sync)."""
         from .mpn import USE_TENSOR_CORES
         m, comm = self.model, self.comm
         dev = x.device
@@ -294,7 +299,6 @@ class ShardedMPN:
         W = m._weights(dev)
         L, n_cls = int(m.num_enc_steps), int(m.num_class_steps)
         n_out = 1 if L == 0 else n_cls
-        total = self._total_edges(g, dev)
         x = x.contiguous().float()
         ea = local_edge_attr.contiguous().float()
         logits = torch.empty(max(n_out, 1), g.n_edges, 2, dtype=torch.float32, device=dev)
@@ -302,11 +306,14 @@ class ShardedMPN:
         prob1 = torch.empty(g.n_edges, dtype=torch.float32, device=dev) if fuse_decisions else None
         peers = self._peer_memory(x.shape[0], dev) if (self.fused and L >= 1) else None
         if peers is not None:
+            total = int(total_edges) if total_edges is not None else -1      # -1: summed on the device, no host collective
             lib = _lib.lib()
             need = lib.mpn_forward_workspace_bytes(g.ref, C.byref(W), L)
             ws = workspace("forward_sharded", dev, need)
             h_local = torch.empty(g.n_nodes, _lib.MPN_DH, dtype=torch.float32, device=dev)
-            ctx = peers.ctx(with_h=L > 1)
+            n_layers = int(W.n_node_layers)
+            shard_enc = self.shard_node_encoder and max(W.node_dims[1:n_layers + 1]) <= _lib.MPN_PEER_CSTAT_COLS
+            ctx = peers.ctx(shard_enc)
             with torch.cuda.device(dev):
                 _lib.check(lib.mpn_forward_sharded(g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, total,
                                                    logits.data_ptr(), h_local.data_ptr(),
@@ -314,8 +321,9 @@ class ShardedMPN:
                                                    prob1.data_ptr() if prob1 is not None else None,
                                                    int(bool(USE_TENSOR_CORES)), C.byref(ctx), ws.data_ptr(), ws.numel(),
                                                    current_stream_ptr(dev)))
-            peers.advance(L)
+            peers.advance(L, shard_enc, n_layers)
             return {'classified_edges': [logits[i] for i in range(n_out)]}, h_local, pred, prob1
+        total = int(total_edges) if total_edges is not None else self._total_edges(g, dev)
         with torch.cuda.device(dev):
             ph = CudaPhases(g, W, x, ea, L, n_cls, total, logits, pred, prob1, USE_TENSOR_CORES)
             try:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPN_B200_ABI_VERSION 2
+#define MPN_B200_ABI_VERSION 3
 
 enum {
   MPN_OK = 0,
@@ -206,8 +206,13 @@ float* mpn_plan_h_full(mpn_fwd_plan* plan);     /* dev [n_cols,32]: row block [r
  * order — bit-identical totals on every rank), and for L > 1 the node-finalize kernel stores its rows of h straight into
  * every peer's h buffer (the all-gather).  `sums[r]`, `flags[r]`, `h[r]` are rank r's buffers as mapped into THIS
  * process (e.g. torch.distributed._symmetric_memory); layout per rank: sums = 2 slots x 96 doubles, flags = 2 uint64
- * (moment sequence, h sequence; zero-initialised, monotonic across calls), h = [n_cols,32] fp32 (may be NULL if L <= 1).
- * All ranks must call with the same seq_moments / seq_h; the call consumes 2+2L moment and max(L-1,0) h sequence numbers.
+ * (moment sequence, h sequence, column-stat sequence; zero-initialised, monotonic across calls), h = [n_cols,32] fp32,
+ * cstats = 2 slots x MPN_PEER_CSTAT_COLS x 2 doubles.  With shard_node_encoder != 0 every rank encodes only its own row
+ * block of x: the per-column BatchNorm sums of each encoder layer are all-reduced through `cstats` inside a kernel and
+ * the encoded rows are stored into every peer's h buffer (needs h != NULL and encoder widths <= MPN_PEER_CSTAT_COLS).
+ * total_edges <= 0: the edge count of the whole graph is summed on the device with the first moment all-reduce.
+ * All ranks must call with the same sequence numbers; the call consumes 2+2L moment numbers, L-1 (+1 with a sharded
+ * encoder) h numbers and, with a sharded encoder, one column-stat number per encoder layer.
  * Every wait traps after 10 s instead of hanging the GPU.
  * ---------------------------------------------------------------------------------------------- */
 #define MPN_MAX_PEERS 16
@@ -216,9 +221,14 @@ typedef struct mpn_peer_ctx {
   double* sums[MPN_MAX_PEERS];
   uint64_t* flags[MPN_MAX_PEERS];
   float* h[MPN_MAX_PEERS];
+  double* cstats[MPN_MAX_PEERS];
   uint64_t seq_moments;     /* last moment sequence number already used (this call uses seq_moments+1 ...) */
   uint64_t seq_h;           /* last h sequence number already used */
+  uint64_t seq_c;           /* last column-stat sequence number already used */
+  int32_t shard_node_encoder;
+  int32_t reserved;
 } mpn_peer_ctx;
+#define MPN_PEER_CSTAT_COLS 1024
 int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x_dev, const float* edge_attr_dev,
                         int32_t num_enc_steps, int32_t num_class_steps, int64_t total_edges, float* logits_out_dev,
                         float* h_out_dev /* [g->n_nodes,32] local rows */, uint8_t* pred_out_dev, float* prob1_out_dev,
