@@ -427,3 +427,18 @@ def test_scc_with_one_directional_cycles(m):
     IDc, _ = m.post_processing(8, None, None, pred, None, {"CUTTING": False, "PRUNING": True, "SPLITTING": True}, data, prob,
                                numbering="canonical")
     assert IDc.numpy().tolist() == [0, 0, 0, 0, 0, 0, 6, 7, 8, 9]
+
+
+def test_multi_gpu_fused_collectives_torchrun(m):
+    """N>1 on real GPUs (skipped on a single-GPU box): fused peer-memory collectives and the NCCL schedule vs the oracle."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+           "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(root, "tests", "dist_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0 and "dist_gpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
