@@ -349,20 +349,20 @@ def run_ours(args):
 
     def e2e_cameras():
         dx.copy_(hx, non_blocking=True)
-        g = m.TrackletGraph.from_cameras(cam_host, dev)                    # K0 from camera ids, on the device
-        batch.x, batch.mpn_graph = dx, g
-        batch.edge_attr = m.edge_features(dx, None, graph=g)
-        net(batch)
-        return net.last_pred
+        if world == 1:
+            g = m.TrackletGraph.from_cameras(cam_host, dev)                # K0 from camera ids, on the device
+            batch.x, batch.mpn_graph = dx, g
+            batch.edge_attr = m.edge_features(dx, None, graph=g)
+            net(batch)
+            return net.last_pred
+        g = m.TrackletGraph.from_cameras(cam_host, dev, row_block=blocks[rank])
+        ea = m.edge_features(dx, None, graph=g)
+        return sharded.forward(dx, None, ea, blocks, fuse_decisions=True, graph=g)[2]
 
     e2e_ei_ms = e2e_loop(e2e_edge_index)
-    if world == 1:
-        e2e_ms = e2e_loop(e2e_cameras)
-        batch.mpn_graph = None
-        h2d = hx.numel() * 4 + cam_host.size * 8
-    else:
-        e2e_ms = e2e_ei_ms
-        h2d = hx.numel() * 4 + hei.numel() * 8
+    e2e_ms = e2e_loop(e2e_cameras)
+    batch.mpn_graph = None
+    h2d = hx.numel() * 4 + cam_host.size * 8
     d2h = hpred.numel()
 
     line = None
@@ -377,8 +377,7 @@ def run_ours(args):
                            "timing": "CUDA events per step on the launching stream, max over ranks, summed over steps"},
                 "e2e": {"value": E_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms,
-                        "inputs": "host node features [N,2048] f32 + camera ids (graph tables built on the device)" if world == 1
-                                  else "host node features + int64 edge_index shard",
+                        "inputs": "host node features [N,2048] f32 + camera ids (graph tables built on the device)",
                         "int64_edge_index": {"value": E_total / (e2e_ei_ms * 1e-3), "ms_per_step": e2e_ei_ms,
                                              "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8}},
                 "gpu_launches": int(launches), "clocks": clk}

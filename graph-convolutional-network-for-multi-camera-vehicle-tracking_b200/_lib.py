@@ -72,6 +72,7 @@ _PROTOS = {
     "mpn_graph_build": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p]),
     "mpn_graph_build_i32": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_cross_camera_edges": (C.c_int64, [C.c_void_p, C.c_int32]),
+    "mpn_cross_camera_block_edges": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "mpn_graph_build_cross_camera": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mpn_edge_features_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph), C.c_int32]),
     "mpn_edge_features": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -119,28 +119,33 @@ struct CamLayout {
   long long ebase[MPN_MAX_CAMERAS + 1];    // first edge of each camera's row block
 };
 
-// dense cross-camera graph straight from the camera layout: row r (camera k) lists every node outside [ptr[k], ptr[k+1])
-__global__ void __launch_bounds__(256) cross_camera_kernel(const CamLayout L, int n_nodes, long long E, int* __restrict__ rowptr,
-                                                           int* __restrict__ col32, long long* __restrict__ edge_index_out) {
+// dense cross-camera graph straight from the camera layout: row r (camera k) lists every node outside [ptr[k], ptr[k+1]).
+// Works on a row block [row0, row0 + n_rows): local edge e corresponds to global edge e + gbase.
+__global__ void __launch_bounds__(256) cross_camera_kernel(const CamLayout L, int n_total, int row0, int n_rows, long long gbase,
+                                                           long long E, int* __restrict__ rowptr, int* __restrict__ col32,
+                                                           long long* __restrict__ edge_index_out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (long long r = tid; r <= n_nodes; r += stride) {            // rowptr
+  for (long long lr = tid; lr <= n_rows; lr += stride) {            // rowptr of the local rows
+    const long long r = row0 + lr;
+    if (lr == n_rows) { rowptr[lr] = (int)E; continue; }
     int k = 0;
     while (k + 1 < L.n_cams && r >= L.ptr[k + 1]) ++k;
-    const long long deg = n_nodes - (L.ptr[k + 1] - L.ptr[k]);
-    rowptr[r] = (r == n_nodes) ? (int)E : (int)(L.ebase[k] + (r - L.ptr[k]) * deg);
+    const long long deg = n_total - (L.ptr[k + 1] - L.ptr[k]);
+    rowptr[lr] = (int)(L.ebase[k] + (r - L.ptr[k]) * deg - gbase);
   }
-  for (long long e = tid; e < E; e += stride) {
+  for (long long le = tid; le < E; le += stride) {
+    const long long e = le + gbase;
     int k = 0;
     while (k + 1 < L.n_cams && e >= L.ebase[k + 1]) ++k;
     const int lo = L.ptr[k], nk = L.ptr[k + 1] - lo;
-    const long long deg = n_nodes - nk;
+    const long long deg = n_total - nk;
     const long long off = e - L.ebase[k];
     const int row = lo + (int)(off / deg);
     const int idx = (int)(off % deg);
     const int c = idx < lo ? idx : idx + nk;
-    col32[e] = c;
-    if (edge_index_out) { edge_index_out[e] = row; edge_index_out[E + e] = c; }
+    col32[le] = c;
+    if (edge_index_out) { edge_index_out[le] = row; edge_index_out[E + le] = c; }
   }
 }
 
@@ -160,13 +165,32 @@ int64_t mpn_cross_camera_edges(const int32_t* cam_ptr, int32_t n_cams) {
   return e;
 }
 
+// global edge id of the first edge of row r
+static long long cross_camera_row_start(const int32_t* cam_ptr, int n_cams, int n_total, long long r) {
+  long long run = 0;
+  for (int k = 0; k < n_cams; ++k) {
+    const long long nk = cam_ptr[k + 1] - cam_ptr[k], deg = n_total - nk;
+    if (r < cam_ptr[k + 1]) return run + (r - cam_ptr[k]) * deg;
+    run += nk * deg;
+  }
+  return run;
+}
+
+int64_t mpn_cross_camera_block_edges(const int32_t* cam_ptr, int32_t n_cams, int32_t row0, int32_t n_rows) {
+  if (!cam_ptr || n_cams < 1 || row0 < 0 || n_rows < 0 || row0 + n_rows > cam_ptr[n_cams]) return -1;
+  const int n_total = cam_ptr[n_cams];
+  return cross_camera_row_start(cam_ptr, n_cams, n_total, (long long)row0 + n_rows) - cross_camera_row_start(cam_ptr, n_cams, n_total, row0);
+}
+
 int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n_cams, int64_t* edge_index_out, void* stream) {
   using namespace mpn;
   MPN_REQUIRE(g && cam_ptr, "cross_camera: NULL argument");
   MPN_REQUIRE(n_cams >= 1 && n_cams <= MPN_MAX_CAMERAS, "cross_camera: n_cams must be in [1,%d]", MPN_MAX_CAMERAS);
-  MPN_REQUIRE(cam_ptr[0] == 0 && cam_ptr[n_cams] == g->n_nodes && g->n_cols == g->n_nodes && g->row_offset == 0,
-              "cross_camera: cam_ptr must run from 0 to n_nodes of an unsharded graph");
-  const long long E = mpn_cross_camera_edges(cam_ptr, n_cams);
+  MPN_REQUIRE(cam_ptr[0] == 0 && cam_ptr[n_cams] == g->n_cols && g->row_offset >= 0 && g->row_offset + g->n_nodes <= g->n_cols,
+              "cross_camera: cam_ptr must run from 0 to n_cols and the row block must lie inside it");
+  const int n_total = g->n_cols;
+  const long long gbase = cross_camera_row_start(cam_ptr, n_cams, n_total, g->row_offset);
+  const long long E = cross_camera_row_start(cam_ptr, n_cams, n_total, (long long)g->row_offset + g->n_nodes) - gbase;
   MPN_REQUIRE(E >= 0 && E == g->n_edges, "cross_camera: g->n_edges (%lld) must be %lld", (long long)g->n_edges, E);
   MPN_REQUIRE(E < (1ll << 31), "n_edges must be < 2^31");
   MPN_REQUIRE(g->chunk >= 32 && g->chunk <= 4096 && (g->chunk & (g->chunk - 1)) == 0, "chunk must be a power of two in [32,4096]");
@@ -178,12 +202,12 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n
   for (int k = 0; k <= n_cams; ++k) {
     L.ptr[k] = cam_ptr[k];
     L.ebase[k] = run;
-    if (k < n_cams) run += (long long)(cam_ptr[k + 1] - cam_ptr[k]) * (g->n_nodes - (cam_ptr[k + 1] - cam_ptr[k]));
+    if (k < n_cams) run += (long long)(cam_ptr[k + 1] - cam_ptr[k]) * (n_total - (cam_ptr[k + 1] - cam_ptr[k]));
   }
   cudaStream_t st = (cudaStream_t)stream;
   const long long work = E > g->n_nodes ? E : g->n_nodes + 1;
-  cross_camera_kernel<<<(int)min((long long)kNumSMs * 16, (work + 255) / 256), 256, 0, st>>>(L, g->n_nodes, E, g->rowptr, g->col,
-                                                                                          (long long*)edge_index_out);
+  cross_camera_kernel<<<(int)min((long long)kNumSMs * 16, (work + 255) / 256), 256, 0, st>>>(L, n_total, g->row_offset, g->n_nodes, gbase, E,
+                                                                                          g->rowptr, g->col, (long long*)edge_index_out);
   MPN_LAUNCH_OK();
   task_scan<<<1, 1024, 0, st>>>(g->rowptr, g->n_nodes, g->chunk, g->taskptr, g->n_tasks);
   MPN_LAUNCH_OK();
@@ -191,7 +215,6 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
-
 
 int mpn_abi_version(void) { return MPN_B200_ABI_VERSION; }
 const char* mpn_last_error(void) { return mpn::g_err; }

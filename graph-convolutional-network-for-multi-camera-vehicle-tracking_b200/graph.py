@@ -110,11 +110,12 @@ class TrackletGraph:
         self._keepalive = ei
 
     @classmethod
-    def from_cameras(cls, cam_ids, device, chunk: int = None, materialize_edge_index: bool = False):
+    def from_cameras(cls, cam_ids, device, chunk: int = None, materialize_edge_index: bool = False, row_block=None):
         """Dense cross-camera graph built on the device from the per-node camera ids (inference.py:407-414), without
         the int64 edge_index ever crossing PCIe or being read: 4 B/edge written instead of 16 B read + 4 B written.
         ``cam_ids``: host sequence / array / CPU tensor, nodes grouped by camera in ascending camera order
         (dataset.py:279-281).  ``materialize_edge_index`` also writes the reference's int64 [2,E] tensor (``.edge_index``).
+        ``row_block=(n0, n1)`` builds only the rows of one shard (column ids stay global).
         """
         import numpy as np
         cam = np.asarray(cam_ids.cpu() if isinstance(cam_ids, torch.Tensor) else cam_ids).reshape(-1)
@@ -127,8 +128,11 @@ class TrackletGraph:
         _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
         L = _lib.lib()
         self = object.__new__(cls)
-        self.device, self.n_cols, self.n_nodes, self.row_offset = dev, int(cam.size), int(cam.size), 0
-        self.n_edges = int(L.mpn_cross_camera_edges(cam_ptr.ctypes.data, n_cams))
+        n0, n1 = (0, int(cam.size)) if row_block is None else (int(row_block[0]), int(row_block[1]))
+        self.device, self.n_cols, self.n_nodes, self.row_offset = dev, int(cam.size), n1 - n0, n0
+        self.n_edges = int(L.mpn_cross_camera_block_edges(cam_ptr.ctypes.data, n_cams, n0, n1 - n0))
+        if self.n_edges < 0:
+            raise ValueError("bad row block")
         self.chunk = int(chunk or choose_chunk(self.n_edges))
         self.max_tasks = self.n_edges // self.chunk + self.n_nodes
         i32 = dict(dtype=torch.int32, device=dev)
@@ -140,7 +144,7 @@ class TrackletGraph:
         self.perm = None
         self.n_graphs, self.node_gid, self.graph_nptr, self.max_graph_nodes = 1, None, None, 0
         self.edge_index = torch.empty(2, self.n_edges, dtype=torch.int64, device=dev) if materialize_edge_index else None
-        self.struct = _lib.MpnGraph(self.n_nodes, self.n_cols, 0, self.chunk, self.n_edges, self.max_tasks, 0,
+        self.struct = _lib.MpnGraph(self.n_nodes, self.n_cols, self.row_offset, self.chunk, self.n_edges, self.max_tasks, 0,
                                     self.rowptr.data_ptr(), self.col.data_ptr(), self.taskptr.data_ptr(),
                                     self.task_row.data_ptr(), self.n_tasks.data_ptr(), 1, 0, None, None)
         with torch.cuda.device(dev):

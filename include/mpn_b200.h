@@ -87,10 +87,13 @@ int mpn_graph_build_i32(mpn_graph* g, const int32_t* row_dev, const int32_t* col
 /* Graph construction on the device.  Replaces inference.py:407-414: for every camera
  * ascending, cartesian_prod(nodes in the camera, nodes not in it).  Nodes must be grouped by camera (dataset.py:279-281);
  * cam_ptr_host[k] = first node of camera k, cam_ptr_host[n_cams] = n_nodes (HOST array, n_cams <= 64).  Fills the tables
- * of `g` (g->n_edges must equal sum_k n_k (N - n_k)) directly from the camera layout: the int64 edge_index (16 B/edge) is
- * never read, and only written when edge_index_out_dev != NULL ([2,E] int64, reference layout).  Does not synchronise. */
+ * of `g` (g->n_edges must equal the number of cross-camera edges of its rows) directly from the camera layout: the int64 edge_index (16 B/edge) is
+ * never read, and only written when edge_index_out_dev != NULL ([2,E] int64, reference layout).  Does not synchronise.
+ * A row-block shard (g->row_offset, g->n_nodes inside g->n_cols nodes) builds just its own rows; its edge count is
+ * mpn_cross_camera_block_edges(). */
 #define MPN_MAX_CAMERAS 64
 int64_t mpn_cross_camera_edges(const int32_t* cam_ptr_host, int32_t n_cams);
+int64_t mpn_cross_camera_block_edges(const int32_t* cam_ptr_host, int32_t n_cams, int32_t row0, int32_t n_rows);
 int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr_host, int32_t n_cams, int64_t* edge_index_out_dev,
                                  void* stream);
 

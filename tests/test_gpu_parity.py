@@ -56,6 +56,14 @@ def test_graph_from_cameras_matches_edge_index_path(m):
     assert torch.equal(g1.task_row[:nt], g2.task_row[:nt])
     with pytest.raises(ValueError):
         m.TrackletGraph.from_cameras(torch.tensor([0, 1, 0, 1]), dev())
+    # row-block shards built from the camera layout == shards cut from the edge list
+    for (n0, n1) in [(0, 40), (40, 95), (95, 113)]:
+        lo, hi = m.shard_edges(ei, n0, n1)
+        gs = m.TrackletGraph.from_cameras(cam, dev(), chunk=64, row_block=(n0, n1), materialize_edge_index=True)
+        gr = m.TrackletGraph(ei[:, lo:hi].to(dev()), cam.numel(), chunk=64, row_offset=n0, n_rows=n1 - n0)
+        assert gs.n_edges == hi - lo and torch.equal(gs.edge_index.cpu(), ei[:, lo:hi])
+        assert torch.equal(gs.rowptr, gr.rowptr) and torch.equal(gs.col[:gs.n_edges], gr.col[:gr.n_edges])
+        assert torch.equal(gs.taskptr, gr.taskptr)
     # forward through data.mpn_graph (no edge_index on the data object)
     params = mo.shipped_model_params(1, 1, 64, (48,))
     sd = mo.init_weights(params, "resnet101", 3)
