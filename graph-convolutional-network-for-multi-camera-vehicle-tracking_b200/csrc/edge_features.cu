@@ -42,9 +42,10 @@ __global__ void col_mean_finalize_kernel(const double* __restrict__ part, int n,
   mu[col] = (float)(s / n);
 }
 
-// xc = x - mu; per-row fp64 statistics of the centred row: st[r] = {|a'|^2, sum a', mu.a' + |mu|^2/2, |a|}
+// xc = x - mu; per-row statistics of the centred row (accumulated in fp64, stored as one float4 = one 16-byte gather
+// per edge; the Gram entry they are combined with is itself only fp32-accurate): st[r] = {|a'|^2, sum a', mu.a' + |mu|^2/2, |a|}
 __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu, int n, int D,
-                                                          float* __restrict__ xc, double* __restrict__ st) {
+                                                          float* __restrict__ xc, float4* __restrict__ st) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -63,10 +64,8 @@ __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restric
     }
     sq = warp_sum(sq); sx = warp_sum(sx); md = warp_sum(md); mm = warp_sum(mm);
     if (lane == 0) {
-      st[4 * (size_t)r + 0] = sq;
-      st[4 * (size_t)r + 1] = sx;
-      st[4 * (size_t)r + 2] = md + 0.5 * mm;          // a.b = g' + (mu.a' + |mu|^2/2) + (mu.b' + |mu|^2/2)
-      st[4 * (size_t)r + 3] = sqrt(fmax(sq + 2.0 * md + mm, 0.0));     // |a|
+      // a.b = g' + (mu.a' + |mu|^2/2) + (mu.b' + |mu|^2/2);  |a| = sqrt(|a'|^2 + 2 mu.a' + |mu|^2)
+      st[r] = make_float4((float)sq, (float)sx, (float)(md + 0.5 * mm), (float)sqrt(fmax(sq + 2.0 * md + mm, 0.0)));
     }
   }
 }
@@ -108,7 +107,7 @@ __global__ void __launch_bounds__(256) gram_blockdiag_simt_kernel(const float* _
 // one warp per task (a run of edges of one row): coalesced Gram reads when the row's columns are consecutive
 __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_graph g, int r0, int r1, const float* __restrict__ G,
                                                                   const long long* __restrict__ g_off,
-                                                                  const double* __restrict__ st, int D,
+                                                                  const float4* __restrict__ st, int D,
                                                                   float2* __restrict__ edge_attr,
                                                                   int* __restrict__ refine_list, int* __restrict__ refine_count) {
   const int lane = threadIdx.x & 31;
@@ -121,7 +120,8 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
     const int beg = g.rowptr[row] + (t - g.taskptr[row]) * g.chunk;
     const int end = min(beg + g.chunk, g.rowptr[row + 1]);
     const size_t grow = (size_t)(row + g.row_offset);
-    const double sa = st[4 * grow], xa = st[4 * grow + 1], ma = st[4 * grow + 2], na = st[4 * grow + 3];
+    const float4 sta = st[grow];
+    const double sa = sta.x, xa = sta.y, ma = sta.z, na = sta.w;
     const float* Grow = G + (size_t)(row - r0) * g.n_cols;
     int cshift = 0;
     if (g_off != nullptr) {                               // batched: this row's block-diagonal Gram block
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
       int c[U];
       bool ok[U];
       float gv[U];
-      double sb[U], xb[U], mb[U], nb[U];
+      float sb[U], xb[U], mb[U], nb[U];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const int e = base + 32 * j + lane;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         gv[j] = Grow[c[j] - cshift];
-        const double4 s4 = *reinterpret_cast<const double4*>(st + 4 * (size_t)c[j]);
+        const float4 s4 = __ldg(st + c[j]);
         sb[j] = s4.x; xb[j] = s4.y; mb[j] = s4.z; nb[j] = s4.w;
       }
 #pragma unroll
@@ -153,14 +153,14 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
         if (!ok[j]) continue;
         const int e = base + 32 * j + lane;
         const double gij = gv[j];
-        double d2 = sa + sb[j] - 2.0 * gij + 2.0 * eps * (xa - xb[j]) + D * eps * eps;
-        if (d2 < (double)REFINE_FRACTION * (sa + sb[j])) {
+        double d2 = sa + (double)sb[j] - 2.0 * gij + 2.0 * eps * (xa - (double)xb[j]) + D * eps * eps;
+        if (d2 < (double)REFINE_FRACTION * (sa + (double)sb[j])) {
           const int slot = atomicAdd(refine_count, 1);
           refine_list[slot] = e;
         }
         if (d2 < 0.0) d2 = 0.0;
-        const double ab = gij + ma + mb[j];
-        const float denom = fmaxf((float)(na * nb[j]), COSINE_EPS);
+        const double ab = gij + ma + (double)mb[j];
+        const float denom = fmaxf((float)na * nb[j], COSINE_EPS);
         edge_attr[e] = make_float2(sqrtf((float)d2), 1.0f - (float)ab / denom);
       }
     }
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_grap
 }
 
 struct EfLayout {
-  double* st;
+  float4* st;
   float *mu, *xc;
   double* mu_part;
   float* G;
@@ -218,7 +218,7 @@ struct EfLayout {
 static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) {
   EfLayout L;
   Arena a(ws, ws_bytes);
-  L.st = a.take<double>((size_t)g->n_cols * 4);
+  L.st = a.take<float4>((size_t)g->n_cols);
   L.mu = a.take<float>(D);
   L.mu_part = a.take<double>((size_t)CM_SPLITS * D);
   L.xc = a.take<float>((size_t)g->n_cols * D);

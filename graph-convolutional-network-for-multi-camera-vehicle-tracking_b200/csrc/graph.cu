@@ -40,6 +40,40 @@ __global__ void __launch_bounds__(256) csr_scan_edges(const IdxT* __restrict__ r
   if (bad) atomicOr(flags, bad);
 }
 
+// int64 fast path: two consecutive edges per thread with 16-byte loads (E even, both rows of edge_index 16-byte aligned)
+__global__ void __launch_bounds__(256) csr_scan_edges_x2(const long long* __restrict__ row, const long long* __restrict__ col,
+                                                         long long E, int n_rows, int n_cols, int row_offset,
+                                                         int* __restrict__ rowptr, int* __restrict__ col32, int* __restrict__ flags) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long pairs = E >> 1;
+  int bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+    const longlong2 r2 = *reinterpret_cast<const longlong2*>(row + 2 * i);
+    const longlong2 c2 = *reinterpret_cast<const longlong2*>(col + 2 * i);
+    long long pr = -1, pc = -1;
+    if (i > 0) { pr = row[2 * i - 1] - row_offset; pc = col[2 * i - 1]; }
+    const long long rr[2] = {r2.x - row_offset, r2.y - row_offset}, cc[2] = {c2.x, c2.y};
+    int out[2] = {0, 0};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const long long e = 2 * i + j, r = rr[j], c = cc[j];
+      if (r < 0 || r >= n_rows || c < 0 || c >= n_cols) { bad |= 2; pr = r; pc = c; continue; }
+      out[j] = (int)c;
+      if (e > 0) {
+        if (pr > r || (pr == r && pc >= c)) bad |= 1;
+        if (pr < 0 || pr >= n_rows) pr = r;
+      }
+      for (long long q = pr + 1; q <= r; ++q) rowptr[q] = (int)e;
+      if (e == E - 1)
+        for (long long q = r + 1; q <= n_rows; ++q) rowptr[q] = (int)E;
+      pr = r;
+      pc = c;
+    }
+    *reinterpret_cast<int2*>(col32 + 2 * i) = make_int2(out[0], out[1]);
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
 __global__ void csr_empty(int n_rows, int* rowptr) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_rows; i += gridDim.x * blockDim.x) rowptr[i] = 0;
 }
@@ -91,8 +125,14 @@ static int graph_build_impl(mpn_graph* g, const IdxT* row, const IdxT* col, cuda
     csr_empty<<<div_up(g->n_nodes + 1, 256), 256, 0, st>>>(g->n_nodes, g->rowptr);
   } else {
     int grid = (int)min((long long)kNumSMs * 16, (long long)div_up(g->n_edges, 256));
-    csr_scan_edges<IdxT><<<grid, 256, 0, st>>>(row, col, g->n_edges, g->n_nodes, g->n_cols, g->row_offset,
-                                               g->rowptr, g->col, flags);
+    const bool x2 = sizeof(IdxT) == 8 && (g->n_edges & 1) == 0 && ((((uintptr_t)row) | ((uintptr_t)col)) & 15) == 0 &&
+                    (((uintptr_t)g->col) & 7) == 0;
+    if (x2)
+      csr_scan_edges_x2<<<grid, 256, 0, st>>>((const long long*)row, (const long long*)col, g->n_edges, g->n_nodes, g->n_cols,
+                                              g->row_offset, g->rowptr, g->col, flags);
+    else
+      csr_scan_edges<IdxT><<<grid, 256, 0, st>>>(row, col, g->n_edges, g->n_nodes, g->n_cols, g->row_offset,
+                                                 g->rowptr, g->col, flags);
   }
   MPN_LAUNCH_OK();
   int h_flags = 0;
