@@ -42,42 +42,82 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: an NVML polling thread (2 ms period; the timed region of
+    the default run is only tens of ms, too short for `nvidia-smi -lms`), with `nvidia-smi` as the fallback."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.samples, self.bits, self.max_mhz, self.power = [], 0, None, []
+        self.stop_flag = threading.Event()
+        self.thread = self.p = self.f = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.bits |= int(reasons_fn(h))
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.how = "nvml thread, 2 ms period"
         except Exception:
-            self.p = None
+            self.how = "nvidia-smi -lms 20"
+            try:
+                self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                           "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+                time.sleep(1.0)                                   # nvidia-smi needs ~0.5 s before its first sample
+            except Exception:
+                self.p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
-        os.unlink(self.f.name)
-        sm, reasons = [], set()
-        for r in rows:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "how": self.how}
+        reasons = set()
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            reasons = {name for name, bit in self.REASONS if self.bits & bit}
+            if self.power:
+                out["power_w_max"] = max(self.power)
+        elif self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(r[0]))
-                out["sm_max_mhz"] = float(r[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(name)
+                self.p.wait(timeout=5)
             except Exception:
-                pass
+                self.p.kill()
+            self.f.flush()
+            rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+            os.unlink(self.f.name)
+            for r in rows:
+                try:
+                    self.samples.append(float(r[0]))
+                    out["sm_max_mhz"] = float(r[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                        if v.strip().lower().startswith("active"):
+                            reasons.add(name)
+                except Exception:
+                    pass
+        sm = sorted(self.samples)
         if sm:
-            sm.sort()
             out["sm_mhz"] = sm[len(sm) // 2]
+            out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
         return out
 

@@ -8,9 +8,11 @@
 // BatchNorm uses batch statistics, so every BN is a global reduction followed by a second sweep.
 // Moments are accumulated in fp64, block partials are reduced in a fixed order (deterministic).
 #include <new>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tcgen05.cuh"
 
 namespace mpn {
 
@@ -729,6 +731,254 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph
 }
 
 // ------------------------------------------------------------------------------------------------
+// SC on the 5th-generation tensor cores (stored-y mode).  The packed-fp32 kernel above is issue bound: ~10 warp
+// instructions per edge, most of them the 32 x 4 message FMAs and the ReLU+add.  Here, for a batch of 128 edges of one row,
+//   Z[128 edges x 32 channels] = E1 (128 x 8) W1^T  +  E2 (128 x 8) W2^T
+//       E1[e] = [ e'_hi (4) | e'_lo (4) ]        W1[c] = [ W'_hi[c] (4) | W'_hi[c] (4) ]
+//       E2[e] = [ e'_hi (4) | 1 1 0 0   ]        W2[c] = [ W'_lo[c] (4) | A'_hi[c] A'_lo[c] 0 0 ]
+// is two tcgen05.mma (M=128, N=32, K=8, kind::tf32; hi.hi + lo.hi + hi.lo = 3xTF32, the row's folded A' enters through two
+// exact "1" columns) into 32 TMEM columns.  Thread i owns TMEM lane i = its own edge and adds |z| of the 32 channels
+// into 32 registers (one FADD each, the absolute value is an operand modifier):
+//     sum relu(z) = ( sum |z| + sum z ) / 2,      sum z = deg A' + W' . S1      (S1 = sum e' is already known from sweep SB),
+// so node_finalize adds the closed-form half.  A masked edge has an all-zero operand row -> z = 0.
+// The 31-shuffle transpose-reduce runs once per RUN of consecutive tasks of one row (the block walks a contiguous task range);
+// the run's sum goes to its last task, zeros to the others (node_finalize adds a row's tasks in order: same result).
+// Pipeline: y streams through a per-thread cp.async ring D batches ahead; operand tiles are double buffered so the MMA of
+// batch k runs while the CUDA cores prepare batch k+1; one __syncthreads per batch.  Deterministic (fixed edge -> lane
+// map, fixed shuffle tree, fixed task order).
+// ------------------------------------------------------------------------------------------------
+constexpr int ATC_THREADS = 128;
+constexpr int ATC_CTAS_PER_SM = 5;
+constexpr int ATC_SEG = 256;                             // task ranges staged in shared memory per segment
+constexpr int ATC_D = 8;                                 // y runs D batches ahead
+constexpr int ATC_RL = ATC_D + 1;                        // ring slots
+constexpr int ATC_SLOT_BYTES = 128 * 16;
+// canonical K-major no-swizzle operand tile: [rows/8 groups][2 K-cores][8 rows][4 floats]
+__device__ __forceinline__ int tile_off(int row, int kcore) { return (row >> 3) * 64 + kcore * 32 + (row & 7) * 4; }
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  // round-to-nearest (ties away) to 10 mantissa bits without cvt.rna.tf32 (which ptxas expands to 4 instructions with an
+  // inf/nan guard): finite inputs only.  The tensor core reads the top 19 bits of lo: error ~2^-22 |v|.
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+  lo = v - hi;
+}
+// per-thread asynchronous copies global -> shared (LDGSTS): the landing ring is private to the thread that issued them, so
+// cp.async.wait_group is the only synchronisation needed
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <bool CLASSIFY, bool DECIDE>
+__global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
+    const mpn_graph g, const float4* __restrict__ ybuf, const float* __restrict__ A, const float* __restrict__ consts,
+    float* __restrict__ msg_task, float2* __restrict__ logits, uint8_t* __restrict__ pred, float* __restrict__ prob1) {
+  __shared__ EdgeConsts sc;
+  __shared__ __align__(128) float e1[2][128 * 8];
+  __shared__ __align__(128) float e2[2][128 * 8];
+  __shared__ __align__(128) float w1[32 * 8];
+  __shared__ __align__(128) float w2[32 * 8];
+  __shared__ __align__(16) float4 ring[ATC_RL][ATC_THREADS];
+  __shared__ int s_row[ATC_SEG], s_beg[ATC_SEG], s_end[ATC_SEG];
+  __shared__ float red[2][ATC_THREADS / 32][32];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  load_consts(sc, consts);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_slot, 32);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {                                        // static parts of the weight tiles (channel = tid)
+    float wh[4], wl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      split_tf32(sc.v[FC_NODE_WE + 4 * tid + k], wh[k], wl[k]);
+      uint32_t lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(wl[k]));
+      wl[k] = __uint_as_float(lb);
+    }
+    *reinterpret_cast<float4*>(&w1[tile_off(tid, 0)]) = make_float4(wh[0], wh[1], wh[2], wh[3]);
+    *reinterpret_cast<float4*>(&w1[tile_off(tid, 1)]) = make_float4(wh[0], wh[1], wh[2], wh[3]);
+    *reinterpret_cast<float4*>(&w2[tile_off(tid, 0)]) = make_float4(wl[0], wl[1], wl[2], wl[3]);
+    *reinterpret_cast<float4*>(&w2[tile_off(tid, 1)]) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  constexpr uint32_t IDESC = make_idesc_tf32(128, 32);
+  const uint64_t d_w1 = make_smem_desc_noswizzle(smem_u32(w1), 128, 256), d_w2 = make_smem_desc_noswizzle(smem_u32(w2), 128, 256);
+  const uint64_t d_e1 = make_smem_desc_noswizzle(smem_u32(e1[0]), 128, 256), d_e2 = make_smem_desc_noswizzle(smem_u32(e2[0]), 128, 256);
+  constexpr uint64_t BUF_STEP = (128 * 8 * sizeof(float)) >> 4;          // second operand buffer, in descriptor address units
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+  float* const e1_mine = &e1[0][tile_off(tid, 0)];                       // K-core 1 of the same row: + 32 floats
+  float* const e2_mine = &e2[0][tile_off(tid, 0)];
+  unsigned char* const ring_mine = reinterpret_cast<unsigned char*>(&ring[0][tid]);
+  *reinterpret_cast<float4*>(&e2[0][tile_off(tid, 1)]) = make_float4(1.f, 1.f, 0.f, 0.f);     // the two "1" columns never change
+  *reinterpret_cast<float4*>(&e2[1][tile_off(tid, 1)]) = make_float4(1.f, 1.f, 0.f, 0.f);
+  uint32_t phase = 0;
+  const int n_tasks = *g.n_tasks;
+  const int per = (n_tasks + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t_first = blockIdx.x * per, t_last = min(n_tasks, t_first + per);
+  const float bn_s = sc.v[FC_BN4_S + lane], bn_t = sc.v[FC_BN4_T + lane];
+  const float s3[4] = {sc.v[FC_BN3_S], sc.v[FC_BN3_S + 1], sc.v[FC_BN3_S + 2], sc.v[FC_BN3_S + 3]};
+  const float t3[4] = {sc.v[FC_BN3_T], sc.v[FC_BN3_T + 1], sc.v[FC_BN3_T + 2], sc.v[FC_BN3_T + 3]};
+  int flushes = 0;
+
+  for (int s0 = t_first; s0 < t_last; s0 += ATC_SEG) {
+    const int ns = min(ATC_SEG, t_last - s0);
+    __syncthreads();                                     // the previous segment's ranges are no longer read
+    for (int i = tid; i < ns; i += ATC_THREADS) {
+      const TaskRange tr = task_range(g, s0 + i);
+      s_row[i] = tr.row; s_beg[i] = tr.beg; s_end[i] = tr.end;
+    }
+    __syncthreads();
+    // stream iterator (block-uniform): the batch whose y is copied next
+    int st_ti = 0, st_pos = s_beg[0], st_end = s_end[0], st_off = 0;
+    auto issue_stream = [&]() {
+      if (st_ti < ns) {
+        cp_async<16>(ring_mine + st_off, ybuf + min(st_pos + tid, st_end - 1));
+        st_pos += ATC_THREADS;
+        if (st_pos >= st_end) {
+          ++st_ti;
+          if (st_ti < ns) { st_pos = s_beg[st_ti]; st_end = s_end[st_ti]; }
+        }
+        st_off = (st_off == (ATC_RL - 1) * ATC_SLOT_BYTES) ? 0 : st_off + ATC_SLOT_BYTES;
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int j = 0; j < ATC_D; ++j) issue_stream();
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    bool pending = false;                                // an MMA is in flight whose result has not been accumulated
+    int run_first = 0;                                   // first task (segment index) of the current run of one row
+    int c_off = 0, buf = 0;
+    bool ok_prev = false;
+    float a_next = __ldg(A + (size_t)s_row[0] * MPN_DH + lane);
+    auto drain = [&](bool live) {                        // accumulate the finished batch (live: this lane's edge was real)
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(my_tmem, v);
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] += fabsf(v[c]);
+      }
+      tc_fence_before();
+    };
+    auto flush_to_red = [&]() {                          // this run's sum |z| per channel: lane c of every warp
+      const float total = transpose_reduce32(acc, lane);
+      red[flushes & 1][warp][lane] = total;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    };
+    auto store_run = [&](int first, int last_t) {        // after the barrier that follows flush_to_red; warp 0 only
+      const float (*r)[32] = red[flushes & 1];
+      msg_task[(size_t)(s0 + last_t) * MPN_DH + lane] = (r[0][lane] + r[1][lane]) + (r[2][lane] + r[3][lane]);
+      for (int t = first; t < last_t; ++t) msg_task[(size_t)(s0 + t) * MPN_DH + lane] = 0.f;
+    };
+    for (int ti = 0; ti < ns; ++ti) {
+      const int row = s_row[ti], t_beg = s_beg[ti], t_end = s_end[ti];
+      const bool new_run = ti == 0 || row != s_row[ti - 1];
+      const float a_cur = a_next;
+      if (ti + 1 < ns) a_next = __ldg(A + (size_t)s_row[ti + 1] * MPN_DH + lane);
+      for (int pos = t_beg; pos < t_end; pos += ATC_THREADS) {
+        cp_async_wait<ATC_D - 1>();                      // this batch's y has landed
+        const float4 yv = *reinterpret_cast<const float4*>(ring_mine + c_off);
+        c_off = (c_off == (ATC_RL - 1) * ATC_SLOT_BYTES) ? 0 : c_off + ATC_SLOT_BYTES;
+        issue_stream();
+        const int e = pos + tid;
+        const bool ok = e < t_end;                       // a masked lane computes on a clamped edge; its TMEM row is never added
+        float ep[4];
+        ep[0] = fmaxf(fmaf(s3[0], yv.x, t3[0]), 0.f);
+        ep[1] = fmaxf(fmaf(s3[1], yv.y, t3[1]), 0.f);
+        ep[2] = fmaxf(fmaf(s3[2], yv.z, t3[2]), 0.f);
+        ep[3] = fmaxf(fmaf(s3[3], yv.w, t3[3]), 0.f);
+        if (CLASSIFY && ok) {
+          float l0 = sc.v[FC_CLS_B + 0], l1 = sc.v[FC_CLS_B + 1];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            l0 = fmaf(sc.v[FC_CLS_W + k], ep[k], l0);
+            l1 = fmaf(sc.v[FC_CLS_W + 4 + k], ep[k], l1);
+          }
+          logits[e] = make_float2(l0, l1);
+          if (DECIDE) {
+            pred[e] = (l1 > l0) ? 1 : 0;                                          // argmax, tie -> class 0 (inference.py:479)
+            prob1[e] = rcp_approx(1.0f + ex2_approx((l0 - l1) * 1.4426950408889634f));   // softmax(.)[1] (inference.py:475-477)
+          }
+        }
+        float eh[4], el[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_tf32(ep[k], eh[k], el[k]);
+        const float4 hi4 = make_float4(eh[0], eh[1], eh[2], eh[3]);
+        float* const t1 = e1_mine + buf * (128 * 8);
+        *reinterpret_cast<float4*>(t1) = hi4;
+        *reinterpret_cast<float4*>(t1 + 32) = make_float4(el[0], el[1], el[2], el[3]);
+        *reinterpret_cast<float4*>(e2_mine + buf * (128 * 8)) = hi4;
+        if (pending) drain(ok_prev);                     // batch k-1 finished while batch k was being prepared
+        ok_prev = ok;
+        const bool first_batch = pos == t_beg;
+        const bool flushed = first_batch && new_run && ti > 0;
+        if (first_batch && new_run) {
+          if (ti > 0) flush_to_red();
+          if (tid < 32) {                                // the new row's folded A' (the previous MMA has completed)
+            float ah, al, al_hi, al_lo;
+            split_tf32(fmaf(bn_s, a_cur, bn_t), ah, al);
+            split_tf32(al, al_hi, al_lo);
+            *reinterpret_cast<float4*>(&w2[tile_off(tid, 1)]) = make_float4(ah, al_hi, 0.f, 0.f);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          umma_tf32(tmem, d_e1 + buf * BUF_STEP, d_w1, IDESC, 0);
+          umma_tf32(tmem, d_e2 + buf * BUF_STEP, d_w2, IDESC, 1);
+          umma_commit(&bar);
+        }
+        pending = true;
+        buf ^= 1;
+        if (flushed) {
+          if (warp == 0) store_run(run_first, ti - 1);
+          ++flushes;
+          run_first = ti;
+        }
+      }
+    }
+    if (pending) drain(ok_prev);
+    flush_to_red();
+    __syncthreads();
+    if (warp == 0) store_run(run_first, ns - 1);
+    ++flushes;
+    cp_async_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 32);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Batched small graphs (BASELINE configs[2]): one launch over all graphs, BatchNorm statistics per graph.
 // Moment sweeps write one partial per task; a block per graph adds its tasks in task order (deterministic) and folds
 // that graph's constants.  Graphs are contiguous in node, task and edge order.
@@ -1063,15 +1313,35 @@ __global__ void __launch_bounds__(NT_THREADS) node_tables_kernel(const float* __
 
 // h'[row] = sum over the row's tasks of msg_task (fixed order)  — the deterministic segment sum of models/mpn.py:202.
 // PEERS: the rows are also stored into every other rank's h buffer over NVLink (the per-step all-gather of h).
+// ABS (tensor-core apply): msg_task holds sum |z|;  sum relu(z) = (sum |z| + deg A' + W' . S1) / 2 with S1 = the row's sum of e'.
+struct AbsFix {
+  int on;
+  const float* A;
+  const float4* s1_task;
+  const float* consts;
+};
 template <bool PEERS>
 __global__ void __launch_bounds__(256) node_finalize_kernel(const mpn_graph g, const float* __restrict__ msg_task,
-                                                            float* __restrict__ h_full, const PeerArgs P) {
+                                                            float* __restrict__ h_full, const PeerArgs P, const AbsFix fix) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int n = gwarp; n < g.n_nodes; n += nwarps) {
     float s = 0.f;
-    for (int t = g.taskptr[n]; t < g.taskptr[n + 1]; ++t) s += msg_task[(size_t)t * MPN_DH + lane];
+    const int tb = g.taskptr[n], te = g.taskptr[n + 1];
+    for (int t = tb; t < te; ++t) s += msg_task[(size_t)t * MPN_DH + lane];
+    if (fix.on && te > tb) {
+      float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = tb; t < te; ++t) {
+        const float4 v = fix.s1_task[t];
+        s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+      }
+      const float deg = (float)(g.rowptr[n + 1] - g.rowptr[n]);
+      const float ap = fmaf(fix.consts[FC_BN4_S + lane], fix.A[(size_t)n * MPN_DH + lane], fix.consts[FC_BN4_T + lane]);
+      const float* w = fix.consts + FC_NODE_WE + 4 * lane;
+      const float lin = fmaf(deg, ap, fmaf(w[0], s1.x, fmaf(w[1], s1.y, fmaf(w[2], s1.z, w[3] * s1.w))));
+      s = 0.5f * (s + lin);
+    }
     const size_t o = (size_t)(g.row_offset + n) * MPN_DH + lane;
     h_full[o] = s;
     if (PEERS)
@@ -1091,6 +1361,7 @@ struct mpn_fwd_plan {
   mpn_graph g;
   mpn_weights w;
   int L, n_cls, use_tc, max_dim;
+  int msg_abs;                // the last apply sweep wrote sum |z| (tensor-core kernel)
   long long total_edges;
   float *act0, *act1, *colscale, *colshift;
   double* colpart;
@@ -1106,6 +1377,25 @@ struct mpn_fwd_plan {
   void* gemm_ws;
   size_t gemm_ws_bytes;
 };
+
+// Is the edge-update pre-activation y materialised (16 B / edge) and re-read by the later sweeps, or recomputed by each of
+// them from (col, edge_attr, Pd[col])?  Multi-step runs need it anyway; for a single large graph with L == 1 it trades
+// 24 B / edge of extra traffic for ~2 x 65 fewer instructions per edge in sweeps that are issue bound (measured: 0.41 ->
+// 0.35 ms on configs[1] with the packed-fp32 apply kernel) and feeds the tensor-core apply kernel.  MPN_STORE_Y=0 disables.
+static bool stores_y(const mpn_fwd_plan& p) {
+  static int opt = -1;
+  if (opt < 0) { const char* e = getenv("MPN_STORE_Y"); opt = e ? atoi(e) : 1; }
+  return p.L > 1 || (p.L == 1 && opt != 0 && p.n_graphs <= 1);
+}
+
+static mpn::AbsFix abs_fix(const mpn_fwd_plan* p) {
+  mpn::AbsFix f;
+  f.on = p->msg_abs;
+  f.A = p->A;
+  f.s1_task = (const float4*)p->s1_task;
+  f.consts = p->consts;
+  return f;
+}
 
 static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need) {
   Arena a(ws, ws_bytes);
@@ -1134,7 +1424,7 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.fin_counter = a.take<unsigned int>(1);
   p.n_total_dev = a.take<double>(1);
   p.col_counter = a.take<unsigned int>((size_t)(max_dim > 0 ? max_dim : 1) / 32 + 1);
-  p.ybuf = (p.L > 1) ? a.take<float>((size_t)g.n_edges * 4) : nullptr;
+  p.ybuf = stores_y(p) ? a.take<float>((size_t)g.n_edges * 4) : nullptr;
   size_t gw = 0;
   if (p.use_tc) {
     int prev = p.w.node_dims[0];
@@ -1306,7 +1596,7 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
   cudaStream_t st = (cudaStream_t)stream;
   const mpn_graph& g = p->g;
   const float2* ea = (const float2*)edge_attr;
-  const bool stored = p->L > 1;           // y materialised in ybuf for multi-step runs
+  const bool stored = stores_y(*p);       // y materialised in ybuf
   const bool fused = p->fuse_fin != 0;
   const int flat_grid = (int)min((long long)SWEEP_GRID, (long long)div_up(g.n_edges > 0 ? g.n_edges : 1, SWEEP_THREADS));
   const bool batched = p->n_graphs > 1;
@@ -1385,6 +1675,19 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
         classify_encoded_kernel<<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, lg, pred_out, prob1_out);
         break;
       }
+      // tensor-core variant: stored-y runs on graphs with >= 128-edge tasks (MPN_APPLY_TC=0 selects the packed-fp32 kernel)
+      static int apply_tc = -1;
+      if (apply_tc < 0) { const char* e = getenv("MPN_APPLY_TC"); apply_tc = e ? atoi(e) : 1; }
+      p->msg_abs = 0;
+      if (p->use_tc && apply_tc && stored && g.chunk >= ATC_THREADS && (!classify || (pred_out != nullptr) == (prob1_out != nullptr))) {
+        p->msg_abs = 1;                                    // msg_task holds sum |z|: node_finalize adds the closed-form half
+#define MPN_ATC(CL, DE) apply_tc_kernel<CL, DE><<<kNumSMs * ATC_CTAS_PER_SM, ATC_THREADS, 0, st>>>(g, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+        if (!classify) MPN_ATC(false, false);
+        else if (pred_out && prob1_out) MPN_ATC(true, true);
+        else MPN_ATC(true, false);
+#undef MPN_ATC
+        break;
+      }
 #define MPN_APPLY(YS, CL) apply_kernel<YS, CL, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
       if (stored) { if (classify) MPN_APPLY(1, true); else MPN_APPLY(1, false); }
       else        { if (classify) MPN_APPLY(0, true); else MPN_APPLY(0, false); }
@@ -1420,7 +1723,7 @@ int mpn_plan_reduce(mpn_fwd_plan* p, int32_t stage, int with_consts, void* strea
 int mpn_plan_node_finalize(mpn_fwd_plan* p, int32_t step, void* stream) {
   MPN_REQUIRE(p, "node_finalize: NULL plan");
   (void)step;
-  node_finalize_kernel<false><<<min(kNumSMs * 8, div_up((long long)p->g.n_nodes * 32, 256)), 256, 0, (cudaStream_t)stream>>>(p->g, p->msg_task, p->h_full, PeerArgs());
+  node_finalize_kernel<false><<<min(kNumSMs * 8, div_up((long long)p->g.n_nodes * 32, 256)), 256, 0, (cudaStream_t)stream>>>(p->g, p->msg_task, p->h_full, PeerArgs(), abs_fix(p));
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -1570,12 +1873,12 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
       if (cls) ++k;
       const int grid = min(kNumSMs * 8, div_up((long long)g->n_nodes * 32, 256));
       if (!last) {
-        node_finalize_kernel<true><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P);
+        node_finalize_kernel<true><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P, abs_fix(p));
         peer_publish_h_kernel<<<1, 32, 0, st>>>(P, ++seq_h);
         mpn::g_kernel_launches += 2;
         h_pending = true;
       } else {
-        node_finalize_kernel<false><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P);
+        node_finalize_kernel<false><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P, abs_fix(p));
         ++mpn::g_kernel_launches;
       }
       if (cudaGetLastError() != cudaSuccess) { set_error("node_finalize launch failed"); rc = MPN_ERR_CUDA; goto done; }

@@ -163,12 +163,15 @@ def test_edge_features_near_duplicates_and_unsorted(m):
 
 
 # ---------------------------------------------------------------------------------------------- forward
-def run_forward(m, params, sd, x, ei, ea, fuse=False):
+def run_forward(m, params, sd, x, ei, ea, fuse=False, chunk=None):
     net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
     net.load_state_dict(sd, strict=True)
     net = net.to(dev()).eval()
     net.fuse_decisions = fuse
     data = Data(x=x.to(dev()), edge_index=ei.to(dev()), edge_attr=ea.to(dev()))
+    if chunk is not None:                                # force the task size (>= 128 selects the tensor-core apply kernel)
+        data.mpn_graph = m.TrackletGraph(data.edge_index, x.shape[0], chunk=chunk)
+        net.use_cuda_graph = False
     out, h = net(data)
     torch.cuda.synchronize()
     return out["classified_edges"], h, net
@@ -222,6 +225,33 @@ def test_forward_multi_step_unsorted_edges(m):
     for o, r in zip(outs, ref):
         assert (o.cpu().double() - r).abs().max().item() <= 1e-4 * r.abs().max().item()
     assert (h.cpu().double() - href).abs().max().item() <= 1e-4 * max(1.0, href.abs().max().item())
+
+
+@pytest.mark.parametrize("L,n_cls,chunk,fuse", [(1, 1, 128, True), (3, 2, 128, False), (2, 1, 256, True), (1, 1, 1024, False)])
+def test_forward_tensor_core_apply_vs_fp64_oracle(m, L, n_cls, chunk, fuse):
+    """Tasks of >= 128 edges take the stored-y + tcgen05 apply path (sum|z| + closed-form half in node_finalize): rows of 400
+    edges = 3 full batches + a masked tail; a thinned copy adds short rows, empty rows and runs that change row every batch."""
+    params = mo.shipped_model_params(L, n_cls, 64, (48, 40))
+    x, ei, cam, _ = mo.synth_graph(600, 3, 5, D=64, planted=True)
+    sd = mo.init_weights(params, "resnet101", 11, affine_jitter=True)
+    keep = torch.rand(ei.shape[1], generator=torch.Generator().manual_seed(3)) < 0.6
+    keep &= ~((ei[0] >= 100) & (ei[0] < 140))                                  # rows without edges
+    keep &= ~((ei[0] >= 300) & (ei[0] < 330) & (ei[1] % 7 != 0))               # short rows (< 128 edges)
+    for ei_t in (ei, ei[:, keep]):
+        ea = mo.edge_features(x, ei_t)
+        ref, href = mo.mpn_forward(sd, params, "resnet101", x, ei_t, ea, dtype=torch.float64)
+        outs, h, net = run_forward(m, params, sd, x, ei_t, ea, fuse=fuse, chunk=chunk)
+        for o, r in zip(outs, ref):
+            assert (o.cpu().double() - r).abs().max().item() <= 1e-4 * r.abs().max().item()
+        assert (h.cpu().double() - href).abs().max().item() <= 1e-4 * max(1.0, href.abs().max().item())
+        outs2, h2, _ = run_forward(m, params, sd, x, ei_t, ea, fuse=fuse, chunk=chunk)
+        assert torch.equal(outs2[-1], outs[-1]) and torch.equal(h2, h)          # bit-reproducible
+        if fuse:
+            margin = (ref[-1][:, 1] - ref[-1][:, 0]).abs()
+            pred_ref = (ref[-1][:, 1] > ref[-1][:, 0]).to(torch.uint8)
+            assert not bool(((net.last_pred.cpu() != pred_ref) & (margin > 1e-4)).any())
+            prob_ref = torch.softmax(ref[-1], dim=1)[:, 1]
+            assert (net.last_prob1.cpu().double() - prob_ref).abs().max().item() <= 5e-6
 
 
 class _NoComm:
