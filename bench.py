@@ -66,14 +66,17 @@ class ClockSampler:
                 pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
 
             def poll():
+                i = 0
                 while not self.stop_flag.is_set():
                     try:
                         self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                        self.bits |= int(reasons_fn(h))
-                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                        if i % 4 == 0:
+                            self.bits |= int(reasons_fn(h))
+                            self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
                     except Exception:
                         pass
-                    time.sleep(0.002)
+                    i += 1
+                    time.sleep(0.001)
             self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
             self.how = "nvml thread, 2 ms period"
@@ -465,7 +468,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -142,19 +142,39 @@ __device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, i
     const int n_partials = f.n_partials, n_partials2 = f.n_partials2;
     const double* partials = f.partials;
     const double* partials2 = f.partials2;
-    for (int col = warp; col < SUMS; col += (int)(blockDim.x >> 5)) {
-      const double* src = partials;
-      int n = n_partials;
-      bool live = col < 8;
-      if (stage == MPN_STAGE_NODE) {
-        live = col < 74;
-        if (col < 64) { src = partials2; n = n_partials2; }
+    // The reduction is the serial tail of the sweep's last block.  ENC/EDGE stages have 8 live columns: one per warp.  The NODE
+    // stage has 74: a warp sums 4 columns per pass (4 independent load streams) instead of one.
+    if (stage != MPN_STAGE_NODE) {
+      for (int col = warp; col < SUMS; col += (int)(blockDim.x >> 5)) {
+        double s = 0.0;
+        if (col < 8)
+          for (int p = lane; p < n_partials; p += 32) s += __ldcg(partials + (size_t)p * SUMS + col);
+        s = warp_sum(s);
+        if (lane == 0) sums[col] = s;
       }
-      double s = 0.0;
-      if (live)
-        for (int p = lane; p < n; p += 32) s += __ldcg(src + (size_t)p * SUMS + col);
-      s = warp_sum(s);
-      if (lane == 0) sums[col] = s;
+    } else {
+      constexpr int CG = 4;
+      constexpr int n_live = 74;
+      for (int col0 = warp * CG; col0 < SUMS; col0 += (int)(blockDim.x >> 5) * CG) {
+        double acc[CG];
+#pragma unroll
+        for (int j = 0; j < CG; ++j) acc[j] = 0.0;
+        if (col0 < n_live) {
+          const bool second = col0 < 64;                 // CG divides 64: a group never straddles the split
+          const double* src = second ? partials2 : partials;
+          const int n = second ? n_partials2 : n_partials;
+          for (int p = lane; p < n; p += 32) {
+#pragma unroll
+            for (int j = 0; j < CG; ++j)
+              if (col0 + j < n_live) acc[j] += __ldcg(src + (size_t)p * SUMS + col0 + j);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < CG; ++j) {
+          const double v = warp_sum(acc[j]);
+          if (lane == 0 && col0 + j < SUMS) sums[col0 + j] = v;
+        }
+      }
     }
   }
   __syncthreads();
@@ -471,10 +491,13 @@ template <int YSRC, bool BATCHED>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                                            const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                                            const float4* __restrict__ ybuf, const float* __restrict__ consts,
-                                                                           float4* __restrict__ s1_task, double* __restrict__ partials) {
+                                                                           float4* __restrict__ s1_task, double* __restrict__ partials,
+                                                                           const float* __restrict__ A, const float* __restrict__ small,
+                                                                           const FinArgs fin) {
   constexpr int U = 4;
   __shared__ EdgeConsts scs[BATCHED ? SWEEP_THREADS / 32 : 1];
   __shared__ double red[(SWEEP_THREADS / 32) * 10];
+  __shared__ double red_m[BATCHED ? 1 : SWEEP_THREADS / 32][64];
   const int lane = threadIdx.x & 31;
   EdgeConsts& sc = scs[BATCHED ? (threadIdx.x >> 5) : 0];
   if (!BATCHED) load_consts(sc, consts);
@@ -482,6 +505,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
   const int nwarps = (gridDim.x * SWEEP_THREADS) >> 5;
   const int n_tasks = *g.n_tasks;
   double t2[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // per-node part of the closed-form node-BN moments, taken per task (it is linear in the task's edge count and S1):
+  //   m1[c] += n_t A[row,c] + w_c.S1_t ;  m2[c] += n_t A[row,c]^2 + 2 A[row,c] (w_c.S1_t)      (w_c = W_node[c, 32:36]; lane = c)
+  double m1 = 0.0, m2 = 0.0;
+  float wn[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!BATCHED) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wn[k] = small[MPN_W_NODE_W + lane * 36 + 32 + k];
+  }
   int cur_gid = -1;
   for (int t = gwarp; t < n_tasks; t += nwarps) {
     const TaskRange tr = task_range(g, t);
@@ -489,6 +520,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
       const int gid = g.node_gid[tr.row];
       if (gid != cur_gid) { warp_load_consts(sc, consts + (size_t)gid * FC_TOTAL, lane); cur_gid = gid; }
     }
+    const float a_row = BATCHED ? 0.f : A[(size_t)tr.row * MPN_DH + lane];
     const float4 ps = (YSRC == 0) ? Ps[tr.row] : make_float4(0.f, 0.f, 0.f, 0.f);
     float s1[4] = {0.f, 0.f, 0.f, 0.f};
     float q[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -512,6 +544,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
 #pragma unroll
     for (int a = 0; a < 4; ++a) s1[a] = warp_sum(s1[a]);
     if (lane == 0) s1_task[t] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    if (!BATCHED) {                                        // one task's term in fp32 (<= chunk edges), the running sums in fp64
+      const float nt = (float)(tr.end - tr.beg);
+      const float qd = fmaf(wn[0], s1[0], fmaf(wn[1], s1[1], fmaf(wn[2], s1[2], wn[3] * s1[3])));
+      m1 += (double)fmaf(nt, a_row, qd);
+      m2 += (double)(a_row * fmaf(nt, a_row, 2.0f * qd));
+    }
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
       if (BATCHED) {
@@ -522,47 +560,18 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
       }
     }
   }
-  if (!BATCHED) block_sum_doubles<10, SWEEP_THREADS>(t2, red, partials + (size_t)blockIdx.x * SUMS + 64);
-}
-
-// per-node part of the closed-form node-BN moments:
-//   m1[c] = sum_n deg_n A[n,c] + w_c·S1_n ;  m2[c] = sum_n deg_n A[n,c]^2 + 2 A[n,c] (w_c·S1_n)     (w_c = W_node[c, 32:36])
-constexpr int NM_THREADS = 256;
-constexpr int NM_GRID = kNumSMs * 2;
-__global__ void __launch_bounds__(NM_THREADS) node_moments_node_kernel(const mpn_graph g, const float* __restrict__ A,
-                                                                       const float4* __restrict__ s1_task,
-                                                                       const float* __restrict__ small,
-                                                                       double* __restrict__ partials, const FinArgs fin) {
-  __shared__ double red[NM_THREADS / 32][64];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gwarp = (blockIdx.x * NM_THREADS + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * NM_THREADS) >> 5;
-  float w[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) w[k] = small[MPN_W_NODE_W + lane * 36 + 32 + k];
-  double m1 = 0.0, m2 = 0.0;
-  for (int n = gwarp; n < g.n_nodes; n += nwarps) {
-    const int deg = g.rowptr[n + 1] - g.rowptr[n];
-    if (deg == 0) continue;
-    double s[4] = {0, 0, 0, 0};
-    for (int t = g.taskptr[n]; t < g.taskptr[n + 1]; ++t) {
-      const float4 v = s1_task[t];
-      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+  if (!BATCHED) {
+    const int warp = threadIdx.x >> 5;
+    red_m[warp][lane] = m1;
+    red_m[warp][32 + lane] = m2;
+    block_sum_doubles<10, SWEEP_THREADS>(t2, red, partials + (size_t)blockIdx.x * SUMS + 64);   // (has the barriers)
+    if (threadIdx.x < 64) {
+      double sm = 0.0;
+      for (int wv = 0; wv < SWEEP_THREADS / 32; ++wv) sm += red_m[wv][threadIdx.x];
+      partials[(size_t)blockIdx.x * SUMS + threadIdx.x] = sm;
     }
-    const double a = A[(size_t)n * MPN_DH + lane];
-    const double qd = w[0] * s[0] + w[1] * s[1] + w[2] * s[2] + w[3] * s[3];
-    m1 += deg * a + qd;
-    m2 += deg * a * a + 2.0 * a * qd;
+    finalize_in_last_block(fin);
   }
-  red[warp][lane] = m1;
-  red[warp][32 + lane] = m2;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    double s = 0.0;
-    for (int wv = 0; wv < NM_THREADS / 32; ++wv) s += red[wv][threadIdx.x];
-    partials[(size_t)blockIdx.x * SUMS + threadIdx.x] = s;
-  }
-  finalize_in_last_block(fin);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1419,7 +1428,7 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.s1_task = a.take<float>((size_t)g.max_tasks * 4);
   p.msg_task = a.take<float>((size_t)g.max_tasks * MPN_DH);
   p.partials = a.take<double>((size_t)SWEEP_GRID * SUMS);
-  p.partials2 = a.take<double>((size_t)NM_GRID * SUMS);
+  p.partials2 = nullptr;                 // (the per-node moment part now lives in the sweep's own partial rows)
   p.sums = a.take<double>(G * SUMS);
   p.fin_counter = a.take<unsigned int>(1);
   p.n_total_dev = a.take<double>(1);
@@ -1494,8 +1503,8 @@ static FinArgs make_fin(const mpn_fwd_plan* p, int stage, bool fused) {
   f.stage = stage;
   f.partials = p->partials;
   f.n_partials = SWEEP_GRID;
-  f.partials2 = p->partials2;
-  f.n_partials2 = NM_GRID;
+  f.partials2 = p->partials;             // the node-BN sweep writes its per-node part into the same partial rows
+  f.n_partials2 = SWEEP_GRID;
   f.sums = p->sums;
   f.consts = p->consts;
   f.small = p->w.small;
@@ -1621,8 +1630,8 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
         }
         break;
       case MPN_STAGE_NODE:
-        if (stored) node_moments_sweep_kernel<1, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, tp);
-        else node_moments_sweep_kernel<0, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, tp);
+        if (stored) node_moments_sweep_kernel<1, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, tp, p->A, p->w.small, make_fin(p, stage, false));
+        else node_moments_sweep_kernel<0, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, tp, p->A, p->w.small, make_fin(p, stage, false));
         break;
       case MPN_STAGE_APPLY: {
         const bool classify = logits_out != nullptr;
@@ -1662,10 +1671,8 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
       }
       break;
     case MPN_STAGE_NODE:
-      if (stored) node_moments_sweep_kernel<1, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, p->partials);
-      else node_moments_sweep_kernel<0, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, p->partials);
-      MPN_LAUNCH_OK();
-      node_moments_node_kernel<<<NM_GRID, NM_THREADS, 0, st>>>(g, p->A, (const float4*)p->s1_task, p->w.small, p->partials2, make_fin(p, stage, fused));
+      if (stored) node_moments_sweep_kernel<1, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, p->partials, p->A, p->w.small, make_fin(p, stage, fused));
+      else node_moments_sweep_kernel<0, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, p->partials, p->A, p->w.small, make_fin(p, stage, fused));
       break;
     case MPN_STAGE_APPLY: {
       const bool classify = logits_out != nullptr;
