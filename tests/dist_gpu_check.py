@@ -18,7 +18,7 @@ import gcn_mtmc_b200 as m                      # noqa: E402
 from oracle import mpn_oracle as mo            # noqa: E402
 
 
-def check_case(rank, world, dev, L, n_cls, N, C, modes):
+def check_case(rank, world, dev, L, n_cls, N, C, modes, chunk=None):
     params = mo.shipped_model_params(L, n_cls, 128, (96, 64))
     x, ei, cam, _ = mo.synth_graph(N, C, 3, D=128, planted=True)
     sd = mo.init_weights(params, "resnet101", 2)
@@ -33,7 +33,7 @@ def check_case(rank, world, dev, L, n_cls, N, C, modes):
     lo, hi = m.shard_edges(ei, n0, n1)
     xd = x.to(dev)
     ei_l = ei[:, lo:hi].to(dev)
-    g = m.TrackletGraph(ei_l, N, row_offset=n0, n_rows=n1 - n0)
+    g = m.TrackletGraph(ei_l, N, row_offset=n0, n_rows=n1 - n0, chunk=chunk)      # chunk >= 128: tensor-core apply kernel
     ea_l = m.edge_features(xd, None, graph=g, use_tensor_cores=False)
     assert torch.allclose(ea_l.cpu(), ea[lo:hi], rtol=3e-6, atol=3e-6)
     worst = 0.0
@@ -68,8 +68,8 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
     worst, modes = 0.0, set()
-    for (L, n_cls, N, C) in [(1, 1, 240, 4), (4, 2, 200, 5)]:
-        worst = max(worst, check_case(rank, world, dev, L, n_cls, N, C, modes))
+    for (L, n_cls, N, C, chunk) in [(1, 1, 240, 4, None), (4, 2, 200, 5, None), (2, 1, 600, 3, 128), (1, 1, 600, 3, 256)]:
+        worst = max(worst, check_case(rank, world, dev, L, n_cls, N, C, modes, chunk))
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
