@@ -36,7 +36,11 @@ class MpnWeights(C.Structure):
                 ("node_w", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_b", C.c_void_p * MPN_MAX_NODE_LAYERS),
                 ("node_gamma", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_beta", C.c_void_p * MPN_MAX_NODE_LAYERS),
                 ("small", C.c_void_p),
-                ("node_w_hi", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_w_lo", C.c_void_p * MPN_MAX_NODE_LAYERS)]
+                ("node_w_hi", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_w_lo", C.c_void_p * MPN_MAX_NODE_LAYERS),
+                ("node_agg", C.c_int32), ("reserved", C.c_int32)]
+
+
+AGG_SUM, AGG_MEAN, AGG_MAX = 0, 1, 2
 
 
 MPN_MAX_PEERS = 16

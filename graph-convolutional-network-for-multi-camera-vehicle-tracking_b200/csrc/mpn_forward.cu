@@ -582,6 +582,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
 // transpose-reduce per task leaves channel c's sum in lane c (deterministic: fixed shuffle tree, fixed task order in
 // node_finalize).
 // ------------------------------------------------------------------------------------------------
+template <bool MAXOP = false>
 __device__ __forceinline__ float transpose_reduce32(float (&acc)[32], int lane) {
   // after the step with offset o the live values per lane halve; the lane keeps the half selected by bit o of its id
 #pragma unroll
@@ -592,7 +593,8 @@ __device__ __forceinline__ float transpose_reduce32(float (&acc)[32], int lane) 
       if (i < n) {
         const float send = upper ? acc[i] : acc[i + n];
         const float keep = upper ? acc[i + n] : acc[i];
-        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        const float other = __shfl_xor_sync(0xffffffffu, send, o);
+        acc[i] = MAXOP ? fmaxf(keep, other) : keep + other;
       }
     }
   }
@@ -640,7 +642,7 @@ __device__ __forceinline__ void classify_store(const EdgeConsts& sc, const float
   if (prob1) prob1[e] = softmax1(l0, l1);
 }
 
-template <int YSRC, bool CLASSIFY, bool BATCHED>
+template <int YSRC, bool CLASSIFY, bool BATCHED, bool AGGMAX>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                               const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                               const float4* __restrict__ ybuf, const float* __restrict__ A,
@@ -717,7 +719,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph
           z = fma2(wb.x, ed[j][2], z);
           z = fma2(wb.y, ed[j][3], z);
           z = relu2(z);
-          if (cur.ok[j]) acc[p] = add2(acc[p], z);
+          if (cur.ok[j]) {
+            if (AGGMAX) {                                  // scatter_max (models/mpn.py:199): messages are >= 0, so 0 is neutral
+              float zl, zh, al, ah;
+              unpack2(z, zl, zh);
+              unpack2(acc[p], al, ah);
+              acc[p] = pack2(fmaxf(al, zl), fmaxf(ah, zh));
+            } else {
+              acc[p] = add2(acc[p], z);
+            }
+          }
         }
       }
 #pragma unroll
@@ -734,7 +745,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph
     float accf[32];
 #pragma unroll
     for (int p = 0; p < 16; ++p) unpack2(acc[p], accf[2 * p], accf[2 * p + 1]);
-    const float total = transpose_reduce32(accf, lane);
+    const float total = transpose_reduce32<AGGMAX>(accf, lane);
     msg_task[(size_t)t * MPN_DH + lane] = total;
   }
 }
@@ -790,7 +801,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-template <bool CLASSIFY, bool DECIDE>
+template <bool CLASSIFY, bool DECIDE, bool AGGMAX>
 __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
     const mpn_graph g, const float4* __restrict__ ybuf, const float* __restrict__ A, const float* __restrict__ consts,
     float* __restrict__ msg_task, float2* __restrict__ logits, uint8_t* __restrict__ pred, float* __restrict__ prob1) {
@@ -888,19 +899,20 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
       tmem_ld32(my_tmem, v);
       if (live) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] += fabsf(v[c]);
+        for (int c = 0; c < 32; ++c) acc[c] = AGGMAX ? fmaxf(acc[c], v[c]) : acc[c] + fabsf(v[c]);   // max relu(z) = max(0, max z)
       }
       tc_fence_before();
     };
     auto flush_to_red = [&]() {                          // this run's sum |z| per channel: lane c of every warp
-      const float total = transpose_reduce32(acc, lane);
+      const float total = transpose_reduce32<AGGMAX>(acc, lane);
       red[flushes & 1][warp][lane] = total;
 #pragma unroll
       for (int c = 0; c < 32; ++c) acc[c] = 0.f;
     };
     auto store_run = [&](int first, int last_t) {        // after the barrier that follows flush_to_red; warp 0 only
       const float (*r)[32] = red[flushes & 1];
-      msg_task[(size_t)(s0 + last_t) * MPN_DH + lane] = (r[0][lane] + r[1][lane]) + (r[2][lane] + r[3][lane]);
+      msg_task[(size_t)(s0 + last_t) * MPN_DH + lane] = AGGMAX ? fmaxf(fmaxf(r[0][lane], r[1][lane]), fmaxf(r[2][lane], r[3][lane]))
+                                                               : (r[0][lane] + r[1][lane]) + (r[2][lane] + r[3][lane]);
       for (int t = first; t < last_t; ++t) msg_task[(size_t)(s0 + t) * MPN_DH + lane] = 0.f;
     };
     for (int ti = 0; ti < ns; ++ti) {
@@ -1325,6 +1337,7 @@ __global__ void __launch_bounds__(NT_THREADS) node_tables_kernel(const float* __
 // ABS (tensor-core apply): msg_task holds sum |z|;  sum relu(z) = (sum |z| + deg A' + W' . S1) / 2 with S1 = the row's sum of e'.
 struct AbsFix {
   int on;
+  int agg;                    // MPN_AGG_SUM | MPN_AGG_MEAN | MPN_AGG_MAX
   const float* A;
   const float4* s1_task;
   const float* consts;
@@ -1338,7 +1351,11 @@ __global__ void __launch_bounds__(256) node_finalize_kernel(const mpn_graph g, c
   for (int n = gwarp; n < g.n_nodes; n += nwarps) {
     float s = 0.f;
     const int tb = g.taskptr[n], te = g.taskptr[n + 1];
-    for (int t = tb; t < te; ++t) s += msg_task[(size_t)t * MPN_DH + lane];
+    if (fix.agg == MPN_AGG_MAX) {
+      for (int t = tb; t < te; ++t) s = fmaxf(s, msg_task[(size_t)t * MPN_DH + lane]);     // rows without edges -> 0 (torch_scatter)
+    } else {
+      for (int t = tb; t < te; ++t) s += msg_task[(size_t)t * MPN_DH + lane];
+    }
     if (fix.on && te > tb) {
       float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int t = tb; t < te; ++t) {
@@ -1351,6 +1368,7 @@ __global__ void __launch_bounds__(256) node_finalize_kernel(const mpn_graph g, c
       const float lin = fmaf(deg, ap, fmaf(w[0], s1.x, fmaf(w[1], s1.y, fmaf(w[2], s1.z, w[3] * s1.w))));
       s = 0.5f * (s + lin);
     }
+    if (fix.agg == MPN_AGG_MEAN) s /= fmaxf((float)(g.rowptr[n + 1] - g.rowptr[n]), 1.f);   // scatter_mean: count clamped to >= 1
     const size_t o = (size_t)(g.row_offset + n) * MPN_DH + lane;
     h_full[o] = s;
     if (PEERS)
@@ -1400,6 +1418,7 @@ static bool stores_y(const mpn_fwd_plan& p) {
 static mpn::AbsFix abs_fix(const mpn_fwd_plan* p) {
   mpn::AbsFix f;
   f.on = p->msg_abs;
+  f.agg = p->w.node_agg;
   f.A = p->A;
   f.s1_task = (const float4*)p->s1_task;
   f.consts = p->consts;
@@ -1460,6 +1479,7 @@ static int check_weights(const mpn_weights* w) {
   for (int i = 0; i < w->n_node_layers; ++i)
     MPN_REQUIRE(w->node_w[i] && w->node_b[i] && w->node_gamma[i] && w->node_beta[i] && w->node_dims[i] > 0, "node layer %d has NULL tensors", i);
   MPN_REQUIRE(w->small != nullptr, "small weight block is NULL");
+  MPN_REQUIRE(w->node_agg >= MPN_AGG_SUM && w->node_agg <= MPN_AGG_MAX, "node_agg must be MPN_AGG_SUM, _MEAN or _MAX (got %d)", w->node_agg);
   return MPN_OK;
 }
 
@@ -1637,10 +1657,12 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
         const bool classify = logits_out != nullptr;
         float2* lg = (float2*)logits_out;
         MPN_REQUIRE(p->L > 0, "batched graphs need num_enc_steps >= 1");
-#define MPN_APPLY_B(YS, CL) apply_kernel<YS, CL, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_APPLY_B2(YS, CL, MX) apply_kernel<YS, CL, true, MX><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_APPLY_B(YS, CL) do { if (p->w.node_agg == MPN_AGG_MAX) MPN_APPLY_B2(YS, CL, true); else MPN_APPLY_B2(YS, CL, false); } while (0)
         if (stored) { if (classify) MPN_APPLY_B(1, true); else MPN_APPLY_B(1, false); }
         else        { if (classify) MPN_APPLY_B(0, true); else MPN_APPLY_B(0, false); }
 #undef MPN_APPLY_B
+#undef MPN_APPLY_B2
         break;
       }
       default:
@@ -1687,18 +1709,23 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
       if (apply_tc < 0) { const char* e = getenv("MPN_APPLY_TC"); apply_tc = e ? atoi(e) : 1; }
       p->msg_abs = 0;
       if (p->use_tc && apply_tc && stored && g.chunk >= ATC_THREADS && (!classify || (pred_out != nullptr) == (prob1_out != nullptr))) {
-        p->msg_abs = 1;                                    // msg_task holds sum |z|: node_finalize adds the closed-form half
-#define MPN_ATC(CL, DE) apply_tc_kernel<CL, DE><<<kNumSMs * ATC_CTAS_PER_SM, ATC_THREADS, 0, st>>>(g, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+        const bool agg_max = p->w.node_agg == MPN_AGG_MAX;
+        p->msg_abs = agg_max ? 0 : 1;                      // msg_task holds sum |z|: node_finalize adds the closed-form half
+#define MPN_ATC2(CL, DE, MX) apply_tc_kernel<CL, DE, MX><<<kNumSMs * ATC_CTAS_PER_SM, ATC_THREADS, 0, st>>>(g, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_ATC(CL, DE) do { if (agg_max) MPN_ATC2(CL, DE, true); else MPN_ATC2(CL, DE, false); } while (0)
         if (!classify) MPN_ATC(false, false);
         else if (pred_out && prob1_out) MPN_ATC(true, true);
         else MPN_ATC(true, false);
 #undef MPN_ATC
+#undef MPN_ATC2
         break;
       }
-#define MPN_APPLY(YS, CL) apply_kernel<YS, CL, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_APPLY2(YS, CL, MX) apply_kernel<YS, CL, false, MX><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_APPLY(YS, CL) do { if (p->w.node_agg == MPN_AGG_MAX) MPN_APPLY2(YS, CL, true); else MPN_APPLY2(YS, CL, false); } while (0)
       if (stored) { if (classify) MPN_APPLY(1, true); else MPN_APPLY(1, false); }
       else        { if (classify) MPN_APPLY(0, true); else MPN_APPLY(0, false); }
 #undef MPN_APPLY
+#undef MPN_APPLY2
       break;
     }
     default:

@@ -186,8 +186,7 @@ class MOTMPNet(nn.Module):
         self.num_class_steps = model_params['num_class_steps']
 
         # ---- what the kernels support; checked once here so forward() fails early and loudly ----
-        if agg != 'sum':
-            raise _unsupported("node_agg_fn=%r" % agg)
+        self._node_agg = {'sum': _lib.AGG_SUM, 'mean': _lib.AGG_MEAN, 'max': _lib.AGG_MAX}[agg.lower()]    # models/mpn.py:196-202
         if self.reattach_initial_nodes or self.reattach_initial_edges:
             raise _unsupported("reattach_initial_nodes/edges=True")
         if not (enc['edge_in_dim'] == 2 and list(enc['edge_fc_dims']) == [4] and enc['edge_out_dim'] == 4):
@@ -221,6 +220,7 @@ class MOTMPNet(nn.Module):
             if p.device != device or p.dtype != torch.float32:
                 raise RuntimeError("all MOTMPNet parameters must be fp32 on %s (got %s %s)" % (device, p.dtype, p.device))
         W = _lib.MpnWeights()
+        W.node_agg = self._node_agg
         keep = []
         nmlp = self.encoder.node_mlp
         W.n_node_layers = len(nmlp.blocks)

@@ -145,7 +145,11 @@ typedef struct mpn_weights {
   /* optional cache: TF32 hi/lo planes of node_w[i] made by mpn_split_tf32 (NULL -> split on every forward) */
   const float* node_w_hi[MPN_MAX_NODE_LAYERS];
   const float* node_w_lo[MPN_MAX_NODE_LAYERS];
+  /* node aggregation of the messages (models/mpn.py:193-202): scatter_add / scatter_mean / scatter_max over row */
+  int32_t node_agg;                               /* MPN_AGG_SUM (shipped config) | MPN_AGG_MEAN | MPN_AGG_MAX */
+  int32_t reserved;
 } mpn_weights;
+enum { MPN_AGG_SUM = 0, MPN_AGG_MEAN = 1, MPN_AGG_MAX = 2 };
 
 /* x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi): the operand planes of the 3xTF32 tensor-core GEMM.
  * n must be a multiple of 4, pointers 16-byte aligned. */

@@ -160,6 +160,22 @@ def scatter_add_rows(src: torch.Tensor, index: torch.Tensor, dim_size: int) -> t
     return torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype).index_add_(0, index, src)
 
 
+def aggregate_rows(src: torch.Tensor, index: torch.Tensor, dim_size: int, how: str) -> torch.Tensor:
+    """node_agg_fn of models/mpn.py:193-202 = torch_scatter 2.0.8 (env_gnn.yml:98, not vendored) scatter_add / scatter_mean /
+    scatter_max along dim 0 with dim_size: mean divides the sum by the per-row count clamped to >= 1; max of a row without
+    elements is 0 (the library fills untouched entries of a fresh output with 0)."""
+    if how == "sum":
+        return scatter_add_rows(src, index, dim_size)
+    if how == "mean":
+        cnt = torch.zeros(dim_size, dtype=src.dtype).index_add_(0, index, torch.ones(index.numel(), dtype=src.dtype))
+        return scatter_add_rows(src, index, dim_size) / cnt.clamp_min(1).unsqueeze(1)
+    if how == "max":
+        out = torch.full((dim_size,) + tuple(src.shape[1:]), float("-inf"), dtype=src.dtype)
+        out = out.scatter_reduce(0, index.unsqueeze(1).expand_as(src), src, reduce="amax", include_self=True)
+        return torch.where(torch.isinf(out), torch.zeros_like(out), out)
+    raise ValueError(how)
+
+
 def mpn_forward(sd, model_params: dict, arch: str, x: torch.Tensor, edge_index: torch.Tensor,
                 edge_attr: torch.Tensor, dtype=torch.float32):
     """MOTMPNet.forward (models/mpn.py:250-299).  Returns (list of [E,2] logits, h [N,node_out])."""
@@ -188,7 +204,7 @@ def mpn_forward(sd, model_params: dict, arch: str, x: torch.Tensor, edge_index: 
         # node update (mpn.py:97-99): messages use the node itself (x[row]) and the edge feature
         m = mlp_forward(sd, "MPNet.node_model.node_mlp.fc_layers", lay["MPNet.node_model.node_mlp.fc_layers"],
                         torch.cat([h[row], e], dim=1))
-        h = scatter_add_rows(m, row, h.shape[0])
+        h = aggregate_rows(m, row, h.shape[0], model_params.get("node_agg_fn", "sum"))
         if step >= first_class_step:
             outs.append(mlp_forward(sd, "classifier.edge_mlp.fc_layers", lay["classifier.edge_mlp.fc_layers"], e))
     if L == 0:
@@ -231,6 +247,15 @@ def cross_camera_edge_index(cam: torch.Tensor) -> torch.Tensor:
     for c in torch.unique(cam).tolist():
         parts.append(torch.cartesian_prod(nodes[cam == c], nodes[cam != c]))
     return torch.cat(parts, dim=0).t().contiguous()
+
+
+def thin_edges(edge_index: torch.Tensor, seed: int, keep: float = 0.7, empty_rows=(3, 7)) -> torch.Tensor:
+    """Drop a random 30% of the edges and every edge leaving ``empty_rows`` (rows that then aggregate nothing)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    m = torch.rand(edge_index.shape[1], generator=g) < keep
+    for r in empty_rows:
+        m &= edge_index[0] != r
+    return edge_index[:, m].contiguous()
 
 
 def balanced_cameras(N: int, C: int) -> torch.Tensor:

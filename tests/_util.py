@@ -28,11 +28,19 @@ def ids(files):
 
 def load_mpn_case(path):
     g = np.load(path)
-    N, C, gseed, wseed, L, n_cls, din, planted, jitter = [int(v) for v in g["spec"]]
+    spec = [int(v) for v in g["spec"]]
+    N, C, gseed, wseed, L, n_cls, din, planted, jitter = spec[:9]
+    agg, thin = (("sum", "mean", "max")[spec[9]], bool(spec[10])) if len(spec) > 9 else ("sum", False)
     fcd = tuple(int(v) for v in g["fc_dims"])
     params = mo.shipped_model_params(L, n_cls, din, fcd)
+    params["node_agg_fn"] = agg
     x, edge_index, cam, _ = mo.synth_graph(N, C, gseed, D=din, planted=bool(planted))
+    if thin:
+        edge_index = mo.thin_edges(edge_index, gseed)
+    assert np.array_equal(edge_index.numpy(), g["edge_index"].astype(np.int64)), "generator drift: edge_index"
+    assert np.allclose([x.double().sum().item(), x.double().abs().sum().item()], g["x_checksum"], rtol=1e-12)
     sd = mo.init_weights(params, "resnet101", wseed, affine_jitter=bool(jitter))
+    assert np.allclose(sum(v.double().sum().item() for v in sd.values()), g["w_checksum"][0], rtol=1e-12)
     return g, params, sd, x, edge_index, C
 
 

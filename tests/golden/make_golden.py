@@ -31,7 +31,13 @@ MPN_CASES = {
     "mpn_small_L4_cls2": (40, 4, 13, 3, 4, 2, 64, (48, 40), True, True),
     "mpn_small_L0": (24, 3, 14, 4, 0, 1, 64, (48,), False, True),
     "mpn_small_L3_cls3_c5": (55, 5, 15, 5, 3, 3, 96, (64, 48, 40), True, True),
+    # node_agg_fn variants (models/mpn.py:193-202), on a thinned graph with rows that lost all their edges:
+    # (..., agg, thin)
+    "mpn_small_L2_mean": (44, 4, 16, 6, 2, 2, 64, (48, 40), True, True, "mean", True),
+    "mpn_small_L3_max": (44, 4, 17, 7, 3, 1, 64, (48, 40), True, True, "max", True),
+    "mpn_shipped_L1_max": (40, 4, 18, 8, 1, 1, 2048, (1024, 512, 128), False, True, "max", False),
 }
+AGG_CODE = {"sum": 0, "mean": 1, "max": 2}
 
 POST_CASES = {
     # name: (N, C, seed, flip_on, flip_off, single_dir)
@@ -45,9 +51,13 @@ POST_CASES = {
 
 
 def run_mpn_case(MOTMPNet, name, spec):
-    N, C, gseed, wseed, L, n_cls, din, fcd, planted, jitter = spec
+    N, C, gseed, wseed, L, n_cls, din, fcd, planted, jitter = spec[:10]
+    agg, thin = (spec[10], spec[11]) if len(spec) > 10 else ("sum", False)
     params = mo.shipped_model_params(L, n_cls, din, fcd)
+    params["node_agg_fn"] = agg
     x, edge_index, cam, ident = mo.synth_graph(N, C, gseed, D=din, planted=planted)
+    if thin:
+        edge_index = mo.thin_edges(edge_index, gseed)
     sd = mo.init_weights(params, "resnet101", wseed, affine_jitter=jitter)
     torch.manual_seed(0)
     model = MOTMPNet(copy.deepcopy(params), None, "resnet101").eval()
@@ -71,7 +81,7 @@ def run_mpn_case(MOTMPNet, name, spec):
         out64, h64 = m64(Data(x=x.double(), edge_index=edge_index, edge_attr=edge_attr.double()))
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),
-        spec=np.array([N, C, gseed, wseed, L, n_cls, din, int(planted), int(jitter)], dtype=np.int64),
+        spec=np.array([N, C, gseed, wseed, L, n_cls, din, int(planted), int(jitter), AGG_CODE[agg], int(thin)], dtype=np.int64),
         fc_dims=np.array(fcd, dtype=np.int64),
         x_checksum=np.array([x.double().sum().item(), x.double().abs().sum().item()]),
         w_checksum=np.array([sum(v.double().sum().item() for v in sd.values())]),

@@ -30,8 +30,23 @@ def install():
             shape[dim] = dim_size if dim_size is not None else int(index.max()) + 1
             return torch.zeros(shape, dtype=src.dtype, device=src.device).index_add_(dim, index, src)
 
-        ts.scatter_add = scatter_add
-        ts.scatter_mean = ts.scatter_max = None       # only 'sum' is exercised by the shipped config
+        # torch_scatter 2.0.8 (env_gnn.yml:98; not installable here) documented semantics, dim=0 + dim_size as mpn.py:196-202 calls:
+        def scatter_mean(src, index, dim=0, dim_size=None, out=None):
+            total = scatter_add(src, index, dim, dim_size)
+            cnt = torch.zeros(total.shape[dim], dtype=src.dtype, device=src.device).index_add_(
+                0, index, torch.ones(index.numel(), dtype=src.dtype, device=src.device))
+            return total / cnt.clamp_(min=1).view([-1] + [1] * (src.dim() - 1))        # count clamped to >= 1
+
+        def scatter_max(src, index, dim=0, dim_size=None, out=None):
+            shape = list(src.shape)
+            shape[dim] = dim_size if dim_size is not None else int(index.max()) + 1
+            res = torch.full(shape, torch.finfo(src.dtype).min, dtype=src.dtype, device=src.device)
+            idx = index.view([-1] + [1] * (src.dim() - 1)).expand_as(src)
+            res = res.scatter_reduce(dim, idx, src, reduce="amax", include_self=True)
+            res = res.masked_fill(res == torch.finfo(src.dtype).min, 0)                 # untouched entries -> 0
+            return res, None                                                            # (values, argmax): mpn.py:199 takes [0]
+
+        ts.scatter_add, ts.scatter_mean, ts.scatter_max = scatter_add, scatter_mean, scatter_max
         sys.modules["torch_scatter"] = ts
     for name in ("matplotlib", "matplotlib.pyplot"):
         if name not in sys.modules:

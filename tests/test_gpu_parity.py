@@ -227,11 +227,14 @@ def test_forward_multi_step_unsorted_edges(m):
     assert (h.cpu().double() - href).abs().max().item() <= 1e-4 * max(1.0, href.abs().max().item())
 
 
-@pytest.mark.parametrize("L,n_cls,chunk,fuse", [(1, 1, 128, True), (3, 2, 128, False), (2, 1, 256, True), (1, 1, 1024, False)])
-def test_forward_tensor_core_apply_vs_fp64_oracle(m, L, n_cls, chunk, fuse):
+@pytest.mark.parametrize("L,n_cls,chunk,fuse,agg", [(1, 1, 128, True, "sum"), (3, 2, 128, False, "sum"), (2, 1, 256, True, "sum"),
+                                                    (1, 1, 1024, False, "sum"), (2, 1, 128, True, "max"), (3, 1, 256, False, "mean"),
+                                                    (2, 2, 32, False, "max"), (2, 1, 64, True, "mean")])
+def test_forward_tensor_core_apply_vs_fp64_oracle(m, L, n_cls, chunk, fuse, agg):
     """Tasks of >= 128 edges take the stored-y + tcgen05 apply path (sum|z| + closed-form half in node_finalize): rows of 400
     edges = 3 full batches + a masked tail; a thinned copy adds short rows, empty rows and runs that change row every batch."""
     params = mo.shipped_model_params(L, n_cls, 64, (48, 40))
+    params["node_agg_fn"] = agg                                                # models/mpn.py:193-202 (chunk < 128: packed-fp32 kernel)
     x, ei, cam, _ = mo.synth_graph(600, 3, 5, D=64, planted=True)
     sd = mo.init_weights(params, "resnet101", 11, affine_jitter=True)
     keep = torch.rand(ei.shape[1], generator=torch.Generator().manual_seed(3)) < 0.6
@@ -320,10 +323,11 @@ def test_batched_edge_features_block_diagonal(m, D, tc):
     assert np.allclose(out, ref, rtol=1e-5, atol=2e-6)
 
 
-@pytest.mark.parametrize("L,n_cls", [(1, 1), (3, 2)])
-def test_batched_graphs_per_graph_batchnorm(m, L, n_cls):
+@pytest.mark.parametrize("L,n_cls,agg", [(1, 1, "sum"), (3, 2, "sum"), (2, 1, "max"), (2, 1, "mean")])
+def test_batched_graphs_per_graph_batchnorm(m, L, n_cls, agg):
     """BASELINE configs[2]: many small graphs in one launch; statistics per graph == one reference forward per graph."""
     params = mo.shipped_model_params(L, n_cls, 64, (48, 40))
+    params["node_agg_fn"] = agg
     sd = mo.init_weights(params, "resnet101", 17)
     sizes, cams = [40, 64, 30, 90, 52, 36], [4, 4, 3, 5, 4, 2]
     x, ei, ptr, xs, eis = _packed_batch(sizes, cams, 64, 300)

@@ -54,9 +54,13 @@ def test_state_dict_layout_matches_reference_names():
 
 def test_unsupported_configs_raise():
     p = mo.shipped_model_params()
-    p["node_agg_fn"] = "max"
-    with pytest.raises(NotImplementedError):
+    p["node_agg_fn"] = "median"                       # the reference's own check (models/mpn.py:193)
+    with pytest.raises(AssertionError):
         m.MOTMPNet(p, None, "resnet101")
+    for agg in ("mean", "max", "sum"):                # all three aggregators of models/mpn.py:196-202 are supported
+        p = mo.shipped_model_params()
+        p["node_agg_fn"] = agg
+        assert m.MOTMPNet(p, None, "resnet101")._node_agg == {"sum": 0, "mean": 1, "max": 2}[agg]
     p = mo.shipped_model_params()
     p["reattach_initial_edges"] = True
     with pytest.raises(NotImplementedError):

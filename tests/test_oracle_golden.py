@@ -14,17 +14,7 @@ MPN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "mpn_*.npz")))
 POST_FILES = sorted(glob.glob(os.path.join(GOLDEN, "post_*.npz")))
 
 
-def load_mpn_case(path):
-    g = np.load(path)
-    N, C, gseed, wseed, L, n_cls, din, planted, jitter = [int(v) for v in g["spec"]]
-    fcd = tuple(int(v) for v in g["fc_dims"])
-    params = mo.shipped_model_params(L, n_cls, din, fcd)
-    x, edge_index, cam, _ = mo.synth_graph(N, C, gseed, D=din, planted=bool(planted))
-    sd = mo.init_weights(params, "resnet101", wseed, affine_jitter=bool(jitter))
-    assert np.allclose([x.double().sum().item(), x.double().abs().sum().item()], g["x_checksum"], rtol=1e-12)
-    assert np.allclose(sum(v.double().sum().item() for v in sd.values()), g["w_checksum"][0], rtol=1e-12)
-    assert np.array_equal(edge_index.numpy(), g["edge_index"].astype(np.int64))
-    return g, params, sd, x, edge_index, C
+from tests._util import load_mpn_case  # noqa: E402  (checks the regenerated inputs against the stored checksums)
 
 
 def test_golden_present():
