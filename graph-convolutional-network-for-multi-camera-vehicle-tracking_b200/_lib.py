@@ -111,6 +111,15 @@ _PROTOS = {
     "mpn_active_edges": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_labels_reference_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
+    "mpn_edge_confusion": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mpn_contingency_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "mpn_contingency": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mpn_expected_mutual_information_host": (C.c_double, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]),
+    "mpn_relabel_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "mpn_relabel_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mpn_write_mtmc_txt_host": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
     "mpn_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "mpn_gemm_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int,
                               C.c_void_p, C.c_size_t, C.c_void_p]),

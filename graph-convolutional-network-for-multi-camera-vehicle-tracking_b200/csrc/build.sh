@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 OBJ="${HERE}/_obj"
 mkdir -p "${OBJ}"
 pids=()
-for f in graph gemm_simt gemm_tc gemm_api edge_features mpn_forward postproc; do
+for f in graph gemm_simt gemm_tc gemm_api edge_features mpn_forward postproc eval; do
   if [ ! -f "${OBJ}/${f}.o" ] || [ "${HERE}/${f}.cu" -nt "${OBJ}/${f}.o" ] || [ "${HERE}/common.cuh" -nt "${OBJ}/${f}.o" ] || \
      [ "${HERE}/kernels.h" -nt "${OBJ}/${f}.o" ] || [ "${HERE}/tcgen05.cuh" -nt "${OBJ}/${f}.o" ] || [ "${HERE}/../../include/mpn_b200.h" -nt "${OBJ}/${f}.o" ]; then
     "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${OBJ}/${f}.o" &

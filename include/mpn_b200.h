@@ -288,6 +288,34 @@ size_t mpn_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int impl);
 int mpn_gemm_nt(const float* A_dev, const float* B_dev, const float* bias_dev, float* C_dev,
                 int32_t M, int32_t N, int32_t K, int impl, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * After the hot path: evaluation counts and the tracking output.
+ *   mpn_edge_confusion   compute_P_R_F (inference.py:20-66): counts_dev int64 [3][3] = label class x prediction class,
+ *                        class = 0 / 1 / 2 for a value == 0 / == 1 / anything else (the reference only ever tests == 0 and == 1).
+ *                        *_kind: 0 = uint8, 1 = int64, 2 = float32 element type.
+ *   mpn_contingency      contingency table of two COMPACT labelings (labels in [0,Ka) x [0,Kb)), the input of every clustering
+ *                        score the reference takes from sklearn.metrics on (ID_GT, ID_pred) (inference.py:507-519): COO entries in
+ *                        arbitrary order (sort on the host), the number of non-zeros and both marginals.  Synchronises.
+ *   mpn_expected_mutual_information_host   the EMI term of adjusted_mutual_info_score (scikit-learn 0.24.2
+ *                        _expected_mutual_info_fast.pyx, env_gnn.yml:107) from the two marginals.  HOST pointers, CPU.
+ *   mpn_relabel_detections   inference.py:540-548: out_id[r] = node_new[n] for the last tracklet n whose (id_cam, old id) equals the
+ *                        detection's, else the detection keeps its id.  id_cam in [0,2^20), ids in [0,2^44).  Synchronises.
+ *   mpn_write_mtmc_txt_host  np.savetxt(..., fmt='%d') of main.py:114 for an int64 table.  HOST pointers, CPU.
+ * ---------------------------------------------------------------------------------------------- */
+int mpn_edge_confusion(const void* pred_dev, int pred_kind, const void* labels_dev, int label_kind, int64_t n_edges,
+                       int64_t* counts_dev /* [9] */, void* stream);
+size_t mpn_contingency_workspace_bytes(int64_t n);
+int mpn_contingency(const int64_t* a_dev, const int64_t* b_dev, int64_t n, int64_t Ka, int64_t Kb, int64_t* rows_out_dev,
+                    int64_t* cols_out_dev, int64_t* counts_out_dev, int64_t* nnz_host, int64_t* row_sums_dev /* [Ka] */,
+                    int64_t* col_sums_dev /* [Kb] */, void* workspace_dev, size_t workspace_bytes, void* stream);
+double mpn_expected_mutual_information_host(const int64_t* row_sums_host, int64_t R, const int64_t* col_sums_host, int64_t C,
+                                            int64_t n_samples);
+size_t mpn_relabel_workspace_bytes(int64_t n_tracklets);
+int mpn_relabel_detections(const int64_t* det_cam_dev, const int64_t* det_id_dev, int64_t n_detections, const int64_t* node_cam_dev,
+                           const int64_t* node_old_id_dev, const int64_t* node_new_id_dev, int64_t n_tracklets,
+                           int64_t* out_id_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+int mpn_write_mtmc_txt_host(const char* path, const int64_t* table_host, int64_t rows, int32_t cols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,6 +130,22 @@ def run_post_case(ref_utils, ref_inference, name, spec):
                                                        out["labels_full"].max() + 1))
 
 
+def run_eval_case(ref_inference):
+    """compute_P_R_F of the reference (inference.py:20-66) on CPU tensors; every count is non-zero so that none of its
+    `.cuda()` zero constants is reached."""
+    g = torch.Generator().manual_seed(77)
+    cases = {}
+    for tag, E, p1 in (("a", 5000, 0.3), ("b", 257, 0.6), ("c", 64, 0.5)):
+        labels = (torch.rand(E, generator=g) < p1).float()                 # labels_edges_GT is a float tensor (dataset.py)
+        preds = torch.where(torch.rand(E, generator=g) < 0.85, labels, 1 - labels).long()
+        TP, FP, TN, FN, P, R, F, pc0, pc1 = ref_inference.compute_P_R_F(preds, labels)
+        cases.update({f"{tag}_preds": preds.numpy(), f"{tag}_labels": labels.numpy(),
+                      f"{tag}_counts": np.array([int(TP), int(FP), int(TN), int(FN)], dtype=np.int64),
+                      f"{tag}_prf": np.array([float(P), float(R), float(F), float(pc0[0]), float(pc1[0])], dtype=np.float32)})
+    np.savez_compressed(os.path.join(HERE, "eval_prf.npz"), **cases)
+    print("eval_prf", {k: v.tolist() for k, v in cases.items() if k.endswith("counts")})
+
+
 def main():
     if not ref_shims.reference_available():
         raise SystemExit("reference not found at %s" % ref_shims.REFERENCE_ROOT)
@@ -141,6 +157,8 @@ def main():
     for name, spec in POST_CASES.items():
         if not only or name in only:
             run_post_case(ref_utils, ref_inference, name, spec)
+    if not only or "eval_prf" in only:
+        run_eval_case(ref_inference)
 
 
 if __name__ == "__main__":
