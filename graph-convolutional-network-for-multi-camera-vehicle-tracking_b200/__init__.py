@@ -10,11 +10,15 @@ Public surface (same names as the reference where one exists):
     evaluation.{adjusted_rand_score, adjusted_mutual_info_score, homogeneity_score, completeness_score, v_measure_score}
                                  the sklearn.metrics calls of inference.py:509-519
     tracking_table, save_mtmc    inference.py:540-551, main.py:114
+    normalize_columns, edge_labels    inference.py:403-404, 446-450
+    pack_reid_features, load_packed_features    one packed file + one H->D copy for libs/dataset.py:298-307 / inference.py:399
 """
 from . import _lib
 from . import evaluation
 from .evaluation import compute_P_R_F, clustering_scores
 from .tracking_output import relabel_detections, save_mtmc, tracking_table
+from .graph_inputs import (edge_labels, load_packed_features, normalize_columns, pack_reid_features,
+                           pack_reid_features_from_pickles, read_packed_features)
 from .edge_features import edge_features
 from .graph import TrackletGraph, graph_for
 from .mpn import MOTMPNet
@@ -25,4 +29,5 @@ from .postprocess import (compute_SCC_and_Clusters, post_processing, pruning, re
 __all__ = ["MOTMPNet", "edge_features", "post_processing", "pruning", "splitting", "remove_edges_single_direction",
            "compute_SCC_and_Clusters", "TrackletGraph", "graph_for", "ShardedMPN", "CudaPhases", "sharded_forward", "partition_rows",
            "shard_edges", "_lib", "evaluation", "compute_P_R_F", "clustering_scores", "relabel_detections", "tracking_table",
-           "save_mtmc"]
+           "save_mtmc", "edge_labels", "normalize_columns", "pack_reid_features", "pack_reid_features_from_pickles",
+           "read_packed_features", "load_packed_features"]

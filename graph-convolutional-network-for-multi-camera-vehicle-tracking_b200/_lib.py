@@ -120,6 +120,9 @@ _PROTOS = {
     "mpn_relabel_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_write_mtmc_txt_host": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
+    "mpn_edge_labels": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpn_normalize_columns_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "mpn_normalize_columns": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "mpn_gemm_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int,
                               C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -316,3 +316,93 @@ int mpn_write_mtmc_txt_host(const char* path, const int64_t* table_host, int64_t
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// Either side of the hot path: the graph-construction leftovers of inference.py:383-451.
+//   mpn_edge_labels         edge_labels_g[e] = 1 if node_labels[row] == node_labels[col] else 0   (inference.py:446-450:
+//                           an O(E*N) Python comprehension in the reference), float32, graph edge order
+//   mpn_normalize_columns   F.normalize(node_embeds, p=2, dim=0) (inference.py:403-404): every FEATURE COLUMN is scaled to unit
+//                           L2 norm over the nodes, eps 1e-12.  Sum of squares in fp64, then one scaling pass.
+// ================================================================================================
+namespace mpn {
+
+__global__ void __launch_bounds__(256) edge_labels_kernel(const mpn_graph g, const long long* __restrict__ node_labels,
+                                                          float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_tasks = *g.n_tasks;
+  for (int t = gwarp; t < n_tasks; t += nwarps) {
+    const int row = g.task_row[t];
+    const int beg = g.rowptr[row] + (t - g.taskptr[row]) * g.chunk;
+    const int end = min(beg + g.chunk, g.rowptr[row + 1]);
+    const long long lr = node_labels[row + g.row_offset];
+    for (int e = beg + lane; e < end; e += 32) out[e] = (node_labels[g.col[e]] == lr) ? 1.f : 0.f;
+  }
+}
+
+constexpr int NC_SPLITS = 64;
+__global__ void __launch_bounds__(256) colsq_partial_kernel(const float* __restrict__ x, int n, int D, int rows_per_split,
+                                                            double* __restrict__ part /*[NC_SPLITS][D]*/) {
+  __shared__ double ssum[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(r0 + rows_per_split, n);
+  double s = 0.0;
+  if (col < D)
+    for (int r = r0 + ry; r < r1; r += 8) { const double v = x[(size_t)r * D + col]; s += v * v; }
+  ssum[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && col < D) {
+    for (int i = 1; i < 8; ++i) s += ssum[i][cx];
+    part[(size_t)blockIdx.y * D + col] = s;
+  }
+}
+__global__ void colnorm_finalize_kernel(const double* __restrict__ part, int D, float* __restrict__ norm_out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= D) return;
+  double s = 0.0;
+  for (int i = 0; i < NC_SPLITS; ++i) s += part[(size_t)i * D + col];
+  const float nrm = fmaxf((float)sqrt(s), 1e-12f);                 // F.normalize: v / max(||v||_2, eps)
+  norm_out[col] = nrm;
+}
+__global__ void colnorm_apply_kernel(const float* __restrict__ x, long long total, int D, const float* __restrict__ norm,
+                                     float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) out[i] = x[i] / norm[i % D];
+}
+
+}  // namespace mpn
+
+extern "C" {
+
+int mpn_edge_labels(const mpn_graph* g, const int64_t* node_labels_dev, float* out_dev, void* stream) {
+  MPN_REQUIRE(g && (g->n_edges == 0 || (node_labels_dev && out_dev)), "edge_labels: NULL argument");
+  if (g->n_edges == 0) return MPN_OK;
+  edge_labels_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(*g, (const long long*)node_labels_dev, out_dev);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+size_t mpn_normalize_columns_workspace_bytes(int32_t D) { return (size_t)NC_SPLITS * D * sizeof(double) + (size_t)D * sizeof(float) + 512; }
+
+int mpn_normalize_columns(const float* x_dev, int32_t n, int32_t D, float* out_dev, void* ws, size_t ws_bytes, void* stream) {
+  MPN_REQUIRE(n >= 0 && D > 0 && ws, "normalize_columns: bad argument");
+  MPN_REQUIRE(ws_bytes >= mpn_normalize_columns_workspace_bytes(D), "normalize_columns workspace too small");
+  MPN_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  if (n == 0) return MPN_OK;
+  MPN_REQUIRE(x_dev && out_dev, "normalize_columns: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* part = (double*)ws;
+  float* norm = (float*)(part + (size_t)NC_SPLITS * D);
+  colsq_partial_kernel<<<dim3(div_up(D, 32), NC_SPLITS), 256, 0, st>>>(x_dev, n, D, div_up(n, NC_SPLITS), part);
+  MPN_LAUNCH_OK();
+  colnorm_finalize_kernel<<<div_up(D, 128), 128, 0, st>>>(part, D, norm);
+  MPN_LAUNCH_OK();
+  const long long total = (long long)n * D;
+  colnorm_apply_kernel<<<grid_for(total), 256, 0, st>>>(x_dev, total, D, norm, out_dev);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+}  // extern "C"

@@ -316,6 +316,18 @@ int mpn_relabel_detections(const int64_t* det_cam_dev, const int64_t* det_id_dev
                            int64_t* out_id_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 int mpn_write_mtmc_txt_host(const char* path, const int64_t* table_host, int64_t rows, int32_t cols);
 
+/* ------------------------------------------------------------------------------------------------
+ * Before the hot path: what inference.py:383-451 still does per graph.
+ *   mpn_edge_labels         edge_labels_g (inference.py:446-450): out[e] = 1.0f if node_labels[row[e]] == node_labels[col[e]]
+ *                           else 0.0f, in the graph's edge order; node_labels_dev int64 [n_cols].
+ *   mpn_normalize_columns   F.normalize(node_embeds, p=2, dim=0) (inference.py:403-404): out[i,j] = x[i,j] / max(||x[:,j]||_2, 1e-12);
+ *                           out may alias x.
+ * ---------------------------------------------------------------------------------------------- */
+int mpn_edge_labels(const mpn_graph* g, const int64_t* node_labels_dev, float* out_dev, void* stream);
+size_t mpn_normalize_columns_workspace_bytes(int32_t D);
+int mpn_normalize_columns(const float* x_dev, int32_t n, int32_t D, float* out_dev, void* workspace_dev, size_t workspace_bytes,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,3 +158,61 @@ def test_tracking_table_matches_reference_loop(tmp_path):
         m.relabel_detections([0], [5], [0], [-1], [3], device=dev())
     assert m.relabel_detections([], [], [], [], [], device=dev()).numel() == 0
     assert m.relabel_detections([1, 2], [5, 6], [], [], [], device=dev()).tolist() == [5, 6]
+
+
+# ------------------------------------------------------------------------------------------------------------ graph inputs (8f rows 1, 4)
+def test_packed_reid_features_roundtrip_from_reference_pickles(tmp_path):
+    """The reference's layout: ./reid_features/<scenario>/c<cam:03d>/<id:04d>/<file>_<model>.pkl, one pickled CPU tensor each."""
+    import pickle
+    gen = torch.Generator().manual_seed(3)
+    cams = [1, 1, 1, 2, 2, 4]
+    ids = [7, 12, 300, 7, 9, 12]
+    feats = [torch.randn(96, generator=gen) for _ in cams]
+    root = tmp_path / "reid_features"
+    for c, t, f in zip(cams, ids, feats):
+        p = m.graph_inputs.reid_feature_path(str(root), "S02", c, t, "bbox", "resnet101")
+        os.makedirs(os.path.dirname(p))
+        with open(p, "wb") as fo:
+            pickle.dump(f, fo)                                             # libs/reid_feature_extraction.py:181-184
+    packed = tmp_path / "S02.mpnfeat"
+    m.pack_reid_features_from_pickles(str(packed), str(root), "S02", "bbox", "resnet101", cams, ids)
+    x, cam, tid = m.read_packed_features(str(packed))
+    assert cam.tolist() == cams and tid.tolist() == ids
+    assert np.array_equal(np.asarray(x), torch.stack(feats).numpy())       # bit-exact
+    m.pack_reid_features(str(packed), np.zeros((0, 5), dtype=np.float32), [], [])
+    x0, c0, t0 = m.read_packed_features(str(packed))
+    assert x0.shape == (0, 5) and c0.size == 0
+    with pytest.raises(ValueError):
+        m.pack_reid_features(str(packed), np.zeros((3, 5)), [1, 2], [1, 2, 3])
+    with pytest.raises(RuntimeError):
+        m.load_packed_features(str(packed), "cpu")
+
+
+@pytest.mark.gpu
+def test_load_packed_normalize_and_edge_labels(tmp_path):
+    from oracle import mpn_oracle as mo
+    x, ei, cam, ident = mo.synth_graph(90, 5, 3, D=64, planted=True)
+    raw = x * (1.0 + torch.arange(64)) + 0.3                               # un-normalised features
+    packed = tmp_path / "seq.mpnfeat"
+    m.pack_reid_features(str(packed), raw, cam.numpy(), np.arange(90))
+    xd, cam2, tid2 = m.load_packed_features(str(packed), dev())
+    assert torch.equal(xd.cpu(), raw) and cam2.tolist() == cam.tolist()
+    ref = torch.nn.functional.normalize(raw, p=2, dim=0)                   # inference.py:403-404
+    got = m.normalize_columns(xd)
+    assert (got.cpu() - ref).abs().max().item() <= 2e-7
+    xn, _, _ = m.load_packed_features(str(packed), dev(), l2norm=True)
+    assert torch.equal(xn, got)
+    z = torch.zeros(5, 3, device=dev())
+    assert torch.equal(m.normalize_columns(z), z)                          # eps: 0 / max(0, 1e-12) = 0
+    # ground-truth edge labels, literally as inference.py:446-450 builds them
+    labels = ident.numpy() if torch.is_tensor(ident) else np.asarray(ident)
+    nodes = np.arange(90)
+    e_np = ei.numpy()
+    ref_l = np.asarray([1 if (labels[nodes == e_np[0][i]] == labels[nodes == e_np[1][i]]) else 0 for i in range(e_np.shape[1])],
+                       dtype=np.float32)
+    got_l = m.edge_labels(labels, ei.to(dev()))
+    assert got_l.dtype == torch.float32 and np.array_equal(got_l.cpu().numpy(), ref_l)
+    g = m.TrackletGraph.from_cameras(cam, dev())
+    assert np.array_equal(m.edge_labels(labels, graph=g).cpu().numpy(), ref_l)
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(1))
+    assert np.array_equal(m.edge_labels(labels, ei[:, perm].to(dev())).cpu().numpy(), ref_l[perm.numpy()])      # caller's edge order
