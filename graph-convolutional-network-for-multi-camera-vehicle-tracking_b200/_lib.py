@@ -124,6 +124,8 @@ _PROTOS = {
     "mpn_normalize_columns_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "mpn_normalize_columns": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int]),
+    "mpn_gram_nt": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
+                              C.c_void_p]),
     "mpn_gemm_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int,
                               C.c_void_p, C.c_size_t, C.c_void_p]),
 }

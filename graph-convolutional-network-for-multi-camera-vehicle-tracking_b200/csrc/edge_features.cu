@@ -45,7 +45,8 @@ __global__ void col_mean_finalize_kernel(const double* __restrict__ part, int n,
 // xc = x - mu; per-row statistics of the centred row (accumulated in fp64, stored as one float4 = one 16-byte gather
 // per edge; the Gram entry they are combined with is itself only fp32-accurate): st[r] = {|a'|^2, sum a', mu.a' + |mu|^2/2, |a|}
 __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu, int n, int D,
-                                                          float* __restrict__ xc, float4* __restrict__ st) {
+                                                          float* __restrict__ xc, float4* __restrict__ st,
+                                                          unsigned int* __restrict__ amax_bits) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -53,16 +54,21 @@ __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restric
     const float* p = x + (size_t)r * D;
     float* q = xc + (size_t)r * D;
     double sq = 0.0, sx = 0.0, md = 0.0, mm = 0.0;
+    float amax = 0.f;
     for (int k = lane; k < D; k += 32) {
       const float m = mu[k];
       const float c = p[k] - m;
       q[k] = c;
+      amax = fmaxf(amax, fabsf(c));
       sq += (double)c * c;
       sx += (double)c;
       md += (double)m * c;
       mm += (double)m * m;
     }
     sq = warp_sum(sq); sx = warp_sum(sx); md = warp_sum(md); mm = warp_sum(mm);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0 && amax_bits) atomicMax(amax_bits, __float_as_uint(amax));      // non-negative floats order like their bits
     if (lane == 0) {
       // a.b = g' + (mu.a' + |mu|^2/2) + (mu.b' + |mu|^2/2);  |a| = sqrt(|a'|^2 + 2 mu.a' + |mu|^2)
       st[r] = make_float4((float)sq, (float)sx, (float)(md + 0.5 * mm), (float)sqrt(fmax(sq + 2.0 * md + mm, 0.0)));
@@ -208,6 +214,7 @@ struct EfLayout {
   double* mu_part;
   float* G;
   int *refine_list, *refine_count;
+  unsigned int* amax_bits;         // max |x'| over the centred features (float bits): scale of the fp16 operand planes
   long long* g_off;
   void* gemm_ws;
   size_t gemm_ws_bytes;
@@ -233,6 +240,7 @@ static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) 
   L.g_off = a.take<long long>((size_t)(batched ? g->n_graphs : 0) + 1);
   L.refine_list = a.take<int>((size_t)(g->n_edges > 0 ? g->n_edges : 1));
   L.refine_count = a.take<int>(1);
+  L.amax_bits = a.take<unsigned int>(1);
   L.gemm_ws_bytes = batched ? gemm_tc_workspace_bytes(1, g->n_cols, D) : gemm_tc_workspace_bytes((int)rows, g->n_cols, D);
   L.gemm_ws = L.gemm_ws_bytes ? (void*)a.take<char>(L.gemm_ws_bytes) : nullptr;
   L.total = a.off;
@@ -266,9 +274,9 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
   MPN_LAUNCH_OK();
   col_mean_finalize_kernel<<<div_up(D, 128), 128, 0, st>>>(L.mu_part, g->n_cols, D, L.mu);
   MPN_LAUNCH_OK();
-  center_rows_kernel<<<min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st>>>(x, L.mu, g->n_cols, D, L.xc, L.st);
+  MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, 2 * 256, st));        // refine_count and amax_bits (adjacent 256-byte slices)
+  center_rows_kernel<<<min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st>>>(x, L.mu, g->n_cols, D, L.xc, L.st, L.amax_bits);
   MPN_LAUNCH_OK();
-  MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, sizeof(int), st));
   if (g->n_graphs > 1 && g->node_gid && g->graph_nptr) {
     // batched small graphs: block-diagonal Gram (one ng x ng block per graph), same epilogue
     MPN_REQUIRE(g->row_offset == 0 && g->n_cols == g->n_nodes && g->max_graph_nodes > 0, "batched edge features: bad graph");
@@ -292,7 +300,7 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
     const int r1 = min(r0 + L.rows_per_block, g->n_nodes);
     const float* Ablk = L.xc + (size_t)(g->row_offset + r0) * D;
     if (use_tc && gemm_tc_supported(r1 - r0, g->n_cols, D))
-      MPN_TRY(gemm_nt_tc(Ablk, L.xc, nullptr, L.G, r1 - r0, g->n_cols, D, L.gemm_ws, L.gemm_ws_bytes, st));
+      MPN_TRY(gram_nt_tc(L.xc, g->row_offset + r0, L.G, r1 - r0, g->n_cols, D, (const float*)L.amax_bits, L.gemm_ws, L.gemm_ws_bytes, st));
     else
       MPN_TRY(gemm_nt_simt(Ablk, L.xc, nullptr, nullptr, nullptr, L.G, r1 - r0, g->n_cols, D, st));
     edge_feature_gather_kernel<<<kNumSMs * 8, 256, 0, st>>>(*g, r0, r1, L.G, nullptr, L.st, D, (float2*)edge_attr,

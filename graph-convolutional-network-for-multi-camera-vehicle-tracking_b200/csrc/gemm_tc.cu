@@ -17,6 +17,7 @@
 //   warps 2..5  epilogue: tcgen05.ld 32x32b of the fp32 accumulator (one TMEM lane = one output row per thread),
 //               bias add, vectorised global stores with edge masking
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,6 +30,11 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                    // 32 fp32 = 128 bytes = one SWIZZLE_128B row
 constexpr int TC_UMMA_K = 8;                 // kind::tf32: 32 bytes of K per instruction
 constexpr int TC_THREADS = 192;
+// F16 variant ("3xFP16"): the operand planes are fp16 (x*s = hi + lo, s a power of two that puts max|x| at 2^14; 11 + 11
+// significant bits = the 22 bits of the TF32 pair), a 128-byte row holds 64 elements and one instruction covers K = 16:
+// the same three products at twice the tensor-pipe rate and half the operand bytes.  Byte geometry of the stages, of the
+// descriptors and of the k-advance is identical to the TF32 variant.  The epilogue multiplies by *out_scale (= s_a^-1 s_b^-1).
+constexpr int TC_BK_F16 = 64;
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte atoms, 1024 bytes apart)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -52,15 +58,18 @@ struct TcCfg {
   static constexpr int TMEM_COLS = 512;                        // main(s) + correction accumulator, power of two
   static constexpr int CORR_COL = N_MAIN * BN;
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  static constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // a/b format 0 = F16
 };
 
 // SYM: C = A A^T (A == B, M == N): only tiles on or above the diagonal are computed, the epilogue also writes the mirror.
-template <int BN, bool SYM>
+template <int BN, bool SYM, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                       const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
-                      const int* __restrict__ graph_nptr, const long long* __restrict__ g_off) {
+                      const int* __restrict__ graph_nptr, const long long* __restrict__ g_off,
+                      const float* __restrict__ out_scale) {
+  constexpr int BK = F16 ? TC_BK_F16 : TC_BK;            // elements of K per stage (128 bytes either way)
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -72,7 +81,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;     // output-local tile origin
   int tm0 = m0, tn0 = n0;                                // TMA row coordinates of the A / B tiles
-  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int num_kb = (K + BK - 1) / BK;
   if (SYM && n0 + BN <= m0) return;                      // strictly below the diagonal: produced by the mirror store
   if (graph_nptr != nullptr) {
     // block-diagonal Gram (batched graphs): blockIdx.z = graph; its rows [base, base+ng) form an ng x ng block of C
@@ -112,7 +121,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-        const int k0 = kb * TC_BK;
+        const int k0 = kb * BK;
         tma_load_2d(&map_a_hi, &full_bar[stage], st, k0, tm0);
         tma_load_2d(&map_a_lo, &full_bar[stage], st + Cfg::A_BYTES, k0, tm0);
         tma_load_2d(&map_b_hi, &full_bar[stage], st + 2 * Cfg::A_BYTES, k0, tn0);
@@ -133,12 +142,18 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         const uint64_t b_hi = make_smem_desc(sbase + 2 * Cfg::A_BYTES), b_lo = make_smem_desc(sbase + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
         for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
-          const uint64_t adv = (uint64_t)((kk * TC_UMMA_K * 4) >> 4);        // advance the start address inside the 128-byte row
+          const uint64_t adv = (uint64_t)((kk * TC_UMMA_K * 4) >> 4);        // 32 bytes of K per instruction (8 tf32 / 16 fp16)
           const int slice = kb * (TC_BK / TC_UMMA_K) + kk;
           const int which = (Cfg::N_MAIN == 2) ? (slice & 1) : 0;
-          umma_tf32(tmem_base + which * BN, a_hi + adv, b_hi + adv, Cfg::IDESC, slice >= Cfg::N_MAIN);
-          umma_tf32(tmem_base + Cfg::CORR_COL, a_lo + adv, b_hi + adv, Cfg::IDESC, slice != 0);
-          umma_tf32(tmem_base + Cfg::CORR_COL, a_hi + adv, b_lo + adv, Cfg::IDESC, 1);
+          if (F16) {
+            umma_f16(tmem_base + which * BN, a_hi + adv, b_hi + adv, Cfg::IDESC_F16, slice >= Cfg::N_MAIN);
+            umma_f16(tmem_base + Cfg::CORR_COL, a_lo + adv, b_hi + adv, Cfg::IDESC_F16, slice != 0);
+            umma_f16(tmem_base + Cfg::CORR_COL, a_hi + adv, b_lo + adv, Cfg::IDESC_F16, 1);
+          } else {
+            umma_tf32(tmem_base + which * BN, a_hi + adv, b_hi + adv, Cfg::IDESC, slice >= Cfg::N_MAIN);
+            umma_tf32(tmem_base + Cfg::CORR_COL, a_lo + adv, b_hi + adv, Cfg::IDESC, slice != 0);
+            umma_tf32(tmem_base + Cfg::CORR_COL, a_hi + adv, b_lo + adv, Cfg::IDESC, 1);
+          }
         }
         umma_commit(&empty_bar[stage]);                                         // slot free once these MMAs retire
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -152,6 +167,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
     const bool vec_ok = ((N & 3) == 0) && ((((uintptr_t)C) & 15) == 0);
+    const float oscale = (F16 && out_scale) ? *out_scale : 1.f;       // power of two: exact
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= N) break;                                                  // warp-uniform
@@ -165,7 +181,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       }
       tmem_ld32(tq + Cfg::CORR_COL, w);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += w[j];
+      for (int j = 0; j < 32; ++j) v[j] = F16 ? (v[j] + w[j]) * oscale : v[j] + w[j];
       if (row < M) {
         float* out = C + (size_t)row * N + n0 + c0;
         if (vec_ok && n0 + c0 + 32 <= N) {
@@ -234,6 +250,38 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restric
   }
 }
 
+// x*s -> (hi, lo) fp16 planes, s = 2^(14 - ceil(log2(amax))) read from the device (amax = max |x|, float bits, made by the
+// producer of x); also publishes out_scale = s^-2 for the epilogue of a Gram GEMM (both operands share the planes).
+__device__ __forceinline__ float f16_scale_of(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);                                     // amax = m * 2^e, m in [0.5, 1)  ->  amax * 2^(14-e) in [2^13, 2^14)
+  return ldexpf(1.f, 14 - e);
+}
+__global__ void __launch_bounds__(256) split_f16_kernel(const float4* __restrict__ x, long long n4, const float* __restrict__ amax,
+                                                        uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ out_scale) {
+  const float s = f16_scale_of(*amax);
+  if (out_scale && blockIdx.x == 0 && threadIdx.x == 0) *out_scale = (1.f / s) * (1.f / s);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = x[i];
+    const float in[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2half_rn(in[j]);
+      l[j] = __float2half_rn(in[j] - __half2float(h[j]));
+    }
+    uint2 ph, pl;
+    ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    hi[i] = ph;
+    lo[i] = pl;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -250,14 +298,14 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows) {
+static int make_map(CUtensorMap* map, const void* base, int rows, int K, int box_rows, bool f16 = false) {
   EncodeTiledFn enc = get_encode_fn();
   MPN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * (f16 ? sizeof(__half) : sizeof(float))};
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? TC_BK_F16 : TC_BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MPN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%d K=%d)", (int)r, rows, K);
   return MPN_OK;
@@ -280,18 +328,18 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K) {
   return 2 * plane_a + 2 * plane_b + 1024;
 }
 
-template <int BN, bool SYM>
+template <int BN, bool SYM, bool F16 = false>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const float* bias,
                      float* C, int M, int N, int K, cudaStream_t st, const int* graph_nptr = nullptr, const long long* g_off = nullptr,
-                     int n_graphs = 1, int max_ng = 0) {
+                     int n_graphs = 1, int max_ng = 0, const float* out_scale = nullptr) {
   static bool configured = false;
   if (!configured) {
-    MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+    MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN, SYM, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
     configured = true;
   }
   dim3 grid(div_up(N, BN), div_up(M, TC_BM));
   if (graph_nptr) grid = dim3(div_up(max_ng, BN), div_up(max_ng, TC_BM), n_graphs);
-  gemm_nt_3xtf32_kernel<BN, SYM><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ah, al, bh, bl, bias, C, M, N, K, graph_nptr, g_off);
+  gemm_nt_3xtf32_kernel<BN, SYM, F16><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ah, al, bh, bl, bias, C, M, N, K, graph_nptr, g_off, out_scale);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -341,6 +389,36 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
   if (BN == 256) return launch_tc<256, false>(ah, al, bh, bl, bias, C, M, N, K, st);
   if (sym) return launch_tc<128, true>(ah, al, bh, bl, bias, C, M, N, K, st);
   return launch_tc<128, false>(ah, al, bh, bl, bias, C, M, N, K, st);
+}
+
+static bool gram_f16_enabled() {
+  static int opt = -1;                               // MPN_GRAM_F16=0 keeps the TF32 planes (diagnostics)
+  if (opt < 0) { const char* e = getenv("MPN_GRAM_F16"); opt = e ? atoi(e) : 1; }
+  return opt != 0;
+}
+
+// Gram block C[M,N] = A X^T where A is the row block of X starting at row a_row0 (X: [N,K], amax_dev = max |X| as float bits
+// written by the producer of X).  fp16 planes (3xFP16) when K % 8 == 0, else the TF32 path.  Symmetric tiles when A == X.
+int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const float* amax_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const float* A = X + (size_t)a_row0 * K;
+  if (!gram_f16_enabled() || amax_dev == nullptr || (K % 8) != 0)
+    return gemm_nt_tc(A, X, nullptr, C, M, N, K, ws, ws_bytes, st);
+  MPN_REQUIRE(gemm_tc_supported(M, N, K), "tcgen05 Gram: unsupported shape %d x %d x %d", M, N, K);
+  MPN_REQUIRE(ws && ws_bytes >= gemm_tc_workspace_bytes(M, N, K), "tcgen05 Gram: workspace too small");
+  char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  const size_t plane = (((size_t)N * K * sizeof(__half)) + 255) & ~(size_t)255;
+  __half* hi = (__half*)w;
+  __half* lo = (__half*)(w + plane);
+  float* out_scale = (float*)(w + 2 * plane);
+  split_f16_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi, (uint2*)lo, out_scale);
+  MPN_LAUNCH_OK();
+  CUtensorMap ah, al, bh, bl;
+  MPN_TRY(make_map(&ah, hi + (size_t)a_row0 * K, M, K, TC_BM, true));
+  MPN_TRY(make_map(&al, lo + (size_t)a_row0 * K, M, K, TC_BM, true));
+  MPN_TRY(make_map(&bh, hi, N, K, 128, true));
+  MPN_TRY(make_map(&bl, lo, N, K, 128, true));
+  if (a_row0 == 0 && M == N) return launch_tc<128, true, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);
+  return launch_tc<128, false, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);
 }
 
 // Block-diagonal Gram matrix of a batch of graphs: for graph i with rows [nptr[i], nptr[i+1]) the ng x ng block

@@ -18,6 +18,10 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
                const float* a_shift = nullptr, const float* b_hi_cached = nullptr, const float* b_lo_cached = nullptr,
                const int* row_gid = nullptr);   // row_gid: a_scale/a_shift are [n_graphs][K] tables indexed by the row's graph
 int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t st);
+// Gram block of the row block [a_row0, a_row0+M) of X [N,K] against all of X: 3xFP16 planes scaled by max|X| (amax_dev: float
+// bits on the device) when K % 8 == 0, else / when amax_dev is NULL the TF32 path of gemm_nt_tc
+int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const float* amax_dev, void* workspace, size_t workspace_bytes,
+               cudaStream_t st);
 bool gemm_tc_supported(int M, int N, int K);
 int gram_blockdiag_tc(const float* X, int N, int K, const int* graph_nptr, const long long* g_off, int n_graphs, int max_ng,
                       float* Gbuf, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -287,6 +287,11 @@ int mpn_labels_reference_host(const int32_t* src_host, const int32_t* dst_host, 
 size_t mpn_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int impl);
 int mpn_gemm_nt(const float* A_dev, const float* B_dev, const float* bias_dev, float* C_dev,
                 int32_t M, int32_t N, int32_t K, int impl, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* The Gram block the edge features use (inference.py:453-456 as one GEMM): C[M,N] = X[row0:row0+M] X^T, X [N,K] fp32.
+ * amax_dev: device float = max |X| -> "3xFP16" operand planes (x * 2^k = hi + lo in fp16, three kind::f16 products, fp32
+ * accumulate; K % 8 == 0); NULL -> 3xTF32.  Workspace: mpn_gemm_nt_workspace_bytes(M, N, K, 1). */
+int mpn_gram_nt(const float* X_dev, int32_t row0, float* C_dev, int32_t M, int32_t N, int32_t K, const float* amax_dev,
+                void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * After the hot path: evaluation counts and the tracking output.

@@ -128,6 +128,34 @@ def test_gemm_tcgen05_3xtf32_matches_fp64(m, shape):
     assert err <= 6e-7 * K, err
 
 
+@pytest.mark.parametrize("N,K,row0,M,scale", [(640, 256, 0, 640, 1.0), (640, 2048, 128, 320, 0.015), (1000, 64, 0, 1000, 3e4),
+                                               (300, 96, 77, 100, 1e-6)])
+def test_gram_3xfp16_matches_fp64(m, N, K, row0, M, scale):
+    """The Gram block of the edge features on fp16 operand planes (x * 2^k = hi + lo, three kind::f16 products): fp32-level
+    accuracy at any input magnitude (the planes are scaled from max |X|), symmetric and row-block shapes."""
+    g = torch.Generator().manual_seed(N + K + row0)
+    X = torch.randn(N, K, generator=g) * scale
+    X[5] *= 1e-3                                                              # a row far below the maximum
+    Xd = X.to(dev())
+    L = m._lib.lib()
+    ws = torch.empty(L.mpn_gemm_nt_workspace_bytes(M, N, K, 1), dtype=torch.uint8, device=dev())
+    amax = Xd.abs().max().reshape(1)
+    ref = X[row0:row0 + M].double() @ X.double().t()
+    # The tensor core adds into its fp32 accumulator with truncation: the bias grows with |accumulator| x accumulation steps, so
+    # coherent sums (|x|^2, the entries where row == column) carry ~5e-6 relative, incoherent ones stay at the fp32 level.  The
+    # edge features never use the coherent entries (node norms come from fp64 row statistics, near-duplicates are recomputed).
+    bound = 1e-5 * K * scale * scale
+    incoherent = ref.abs() < 0.2 * K * scale * scale
+    for am in (amax.data_ptr(), None):
+        Cd = torch.full((M, N), float("nan"), device=dev())
+        m._lib.check(L.mpn_gram_nt(Xd.data_ptr(), row0, Cd.data_ptr(), M, N, K, am, ws.data_ptr(), ws.numel(),
+                                   torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        diff = (Cd.cpu().double() - ref).abs()
+        assert diff.max().item() <= bound, (am is None, diff.max().item(), bound)
+        assert diff[incoherent].max().item() <= 6e-7 * K * scale * scale, (am is None, diff[incoherent].max().item())
+
+
 def test_gemm_tcgen05_gram_aliasing(m):
     """A given as a row block of B (the Gram-matrix call of the edge features) shares the split planes."""
     g = torch.Generator().manual_seed(5)
