@@ -37,6 +37,9 @@ class MpnWeights(C.Structure):
                 ("node_gamma", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_beta", C.c_void_p * MPN_MAX_NODE_LAYERS),
                 ("small", C.c_void_p),
                 ("node_w_hi", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_w_lo", C.c_void_p * MPN_MAX_NODE_LAYERS),
+                ("node_w_hi16", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_w_lo16", C.c_void_p * MPN_MAX_NODE_LAYERS),
+                ("node_w_scale16", C.c_float * MPN_MAX_NODE_LAYERS), ("node_bn_gmax", C.c_float * MPN_MAX_NODE_LAYERS),
+                ("node_bn_bmax", C.c_float * MPN_MAX_NODE_LAYERS),
                 ("node_agg", C.c_int32), ("reserved", C.c_int32)]
 
 
@@ -95,6 +98,7 @@ _PROTOS = {
     "mpn_plan_node_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "mpn_plan_h_full": (C.c_void_p, [C.c_void_p]),
     "mpn_split_tf32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpn_split_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "mpn_forward_sharded": (C.c_int, [C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(MpnPeerCtx),
                                       C.c_void_p, C.c_size_t, C.c_void_p]),

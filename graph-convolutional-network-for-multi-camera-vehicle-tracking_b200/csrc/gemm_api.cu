@@ -28,6 +28,10 @@ int mpn_gram_nt(const float* X, int32_t row0, float* C, int32_t M, int32_t N, in
   return gram_nt_tc(X, row0, C, M, N, K, amax_dev, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int mpn_split_f16(const float* x, int64_t n, float amax, void* hi, void* lo, float* scale_out_host, void* stream) {
+  return split_f16_host_scale(x, (long long)n, amax, hi, lo, scale_out_host, (cudaStream_t)stream);
+}
+
 int mpn_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream) {
   return split_tf32(x, (long long)n, hi, lo, (cudaStream_t)stream);
 }

@@ -20,6 +20,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <cmath>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tcgen05.cuh"
@@ -389,6 +391,105 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
   if (BN == 256) return launch_tc<256, false>(ah, al, bh, bl, bias, C, M, N, K, st);
   if (sym) return launch_tc<128, true>(ah, al, bh, bl, bias, C, M, N, K, st);
   return launch_tc<128, false>(ah, al, bh, bl, bias, C, M, N, K, st);
+}
+
+// fp16 operand planes with the fused input transform f(x)[m,k] = relu(x*scale[k] + shift[k]) of the previous encoder layer.
+// The plane scale comes from *amax_dev (float bits, device) when given, else from amax_host; out_scale = 1 / (s_a * b_scale).
+__global__ void __launch_bounds__(256) split_f16_bn_kernel(const float4* __restrict__ x, long long n4, int K, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, const int* __restrict__ row_gid,
+                                                           const float* __restrict__ amax_dev, float amax_host, float b_scale,
+                                                           uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ out_scale) {
+  const float s = f16_scale_of(amax_dev ? *amax_dev : amax_host);
+  if (out_scale && blockIdx.x == 0 && threadIdx.x == 0) *out_scale = (1.f / s) * (1.f / b_scale);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = x[i];
+    float in[4] = {v.x, v.y, v.z, v.w};
+    if (scale != nullptr) {
+      const int k = (int)((i * 4) % K);
+      const size_t o = (row_gid ? (size_t)row_gid[(i * 4) / K] * K : 0) + k;
+      const float4 sc = *reinterpret_cast<const float4*>(scale + o), sh = *reinterpret_cast<const float4*>(shift + o);
+      in[0] = fmaxf(fmaf(in[0], sc.x, sh.x), 0.f);
+      in[1] = fmaxf(fmaf(in[1], sc.y, sh.y), 0.f);
+      in[2] = fmaxf(fmaf(in[2], sc.z, sh.z), 0.f);
+      in[3] = fmaxf(fmaf(in[3], sc.w, sh.w), 0.f);
+    }
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t = fminf(in[j] * s, 65000.f);        // (the activation bound is mathematical: the clamp never binds)
+      h[j] = __float2half_rn(t);
+      l[j] = __float2half_rn(t - __half2float(h[j]));
+    }
+    uint2 ph, pl;
+    ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    hi[i] = ph;
+    lo[i] = pl;
+  }
+}
+__global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, long long n4, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = x[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));
+}
+
+float f16_plane_scale_host(float amax) {
+  if (!(amax > 0.f) || !std::isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);
+  return ldexpf(1.f, 14 - e);
+}
+
+// weights -> cached fp16 planes (host-known amax); returns the power-of-two scale that was applied
+int split_f16_host_scale(const float* x, long long n, float amax, void* hi, void* lo, float* scale_out, cudaStream_t st) {
+  MPN_REQUIRE(x && hi && lo && n > 0 && (n % 4) == 0, "split_f16: bad arguments (n must be a positive multiple of 4)");
+  MPN_REQUIRE((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "split_f16: pointers must be 16-byte aligned");
+  split_f16_bn_kernel<<<(int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256), 256, 0, st>>>((const float4*)x, n / 4, 4, nullptr, nullptr, nullptr,
+                                                                                           nullptr, amax, 1.f, (uint2*)hi, (uint2*)lo, nullptr);
+  MPN_LAUNCH_OK();
+  if (scale_out) *scale_out = f16_plane_scale_host(amax);
+  return MPN_OK;
+}
+
+// C = f(A) B^T + bias on 3xFP16 planes: A split here (fused BatchNorm+ReLU of the previous layer), B planes cached.
+// a_amax_dev == nullptr && a_amax_host <= 0: max |A| is measured first (one pass over A; layer 0).
+int gemm_nt_tc_f16(const float* A, const float* bias, float* C, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t st,
+                   const float* a_scale, const float* a_shift, const int* row_gid, float a_amax_host, const void* b_hi16,
+                   const void* b_lo16, float b_scale) {
+  MPN_REQUIRE(gemm_tc_supported(M, N, K) && (K % 8) == 0, "tcgen05 fp16-plane GEMM: unsupported shape %d x %d x %d", M, N, K);
+  MPN_REQUIRE(ws && ws_bytes >= gemm_tc_workspace_bytes(M, N, K), "tcgen05 GEMM: workspace too small");
+  MPN_REQUIRE(b_hi16 && b_lo16 && b_scale > 0.f, "tcgen05 fp16-plane GEMM: missing weight planes");
+  char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  const size_t plane = (((size_t)M * K * sizeof(__half)) + 255) & ~(size_t)255;
+  __half* a_hi = (__half*)w;
+  __half* a_lo = (__half*)(w + plane);
+  float* out_scale = (float*)(w + 2 * plane);
+  unsigned int* amax_bits = (unsigned int*)(w + 2 * plane + 256);
+  const float* amax_dev = nullptr;
+  if (!(a_amax_host > 0.f)) {
+    MPN_CUDA_OK(cudaMemsetAsync(amax_bits, 0, sizeof(unsigned int), st));
+    absmax_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, amax_bits);
+    MPN_LAUNCH_OK();
+    amax_dev = (const float*)amax_bits;
+  }
+  split_f16_bn_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, K, a_scale, a_shift, row_gid, amax_dev, a_amax_host,
+                                                   b_scale, (uint2*)a_hi, (uint2*)a_lo, out_scale);
+  MPN_LAUNCH_OK();
+  CUtensorMap ah, al, bh, bl;
+  MPN_TRY(make_map(&ah, a_hi, M, K, TC_BM, true));
+  MPN_TRY(make_map(&al, a_lo, M, K, TC_BM, true));
+  MPN_TRY(make_map(&bh, b_hi16, N, K, 128, true));
+  MPN_TRY(make_map(&bl, b_lo16, N, K, 128, true));
+  return launch_tc<128, false, true>(ah, al, bh, bl, bias, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);
 }
 
 static bool gram_f16_enabled() {

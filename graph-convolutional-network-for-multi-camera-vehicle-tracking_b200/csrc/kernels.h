@@ -23,6 +23,12 @@ int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t s
 int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const float* amax_dev, void* workspace, size_t workspace_bytes,
                cudaStream_t st);
 bool gemm_tc_supported(int M, int N, int K);
+// 3xFP16 variant for the node encoder: A is split here into fp16 planes (fused BatchNorm+ReLU; plane scale from a_amax_host, or
+// measured on the device when a_amax_host <= 0), B planes (b_hi16/b_lo16, scaled by b_scale) are cached by the caller
+int gemm_nt_tc_f16(const float* A, const float* bias, float* C, int M, int N, int K, void* workspace, size_t workspace_bytes,
+                   cudaStream_t st, const float* a_scale, const float* a_shift, const int* row_gid, float a_amax_host,
+                   const void* b_hi16, const void* b_lo16, float b_scale);
+int split_f16_host_scale(const float* x, long long n, float amax, void* hi, void* lo, float* scale_out, cudaStream_t st);
 int gram_blockdiag_tc(const float* X, int N, int K, const int* graph_nptr, const long long* g_off, int n_graphs, int max_ng,
                       float* Gbuf, void* ws, size_t ws_bytes, cudaStream_t st);
 

@@ -1535,6 +1535,20 @@ static FinArgs make_fin(const mpn_fwd_plan* p, int stage, bool fused) {
   return f;
 }
 
+// 3xFP16 planes for encoder layer l: cached weight planes present, K a multiple of 8 (TMA row stride), not disabled
+static bool encoder_f16(const mpn_fwd_plan* p, int l, int K) {
+  static int opt = -1;                               // MPN_ENC_F16=0 keeps the TF32 planes (diagnostics)
+  if (opt < 0) { const char* e = getenv("MPN_ENC_F16"); opt = e ? atoi(e) : 1; }
+  return opt != 0 && (K % 8) == 0 && p->w.node_w_hi16[l] && p->w.node_w_lo16[l] && p->w.node_w_scale16[l] > 0.f;
+}
+// Upper bound of |input of layer l|.  Layer 0: unknown (-1: measured on the device).  Layer l > 0 reads relu(BN(y)) of layer
+// l-1 over M_total rows: a z-score of M values is at most sqrt(M-1) in magnitude, so |.| <= max|beta| + max|gamma| sqrt(M-1).
+static float encoder_input_bound(const mpn_fwd_plan* p, int l, int M_total) {
+  if (l == 0) return -1.f;
+  const float b = p->w.node_bn_bmax[l - 1] + p->w.node_bn_gmax[l - 1] * sqrtf((float)(M_total > 1 ? M_total - 1 : 1));
+  return b > 0.f ? b * 1.0001f : 1.f;
+}
+
 int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
   MPN_REQUIRE(p && x, "node_encoder: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1550,9 +1564,13 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
     bool done = false;
     const int* gid = batched ? p->g.node_gid : nullptr;        // per-graph BatchNorm tables [G][K] when batched
     if (p->use_tc && gemm_tc_supported(M, Nc, K)) {
-      // tensor-core path: BatchNorm+ReLU of the previous layer is applied while the operand is split into TF32 planes
-      MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh,
-                         p->w.node_w_hi[l], p->w.node_w_lo[l], gid));
+      // tensor-core path: BatchNorm+ReLU of the previous layer is applied while the operand is split into its two planes
+      if (encoder_f16(p, l, K))
+        MPN_TRY(gemm_nt_tc_f16(in, p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh, gid,
+                               encoder_input_bound(p, l, M), p->w.node_w_hi16[l], p->w.node_w_lo16[l], p->w.node_w_scale16[l]));
+      else
+        MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh,
+                           p->w.node_w_hi[l], p->w.node_w_lo[l], gid));
       done = true;
     }
     if (!done) MPN_TRY(gemm_nt_simt(in, p->w.node_w[l], p->w.node_b[l], sc, sh, out, M, Nc, K, st, gid));
@@ -1587,7 +1605,10 @@ static int node_encoder_sharded(mpn_fwd_plan* p, const float* x, const PeerArgs&
     const int K = p->w.node_dims[l], Nc = p->w.node_dims[l + 1];
     MPN_REQUIRE(Nc <= MPN_PEER_CSTAT_COLS, "sharded node encoder: layer width %d > %d", Nc, MPN_PEER_CSTAT_COLS);
     float* out = bufs[l & 1];
-    if (p->use_tc && gemm_tc_supported(M, Nc, K))
+    if (p->use_tc && gemm_tc_supported(M, Nc, K) && encoder_f16(p, l, K))
+      MPN_TRY(gemm_nt_tc_f16(in, p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh, nullptr,
+                             encoder_input_bound(p, l, p->g.n_cols), p->w.node_w_hi16[l], p->w.node_w_lo16[l], p->w.node_w_scale16[l]));
+    else if (p->use_tc && gemm_tc_supported(M, Nc, K))
       MPN_TRY(gemm_nt_tc(in, p->w.node_w[l], p->w.node_b[l], out, M, Nc, K, p->gemm_ws, p->gemm_ws_bytes, st, sc, sh,
                          p->w.node_w_hi[l], p->w.node_w_lo[l], nullptr));
     else

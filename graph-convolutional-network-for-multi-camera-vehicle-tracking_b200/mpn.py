@@ -241,6 +241,19 @@ class MOTMPNet(nn.Module):
                                                          current_stream_ptr(device)))
                 keep += [hi, lo]
                 W.node_w_hi[i], W.node_w_lo[i] = hi.data_ptr(), lo.data_ptr()
+                if l.in_features % 8 == 0:
+                    # fp16 planes of weight * 2^k (operands of the 3xFP16 GEMM: twice the tensor-pipe rate of TF32, same 22 bits)
+                    hi16 = torch.empty(ts[0].shape, dtype=torch.float16, device=device)
+                    lo16 = torch.empty_like(hi16)
+                    scale = C.c_float(0.0)
+                    with torch.cuda.device(device):
+                        _lib.check(_lib.lib().mpn_split_f16(ts[0].data_ptr(), ts[0].numel(), float(ts[0].abs().max()),
+                                                            hi16.data_ptr(), lo16.data_ptr(), C.byref(scale),
+                                                            current_stream_ptr(device)))
+                    keep += [hi16, lo16]
+                    W.node_w_hi16[i], W.node_w_lo16[i], W.node_w_scale16[i] = hi16.data_ptr(), lo16.data_ptr(), scale.value
+            # bound of the next layer's input: |relu(BN(y))| <= max|beta| + max|gamma| * sqrt(M - 1)
+            W.node_bn_gmax[i], W.node_bn_bmax[i] = float(ts[2].abs().max()), float(ts[3].abs().max())
         small = torch.zeros(_lib.W_SMALL_FLOATS, dtype=torch.float32, device=device)
 
         def put(off, t):

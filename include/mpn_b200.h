@@ -145,6 +145,13 @@ typedef struct mpn_weights {
   /* optional cache: TF32 hi/lo planes of node_w[i] made by mpn_split_tf32 (NULL -> split on every forward) */
   const float* node_w_hi[MPN_MAX_NODE_LAYERS];
   const float* node_w_lo[MPN_MAX_NODE_LAYERS];
+  /* optional cache: fp16 planes of node_w[i] * node_w_scale16[i] made by mpn_split_f16 ("3xFP16" GEMM, used when K % 8 == 0),
+   * and max|gamma|, max|beta| of the layer's BatchNorm (bound of the next layer's input: |relu(BN(y))| <= bmax + gmax*sqrt(M-1)) */
+  const void* node_w_hi16[MPN_MAX_NODE_LAYERS];
+  const void* node_w_lo16[MPN_MAX_NODE_LAYERS];
+  float node_w_scale16[MPN_MAX_NODE_LAYERS];
+  float node_bn_gmax[MPN_MAX_NODE_LAYERS];
+  float node_bn_bmax[MPN_MAX_NODE_LAYERS];
   /* node aggregation of the messages (models/mpn.py:193-202): scatter_add / scatter_mean / scatter_max over row */
   int32_t node_agg;                               /* MPN_AGG_SUM (shipped config) | MPN_AGG_MEAN | MPN_AGG_MAX */
   int32_t reserved;
@@ -154,6 +161,9 @@ enum { MPN_AGG_SUM = 0, MPN_AGG_MEAN = 1, MPN_AGG_MAX = 2 };
 /* x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi): the operand planes of the 3xTF32 tensor-core GEMM.
  * n must be a multiple of 4, pointers 16-byte aligned. */
 int mpn_split_tf32(const float* x_dev, int64_t n, float* hi_dev, float* lo_dev, void* stream);
+/* x * s = hi + lo in fp16 with s = the power of two that puts amax (= max |x|, given by the caller) in [2^13, 2^14);
+ * *scale_out_host receives s.  hi/lo: dev fp16 [n]. */
+int mpn_split_f16(const float* x_dev, int64_t n, float amax, void* hi_dev, void* lo_dev, float* scale_out_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Forward (K1b-K4).  Replaces MOTMPNet.forward (models/mpn.py:250-299) for the supported family:
