@@ -111,15 +111,24 @@ __global__ void task_fill(const int* __restrict__ taskptr, int n_rows, int max_t
     for (int t = taskptr[r]; t < taskptr[r + 1] && t < max_tasks; ++t) task_row[t] = r;
 }
 
+// deferred validation: an invalid edge list must not reach the sweeps as inconsistent tables -> turn it into an empty graph
+// (rowptr = 0 everywhere, hence no tasks); the host raises when it reads the flag word later
+__global__ void csr_guard(const int* __restrict__ flags, int n_rows, int* __restrict__ rowptr) {
+  if (*flags == 0) return;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n_rows; r += gridDim.x * blockDim.x) rowptr[r] = 0;
+}
+
 template <typename IdxT>
-static int graph_build_impl(mpn_graph* g, const IdxT* row, const IdxT* col, cudaStream_t st) {
+static int graph_build_impl(mpn_graph* g, const IdxT* row, const IdxT* col, cudaStream_t st, int* flags_dev = nullptr,
+                            int* flags_host_pinned = nullptr) {
   MPN_REQUIRE(g != nullptr, "graph is NULL");
   MPN_REQUIRE(g->n_nodes > 0 && g->n_cols > 0 && g->n_edges >= 0, "bad graph sizes");
   MPN_REQUIRE(g->n_edges < (1ll << 31), "n_edges must be < 2^31 per shard");
   MPN_REQUIRE(g->chunk >= 32 && g->chunk <= 4096 && (g->chunk & (g->chunk - 1)) == 0, "chunk must be a power of two in [32,4096]");
   MPN_REQUIRE(g->max_tasks >= g->n_edges / g->chunk + g->n_nodes, "max_tasks too small (need E/chunk + N)");
   MPN_REQUIRE(g->rowptr && g->taskptr && g->task_row && g->n_tasks && (g->col || g->n_edges == 0), "graph table pointer is NULL");
-  int* flags = g->n_tasks;                        // reused as the flag word until task_scan overwrites it
+  const bool deferred = flags_dev != nullptr && flags_host_pinned != nullptr;
+  int* flags = deferred ? flags_dev : g->n_tasks;  // (sync mode: n_tasks doubles as the flag word until task_scan overwrites it)
   MPN_CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(int), st));
   if (g->n_edges == 0) {
     csr_empty<<<div_up(g->n_nodes + 1, 256), 256, 0, st>>>(g->n_nodes, g->rowptr);
@@ -135,16 +144,24 @@ static int graph_build_impl(mpn_graph* g, const IdxT* row, const IdxT* col, cuda
                                                  g->rowptr, g->col, flags);
   }
   MPN_LAUNCH_OK();
-  int h_flags = 0;
-  MPN_CUDA_OK(cudaMemcpyAsync(&h_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-  MPN_CUDA_OK(cudaStreamSynchronize(st));
-  if (h_flags & 2) {
-    set_error("edge_index has node ids outside [row_offset, row_offset+n_nodes) x [0, n_cols)");
-    return MPN_ERR_INVALID;
-  }
-  if (h_flags & 1) {
-    set_error("edge_index is not strictly (row, col)-sorted (unsorted or duplicate edges)");
-    return MPN_ERR_UNSORTED;
+  if (deferred) {
+    // no host round trip on the critical path: the flag word travels to pinned host memory behind the scan, the tables of an
+    // invalid edge list are emptied on the device, and the caller checks *flags_host_pinned at its next synchronisation point
+    MPN_CUDA_OK(cudaMemcpyAsync(flags_host_pinned, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    csr_guard<<<min(kNumSMs, div_up(g->n_nodes + 1, 256)), 256, 0, st>>>(flags, g->n_nodes, g->rowptr);
+    MPN_LAUNCH_OK();
+  } else {
+    int h_flags = 0;
+    MPN_CUDA_OK(cudaMemcpyAsync(&h_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MPN_CUDA_OK(cudaStreamSynchronize(st));
+    if (h_flags & 2) {
+      set_error("edge_index has node ids outside [row_offset, row_offset+n_nodes) x [0, n_cols)");
+      return MPN_ERR_INVALID;
+    }
+    if (h_flags & 1) {
+      set_error("edge_index is not strictly (row, col)-sorted (unsorted or duplicate edges)");
+      return MPN_ERR_UNSORTED;
+    }
   }
   task_scan<<<1, 1024, 0, st>>>(g->rowptr, g->n_nodes, g->chunk, g->taskptr, g->n_tasks);
   MPN_LAUNCH_OK();
@@ -279,6 +296,12 @@ int mpn_graph_build(mpn_graph* g, const int64_t* edge_index_dev, void* stream) {
   if (!g) { mpn::set_error("graph is NULL"); return MPN_ERR_INVALID; }
   return mpn::graph_build_impl<long long>(g, (const long long*)edge_index_dev,
                                           (const long long*)edge_index_dev + g->n_edges, (cudaStream_t)stream);
+}
+
+int mpn_graph_build_deferred(mpn_graph* g, const int64_t* edge_index_dev, int32_t* flags_dev, int32_t* flags_host_pinned, void* stream) {
+  if (!g || !flags_dev || !flags_host_pinned) { mpn::set_error("graph_build_deferred: NULL argument"); return MPN_ERR_INVALID; }
+  return mpn::graph_build_impl<long long>(g, (const long long*)edge_index_dev, (const long long*)edge_index_dev + g->n_edges,
+                                          (cudaStream_t)stream, flags_dev, flags_host_pinned);
 }
 
 int mpn_graph_build_i32(mpn_graph* g, const int32_t* row_dev, const int32_t* col_dev, void* stream) {

@@ -30,6 +30,21 @@ def current_stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_FLAG_SLOTS = {}
+
+
+def _flag_slot(dev):
+    """(device int, pinned host int) pair for one deferred graph build; recycled by validate()."""
+    free = _FLAG_SLOTS.setdefault(str(dev), [])
+    if free:
+        return free.pop()
+    return (torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32).pin_memory())
+
+
+def _release_flag_slot(dev, slot):
+    _FLAG_SLOTS.setdefault(str(dev), []).append(slot)
+
+
 def choose_chunk(n_edges: int) -> int:
     """Edges per task: aim for >= 4 tasks per resident warp slot of a 148-SM part, within [32, 1024]."""
     target = max(1, n_edges // (148 * 32 * 4))
@@ -44,7 +59,11 @@ class TrackletGraph:
     otherwise ``sorted_edge = original_edge[perm]``."""
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int, chunk: int = None, row_offset: int = 0,
-                 n_rows: int = None, ptr: torch.Tensor = None):
+                 n_rows: int = None, ptr: torch.Tensor = None, validate: str = "sync"):
+        """``validate='sync'`` (default) checks the edge list before returning (one host round trip; unsorted training-style
+        graphs are sorted transparently).  ``validate='deferred'`` returns without synchronising: the check result travels to
+        pinned host memory behind the build and ``.validate()`` (called by the user after the pipeline has been enqueued, and by
+        post_processing) raises then; an invalid list leaves an empty graph on the device, never inconsistent tables."""
         if not edge_index.is_cuda:
             raise RuntimeError("TrackletGraph needs a CUDA edge_index: the B200 path has no CPU fallback")
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
@@ -95,6 +114,19 @@ class TrackletGraph:
             ei = ei.long()
         ei = ei.contiguous()
         stream = current_stream_ptr(dev)
+        self._pending = None
+        if validate not in ("sync", "deferred"):
+            raise ValueError("validate must be 'sync' or 'deferred'")
+        if validate == "deferred":
+            slot = _flag_slot(dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().mpn_graph_build_deferred(C.byref(self.struct), ei.data_ptr(), slot[0].data_ptr(),
+                                                               slot[1].data_ptr(), stream))
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._pending = (slot, ev)
+            self._keepalive = ei
+            return
         with torch.cuda.device(dev):
             try:
                 _lib.check(_lib.lib().mpn_graph_build(C.byref(self.struct), ei.data_ptr(), stream))
@@ -108,6 +140,22 @@ class TrackletGraph:
                 ei = ei[:, perm].contiguous()
                 _lib.check(_lib.lib().mpn_graph_build(C.byref(self.struct), ei.data_ptr(), stream))
         self._keepalive = ei
+
+    def validate(self):
+        """Deferred validation: wait for the build, then raise what ``validate='sync'`` would have raised.  No-op otherwise."""
+        if getattr(self, "_pending", None) is None:
+            return self
+        slot, ev = self._pending
+        ev.synchronize()
+        flags = int(slot[1].item())
+        self._pending = None
+        _release_flag_slot(self.device, slot)
+        if flags & 2:
+            raise _lib.MpnError(_lib.MPN_ERR_INVALID, "edge_index has node ids outside [row_offset, row_offset+n_nodes) x [0, n_cols)")
+        if flags & 1:
+            raise _lib.UnsortedEdgeIndex(_lib.MPN_ERR_UNSORTED, "edge_index is not strictly (row, col)-sorted (unsorted or duplicate "
+                                         "edges): build the graph with validate='sync' to have it sorted")
+        return self
 
     @classmethod
     def from_cameras(cls, cam_ids, device, chunk: int = None, materialize_edge_index: bool = False, row_block=None):

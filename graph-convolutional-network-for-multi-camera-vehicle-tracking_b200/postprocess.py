@@ -29,6 +29,7 @@ class _Post:
         self.dev = predictions.device
         pre = getattr(data, "mpn_graph", None)
         self.g = pre if pre is not None else graph_for(data, data.edge_index, int(data.num_nodes))
+        self.g.validate()                          # a graph built with validate='deferred' is checked here at the latest
         self.lib = _lib.lib()
         act = (predictions.reshape(-1) != 0).to(torch.uint8)
         self.act = act[self.g.perm].contiguous() if self.g.perm is not None else act.contiguous()

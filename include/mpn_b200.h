@@ -83,6 +83,12 @@ typedef struct mpn_graph {
 int mpn_graph_build(mpn_graph* g, const int64_t* edge_index_dev, void* stream);
 /* Same from int32 row/col arrays already split (used for row-block shards). */
 int mpn_graph_build_i32(mpn_graph* g, const int32_t* row_dev, const int32_t* col_dev, void* stream);
+/* Same tables without the host round trip: the validity flags (bit 0: not strictly (row,col)-sorted, bit 1: node id out of
+ * range) are copied to *flags_host_pinned (page-locked host int) behind the scan and the call returns without synchronising;
+ * an invalid edge list leaves an EMPTY graph on the device (no task, so later sweeps touch nothing).  The caller reads the
+ * flag word after its next synchronisation of `stream`.  flags_dev: one device int of scratch that must stay alive until then. */
+int mpn_graph_build_deferred(mpn_graph* g, const int64_t* edge_index_dev, int32_t* flags_dev, int32_t* flags_host_pinned,
+                             void* stream);
 
 /* Graph construction on the device.  Replaces inference.py:407-414: for every camera
  * ascending, cartesian_prod(nodes in the camera, nodes not in it).  Nodes must be grouped by camera (dataset.py:279-281);

@@ -93,6 +93,37 @@ def test_graph_unsorted_and_invalid(m):
         m.TrackletGraph(bad.to(dev()), 40)                                         # node id out of range
 
 
+def test_graph_deferred_validation(m):
+    """validate='deferred': no host round trip in the build; same tables; an invalid edge list leaves an EMPTY graph on the
+    device (sweeps touch nothing) and raises at .validate() what the synchronous build raises immediately."""
+    x, ei, cam, _ = mo.synth_graph(60, 4, 5, D=64)
+    g0 = m.TrackletGraph(ei.to(dev()), 60, chunk=32)
+    g1 = m.TrackletGraph(ei.to(dev()), 60, chunk=32, validate="deferred")
+    assert g1.validate() is g1 and g1.validate() is g1                          # idempotent
+    for name in ("rowptr", "taskptr", "n_tasks"):
+        assert torch.equal(getattr(g0, name), getattr(g1, name)), name
+    assert torch.equal(g0.col[:g0.n_edges], g1.col[:g1.n_edges])
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(0))
+    gu = m.TrackletGraph(ei[:, perm].to(dev()), 60, validate="deferred")
+    params = mo.shipped_model_params(1, 1, 64, (48,))
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(mo.init_weights(params, "resnet101", 3), strict=True)
+    net = net.to(dev()).eval()
+    ea = torch.rand(ei.shape[1], 2, device=dev())
+    net.use_cuda_graph = False
+    net(Data(x=x.to(dev()), edge_attr=ea, mpn_graph=gu))                        # enqueued on the emptied tables: must not fault
+    torch.cuda.synchronize()
+    assert int(gu.n_tasks.item()) == 0 and int(gu.rowptr.abs().sum().item()) == 0
+    with pytest.raises(m._lib.UnsortedEdgeIndex):
+        gu.validate()
+    bad = ei.clone(); bad[1, 7] = 99
+    gb = m.TrackletGraph(bad.to(dev()), 60, validate="deferred")
+    with pytest.raises(m._lib.MpnError):
+        gb.validate()
+    with pytest.raises(ValueError):
+        m.TrackletGraph(ei.to(dev()), 60, validate="later")
+
+
 # ---------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("shape", [(300, 1024, 2048), (257, 130, 96), (64, 32, 128), (1000, 512, 1024), (33, 7, 50)])
 def test_gemm_simt_matches_fp64(m, shape):
