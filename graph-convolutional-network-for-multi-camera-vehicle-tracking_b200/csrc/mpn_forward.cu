@@ -109,6 +109,30 @@ __device__ __forceinline__ TaskRange task_range(const mpn_graph& g, int t) {
   return r;
 }
 
+// Task ranges two strides ahead: task_range() is a chain of dependent loads (task_row -> rowptr/taskptr), ~2 L2 round trips that
+// a warp would otherwise pay at the start of every task.  Stage A fetches the row of task t + 2*stride, stage B the range of task
+// t + stride from the row fetched one iteration earlier; the current task never waits.
+struct TaskPrefetch {
+  TaskRange cur, nxt;
+  int row_n;                                         // row of task t + stride (stage A result of the previous iteration)
+  __device__ __forceinline__ void start(const mpn_graph& g, int t, int stride, int n_tasks) {
+    if (t < n_tasks) cur = task_range(g, t);
+    row_n = (t + stride < n_tasks) ? g.task_row[t + stride] : 0;
+  }
+  // call at the top of the iteration for task t; afterwards `cur` is valid; call rotate() at the bottom
+  __device__ __forceinline__ int issue(const mpn_graph& g, int t, int stride, int n_tasks) {
+    if (t + stride < n_tasks) {
+      const int tn = t + stride;
+      nxt.row = row_n;
+      const int rb = g.rowptr[row_n];
+      nxt.beg = rb + (tn - g.taskptr[row_n]) * g.chunk;
+      nxt.end = min(nxt.beg + g.chunk, g.rowptr[row_n + 1]);
+    }
+    return (t + 2 * stride < n_tasks) ? g.task_row[t + 2 * stride] : 0;
+  }
+  __device__ __forceinline__ void rotate(int row_nn) { cur = nxt; row_n = row_nn; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // finalize: fixed-order reduction of block partials -> sums; sums -> folded constants.  Runs either as its own
 // one-block kernel (sharded runs: the host all-reduces the sums in between) or inside the LAST block of the sweep that
@@ -428,8 +452,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mp
   const int n_tasks = *g.n_tasks;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int cur_gid = -1;
+  TaskPrefetch tp;
+  tp.start(g, gwarp, nwarps, n_tasks);
   for (int t = gwarp; t < n_tasks; t += nwarps) {
-    const TaskRange tr = task_range(g, t);
+    const int row_nn = tp.issue(g, t, nwarps, n_tasks);
+    const TaskRange tr = tp.cur;
     if (BATCHED) {
       const int gid = g.node_gid[tr.row];
       if (gid != cur_gid) { warp_load_consts(sc, consts + (size_t)gid * FC_TOTAL, lane); cur_gid = gid; }
@@ -464,6 +491,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mp
         if (lane == 0) partials[(size_t)t * TASK_PART + k] = v;
       }
     }
+    tp.rotate(row_nn);
   }
   if (!BATCHED) {
     block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
@@ -494,7 +522,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
                                                                            float4* __restrict__ s1_task, double* __restrict__ partials,
                                                                            const float* __restrict__ A, const float* __restrict__ small,
                                                                            const FinArgs fin) {
-  constexpr int U = 4;
+  constexpr int U = (YSRC == 1 && !BATCHED) ? 8 : 4;     // stored y: 8 x 16 B in flight per lane (the sweep is bound by bytes in flight)
   __shared__ EdgeConsts scs[BATCHED ? SWEEP_THREADS / 32 : 1];
   __shared__ double red[(SWEEP_THREADS / 32) * 10];
   __shared__ double red_m[BATCHED ? 1 : SWEEP_THREADS / 32][64];
@@ -508,14 +536,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
   // per-node part of the closed-form node-BN moments, taken per task (it is linear in the task's edge count and S1):
   //   m1[c] += n_t A[row,c] + w_c.S1_t ;  m2[c] += n_t A[row,c]^2 + 2 A[row,c] (w_c.S1_t)      (w_c = W_node[c, 32:36]; lane = c)
   double m1 = 0.0, m2 = 0.0;
-  float wn[4] = {0.f, 0.f, 0.f, 0.f};
-  if (!BATCHED) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) wn[k] = small[MPN_W_NODE_W + lane * 36 + 32 + k];
-  }
   int cur_gid = -1;
+  TaskPrefetch tp;
+  tp.start(g, gwarp, nwarps, n_tasks);
   for (int t = gwarp; t < n_tasks; t += nwarps) {
-    const TaskRange tr = task_range(g, t);
+    const int row_nn = tp.issue(g, t, nwarps, n_tasks);
+    const TaskRange tr = tp.cur;
     if (BATCHED) {
       const int gid = g.node_gid[tr.row];
       if (gid != cur_gid) { warp_load_consts(sc, consts + (size_t)gid * FC_TOTAL, lane); cur_gid = gid; }
@@ -546,7 +572,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
     if (lane == 0) s1_task[t] = make_float4(s1[0], s1[1], s1[2], s1[3]);
     if (!BATCHED) {                                        // one task's term in fp32 (<= chunk edges), the running sums in fp64
       const float nt = (float)(tr.end - tr.beg);
-      const float qd = fmaf(wn[0], s1[0], fmaf(wn[1], s1[1], fmaf(wn[2], s1[2], wn[3] * s1[3])));
+      const float4 wn = *reinterpret_cast<const float4*>(small + MPN_W_NODE_W + lane * 36 + 32);      // L1-resident, once per task
+      const float qd = fmaf(wn.x, s1[0], fmaf(wn.y, s1[1], fmaf(wn.z, s1[2], wn.w * s1[3])));
       m1 += (double)fmaf(nt, a_row, qd);
       m2 += (double)(a_row * fmaf(nt, a_row, 2.0f * qd));
     }
@@ -559,6 +586,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
         t2[i] += (double)q[i];                              // <= chunk/32 fp32 terms per lane, then fp64
       }
     }
+    tp.rotate(row_nn);
   }
   if (!BATCHED) {
     const int warp = threadIdx.x >> 5;
