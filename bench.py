@@ -23,6 +23,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly one JSON line: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 NODES_1GPU, CAMS, FEAT_DIM = 4096, 8, 2048
