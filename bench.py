@@ -32,7 +32,8 @@ import torch  # noqa: E402
 NODES_1GPU, CAMS, FEAT_DIM = 4096, 8, 2048
 METRIC, UNIT = "mpn_inference_directed_edges_per_sec", "edges/s"
 # algorithmic work per directed edge (SURVEY.md section 8d / DESIGN.md "Kernels")
-BYTES_PER_EDGE = {"enc_moments": 16.0, "edge_update": 28.0, "node_moments": 16.0, "node_apply": 24.0, "forward": 84.0}
+# node_apply: y read 16 + logits 8 + the fused decisions this bench asks for (u8 prediction 1 + fp32 probability 4), SURVEY 8d row K4
+BYTES_PER_EDGE = {"enc_moments": 16.0, "edge_update": 28.0, "node_moments": 16.0, "node_apply": 29.0, "forward": 89.0}
 FLOP_PER_EDGE_GRAM = 4096.0
 
 
