@@ -20,7 +20,8 @@ W_ENC1_W, W_ENC1_B, W_ENC1_G, W_ENC1_BETA = 0, 8, 12, 16
 W_ENC2_W, W_ENC2_B, W_ENC2_G, W_ENC2_BETA = 20, 36, 40, 44
 W_EDGE_W, W_EDGE_B, W_EDGE_G, W_EDGE_BETA = 48, 320, 324, 328
 W_NODE_W, W_NODE_B, W_NODE_G, W_NODE_BETA = 332, 1484, 1516, 1548
-W_CLS_W, W_CLS_B, W_SMALL_FLOATS = 1580, 1588, 1592
+W_CLS_W, W_CLS_B = 1580, 1588
+W_EDGE_W0, W_NODE_W0, W_SMALL_FLOATS = 1592, 1864, 2888
 
 
 class MpnGraph(C.Structure):
@@ -40,7 +41,7 @@ class MpnWeights(C.Structure):
                 ("node_w_hi16", C.c_void_p * MPN_MAX_NODE_LAYERS), ("node_w_lo16", C.c_void_p * MPN_MAX_NODE_LAYERS),
                 ("node_w_scale16", C.c_float * MPN_MAX_NODE_LAYERS), ("node_bn_gmax", C.c_float * MPN_MAX_NODE_LAYERS),
                 ("node_bn_bmax", C.c_float * MPN_MAX_NODE_LAYERS),
-                ("node_agg", C.c_int32), ("reserved", C.c_int32)]
+                ("node_agg", C.c_int32), ("reattach_nodes", C.c_int32), ("reattach_edges", C.c_int32), ("reserved", C.c_int32)]
 
 
 AGG_SUM, AGG_MEAN, AGG_MAX = 0, 1, 2

@@ -32,7 +32,8 @@ enum {
   FC_BN4_T = 224,    // [32]
   FC_CLS_W = 256,    // [2][4]
   FC_CLS_B = 264,    // [2]
-  FC_TOTAL = 272
+  FC_EDGE_WE0 = 272, // [4][4]  reattach_initial_edges: W_edge columns of the initial edge encoding e0 (steps >= 2)
+  FC_TOTAL = 288
 };
 
 constexpr int SUMS = MPN_SUMS_DOUBLES;     // 96 doubles per partial row
@@ -152,6 +153,8 @@ struct FinArgs {
   unsigned int* counter;      // != nullptr: fuse into the producing kernel's last block
   double* n_total_dev;        // != nullptr: total edge count lives on the device (exchanged with the first all-reduce)
   double local_edges;         // this rank's edge count (sharded runs)
+  int re_e;                   // reattach_initial_edges: 0 off, 1 on (y of the current step is recomputed later: keep the folded
+                              // step-1 weights), 2 on and y stored (switch to the split weights after the first edge update)
 };
 
 __device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, int do_consts) {
@@ -206,7 +209,10 @@ __device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, i
   const double inv_n = 1.0 / (f.n_total_dev ? *f.n_total_dev : f.n_total);
   if (stage == MPN_STAGE_ENC0) {
     // static constants
-    if (k < 16) consts[FC_EDGE_WE + k] = small[MPN_W_EDGE_W + (k >> 2) * 68 + 64 + (k & 3)];
+    // step 1 of reattach_initial_edges sees e_in = [e0 | e0]: one folded 4x4 block (We0 + We1)
+    if (k < 16) consts[FC_EDGE_WE + k] = small[MPN_W_EDGE_W + (k >> 2) * 68 + 64 + (k & 3)] +
+                                         (f.re_e ? small[MPN_W_EDGE_W0 + (k >> 2) * 68 + 64 + (k & 3)] : 0.f);
+    if (k < 16) consts[FC_EDGE_WE0 + k] = 0.f;
     if (k < 8) consts[FC_CLS_W + k] = small[MPN_W_CLS_W + k];
     if (k < 2) consts[FC_CLS_B + k] = small[MPN_W_CLS_B + k];
     if (k < 4) {
@@ -238,6 +244,11 @@ __device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, i
         consts[FC_BN3_S + k] = (float)s;
         consts[FC_BN3_T + k] = (float)t;
       }
+    }
+    if (stage == MPN_STAGE_EDGE && f.re_e == 2 && k < 16) {
+      // every later edge update sees e_in = [e0 | e]: the two 4x4 blocks separately (idempotent after the first step)
+      consts[FC_EDGE_WE + k] = small[MPN_W_EDGE_W + (k >> 2) * 68 + 64 + (k & 3)];
+      consts[FC_EDGE_WE0 + k] = small[MPN_W_EDGE_W0 + (k >> 2) * 68 + 64 + (k & 3)];
     }
   } else if (stage == MPN_STAGE_NODE) {
     if (k < 32) {
@@ -436,7 +447,8 @@ __device__ __forceinline__ void load_edges(EdgeLoad<U>& L, const mpn_graph& g, i
 // SA: moments of the edge-update pre-activation y (and optionally materialise y)
 //   SRC 0: e_in = encoder(edge_attr[e])            (step 1)
 //   SRC 1: e_in = relu(BN3_prev(ybuf[e]))          (step >= 2; ybuf updated in place)
-template <int SRC, bool WRITE_Y, bool BATCHED>
+//   RE_E (reattach_initial_edges, steps >= 2): e_in = [e0 | e] with e0 = encoder(edge_attr[e]) recomputed: y += We0 . e0
+template <int SRC, bool WRITE_Y, bool BATCHED, bool RE_E = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                                      const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                                      float4* __restrict__ ybuf, const float* __restrict__ consts,
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mp
     const float4 ps = Ps[tr.row];
     for (int base = tr.beg; base < tr.end; base += 32 * U) {
       EdgeLoad<U> L;
-      load_edges<U, SRC == 0, true, SRC == 1>(L, g, base, tr.end, lane, edge_attr, Pd, ybuf);
+      load_edges<U, SRC == 0 || RE_E, true, SRC == 1>(L, g, base, tr.end, lane, edge_attr, Pd, ybuf);
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         float ein[4], y[4];
@@ -477,6 +489,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mp
           bn3_relu(sc, ypv, ein);
         }
         edge_pre(sc, ps, L.pd[j], ein, y);
+        if (RE_E) {
+          float e0[4];
+          enc_full(sc, L.ea[j], e0);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) y[a] = fmaf(sc.v[FC_EDGE_WE0 + 4 * a + b], e0[b], y[a]);
+        }
         if (L.ok[j]) {
           if (WRITE_Y) ybuf[L.e[j]] = make_float4(y[0], y[1], y[2], y[3]);
 #pragma unroll
@@ -1079,7 +1099,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_task_kernel(const m
 __global__ void __launch_bounds__(128) graph_finalize_kernel(int stage, const mpn_graph g, const double* __restrict__ task_part,
                                                              const float* __restrict__ A, const float4* __restrict__ s1_task,
                                                              const float* __restrict__ small, double* __restrict__ sums_all,
-                                                             float* __restrict__ consts_all) {
+                                                             float* __restrict__ consts_all, int re_e) {
   __shared__ double red[4][64];
   const int gi = blockIdx.x;
   const int n0 = g.graph_nptr[gi], n1 = g.graph_nptr[gi + 1];
@@ -1128,6 +1148,7 @@ __global__ void __launch_bounds__(128) graph_finalize_kernel(int stage, const mp
   f.counter = nullptr;
   f.n_total_dev = nullptr;
   f.local_edges = 0.0;
+  f.re_e = re_e;
   finalize_body(f, 0, 1);
 }
 
@@ -1319,25 +1340,46 @@ __global__ void bn_relu_apply_kernel(const float* __restrict__ Y, long long tota
 // per-step node tables:  Ps = h·Ws^T + b_e, Pd = h·Wd^T, A = h·Wh^T + b_n
 // ------------------------------------------------------------------------------------------------
 constexpr int NT_NODES = 64, NT_THREADS = 256, NT_OUT = 40;
-__global__ void __launch_bounds__(NT_THREADS) node_tables_kernel(const float* __restrict__ h_full, int n_cols, int row_offset,
+// reattach_initial_nodes (RE_N): h_in = [h0 | h], so every table gets a second term with the weight columns of the initial
+// encoding h0 (MPN_W_EDGE_W0 / MPN_W_NODE_W0).  At step 1 h == h0: the kernel reads h for both and saves it as h0.
+template <bool RE_N>
+__global__ void __launch_bounds__(NT_THREADS) node_tables_kernel(const float* __restrict__ h_full, float* __restrict__ h0_full,
+                                                                 int first_step, int n_cols, int row_offset,
                                                                  int n_rows, const float* __restrict__ small,
                                                                  float* __restrict__ Ps, float* __restrict__ Pd,
                                                                  float* __restrict__ A) {
   __shared__ float hs[NT_NODES][33];
   __shared__ float ws[NT_OUT][33];
+  __shared__ float hs0[RE_N ? NT_NODES : 1][33];
+  __shared__ float ws0[RE_N ? NT_OUT : 1][33];
   __shared__ float bs[NT_OUT];
   const int n0 = blockIdx.x * NT_NODES;
   for (int i = threadIdx.x; i < NT_NODES * 32; i += NT_THREADS) {
     const int n = n0 + (i >> 5);
-    hs[i >> 5][i & 31] = (n < n_cols) ? h_full[(size_t)n * 32 + (i & 31)] : 0.f;
+    const float v = (n < n_cols) ? h_full[(size_t)n * 32 + (i & 31)] : 0.f;
+    hs[i >> 5][i & 31] = v;
+    if (RE_N) {
+      float v0 = v;
+      if (n < n_cols) {
+        if (first_step) h0_full[(size_t)n * 32 + (i & 31)] = v;
+        else v0 = h0_full[(size_t)n * 32 + (i & 31)];
+      }
+      hs0[i >> 5][i & 31] = v0;
+    }
   }
   for (int i = threadIdx.x; i < NT_OUT * 32; i += NT_THREADS) {
     const int o = i >> 5, c = i & 31;
-    float v;
+    float v, v0 = 0.f;
     if (o < 4) v = small[MPN_W_EDGE_W + o * 68 + c];                 // Ws: columns 0..31 of the 68-wide weight
     else if (o < 8) v = small[MPN_W_EDGE_W + (o - 4) * 68 + 32 + c]; // Wd: columns 32..63
     else v = small[MPN_W_NODE_W + (o - 8) * 36 + c];                 // Wh: columns 0..31 of the 36-wide weight
     ws[o][c] = v;
+    if (RE_N) {
+      if (o < 4) v0 = small[MPN_W_EDGE_W0 + o * 68 + c];
+      else if (o < 8) v0 = small[MPN_W_EDGE_W0 + (o - 4) * 68 + 32 + c];
+      else v0 = small[MPN_W_NODE_W0 + (o - 8) * 32 + c];
+      ws0[o][c] = v0;
+    }
   }
   if (threadIdx.x < NT_OUT) {
     const int o = threadIdx.x;
@@ -1349,6 +1391,10 @@ __global__ void __launch_bounds__(NT_THREADS) node_tables_kernel(const float* __
     const int n = n0 + ln;
     if (n >= n_cols) continue;
     float s = bs[o];
+    if (RE_N) {                                           // the reference's concat order: initial features first
+#pragma unroll
+      for (int c = 0; c < 32; ++c) s = fmaf(ws0[o][c], hs0[ln][c], s);
+    }
 #pragma unroll
     for (int c = 0; c < 32; ++c) s = fmaf(ws[o][c], hs[ln][c], s);
     const int lr = n - row_offset;
@@ -1420,7 +1466,7 @@ struct mpn_fwd_plan {
   long long total_edges;
   float *act0, *act1, *colscale, *colshift;
   double* colpart;
-  float *h_full, *Ps, *Pd, *A, *consts, *s1_task, *msg_task, *ybuf;
+  float *h_full, *h0_full, *Ps, *Pd, *A, *consts, *s1_task, *msg_task, *ybuf;
   double *partials, *partials2, *sums;
   unsigned int* fin_counter;
   unsigned int* col_counter;   // [max_dim/32 + 1] ticket counters of the column-statistics tiles
@@ -1467,6 +1513,7 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.colshift = a.take<float>(G * (max_dim > 0 ? max_dim : 1));
   p.colpart = a.take<double>((size_t)CS_ROWSPLIT_MAX * (max_dim > 0 ? max_dim : 1) * 2);
   p.h_full = a.take<float>((size_t)g.n_cols * MPN_DH);
+  p.h0_full = p.w.reattach_nodes ? a.take<float>((size_t)g.n_cols * MPN_DH) : nullptr;     // initial node encodings (reattach_initial_nodes)
   p.Ps = a.take<float>((size_t)g.n_nodes * 4);
   p.Pd = a.take<float>((size_t)g.n_cols * 4);
   p.A = a.take<float>((size_t)g.n_nodes * MPN_DH);
@@ -1560,6 +1607,7 @@ static FinArgs make_fin(const mpn_fwd_plan* p, int stage, bool fused) {
   f.counter = fused ? p->fin_counter : nullptr;
   f.n_total_dev = p->n_total_on_device ? p->n_total_dev : nullptr;
   f.local_edges = (double)p->g.n_edges;
+  f.re_e = p->w.reattach_edges ? (stores_y(*p) ? 2 : 1) : 0;
   return f;
 }
 
@@ -1661,9 +1709,12 @@ static int node_encoder_sharded(mpn_fwd_plan* p, const float* x, const PeerArgs&
 
 int mpn_plan_node_tables(mpn_fwd_plan* p, int32_t step, void* stream) {
   MPN_REQUIRE(p, "node_tables: NULL plan");
-  (void)step;
-  node_tables_kernel<<<div_up(p->g.n_cols, NT_NODES), NT_THREADS, 0, (cudaStream_t)stream>>>(
-      p->h_full, p->g.n_cols, p->g.row_offset, p->g.n_nodes, p->w.small, p->Ps, p->Pd, p->A);
+  if (p->w.reattach_nodes)
+    node_tables_kernel<true><<<div_up(p->g.n_cols, NT_NODES), NT_THREADS, 0, (cudaStream_t)stream>>>(
+        p->h_full, p->h0_full, step <= 1, p->g.n_cols, p->g.row_offset, p->g.n_nodes, p->w.small, p->Ps, p->Pd, p->A);
+  else
+    node_tables_kernel<false><<<div_up(p->g.n_cols, NT_NODES), NT_THREADS, 0, (cudaStream_t)stream>>>(
+        p->h_full, nullptr, step <= 1, p->g.n_cols, p->g.row_offset, p->g.n_nodes, p->w.small, p->Ps, p->Pd, p->A);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -1695,7 +1746,8 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
           if (stored) edge_moments_kernel<0, true, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
           else edge_moments_kernel<0, false, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, tp, make_fin(p, stage, false));
         } else {
-          edge_moments_kernel<1, true, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
+          if (p->w.reattach_edges) edge_moments_kernel<1, true, true, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
+          else edge_moments_kernel<1, true, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
         }
         break;
       case MPN_STAGE_NODE:
@@ -1719,7 +1771,8 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
     }
     MPN_LAUNCH_OK();
     if (stage != MPN_STAGE_APPLY) {
-      graph_finalize_kernel<<<p->n_graphs, 128, 0, st>>>(stage, g, tp, p->A, (const float4*)p->s1_task, p->w.small, p->sums, p->consts);
+      graph_finalize_kernel<<<p->n_graphs, 128, 0, st>>>(stage, g, tp, p->A, (const float4*)p->s1_task, p->w.small, p->sums, p->consts,
+                                                         p->w.reattach_edges ? (stored ? 2 : 1) : 0);
       MPN_LAUNCH_OK();
     }
     return MPN_OK;
@@ -1738,7 +1791,8 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
         if (stored) edge_moments_kernel<0, true, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
         else edge_moments_kernel<0, false, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, p->partials, make_fin(p, stage, fused));
       } else {
-        edge_moments_kernel<1, true, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
+        if (p->w.reattach_edges) edge_moments_kernel<1, true, false, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
+        else edge_moments_kernel<1, true, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
       }
       break;
     case MPN_STAGE_NODE:

@@ -187,8 +187,6 @@ class MOTMPNet(nn.Module):
 
         # ---- what the kernels support; checked once here so forward() fails early and loudly ----
         self._node_agg = {'sum': _lib.AGG_SUM, 'mean': _lib.AGG_MEAN, 'max': _lib.AGG_MAX}[agg.lower()]    # models/mpn.py:196-202
-        if self.reattach_initial_nodes or self.reattach_initial_edges:
-            raise _unsupported("reattach_initial_nodes/edges=True")
         if not (enc['edge_in_dim'] == 2 and list(enc['edge_fc_dims']) == [4] and enc['edge_out_dim'] == 4):
             raise _unsupported("an edge encoder other than 2->[4]->4")
         if enc['node_out_dim'] != _lib.MPN_DH or len(enc['node_fc_dims']) + 1 > _lib.MPN_MAX_NODE_LAYERS:
@@ -265,13 +263,30 @@ class MOTMPNet(nn.Module):
         put(_lib.W_ENC1_G, e.fc_layers[b1].weight); put(_lib.W_ENC1_BETA, e.fc_layers[b1].bias)
         put(_lib.W_ENC2_W, e.fc_layers[l2].weight); put(_lib.W_ENC2_B, e.fc_layers[l2].bias)
         put(_lib.W_ENC2_G, e.fc_layers[b2].weight); put(_lib.W_ENC2_BETA, e.fc_layers[b2].bias)
+        # MPNet weights.  With reattach_initial_nodes / _edges (models/mpn.py:207-215, 283-287) the inputs are
+        # [h0_row | h_row | h0_col | h_col | e0 | e] (edge MLP) and [h0_row | h_row | e'] (node MLP), initial encodings first:
+        # the columns of the current features go to the [4,68] / [32,36] blocks, those of the initial encodings to the *_W0 blocks.
+        re_n, re_e = bool(self.reattach_initial_nodes), bool(self.reattach_initial_edges)
+        W.reattach_nodes, W.reattach_edges = int(re_n), int(re_e)
+        D, De = _lib.MPN_DH, 4
         m = self.MPNet.edge_model.edge_mlp
         (l, b), = m.blocks
-        put(_lib.W_EDGE_W, m.fc_layers[l].weight); put(_lib.W_EDGE_B, m.fc_layers[l].bias)
+        we = m.fc_layers[l].weight.detach()
+        nb = 2 if re_n else 1
+        h_row, h_col = we[:, (nb - 1) * D:nb * D], we[:, (2 * nb - 1) * D:2 * nb * D]
+        e_cur = we[:, 2 * nb * D + (De if re_e else 0):2 * nb * D + (2 * De if re_e else De)]
+        put(_lib.W_EDGE_W, torch.cat([h_row, h_col, e_cur], dim=1).contiguous())
+        zeros_d, zeros_e = we.new_zeros(we.shape[0], D), we.new_zeros(we.shape[0], De)
+        put(_lib.W_EDGE_W0, torch.cat([we[:, 0:D] if re_n else zeros_d, we[:, 2 * D:3 * D] if re_n else zeros_d,
+                                       we[:, 2 * nb * D:2 * nb * D + De] if re_e else zeros_e], dim=1).contiguous())
+        put(_lib.W_EDGE_B, m.fc_layers[l].bias)
         put(_lib.W_EDGE_G, m.fc_layers[b].weight); put(_lib.W_EDGE_BETA, m.fc_layers[b].bias)
         m = self.MPNet.node_model.node_mlp
         (l, b), = m.blocks
-        put(_lib.W_NODE_W, m.fc_layers[l].weight); put(_lib.W_NODE_B, m.fc_layers[l].bias)
+        wn = m.fc_layers[l].weight.detach()
+        put(_lib.W_NODE_W, torch.cat([wn[:, (nb - 1) * D:nb * D], wn[:, nb * D:nb * D + De]], dim=1).contiguous())
+        put(_lib.W_NODE_W0, (wn[:, 0:D] if re_n else wn.new_zeros(wn.shape[0], D)).contiguous())
+        put(_lib.W_NODE_B, m.fc_layers[l].bias)
         put(_lib.W_NODE_G, m.fc_layers[b].weight); put(_lib.W_NODE_BETA, m.fc_layers[b].bias)
         c = self.classifier.edge_mlp
         (l, _), = c.blocks

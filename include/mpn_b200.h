@@ -137,7 +137,13 @@ enum {                                   /* offsets (in floats) inside mpn_weigh
   MPN_W_NODE_BETA = 1548,
   MPN_W_CLS_W = 1580,                    /* classifier.edge_mlp.fc_layers.0.weight [2,4] */
   MPN_W_CLS_B = 1588,
-  MPN_W_SMALL_FLOATS = 1592
+  /* reattach_initial_nodes / reattach_initial_edges (models/mpn.py:207-215, 283-287): the columns of the two MPNet weights
+   * that multiply the INITIAL encodings, split off by the host; all zero when the option is off.
+   *   EDGE_W0 [4,68]  = [h0_row | h0_col | e0]   (the [4,68] block above then holds [h_row | h_col | e])
+   *   NODE_W0 [32,32] = [h0_row]                 (the [32,36] block above holds [h_row | e]) */
+  MPN_W_EDGE_W0 = 1592,
+  MPN_W_NODE_W0 = 1864,
+  MPN_W_SMALL_FLOATS = 2888
 };
 
 typedef struct mpn_weights {
@@ -160,6 +166,8 @@ typedef struct mpn_weights {
   float node_bn_bmax[MPN_MAX_NODE_LAYERS];
   /* node aggregation of the messages (models/mpn.py:193-202): scatter_add / scatter_mean / scatter_max over row */
   int32_t node_agg;                               /* MPN_AGG_SUM (shipped config) | MPN_AGG_MEAN | MPN_AGG_MAX */
+  int32_t reattach_nodes;                         /* reattach_initial_nodes: h_in = [h0 | h] before every step */
+  int32_t reattach_edges;                         /* reattach_initial_edges: e_in = [e0 | e] before every step */
   int32_t reserved;
 } mpn_weights;
 enum { MPN_AGG_SUM = 0, MPN_AGG_MEAN = 1, MPN_AGG_MAX = 2 };

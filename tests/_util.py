@@ -34,6 +34,8 @@ def load_mpn_case(path):
     fcd = tuple(int(v) for v in g["fc_dims"])
     params = mo.shipped_model_params(L, n_cls, din, fcd)
     params["node_agg_fn"] = agg
+    if len(spec) > 11:
+        params["reattach_initial_nodes"], params["reattach_initial_edges"] = bool(spec[11]), bool(spec[12])
     x, edge_index, cam, _ = mo.synth_graph(N, C, gseed, D=din, planted=bool(planted))
     if thin:
         edge_index = mo.thin_edges(edge_index, gseed)

@@ -18,8 +18,9 @@ import gcn_mtmc_b200 as m                      # noqa: E402
 from oracle import mpn_oracle as mo            # noqa: E402
 
 
-def check_case(rank, world, dev, L, n_cls, N, C, modes, chunk=None):
+def check_case(rank, world, dev, L, n_cls, N, C, modes, chunk=None, reattach=False):
     params = mo.shipped_model_params(L, n_cls, 128, (96, 64))
+    params["reattach_initial_nodes"] = params["reattach_initial_edges"] = reattach
     x, ei, cam, _ = mo.synth_graph(N, C, 3, D=128, planted=True)
     sd = mo.init_weights(params, "resnet101", 2)
     ea = mo.edge_features(x, ei)
@@ -68,8 +69,9 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
     worst, modes = 0.0, set()
-    for (L, n_cls, N, C, chunk) in [(1, 1, 240, 4, None), (4, 2, 200, 5, None), (2, 1, 600, 3, 128), (1, 1, 600, 3, 256)]:
-        worst = max(worst, check_case(rank, world, dev, L, n_cls, N, C, modes, chunk))
+    for (L, n_cls, N, C, chunk, reattach) in [(1, 1, 240, 4, None, False), (4, 2, 200, 5, None, False), (2, 1, 600, 3, 128, False),
+                                              (1, 1, 600, 3, 256, False), (3, 1, 600, 3, 128, True)]:
+        worst = max(worst, check_case(rank, world, dev, L, n_cls, N, C, modes, chunk, reattach))
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

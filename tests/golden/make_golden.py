@@ -36,6 +36,11 @@ MPN_CASES = {
     "mpn_small_L2_mean": (44, 4, 16, 6, 2, 2, 64, (48, 40), True, True, "mean", True),
     "mpn_small_L3_max": (44, 4, 17, 7, 3, 1, 64, (48, 40), True, True, "max", True),
     "mpn_shipped_L1_max": (40, 4, 18, 8, 1, 1, 2048, (1024, 512, 128), False, True, "max", False),
+    # reattach_initial_nodes / reattach_initial_edges (models/mpn.py:207-215, 283-287): (..., agg, thin, re_n, re_e)
+    "mpn_small_L3_reattach_both": (44, 4, 19, 9, 3, 2, 64, (48, 40), True, True, "sum", False, True, True),
+    "mpn_small_L2_reattach_nodes": (40, 4, 20, 10, 2, 1, 64, (48, 40), True, True, "sum", True, True, False),
+    "mpn_small_L3_reattach_edges": (40, 4, 21, 11, 3, 3, 64, (48, 40), True, True, "mean", False, False, True),
+    "mpn_shipped_L1_reattach_both": (36, 4, 22, 12, 1, 1, 2048, (1024, 512, 128), False, True, "sum", False, True, True),
 }
 AGG_CODE = {"sum": 0, "mean": 1, "max": 2}
 
@@ -53,8 +58,10 @@ POST_CASES = {
 def run_mpn_case(MOTMPNet, name, spec):
     N, C, gseed, wseed, L, n_cls, din, fcd, planted, jitter = spec[:10]
     agg, thin = (spec[10], spec[11]) if len(spec) > 10 else ("sum", False)
+    re_n, re_e = (spec[12], spec[13]) if len(spec) > 12 else (False, False)
     params = mo.shipped_model_params(L, n_cls, din, fcd)
     params["node_agg_fn"] = agg
+    params["reattach_initial_nodes"], params["reattach_initial_edges"] = re_n, re_e
     x, edge_index, cam, ident = mo.synth_graph(N, C, gseed, D=din, planted=planted)
     if thin:
         edge_index = mo.thin_edges(edge_index, gseed)
@@ -81,7 +88,8 @@ def run_mpn_case(MOTMPNet, name, spec):
         out64, h64 = m64(Data(x=x.double(), edge_index=edge_index, edge_attr=edge_attr.double()))
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),
-        spec=np.array([N, C, gseed, wseed, L, n_cls, din, int(planted), int(jitter), AGG_CODE[agg], int(thin)], dtype=np.int64),
+        spec=np.array([N, C, gseed, wseed, L, n_cls, din, int(planted), int(jitter), AGG_CODE[agg], int(thin), int(re_n), int(re_e)],
+                      dtype=np.int64),
         fc_dims=np.array(fcd, dtype=np.int64),
         x_checksum=np.array([x.double().sum().item(), x.double().abs().sum().item()]),
         w_checksum=np.array([sum(v.double().sum().item() for v in sd.values())]),

@@ -316,6 +316,28 @@ def test_forward_tensor_core_apply_vs_fp64_oracle(m, L, n_cls, chunk, fuse, agg)
             assert (net.last_prob1.cpu().double() - prob_ref).abs().max().item() <= 5e-6
 
 
+@pytest.mark.parametrize("re_n,re_e,L,n_cls,chunk,agg", [(True, True, 3, 2, 128, "sum"), (True, False, 2, 1, 128, "sum"),
+                                                         (False, True, 3, 1, 256, "max"), (True, True, 1, 1, 128, "sum"),
+                                                         (True, True, 4, 4, 32, "mean"), (False, True, 2, 2, None, "sum")])
+def test_forward_reattach_initial_features(m, re_n, re_e, L, n_cls, chunk, agg):
+    """reattach_initial_nodes / reattach_initial_edges (models/mpn.py:207-215, 283-287): [h0 | h] and [e0 | e] before every
+    step, on the packed-fp32 (chunk < 128) and the tensor-core sweeps, against the fp64 oracle."""
+    params = mo.shipped_model_params(L, n_cls, 64, (48, 40))
+    params["reattach_initial_nodes"], params["reattach_initial_edges"], params["node_agg_fn"] = re_n, re_e, agg
+    x, ei, cam, _ = mo.synth_graph(600, 3, 8, D=64, planted=True)
+    sd = mo.init_weights(params, "resnet101", 13, affine_jitter=True)
+    assert sd["MPNet.edge_model.edge_mlp.fc_layers.0.weight"].shape[1] == (2 if re_n else 1) * 64 + (2 if re_e else 1) * 4
+    ea = mo.edge_features(x, ei)
+    ref, href = mo.mpn_forward(sd, params, "resnet101", x, ei, ea, dtype=torch.float64)
+    outs, h, net = run_forward(m, params, sd, x, ei, ea, fuse=True, chunk=chunk)
+    assert len(outs) == n_cls
+    for o, r in zip(outs, ref):
+        assert (o.cpu().double() - r).abs().max().item() <= 1e-4 * r.abs().max().item()
+    assert (h.cpu().double() - href).abs().max().item() <= 1e-4 * max(1.0, href.abs().max().item())
+    margin = (ref[-1][:, 1] - ref[-1][:, 0]).abs()
+    assert not bool(((net.last_pred.cpu() != (ref[-1][:, 1] > ref[-1][:, 0]).to(torch.uint8)) & (margin > 1e-4)).any())
+
+
 class _NoComm:
     world, rank = 1, 0
 
@@ -382,11 +404,13 @@ def test_batched_edge_features_block_diagonal(m, D, tc):
     assert np.allclose(out, ref, rtol=1e-5, atol=2e-6)
 
 
-@pytest.mark.parametrize("L,n_cls,agg", [(1, 1, "sum"), (3, 2, "sum"), (2, 1, "max"), (2, 1, "mean")])
-def test_batched_graphs_per_graph_batchnorm(m, L, n_cls, agg):
+@pytest.mark.parametrize("L,n_cls,agg,reattach", [(1, 1, "sum", False), (3, 2, "sum", False), (2, 1, "max", False), (2, 1, "mean", False),
+                                                  (3, 1, "sum", True)])
+def test_batched_graphs_per_graph_batchnorm(m, L, n_cls, agg, reattach):
     """BASELINE configs[2]: many small graphs in one launch; statistics per graph == one reference forward per graph."""
     params = mo.shipped_model_params(L, n_cls, 64, (48, 40))
     params["node_agg_fn"] = agg
+    params["reattach_initial_nodes"] = params["reattach_initial_edges"] = reattach
     sd = mo.init_weights(params, "resnet101", 17)
     sizes, cams = [40, 64, 30, 90, 52, 36], [4, 4, 3, 5, 4, 2]
     x, ei, ptr, xs, eis = _packed_batch(sizes, cams, 64, 300)

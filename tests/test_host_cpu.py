@@ -61,8 +61,15 @@ def test_unsupported_configs_raise():
         p = mo.shipped_model_params()
         p["node_agg_fn"] = agg
         assert m.MOTMPNet(p, None, "resnet101")._node_agg == {"sum": 0, "mean": 1, "max": 2}[agg]
+    for re_n, re_e, edge_in, node_in in [(True, False, 132, 68), (False, True, 72, 36), (True, True, 136, 68)]:
+        p = mo.shipped_model_params()                 # reattach_initial_* (models/mpn.py:207-215): the MLP input widths follow
+        p["reattach_initial_nodes"], p["reattach_initial_edges"] = re_n, re_e
+        net = m.MOTMPNet(p, None, "resnet101")
+        sd = net.state_dict()
+        assert sd["MPNet.edge_model.edge_mlp.fc_layers.0.weight"].shape == (4, edge_in)
+        assert sd["MPNet.node_model.node_mlp.fc_layers.0.weight"].shape == (32, node_in)
     p = mo.shipped_model_params()
-    p["reattach_initial_edges"] = True
+    p["edge_model_feats_dict"]["fc_dims"] = [8]
     with pytest.raises(NotImplementedError):
         m.MOTMPNet(p, None, "resnet101")
 
