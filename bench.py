@@ -23,9 +23,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# stdout carries exactly one JSON line: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints a "NCCL version ..." banner through C stdio when
+# the first communicator is created), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a
+# private duplicate of the original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 import torch  # noqa: E402
 
@@ -216,7 +223,7 @@ def run_reference_arm(args):
             "config": {"workload": "L=1 MPN + edge features, %d tracklets x %d cameras (bounded CPU sample of configs[1])" % (2048, 8)},
             "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -284,6 +291,41 @@ def time_phases(m, net, x, ei, reps=5):
             t_gemm += a.elapsed_time(b) / reps
     acc["gram_gemm"] = t_gemm
     return acc
+
+
+def s02_latency(m, dev, reps=200):
+    """Second half of BASELINE.json's metric: p50 latency of one S02-shaped graph (configs[0]: N=300, C=4, E=67,500, L=1):
+    graph tables + edge features + forward + fused decisions, device time per call (CUDA events), host wall clock beside it."""
+    net = make_model(dev)
+    x, ei = device_graph(300, 4, 0, dev)
+    b = Batch()
+    b.x, b.edge_index, b.num_nodes = x, ei, 300
+
+    def call():
+        g = m.TrackletGraph(ei, 300, validate="deferred")
+        b._mpn_b200_graph = ((ei.data_ptr(), tuple(ei.shape), ei._version, 300, None), g)
+        b.edge_attr = m.edge_features(x, ei, graph=g)
+        net(b)
+        g.validate()
+        return net.last_pred
+    for _ in range(20):
+        call()
+    dts, hts = [], []
+    for _ in range(reps):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a.record()
+        call()
+        e.record()
+        e.synchronize()
+        hts.append(1e3 * (time.perf_counter() - t0))
+        dts.append(a.elapsed_time(e))
+    dts.sort()
+    hts.sort()
+    return {"config": "BASELINE configs[0] shape: 300 tracklets, 4 cameras, E=%d directed edges, L=1; K0 + K1 + forward + decisions per call "
+                      "(forward replayed as one CUDA graph)" % ei.shape[1],
+            "p50_ms": dts[len(dts) // 2], "p99_ms": dts[int(len(dts) * 0.99)], "host_wall_p50_ms": hts[len(hts) // 2], "calls": reps}
 
 
 def run_ours(args):
@@ -468,9 +510,10 @@ def run_ours(args):
                                 traffic_source=traffic.get("_source"))
         line["roofline_all"] = roof
         line["phase_ms"] = ph
+        line["s02_latency"] = s02_latency(m, dev)
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(reps=1).items()}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
