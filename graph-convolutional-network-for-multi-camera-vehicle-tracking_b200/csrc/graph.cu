@@ -191,18 +191,22 @@ __global__ void __launch_bounds__(256) cross_camera_kernel(const CamLayout L, in
     const long long deg = n_total - (L.ptr[k + 1] - L.ptr[k]);
     rowptr[lr] = (int)(L.ebase[k] + (r - L.ptr[k]) * deg - gbase);
   }
-  for (long long le = tid; le < E; le += stride) {
-    const long long e = le + gbase;
+  // one warp per local row: its columns are 0..n_total-1 without the row's own camera block, written in order (coalesced,
+  // no per-edge division)
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = tid >> 5, nwarps = stride >> 5;
+  for (long long lr = warp0; lr < n_rows; lr += nwarps) {
+    const long long r = row0 + lr;
     int k = 0;
-    while (k + 1 < L.n_cams && e >= L.ebase[k + 1]) ++k;
+    while (k + 1 < L.n_cams && r >= L.ptr[k + 1]) ++k;
     const int lo = L.ptr[k], nk = L.ptr[k + 1] - lo;
-    const long long deg = n_total - nk;
-    const long long off = e - L.ebase[k];
-    const int row = lo + (int)(off / deg);
-    const int idx = (int)(off % deg);
-    const int c = idx < lo ? idx : idx + nk;
-    col32[le] = c;
-    if (edge_index_out) { edge_index_out[le] = row; edge_index_out[E + le] = c; }
+    const int deg = n_total - nk;
+    const long long le0 = L.ebase[k] + (r - lo) * (long long)deg - gbase;
+    for (int idx = lane; idx < deg; idx += 32) {
+      const int c = idx < lo ? idx : idx + nk;
+      col32[le0 + idx] = c;
+      if (edge_index_out) { edge_index_out[le0 + idx] = r; edge_index_out[E + le0 + idx] = c; }
+    }
   }
 }
 

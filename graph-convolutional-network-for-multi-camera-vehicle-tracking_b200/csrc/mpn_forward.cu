@@ -849,6 +849,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
+// shared-memory accesses through explicit 32-bit addresses that the compiler must keep in registers (opaque): ptxas otherwise
+// rebuilds every tile / ring address from threadIdx in each iteration of the batch loop (~15 instructions per batch)
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 template <bool CLASSIFY, bool DECIDE, bool AGGMAX>
 __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
     const mpn_graph g, const float4* __restrict__ ybuf, const float* __restrict__ A, const float* __restrict__ consts,
@@ -892,10 +907,11 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
   const uint64_t d_w1 = make_smem_desc_noswizzle(smem_u32(w1), 128, 256), d_w2 = make_smem_desc_noswizzle(smem_u32(w2), 128, 256);
   const uint64_t d_e1 = make_smem_desc_noswizzle(smem_u32(e1[0]), 128, 256), d_e2 = make_smem_desc_noswizzle(smem_u32(e2[0]), 128, 256);
   constexpr uint64_t BUF_STEP = (128 * 8 * sizeof(float)) >> 4;          // second operand buffer, in descriptor address units
-  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
-  float* const e1_mine = &e1[0][tile_off(tid, 0)];                       // K-core 1 of the same row: + 32 floats
-  float* const e2_mine = &e2[0][tile_off(tid, 0)];
-  unsigned char* const ring_mine = reinterpret_cast<unsigned char*>(&ring[0][tid]);
+  const uint32_t my_tmem = opaque_u32(tmem + ((uint32_t)(warp * 32) << 16));
+  const uint32_t e1_addr = opaque_u32(smem_u32(&e1[0][tile_off(tid, 0)]));     // K-core 1 of the same row: + 128 bytes
+  const uint32_t e2_addr = opaque_u32(smem_u32(&e2[0][tile_off(tid, 0)]));
+  const uint32_t ring_addr = opaque_u32(smem_u32(&ring[0][tid]));
+  constexpr uint32_t TILE_BYTES = 128 * 8 * sizeof(float);
   *reinterpret_cast<float4*>(&e2[0][tile_off(tid, 1)]) = make_float4(1.f, 1.f, 0.f, 0.f);     // the two "1" columns never change
   *reinterpret_cast<float4*>(&e2[1][tile_off(tid, 1)]) = make_float4(1.f, 1.f, 0.f, 0.f);
   uint32_t phase = 0;
@@ -919,7 +935,7 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
     int st_ti = 0, st_pos = s_beg[0], st_end = s_end[0], st_off = 0;
     auto issue_stream = [&]() {
       if (st_ti < ns) {
-        cp_async<16>(ring_mine + st_off, ybuf + min(st_pos + tid, st_end - 1));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring_addr + (uint32_t)st_off), "l"(ybuf + min(st_pos + tid, st_end - 1)) : "memory");
         st_pos += ATC_THREADS;
         if (st_pos >= st_end) {
           ++st_ti;
@@ -970,7 +986,7 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
       if (ti + 1 < ns) a_next = __ldg(A + (size_t)s_row[ti + 1] * MPN_DH + lane);
       for (int pos = t_beg; pos < t_end; pos += ATC_THREADS) {
         cp_async_wait<ATC_D - 1>();                      // this batch's y has landed
-        const float4 yv = *reinterpret_cast<const float4*>(ring_mine + c_off);
+        const float4 yv = lds128(ring_addr + (uint32_t)c_off);
         c_off = (c_off == (ATC_RL - 1) * ATC_SLOT_BYTES) ? 0 : c_off + ATC_SLOT_BYTES;
         issue_stream();
         const int e = pos + tid;
@@ -996,11 +1012,10 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
         float eh[4], el[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) split_tf32(ep[k], eh[k], el[k]);
-        const float4 hi4 = make_float4(eh[0], eh[1], eh[2], eh[3]);
-        float* const t1 = e1_mine + buf * (128 * 8);
-        *reinterpret_cast<float4*>(t1) = hi4;
-        *reinterpret_cast<float4*>(t1 + 32) = make_float4(el[0], el[1], el[2], el[3]);
-        *reinterpret_cast<float4*>(e2_mine + buf * (128 * 8)) = hi4;
+        const uint32_t boff = (uint32_t)buf * TILE_BYTES;
+        sts128(e1_addr + boff, eh[0], eh[1], eh[2], eh[3]);
+        sts128(e1_addr + boff + 128, el[0], el[1], el[2], el[3]);
+        sts128(e2_addr + boff, eh[0], eh[1], eh[2], eh[3]);
         if (pending) drain(ok_prev);                     // batch k-1 finished while batch k was being prepared
         ok_prev = ok;
         const bool first_batch = pos == t_beg;
