@@ -284,7 +284,7 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
     MPN_LAUNCH_OK();
     if (use_tc && gemm_tc_supported(g->n_cols, 64, D) && g->n_graphs <= 65535) {
       MPN_TRY(gram_blockdiag_tc(L.xc, g->n_cols, D, g->graph_nptr, L.g_off, g->n_graphs, g->max_graph_nodes, L.G, L.gemm_ws,
-                                L.gemm_ws_bytes, st));
+                                L.gemm_ws_bytes, st, (const float*)L.amax_bits));
     } else {
       gram_blockdiag_simt_kernel<<<kNumSMs * 8, 256, 0, st>>>(L.xc, g->n_cols, D, g->node_gid, g->graph_nptr, L.g_off, L.G);
       MPN_LAUNCH_OK();

@@ -525,12 +525,23 @@ int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const 
 // Block-diagonal Gram matrix of a batch of graphs: for graph i with rows [nptr[i], nptr[i+1]) the ng x ng block
 // X_i X_i^T is written (row-major, ld = ng) at Gbuf + g_off[i].  Symmetric tiles only.
 int gram_blockdiag_tc(const float* X, int N, int K, const int* graph_nptr, const long long* g_off, int n_graphs, int max_ng,
-                      float* Gbuf, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      float* Gbuf, void* ws, size_t ws_bytes, cudaStream_t st, const float* amax_dev) {
   MPN_REQUIRE(gemm_tc_supported(N, 64, K), "block-diagonal tcgen05 Gram: unsupported K=%d", K);
   MPN_REQUIRE(n_graphs >= 1 && n_graphs <= 65535, "block-diagonal Gram: at most 65535 graphs per launch");
   const size_t plane = (((size_t)N * K * sizeof(float)) + 255) & ~(size_t)255;
   MPN_REQUIRE(ws && ws_bytes >= 2 * plane + 256, "block-diagonal Gram: workspace too small");
   char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  if (gram_f16_enabled() && amax_dev != nullptr && (K % 8) == 0) {     // 3xFP16 planes (see gram_nt_tc)
+    const size_t plane16 = (((size_t)N * K * sizeof(__half)) + 255) & ~(size_t)255;
+    __half *hi16 = (__half*)w, *lo16 = (__half*)(w + plane16);
+    float* out_scale = (float*)(w + 2 * plane16);
+    split_f16_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi16, (uint2*)lo16, out_scale);
+    MPN_LAUNCH_OK();
+    CUtensorMap mh16, ml16;
+    MPN_TRY(make_map(&mh16, hi16, N, K, TC_BM, true));
+    MPN_TRY(make_map(&ml16, lo16, N, K, TC_BM, true));
+    return launch_tc<128, true, true>(mh16, ml16, mh16, ml16, nullptr, Gbuf, N, N, K, st, graph_nptr, g_off, n_graphs, max_ng, out_scale);
+  }
   float *hi = (float*)w, *lo = (float*)(w + plane);
   split_tf32_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)X, (long long)N * K / 4, K, nullptr, nullptr, nullptr, (float4*)hi, (float4*)lo);
   MPN_LAUNCH_OK();

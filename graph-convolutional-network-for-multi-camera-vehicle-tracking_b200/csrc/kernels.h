@@ -30,6 +30,6 @@ int gemm_nt_tc_f16(const float* A, const float* bias, float* C, int M, int N, in
                    const void* b_hi16, const void* b_lo16, float b_scale);
 int split_f16_host_scale(const float* x, long long n, float amax, void* hi, void* lo, float* scale_out, cudaStream_t st);
 int gram_blockdiag_tc(const float* X, int N, int K, const int* graph_nptr, const long long* g_off, int n_graphs, int max_ng,
-                      float* Gbuf, void* ws, size_t ws_bytes, cudaStream_t st);
+                      float* Gbuf, void* ws, size_t ws_bytes, cudaStream_t st, const float* amax_dev = nullptr);
 
 }  // namespace mpn

@@ -816,9 +816,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph
 // map, fixed shuffle tree, fixed task order).
 // ------------------------------------------------------------------------------------------------
 constexpr int ATC_THREADS = 128;
-constexpr int ATC_CTAS_PER_SM = 5;
-constexpr int ATC_SEG = 256;                             // task ranges staged in shared memory per segment
-constexpr int ATC_D = 8;                                 // y runs D batches ahead
+constexpr int ATC_CTAS_PER_SM = 4;
+constexpr int ATC_SEG = 128;                             // task ranges staged in shared memory per segment
+constexpr int ATC_NB = 2;                                // 128-edge batches per iteration (one barrier / fence / commit for both)
+constexpr int ATC_D = 4;                                 // y runs D batches ahead
 constexpr int ATC_RL = ATC_D + 1;                        // ring slots
 constexpr int ATC_SLOT_BYTES = 128 * 16;
 // canonical K-major no-swizzle operand tile: [rows/8 groups][2 K-cores][8 rows][4 floats]
@@ -869,8 +870,8 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
     const mpn_graph g, const float4* __restrict__ ybuf, const float* __restrict__ A, const float* __restrict__ consts,
     float* __restrict__ msg_task, float2* __restrict__ logits, uint8_t* __restrict__ pred, float* __restrict__ prob1) {
   __shared__ EdgeConsts sc;
-  __shared__ __align__(128) float e1[2][128 * 8];
-  __shared__ __align__(128) float e2[2][128 * 8];
+  __shared__ __align__(128) float e1[2 * ATC_NB][128 * 8];            // [buffer][half]
+  __shared__ __align__(128) float e2[2 * ATC_NB][128 * 8];
   __shared__ __align__(128) float w1[32 * 8];
   __shared__ __align__(128) float w2[32 * 8];
   __shared__ __align__(16) float4 ring[ATC_RL][ATC_THREADS];
@@ -880,7 +881,7 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
   __shared__ uint32_t tmem_slot;
   load_consts(sc, consts);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (warp == 0) tmem_alloc(&tmem_slot, 32);
+  if (warp == 0) tmem_alloc(&tmem_slot, 32 * ATC_NB);
   if (tid == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -912,8 +913,9 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
   const uint32_t e2_addr = opaque_u32(smem_u32(&e2[0][tile_off(tid, 0)]));
   const uint32_t ring_addr = opaque_u32(smem_u32(&ring[0][tid]));
   constexpr uint32_t TILE_BYTES = 128 * 8 * sizeof(float);
-  *reinterpret_cast<float4*>(&e2[0][tile_off(tid, 1)]) = make_float4(1.f, 1.f, 0.f, 0.f);     // the two "1" columns never change
-  *reinterpret_cast<float4*>(&e2[1][tile_off(tid, 1)]) = make_float4(1.f, 1.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 2 * ATC_NB; ++i)                   // the two "1" columns never change
+    *reinterpret_cast<float4*>(&e2[i][tile_off(tid, 1)]) = make_float4(1.f, 1.f, 0.f, 0.f);
   uint32_t phase = 0;
   const int n_tasks = *g.n_tasks;
   const int per = (n_tasks + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -950,20 +952,27 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-    bool pending = false;                                // an MMA is in flight whose result has not been accumulated
+    int pending = 0;                                     // batches of the MMA group in flight whose result has not been accumulated
     int run_first = 0;                                   // first task (segment index) of the current run of one row
     int c_off = 0, buf = 0;
-    bool ok_prev = false;
+    bool ok_prev[ATC_NB];
+#pragma unroll
+    for (int h = 0; h < ATC_NB; ++h) ok_prev[h] = false;
     float a_next = __ldg(A + (size_t)s_row[0] * MPN_DH + lane);
-    auto drain = [&](bool live) {                        // accumulate the finished batch (live: this lane's edge was real)
+    auto drain = [&]() {                                 // accumulate the finished batches (only lanes whose edge was real)
       mbar_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
-      float v[32];
-      tmem_ld32(my_tmem, v);
-      if (live) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = AGGMAX ? fmaxf(acc[c], v[c]) : acc[c] + fabsf(v[c]);   // max relu(z) = max(0, max z)
+      for (int h = 0; h < ATC_NB; ++h) {
+        if (h < pending) {
+          float v[32];
+          tmem_ld32(my_tmem + 32 * h, v);
+          if (ok_prev[h]) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = AGGMAX ? fmaxf(acc[c], v[c]) : acc[c] + fabsf(v[c]);   // max relu(z) = max(0, max z)
+          }
+        }
       }
       tc_fence_before();
     };
@@ -984,40 +993,49 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
       const bool new_run = ti == 0 || row != s_row[ti - 1];
       const float a_cur = a_next;
       if (ti + 1 < ns) a_next = __ldg(A + (size_t)s_row[ti + 1] * MPN_DH + lane);
-      for (int pos = t_beg; pos < t_end; pos += ATC_THREADS) {
-        cp_async_wait<ATC_D - 1>();                      // this batch's y has landed
-        const float4 yv = lds128(ring_addr + (uint32_t)c_off);
-        c_off = (c_off == (ATC_RL - 1) * ATC_SLOT_BYTES) ? 0 : c_off + ATC_SLOT_BYTES;
-        issue_stream();
-        const int e = pos + tid;
-        const bool ok = e < t_end;                       // a masked lane computes on a clamped edge; its TMEM row is never added
-        float ep[4];
-        ep[0] = fmaxf(fmaf(s3[0], yv.x, t3[0]), 0.f);
-        ep[1] = fmaxf(fmaf(s3[1], yv.y, t3[1]), 0.f);
-        ep[2] = fmaxf(fmaf(s3[2], yv.z, t3[2]), 0.f);
-        ep[3] = fmaxf(fmaf(s3[3], yv.w, t3[3]), 0.f);
-        if (CLASSIFY && ok) {
-          float l0 = sc.v[FC_CLS_B + 0], l1 = sc.v[FC_CLS_B + 1];
+      for (int pos = t_beg; pos < t_end; pos += ATC_NB * ATC_THREADS) {
+        const int nb = (pos + ATC_THREADS < t_end) ? ATC_NB : 1;      // batches of this iteration (block-uniform)
+        bool ok[ATC_NB];
+        float ep[ATC_NB][4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            l0 = fmaf(sc.v[FC_CLS_W + k], ep[k], l0);
-            l1 = fmaf(sc.v[FC_CLS_W + 4 + k], ep[k], l1);
-          }
-          logits[e] = make_float2(l0, l1);
-          if (DECIDE) {
-            pred[e] = (l1 > l0) ? 1 : 0;                                          // argmax, tie -> class 0 (inference.py:479)
-            prob1[e] = rcp_approx(1.0f + ex2_approx((l0 - l1) * 1.4426950408889634f));   // softmax(.)[1] (inference.py:475-477)
+        for (int h = 0; h < ATC_NB; ++h) {
+          ok[h] = false;
+          if (h < nb) {
+            cp_async_wait<ATC_D - 1>();                  // this batch's y has landed
+            const float4 yv = lds128(ring_addr + (uint32_t)c_off);
+            c_off = (c_off == (ATC_RL - 1) * ATC_SLOT_BYTES) ? 0 : c_off + ATC_SLOT_BYTES;
+            issue_stream();
+            const int e = pos + h * ATC_THREADS + tid;
+            ok[h] = e < t_end;                           // a masked lane computes on a clamped edge; its TMEM row is never added
+            ep[h][0] = fmaxf(fmaf(s3[0], yv.x, t3[0]), 0.f);
+            ep[h][1] = fmaxf(fmaf(s3[1], yv.y, t3[1]), 0.f);
+            ep[h][2] = fmaxf(fmaf(s3[2], yv.z, t3[2]), 0.f);
+            ep[h][3] = fmaxf(fmaf(s3[3], yv.w, t3[3]), 0.f);
+            if (CLASSIFY && ok[h]) {
+              float l0 = sc.v[FC_CLS_B + 0], l1 = sc.v[FC_CLS_B + 1];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                l0 = fmaf(sc.v[FC_CLS_W + k], ep[h][k], l0);
+                l1 = fmaf(sc.v[FC_CLS_W + 4 + k], ep[h][k], l1);
+              }
+              logits[e] = make_float2(l0, l1);
+              if (DECIDE) {
+                pred[e] = (l1 > l0) ? 1 : 0;                                      // argmax, tie -> class 0 (inference.py:479)
+                prob1[e] = rcp_approx(1.0f + ex2_approx((l0 - l1) * 1.4426950408889634f));   // softmax(.)[1] (inference.py:475-477)
+              }
+            }
+            float eh[4], el[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_tf32(ep[h][k], eh[k], el[k]);
+            const uint32_t boff = (uint32_t)(buf * ATC_NB + h) * TILE_BYTES;
+            sts128(e1_addr + boff, eh[0], eh[1], eh[2], eh[3]);
+            sts128(e1_addr + boff + 128, el[0], el[1], el[2], el[3]);
+            sts128(e2_addr + boff, eh[0], eh[1], eh[2], eh[3]);
           }
         }
-        float eh[4], el[4];
+        if (pending) drain();                            // the previous iteration's MMAs finished while this one was being prepared
 #pragma unroll
-        for (int k = 0; k < 4; ++k) split_tf32(ep[k], eh[k], el[k]);
-        const uint32_t boff = (uint32_t)buf * TILE_BYTES;
-        sts128(e1_addr + boff, eh[0], eh[1], eh[2], eh[3]);
-        sts128(e1_addr + boff + 128, el[0], el[1], el[2], el[3]);
-        sts128(e2_addr + boff, eh[0], eh[1], eh[2], eh[3]);
-        if (pending) drain(ok_prev);                     // batch k-1 finished while batch k was being prepared
-        ok_prev = ok;
+        for (int h = 0; h < ATC_NB; ++h) ok_prev[h] = ok[h];
         const bool first_batch = pos == t_beg;
         const bool flushed = first_batch && new_run && ti > 0;
         if (first_batch && new_run) {
@@ -1034,11 +1052,16 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
         __syncthreads();
         if (tid == 0) {
           tc_fence_after();
-          umma_tf32(tmem, d_e1 + buf * BUF_STEP, d_w1, IDESC, 0);
-          umma_tf32(tmem, d_e2 + buf * BUF_STEP, d_w2, IDESC, 1);
+#pragma unroll
+          for (int h = 0; h < ATC_NB; ++h) {
+            if (h < nb) {
+              umma_tf32(tmem + 32 * h, d_e1 + (uint64_t)(buf * ATC_NB + h) * BUF_STEP, d_w1, IDESC, 0);
+              umma_tf32(tmem + 32 * h, d_e2 + (uint64_t)(buf * ATC_NB + h) * BUF_STEP, d_w2, IDESC, 1);
+            }
+          }
           umma_commit(&bar);
         }
-        pending = true;
+        pending = nb;
         buf ^= 1;
         if (flushed) {
           if (warp == 0) store_run(run_first, ti - 1);
@@ -1047,7 +1070,7 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
         }
       }
     }
-    if (pending) drain(ok_prev);
+    if (pending) drain();
     flush_to_red();
     __syncthreads();
     if (warp == 0) store_run(run_first, ns - 1);
@@ -1058,7 +1081,7 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 32);
+    tmem_dealloc(tmem, 32 * ATC_NB);
   }
 }
 
