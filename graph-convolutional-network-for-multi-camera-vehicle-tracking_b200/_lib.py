@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libmpn_b200.so")
 MPN_OK, MPN_ERR_INVALID, MPN_ERR_CUDA, MPN_ERR_UNSORTED, MPN_ERR_WORKSPACE, MPN_ERR_NO_DEVICE = range(6)
 MPN_DE, MPN_DH, MPN_MAX_NODE_LAYERS = 4, 32, 8
 MPN_SUMS_DOUBLES = 96
+ABI_VERSION = 4             # MPN_B200_ABI_VERSION of include/mpn_b200.h (bumped when a struct or a signature changes)
 STAGE_ENC0, STAGE_ENC1, STAGE_EDGE, STAGE_NODE, STAGE_APPLY = range(5)
 POST_CUT, POST_PRUNE, POST_SPLIT = 1, 2, 4
 
@@ -150,7 +151,7 @@ def lib():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.mpn_abi_version() != 3:
+        if l.mpn_abi_version() != ABI_VERSION:
             raise ImportError("libmpn_b200.so ABI version mismatch")
         _lib = l
     return _lib

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPN_B200_ABI_VERSION 3
+#define MPN_B200_ABI_VERSION 4
 
 enum {
   MPN_OK = 0,

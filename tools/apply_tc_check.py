@@ -1,5 +1,6 @@
-"""Diagnostics for the tensor-core apply kernel: run the same forwards with MPN_APPLY_TC=0/1/2 (separate processes, the
-switch is read once) and compare h / logits; print the per-phase times of configs[1].  Not a benchmark."""
+"""Diagnostics for the apply sweep: the same forwards with the tensor-core kernel (MPN_APPLY_TC=1) and the packed-fp32 kernel
+(MPN_APPLY_TC=0), on stored y, in separate processes (the switches are read once); compares h / logits and prints the
+per-phase times of configs[1].  Not a benchmark."""
 import os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = "/tmp"
@@ -17,19 +18,17 @@ def child(mode):
         g = m.TrackletGraph(ei, N, chunk=chunk)
         b = bench.Batch(); b.x, b.edge_index, b.num_nodes = x, ei, N
         b.edge_attr = m.edge_features(x, ei, graph=g)
-        b._mpn_b200_graph = ((ei.data_ptr(), tuple(ei.shape), ei._version, N, None), g)
+        b.mpn_graph = g
         out, h = net(b)
         torch.cuda.synchronize()
         res[tag + "_h"] = h.cpu().numpy()
         res[tag + "_lg"] = out["classified_edges"][-1].cpu().numpy()
-        res[tag + "_pred"] = net.last_pred.cpu().numpy()
         print(mode, tag, "chunk", g.chunk, "E", g.n_edges, "h absmax", float(h.abs().max()), flush=True)
     np.savez(os.path.join(OUT, "atc_%s.npz" % mode), **res)
-    if True:
-        net = bench.make_model(dev)
-        x, ei = bench.device_graph(4096, 8, 0, dev)
-        ph = bench.time_phases(m, net, x, ei)
-        print(mode, "phases", {k: round(v, 4) for k, v in ph.items()}, flush=True)
+    net = bench.make_model(dev)
+    x, ei = bench.device_graph(4096, 8, 0, dev)
+    ph = bench.time_phases(m, net, x, ei)
+    print(mode, "phases", {k: round(v, 4) for k, v in ph.items()}, flush=True)
 
 
 if __name__ == "__main__":
@@ -37,16 +36,10 @@ if __name__ == "__main__":
         child(sys.argv[1])
         sys.exit(0)
     import numpy as np
-    for mode in ("11",):
-        env = dict(os.environ, MPN_APPLY_TC=mode[0], MPN_STORE_Y=mode[1])
-        r = subprocess.run([sys.executable, __file__, mode], env=env, timeout=600)
-        print("mode", mode, "rc", r.returncode, flush=True)
-    ref = np.load(os.path.join(OUT, "atc_00.npz"))
-    for mode in ("01", "11"):
-        p = os.path.join(OUT, "atc_%s.npz" % mode)
-        if not os.path.isfile(p):
-            continue
-        z = np.load(p)
-        for k in ref.files:
-            a, b = ref[k].astype(np.float64), z[k].astype(np.float64)
-            print("mode %s %-7s max|diff| %.3e  (max|ref| %.3e)  mismatches %d" % (mode, k, np.abs(a - b).max(), np.abs(a).max(), int((a != b).sum())))
+    for mode in ("0", "1"):
+        r = subprocess.run([sys.executable, __file__, mode], env=dict(os.environ, MPN_APPLY_TC=mode, MPN_STORE_Y="1"), timeout=600)
+        print("MPN_APPLY_TC=%s rc %d" % (mode, r.returncode), flush=True)
+    ref, z = np.load(os.path.join(OUT, "atc_0.npz")), np.load(os.path.join(OUT, "atc_1.npz"))
+    for k in ref.files:
+        a, b = ref[k].astype(np.float64), z[k].astype(np.float64)
+        print("%-5s max|tensor-core - packed fp32| %.3e  (max|value| %.3e)" % (k, np.abs(a - b).max(), np.abs(a).max()))
