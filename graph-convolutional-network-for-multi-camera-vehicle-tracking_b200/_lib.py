@@ -89,6 +89,9 @@ _PROTOS = {
     "mpn_forward_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_int32]),
     "mpn_forward": (C.c_int, [C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mpn_forward_with_edge_features": (C.c_int, [C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_int32, C.c_int32,
                                   C.c_int64, C.c_int, C.c_void_p, C.c_size_t]),
     "mpn_plan_destroy": (None, [C.c_void_p]),

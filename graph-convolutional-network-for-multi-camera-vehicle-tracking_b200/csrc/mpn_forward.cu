@@ -1923,9 +1923,12 @@ static SideStream* side_stream() {
   return state[dev] == 1 ? &table[dev] : nullptr;
 }
 
-int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const float* edge_attr, int32_t L, int32_t n_cls,
-                float* logits_out, float* h_out, uint8_t* pred_out, float* prob1_out, int use_tc, void* ws, size_t ws_bytes,
-                void* stream) {
+// ef_ws != NULL: edge_attr is an OUTPUT, produced here by mpn_edge_features on the main stream while the node encoder runs on
+// the side stream (both only read x)
+static int forward_impl(const mpn_graph* g, const mpn_weights* w, const float* x, float* edge_attr_rw, int32_t L, int32_t n_cls,
+                        float* logits_out, float* h_out, uint8_t* pred_out, float* prob1_out, int use_tc, void* ws, size_t ws_bytes,
+                        void* ef_ws, size_t ef_ws_bytes, void* stream) {
+  const float* edge_attr = edge_attr_rw;
   MPN_REQUIRE(g && x && edge_attr && logits_out, "forward: NULL argument");
   MPN_REQUIRE(g->row_offset == 0 && g->n_cols == g->n_nodes, "mpn_forward runs an unsharded graph; use the plan API for row blocks");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1936,11 +1939,13 @@ int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const 
 #define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
   p->fuse_fin = (p->n_graphs > 1) ? 0 : 1;
   {
-    // the node encoder (tensor-core GEMM chain) does not depend on the edge-encoder sweeps: run it on a side stream
+    // the node encoder (tensor-core GEMM chain) depends neither on the edge features nor on the edge-encoder sweeps: it runs
+    // on a side stream while the caller's stream does the edge chain
     SideStream* ss = side_stream();
     const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
     STEP_TRY(mpn_plan_node_encoder(p, x, fork ? ss->stream : st));
     if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
+    if (ef_ws != nullptr) STEP_TRY(mpn_edge_features(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st));
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
     if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
@@ -1971,6 +1976,21 @@ int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const 
 done:
   mpn_plan_destroy(p);
   return rc;
+}
+
+int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x, const float* edge_attr, int32_t L, int32_t n_cls,
+                float* logits_out, float* h_out, uint8_t* pred_out, float* prob1_out, int use_tc, void* ws, size_t ws_bytes,
+                void* stream) {
+  return forward_impl(g, w, x, const_cast<float*>(edge_attr), L, n_cls, logits_out, h_out, pred_out, prob1_out, use_tc, ws, ws_bytes,
+                      nullptr, 0, stream);
+}
+
+int mpn_forward_with_edge_features(const mpn_graph* g, const mpn_weights* w, const float* x, float* edge_attr_out, int32_t L,
+                                   int32_t n_cls, float* logits_out, float* h_out, uint8_t* pred_out, float* prob1_out, int use_tc,
+                                   void* ws, size_t ws_bytes, void* ef_ws, size_t ef_ws_bytes, void* stream) {
+  MPN_REQUIRE(ef_ws != nullptr && edge_attr_out != nullptr, "forward_with_edge_features: NULL edge-feature buffer / workspace");
+  return forward_impl(g, w, x, edge_attr_out, L, n_cls, logits_out, h_out, pred_out, prob1_out, use_tc, ws, ws_bytes, ef_ws,
+                      ef_ws_bytes, stream);
 }
 
 int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x, const float* edge_attr, int32_t L, int32_t n_cls,

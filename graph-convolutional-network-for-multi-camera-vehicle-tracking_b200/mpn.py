@@ -209,9 +209,17 @@ class MOTMPNet(nn.Module):
         self.last_pred = self.last_prob1 = None
 
     # ------------------------------------------------------------------------------------------
+    def invalidate_weight_cache(self):
+        """Needed only after a Parameter OBJECT is replaced (``module.weight = nn.Parameter(...)``); in-place updates
+        (``load_state_dict``, ``.to()``, ``p.data.copy_``) are detected through the tensors' data pointers and versions."""
+        self.__dict__.pop("_param_list", None)
+        self._packed = None
+
     def _weights(self, device):
-        params = list(self.parameters())
-        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
+        params = self.__dict__.get("_param_list")          # Parameter objects keep their identity across .to() / load_state_dict
+        if params is None:                                 # (walking the module tree costs ~40 us per call)
+            params = self.__dict__["_param_list"] = list(self.parameters())
+        key = (device,) + tuple([(p.data_ptr(), p._version) for p in params])
         if self._packed is not None and self._packed[0] == key:
             return self._packed[2]
         for p in params:
@@ -299,22 +307,38 @@ class MOTMPNet(nn.Module):
     @torch.no_grad()
     def forward(self, data):
         """data.x [N,D] fp32, data.edge_index [2,E] int64, data.edge_attr [E,2] fp32, all on one CUDA device.
-        Returns ({'classified_edges': [logits [E,2], ...]}, latent_node_feats [N,32]) as models/mpn.py:299."""
-        x, edge_attr = data.x, data.edge_attr
+        Returns ({'classified_edges': [logits [E,2], ...]}, latent_node_feats [N,32]) as models/mpn.py:299.
+
+        Extension: when ``data.edge_attr`` is None (or absent) the initial edge features of inference.py:453-456 are computed
+        here from ``data.x`` — in the same call, so that the node encoder overlaps them on a side stream — and stored back into
+        ``data.edge_attr`` (same values as ``edge_features(data.x, data.edge_index)``)."""
+        x, edge_attr = data.x, getattr(data, "edge_attr", None)
         # data.mpn_graph: tables built on the device by TrackletGraph.from_cameras (no int64 edge_index needed)
         pre = getattr(data, "mpn_graph", None)
         edge_index = None if pre is not None else data.edge_index
-        if not (x.is_cuda and edge_attr.is_cuda and (edge_index is None or edge_index.is_cuda)):
+        if not (x.is_cuda and (edge_attr is None or edge_attr.is_cuda) and (edge_index is None or edge_index.is_cuda)):
             raise RuntimeError("MOTMPNet.forward needs CUDA tensors: the B200 path has no CPU fallback")
         if self.training:
             raise _unsupported("training mode (dropout active / autograd); call .eval() as main.py:98 does")
         dev = x.device
         x = x.contiguous().float()
         g = pre if pre is not None else graph_for(data, edge_index, x.shape[0])
-        ea = edge_attr.contiguous().float()
-        if g.perm is not None:
-            ea = ea[g.perm].contiguous()
         W = self._weights(dev)
+        make_features = edge_attr is None
+        fused_features = (make_features and g.n_graphs <= 1 and g.n_edges > 0 and
+                          not (self.use_cuda_graph and g.n_edges <= self.cuda_graph_max_edges))
+        if make_features and not fused_features:          # small graphs (CUDA-graph replay), batched graphs: two calls
+            from .edge_features import edge_features
+            edge_attr = edge_features(x, None, graph=g)
+            if g.perm is not None:
+                edge_attr = edge_attr[g.perm]             # (edge_features returned the caller's order)
+            ea = edge_attr.contiguous()
+        elif fused_features:
+            ea = torch.empty(g.n_edges, 2, dtype=torch.float32, device=dev)          # filled by the fused call, graph edge order
+        else:
+            ea = edge_attr.contiguous().float()
+            if g.perm is not None:
+                ea = ea[g.perm].contiguous()
         if x.shape[1] != W.node_dims[0]:
             raise ValueError("data.x has %d features, the node encoder expects %d" % (x.shape[1], W.node_dims[0]))
         if ea.shape != (g.n_edges, 2):
@@ -339,10 +363,18 @@ class MOTMPNet(nn.Module):
             need = lib.mpn_forward_workspace_bytes(g.ref, C.byref(W), L)
             ws = workspace("forward", dev, need)
             with torch.cuda.device(dev):
-                _lib.check(lib.mpn_forward(g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, logits.data_ptr(),
-                                           h.data_ptr(), pred.data_ptr() if pred is not None else None,
-                                           prob1.data_ptr() if prob1 is not None else None, int(bool(USE_TENSOR_CORES)),
-                                           ws.data_ptr(), ws.numel(), current_stream_ptr(dev)))
+                if fused_features:
+                    ef_ws = workspace("edge_features", dev, lib.mpn_edge_features_workspace_bytes(g.ref, x.shape[1]))
+                    _lib.check(lib.mpn_forward_with_edge_features(
+                        g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, logits.data_ptr(), h.data_ptr(),
+                        pred.data_ptr() if pred is not None else None, prob1.data_ptr() if prob1 is not None else None,
+                        int(bool(USE_TENSOR_CORES)), ws.data_ptr(), ws.numel(), ef_ws.data_ptr(), ef_ws.numel(),
+                        current_stream_ptr(dev)))
+                else:
+                    _lib.check(lib.mpn_forward(g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, logits.data_ptr(),
+                                               h.data_ptr(), pred.data_ptr() if pred is not None else None,
+                                               prob1.data_ptr() if prob1 is not None else None, int(bool(USE_TENSOR_CORES)),
+                                               ws.data_ptr(), ws.numel(), current_stream_ptr(dev)))
         if g.perm is not None:                       # back to the caller's edge order
             inv = torch.empty_like(logits)
             inv[:, g.perm] = logits
@@ -351,5 +383,14 @@ class MOTMPNet(nn.Module):
                 p2, q2 = torch.empty_like(pred), torch.empty_like(prob1)
                 p2[g.perm], q2[g.perm] = pred, prob1
                 pred, prob1 = p2, q2
+        if make_features:                                 # hand the features back in the caller's edge order
+            out_ea = ea
+            if g.perm is not None:
+                out_ea = torch.empty_like(ea)
+                out_ea[g.perm] = ea
+            try:
+                data.edge_attr = out_ea
+            except Exception:
+                pass
         self.last_pred, self.last_prob1 = pred, prob1
         return {'classified_edges': [logits[i] for i in range(n_out)]}, h

@@ -197,6 +197,14 @@ int mpn_forward(const mpn_graph* g, const mpn_weights* w, const float* x_dev, co
                 uint8_t* pred_out_dev, float* prob1_out_dev, int use_tensor_cores,
                 void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* K1 + forward in one call: edge_attr_out (dev [E,2]) is PRODUCED here by mpn_edge_features (inference.py:453-456) on `stream`
+ * while the node encoder runs on a side stream — the two only share the read-only x, so the encoder's GEMM chain hides behind the
+ * Gram GEMM and the feature epilogue.  ef_workspace: mpn_edge_features_workspace_bytes(g, node_dims[0]).  Unsharded graphs. */
+int mpn_forward_with_edge_features(const mpn_graph* g, const mpn_weights* w, const float* x_dev, float* edge_attr_out_dev,
+                                   int32_t num_enc_steps, int32_t num_class_steps, float* logits_out_dev, float* h_out_dev,
+                                   uint8_t* pred_out_dev, float* prob1_out_dev, int use_tensor_cores, void* workspace_dev,
+                                   size_t workspace_bytes, void* ef_workspace_dev, size_t ef_workspace_bytes, void* stream);
+
 /* Phase-level entry points of the same forward, for row-block sharded execution where the host inserts
  * the collectives (all-reduce of BatchNorm moment sums, all-gather of h) between phases.  See DESIGN.md. */
 typedef struct mpn_fwd_plan mpn_fwd_plan;       /* opaque; lives inside the caller's workspace */

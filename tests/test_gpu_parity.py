@@ -338,6 +338,31 @@ def test_forward_reattach_initial_features(m, re_n, re_e, L, n_cls, chunk, agg):
     assert not bool(((net.last_pred.cpu() != (ref[-1][:, 1] > ref[-1][:, 0]).to(torch.uint8)) & (margin > 1e-4)).any())
 
 
+def test_forward_computes_edge_features_when_absent(m):
+    """data.edge_attr = None: K1 runs inside forward (node encoder on the side stream) — same bits as the two-call path, on the
+    large-graph path, the CUDA-graph path for small graphs, unsorted edges and batched graphs; the features are handed back."""
+    params = mo.shipped_model_params(2, 1, 64, (48, 40))
+    sd = mo.init_weights(params, "resnet101", 21)
+    x, ei, cam, _ = mo.synth_graph(200, 4, 9, D=64, planted=True)
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(4))
+    for edges, cuda_graph in ((ei, False), (ei, True), (ei[:, perm], False)):
+        net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+        net.load_state_dict(sd, strict=True)
+        net = net.to(dev()).eval()
+        net.use_cuda_graph = cuda_graph
+        xd, eid = x.to(dev()), edges.to(dev())
+        ea = m.edge_features(xd, eid)
+        o1, h1 = net(Data(x=xd, edge_index=eid, edge_attr=ea))
+        d2 = Data(x=xd, edge_index=eid, edge_attr=None)
+        o2, h2 = net(d2)
+        torch.cuda.synchronize()
+        assert torch.equal(d2.edge_attr, ea)
+        assert torch.equal(o1["classified_edges"][-1], o2["classified_edges"][-1]) and torch.equal(h1, h2)
+    d3 = Data(x=x.to(dev()), edge_index=ei.to(dev()))                          # attribute absent altogether
+    net(d3)
+    assert torch.equal(d3.edge_attr, m.edge_features(x.to(dev()), ei.to(dev())))
+
+
 class _NoComm:
     world, rank = 1, 0
 
