@@ -120,6 +120,11 @@ _PROTOS = {
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_active_edges": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mpn_compact_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph)]),
+    "mpn_count_active": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mpn_compact_active": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mpn_clear_inactive": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mpn_labels_reference_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "mpn_edge_confusion": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "mpn_contingency_workspace_bytes": (C.c_size_t, [C.c_int64]),

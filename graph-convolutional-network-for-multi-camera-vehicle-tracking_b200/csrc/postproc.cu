@@ -132,9 +132,13 @@ __device__ __forceinline__ int find_edge(const mpn_graph& g, int u, int v) {
   return -1;
 }
 
+// SHARD: row-block graph (global src = row_offset + local row), no reverse-edge lookup (the reverse edge lives on another rank),
+// the edge's probability is compacted along
+template <bool SHARD>
 __global__ void __launch_bounds__(256) write_active_kernel(const mpn_graph g, const uint8_t* __restrict__ act,
                                                            const int* __restrict__ blockoff, int* __restrict__ a_eid,
-                                                           int* __restrict__ a_src, int* __restrict__ a_dst, int* __restrict__ a_rev) {
+                                                           int* __restrict__ a_src, int* __restrict__ a_dst, int* __restrict__ a_rev,
+                                                           const float* __restrict__ prob, int pstride, float* __restrict__ a_prob) {
   __shared__ int tsum[256];
   const long long E = g.n_edges;
   const long long base = (long long)blockIdx.x * EPB + (long long)threadIdx.x * 16;
@@ -158,9 +162,14 @@ __global__ void __launch_bounds__(256) write_active_kernel(const mpn_graph g, co
     const int u = find_row(g.rowptr, g.n_nodes, e);
     const int v = g.col[e];
     a_eid[pos] = e;
-    a_src[pos] = u;
     a_dst[pos] = v;
-    a_rev[pos] = find_edge(g, v, u);
+    if (SHARD) {
+      a_src[pos] = g.row_offset + u;
+      a_prob[pos] = prob[(size_t)e * pstride];
+    } else {
+      a_src[pos] = u;
+      a_rev[pos] = find_edge(g, v, u);
+    }
     ++pos;
   }
 }
@@ -171,7 +180,7 @@ static int build_active_list(PostCtx& c, const uint8_t* act) {
   MPN_LAUNCH_OK();
   scan_blocks_kernel<<<1, 1024, 0, c.st>>>(c.blockoff, c.n_blocks, c.counters);
   MPN_LAUNCH_OK();
-  write_active_kernel<<<c.n_blocks, 256, 0, c.st>>>(c.g, act, c.blockoff, c.a_eid, c.a_src, c.a_dst, c.a_rev);
+  write_active_kernel<false><<<c.n_blocks, 256, 0, c.st>>>(c.g, act, c.blockoff, c.a_eid, c.a_src, c.a_dst, c.a_rev, nullptr, 0, nullptr);
   MPN_LAUNCH_OK();
   MPN_CUDA_OK(cudaMemcpyAsync(&c.n_active, c.counters, sizeof(int), cudaMemcpyDeviceToHost, c.st));
   MPN_CUDA_OK(cudaStreamSynchronize(c.st));
@@ -765,6 +774,26 @@ static void labels_reference(const int* src, const int* dst, long long m, int n_
   *n_comp = (int)k;
 }
 
+__global__ void clear_inactive_kernel(long long n, const int* __restrict__ eid, const uint8_t* __restrict__ keep,
+                                      uint8_t* __restrict__ act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!keep[i]) act[eid[i]] = 0;
+}
+
+// workspace of the shard compaction: block offsets + one counter
+struct CompactCtx {
+  int n_blocks;
+  int *blockoff, *counter;
+  size_t total;
+};
+static void compact_layout(CompactCtx& c, const mpn_graph& g, void* ws, size_t ws_bytes) {
+  Arena a(ws, ws_bytes);
+  c.n_blocks = div_up((long long)(g.n_edges > 0 ? g.n_edges : 1), EPB);
+  c.blockoff = a.take<int>(c.n_blocks + 1);
+  c.counter = a.take<int>(8);
+  c.total = a.off;
+}
+
 }  // namespace mpn
 
 using namespace mpn;
@@ -864,6 +893,65 @@ int mpn_active_edges(const mpn_graph* g, const uint8_t* act, int32_t* src_out, i
     MPN_CUDA_OK(cudaMemcpyAsync(dst_out, c.a_dst, sizeof(int) * c.n_active, cudaMemcpyDeviceToDevice, c.st));
     MPN_CUDA_OK(cudaStreamSynchronize(c.st));
   }
+  return MPN_OK;
+}
+
+size_t mpn_compact_workspace_bytes(const mpn_graph* g) {
+  if (!g) return 0;
+  CompactCtx c;
+  compact_layout(c, *g, nullptr, 0);
+  return c.total + 256;
+}
+
+static int compact_begin(CompactCtx& c, const mpn_graph* g, const uint8_t* act, void* ws, size_t ws_bytes) {
+  MPN_REQUIRE(g && ws, "compact: NULL argument");
+  MPN_REQUIRE(act || g->n_edges == 0, "compact: NULL activity flags");
+  MPN_REQUIRE(g->n_graphs <= 1, "compact: batched graphs are not row-sharded");
+  MPN_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  compact_layout(c, *g, ws, ws_bytes);
+  if (c.total > ws_bytes) {
+    set_error("compact workspace too small: need %zu bytes, have %zu", c.total, ws_bytes);
+    return MPN_ERR_WORKSPACE;
+  }
+  return MPN_OK;
+}
+
+int mpn_count_active(const mpn_graph* g, const uint8_t* act, int64_t* n_active, void* ws, size_t ws_bytes, void* stream) {
+  CompactCtx c;
+  MPN_REQUIRE(n_active, "count_active: NULL output");
+  MPN_TRY(compact_begin(c, g, act, ws, ws_bytes));
+  *n_active = 0;
+  if (g->n_edges == 0) return MPN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  count_active_kernel<<<c.n_blocks, 256, 0, st>>>(act, g->n_edges, c.blockoff);
+  MPN_LAUNCH_OK();
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(c.blockoff, c.n_blocks, c.counter);
+  MPN_LAUNCH_OK();
+  int n = 0;
+  MPN_CUDA_OK(cudaMemcpyAsync(&n, c.counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MPN_CUDA_OK(cudaStreamSynchronize(st));
+  *n_active = n;
+  return MPN_OK;
+}
+
+int mpn_compact_active(const mpn_graph* g, const uint8_t* act, const float* prob1, int32_t pstride, int32_t* src_out,
+                       int32_t* dst_out, int32_t* eid_out, float* prob_out, void* ws, size_t ws_bytes, void* stream) {
+  CompactCtx c;
+  MPN_TRY(compact_begin(c, g, act, ws, ws_bytes));
+  if (g->n_edges == 0) return MPN_OK;
+  MPN_REQUIRE(prob1 && pstride >= 1 && src_out && dst_out && eid_out && prob_out, "compact_active: bad arguments");
+  write_active_kernel<true><<<c.n_blocks, 256, 0, (cudaStream_t)stream>>>(*g, act, c.blockoff, eid_out, src_out, dst_out, nullptr,
+                                                                          prob1, pstride, prob_out);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+int mpn_clear_inactive(uint8_t* act, const int32_t* eid, const uint8_t* keep, int64_t n, void* stream) {
+  if (n <= 0) return MPN_OK;
+  MPN_REQUIRE(act && eid && keep, "clear_inactive: NULL argument");
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs * 8, (n + 255) / 256));
+  clear_inactive_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, eid, keep, act);
+  MPN_LAUNCH_OK();
   return MPN_OK;
 }
 

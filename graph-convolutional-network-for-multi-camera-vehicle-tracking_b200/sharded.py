@@ -66,6 +66,22 @@ class TorchComm:
             self.dist.all_reduce(full, op=self.dist.ReduceOp.SUM, group=self.group)
 
 
+    def all_gather_ragged(self, t):
+        """t: [R, n_local] (n_local differs per rank).  Returns the list of every rank's tensor, in rank order."""
+        if self.world == 1:
+            return [t]
+        counts = torch.zeros(self.world, dtype=torch.int64, device=t.device)
+        counts[self.rank] = t.shape[1]
+        self.dist.all_reduce(counts, op=self.dist.ReduceOp.SUM, group=self.group)
+        counts = [int(c) for c in counts.tolist()]
+        width = max(max(counts), 1)
+        mine = torch.zeros(t.shape[0], width, dtype=t.dtype, device=t.device)
+        mine[:, :t.shape[1]] = t
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(parts, mine, group=self.group)
+        return [p[:, :c] for p, c in zip(parts, counts)]
+
+
 def _combine_sums(shards, comm):
     """Global BatchNorm moment sums: add the shards of this process, then all-reduce across processes."""
     if len(shards) == 1:
@@ -286,6 +302,11 @@ class ShardedMPN:
             self.peers = None
         return self.peers
 
+    def post_processing(self, num_cameras, graph, pred, prob1, CONFIG, numbering='reference'):
+        """CUT / PRUNE / CUT / SPLIT + labels for this rank's shard (see ``sharded_post_processing``)."""
+        return sharded_post_processing(num_cameras, (graph, pred, prob1), CONFIG, graph.n_cols, comm=self.comm,
+                                       numbering=numbering)
+
     @torch.no_grad()
     def forward(self, x, local_edge_index, local_edge_attr, blocks, fuse_decisions=False, graph=None, total_edges=None):
         """``total_edges``: number of edges of the WHOLE graph if the caller knows it (saves one all-reduce + host sync)."""
@@ -332,3 +353,99 @@ class ShardedMPN:
             finally:
                 ph.close()
         return {'classified_edges': [logits[i] for i in range(n_out)]}, h_local, pred, prob1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Post-processing of a row-block sharded graph (new; inference.post_processing, inference.py:70-169, is single-GPU)
+# ------------------------------------------------------------------------------------------------------------------
+class CudaPostOps:
+    """Per-rank pieces of the sharded post-processing through libmpn_b200 (include/mpn_b200.h): shard compaction,
+    the fixed-point rounds on the merged active list, and the write-back into the shard's decisions."""
+
+    def compact(self, graph, pred, prob1):
+        """Active edges of one shard in edge order: (src, dst) global int32, shard-local edge id int32, prob1 f32."""
+        if not (pred.is_cuda and prob1.is_cuda):
+            raise RuntimeError("sharded post-processing needs CUDA tensors: the B200 path has no CPU fallback")
+        if pred.dtype != torch.uint8 or not pred.is_contiguous() or pred.numel() != graph.n_edges:
+            raise ValueError("pred must be the shard's contiguous uint8 decisions, one per local edge")
+        if graph.perm is not None:
+            raise ValueError("sharded post-processing needs (row, col)-sorted local edges")
+        stride = 1
+        if prob1.dim() == 2:                                  # [E,2] softmax: column 1 in place
+            prob1, stride = prob1[:, 1], int(prob1.stride(0))
+        elif prob1.numel() > 1:
+            stride = int(prob1.stride(0))
+        if prob1.dtype != torch.float32 or stride < 1 or prob1.numel() != graph.n_edges:
+            raise ValueError("prob1 must be float32 with one entry per local edge")
+        dev, lib = pred.device, _lib.lib()
+        ws = workspace("compact", dev, lib.mpn_compact_workspace_bytes(graph.ref))
+        n = C.c_int64(0)
+        stream = current_stream_ptr(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mpn_count_active(graph.ref, pred.data_ptr(), C.byref(n), ws.data_ptr(), ws.numel(), stream))
+            n = int(n.value)
+            src, dst, eid = (torch.empty(n, dtype=torch.int32, device=dev) for _ in range(3))
+            prob = torch.empty(n, dtype=torch.float32, device=dev)
+            if n:
+                _lib.check(lib.mpn_compact_active(graph.ref, pred.data_ptr(), prob1.data_ptr(), stride, src.data_ptr(),
+                                                  dst.data_ptr(), eid.data_ptr(), prob.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  stream))
+        return src, dst, eid, prob
+
+    def run(self, num_cameras, src, dst, prob, CONFIG, n_nodes, numbering):
+        """CUT / PRUNE / CUT / SPLIT + labels on the merged active list (every entry active).  Returns
+        (ID_pred int64 CPU [n_nodes], keep uint8 [A] on the device)."""
+        from types import SimpleNamespace
+        from .postprocess import compute_SCC_and_Clusters, post_processing
+        a = int(src.numel())
+        keep = torch.ones(a, dtype=torch.uint8, device=src.device)
+        if a == 0:
+            return torch.arange(n_nodes, dtype=torch.int64), keep
+        ei = torch.stack([src.long(), dst.long()])
+        if not any(CONFIG[k] for k in ('CUTTING', 'PRUNING', 'SPLITTING')):
+            return compute_SCC_and_Clusters(ei.t().cpu().numpy(), n_nodes)[0], keep
+        data = SimpleNamespace(edge_index=ei, num_nodes=int(n_nodes))
+        ID, new_pred = post_processing(num_cameras, None, None, keep.long(), None, CONFIG, data, prob.contiguous(),
+                                       numbering=numbering)
+        return ID, (new_pred != 0).to(torch.uint8)
+
+    def clear(self, pred, eid, keep):
+        if eid.numel():
+            keep = keep.contiguous()
+            with torch.cuda.device(pred.device):
+                _lib.check(_lib.lib().mpn_clear_inactive(pred.data_ptr(), eid.data_ptr(), keep.data_ptr(), eid.numel(),
+                                                         current_stream_ptr(pred.device)))
+
+
+def sharded_post_processing(num_cameras, shards, CONFIG, n_nodes, comm=None, numbering='reference', ops=None):
+    """inference.post_processing (inference.py:70-169) for a graph whose edges are sharded by row block.
+
+    ``shards``: ``(graph, pred, prob1)`` of this rank - the shard's TrackletGraph, its uint8 decisions and softmax[:,1]
+    as ``ShardedMPN.forward(..., fuse_decisions=True)`` returns them - or a list of such triples held by this process
+    (consecutive row blocks; how the 1-GPU and CPU tests emulate N > 1).  Every stage of the reference only ever looks
+    at ACTIVE edges, so each shard contributes the order-preserving compaction of its active edges (the E-sized sweep
+    stays sharded), the ranks exchange those lists ONCE (A << E entries of 12 bytes) and run the fixed-point rounds on
+    the merged list, whose order is the global edge order (so arg-min ties and the label numbering match the reference
+    bit for bit); finally every shard clears the decisions the rounds removed.
+
+    Returns ``(ID_pred, preds)``: int64 CPU labels [n_nodes], identical on every rank, and the shard decisions (updated in
+    place), one tensor per triple passed in."""
+    from .postprocess import _as_bool
+    single = isinstance(shards, tuple)
+    if single:
+        shards = [shards]
+    comm = comm if comm is not None else TorchComm()
+    ops = ops if ops is not None else CudaPostOps()
+    cfg = {k: _as_bool(CONFIG[k]) for k in ('CUTTING', 'PRUNING', 'SPLITTING')}
+    lists = [ops.compact(g, pred, prob1) for (g, pred, prob1) in shards]
+    mine = torch.cat([torch.stack([s, d, p.view(torch.int32)]) for (s, d, _e, p) in lists], dim=1)
+    parts = comm.all_gather_ragged(mine)
+    merged = torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]
+    ID, keep = ops.run(int(num_cameras), merged[0].contiguous(), merged[1].contiguous(),
+                       merged[2].contiguous().view(torch.float32), cfg, int(n_nodes), numbering)
+    off = sum(int(p.shape[1]) for p in parts[:comm.rank])
+    for (g, pred, _prob1), (_s, _d, eid, _p) in zip(shards, lists):
+        ops.clear(pred, eid, keep[off:off + eid.numel()])
+        off += int(eid.numel())
+    preds = [pred for (_g, pred, _p) in shards]
+    return ID, (preds[0] if single else preds)

@@ -306,6 +306,24 @@ int mpn_post_processing(const mpn_graph* g, uint8_t* act_dev, const float* prob1
  * n_active_host receives the count; src_out/dst_out dev [capacity].  Synchronises. */
 int mpn_active_edges(const mpn_graph* g, const uint8_t* act_dev, int32_t* src_out_dev, int32_t* dst_out_dev,
                      int64_t capacity, int64_t* n_active_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Row-block sharded post-processing (new; the reference is single-GPU).  Only ACTIVE edges take part in any stage of
+ * inference.post_processing (inference.py:93-166: CUT looks for an active reverse edge, PRUNE / SPLIT pick among active edges, the
+ * labels are the SCCs of the active digraph), so a shard only has to contribute the order-preserving compaction of its own active
+ * edges: the E-sized sweep stays sharded, the ranks exchange A << E entries once, and the fixed-point rounds run on the merged
+ * active list (concatenated in rank order = global edge order, which keeps torch.argmin's lowest-edge-id tie rule).
+ *   mpn_count_active     number of active edges of this shard (row-block graphs allowed); leaves the block offsets in the workspace
+ *   mpn_compact_active   must follow mpn_count_active on the same workspace / stream with `act` unchanged: writes, in edge order,
+ *                        src (GLOBAL row id = row_offset + local row), dst (global), the shard-local edge id and prob1 of every
+ *                        active edge; outputs dev [n_active]
+ *   mpn_clear_inactive   act[eid[i]] = 0 where keep[i] == 0 (the shard applies the merged result to its own decisions)
+ * mpn_count_active synchronises the stream (the count is returned to the host); the other two do not. */
+size_t mpn_compact_workspace_bytes(const mpn_graph* g);
+int mpn_count_active(const mpn_graph* g, const uint8_t* act_dev, int64_t* n_active_host, void* workspace_dev,
+                     size_t workspace_bytes, void* stream);
+int mpn_compact_active(const mpn_graph* g, const uint8_t* act_dev, const float* prob1_dev, int32_t prob_stride,
+                       int32_t* src_out_dev, int32_t* dst_out_dev, int32_t* eid_out_dev, float* prob_out_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+int mpn_clear_inactive(uint8_t* act_dev, const int32_t* eid_dev, const uint8_t* keep_dev, int64_t n, void* stream);
 /* Host-side (CPU, sequential by nature): label integers exactly as compute_SCC_and_Clusters (utils.py:30-52)
  * assigns them — networkx SCC emission order, stable sort by size, isolated nodes last.  HOST pointers. */
 int mpn_labels_reference_host(const int32_t* src_host, const int32_t* dst_host, int64_t n_active, int32_t n_nodes,

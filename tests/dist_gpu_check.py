@@ -4,18 +4,21 @@
 
 Each rank runs its row-block shard through ShardedMPN, once with the collectives fused into the kernels over NVLink
 peer memory (mpn_forward_sharded) and once with the NCCL schedule; both are compared with the fp64 oracle of the whole
-graph.  Repeated calls exercise the sequence-number / slot reuse of the peer protocol.
+graph.  Repeated calls exercise the sequence-number / slot reuse of the peer protocol.  The decisions then go through
+the sharded post-processing (active lists exchanged over NCCL) and are compared with the CPU restatement on the whole graph.
 """
 import copy
 import os
 import sys
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gcn_mtmc_b200 as m                      # noqa: E402
 from oracle import mpn_oracle as mo            # noqa: E402
+from oracle import postproc_oracle as po       # noqa: E402
 
 
 def check_case(rank, world, dev, L, n_cls, N, C, modes, chunk=None, reattach=False):
@@ -60,7 +63,42 @@ def check_case(rank, world, dev, L, n_cls, N, C, modes, chunk=None, reattach=Fal
         assert not bool(bad.any()), mode
     if len(results) == 2:
         assert (results["fused"] - results["nccl"]).abs().max().item() <= 2e-6
+    # the decisions of the last forward go straight into the sharded post-processing (shard compaction, one exchange of the
+    # active lists over NCCL, rounds on the merged list): bit-exact against the CPU restatement run on the gathered graph
+    parts = [None] * world
+    dist.all_gather_object(parts, (pred.cpu().numpy(), prob1.cpu().numpy()))
+    pred_all = np.concatenate([p[0] for p in parts]).astype(np.int64)
+    prob_all = np.concatenate([p[1] for p in parts])
+    lab_ref, act_ref = po.post_processing_rounds(ei[0].numpy(), ei[1].numpy(), pred_all, prob_all, C, N, numbering="reference")
+    ID, new_pred = sh.post_processing(C, g, pred, prob1, {"CUTTING": True, "PRUNING": "True", "SPLITTING": True})
+    assert new_pred.data_ptr() == pred.data_ptr()
+    assert np.array_equal(new_pred.cpu().numpy().astype(np.int64), act_ref[lo:hi]), "sharded post-processing: decisions"
+    assert np.array_equal(ID.numpy(), lab_ref), "sharded post-processing: labels"
     return worst
+
+
+def check_post(rank, world, dev, n_nodes=20000, cams=8):
+    """Sparse predicted graph (planted clusters + noise), sharded by row block: decisions and reference label integers."""
+    src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, cams, 9, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03,
+                                                          single_dir=0.05)
+    order = np.lexsort((dst, src))
+    src, dst, prob, pred = src[order], dst[order], prob[order], pred[order]
+    lab_ref, act_ref = po.post_processing_rounds(src, dst, pred, prob, cams, n_nodes, numbering="reference")
+    ei = torch.from_numpy(np.stack([src, dst]))
+    rowptr = torch.searchsorted(ei[0].contiguous(), torch.arange(n_nodes + 1))
+    n0, n1 = m.partition_rows(rowptr, world)[rank]
+    lo, hi = m.shard_edges(ei, n0, n1)
+    g = m.TrackletGraph(ei[:, lo:hi].to(dev), n_nodes, row_offset=n0, n_rows=n1 - n0)
+    p_l = torch.from_numpy(pred[lo:hi].astype(np.uint8)).to(dev)
+    q_l = torch.from_numpy(prob[lo:hi]).to(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    ID, p_new = m.sharded_post_processing(cams, (g, p_l, q_l), {"CUTTING": True, "PRUNING": True, "SPLITTING": True}, n_nodes)
+    ev1.record()
+    torch.cuda.synchronize()
+    assert np.array_equal(p_new.cpu().numpy().astype(np.int64), act_ref[lo:hi]) and np.array_equal(ID.numpy(), lab_ref)
+    assert int(act_ref.sum()) < int(pred.sum())
+    return ev0.elapsed_time(ev1)
 
 
 def main():
@@ -72,10 +110,12 @@ def main():
     for (L, n_cls, N, C, chunk, reattach) in [(1, 1, 240, 4, None, False), (4, 2, 200, 5, None, False), (2, 1, 600, 3, 128, False),
                                               (1, 1, 600, 3, 256, False), (3, 1, 600, 3, 128, True)]:
         worst = max(worst, check_case(rank, world, dev, L, n_cls, N, C, modes, chunk, reattach))
+    post_ms = check_post(rank, world, dev)
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print("dist_gpu_check ok: world=%d worst err/tol=%.3f modes=%s" % (world, t.item(), sorted(modes)))
+        print("dist_gpu_check ok: world=%d worst err/tol=%.3f modes=%s sharded post-processing (20000 nodes) %.2f ms"
+              % (world, t.item(), sorted(modes), post_ms))
     dist.destroy_process_group()
 
 

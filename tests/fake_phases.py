@@ -136,3 +136,25 @@ class FakePhases:
 
     def node_finalize(self, step):
         self._h[self.n0:self.n1] = self.msg
+
+
+class FakePostOps:
+    """CPU stand-in for ``CudaPostOps`` (shard compaction / rounds on the merged active list / write-back), backed by the
+    post-processing oracle, so the exchange logic of ``sharded_post_processing`` can run under gloo.  A fake "graph" is any
+    object with ``src`` / ``dst`` (global int64 ids of the shard's edges, edge order)."""
+
+    def compact(self, graph, pred, prob1):
+        idx = torch.nonzero(pred != 0).reshape(-1)
+        return (graph.src[idx].to(torch.int32), graph.dst[idx].to(torch.int32), idx.to(torch.int32), prob1[idx].float())
+
+    def run(self, num_cameras, src, dst, prob, CONFIG, n_nodes, numbering):
+        import numpy as np
+        from oracle import postproc_oracle as po
+        labels, act = po.post_processing_rounds(src.numpy().astype(np.int64), dst.numpy().astype(np.int64),
+                                                np.ones(src.numel(), dtype=np.int64), prob.numpy(), num_cameras, n_nodes,
+                                                cutting=CONFIG['CUTTING'], pruning=CONFIG['PRUNING'],
+                                                splitting=CONFIG['SPLITTING'], numbering=numbering)
+        return torch.from_numpy(np.asarray(labels).astype(np.int64)), torch.from_numpy(act.astype(np.uint8))
+
+    def clear(self, pred, eid, keep):
+        pred[eid.long()[keep == 0]] = 0

@@ -372,6 +372,9 @@ class _NoComm:
     def all_gather_rows(self, full, blocks):
         pass
 
+    def all_gather_ragged(self, t):
+        return [t]
+
 
 @pytest.mark.parametrize("L,n_cls,world", [(1, 1, 2), (3, 2, 3), (0, 1, 2)])
 def test_sharded_cuda_shards_in_one_process(m, L, n_cls, world):
@@ -577,6 +580,65 @@ def test_scc_with_one_directional_cycles(m):
     IDc, _ = m.post_processing(8, None, None, pred, None, {"CUTTING": False, "PRUNING": True, "SPLITTING": True}, data, prob,
                                numbering="canonical")
     assert IDc.numpy().tolist() == [0, 0, 0, 0, 0, 0, 6, 7, 8, 9]
+
+
+def _device_shards(m, src, dst, pred, prob1, n_nodes, world):
+    ei = torch.from_numpy(np.stack([src, dst]).astype(np.int64))
+    rowptr = torch.searchsorted(ei[0].contiguous(), torch.arange(n_nodes + 1))
+    out = []
+    for (n0, n1) in m.partition_rows(rowptr, world):
+        lo, hi = m.shard_edges(ei, n0, n1)
+        g = m.TrackletGraph(ei[:, lo:hi].to(dev()), n_nodes, row_offset=n0, n_rows=n1 - n0)
+        out.append((g, torch.from_numpy(pred[lo:hi].astype(np.uint8)).to(dev()), torch.from_numpy(prob1[lo:hi]).to(dev())))
+    return out
+
+
+@pytest.mark.parametrize("path", POST_FILES, ids=ids(POST_FILES))
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_post_processing_matches_reference_golden(m, path, world):
+    """Row-block shards (in one process): shard compaction, merged active list, rounds, write-back — decisions and label
+    integers bit-exact against the reference's own post_processing outputs, for every flag combination."""
+    g = np.load(path)
+    N, Cn, _ = [int(v) for v in g["spec"]]
+    for tag, cfg in CONFIGS:
+        shards = _device_shards(m, g["src"], g["dst"], g["pred"], g["prob1"], N, world)
+        CONFIG = {"CUTTING": cfg[0], "PRUNING": str(cfg[1]), "SPLITTING": cfg[2]}
+        ID, preds = m.sharded_post_processing(Cn, shards, CONFIG, N, comm=_NoComm())
+        assert np.array_equal(torch.cat(preds).cpu().numpy().astype(np.int64), g["pred_" + tag]), tag
+        assert ID.dtype == torch.int64 and np.array_equal(ID.numpy(), g["labels_" + tag]), tag
+    shards = _device_shards(m, g["src"], g["dst"], g["pred"], g["prob1"], N, world)       # no flag set: initial labels, no change
+    ID, preds = m.sharded_post_processing(Cn, shards, {"CUTTING": False, "PRUNING": False, "SPLITTING": False}, N, comm=_NoComm())
+    assert np.array_equal(ID.numpy(), g["labels_initial"]) and np.array_equal(torch.cat(preds).cpu().numpy(), g["pred"])
+
+
+def test_sharded_post_processing_large_and_edge_cases(m):
+    n_nodes, cams = 20000, 8
+    src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, cams, 5, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03,
+                                                          single_dir=0.05)
+    order = np.lexsort((dst, src))
+    src, dst, prob, pred = src[order], dst[order], prob[order], pred[order]
+    lab_ref, act_ref = po.post_processing_rounds(src, dst, pred, prob, cams, n_nodes, numbering="reference")
+    shards = _device_shards(m, src, dst, pred, prob, n_nodes, 4)
+    single = m.sharded_post_processing(cams, shards[0], {"CUTTING": False, "PRUNING": False, "SPLITTING": False}, n_nodes,
+                                       comm=_NoComm())                                     # a bare triple -> a bare tensor back
+    assert isinstance(single[1], torch.Tensor) and single[1].data_ptr() == shards[0][1].data_ptr()
+    ID, preds = m.sharded_post_processing(cams, shards, {"CUTTING": True, "PRUNING": True, "SPLITTING": True}, n_nodes, comm=_NoComm())
+    assert np.array_equal(torch.cat(preds).cpu().numpy().astype(np.int64), act_ref) and np.array_equal(ID.numpy(), lab_ref)
+    assert np.bincount(ID.numpy()).max() <= cams
+    IDc, _ = m.sharded_post_processing(cams, _device_shards(m, src, dst, pred, prob, n_nodes, 4),
+                                       {"CUTTING": True, "PRUNING": True, "SPLITTING": True}, n_nodes, comm=_NoComm(),
+                                       numbering="canonical")
+    assert same_partition(IDc.numpy(), lab_ref)
+    # nothing active anywhere: every node its own cluster, decisions untouched
+    shards = _device_shards(m, src, dst, 0 * pred, prob, n_nodes, 2)
+    ID, preds = m.sharded_post_processing(cams, shards, {"CUTTING": True, "PRUNING": True, "SPLITTING": True}, n_nodes, comm=_NoComm())
+    assert ID.tolist() == list(range(n_nodes)) and not any(bool(p.any()) for p in preds)
+    with pytest.raises(ValueError):
+        m.sharded_post_processing(cams, (shards[0][0], shards[0][1].long(), shards[0][2]), {"CUTTING": True, "PRUNING": True,
+                                                                                              "SPLITTING": True}, n_nodes, comm=_NoComm())
+    with pytest.raises(RuntimeError):
+        m.sharded_post_processing(cams, (shards[0][0], shards[0][1].cpu(), shards[0][2]), {"CUTTING": True, "PRUNING": True,
+                                                                                             "SPLITTING": True}, n_nodes, comm=_NoComm())
 
 
 def test_multi_gpu_fused_collectives_torchrun(m):
