@@ -456,6 +456,31 @@ def run_ours(args):
     e2e_ei_ms = e2e_loop(e2e_edge_index)
     e2e_ms = e2e_loop(e2e_cameras)
     batch.mpn_graph = None
+    # Throughput of a STREAM of host-resident graphs (the reference loops over one-graph batches, inference.py:375): GraphStream
+    # keeps two graphs in flight so the PCIe copies of neighbouring graphs overlap the kernels.  Every graph still pays its own
+    # H2D (features + camera ids) and D2H (decisions) inside the timed region; the region closes after the last D2H.
+    pipe_ms, pipe_depth, n_pipe = None, 2, max(args.steps, 3)
+    if world == 1:
+        gs = m.GraphStream(net, dev, depth=pipe_depth)
+        hpreds = [torch.empty(E_local, dtype=torch.uint8).pin_memory() for _ in range(pipe_depth + 1)]
+
+        def run_pipe(k):
+            for i in range(k):
+                gs.submit(hx, cam_host, hpreds[i % len(hpreds)])
+            gs.drain(host_sync=False)
+
+        run_pipe(3)
+        flush.fill_(1)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run_pipe(n_pipe)
+        b.record()
+        barrier()
+        pipe_ms = a.elapsed_time(b) / n_pipe
+        gs.drain()
+        if not torch.equal(hpreds[(n_pipe - 1) % len(hpreds)], hpred):
+            raise RuntimeError("GraphStream decisions differ from the one-at-a-time call")
     h2d = hx.numel() * 4 + cam_host.size * 8
     d2h = hpred.numel()
 
@@ -469,10 +494,17 @@ def run_ours(args):
                                        (n_nodes, CAMS, E_total, "" if world == 1 else " row-block sharded over %d GPUs" % world),
                            "l2": "256 MiB flush between timed iterations; inputs (edge_index 235 MB) exceed L2",
                            "timing": "CUDA events per step on the launching stream, max over ranks, summed over steps"},
-                "e2e": {"value": E_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms,
+                "e2e": {"value": E_total / ((pipe_ms or e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": pipe_ms or e2e_ms,
                         "inputs": "host node features [N,2048] f32 + camera ids (graph tables built on the device; one "
                                   "MOTMPNet.forward call with data.edge_attr=None, i.e. edge features computed inside it)",
+                        "how": ("GraphStream(depth=%d): %d graphs submitted back to back from pinned host memory, timed from the first "
+                                "H2D to the last D2H (CUDA events); the H2D / D2H of neighbouring graphs overlap the kernels, every "
+                                "graph pays its own copies; no L2 flush (each graph's ~600 MB of edge arrays exceed L2)"
+                                % (pipe_depth, n_pipe)) if pipe_ms else
+                               "one graph at a time: H2D, kernels, D2H serial; median over the timed calls, max over ranks",
+                        "one_at_a_time": {"value": E_total / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
+                                          "how": "H2D, kernels, D2H serial per call, barrier + L2 flush between calls; median"},
                         "int64_edge_index": {"value": E_total / (e2e_ei_ms * 1e-3), "ms_per_step": e2e_ei_ms,
                                              "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8}},
                 "gpu_launches": int(launches), "clocks": clk}

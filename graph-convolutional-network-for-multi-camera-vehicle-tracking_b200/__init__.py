@@ -6,6 +6,7 @@ Public surface (same names as the reference where one exists):
     post_processing              inference.py:70
     pruning, splitting, remove_edges_single_direction, compute_SCC_and_Clusters      utils.py
     ShardedMPN                   row-block sharded forward across the GPUs of one box (new)
+    GraphStream                  a stream of host-resident graphs: PCIe copies of neighbouring graphs overlap the kernels (new)
     sharded_post_processing      post_processing for row-block shards: active lists merged across ranks (new)
     compute_P_R_F                inference.py:20-66
     evaluation.{adjusted_rand_score, adjusted_mutual_info_score, homogeneity_score, completeness_score, v_measure_score}
@@ -23,6 +24,7 @@ from .graph_inputs import (edge_labels, load_packed_features, normalize_columns,
 from .edge_features import edge_features
 from .graph import TrackletGraph, graph_for
 from .mpn import MOTMPNet
+from .pipeline import GraphStream
 from .sharded import (CudaPhases, CudaPostOps, ShardedMPN, partition_rows, shard_edges, sharded_forward,
                       sharded_post_processing)
 from .postprocess import (compute_SCC_and_Clusters, post_processing, pruning, remove_edges_single_direction,
@@ -30,6 +32,6 @@ from .postprocess import (compute_SCC_and_Clusters, post_processing, pruning, re
 
 __all__ = ["MOTMPNet", "edge_features", "post_processing", "pruning", "splitting", "remove_edges_single_direction",
            "compute_SCC_and_Clusters", "TrackletGraph", "graph_for", "ShardedMPN", "CudaPhases", "sharded_forward", "partition_rows",
-           "shard_edges", "sharded_post_processing", "CudaPostOps", "_lib", "evaluation", "compute_P_R_F", "clustering_scores", "relabel_detections", "tracking_table",
+           "shard_edges", "GraphStream", "sharded_post_processing", "CudaPostOps", "_lib", "evaluation", "compute_P_R_F", "clustering_scores", "relabel_detections", "tracking_table",
            "save_mtmc", "edge_labels", "normalize_columns", "pack_reid_features", "pack_reid_features_from_pickles",
            "read_packed_features", "load_packed_features"]

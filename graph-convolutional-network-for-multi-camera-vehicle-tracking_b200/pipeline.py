@@ -1,0 +1,127 @@
+"""Throughput path for a stream of tracklet graphs held in HOST memory.
+
+The reference driver handles one graph per loop iteration (``for data in val_loader`` with batch size 1,
+inference.py:375): load the tracklets' ReID features, ``.cuda()`` them (inference.py:399), build the graph, run the MPN
+(inference.py:469), read the decisions back (inference.py:482-485).  Done one graph at a time, the PCIe copies either side of
+the kernels are serial time (configs[1]: 0.6 ms in, 0.27 ms out, around 0.9 ms of kernels).  ``GraphStream`` keeps ``depth``
+graphs in flight on three CUDA streams so that the host->device copy of graph i+1 and the device->host copy of graph i-1
+overlap the kernels of graph i; every graph still pays its own copies, they just stop being serial.
+
+Nothing here computes: it is stream / event / buffer plumbing around ``TrackletGraph.from_cameras`` and
+``MOTMPNet.forward`` (edge features inside the call), which run unchanged on the caller's current stream.
+"""
+import torch
+
+from .graph import TrackletGraph
+
+
+class _Slot:
+    __slots__ = ("x_dev", "in_done", "compute_done", "out_done", "keep", "busy")
+
+    def __init__(self):
+        self.x_dev = None
+        self.in_done = torch.cuda.Event()
+        self.compute_done = torch.cuda.Event()
+        self.out_done = torch.cuda.Event()
+        self.keep = None             # device tensors of the graph in flight (outputs of the forward, graph tables)
+        self.busy = False
+
+
+class GraphStream:
+    """``submit`` enqueues one graph (pinned host features + camera ids in, pinned host decisions out) and returns without
+    waiting; ``drain`` waits for everything submitted.  A slot's buffers are reused ``depth`` submits later; the stream /
+    event order guarantees the previous occupant's copies have finished by then, so the caller must have consumed a
+    ``pred_host`` buffer before passing the same buffer to a submit ``depth`` calls later (or simply use ``depth + 1`` buffers).
+    """
+
+    def __init__(self, model, device, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.model, self.device, self.depth = model, torch.device(device), int(depth)
+        if self.device.type != "cuda":
+            raise RuntimeError("GraphStream needs a CUDA device: the B200 path has no CPU fallback")
+        self.copy_in = torch.cuda.Stream(self.device)
+        self.copy_out = torch.cuda.Stream(self.device)
+        self.slots = [_Slot() for _ in range(self.depth)]
+        self.n_submitted = 0
+
+    def submit(self, x_host, cam_ids, pred_host, prob_host=None):
+        """``x_host``: pinned fp32 [N, D] (column-normalised ReID features, inference.py:403-404); ``cam_ids``: host sequence of
+        per-node camera ids, nodes grouped by ascending camera (dataset.py:279-281); ``pred_host``: pinned uint8 [E] that
+        receives argmax(logits) (inference.py:479) in the graph's edge order; ``prob_host``: optional pinned fp32 [E] for
+        softmax(logits)[:, 1] (inference.py:475-477).  Returns the ticket to pass to ``wait``."""
+        if x_host.is_cuda or pred_host.is_cuda or not (x_host.is_pinned() and pred_host.is_pinned()):
+            raise ValueError("GraphStream.submit takes pinned HOST tensors (x_host, pred_host)")
+        if x_host.dtype != torch.float32 or x_host.dim() != 2 or not x_host.is_contiguous():
+            raise ValueError("x_host must be a contiguous float32 [N, D] tensor")
+        dev = self.device
+        compute = torch.cuda.current_stream(dev)
+        slot = self.slots[self.n_submitted % self.depth]
+        ticket = self.n_submitted
+        with torch.cuda.device(dev):
+            if slot.x_dev is None or slot.x_dev.shape != x_host.shape:
+                if slot.busy:
+                    slot.compute_done.synchronize()
+                slot.x_dev = torch.empty(x_host.shape, dtype=torch.float32, device=dev)
+                self.copy_in.wait_stream(compute)          # the allocator may hand out memory this stream still uses
+            if slot.busy:
+                compute.wait_event(slot.out_done)            # the previous occupant's outputs have left the device: free them
+            slot.keep = None
+            g = TrackletGraph.from_cameras(cam_ids, dev)   # K0 on the device (does not need x): only the camera layout crosses PCIe
+            if pred_host.numel() != g.n_edges or pred_host.dtype != torch.uint8:
+                raise ValueError("pred_host must be uint8 with one entry per edge (%d)" % g.n_edges)
+            if prob_host is not None and (prob_host.numel() != g.n_edges or prob_host.dtype != torch.float32
+                                          or not prob_host.is_pinned()):
+                raise ValueError("prob_host must be pinned float32 with one entry per edge")
+            if g.n_cols != x_host.shape[0]:
+                raise ValueError("cam_ids has %d entries, x_host %d rows" % (g.n_cols, x_host.shape[0]))
+            if slot.busy:
+                self.copy_in.wait_event(slot.compute_done)   # the previous occupant's kernels have read x_dev
+            with torch.cuda.stream(self.copy_in):
+                slot.x_dev.copy_(x_host, non_blocking=True)
+                slot.in_done.record(self.copy_in)
+            compute.wait_event(slot.in_done)
+            data = _Batch()
+            data.x, data.mpn_graph, data.edge_attr, data.num_nodes = slot.x_dev, g, None, g.n_cols
+            fuse = self.model.fuse_decisions
+            self.model.fuse_decisions = True
+            try:
+                self.model(data)
+            finally:
+                self.model.fuse_decisions = fuse
+            pred, prob1 = self.model.last_pred, self.model.last_prob1
+            slot.compute_done.record(compute)
+            self.copy_out.wait_event(slot.compute_done)
+            with torch.cuda.stream(self.copy_out):
+                pred_host.copy_(pred, non_blocking=True)
+                if prob_host is not None:
+                    prob_host.copy_(prob1, non_blocking=True)
+                slot.out_done.record(self.copy_out)
+            slot.keep = (g, pred, prob1, data)
+            slot.busy = True
+        self.n_submitted += 1
+        return ticket
+
+    def wait(self, ticket: int):
+        """Blocks the host until the decisions of ``ticket`` are in its ``pred_host``."""
+        if not 0 <= ticket < self.n_submitted:
+            raise ValueError("unknown ticket")
+        # a reused slot's event belongs to a later graph: the copy-out stream is in order, so that one implies this one
+        self.slots[ticket % self.depth].out_done.synchronize()
+
+    def drain(self, host_sync: bool = True):
+        """Orders the caller's current stream after every outstanding copy (so an event recorded next on that stream closes a
+        timed region around the whole pipeline) and, with ``host_sync``, blocks the host until they are done."""
+        compute = torch.cuda.current_stream(self.device)
+        for slot in self.slots:
+            if slot.busy:
+                compute.wait_event(slot.out_done)
+        if host_sync:
+            for slot in self.slots:
+                if slot.busy:
+                    slot.out_done.synchronize()
+                    slot.keep = None
+
+
+class _Batch:
+    """Attribute bag standing in for torch_geometric.data.Data (inference.py:458)."""

@@ -363,6 +363,37 @@ def test_forward_computes_edge_features_when_absent(m):
     assert torch.equal(d3.edge_attr, m.edge_features(x.to(dev()), ei.to(dev())))
 
 
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_graph_stream_pipelined_copies_match_direct_forward(m, depth):
+    """GraphStream: several graphs of different shapes in flight (H2D / kernels / D2H on three streams) give the same bits as
+    one direct forward per graph; buffers are reused every ``depth`` submits."""
+    params = mo.shipped_model_params(1, 1, 64, (48, 40))
+    sd = mo.init_weights(params, "resnet101", 21)
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev()).eval()
+    net.fuse_decisions = True
+    cases = []
+    for (N, Cn, seed) in [(200, 4, 1), (2048, 4, 2), (200, 4, 3), (330, 3, 4), (2048, 4, 5), (2048, 4, 6), (200, 4, 7)]:
+        x, ei, cam, _ = mo.synth_graph(N, Cn, seed, D=64, planted=True)
+        d = Data(x=x.to(dev()), edge_index=ei.to(dev()))
+        net(d)
+        cases.append((x.pin_memory(), cam.numpy(), net.last_pred.cpu(), net.last_prob1.cpu(), ei.shape[1]))
+    gs = m.GraphStream(net, dev(), depth=depth)
+    outs = [(torch.zeros(c[4], dtype=torch.uint8).pin_memory(), torch.zeros(c[4], dtype=torch.float32).pin_memory()) for c in cases]
+    tickets = [gs.submit(c[0], c[1], o[0], o[1]) for c, o in zip(cases, outs)]
+    gs.wait(tickets[0])
+    assert torch.equal(outs[0][0], cases[0][2])
+    gs.drain()
+    for c, o in zip(cases, outs):
+        assert torch.equal(o[0], c[2]) and torch.equal(o[1], c[3])
+    assert net.fuse_decisions is True
+    with pytest.raises(ValueError):
+        gs.submit(cases[0][0].clone(), cases[0][1], outs[0][0])                 # not pinned
+    with pytest.raises(ValueError):
+        gs.submit(cases[0][0], cases[0][1], outs[1][0])                         # wrong number of edges
+
+
 class _NoComm:
     world, rank = 1, 0
 
