@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph
 // map, fixed shuffle tree, fixed task order).
 // ------------------------------------------------------------------------------------------------
 constexpr int ATC_THREADS = 128;
-constexpr int ATC_CTAS_PER_SM = 4;
+constexpr int ATC_CTAS_PER_SM = 5;                       // 40.6 KB shared memory, 89 registers, 64 TMEM columns per block
 constexpr int ATC_SEG = 128;                             // task ranges staged in shared memory per segment
 constexpr int ATC_NB = 2;                                // 128-edge batches per iteration (one barrier / fence / commit for both)
 constexpr int ATC_D = 4;                                 // y runs D batches ahead
@@ -824,6 +824,11 @@ constexpr int ATC_RL = ATC_D + 1;                        // ring slots
 constexpr int ATC_SLOT_BYTES = 128 * 16;
 // canonical K-major no-swizzle operand tile: [rows/8 groups][2 K-cores][8 rows][4 floats]
 __device__ __forceinline__ int tile_off(int row, int kcore) { return (row >> 3) * 64 + kcore * 32 + (row & 7) * 4; }
+// edge-operand tile of the apply sweep: THREE K-core blocks per 8-row group, [e'_lo | e'_hi | 1 1 0 0].  E1 = [e'_lo | e'_hi]
+// starts at block 0, E2 = [e'_hi | 1 1 0 0] at block 1 (same LBO = 128 B, SBO = 384 B): e'_hi is stored once and read by both
+// MMAs (2 instead of 3 shared-memory stores per edge, 6 instead of 8 KB per 128-edge batch -> a 5th block per SM fits).
+constexpr int ATC_GROUP_BYTES = 3 * 128;
+constexpr int ATC_TILE_BYTES = 16 * ATC_GROUP_BYTES;
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   // round-to-nearest (ties away) to 10 mantissa bits without cvt.rna.tf32 (which ptxas expands to 4 instructions with an
   // inf/nan guard): finite inputs only.  The tensor core reads the top 19 bits of lo: error ~2^-22 |v|.
@@ -865,13 +870,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-template <bool CLASSIFY, bool DECIDE, bool AGGMAX>
-__global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
+template <bool CLASSIFY, bool DECIDE, bool AGGMAX, int CTAS>
+__global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
     const mpn_graph g, const float4* __restrict__ ybuf, const float* __restrict__ A, const float* __restrict__ consts,
     float* __restrict__ msg_task, float2* __restrict__ logits, uint8_t* __restrict__ pred, float* __restrict__ prob1) {
   __shared__ EdgeConsts sc;
-  __shared__ __align__(128) float e1[2 * ATC_NB][128 * 8];            // [buffer][half]
-  __shared__ __align__(128) float e2[2 * ATC_NB][128 * 8];
+  __shared__ __align__(128) float et[2 * ATC_NB][ATC_TILE_BYTES / 4];  // [buffer][half]: [e'_lo | e'_hi | 1 1 0 0] per 8-row group
   __shared__ __align__(128) float w1[32 * 8];
   __shared__ __align__(128) float w2[32 * 8];
   __shared__ __align__(16) float4 ring[ATC_RL][ATC_THREADS];
@@ -906,16 +910,16 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
   const uint32_t tmem = tmem_slot;
   constexpr uint32_t IDESC = make_idesc_tf32(128, 32);
   const uint64_t d_w1 = make_smem_desc_noswizzle(smem_u32(w1), 128, 256), d_w2 = make_smem_desc_noswizzle(smem_u32(w2), 128, 256);
-  const uint64_t d_e1 = make_smem_desc_noswizzle(smem_u32(e1[0]), 128, 256), d_e2 = make_smem_desc_noswizzle(smem_u32(e2[0]), 128, 256);
-  constexpr uint64_t BUF_STEP = (128 * 8 * sizeof(float)) >> 4;          // second operand buffer, in descriptor address units
+  const uint64_t d_e1 = make_smem_desc_noswizzle(smem_u32(et[0]), 128, ATC_GROUP_BYTES);            // [e'_lo | e'_hi]
+  const uint64_t d_e2 = make_smem_desc_noswizzle(smem_u32(et[0]) + 128, 128, ATC_GROUP_BYTES);      // [e'_hi | 1 1 0 0]
+  constexpr uint64_t BUF_STEP = ATC_TILE_BYTES >> 4;                     // next operand buffer, in descriptor address units
   const uint32_t my_tmem = opaque_u32(tmem + ((uint32_t)(warp * 32) << 16));
-  const uint32_t e1_addr = opaque_u32(smem_u32(&e1[0][tile_off(tid, 0)]));     // K-core 1 of the same row: + 128 bytes
-  const uint32_t e2_addr = opaque_u32(smem_u32(&e2[0][tile_off(tid, 0)]));
+  const uint32_t et_addr = opaque_u32(smem_u32(et[0]) + (uint32_t)((tid >> 3) * ATC_GROUP_BYTES + (tid & 7) * 16));   // this edge's row of block 0
   const uint32_t ring_addr = opaque_u32(smem_u32(&ring[0][tid]));
-  constexpr uint32_t TILE_BYTES = 128 * 8 * sizeof(float);
+  constexpr uint32_t TILE_BYTES = ATC_TILE_BYTES;
 #pragma unroll
   for (int i = 0; i < 2 * ATC_NB; ++i)                   // the two "1" columns never change
-    *reinterpret_cast<float4*>(&e2[i][tile_off(tid, 1)]) = make_float4(1.f, 1.f, 0.f, 0.f);
+    sts128(et_addr + (uint32_t)i * TILE_BYTES + 256, 1.f, 1.f, 0.f, 0.f);
   uint32_t phase = 0;
   const int n_tasks = *g.n_tasks;
   const int per = (n_tasks + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -1028,9 +1032,8 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) apply_tc_kernel(
 #pragma unroll
             for (int k = 0; k < 4; ++k) split_tf32(ep[h][k], eh[k], el[k]);
             const uint32_t boff = (uint32_t)(buf * ATC_NB + h) * TILE_BYTES;
-            sts128(e1_addr + boff, eh[0], eh[1], eh[2], eh[3]);
-            sts128(e1_addr + boff + 128, el[0], el[1], el[2], el[3]);
-            sts128(e2_addr + boff, eh[0], eh[1], eh[2], eh[3]);
+            sts128(et_addr + boff, el[0], el[1], el[2], el[3]);
+            sts128(et_addr + boff + 128, eh[0], eh[1], eh[2], eh[3]);
           }
         }
         if (pending) drain();                            // the previous iteration's MMAs finished while this one was being prepared
@@ -1852,13 +1855,17 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
       if (p->use_tc && apply_tc && stored && g.chunk >= ATC_THREADS && (!classify || (pred_out != nullptr) == (prob1_out != nullptr))) {
         const bool agg_max = p->w.node_agg == MPN_AGG_MAX;
         p->msg_abs = agg_max ? 0 : 1;                      // msg_task holds sum |z|: node_finalize adds the closed-form half
-#define MPN_ATC2(CL, DE, MX) apply_tc_kernel<CL, DE, MX><<<kNumSMs * ATC_CTAS_PER_SM, ATC_THREADS, 0, st>>>(g, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+        const char* ctas_env = getenv("MPN_ATC_CTAS");     // resident blocks per SM: 4 | 5, read per launch (measurements flip it)
+        const int atc_ctas = ctas_env ? (atoi(ctas_env) == 5 ? 5 : 4) : ATC_CTAS_PER_SM;
+#define MPN_ATC3(CL, DE, MX, NC) apply_tc_kernel<CL, DE, MX, NC><<<kNumSMs * NC, ATC_THREADS, 0, st>>>(g, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_ATC2(CL, DE, MX) do { if (atc_ctas == 5) MPN_ATC3(CL, DE, MX, 5); else MPN_ATC3(CL, DE, MX, 4); } while (0)
 #define MPN_ATC(CL, DE) do { if (agg_max) MPN_ATC2(CL, DE, true); else MPN_ATC2(CL, DE, false); } while (0)
         if (!classify) MPN_ATC(false, false);
         else if (pred_out && prob1_out) MPN_ATC(true, true);
         else MPN_ATC(true, false);
 #undef MPN_ATC
 #undef MPN_ATC2
+#undef MPN_ATC3
         break;
       }
 #define MPN_APPLY2(YS, CL, MX) apply_kernel<YS, CL, false, MX><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
