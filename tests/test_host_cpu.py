@@ -89,3 +89,16 @@ def test_host_reference_numbering_matches_oracle():
         ref, nref = po.scc_labels_reference(s, d, np.ones(s.size), n)
         lab, nc = m.compute_SCC_and_Clusters(list(zip(s.tolist(), d.tolist())), n)
         assert nc == nref and np.array_equal(lab.numpy(), ref)
+
+
+def test_stream_and_sharded_post_refuse_cpu():
+    """The throughput pipeline and the sharded post-processing are CUDA-only like the rest of the product path."""
+    from types import SimpleNamespace
+    net = m.MOTMPNet(copy.deepcopy(mo.shipped_model_params(1, 1, 64, (48,))), None, "resnet101").eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.GraphStream(net, "cpu")
+    with pytest.raises(ValueError):
+        m.GraphStream(net, "cuda:0", depth=0)
+    g = SimpleNamespace(n_edges=4, perm=None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.CudaPostOps().compact(g, torch.ones(4, dtype=torch.uint8), torch.rand(4))
