@@ -147,13 +147,28 @@ def test_sharded_post_processing_no_active_edges():
     assert ID.tolist() == list(range(n_nodes)) and not any(bool(p.any()) for p in preds)
 
 
-def _post_worker(rank, world, port, q):
+def test_sharded_post_processing_default_comm_without_process_group():
+    """comm=None outside torch.distributed: a world of one, the whole graph as a single shard."""
+    import numpy as np
+    from oracle import postproc_oracle as po
+    src, dst, prob, pred, n_nodes, cams = _post_case(seed=11)
+    ref_lab, ref_act = po.post_processing_rounds(src, dst, pred, prob, cams, n_nodes, numbering="reference")
+    (_lo, _hi, triple), = _post_shards(src, dst, prob, pred, n_nodes, 1)
+    ID, p = m.sharded_post_processing(cams, triple, {"CUTTING": True, "PRUNING": True, "SPLITTING": True}, n_nodes, ops=FakePostOps())
+    assert np.array_equal(p.numpy().astype(np.int64), ref_act) and np.array_equal(ID.numpy(), ref_lab)
+
+
+def _post_worker(rank, world, port, q, empty_rank=-1):
     import numpy as np
     from oracle import postproc_oracle as po
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         src, dst, prob, pred, n_nodes, cams = _post_case(seed=7)
+        if empty_rank >= 0:                                # one rank contributes an EMPTY active list to the ragged all-gather
+            lo, hi, _ = _post_shards(src, dst, prob, pred, n_nodes, world)[empty_rank]
+            pred = pred.copy()
+            pred[lo:hi] = 0
         ref_lab, ref_act = po.post_processing_rounds(src, dst, pred, prob, cams, n_nodes, numbering="reference")
         lo, hi, triple = _post_shards(src, dst, prob, pred, n_nodes, world)[rank]
         ID, p = m.sharded_post_processing(cams, triple, {"CUTTING": "True", "PRUNING": True, "SPLITTING": True}, n_nodes,
@@ -164,11 +179,12 @@ def _post_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_post_processing_gloo_world2():
+@pytest.mark.parametrize("empty_rank", [-1, 1])
+def test_sharded_post_processing_gloo_world2(empty_rank):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_post_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 31500 + (os.getpid() % 2000) + (7 if empty_rank >= 0 else 0)
+    procs = [ctx.Process(target=_post_worker, args=(r, 2, port, q, empty_rank)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
