@@ -461,7 +461,7 @@ def run_ours(args):
     # H2D (features + camera ids) and D2H (decisions) inside the timed region; the region closes after the last D2H.
     pipe_ms, pipe_depth, n_pipe = None, 2, max(args.steps, 3)
     if world == 1:
-        gs = m.GraphStream(net, dev, depth=pipe_depth)
+        gs = m.GraphStream(net, dev, depth=pipe_depth, graph_replay=os.environ.get("MPN_BENCH_GRAPH_REPLAY") == "1")   # experimental knob
         hpreds = [torch.empty(E_local, dtype=torch.uint8).pin_memory() for _ in range(pipe_depth + 1)]
 
         def run_pipe(k):
@@ -469,7 +469,7 @@ def run_ours(args):
                 gs.submit(hx, cam_host, hpreds[i % len(hpreds)])
             gs.drain(host_sync=False)
 
-        run_pipe(3)
+        run_pipe(2 * pipe_depth)                  # every slot used twice (the experimental replay mode captures on the second use)
         flush.fill_(1)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -394,6 +394,32 @@ def test_graph_stream_pipelined_copies_match_direct_forward(m, depth):
         gs.submit(cases[0][0], cases[0][1], outs[1][0])                         # wrong number of edges
 
 
+@pytest.mark.skipif(__import__("os").environ.get("MPN_TEST_EXPERIMENTAL") != "1",
+                    reason="GraphStream(graph_replay=True) is experimental and not yet validated on hardware; MPN_TEST_EXPERIMENTAL=1 runs it")
+def test_graph_stream_graph_replay_experimental(m):
+    """Slot-level CUDA-graph replay: the third and later submits of one signature per slot are replays; same bits as eager."""
+    params = mo.shipped_model_params(1, 1, 64, (48, 40))
+    sd = mo.init_weights(params, "resnet101", 21)
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev()).eval()
+    net.fuse_decisions = True
+    for N in (200, 2048):                                                      # small-graph path and large-graph path
+        xs, refs, cam = [], [], None
+        for seed in range(6):
+            x, ei, cam, _ = mo.synth_graph(N, 4, seed, D=64, planted=True)
+            net(Data(x=x.to(dev()), edge_index=ei.to(dev())))
+            xs.append(x.pin_memory()); refs.append(net.last_pred.cpu())
+        gs = m.GraphStream(net, dev(), depth=2, graph_replay=True)
+        outs = [torch.zeros(refs[0].numel(), dtype=torch.uint8).pin_memory() for _ in xs]
+        for x, o in zip(xs, outs):                                            # per slot: eager, capture + replay, replay
+            gs.submit(x, cam.numpy(), o)
+        gs.drain()
+        assert all(s.cap is not None for s in gs.slots)
+        for o, r in zip(outs, refs):
+            assert torch.equal(o, r)
+
+
 class _NoComm:
     world, rank = 1, 0
 
