@@ -138,6 +138,21 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- synthetic graph
+def workload_shape(world):
+    """(tracklets, directed edges) of the bench workload on ``world`` GPUs: configs[1] at 1 GPU, E per GPU ~ constant above."""
+    if world == 1:
+        n = NODES_1GPU
+    else:
+        n = int(round(NODES_1GPU * world ** 0.5 / (CAMS * world))) * CAMS * world           # weak scaling
+    return n, n * (n - n // CAMS)                                                            # equal cameras, all cross-camera pairs
+
+
+def workload_name(n_nodes, e_total, world):
+    return ("BASELINE configs[1]: L=1 MPN (shipped config) + edge features + decisions, %d tracklets, %d cameras, dense "
+            "cross-camera edges, E=%d directed edges%s" %
+            (n_nodes, CAMS, e_total, "" if world == 1 else " row-block sharded over %d GPUs" % world))
+
+
 def device_graph(n_nodes, cams, seed, dev, row_block=None):
     """Graph(N,C,seed) of SURVEY.md section 8d built on the device.  row_block=(n0,n1) builds only that shard's edges."""
     g = torch.Generator(device=dev).manual_seed(seed)
@@ -217,10 +232,14 @@ def run_reference_arm(args):
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     v = info["value"]
+    world = max(int(args.gpus), 1)
+    n_nodes, e_total = workload_shape(world)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / max(len(times), 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "L=1 MPN + edge features, %d tracklets x %d cameras (bounded CPU sample of configs[1])" % (2048, 8)},
+            "config": {"workload": workload_name(n_nodes, e_total, world),
+                       "sample": "each step = one bounded CPU sample of that workload: the same model and graph family at "
+                                 "2048 tracklets x %d cameras, rate per directed edge (see cpu_baseline.sample)" % CAMS},
             "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -343,13 +362,9 @@ def run_ours(args):
     peaks = load_peaks()
     net = make_model(dev)
 
-    if world == 1:
-        n_nodes = NODES_1GPU
-        blocks = [(0, n_nodes)]
-    else:
-        n_nodes = int(round(NODES_1GPU * world ** 0.5 / (CAMS * world))) * CAMS * world     # weak scaling: E/GPU ~ constant
-        per = n_nodes // world
-        blocks = [(r * per, (r + 1) * per) for r in range(world)]
+    n_nodes, e_expected = workload_shape(world)
+    per = n_nodes // world
+    blocks = [(r * per, (r + 1) * per) for r in range(world)]
     x, ei = device_graph(n_nodes, CAMS, 0, dev, row_block=blocks[rank])
     E_local = ei.shape[1]
     tot = torch.tensor([E_local], dtype=torch.float64, device=dev)
@@ -489,9 +504,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: L=1 MPN (shipped config) + edge features + decisions, %d tracklets, "
-                                       "%d cameras, dense cross-camera edges, E=%d directed edges%s" %
-                                       (n_nodes, CAMS, E_total, "" if world == 1 else " row-block sharded over %d GPUs" % world),
+                "config": {"workload": workload_name(n_nodes, E_total, world),
                            "l2": "256 MiB flush between timed iterations; inputs (edge_index 235 MB) exceed L2",
                            "timing": "CUDA events per step on the launching stream, max over ranks, summed over steps"},
                 "e2e": {"value": E_total / ((pipe_ms or e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
