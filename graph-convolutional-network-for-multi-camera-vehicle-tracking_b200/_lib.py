@@ -78,6 +78,7 @@ _PROTOS = {
     "mpn_last_error": (C.c_char_p, []),
     "mpn_kernel_launches": (C.c_uint64, []),
     "mpn_check_device": (C.c_int, [C.c_int]),
+    "mpn_set_pdl": (C.c_int, [C.c_int]),
     "mpn_graph_build": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p]),
     "mpn_graph_build_i32": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_graph_build_deferred": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -4,9 +4,12 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="${HERE}/../libmpn_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3 ${MPN_NVCC_EXTRA:-})
+# MPN_PDL=1: compile the experimental programmatic-dependent-launch support in (common.cuh); default 0 = plain launches
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3 -DMPN_PDL=${MPN_PDL:-0} ${MPN_NVCC_EXTRA:-})
 OBJ="${HERE}/_obj"
 mkdir -p "${OBJ}"
+# objects built with other flags are stale
+if [ "$(cat "${OBJ}/.flags" 2>/dev/null)" != "${FLAGS[*]}" ]; then rm -f "${OBJ}"/*.o; echo "${FLAGS[*]}" > "${OBJ}/.flags"; fi
 pids=()
 for f in graph gemm_simt gemm_tc gemm_api edge_features mpn_forward postproc eval; do
   if [ ! -f "${OBJ}/${f}.o" ] || [ "${HERE}/${f}.cu" -nt "${OBJ}/${f}.o" ] || [ "${HERE}/common.cuh" -nt "${OBJ}/${f}.o" ] || \

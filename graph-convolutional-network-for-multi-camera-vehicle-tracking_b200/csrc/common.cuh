@@ -66,7 +66,45 @@ struct Arena {
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (EXPERIMENTAL, compiled out unless the library is built with -DMPN_PDL=1, i.e.
+// `MPN_PDL=1 csrc/build.sh`; then still off until mpn_set_pdl(1) / MPN_PDL_LAUNCH=1).  A kernel launched through launch()
+// with the attribute may be scheduled while its predecessor in the stream drains; its first statement, pdl_wait()
+// (griddepcontrol.wait), blocks every thread until the predecessor grid has completed and its writes are visible, so only
+// the launch latency overlaps.  Rule: pdl_wait() is the FIRST statement of every kernel launched through launch(), before any
+// early return (a grid whose blocks all skipped it would let its own successor overtake the predecessor).
+#ifndef MPN_PDL
+#define MPN_PDL 0
+#endif
+extern int g_pdl_launch;             // run-time switch (only read when MPN_PDL=1)
+
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() {
+#if MPN_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... Params, typename... Args>
+static inline void launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+#if MPN_PDL
+  if (g_pdl_launch) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);     // errors surface through MPN_LAUNCH_OK()
+    return;
+  }
+#endif
+  kernel<<<grid, block, smem, st>>>(static_cast<Args&&>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

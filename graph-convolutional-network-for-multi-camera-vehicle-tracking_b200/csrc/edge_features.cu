@@ -20,6 +20,7 @@ constexpr float REFINE_FRACTION = 0.25f;
 constexpr int CM_SPLITS = 32;
 __global__ void __launch_bounds__(256) col_mean_partial_kernel(const float* __restrict__ x, int n, int D, int rows_per_split,
                                                                double* __restrict__ part /*[CM_SPLITS][D]*/) {
+  pdl_wait();
   __shared__ double ssum[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(256) col_mean_partial_kernel(const float* __re
   }
 }
 __global__ void col_mean_finalize_kernel(const double* __restrict__ part, int n, int D, float* __restrict__ mu) {
+  pdl_wait();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= D) return;
   double s = 0.0;
@@ -47,6 +49,7 @@ __global__ void col_mean_finalize_kernel(const double* __restrict__ part, int n,
 __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu, int n, int D,
                                                           float* __restrict__ xc, float4* __restrict__ st,
                                                           unsigned int* __restrict__ amax_bits) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -78,6 +81,7 @@ __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restric
 
 // batched graphs: offsets of the per-graph ng x ng Gram blocks (single thread; G <= 65535)
 __global__ void gram_offsets_kernel(const int* __restrict__ graph_nptr, int n_graphs, long long* __restrict__ g_off) {
+  pdl_wait();
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   long long run = 0;
   for (int i = 0; i < n_graphs; ++i) {
@@ -92,6 +96,7 @@ __global__ void gram_offsets_kernel(const int* __restrict__ graph_nptr, int n_gr
 __global__ void __launch_bounds__(256) gram_blockdiag_simt_kernel(const float* __restrict__ X, int N, int K, const int* __restrict__ node_gid,
                                                                   const int* __restrict__ graph_nptr, const long long* __restrict__ g_off,
                                                                   float* __restrict__ Gbuf) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -116,6 +121,7 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
                                                                   const float4* __restrict__ st, int D,
                                                                   float2* __restrict__ edge_attr,
                                                                   int* __restrict__ refine_list, int* __restrict__ refine_count) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -178,6 +184,7 @@ __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_grap
                                                                   const int* __restrict__ refine_list,
                                                                   const int* __restrict__ refine_count,
                                                                   float2* __restrict__ edge_attr) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -270,29 +277,29 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
     return MPN_ERR_WORKSPACE;
   }
   if (g->n_edges == 0) return MPN_OK;
-  col_mean_partial_kernel<<<dim3(div_up(D, 32), CM_SPLITS), 256, 0, st>>>(x, g->n_cols, D, div_up(g->n_cols, CM_SPLITS), L.mu_part);
+  mpn::launch(col_mean_partial_kernel, dim3(div_up(D, 32), CM_SPLITS), 256, 0, st, x, g->n_cols, D, div_up(g->n_cols, CM_SPLITS), L.mu_part);
   MPN_LAUNCH_OK();
-  col_mean_finalize_kernel<<<div_up(D, 128), 128, 0, st>>>(L.mu_part, g->n_cols, D, L.mu);
+  mpn::launch(col_mean_finalize_kernel, div_up(D, 128), 128, 0, st, L.mu_part, g->n_cols, D, L.mu);
   MPN_LAUNCH_OK();
   MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, 2 * 256, st));        // refine_count and amax_bits (adjacent 256-byte slices)
-  center_rows_kernel<<<min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st>>>(x, L.mu, g->n_cols, D, L.xc, L.st, L.amax_bits);
+  mpn::launch(center_rows_kernel, min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st, x, L.mu, g->n_cols, D, L.xc, L.st, L.amax_bits);
   MPN_LAUNCH_OK();
   if (g->n_graphs > 1 && g->node_gid && g->graph_nptr) {
     // batched small graphs: block-diagonal Gram (one ng x ng block per graph), same epilogue
     MPN_REQUIRE(g->row_offset == 0 && g->n_cols == g->n_nodes && g->max_graph_nodes > 0, "batched edge features: bad graph");
-    gram_offsets_kernel<<<1, 32, 0, st>>>(g->graph_nptr, g->n_graphs, L.g_off);
+    mpn::launch(gram_offsets_kernel, 1, 32, 0, st, g->graph_nptr, g->n_graphs, L.g_off);
     MPN_LAUNCH_OK();
     if (use_tc && gemm_tc_supported(g->n_cols, 64, D) && g->n_graphs <= 65535) {
       MPN_TRY(gram_blockdiag_tc(L.xc, g->n_cols, D, g->graph_nptr, L.g_off, g->n_graphs, g->max_graph_nodes, L.G, L.gemm_ws,
                                 L.gemm_ws_bytes, st, (const float*)L.amax_bits));
     } else {
-      gram_blockdiag_simt_kernel<<<kNumSMs * 8, 256, 0, st>>>(L.xc, g->n_cols, D, g->node_gid, g->graph_nptr, L.g_off, L.G);
+      mpn::launch(gram_blockdiag_simt_kernel, kNumSMs * 8, 256, 0, st, L.xc, g->n_cols, D, g->node_gid, g->graph_nptr, L.g_off, L.G);
       MPN_LAUNCH_OK();
     }
-    edge_feature_gather_kernel<<<kNumSMs * 8, 256, 0, st>>>(*g, 0, g->n_nodes, L.G, L.g_off, L.st, D, (float2*)edge_attr, L.refine_list,
+    mpn::launch(edge_feature_gather_kernel, kNumSMs * 8, 256, 0, st, *g, 0, g->n_nodes, L.G, L.g_off, L.st, D, (float2*)edge_attr, L.refine_list,
                                                            L.refine_count);
     MPN_LAUNCH_OK();
-    edge_feature_refine_kernel<<<kNumSMs * 4, 256, 0, st>>>(*g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
+    mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
     MPN_LAUNCH_OK();
     return MPN_OK;
   }
@@ -303,11 +310,11 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
       MPN_TRY(gram_nt_tc(L.xc, g->row_offset + r0, L.G, r1 - r0, g->n_cols, D, (const float*)L.amax_bits, L.gemm_ws, L.gemm_ws_bytes, st));
     else
       MPN_TRY(gemm_nt_simt(Ablk, L.xc, nullptr, nullptr, nullptr, L.G, r1 - r0, g->n_cols, D, st));
-    edge_feature_gather_kernel<<<kNumSMs * 8, 256, 0, st>>>(*g, r0, r1, L.G, nullptr, L.st, D, (float2*)edge_attr,
+    mpn::launch(edge_feature_gather_kernel, kNumSMs * 8, 256, 0, st, *g, r0, r1, L.G, nullptr, L.st, D, (float2*)edge_attr,
                                                            L.refine_list, L.refine_count);
     MPN_LAUNCH_OK();
   }
-  edge_feature_refine_kernel<<<kNumSMs * 4, 256, 0, st>>>(*g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
+  mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }

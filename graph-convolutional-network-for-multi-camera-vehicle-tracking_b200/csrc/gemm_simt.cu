@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(GT) gemm_nt_simt_kernel(const float* __restric
                                                           const float* __restrict__ bias, const float* __restrict__ a_scale,
                                                           const float* __restrict__ a_shift, const int* __restrict__ row_gid,
                                                           float* __restrict__ C, int M, int N, int K) {
+  pdl_wait();
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -98,9 +99,9 @@ int gemm_nt_simt(const float* A, const float* B, const float* bias, const float*
   dim3 grid(div_up(N, BN), div_up(M, BM));
   const bool aligned = (K % 4 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
   if (aligned)
-    gemm_nt_simt_kernel<true><<<grid, GT, 0, st>>>(A, B, bias, a_scale, a_shift, row_gid, C, M, N, K);
+    mpn::launch(gemm_nt_simt_kernel<true>, grid, GT, 0, st, A, B, bias, a_scale, a_shift, row_gid, C, M, N, K);
   else
-    gemm_nt_simt_kernel<false><<<grid, GT, 0, st>>>(A, B, bias, a_scale, a_shift, row_gid, C, M, N, K);
+    mpn::launch(gemm_nt_simt_kernel<false>, grid, GT, 0, st, A, B, bias, a_scale, a_shift, row_gid, C, M, N, K);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }

@@ -71,6 +71,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                       const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
                       const int* __restrict__ graph_nptr, const long long* __restrict__ g_off,
                       const float* __restrict__ out_scale) {
+  pdl_wait();
   constexpr int BK = F16 ? TC_BK_F16 : TC_BK;            // elements of K per stage (128 bytes either way)
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -224,6 +225,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, long long n4, int K, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, const int* __restrict__ row_gid,
                                                          float4* __restrict__ hi, float4* __restrict__ lo) {
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = x[i];
@@ -262,6 +264,7 @@ __device__ __forceinline__ float f16_scale_of(float amax) {
 }
 __global__ void __launch_bounds__(256) split_f16_kernel(const float4* __restrict__ x, long long n4, const float* __restrict__ amax,
                                                         uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ out_scale) {
+  pdl_wait();
   const float s = f16_scale_of(*amax);
   if (out_scale && blockIdx.x == 0 && threadIdx.x == 0) *out_scale = (1.f / s) * (1.f / s);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -316,7 +319,7 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int K, int box
 int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t st) {
   MPN_REQUIRE(x && hi && lo && n > 0 && (n % 4) == 0, "split_tf32: bad arguments (n must be a positive multiple of 4)");
   MPN_REQUIRE((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "split_tf32: pointers must be 16-byte aligned");
-  split_tf32_kernel<<<(int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256), 256, 0, st>>>((const float4*)x, n / 4, 4, nullptr, nullptr, nullptr, (float4*)hi, (float4*)lo);
+  mpn::launch(split_tf32_kernel, (int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256), 256, 0, st, (const float4*)x, n / 4, 4, nullptr, nullptr, nullptr, (float4*)hi, (float4*)lo);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -341,7 +344,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
   }
   dim3 grid(div_up(N, BN), div_up(M, TC_BM));
   if (graph_nptr) grid = dim3(div_up(max_ng, BN), div_up(max_ng, TC_BM), n_graphs);
-  gemm_nt_3xtf32_kernel<BN, SYM, F16><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ah, al, bh, bl, bias, C, M, N, K, graph_nptr, g_off, out_scale);
+  mpn::launch(gemm_nt_3xtf32_kernel<BN, SYM, F16>, grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st, ah, al, bh, bl, bias, C, M, N, K, graph_nptr, g_off, out_scale);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -363,7 +366,7 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
     b_hi = (float*)b_hi_cached;
     b_lo = (float*)b_lo_cached;
   } else {
-    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)B, (long long)N * K / 4, K, nullptr, nullptr, nullptr, (float4*)b_hi, (float4*)b_lo);
+    mpn::launch(split_tf32_kernel, split_grid, 256, 0, st, (const float4*)B, (long long)N * K / 4, K, nullptr, nullptr, nullptr, (float4*)b_hi, (float4*)b_lo);
     MPN_LAUNCH_OK();
   }
   if (a_scale == nullptr && A >= B && A + (size_t)M * K <= B + (size_t)N * K) {      // A is a row block of B (Gram matrix): share the planes
@@ -372,7 +375,7 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
   } else {
     a_hi = (float*)(w + 2 * plane_b);
     a_lo = (float*)(w + 2 * plane_b + plane_a);
-    split_tf32_kernel<<<split_grid, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, K, a_scale, a_shift, row_gid, (float4*)a_hi, (float4*)a_lo);
+    mpn::launch(split_tf32_kernel, split_grid, 256, 0, st, (const float4*)A, (long long)M * K / 4, K, a_scale, a_shift, row_gid, (float4*)a_hi, (float4*)a_lo);
     MPN_LAUNCH_OK();
   }
   CUtensorMap ah, al, bh, bl;
@@ -399,6 +402,7 @@ __global__ void __launch_bounds__(256) split_f16_bn_kernel(const float4* __restr
                                                            const float* __restrict__ shift, const int* __restrict__ row_gid,
                                                            const float* __restrict__ amax_dev, float amax_host, float b_scale,
                                                            uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ out_scale) {
+  pdl_wait();
   const float s = f16_scale_of(amax_dev ? *amax_dev : amax_host);
   if (out_scale && blockIdx.x == 0 && threadIdx.x == 0) *out_scale = (1.f / s) * (1.f / b_scale);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -431,6 +435,7 @@ __global__ void __launch_bounds__(256) split_f16_bn_kernel(const float4* __restr
   }
 }
 __global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ x, long long n4, unsigned int* __restrict__ amax_bits) {
+  pdl_wait();
   float m = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -453,7 +458,7 @@ float f16_plane_scale_host(float amax) {
 int split_f16_host_scale(const float* x, long long n, float amax, void* hi, void* lo, float* scale_out, cudaStream_t st) {
   MPN_REQUIRE(x && hi && lo && n > 0 && (n % 4) == 0, "split_f16: bad arguments (n must be a positive multiple of 4)");
   MPN_REQUIRE((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "split_f16: pointers must be 16-byte aligned");
-  split_f16_bn_kernel<<<(int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256), 256, 0, st>>>((const float4*)x, n / 4, 4, nullptr, nullptr, nullptr,
+  mpn::launch(split_f16_bn_kernel, (int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256), 256, 0, st, (const float4*)x, n / 4, 4, nullptr, nullptr, nullptr,
                                                                                            nullptr, amax, 1.f, (uint2*)hi, (uint2*)lo, nullptr);
   MPN_LAUNCH_OK();
   if (scale_out) *scale_out = f16_plane_scale_host(amax);
@@ -477,11 +482,11 @@ int gemm_nt_tc_f16(const float* A, const float* bias, float* C, int M, int N, in
   const float* amax_dev = nullptr;
   if (!(a_amax_host > 0.f)) {
     MPN_CUDA_OK(cudaMemsetAsync(amax_bits, 0, sizeof(unsigned int), st));
-    absmax_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, amax_bits);
+    mpn::launch(absmax_kernel, kNumSMs * 8, 256, 0, st, (const float4*)A, (long long)M * K / 4, amax_bits);
     MPN_LAUNCH_OK();
     amax_dev = (const float*)amax_bits;
   }
-  split_f16_bn_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)A, (long long)M * K / 4, K, a_scale, a_shift, row_gid, amax_dev, a_amax_host,
+  mpn::launch(split_f16_bn_kernel, kNumSMs * 8, 256, 0, st, (const float4*)A, (long long)M * K / 4, K, a_scale, a_shift, row_gid, amax_dev, a_amax_host,
                                                    b_scale, (uint2*)a_hi, (uint2*)a_lo, out_scale);
   MPN_LAUNCH_OK();
   CUtensorMap ah, al, bh, bl;
@@ -511,7 +516,7 @@ int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const 
   __half* hi = (__half*)w;
   __half* lo = (__half*)(w + plane);
   float* out_scale = (float*)(w + 2 * plane);
-  split_f16_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi, (uint2*)lo, out_scale);
+  mpn::launch(split_f16_kernel, kNumSMs * 8, 256, 0, st, (const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi, (uint2*)lo, out_scale);
   MPN_LAUNCH_OK();
   CUtensorMap ah, al, bh, bl;
   MPN_TRY(make_map(&ah, hi + (size_t)a_row0 * K, M, K, TC_BM, true));
@@ -535,7 +540,7 @@ int gram_blockdiag_tc(const float* X, int N, int K, const int* graph_nptr, const
     const size_t plane16 = (((size_t)N * K * sizeof(__half)) + 255) & ~(size_t)255;
     __half *hi16 = (__half*)w, *lo16 = (__half*)(w + plane16);
     float* out_scale = (float*)(w + 2 * plane16);
-    split_f16_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi16, (uint2*)lo16, out_scale);
+    mpn::launch(split_f16_kernel, kNumSMs * 8, 256, 0, st, (const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi16, (uint2*)lo16, out_scale);
     MPN_LAUNCH_OK();
     CUtensorMap mh16, ml16;
     MPN_TRY(make_map(&mh16, hi16, N, K, TC_BM, true));
@@ -543,7 +548,7 @@ int gram_blockdiag_tc(const float* X, int N, int K, const int* graph_nptr, const
     return launch_tc<128, true, true>(mh16, ml16, mh16, ml16, nullptr, Gbuf, N, N, K, st, graph_nptr, g_off, n_graphs, max_ng, out_scale);
   }
   float *hi = (float*)w, *lo = (float*)(w + plane);
-  split_tf32_kernel<<<kNumSMs * 8, 256, 0, st>>>((const float4*)X, (long long)N * K / 4, K, nullptr, nullptr, nullptr, (float4*)hi, (float4*)lo);
+  mpn::launch(split_tf32_kernel, kNumSMs * 8, 256, 0, st, (const float4*)X, (long long)N * K / 4, K, nullptr, nullptr, nullptr, (float4*)hi, (float4*)lo);
   MPN_LAUNCH_OK();
   CUtensorMap mh, ml;
   MPN_TRY(make_map(&mh, hi, N, K, TC_BM));

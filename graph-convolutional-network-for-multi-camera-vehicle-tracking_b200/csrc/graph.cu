@@ -1,5 +1,6 @@
 // K0: int32 CSR + task tables from the reference's edge_index (models/mpn.py:44 `row, col = edge_index`).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -7,6 +8,11 @@ namespace mpn {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_kernel_launches = 0;
+static int pdl_from_env() {
+  const char* e = getenv("MPN_PDL_LAUNCH");
+  return MPN_PDL && e != nullptr && e[0] == '1';
+}
+int g_pdl_launch = pdl_from_env();
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -20,6 +26,7 @@ __global__ void __launch_bounds__(256) csr_scan_edges(const IdxT* __restrict__ r
                                                       long long E, int n_rows, int n_cols, int row_offset,
                                                       int* __restrict__ rowptr, int* __restrict__ col32,
                                                       int* __restrict__ flags) {
+  pdl_wait();
   long long stride = (long long)gridDim.x * blockDim.x;
   int bad = 0;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
@@ -44,6 +51,7 @@ __global__ void __launch_bounds__(256) csr_scan_edges(const IdxT* __restrict__ r
 __global__ void __launch_bounds__(256) csr_scan_edges_x2(const long long* __restrict__ row, const long long* __restrict__ col,
                                                          long long E, int n_rows, int n_cols, int row_offset,
                                                          int* __restrict__ rowptr, int* __restrict__ col32, int* __restrict__ flags) {
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long pairs = E >> 1;
   int bad = 0;
@@ -75,12 +83,14 @@ __global__ void __launch_bounds__(256) csr_scan_edges_x2(const long long* __rest
 }
 
 __global__ void csr_empty(int n_rows, int* rowptr) {
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_rows; i += gridDim.x * blockDim.x) rowptr[i] = 0;
 }
 
 // Single-block exclusive scan of ceil(deg/chunk) -> taskptr, n_tasks.  n_rows <= a few million.
 __global__ void __launch_bounds__(1024) task_scan(const int* __restrict__ rowptr, int n_rows, int chunk,
                                                   int* __restrict__ taskptr, int* __restrict__ n_tasks) {
+  pdl_wait();
   __shared__ int strip_sum[1024];
   const int t = threadIdx.x;
   const int per = (n_rows + 1023) / 1024;
@@ -107,6 +117,7 @@ __global__ void __launch_bounds__(1024) task_scan(const int* __restrict__ rowptr
 }
 
 __global__ void task_fill(const int* __restrict__ taskptr, int n_rows, int max_tasks, int* __restrict__ task_row) {
+  pdl_wait();
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
     for (int t = taskptr[r]; t < taskptr[r + 1] && t < max_tasks; ++t) task_row[t] = r;
 }
@@ -114,6 +125,7 @@ __global__ void task_fill(const int* __restrict__ taskptr, int n_rows, int max_t
 // deferred validation: an invalid edge list must not reach the sweeps as inconsistent tables -> turn it into an empty graph
 // (rowptr = 0 everywhere, hence no tasks); the host raises when it reads the flag word later
 __global__ void csr_guard(const int* __restrict__ flags, int n_rows, int* __restrict__ rowptr) {
+  pdl_wait();
   if (*flags == 0) return;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n_rows; r += gridDim.x * blockDim.x) rowptr[r] = 0;
 }
@@ -131,16 +143,16 @@ static int graph_build_impl(mpn_graph* g, const IdxT* row, const IdxT* col, cuda
   int* flags = deferred ? flags_dev : g->n_tasks;  // (sync mode: n_tasks doubles as the flag word until task_scan overwrites it)
   MPN_CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(int), st));
   if (g->n_edges == 0) {
-    csr_empty<<<div_up(g->n_nodes + 1, 256), 256, 0, st>>>(g->n_nodes, g->rowptr);
+    mpn::launch(csr_empty, div_up(g->n_nodes + 1, 256), 256, 0, st, g->n_nodes, g->rowptr);
   } else {
     int grid = (int)min((long long)kNumSMs * 16, (long long)div_up(g->n_edges, 256));
     const bool x2 = sizeof(IdxT) == 8 && (g->n_edges & 1) == 0 && ((((uintptr_t)row) | ((uintptr_t)col)) & 15) == 0 &&
                     (((uintptr_t)g->col) & 7) == 0;
     if (x2)
-      csr_scan_edges_x2<<<grid, 256, 0, st>>>((const long long*)row, (const long long*)col, g->n_edges, g->n_nodes, g->n_cols,
+      mpn::launch(csr_scan_edges_x2, grid, 256, 0, st, (const long long*)row, (const long long*)col, g->n_edges, g->n_nodes, g->n_cols,
                                               g->row_offset, g->rowptr, g->col, flags);
     else
-      csr_scan_edges<IdxT><<<grid, 256, 0, st>>>(row, col, g->n_edges, g->n_nodes, g->n_cols, g->row_offset,
+      mpn::launch(csr_scan_edges<IdxT>, grid, 256, 0, st, row, col, g->n_edges, g->n_nodes, g->n_cols, g->row_offset,
                                                  g->rowptr, g->col, flags);
   }
   MPN_LAUNCH_OK();
@@ -148,7 +160,7 @@ static int graph_build_impl(mpn_graph* g, const IdxT* row, const IdxT* col, cuda
     // no host round trip on the critical path: the flag word travels to pinned host memory behind the scan, the tables of an
     // invalid edge list are emptied on the device, and the caller checks *flags_host_pinned at its next synchronisation point
     MPN_CUDA_OK(cudaMemcpyAsync(flags_host_pinned, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-    csr_guard<<<min(kNumSMs, div_up(g->n_nodes + 1, 256)), 256, 0, st>>>(flags, g->n_nodes, g->rowptr);
+    mpn::launch(csr_guard, min(kNumSMs, div_up(g->n_nodes + 1, 256)), 256, 0, st, flags, g->n_nodes, g->rowptr);
     MPN_LAUNCH_OK();
   } else {
     int h_flags = 0;
@@ -163,9 +175,9 @@ static int graph_build_impl(mpn_graph* g, const IdxT* row, const IdxT* col, cuda
       return MPN_ERR_UNSORTED;
     }
   }
-  task_scan<<<1, 1024, 0, st>>>(g->rowptr, g->n_nodes, g->chunk, g->taskptr, g->n_tasks);
+  mpn::launch(task_scan, 1, 1024, 0, st, g->rowptr, g->n_nodes, g->chunk, g->taskptr, g->n_tasks);
   MPN_LAUNCH_OK();
-  task_fill<<<min(kNumSMs * 8, div_up(g->n_nodes, 256)), 256, 0, st>>>(g->taskptr, g->n_nodes, g->max_tasks, g->task_row);
+  mpn::launch(task_fill, min(kNumSMs * 8, div_up(g->n_nodes, 256)), 256, 0, st, g->taskptr, g->n_nodes, g->max_tasks, g->task_row);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -181,6 +193,7 @@ struct CamLayout {
 __global__ void __launch_bounds__(256) cross_camera_kernel(const CamLayout L, int n_total, int row0, int n_rows, long long gbase,
                                                            long long E, int* __restrict__ rowptr, int* __restrict__ col32,
                                                            long long* __restrict__ edge_index_out) {
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (long long lr = tid; lr <= n_rows; lr += stride) {            // rowptr of the local rows
@@ -267,12 +280,12 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n
   }
   cudaStream_t st = (cudaStream_t)stream;
   const long long work = E > g->n_nodes ? E : g->n_nodes + 1;
-  cross_camera_kernel<<<(int)min((long long)kNumSMs * 16, (work + 255) / 256), 256, 0, st>>>(L, n_total, g->row_offset, g->n_nodes, gbase, E,
+  mpn::launch(cross_camera_kernel, (int)min((long long)kNumSMs * 16, (work + 255) / 256), 256, 0, st, L, n_total, g->row_offset, g->n_nodes, gbase, E,
                                                                                           g->rowptr, g->col, (long long*)edge_index_out);
   MPN_LAUNCH_OK();
-  task_scan<<<1, 1024, 0, st>>>(g->rowptr, g->n_nodes, g->chunk, g->taskptr, g->n_tasks);
+  mpn::launch(task_scan, 1, 1024, 0, st, g->rowptr, g->n_nodes, g->chunk, g->taskptr, g->n_tasks);
   MPN_LAUNCH_OK();
-  task_fill<<<min(kNumSMs * 8, div_up(g->n_nodes, 256)), 256, 0, st>>>(g->taskptr, g->n_nodes, g->max_tasks, g->task_row);
+  mpn::launch(task_fill, min(kNumSMs * 8, div_up(g->n_nodes, 256)), 256, 0, st, g->taskptr, g->n_nodes, g->max_tasks, g->task_row);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -280,6 +293,12 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n
 int mpn_abi_version(void) { return MPN_B200_ABI_VERSION; }
 const char* mpn_last_error(void) { return mpn::g_err; }
 uint64_t mpn_kernel_launches(void) { return mpn::g_kernel_launches; }
+
+int mpn_set_pdl(int enable) {
+  if (!MPN_PDL) return 0;
+  if (enable >= 0) mpn::g_pdl_launch = enable != 0;
+  return mpn::g_pdl_launch ? 2 : 1;
+}
 
 int mpn_check_device(int dev) {
   int n = 0;

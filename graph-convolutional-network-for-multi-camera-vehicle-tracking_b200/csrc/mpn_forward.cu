@@ -272,6 +272,7 @@ __device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, i
 
 constexpr int FIN_THREADS = 1024;
 __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinArgs f, int do_reduce, int do_consts) {
+  pdl_wait();
   finalize_body(f, do_reduce, do_consts);
 }
 
@@ -306,6 +307,7 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned 
 // moment all-reduce + constant folding in one kernel: local partials -> my slot -> flag; wait for every rank; add the
 // slots in rank order (the same order on every rank => bit-identical totals); fold.
 __global__ void __launch_bounds__(1024) finalize_peer_kernel(const FinArgs f, const PeerArgs P, unsigned long long seq) {
+  pdl_wait();
   finalize_body(f, 1, 0);                                   // local block partials -> f.sums
   __syncthreads();
   const int k = threadIdx.x;
@@ -335,12 +337,14 @@ __global__ void __launch_bounds__(1024) finalize_peer_kernel(const FinArgs f, co
 
 // h all-gather: publish / wait on the second flag word
 __global__ void peer_publish_h_kernel(const PeerArgs P, unsigned long long seq) {
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     __threadfence_system();
     st_release_sys(P.flags[P.rank] + 1, seq);
   }
 }
 __global__ void peer_wait_h_kernel(const PeerArgs P, unsigned long long seq) {
+  pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x < P.world) wait_flag(P.flags[threadIdx.x] + 1, seq);
 }
 
@@ -367,6 +371,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_kernel(const float2
                                                                     const float* __restrict__ consts,
                                                                     const float* __restrict__ small,
                                                                     double* __restrict__ partials, const FinArgs fin) {
+  pdl_wait();
   __shared__ EdgeConsts sc;
   __shared__ double red[(SWEEP_THREADS / 32) * 8];
   __shared__ float w2raw[20];
@@ -453,6 +458,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mp
                                                                      const float4* __restrict__ Ps, const float4* __restrict__ Pd,
                                                                      float4* __restrict__ ybuf, const float* __restrict__ consts,
                                                                      double* __restrict__ partials, const FinArgs fin) {
+  pdl_wait();
   constexpr int U = 4;
   __shared__ EdgeConsts scs[BATCHED ? SWEEP_THREADS / 32 : 1];
   __shared__ double red[(SWEEP_THREADS / 32) * 8];
@@ -542,6 +548,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) node_moments_sweep_kernel(co
                                                                            float4* __restrict__ s1_task, double* __restrict__ partials,
                                                                            const float* __restrict__ A, const float* __restrict__ small,
                                                                            const FinArgs fin) {
+  pdl_wait();
   constexpr int U = (YSRC == 1 && !BATCHED) ? 8 : 4;     // stored y: 8 x 16 B in flight per lane (the sweep is bound by bytes in flight)
   __shared__ EdgeConsts scs[BATCHED ? SWEEP_THREADS / 32 : 1];
   __shared__ double red[(SWEEP_THREADS / 32) * 10];
@@ -697,6 +704,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph
                                                               const float* __restrict__ consts, float* __restrict__ msg_task,
                                                               float2* __restrict__ logits, uint8_t* __restrict__ pred,
                                                               float* __restrict__ prob1) {
+  pdl_wait();
   constexpr int U = 2;
   constexpr int NW = BATCHED ? SWEEP_THREADS / 32 : 1;
   __shared__ EdgeConsts scs[NW];
@@ -874,6 +882,7 @@ template <bool CLASSIFY, bool DECIDE, bool AGGMAX, int CTAS>
 __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
     const mpn_graph g, const float4* __restrict__ ybuf, const float* __restrict__ A, const float* __restrict__ consts,
     float* __restrict__ msg_task, float2* __restrict__ logits, uint8_t* __restrict__ pred, float* __restrict__ prob1) {
+  pdl_wait();
   __shared__ EdgeConsts sc;
   __shared__ __align__(128) float et[2 * ATC_NB][ATC_TILE_BYTES / 4];  // [buffer][half]: [e'_lo | e'_hi | 1 1 0 0] per 8-row group
   __shared__ __align__(128) float w1[32 * 8];
@@ -1097,6 +1106,7 @@ template <int STAGE>
 __global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_task_kernel(const mpn_graph g, const float2* __restrict__ edge_attr,
                                                                          const float* __restrict__ consts, const float* __restrict__ small,
                                                                          double* __restrict__ task_part) {
+  pdl_wait();
   __shared__ EdgeConsts scs[SWEEP_THREADS / 32];
   __shared__ float w2raw[20];
   if (threadIdx.x < 16) w2raw[threadIdx.x] = small[MPN_W_ENC2_W + threadIdx.x];
@@ -1141,6 +1151,7 @@ __global__ void __launch_bounds__(128) graph_finalize_kernel(int stage, const mp
                                                              const float* __restrict__ A, const float4* __restrict__ s1_task,
                                                              const float* __restrict__ small, double* __restrict__ sums_all,
                                                              float* __restrict__ consts_all, int re_e) {
+  pdl_wait();
   __shared__ double red[4][64];
   const int gi = blockIdx.x;
   const int n0 = g.graph_nptr[gi], n1 = g.graph_nptr[gi + 1];
@@ -1197,6 +1208,7 @@ __global__ void __launch_bounds__(128) graph_finalize_kernel(int stage, const mp
 __global__ void __launch_bounds__(256) colstats_graph_kernel(const float* __restrict__ Y, int Nc, const int* __restrict__ graph_nptr,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_wait();
   __shared__ double ssum[8][33], ssq[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -1229,6 +1241,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) classify_encoded_kernel(const f
                                                                          const float* __restrict__ consts,
                                                                          float2* __restrict__ logits, uint8_t* __restrict__ pred,
                                                                          float* __restrict__ prob1) {
+  pdl_wait();
   __shared__ EdgeConsts sc;
   load_consts(sc, consts);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1248,6 +1261,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) classify_encoded_kernel(const f
 }
 
 __global__ void decide_kernel(const float2* __restrict__ logits, long long E, uint8_t* __restrict__ pred, float* __restrict__ prob1) {
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     const float2 l = logits[e];
@@ -1269,6 +1283,7 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
                                                        double* __restrict__ part /*[splits][Nc][2]*/, unsigned int* __restrict__ tile_counter,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_wait();
   __shared__ double ssum[8][33], ssq[8][33];
   __shared__ unsigned int s_ticket;
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -1318,6 +1333,7 @@ __global__ void __launch_bounds__(1024) colstats_peer_kernel(const double* __res
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              float* __restrict__ scale, float* __restrict__ shift,
                                                              const PeerArgs P, unsigned long long seq) {
+  pdl_wait();
   const int col = threadIdx.x;
   const int slot = (int)(seq & 1ull);
   double* mine = P.cstats[P.rank] + (size_t)slot * MPN_PEER_CSTAT_COLS * 2;
@@ -1357,6 +1373,7 @@ __global__ void __launch_bounds__(1024) colstats_peer_kernel(const double* __res
 // final BatchNorm+ReLU of the sharded encoder: this rank's rows of h, stored locally and into every peer's h buffer
 __global__ void bn_relu_apply_peer_kernel(const float* __restrict__ Y, int rows, int row_offset, const float* __restrict__ scale,
                                           const float* __restrict__ shift, const PeerArgs P) {
+  pdl_wait();
   const long long total = (long long)rows * MPN_DH;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -1369,6 +1386,7 @@ __global__ void bn_relu_apply_peer_kernel(const float* __restrict__ Y, int rows,
 
 __global__ void bn_relu_apply_kernel(const float* __restrict__ Y, long long total, int Nc, const float* __restrict__ scale,
                                      const float* __restrict__ shift, const int* __restrict__ row_gid, float* __restrict__ out) {
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int c = (int)(i % Nc);
@@ -1389,6 +1407,7 @@ __global__ void __launch_bounds__(NT_THREADS) node_tables_kernel(const float* __
                                                                  int n_rows, const float* __restrict__ small,
                                                                  float* __restrict__ Ps, float* __restrict__ Pd,
                                                                  float* __restrict__ A) {
+  pdl_wait();
   __shared__ float hs[NT_NODES][33];
   __shared__ float ws[NT_OUT][33];
   __shared__ float hs0[RE_N ? NT_NODES : 1][33];
@@ -1460,6 +1479,7 @@ struct AbsFix {
 template <bool PEERS>
 __global__ void __launch_bounds__(256) node_finalize_kernel(const mpn_graph g, const float* __restrict__ msg_task,
                                                             float* __restrict__ h_full, const PeerArgs P, const AbsFix fix) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1692,13 +1712,13 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
     }
     if (!done) MPN_TRY(gemm_nt_simt(in, p->w.node_w[l], p->w.node_b[l], sc, sh, out, M, Nc, K, st, gid));
     if (batched) {
-      colstats_graph_kernel<<<dim3(div_up(Nc, 32), p->n_graphs), 256, 0, st>>>(out, Nc, p->g.graph_nptr, p->w.node_gamma[l],
+      mpn::launch(colstats_graph_kernel, dim3(div_up(Nc, 32), p->n_graphs), 256, 0, st, out, Nc, p->g.graph_nptr, p->w.node_gamma[l],
                                                                               p->w.node_beta[l], p->colscale, p->colshift);
     } else {
       int splits = div_up(M, 256);
       splits = splits > CS_ROWSPLIT_MAX ? CS_ROWSPLIT_MAX : splits;
       const int rps = div_up(M, splits);
-      colstats_kernel<<<dim3(div_up(Nc, 32), splits), 256, 0, st>>>(out, M, Nc, rps, p->colpart, p->col_counter, p->w.node_gamma[l],
+      mpn::launch(colstats_kernel, dim3(div_up(Nc, 32), splits), 256, 0, st, out, M, Nc, rps, p->colpart, p->col_counter, p->w.node_gamma[l],
                                                                     p->w.node_beta[l], p->colscale, p->colshift);
     }
     MPN_LAUNCH_OK();
@@ -1706,7 +1726,7 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
     sc = p->colscale;
     sh = p->colshift;
   }
-  bn_relu_apply_kernel<<<min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st>>>(in, (long long)M * MPN_DH, MPN_DH, sc, sh, batched ? p->g.node_gid : nullptr, p->h_full);
+  mpn::launch(bn_relu_apply_kernel, min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st, in, (long long)M * MPN_DH, MPN_DH, sc, sh, batched ? p->g.node_gid : nullptr, p->h_full);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -1733,17 +1753,17 @@ static int node_encoder_sharded(mpn_fwd_plan* p, const float* x, const PeerArgs&
     int splits = div_up(M, 256);
     splits = splits > CS_ROWSPLIT_MAX ? CS_ROWSPLIT_MAX : splits;
     const int rps = div_up(M, splits);
-    colstats_kernel<<<dim3(div_up(Nc, 32), splits), 256, 0, st>>>(out, M, Nc, rps, p->colpart, nullptr, p->w.node_gamma[l],
+    mpn::launch(colstats_kernel, dim3(div_up(Nc, 32), splits), 256, 0, st, out, M, Nc, rps, p->colpart, nullptr, p->w.node_gamma[l],
                                                                   p->w.node_beta[l], p->colscale, p->colshift);
     MPN_LAUNCH_OK();
-    colstats_peer_kernel<<<1, 1024, 0, st>>>(p->colpart, splits, Nc, p->g.n_cols, p->w.node_gamma[l], p->w.node_beta[l], p->colscale,
+    mpn::launch(colstats_peer_kernel, 1, 1024, 0, st, p->colpart, splits, Nc, p->g.n_cols, p->w.node_gamma[l], p->w.node_beta[l], p->colscale,
                                             p->colshift, P, ++seq_c);
     MPN_LAUNCH_OK();
     in = out;
     sc = p->colscale;
     sh = p->colshift;
   }
-  bn_relu_apply_peer_kernel<<<min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st>>>(in, M, off, sc, sh, P);
+  mpn::launch(bn_relu_apply_peer_kernel, min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st, in, M, off, sc, sh, P);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -1751,10 +1771,10 @@ static int node_encoder_sharded(mpn_fwd_plan* p, const float* x, const PeerArgs&
 int mpn_plan_node_tables(mpn_fwd_plan* p, int32_t step, void* stream) {
   MPN_REQUIRE(p, "node_tables: NULL plan");
   if (p->w.reattach_nodes)
-    node_tables_kernel<true><<<div_up(p->g.n_cols, NT_NODES), NT_THREADS, 0, (cudaStream_t)stream>>>(
+    mpn::launch(node_tables_kernel<true>, div_up(p->g.n_cols, NT_NODES), NT_THREADS, 0, (cudaStream_t)stream, 
         p->h_full, p->h0_full, step <= 1, p->g.n_cols, p->g.row_offset, p->g.n_nodes, p->w.small, p->Ps, p->Pd, p->A);
   else
-    node_tables_kernel<false><<<div_up(p->g.n_cols, NT_NODES), NT_THREADS, 0, (cudaStream_t)stream>>>(
+    mpn::launch(node_tables_kernel<false>, div_up(p->g.n_cols, NT_NODES), NT_THREADS, 0, (cudaStream_t)stream, 
         p->h_full, nullptr, step <= 1, p->g.n_cols, p->g.row_offset, p->g.n_nodes, p->w.small, p->Ps, p->Pd, p->A);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -1777,29 +1797,29 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
     double* tp = p->task_part;
     switch (stage) {
       case MPN_STAGE_ENC0:
-        enc_moments_task_kernel<0><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, p->consts, p->w.small, tp);
+        mpn::launch(enc_moments_task_kernel<0>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, p->consts, p->w.small, tp);
         break;
       case MPN_STAGE_ENC1:
-        enc_moments_task_kernel<1><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, p->consts, p->w.small, tp);
+        mpn::launch(enc_moments_task_kernel<1>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, p->consts, p->w.small, tp);
         break;
       case MPN_STAGE_EDGE:
         if (step == 1) {
-          if (stored) edge_moments_kernel<0, true, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
-          else edge_moments_kernel<0, false, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, tp, make_fin(p, stage, false));
+          if (stored) mpn::launch(edge_moments_kernel<0, true, true>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
+          else mpn::launch(edge_moments_kernel<0, false, true>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, nullptr, p->consts, tp, make_fin(p, stage, false));
         } else {
-          if (p->w.reattach_edges) edge_moments_kernel<1, true, true, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
-          else edge_moments_kernel<1, true, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
+          if (p->w.reattach_edges) mpn::launch(edge_moments_kernel<1, true, true, true>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
+          else mpn::launch(edge_moments_kernel<1, true, true>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->consts, tp, make_fin(p, stage, false));
         }
         break;
       case MPN_STAGE_NODE:
-        if (stored) node_moments_sweep_kernel<1, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, tp, p->A, p->w.small, make_fin(p, stage, false));
-        else node_moments_sweep_kernel<0, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, tp, p->A, p->w.small, make_fin(p, stage, false));
+        if (stored) mpn::launch(node_moments_sweep_kernel<1, true>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, tp, p->A, p->w.small, make_fin(p, stage, false));
+        else mpn::launch(node_moments_sweep_kernel<0, true>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, tp, p->A, p->w.small, make_fin(p, stage, false));
         break;
       case MPN_STAGE_APPLY: {
         const bool classify = logits_out != nullptr;
         float2* lg = (float2*)logits_out;
         MPN_REQUIRE(p->L > 0, "batched graphs need num_enc_steps >= 1");
-#define MPN_APPLY_B2(YS, CL, MX) apply_kernel<YS, CL, true, MX><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_APPLY_B2(YS, CL, MX) mpn::launch(apply_kernel<YS, CL, true, MX>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
 #define MPN_APPLY_B(YS, CL) do { if (p->w.node_agg == MPN_AGG_MAX) MPN_APPLY_B2(YS, CL, true); else MPN_APPLY_B2(YS, CL, false); } while (0)
         if (stored) { if (classify) MPN_APPLY_B(1, true); else MPN_APPLY_B(1, false); }
         else        { if (classify) MPN_APPLY_B(0, true); else MPN_APPLY_B(0, false); }
@@ -1812,7 +1832,7 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
     }
     MPN_LAUNCH_OK();
     if (stage != MPN_STAGE_APPLY) {
-      graph_finalize_kernel<<<p->n_graphs, 128, 0, st>>>(stage, g, tp, p->A, (const float4*)p->s1_task, p->w.small, p->sums, p->consts,
+      mpn::launch(graph_finalize_kernel, p->n_graphs, 128, 0, st, stage, g, tp, p->A, (const float4*)p->s1_task, p->w.small, p->sums, p->consts,
                                                          p->w.reattach_edges ? (stored ? 2 : 1) : 0);
       MPN_LAUNCH_OK();
     }
@@ -1822,30 +1842,30 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
     case MPN_STAGE_ENC0:
       MPN_CUDA_OK(cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st));
       MPN_CUDA_OK(cudaMemsetAsync(p->fin_counter, 0, sizeof(unsigned int), st));
-      enc_moments_kernel<0><<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused));
+      mpn::launch(enc_moments_kernel<0>, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused));
       break;
     case MPN_STAGE_ENC1:
-      enc_moments_kernel<1><<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused));
+      mpn::launch(enc_moments_kernel<1>, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused));
       break;
     case MPN_STAGE_EDGE:
       if (step == 1) {
-        if (stored) edge_moments_kernel<0, true, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
-        else edge_moments_kernel<0, false, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, p->partials, make_fin(p, stage, fused));
+        if (stored) mpn::launch(edge_moments_kernel<0, true, false>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
+        else mpn::launch(edge_moments_kernel<0, false, false>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, nullptr, p->consts, p->partials, make_fin(p, stage, fused));
       } else {
-        if (p->w.reattach_edges) edge_moments_kernel<1, true, false, true><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
-        else edge_moments_kernel<1, true, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
+        if (p->w.reattach_edges) mpn::launch(edge_moments_kernel<1, true, false, true>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
+        else mpn::launch(edge_moments_kernel<1, true, false>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->consts, p->partials, make_fin(p, stage, fused));
       }
       break;
     case MPN_STAGE_NODE:
-      if (stored) node_moments_sweep_kernel<1, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, p->partials, p->A, p->w.small, make_fin(p, stage, fused));
-      else node_moments_sweep_kernel<0, false><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, p->partials, p->A, p->w.small, make_fin(p, stage, fused));
+      if (stored) mpn::launch(node_moments_sweep_kernel<1, false>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->consts, (float4*)p->s1_task, p->partials, p->A, p->w.small, make_fin(p, stage, fused));
+      else mpn::launch(node_moments_sweep_kernel<0, false>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, nullptr, p->consts, (float4*)p->s1_task, p->partials, p->A, p->w.small, make_fin(p, stage, fused));
       break;
     case MPN_STAGE_APPLY: {
       const bool classify = logits_out != nullptr;
       float2* lg = (float2*)logits_out;
       if (p->L == 0) {
         MPN_REQUIRE(classify, "L == 0 needs a logits buffer");
-        classify_encoded_kernel<<<flat_grid, SWEEP_THREADS, 0, st>>>(ea, g.n_edges, p->consts, lg, pred_out, prob1_out);
+        mpn::launch(classify_encoded_kernel, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, lg, pred_out, prob1_out);
         break;
       }
       // tensor-core variant: stored-y runs on graphs with >= 128-edge tasks (MPN_APPLY_TC=0 selects the packed-fp32 kernel)
@@ -1857,7 +1877,7 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
         p->msg_abs = agg_max ? 0 : 1;                      // msg_task holds sum |z|: node_finalize adds the closed-form half
         const char* ctas_env = getenv("MPN_ATC_CTAS");     // resident blocks per SM: 4 | 5, read per launch (measurements flip it)
         const int atc_ctas = ctas_env ? (atoi(ctas_env) == 5 ? 5 : 4) : ATC_CTAS_PER_SM;
-#define MPN_ATC3(CL, DE, MX, NC) apply_tc_kernel<CL, DE, MX, NC><<<kNumSMs * NC, ATC_THREADS, 0, st>>>(g, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_ATC3(CL, DE, MX, NC) mpn::launch(apply_tc_kernel<CL, DE, MX, NC>, kNumSMs * NC, ATC_THREADS, 0, st, g, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
 #define MPN_ATC2(CL, DE, MX) do { if (atc_ctas == 5) MPN_ATC3(CL, DE, MX, 5); else MPN_ATC3(CL, DE, MX, 4); } while (0)
 #define MPN_ATC(CL, DE) do { if (agg_max) MPN_ATC2(CL, DE, true); else MPN_ATC2(CL, DE, false); } while (0)
         if (!classify) MPN_ATC(false, false);
@@ -1868,7 +1888,7 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
 #undef MPN_ATC3
         break;
       }
-#define MPN_APPLY2(YS, CL, MX) apply_kernel<YS, CL, false, MX><<<SWEEP_GRID, SWEEP_THREADS, 0, st>>>(g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
+#define MPN_APPLY2(YS, CL, MX) mpn::launch(apply_kernel<YS, CL, false, MX>, SWEEP_GRID, SWEEP_THREADS, 0, st, g, ea, Ps4, Pd4, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
 #define MPN_APPLY(YS, CL) do { if (p->w.node_agg == MPN_AGG_MAX) MPN_APPLY2(YS, CL, true); else MPN_APPLY2(YS, CL, false); } while (0)
       if (stored) { if (classify) MPN_APPLY(1, true); else MPN_APPLY(1, false); }
       else        { if (classify) MPN_APPLY(0, true); else MPN_APPLY(0, false); }
@@ -1888,7 +1908,7 @@ int mpn_plan_finalize(mpn_fwd_plan* p, int32_t step, int32_t stage, void* stream
   (void)step;
   if (p->n_graphs > 1) return MPN_OK;     // batched: graph_finalize_kernel already ran after the sweep
   // sums already reduced (and possibly all-reduced by the host): constants only
-  finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(make_fin(p, stage, false), 0, 1);
+  mpn::launch(finalize_kernel, 1, FIN_THREADS, 0, (cudaStream_t)stream, make_fin(p, stage, false), 0, 1);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -1897,7 +1917,7 @@ int mpn_plan_finalize(mpn_fwd_plan* p, int32_t step, int32_t stage, void* stream
 int mpn_plan_reduce(mpn_fwd_plan* p, int32_t stage, int with_consts, void* stream) {
   MPN_REQUIRE(p, "reduce: NULL plan");
   if (p->n_graphs > 1) return MPN_OK;     // batched: graph_finalize_kernel already ran after the sweep
-  finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(make_fin(p, stage, false), 1, with_consts);
+  mpn::launch(finalize_kernel, 1, FIN_THREADS, 0, (cudaStream_t)stream, make_fin(p, stage, false), 1, with_consts);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -1905,7 +1925,7 @@ int mpn_plan_reduce(mpn_fwd_plan* p, int32_t stage, int with_consts, void* strea
 int mpn_plan_node_finalize(mpn_fwd_plan* p, int32_t step, void* stream) {
   MPN_REQUIRE(p, "node_finalize: NULL plan");
   (void)step;
-  node_finalize_kernel<false><<<min(kNumSMs * 8, div_up((long long)p->g.n_nodes * 32, 256)), 256, 0, (cudaStream_t)stream>>>(p->g, p->msg_task, p->h_full, PeerArgs(), abs_fix(p));
+  mpn::launch(node_finalize_kernel<false>, min(kNumSMs * 8, div_up((long long)p->g.n_nodes * 32, 256)), 256, 0, (cudaStream_t)stream, p->g, p->msg_task, p->h_full, PeerArgs(), abs_fix(p));
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -2031,12 +2051,12 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
   bool h_pending = false;                                   // an h exchange has been published and not yet awaited
   const size_t lstride = (size_t)g->n_edges * 2;
 #define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
-#define PEER_FINALIZE(stage) do { finalize_peer_kernel<<<1, FIN_THREADS, 0, st>>>(make_fin(p, stage, false), P, ++seq_m); \
+#define PEER_FINALIZE(stage) do { mpn::launch(finalize_peer_kernel, 1, FIN_THREADS, 0, st, make_fin(p, stage, false), P, ++seq_m); \
     ++mpn::g_kernel_launches; if (cudaGetLastError() != cudaSuccess) { set_error("finalize_peer launch failed"); rc = MPN_ERR_CUDA; goto done; } } while (0)
   if (shard_enc) {
     // every rank encodes its own rows; column statistics and the encoded rows travel over NVLink inside the kernels
     STEP_TRY(node_encoder_sharded(p, x, P, seq_c, st));
-    peer_publish_h_kernel<<<1, 32, 0, st>>>(P, ++seq_h);
+    mpn::launch(peer_publish_h_kernel, 1, 32, 0, st, P, ++seq_h);
     ++mpn::g_kernel_launches;
     h_pending = true;
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
@@ -2059,7 +2079,7 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
     int k = 0;
     for (int step = 1; step <= L; ++step) {
       if (h_pending) {                                      // every rank's rows of h must have landed in my buffer
-        peer_wait_h_kernel<<<1, 32, 0, st>>>(P, seq_h);
+        mpn::launch(peer_wait_h_kernel, 1, 32, 0, st, P, seq_h);
         ++mpn::g_kernel_launches;
         h_pending = false;
       }
@@ -2075,12 +2095,12 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
       if (cls) ++k;
       const int grid = min(kNumSMs * 8, div_up((long long)g->n_nodes * 32, 256));
       if (!last) {
-        node_finalize_kernel<true><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P, abs_fix(p));
-        peer_publish_h_kernel<<<1, 32, 0, st>>>(P, ++seq_h);
+        mpn::launch(node_finalize_kernel<true>, grid, 256, 0, st, p->g, p->msg_task, p->h_full, P, abs_fix(p));
+        mpn::launch(peer_publish_h_kernel, 1, 32, 0, st, P, ++seq_h);
         mpn::g_kernel_launches += 2;
         h_pending = true;
       } else {
-        node_finalize_kernel<false><<<grid, 256, 0, st>>>(p->g, p->msg_task, p->h_full, P, abs_fix(p));
+        mpn::launch(node_finalize_kernel<false>, grid, 256, 0, st, p->g, p->msg_task, p->h_full, P, abs_fix(p));
         ++mpn::g_kernel_launches;
       }
       if (cudaGetLastError() != cudaSuccess) { set_error("node_finalize launch failed"); rc = MPN_ERR_CUDA; goto done; }
@@ -2101,7 +2121,7 @@ done:
 int mpn_decide(const float* logits, int64_t E, uint8_t* pred, float* prob1, void* stream) {
   MPN_REQUIRE(logits || E == 0, "decide: NULL logits");
   if (E == 0) return MPN_OK;
-  decide_kernel<<<(int)min((long long)kNumSMs * 8, (long long)div_up(E, 256)), 256, 0, (cudaStream_t)stream>>>(
+  mpn::launch(decide_kernel, (int)min((long long)kNumSMs * 8, (long long)div_up(E, 256)), 256, 0, (cudaStream_t)stream, 
       (const float2*)logits, E, pred, prob1);
   MPN_LAUNCH_OK();
   return MPN_OK;

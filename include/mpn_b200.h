@@ -46,6 +46,12 @@ int mpn_abi_version(void);
 const char* mpn_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (monotonic) */
 uint64_t mpn_kernel_launches(void);
+/* EXPERIMENTAL (off by default): programmatic dependent launch of the graph-build / edge-feature / forward kernels, so the
+ * launch latency of kernel n+1 overlaps the tail of kernel n (every kernel starts with griddepcontrol.wait).
+ * enable > 0 / == 0 switches it on / off, enable < 0 only queries.  Returns 0 when the support is compiled out (the default
+ * build: launches are plain <<<>>> and this call changes nothing); when the library was built with `MPN_PDL=1 csrc/build.sh`:
+ * 1 = switch is off, 2 = switch is on (initial state: on iff the environment has MPN_PDL_LAUNCH=1). */
+int mpn_set_pdl(int enable);
 /* 0 if device `dev` exists and is sm_100; error otherwise.  Never falls back to CPU. */
 int mpn_check_device(int dev);
 

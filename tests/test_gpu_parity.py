@@ -420,6 +420,38 @@ def test_graph_stream_graph_replay_experimental(m):
             assert torch.equal(o, r)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("MPN_TEST_EXPERIMENTAL") != "1",
+                    reason="programmatic dependent launch is experimental (MPN_PDL=1 csrc/build.sh); MPN_TEST_EXPERIMENTAL=1 runs it")
+def test_programmatic_dependent_launch_experimental(m):
+    """Same bits with the launch attribute on: graph tables, edge features, forward (small-graph replay and large-graph path)."""
+    lib = m._lib.lib()
+    if lib.mpn_set_pdl(-1) == 0:
+        pytest.skip("library built without MPN_PDL=1")
+    params = mo.shipped_model_params(2, 1, 64, (48, 40))
+    sd = mo.init_weights(params, "resnet101", 23)
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev()).eval()
+    net.fuse_decisions = True
+    try:
+        for N in (200, 3000):
+            x, ei, cam, _ = mo.synth_graph(N, 4, 7, D=64, planted=True)
+            outs = []
+            for on in (0, 1, 1, 0):
+                assert lib.mpn_set_pdl(on) == 1 + on
+                g = m.TrackletGraph.from_cameras(cam.numpy(), dev())
+                d = Data(x=x.to(dev()), edge_index=None, mpn_graph=g, edge_attr=None)
+                net._graphs.clear()                              # the small-graph CUDA graph is re-captured in each mode
+                out, h = net(d)
+                torch.cuda.synchronize()
+                outs.append((d.edge_attr.clone(), out["classified_edges"][-1].clone(), h.clone(), net.last_pred.clone()))
+            for o in outs[1:]:
+                for a, b in zip(outs[0], o):
+                    assert torch.equal(a, b)
+    finally:
+        lib.mpn_set_pdl(0)
+
+
 class _NoComm:
     world, rank = 1, 0
 
