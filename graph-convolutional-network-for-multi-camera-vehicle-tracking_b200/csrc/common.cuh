@@ -76,6 +76,7 @@ static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / 
 #define MPN_PDL 0
 #endif
 extern int g_pdl_launch;             // run-time switch (only read when MPN_PDL=1)
+extern int g_fused_distance;         // run-time switch of the fused distance epilogue (mpn_set_fused_distance; default off)
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() {

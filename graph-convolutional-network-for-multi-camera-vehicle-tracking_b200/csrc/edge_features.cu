@@ -12,10 +12,6 @@
 
 namespace mpn {
 
-constexpr float PAIRWISE_EPS = 1e-6f;
-constexpr float COSINE_EPS = 1e-8f;
-constexpr float REFINE_FRACTION = 0.25f;
-
 // column means of x [n, D] (fp64 accumulation): grid (32-column tiles, row splits) -> partials -> fixed-order finalize
 constexpr int CM_SPLITS = 32;
 __global__ void __launch_bounds__(256) col_mean_partial_kernel(const float* __restrict__ x, int n, int D, int rows_per_split,
@@ -215,6 +211,21 @@ __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_grap
   }
 }
 
+// EXPERIMENTAL fused distance epilogue: (first column, length) of the one gap in each row's column list.  Rows are strictly
+// ascending (K0), so col[beg+k] - k is non-decreasing: 0 before the gap, the gap length after it -> binary search.
+__global__ void __launch_bounds__(256) gap_table_kernel(const mpn_graph g, int2* __restrict__ gap) {
+  pdl_wait();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= g.n_nodes) return;
+  const int beg = g.rowptr[r], deg = g.rowptr[r + 1] - beg;
+  int lo = 0, hi = deg;                                  // first k with col[beg+k] != k (deg: the gap is at the end)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (g.col[beg + mid] == mid) lo = mid + 1; else hi = mid;
+  }
+  gap[r] = make_int2(lo, g.n_cols - deg);
+}
+
 struct EfLayout {
   float4* st;
   float *mu, *xc;
@@ -226,6 +237,7 @@ struct EfLayout {
   void* gemm_ws;
   size_t gemm_ws_bytes;
   int rows_per_block;
+  int2* gap;                       // fused distance epilogue: one-gap table of the rows (last slice: the other offsets do not move)
   size_t total;
 };
 
@@ -250,6 +262,7 @@ static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) 
   L.amax_bits = a.take<unsigned int>(1);
   L.gemm_ws_bytes = batched ? gemm_tc_workspace_bytes(1, g->n_cols, D) : gemm_tc_workspace_bytes((int)rows, g->n_cols, D);
   L.gemm_ws = L.gemm_ws_bytes ? (void*)a.take<char>(L.gemm_ws_bytes) : nullptr;
+  L.gap = a.take<int2>((size_t)(g->n_nodes > 0 ? g->n_nodes : 1));
   L.total = a.off;
   return L;
 }
@@ -299,6 +312,24 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
     mpn::launch(edge_feature_gather_kernel, kNumSMs * 8, 256, 0, st, *g, 0, g->n_nodes, L.G, L.g_off, L.st, D, (float2*)edge_attr, L.refine_list,
                                                            L.refine_count);
     MPN_LAUNCH_OK();
+    mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
+  // EXPERIMENTAL (mpn_set_fused_distance, off by default): distances formed by the epilogue warps of the Gram GEMM for graphs
+  // whose builder promises one-gap rows (MPN_GRAPH_ONE_GAP_ROWS: mpn_graph_build_cross_camera)
+  if (g_fused_distance && use_tc && (g->flags & MPN_GRAPH_ONE_GAP_ROWS) != 0 &&
+      gram_ef_supported(min(L.rows_per_block, g->n_nodes), g->n_cols, D, (const float*)L.amax_bits)) {
+    mpn::launch(gap_table_kernel, div_up(g->n_nodes, 256), 256, 0, st, *g, L.gap);
+    MPN_LAUNCH_OK();
+    for (int r0 = 0; r0 < g->n_nodes; r0 += L.rows_per_block) {
+      const int r1 = min(r0 + L.rows_per_block, g->n_nodes);
+      EfEpilogue ef;
+      ef.st = L.st; ef.rowptr = g->rowptr; ef.gap = L.gap; ef.edge_attr = (float2*)edge_attr;
+      ef.refine_list = L.refine_list; ef.refine_count = L.refine_count;
+      ef.row_local0 = r0; ef.row_global0 = g->row_offset + r0; ef.D = D;
+      MPN_TRY(gram_nt_tc(L.xc, g->row_offset + r0, nullptr, r1 - r0, g->n_cols, D, (const float*)L.amax_bits, L.gemm_ws, L.gemm_ws_bytes, st, &ef));
+    }
     mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
     MPN_LAUNCH_OK();
     return MPN_OK;

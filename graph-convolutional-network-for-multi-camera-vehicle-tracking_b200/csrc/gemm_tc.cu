@@ -64,14 +64,35 @@ struct TcCfg {
 };
 
 // SYM: C = A A^T (A == B, M == N): only tiles on or above the diagonal are computed, the epilogue also writes the mirror.
-template <int BN, bool SYM, bool F16>
+// distance epilogue of one Gram entry g = a'.b' for the ordered pair (a = aggregated-at node, b = neighbour): the arithmetic
+// of edge_feature_gather_kernel (edge_features.cu), statement for statement
+__device__ __forceinline__ void ef_store(const EfEpilogue& E, int e, const float4 a, const float4 b, float g) {
+  const double eps = (double)PAIRWISE_EPS;
+  const double sa = a.x, xa = a.y, ma = a.z;
+  const double gij = g;
+  double d2 = sa + (double)b.x - 2.0 * gij + 2.0 * eps * (xa - (double)b.y) + E.D * eps * eps;
+  if (d2 < (double)REFINE_FRACTION * (sa + (double)b.x)) {
+    const int slot = atomicAdd(E.refine_count, 1);
+    E.refine_list[slot] = e;
+  }
+  if (d2 < 0.0) d2 = 0.0;
+  const double ab = gij + ma + (double)b.z;
+  const float denom = fmaxf(a.w * b.w, COSINE_EPS);
+  E.edge_attr[e] = make_float2(sqrtf((float)d2), 1.0f - (float)ab / denom);
+}
+
+template <bool EF> struct EfParam { typedef EfNone type; };
+template <> struct EfParam<true> { typedef EfEpilogue type; };
+
+template <int BN, bool SYM, bool F16, bool EF = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                       const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
                       const int* __restrict__ graph_nptr, const long long* __restrict__ g_off,
-                      const float* __restrict__ out_scale) {
+                      const float* __restrict__ out_scale, const typename EfParam<EF>::type ef) {
   pdl_wait();
+  static_assert(!EF || (F16 && BN == TC_BM), "the distance epilogue is written for the fp16 planes and square tiles");
   constexpr int BK = F16 ? TC_BK_F16 : TC_BK;            // elements of K per stage (128 bytes either way)
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -95,6 +116,25 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     tn0 = base + n0;
     M = N = ng;
     C += g_off[blockIdx.z];
+  }
+  if constexpr (EF) {
+    // a tile without edges (all of its rows have their gap across all of its columns: a same-camera tile) skips the main loop
+    int no_edges = 1;
+    if (threadIdx.x < TC_BM) {
+      const int r = m0 + threadIdx.x;
+      if (r < M) {
+        const int2 gp = ef.gap[ef.row_local0 + r];
+        no_edges = gp.x <= n0 && gp.x + gp.y >= min(n0 + BN, N);
+      }
+      if (SYM && no_edges && n0 >= m0 + TC_BM) {       // the mirrored block: rows n0.., columns m0..
+        const int c = n0 + threadIdx.x;
+        if (c < N) {
+          const int2 gp = ef.gap[c];
+          no_edges = gp.x <= m0 && gp.x + gp.y >= min(m0 + TC_BM, M);
+        }
+      }
+    }
+    if (__syncthreads_and(no_edges)) return;
   }
 
   if (threadIdx.x == 0) {
@@ -171,6 +211,18 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     const int row = m0 + q * 32 + lane;
     const bool vec_ok = ((N & 3) == 0) && ((((uintptr_t)C) & 15) == 0);
     const float oscale = (F16 && out_scale) ? *out_scale : 1.f;       // power of two: exact
+    // EF: this thread's row as the aggregated-at node (direct entries) and as the neighbour (mirrored entries)
+    float4 st_row = make_float4(0.f, 0.f, 0.f, 0.f);
+    int rp_row = 0, gap0 = 0, gap1 = 0;
+    if constexpr (EF) {
+      if (row < M) {
+        st_row = ef.st[ef.row_global0 + row];
+        rp_row = ef.rowptr[ef.row_local0 + row];
+        const int2 gp = ef.gap[ef.row_local0 + row];
+        gap0 = gp.x;
+        gap1 = gp.x + gp.y;
+      }
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= N) break;                                                  // warp-uniform
@@ -185,6 +237,30 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       tmem_ld32(tq + Cfg::CORR_COL, w);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = F16 ? (v[j] + w[j]) * oscale : v[j] + w[j];
+      if constexpr (EF) {
+        if (row < M) {
+          // direct entries (row -> col): 32 consecutive edges of this thread's row, but for the gap
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c0 + j;
+            if (col < N && (col < gap0 || col >= gap1))
+              ef_store(ef, rp_row + col - (col >= gap1 ? gap1 - gap0 : 0), st_row, __ldg(ef.st + col), v[j]);
+          }
+          if (SYM && n0 >= m0 + TC_BM) {
+            // mirrored entries (col -> row): the lanes of a warp hold consecutive rows = consecutive edges of node `col`
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = n0 + c0 + j;
+              if (col < N) {                                                    // warp-uniform
+                const int2 gp = __ldg(ef.gap + col);
+                if (row < gp.x || row >= gp.x + gp.y)
+                  ef_store(ef, __ldg(ef.rowptr + col) + row - (row >= gp.x + gp.y ? gp.y : 0), __ldg(ef.st + col), st_row, v[j]);
+              }
+            }
+          }
+        }
+        continue;
+      }
       if (row < M) {
         float* out = C + (size_t)row * N + n0 + c0;
         if (vec_ok && n0 + c0 + 32 <= N) {
@@ -333,18 +409,19 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K) {
   return 2 * plane_a + 2 * plane_b + 1024;
 }
 
-template <int BN, bool SYM, bool F16 = false>
+template <int BN, bool SYM, bool F16 = false, bool EF = false>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const float* bias,
                      float* C, int M, int N, int K, cudaStream_t st, const int* graph_nptr = nullptr, const long long* g_off = nullptr,
-                     int n_graphs = 1, int max_ng = 0, const float* out_scale = nullptr) {
+                     int n_graphs = 1, int max_ng = 0, const float* out_scale = nullptr,
+                     const typename EfParam<EF>::type& ef = typename EfParam<EF>::type()) {
   static bool configured = false;
   if (!configured) {
-    MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN, SYM, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+    MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN, SYM, F16, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
     configured = true;
   }
   dim3 grid(div_up(N, BN), div_up(M, TC_BM));
   if (graph_nptr) grid = dim3(div_up(max_ng, BN), div_up(max_ng, TC_BM), n_graphs);
-  mpn::launch(gemm_nt_3xtf32_kernel<BN, SYM, F16>, grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st, ah, al, bh, bl, bias, C, M, N, K, graph_nptr, g_off, out_scale);
+  mpn::launch(gemm_nt_3xtf32_kernel<BN, SYM, F16, EF>, grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st, ah, al, bh, bl, bias, C, M, N, K, graph_nptr, g_off, out_scale, ef);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -505,8 +582,14 @@ static bool gram_f16_enabled() {
 
 // Gram block C[M,N] = A X^T where A is the row block of X starting at row a_row0 (X: [N,K], amax_dev = max |X| as float bits
 // written by the producer of X).  fp16 planes (3xFP16) when K % 8 == 0, else the TF32 path.  Symmetric tiles when A == X.
-int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const float* amax_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
+bool gram_ef_supported(int M, int N, int K, const float* amax_dev) {
+  return gram_f16_enabled() && amax_dev != nullptr && (K % 8) == 0 && gemm_tc_supported(M, N, K);
+}
+
+int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const float* amax_dev, void* ws, size_t ws_bytes, cudaStream_t st,
+               const EfEpilogue* ef) {
   const float* A = X + (size_t)a_row0 * K;
+  MPN_REQUIRE(ef == nullptr || gram_ef_supported(M, N, K, amax_dev), "fused distance epilogue: needs the fp16 operand planes");
   if (!gram_f16_enabled() || amax_dev == nullptr || (K % 8) != 0)
     return gemm_nt_tc(A, X, nullptr, C, M, N, K, ws, ws_bytes, st);
   MPN_REQUIRE(gemm_tc_supported(M, N, K), "tcgen05 Gram: unsupported shape %d x %d x %d", M, N, K);
@@ -523,6 +606,11 @@ int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const 
   MPN_TRY(make_map(&al, lo + (size_t)a_row0 * K, M, K, TC_BM, true));
   MPN_TRY(make_map(&bh, hi, N, K, 128, true));
   MPN_TRY(make_map(&bl, lo, N, K, 128, true));
+  if (ef != nullptr) {
+    if (a_row0 == 0 && M == N && ef->row_local0 == 0 && ef->row_global0 == 0)
+      return launch_tc<128, true, true, true>(ah, al, bh, bl, nullptr, nullptr, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, *ef);
+    return launch_tc<128, false, true, true>(ah, al, bh, bl, nullptr, nullptr, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, *ef);
+  }
   if (a_row0 == 0 && M == N) return launch_tc<128, true, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);
   return launch_tc<128, false, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);
 }

@@ -13,6 +13,11 @@ static int pdl_from_env() {
   return MPN_PDL && e != nullptr && e[0] == '1';
 }
 int g_pdl_launch = pdl_from_env();
+static int fused_distance_from_env() {
+  const char* e = getenv("MPN_FUSED_DISTANCE");
+  return e != nullptr && e[0] == '1';
+}
+int g_fused_distance = fused_distance_from_env();
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -279,6 +284,7 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n
     if (k < n_cams) run += (long long)(cam_ptr[k + 1] - cam_ptr[k]) * (n_total - (cam_ptr[k + 1] - cam_ptr[k]));
   }
   cudaStream_t st = (cudaStream_t)stream;
+  g->flags |= MPN_GRAPH_ONE_GAP_ROWS;                 // every row: all columns but the node's own camera segment
   const long long work = E > g->n_nodes ? E : g->n_nodes + 1;
   mpn::launch(cross_camera_kernel, (int)min((long long)kNumSMs * 16, (work + 255) / 256), 256, 0, st, L, n_total, g->row_offset, g->n_nodes, gbase, E,
                                                                                           g->rowptr, g->col, (long long*)edge_index_out);
@@ -293,6 +299,11 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n
 int mpn_abi_version(void) { return MPN_B200_ABI_VERSION; }
 const char* mpn_last_error(void) { return mpn::g_err; }
 uint64_t mpn_kernel_launches(void) { return mpn::g_kernel_launches; }
+
+int mpn_set_fused_distance(int enable) {
+  if (enable >= 0) mpn::g_fused_distance = enable != 0;
+  return mpn::g_fused_distance ? 2 : 1;
+}
 
 int mpn_set_pdl(int enable) {
   if (!MPN_PDL) return 0;

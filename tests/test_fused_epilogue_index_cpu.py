@@ -1,0 +1,113 @@
+"""CPU check of the index arithmetic behind the (experimental) fused distance epilogue of the Gram GEMM.
+
+The kernel (csrc/gemm_tc.cu, EF = true) never looks an edge id up: for graphs whose rows are "all columns but one contiguous
+gap" it computes e = rowptr[i] + j - (j past the gap ? gap length : 0), walks only the tiles on or above the diagonal (symmetric
+Gram), writes the mirrored entries from the same accumulator and skips tiles without edges.  This test replays exactly that walk
+in numpy — gap table by binary search (gap_table_kernel), tile skip vote, direct and mirrored entries — on the reference's
+edge order (inference.py:407-413) and checks that every edge is written exactly once with the right (row, col) pair."""
+import numpy as np
+import pytest
+
+from oracle import mpn_oracle as mo
+
+BM = BN = 128
+
+
+def gap_table(rowptr, col, n_cols):
+    """gap_table_kernel: first k with col[beg+k] != k (binary search on the non-decreasing col[beg+k] - k), gap length."""
+    gap = np.zeros((rowptr.size - 1, 2), dtype=np.int64)
+    for r in range(rowptr.size - 1):
+        beg, deg = rowptr[r], rowptr[r + 1] - rowptr[r]
+        lo, hi = 0, deg
+        while lo < hi:
+            mid = (lo + hi) >> 1
+            if col[beg + mid] == mid:
+                lo = mid + 1
+            else:
+                hi = mid
+        gap[r] = (lo, n_cols - deg)
+    return gap
+
+
+def replay(rowptr, gap, row0, M, N, sym):
+    """(edge id -> (row, col), times written) produced by the tile walk of the kernel for the A block [row0, row0+M)."""
+    writes = {}
+    rp = rowptr                                          # local rows
+    tiles_run = tiles_skipped = 0
+    for by in range((M + BM - 1) // BM):
+        for bx in range((N + BN - 1) // BN):
+            m0, n0 = by * BM, bx * BN
+            if sym and n0 + BN <= m0:
+                continue
+            rows = np.arange(m0, min(m0 + BM, M))
+            no_edges = np.all((gap[rows, 0] <= n0) & (gap[rows, 0] + gap[rows, 1] >= min(n0 + BN, N)))
+            if sym and no_edges and n0 >= m0 + BM:
+                cols = np.arange(n0, min(n0 + BN, N))
+                no_edges = np.all((gap[cols, 0] <= m0) & (gap[cols, 0] + gap[cols, 1] >= min(m0 + BM, M)))
+            if no_edges:
+                tiles_skipped += 1
+                continue
+            tiles_run += 1
+            for r in rows:
+                g0, g1 = gap[r, 0], gap[r, 0] + gap[r, 1]
+                for c in range(n0, min(n0 + BN, N)):
+                    if c < g0 or c >= g1:
+                        e = rp[r] + c - (g1 - g0 if c >= g1 else 0)
+                        writes.setdefault(int(e), []).append((row0 + r, c))
+                if sym and n0 >= m0 + BM:
+                    for c in range(n0, min(n0 + BN, N)):
+                        h0, h1 = gap[c, 0], gap[c, 0] + gap[c, 1]
+                        if r < h0 or r >= h1:
+                            e = rp[c] + r - (h1 - h0 if r >= h1 else 0)
+                            writes.setdefault(int(e), []).append((c, r))
+    return writes, tiles_run, tiles_skipped
+
+
+@pytest.mark.parametrize("sizes", [(70, 90, 60, 80), (128, 128, 128), (1, 300, 2), (257,), (130, 140)])
+def test_closed_form_edge_ids_cover_every_edge_once(sizes):
+    import torch
+    cam = torch.from_numpy(np.repeat(np.arange(len(sizes)), sizes))
+    ei = mo.cross_camera_edge_index(cam).numpy()
+    N, E = int(cam.numel()), ei.shape[1]
+    rowptr = np.zeros(N + 1, dtype=np.int64)
+    np.add.at(rowptr, ei[0] + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    gap = gap_table(rowptr, ei[1], N)
+    starts = np.r_[0, np.cumsum(sizes)]
+    for c, (a, b) in enumerate(zip(starts[:-1], starts[1:])):               # the gap is the node's own camera segment
+        if E:
+            assert np.all(gap[a:b, 1] == b - a)
+            assert np.all(gap[a:b, 0] == a) or b == N                       # (a trailing gap may also be reported at deg)
+    # whole graph, symmetric walk
+    writes, run, skipped = replay(rowptr, gap, 0, N, N, sym=True)
+    assert sorted(writes) == list(range(E))
+    for e, w in writes.items():
+        assert len(w) == 1 and w[0] == (ei[0, e], ei[1, e])
+    if len(sizes) > 1 and min(sizes) >= 2 * BM:
+        assert skipped > 0
+    # row-block shards, plain walk
+    for r0, r1 in ((0, N // 3), (N // 3, N)):
+        if r1 <= r0:
+            continue
+        local = rowptr[r0:r1 + 1] - rowptr[r0]
+        writes, _, _ = replay(local, gap[r0:r1], r0, r1 - r0, N, sym=False)
+        e0 = int(rowptr[r0])
+        assert sorted(writes) == list(range(int(rowptr[r1]) - e0))
+        for e, w in writes.items():
+            assert len(w) == 1 and w[0] == (ei[0, e0 + e], ei[1, e0 + e])
+
+
+def test_same_camera_tiles_are_skipped():
+    import torch
+    sizes = (256, 384, 256)
+    cam = torch.from_numpy(np.repeat(np.arange(len(sizes)), sizes))
+    ei = mo.cross_camera_edge_index(cam).numpy()
+    N = int(cam.numel())
+    rowptr = np.zeros(N + 1, dtype=np.int64)
+    np.add.at(rowptr, ei[0] + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    gap = gap_table(rowptr, ei[1], N)
+    writes, run, skipped = replay(rowptr, gap, 0, N, N, sym=True)
+    assert len(writes) == ei.shape[1]
+    assert skipped == 3 + 6 + 3            # upper-triangular tiles inside the cameras: 2x2, 3x3, 2x2 blocks of 128
+    assert run + skipped == 7 * 8 // 2

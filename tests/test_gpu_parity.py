@@ -452,6 +452,56 @@ def test_programmatic_dependent_launch_experimental(m):
         lib.mpn_set_pdl(0)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("MPN_TEST_EXPERIMENTAL") != "1",
+                    reason="the fused distance epilogue is experimental and not yet validated on hardware; MPN_TEST_EXPERIMENTAL=1 runs it")
+def test_fused_distance_epilogue_experimental(m):
+    """mpn_set_fused_distance(1): edge features formed by the epilogue warps of the Gram GEMM (camera-built graphs) against the
+    Gram + gather path: same arithmetic on the same accumulator, so the values are expected to agree to the last bit; the gate
+    is 1e-6.  Unequal cameras, sizes that are not tile multiples, near-duplicate rows (refine list), row-block shards."""
+    import numpy as np
+    lib = m._lib.lib()
+    try:
+        for sizes, D, seed in (((70, 90, 60, 80), 64, 1), ((124, 90, 99, 137), 2048, 2), ((300, 260, 200, 141, 123), 128, 3),
+                               ((512,) * 8, 256, 4)):
+            cam = np.repeat(np.arange(len(sizes)), sizes)
+            N = int(cam.size)
+            gen = torch.Generator().manual_seed(seed)
+            x = torch.randn(N, D, generator=gen)
+            x[N // 2] = x[3] + 1e-4 * torch.randn(D, generator=gen)            # same-identity pairs: cancellation -> refine list
+            x[N - 1] = x[0]
+            x = torch.nn.functional.normalize(x, p=2, dim=0).to(dev())
+            for block in (None, (0, N // 3), (N // 3, N)):
+                g = m.TrackletGraph.from_cameras(cam, dev(), row_block=block)
+                assert g.struct.flags & m._lib.GRAPH_ONE_GAP_ROWS
+                assert lib.mpn_set_fused_distance(0) == 1
+                ref = m.edge_features(x, None, graph=g)
+                assert lib.mpn_set_fused_distance(1) == 2
+                got = torch.full((g.n_edges, 2), float("nan"), device=dev())          # every edge must be written by the fused path
+                assert m.edge_features(x, None, graph=g, out=got) is got
+                again = m.edge_features(x, None, graph=g)
+                torch.cuda.synchronize()
+                assert torch.isfinite(got).all() and torch.equal(got, again)
+                err = (got - ref).abs().max().item()
+                assert err <= 1e-6, "fused distance epilogue differs from the gather path by %g (N=%d D=%d block=%s)" % (err, N, D, block)
+        # end to end: decisions of the forward with the features computed inside it
+        params = mo.shipped_model_params(1, 1, 64, (48, 40))
+        net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+        net.load_state_dict(mo.init_weights(params, "resnet101", 5), strict=True)
+        net = net.to(dev()).eval()
+        net.fuse_decisions = True
+        x, ei, cam, _ = mo.synth_graph(3000, 6, 9, D=64, planted=True)
+        preds = []
+        for on in (0, 1):
+            lib.mpn_set_fused_distance(on)
+            d = Data(x=x.to(dev()), edge_index=None, mpn_graph=m.TrackletGraph.from_cameras(cam.numpy(), dev()), edge_attr=None)
+            net(d)
+            preds.append((net.last_pred.clone(), d.edge_attr.clone()))
+        assert (preds[0][1] - preds[1][1]).abs().max().item() <= 1e-6
+        assert (preds[0][0] != preds[1][0]).sum().item() <= 2
+    finally:
+        lib.mpn_set_fused_distance(0)
+
+
 class _NoComm:
     world, rank = 1, 0
 
