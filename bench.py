@@ -521,7 +521,8 @@ def run_ours(args):
                         "int64_edge_index": {"value": E_total / (e2e_ei_ms * 1e-3), "ms_per_step": e2e_ei_ms,
                                              "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8}},
                 "gpu_launches": int(launches), "clocks": clk}
-        knobs = {"pdl": lib.mpn_set_pdl(-1) == 2, "graph_replay": os.environ.get("MPN_BENCH_GRAPH_REPLAY") == "1"}
+        knobs = {"pdl": lib.mpn_set_pdl(-1) == 2, "fused_distance": lib.mpn_set_fused_distance(-1) == 2,
+                 "graph_replay": os.environ.get("MPN_BENCH_GRAPH_REPLAY") == "1"}
         if any(knobs.values()):                        # experimental switches (off by default) label the line they produced
             line["experimental"] = knobs
     if world == 1:
