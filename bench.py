@@ -522,6 +522,7 @@ def run_ours(args):
                                              "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8}},
                 "gpu_launches": int(launches), "clocks": clk}
         knobs = {"pdl": lib.mpn_set_pdl(-1) == 2, "fused_distance": lib.mpn_set_fused_distance(-1) == 2,
+                 "apply_arrive": os.environ.get("MPN_ATC_ARRIVE", "0")[:1] == "1",
                  "graph_replay": os.environ.get("MPN_BENCH_GRAPH_REPLAY") == "1"}
         if any(knobs.values()):                        # experimental switches (off by default) label the line they produced
             line["experimental"] = knobs

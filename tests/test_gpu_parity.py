@@ -502,6 +502,40 @@ def test_fused_distance_epilogue_experimental(m):
         lib.mpn_set_fused_distance(0)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("MPN_TEST_EXPERIMENTAL") != "1",
+                    reason="MPN_ATC_ARRIVE (mbarrier arrive instead of the block barrier in the apply sweep) is experimental; "
+                           "MPN_TEST_EXPERIMENTAL=1 runs it")
+def test_apply_sweep_arrive_variant_experimental(m):
+    """Same arithmetic, different synchronisation: logits, h and decisions must be bit-identical, run after run."""
+    import os
+    params = mo.shipped_model_params(3, 2, 64, (48, 40))
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(mo.init_weights(params, "resnet101", 31), strict=True)
+    net = net.to(dev()).eval()
+    net.fuse_decisions = True
+    old = os.environ.get("MPN_ATC_ARRIVE")
+    try:
+        for N, C_, chunk in ((600, 3, 128), (4096, 8, None), (1500, 5, 256)):
+            x, ei, _, _ = mo.synth_graph(N, C_, 13, D=64, planted=True)
+            outs = []
+            for on in ("0", "1", "1", "0"):
+                os.environ["MPN_ATC_ARRIVE"] = on
+                d = Data(x=x.to(dev()), edge_index=ei.to(dev()))
+                d.mpn_graph = m.TrackletGraph(d.edge_index, N, chunk=chunk)
+                d.edge_attr = m.edge_features(d.x, None, graph=d.mpn_graph)
+                out, h = net(d)
+                torch.cuda.synchronize()
+                outs.append([t.clone() for t in out["classified_edges"]] + [h.clone(), net.last_pred.clone()])
+            for o in outs[1:]:
+                for a, b in zip(outs[0], o):
+                    assert torch.equal(a, b)
+    finally:
+        if old is None:
+            os.environ.pop("MPN_ATC_ARRIVE", None)
+        else:
+            os.environ["MPN_ATC_ARRIVE"] = old
+
+
 class _NoComm:
     world, rank = 1, 0
 

@@ -11,12 +11,12 @@ mkdir -p gpurun_out
   bash ${CSRC}/build.sh && timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
   echo "== PDL build"
   MPN_PDL=1 bash ${CSRC}/build.sh
-  echo "== experimental parity tests (graph replay, PDL, fused distance epilogue)"
+  echo "== experimental parity tests (graph replay, PDL, fused distance epilogue, apply-sweep arrive)"
   MPN_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -k experimental -q 2>&1 | tail -15
   echo "== A/B table"
   timeout 600 python tools/gap_experiments.py 30
   echo "== bench with every switch on (labelled 'experimental' in its line)"
-  MPN_PDL_LAUNCH=1 MPN_FUSED_DISTANCE=1 timeout 600 python bench.py --steps 20 --warmup 3 | tail -1 > gpurun_out/bench_experimental.json
+  MPN_PDL_LAUNCH=1 MPN_FUSED_DISTANCE=1 MPN_ATC_ARRIVE=1 timeout 600 python bench.py --steps 20 --warmup 3 | tail -1 > gpurun_out/bench_experimental.json
   echo "== back to the default build"
   bash ${CSRC}/build.sh
 } 2>&1 | tee gpurun_out/experimental_gpu_pass.log

@@ -4,6 +4,7 @@
     pdl                        same, programmatic dependent launch on   (needs `MPN_PDL=1 csrc/build.sh`; skipped otherwise)
     graph                      the same calls captured once as a CUDA graph and replayed
     graph+pdl                  captured with the launch attribute on (programmatic edges inside the graph)
+    arrive                     eager with MPN_ATC_ARRIVE=1: the apply sweep's block barrier replaced by an mbarrier arrive
     cameras                    tables from the camera ids (bench.py's e2e path without the copies), Gram + gather
     cameras+fused[+pdl][+graph]    the fused distance epilogue of the Gram GEMM (mpn_set_fused_distance), alone and combined
 
@@ -119,6 +120,15 @@ def main():
             rows[name] = {"error": str(exc)}
         finally:
             lib.mpn_set_pdl(0)
+    # apply sweep: mbarrier arrive instead of the per-iteration block barrier (read from the environment at every launch)
+    os.environ["MPN_ATC_ARRIVE"] = "1"
+    try:
+        record("arrive", step)
+    except Exception as exc:
+        print("%-22s failed: %s" % ("arrive", exc))
+        rows["arrive"] = {"error": str(exc)}
+    finally:
+        os.environ["MPN_ATC_ARRIVE"] = "0"
     # camera-built graphs: Gram + gather against the fused distance epilogue (mpn_set_fused_distance)
     record("cameras", step_cameras)
     for name, fused, pdl, graph in (("cameras+fused", 1, 0, 0), ("cameras+fused+pdl", 1, 1, 0), ("cameras+fused+graph", 1, 0, 1),
