@@ -15,7 +15,6 @@ MPN_SUMS_DOUBLES = 96
 ABI_VERSION = 4             # MPN_B200_ABI_VERSION of include/mpn_b200.h (bumped when a struct or a signature changes)
 STAGE_ENC0, STAGE_ENC1, STAGE_EDGE, STAGE_NODE, STAGE_APPLY = range(5)
 POST_CUT, POST_PRUNE, POST_SPLIT = 1, 2, 4
-GRAPH_ONE_GAP_ROWS = 1      # MPN_GRAPH_ONE_GAP_ROWS (mpn_graph.flags)
 
 # offsets inside mpn_weights.small (floats) — keep in sync with include/mpn_b200.h
 W_ENC1_W, W_ENC1_B, W_ENC1_G, W_ENC1_BETA = 0, 8, 12, 16
@@ -28,7 +27,7 @@ W_EDGE_W0, W_NODE_W0, W_SMALL_FLOATS = 1592, 1864, 2888
 
 class MpnGraph(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_cols", C.c_int32), ("row_offset", C.c_int32), ("chunk", C.c_int32),
-                ("n_edges", C.c_int64), ("max_tasks", C.c_int32), ("flags", C.c_int32),
+                ("n_edges", C.c_int64), ("max_tasks", C.c_int32), ("reserved", C.c_int32),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("taskptr", C.c_void_p), ("task_row", C.c_void_p),
                 ("n_tasks", C.c_void_p), ("n_graphs", C.c_int32), ("max_graph_nodes", C.c_int32),
                 ("node_gid", C.c_void_p), ("graph_nptr", C.c_void_p)]

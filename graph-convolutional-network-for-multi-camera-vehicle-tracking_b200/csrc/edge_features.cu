@@ -118,61 +118,18 @@ __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_grap
                                                                   float2* __restrict__ edge_attr,
                                                                   int* __restrict__ refine_list, int* __restrict__ refine_count) {
   pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int t0 = g.taskptr[r0], t1 = g.taskptr[r1];
-  const double eps = (double)PAIRWISE_EPS;
-  for (int t = t0 + gwarp; t < t1; t += nwarps) {
-    const int row = g.task_row[t];
-    const int beg = g.rowptr[row] + (t - g.taskptr[row]) * g.chunk;
-    const int end = min(beg + g.chunk, g.rowptr[row + 1]);
-    const size_t grow = (size_t)(row + g.row_offset);
-    const float4 sta = st[grow];
-    const double sa = sta.x, xa = sta.y, ma = sta.z, na = sta.w;
-    const float* Grow = G + (size_t)(row - r0) * g.n_cols;
-    int cshift = 0;
-    if (g_off != nullptr) {                               // batched: this row's block-diagonal Gram block
-      const int gi = g.node_gid[row];
-      const int base = g.graph_nptr[gi], ng = g.graph_nptr[gi + 1] - base;
-      Grow = G + g_off[gi] + (size_t)(row - base) * ng;
-      cshift = base;
-    }
-    constexpr int U = 4;                                   // independent col -> (G, st) gathers in flight per lane
-    for (int base = beg; base < end; base += 32 * U) {
-      int c[U];
-      bool ok[U];
-      float gv[U];
-      float sb[U], xb[U], mb[U], nb[U];
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const int e = base + 32 * j + lane;
-        ok[j] = e < end;
-        c[j] = g.col[ok[j] ? e : end - 1];
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        gv[j] = Grow[c[j] - cshift];
-        const float4 s4 = __ldg(st + c[j]);
-        sb[j] = s4.x; xb[j] = s4.y; mb[j] = s4.z; nb[j] = s4.w;
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        if (!ok[j]) continue;
-        const int e = base + 32 * j + lane;
-        const double gij = gv[j];
-        double d2 = sa + (double)sb[j] - 2.0 * gij + 2.0 * eps * (xa - (double)xb[j]) + D * eps * eps;
-        if (d2 < (double)REFINE_FRACTION * (sa + (double)sb[j])) {
-          const int slot = atomicAdd(refine_count, 1);
-          refine_list[slot] = e;
-        }
-        if (d2 < 0.0) d2 = 0.0;
-        const double ab = gij + ma + (double)mb[j];
-        const float denom = fmaxf((float)na * nb[j], COSINE_EPS);
-        edge_attr[e] = make_float2(sqrtf((float)d2), 1.0f - (float)ab / denom);
-      }
-    }
-  }
+#include "edge_feature_gather.inc"
+}
+// the same pass behind the fused distance epilogue: nothing to do when the GEMM's epilogue wrote the features itself
+__global__ void __launch_bounds__(256) edge_feature_gather_unless_fused_kernel(const mpn_graph g, int r0, int r1, const float* __restrict__ G,
+                                                                               const float4* __restrict__ st, int D,
+                                                                               float2* __restrict__ edge_attr, int* __restrict__ refine_list,
+                                                                               int* __restrict__ refine_count,
+                                                                               const int* __restrict__ not_one_gap) {
+  pdl_wait();
+  if (*not_one_gap == 0) return;
+  const long long* g_off = nullptr;
+#include "edge_feature_gather.inc"
 }
 
 // direct recomputation for the flagged pairs (one warp per pair), fp32 elementwise like ATen
@@ -211,19 +168,25 @@ __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_grap
   }
 }
 
-// EXPERIMENTAL fused distance epilogue: (first column, length) of the one gap in each row's column list.  Rows are strictly
-// ascending (K0), so col[beg+k] - k is non-decreasing: 0 before the gap, the gap length after it -> binary search.
-__global__ void __launch_bounds__(256) gap_table_kernel(const mpn_graph g, int2* __restrict__ gap) {
+// EXPERIMENTAL fused distance epilogue: (first column, length) of the one gap in each row's column list, and the proof that
+// the row has that shape.  Columns are strictly ascending within a row (K0), so col[beg+k] - k is non-decreasing: 0 before
+// the gap, the gap length after it -> binary search for the first k with col[beg+k] != k.  The row is "all columns but
+// [k, k+gl)" iff the entry after the gap is k+gl and the last entry is n_cols-1 (deg-k strictly ascending values in a range
+// of exactly deg-k integers); the prefix is 0..k-1 by the search invariant.  Any other row raises *not_one_gap.
+__global__ void __launch_bounds__(256) gap_table_kernel(const mpn_graph g, int2* __restrict__ gap, int* __restrict__ not_one_gap) {
   pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= g.n_nodes) return;
   const int beg = g.rowptr[r], deg = g.rowptr[r + 1] - beg;
+  const int gl = g.n_cols - deg;
   int lo = 0, hi = deg;                                  // first k with col[beg+k] != k (deg: the gap is at the end)
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (g.col[beg + mid] == mid) lo = mid + 1; else hi = mid;
   }
-  gap[r] = make_int2(lo, g.n_cols - deg);
+  gap[r] = make_int2(lo, gl);
+  const bool ok = gl >= 0 && (lo == deg || (g.col[beg + lo] == lo + gl && g.col[beg + deg - 1] == g.n_cols - 1));
+  if (!ok) atomicOr(not_one_gap, 1);
 }
 
 struct EfLayout {
@@ -237,7 +200,8 @@ struct EfLayout {
   void* gemm_ws;
   size_t gemm_ws_bytes;
   int rows_per_block;
-  int2* gap;                       // fused distance epilogue: one-gap table of the rows (last slice: the other offsets do not move)
+  int2* gap;                       // fused distance epilogue: one-gap table of the rows (last slices: the other offsets do not move)
+  int* not_one_gap;
   size_t total;
 };
 
@@ -263,6 +227,7 @@ static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) 
   L.gemm_ws_bytes = batched ? gemm_tc_workspace_bytes(1, g->n_cols, D) : gemm_tc_workspace_bytes((int)rows, g->n_cols, D);
   L.gemm_ws = L.gemm_ws_bytes ? (void*)a.take<char>(L.gemm_ws_bytes) : nullptr;
   L.gap = a.take<int2>((size_t)(g->n_nodes > 0 ? g->n_nodes : 1));
+  L.not_one_gap = a.take<int>(1);
   L.total = a.off;
   return L;
 }
@@ -316,19 +281,23 @@ int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge
     MPN_LAUNCH_OK();
     return MPN_OK;
   }
-  // EXPERIMENTAL (mpn_set_fused_distance, off by default): distances formed by the epilogue warps of the Gram GEMM for graphs
-  // whose builder promises one-gap rows (MPN_GRAPH_ONE_GAP_ROWS: mpn_graph_build_cross_camera)
-  if (g_fused_distance && use_tc && (g->flags & MPN_GRAPH_ONE_GAP_ROWS) != 0 &&
-      gram_ef_supported(min(L.rows_per_block, g->n_nodes), g->n_cols, D, (const float*)L.amax_bits)) {
-    mpn::launch(gap_table_kernel, div_up(g->n_nodes, 256), 256, 0, st, *g, L.gap);
+  // EXPERIMENTAL (mpn_set_fused_distance, off by default): distances formed by the epilogue warps of the Gram GEMM when every
+  // row of the graph is "all columns but one gap" (decided on the device; otherwise the same launches store the Gram block
+  // and gather from it as below)
+  if (g_fused_distance && use_tc && gram_ef_supported(min(L.rows_per_block, g->n_nodes), g->n_cols, D, (const float*)L.amax_bits)) {
+    MPN_CUDA_OK(cudaMemsetAsync(L.not_one_gap, 0, sizeof(int), st));
+    mpn::launch(gap_table_kernel, div_up(g->n_nodes, 256), 256, 0, st, *g, L.gap, L.not_one_gap);
     MPN_LAUNCH_OK();
     for (int r0 = 0; r0 < g->n_nodes; r0 += L.rows_per_block) {
       const int r1 = min(r0 + L.rows_per_block, g->n_nodes);
       EfEpilogue ef;
-      ef.st = L.st; ef.rowptr = g->rowptr; ef.gap = L.gap; ef.edge_attr = (float2*)edge_attr;
+      ef.st = L.st; ef.rowptr = g->rowptr; ef.gap = L.gap; ef.not_one_gap = L.not_one_gap; ef.edge_attr = (float2*)edge_attr;
       ef.refine_list = L.refine_list; ef.refine_count = L.refine_count;
       ef.row_local0 = r0; ef.row_global0 = g->row_offset + r0; ef.D = D;
-      MPN_TRY(gram_nt_tc(L.xc, g->row_offset + r0, nullptr, r1 - r0, g->n_cols, D, (const float*)L.amax_bits, L.gemm_ws, L.gemm_ws_bytes, st, &ef));
+      MPN_TRY(gram_nt_tc(L.xc, g->row_offset + r0, L.G, r1 - r0, g->n_cols, D, (const float*)L.amax_bits, L.gemm_ws, L.gemm_ws_bytes, st, &ef));
+      mpn::launch(edge_feature_gather_unless_fused_kernel, kNumSMs * 8, 256, 0, st, *g, r0, r1, L.G, L.st, D, (float2*)edge_attr,
+                  L.refine_list, L.refine_count, L.not_one_gap);
+      MPN_LAUNCH_OK();
     }
     mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
     MPN_LAUNCH_OK();

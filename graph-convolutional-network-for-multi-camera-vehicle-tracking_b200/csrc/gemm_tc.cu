@@ -117,7 +117,10 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     M = N = ng;
     C += g_off[blockIdx.z];
   }
+  bool ef_on = false;                                    // block-uniform: the graph has the one-gap shape
+  if constexpr (EF) ef_on = *ef.not_one_gap == 0;
   if constexpr (EF) {
+   if (ef_on) {
     // a tile without edges (all of its rows have their gap across all of its columns: a same-camera tile) skips the main loop
     int no_edges = 1;
     if (threadIdx.x < TC_BM) {
@@ -135,6 +138,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       }
     }
     if (__syncthreads_and(no_edges)) return;
+   }
   }
 
   if (threadIdx.x == 0) {
@@ -215,7 +219,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     float4 st_row = make_float4(0.f, 0.f, 0.f, 0.f);
     int rp_row = 0, gap0 = 0, gap1 = 0;
     if constexpr (EF) {
-      if (row < M) {
+      if (ef_on && row < M) {
         st_row = ef.st[ef.row_global0 + row];
         rp_row = ef.rowptr[ef.row_local0 + row];
         const int2 gp = ef.gap[ef.row_local0 + row];
@@ -238,6 +242,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = F16 ? (v[j] + w[j]) * oscale : v[j] + w[j];
       if constexpr (EF) {
+       if (ef_on) {
         if (row < M) {
           // direct entries (row -> col): 32 consecutive edges of this thread's row, but for the gap
 #pragma unroll
@@ -260,6 +265,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
           }
         }
         continue;
+       }
       }
       if (row < M) {
         float* out = C + (size_t)row * N + n0 + c0;
@@ -607,9 +613,10 @@ int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const 
   MPN_TRY(make_map(&bh, hi, N, K, 128, true));
   MPN_TRY(make_map(&bl, lo, N, K, 128, true));
   if (ef != nullptr) {
+    MPN_REQUIRE(C != nullptr && ef->not_one_gap != nullptr, "fused distance epilogue: the Gram block is the fallback and must exist");
     if (a_row0 == 0 && M == N && ef->row_local0 == 0 && ef->row_global0 == 0)
-      return launch_tc<128, true, true, true>(ah, al, bh, bl, nullptr, nullptr, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, *ef);
-    return launch_tc<128, false, true, true>(ah, al, bh, bl, nullptr, nullptr, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, *ef);
+      return launch_tc<128, true, true, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, *ef);
+    return launch_tc<128, false, true, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, *ef);
   }
   if (a_row0 == 0 && M == N) return launch_tc<128, true, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);
   return launch_tc<128, false, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);

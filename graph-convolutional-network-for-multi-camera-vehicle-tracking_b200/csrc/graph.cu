@@ -284,7 +284,6 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n
     if (k < n_cams) run += (long long)(cam_ptr[k + 1] - cam_ptr[k]) * (n_total - (cam_ptr[k + 1] - cam_ptr[k]));
   }
   cudaStream_t st = (cudaStream_t)stream;
-  g->flags |= MPN_GRAPH_ONE_GAP_ROWS;                 // every row: all columns but the node's own camera segment
   const long long work = E > g->n_nodes ? E : g->n_nodes + 1;
   mpn::launch(cross_camera_kernel, (int)min((long long)kNumSMs * 16, (work + 255) / 256), 256, 0, st, L, n_total, g->row_offset, g->n_nodes, gbase, E,
                                                                                           g->rowptr, g->col, (long long*)edge_index_out);

@@ -15,11 +15,14 @@ constexpr float REFINE_FRACTION = 0.25f;
 // EXPERIMENTAL (mpn_set_fused_distance): the distance epilogue inside the Gram GEMM.  For graphs whose rows are "all columns
 // but one contiguous gap" (dense cross-camera graphs: the gap is the node's own camera) the edge id of the ordered pair
 // (i, j) is closed-form, e = rowptr[i] + j - (j past the gap ? gap length : 0), so the epilogue warps turn the accumulator
-// straight into edge_attr rows: no Gram matrix in HBM, no gather launch.
+// straight into edge_attr rows: no Gram matrix in HBM, no gather pass.  Whether a graph has that shape is decided on the
+// device (gap_table_kernel verifies every row and raises *not_one_gap otherwise): the kernel then falls back to storing the
+// Gram block, and the gather kernel that follows — skipped when the flag is clear — does the work as before.
 struct EfEpilogue {
   const float4* st;        // [n_cols] per-node statistics of the centred rows (center_rows_kernel), global node ids
   const int* rowptr;       // [n_rows+1] of the graph (local rows)
   const int2* gap;         // [n_rows] (first column of the gap, length of the gap) of each local row, global column ids
+  const int* not_one_gap;  // device flag: 0 = every row has the one-gap shape (fused epilogue), else store the Gram block
   float2* edge_attr;       // [E]
   int* refine_list;
   int* refine_count;
@@ -44,7 +47,7 @@ int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t s
 // Gram block of the row block [a_row0, a_row0+M) of X [N,K] against all of X: 3xFP16 planes scaled by max|X| (amax_dev: float
 // bits on the device) when K % 8 == 0, else / when amax_dev is NULL the TF32 path of gemm_nt_tc
 int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const float* amax_dev, void* workspace, size_t workspace_bytes,
-               cudaStream_t st, const EfEpilogue* ef = nullptr);   // ef: fused distance epilogue (fp16 planes only; C unused)
+               cudaStream_t st, const EfEpilogue* ef = nullptr);   // ef: fused distance epilogue (fp16 planes only; C = its fallback)
 bool gram_ef_supported(int M, int N, int K, const float* amax_dev);
 bool gemm_tc_supported(int M, int N, int K);
 // 3xFP16 variant for the node encoder: A is split here into fp16 planes (fused BatchNorm+ReLU; plane scale from a_amax_host, or

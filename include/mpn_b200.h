@@ -53,9 +53,11 @@ uint64_t mpn_kernel_launches(void);
  * 1 = switch is off, 2 = switch is on (initial state: on iff the environment has MPN_PDL_LAUNCH=1). */
 int mpn_set_pdl(int enable);
 /* EXPERIMENTAL (off by default, not yet validated on hardware): form the edge features (inference.py:453-456) in the epilogue
- * of the Gram GEMM — TMEM accumulator -> distance / cosine -> edge_attr, no Gram matrix in HBM and no gather launch — for graphs
- * flagged MPN_GRAPH_ONE_GAP_ROWS.  enable > 0 / == 0 switches it on / off, < 0 only queries; returns 1 = off, 2 = on
- * (initial state: on iff the environment has MPN_FUSED_DISTANCE=1).  Other graphs keep the Gram + gather path. */
+ * of the Gram GEMM — TMEM accumulator -> distance / cosine -> edge_attr, no Gram matrix in HBM and no gather pass — for graphs
+ * whose every row is "all columns but one contiguous gap" (dense cross-camera graphs: the gap is the node's own camera), which
+ * is checked on the device in the same call; any other graph takes the Gram + gather path inside the same launches.
+ * enable > 0 / == 0 switches it on / off, < 0 only queries; returns 1 = off, 2 = on (initial state: on iff the environment has
+ * MPN_FUSED_DISTANCE=1). */
 int mpn_set_fused_distance(int enable);
 /* 0 if device `dev` exists and is sm_100; error otherwise.  Never falls back to CPU. */
 int mpn_check_device(int dev);
@@ -68,10 +70,6 @@ int mpn_check_device(int dev);
  * (inference.py:407-413); MPN_ERR_UNSORTED otherwise (the Python host then sorts and permutes).
  * A task is a run of <= `chunk` consecutive edges of one row; max_tasks = E / chunk + N.
  * ---------------------------------------------------------------------------------------------- */
-/* mpn_graph.flags: every row's column list is all of [0, n_cols) but ONE contiguous gap (dense cross-camera graphs: the gap
- * is the node's own camera).  Set by mpn_graph_build_cross_camera; lets the edge id of a pair be computed instead of looked up. */
-#define MPN_GRAPH_ONE_GAP_ROWS 1
-
 typedef struct mpn_graph {
   int32_t n_nodes;          /* nodes whose rows this table holds (all nodes of the graph, or a row block) */
   int32_t n_cols;           /* size of the column (neighbour) id space: total nodes of the graph */
@@ -79,7 +77,7 @@ typedef struct mpn_graph {
   int32_t chunk;            /* edges per task (power of two, 32..4096) */
   int64_t n_edges;
   int32_t max_tasks;        /* capacity of task_row / task_beg */
-  int32_t flags;            /* MPN_GRAPH_* bits, 0 unless a builder sets them (was `reserved`, always 0: same layout) */
+  int32_t reserved;
   int32_t* rowptr;          /* dev [n_nodes+1]  */
   int32_t* col;             /* dev [n_edges]    global column ids */
   int32_t* taskptr;         /* dev [n_nodes+1]  first task of each row */

@@ -13,9 +13,11 @@ from oracle import mpn_oracle as mo
 BM = BN = 128
 
 
-def gap_table(rowptr, col, n_cols):
-    """gap_table_kernel: first k with col[beg+k] != k (binary search on the non-decreasing col[beg+k] - k), gap length."""
+def gap_table(rowptr, col, n_cols, with_flag=False):
+    """gap_table_kernel: first k with col[beg+k] != k (binary search on the non-decreasing col[beg+k] - k), gap length, and
+    the two end-point checks that prove the row is 'all columns but that gap' (else the not_one_gap flag is raised)."""
     gap = np.zeros((rowptr.size - 1, 2), dtype=np.int64)
+    not_one_gap = 0
     for r in range(rowptr.size - 1):
         beg, deg = rowptr[r], rowptr[r + 1] - rowptr[r]
         lo, hi = 0, deg
@@ -25,8 +27,11 @@ def gap_table(rowptr, col, n_cols):
                 lo = mid + 1
             else:
                 hi = mid
-        gap[r] = (lo, n_cols - deg)
-    return gap
+        gl = n_cols - deg
+        gap[r] = (lo, gl)
+        ok = gl >= 0 and (lo == deg or (col[beg + lo] == lo + gl and col[beg + deg - 1] == n_cols - 1))
+        not_one_gap |= int(not ok)
+    return (gap, not_one_gap) if with_flag else gap
 
 
 def replay(rowptr, gap, row0, M, N, sym):
@@ -111,3 +116,19 @@ def test_same_camera_tiles_are_skipped():
     assert len(writes) == ei.shape[1]
     assert skipped == 3 + 6 + 3            # upper-triangular tiles inside the cameras: 2x2, 3x3, 2x2 blocks of 128
     assert run + skipped == 7 * 8 // 2
+
+
+def test_one_gap_shape_is_recognised_exactly():
+    """The device-side check must accept exactly the rows that are 'all columns but one contiguous gap' (strictly ascending
+    columns are K0's precondition): brute force over every column subset of a small id space."""
+    n = 7
+    for mask in range(1 << n):
+        cols = np.array([c for c in range(n) if mask >> c & 1], dtype=np.int64)
+        rowptr = np.array([0, cols.size], dtype=np.int64)
+        (gap,), flag = gap_table(rowptr, cols, n, with_flag=True)
+        missing = [c for c in range(n) if not mask >> c & 1]
+        one_gap = len(missing) == 0 or missing == list(range(missing[0], missing[0] + len(missing)))
+        assert (flag == 0) == one_gap, (mask, gap, flag)
+        if one_gap:
+            expect = np.array([c for c in range(n) if not (gap[0] <= c < gap[0] + gap[1])])
+            assert np.array_equal(expect, cols)

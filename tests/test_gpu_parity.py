@@ -455,7 +455,7 @@ def test_programmatic_dependent_launch_experimental(m):
 @pytest.mark.skipif(__import__("os").environ.get("MPN_TEST_EXPERIMENTAL") != "1",
                     reason="the fused distance epilogue is experimental and not yet validated on hardware; MPN_TEST_EXPERIMENTAL=1 runs it")
 def test_fused_distance_epilogue_experimental(m):
-    """mpn_set_fused_distance(1): edge features formed by the epilogue warps of the Gram GEMM (camera-built graphs) against the
+    """mpn_set_fused_distance(1): edge features formed by the epilogue warps of the Gram GEMM (one-gap graphs) against the
     Gram + gather path: same arithmetic on the same accumulator, so the values are expected to agree to the last bit; the gate
     is 1e-6.  Unequal cameras, sizes that are not tile multiples, near-duplicate rows (refine list), row-block shards."""
     import numpy as np
@@ -472,7 +472,6 @@ def test_fused_distance_epilogue_experimental(m):
             x = torch.nn.functional.normalize(x, p=2, dim=0).to(dev())
             for block in (None, (0, N // 3), (N // 3, N)):
                 g = m.TrackletGraph.from_cameras(cam, dev(), row_block=block)
-                assert g.struct.flags & m._lib.GRAPH_ONE_GAP_ROWS
                 assert lib.mpn_set_fused_distance(0) == 1
                 ref = m.edge_features(x, None, graph=g)
                 assert lib.mpn_set_fused_distance(1) == 2
@@ -483,6 +482,25 @@ def test_fused_distance_epilogue_experimental(m):
                 assert torch.isfinite(got).all() and torch.equal(got, again)
                 err = (got - ref).abs().max().item()
                 assert err <= 1e-6, "fused distance epilogue differs from the gather path by %g (N=%d D=%d block=%s)" % (err, N, D, block)
+        # graphs from an int64 edge_index take the same path (the shape is recognised on the device) ...
+        x, ei, cam, _ = mo.synth_graph(1100, 5, 4, D=64, planted=True)
+        xd, eid = x.to(dev()), ei.to(dev())
+        lib.mpn_set_fused_distance(0)
+        ref = m.edge_features(xd, eid)
+        lib.mpn_set_fused_distance(1)
+        got = torch.full_like(ref, float("nan"))
+        m.edge_features(xd, None, graph=m.TrackletGraph(eid, 1100), out=got)
+        assert (got - ref).abs().max().item() <= 1e-6
+        # ... and a graph that is not "all columns but one gap" falls back to the Gram + gather pass inside the same launches
+        keep = torch.rand(ei.shape[1], generator=torch.Generator().manual_seed(0)) < 0.7
+        keep[:5] = torch.tensor([True, False, True, False, True])
+        eit = ei[:, keep].contiguous().to(dev())
+        lib.mpn_set_fused_distance(0)
+        ref = m.edge_features(xd, eit)
+        lib.mpn_set_fused_distance(1)
+        got = torch.full_like(ref, float("nan"))
+        m.edge_features(xd, None, graph=m.TrackletGraph(eit, 1100), out=got)
+        assert torch.equal(got, ref)
         # end to end: decisions of the forward with the features computed inside it
         params = mo.shipped_model_params(1, 1, 64, (48, 40))
         net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")

@@ -42,8 +42,6 @@ def test_fused_distance_switch_defaults_off():
     if os.environ.get("MPN_FUSED_DISTANCE") != "1":
         assert lib.mpn_set_fused_distance(-1) == 1             # 1 = off, 2 = on
     assert lib.mpn_set_fused_distance(1) == 2 and lib.mpn_set_fused_distance(0) == 1
-    assert m._lib.GRAPH_ONE_GAP_ROWS == int(re.search(r"#define MPN_GRAPH_ONE_GAP_ROWS (\d+)",
-                                                      open(os.path.join(ROOT, "include", "mpn_b200.h")).read()).group(1))
 
 
 def test_no_device_fails_loudly():

@@ -5,8 +5,8 @@
     graph                      the same calls captured once as a CUDA graph and replayed
     graph+pdl                  captured with the launch attribute on (programmatic edges inside the graph)
     arrive                     eager with MPN_ATC_ARRIVE=1: the apply sweep's block barrier replaced by an mbarrier arrive
-    cameras                    tables from the camera ids (bench.py's e2e path without the copies), Gram + gather
-    cameras+fused[+pdl][+graph]    the fused distance epilogue of the Gram GEMM (mpn_set_fused_distance), alone and combined
+    fused[+pdl][+graph][+arrive]   the fused distance epilogue of the Gram GEMM (mpn_set_fused_distance), alone and combined
+    cameras, cameras+fused...  the same with the tables built from the camera ids (bench.py's e2e path without the copies)
 
 Every variant is checked bit for bit against the eager decisions before it is timed (L2 flushed between calls, CUDA events,
 median of `reps`).  Diagnostic: prints a table and writes gpurun_out/gap_experiments.json.
@@ -98,7 +98,7 @@ def main():
         med, best = timeit(fn)
         rows[name] = {"median_ms": med, "min_ms": best, "G_edges_per_s": E / med / 1e6, "decisions_that_differ": diff,
                       "launch_calls_per_step": (lib.mpn_kernel_launches() - l0) / (reps + 3)}
-        print("%-22s median %.3f ms  min %.3f ms  %.2f G edges/s  decisions that differ from eager: %d" %
+        print("%-30s median %.3f ms  min %.3f ms  %.2f G edges/s  decisions that differ from eager: %d" %
               (name, med, best, E / med / 1e6, diff), flush=True)
 
     record("eager", step)
@@ -116,7 +116,7 @@ def main():
             cg, out = captured()
             record(name, cg.replay, out)
         except Exception as exc:                       # a capture that fails must not hide the other rows
-            print("%-22s failed: %s" % (name, exc))
+            print("%-30s failed: %s" % (name, exc))
             rows[name] = {"error": str(exc)}
         finally:
             lib.mpn_set_pdl(0)
@@ -125,30 +125,34 @@ def main():
     try:
         record("arrive", step)
     except Exception as exc:
-        print("%-22s failed: %s" % ("arrive", exc))
+        print("%-30s failed: %s" % ("arrive", exc))
         rows["arrive"] = {"error": str(exc)}
     finally:
         os.environ["MPN_ATC_ARRIVE"] = "0"
-    # camera-built graphs: Gram + gather against the fused distance epilogue (mpn_set_fused_distance)
+    # the fused distance epilogue (mpn_set_fused_distance), alone and combined, on both ways of building the graph tables
     record("cameras", step_cameras)
-    for name, fused, pdl, graph in (("cameras+fused", 1, 0, 0), ("cameras+fused+pdl", 1, 1, 0), ("cameras+fused+graph", 1, 0, 1),
-                                    ("cameras+fused+graph+pdl", 1, 1, 1)):
-        if pdl and not has_pdl:
-            continue
-        lib.mpn_set_fused_distance(fused)
-        lib.mpn_set_pdl(pdl)
-        try:
-            if graph:
-                cg, out = captured(step_cameras)
-                record(name, cg.replay, out)
-            else:
-                record(name, step_cameras)
-        except Exception as exc:
-            print("%-22s failed: %s" % (name, exc))
-            rows[name] = {"error": str(exc)}
-        finally:
-            lib.mpn_set_fused_distance(0)
-            lib.mpn_set_pdl(0)
+    for base, fn in (("", step), ("cameras+", step_cameras)):
+        for name, pdl, graph, arrive in (("fused", 0, 0, 0), ("fused+pdl", 1, 0, 0), ("fused+graph", 0, 1, 0),
+                                         ("fused+graph+pdl", 1, 1, 0), ("fused+graph+pdl+arrive", 1, 1, 1)):
+            if pdl and not has_pdl:
+                continue
+            name = base + name
+            lib.mpn_set_fused_distance(1)
+            lib.mpn_set_pdl(pdl)
+            os.environ["MPN_ATC_ARRIVE"] = "1" if arrive else "0"
+            try:
+                if graph:
+                    cg, out = captured(fn)
+                    record(name, cg.replay, out)
+                else:
+                    record(name, fn)
+            except Exception as exc:
+                print("%-30s failed: %s" % (name, exc))
+                rows[name] = {"error": str(exc)}
+            finally:
+                lib.mpn_set_fused_distance(0)
+                lib.mpn_set_pdl(0)
+                os.environ["MPN_ATC_ARRIVE"] = "0"
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/gap_experiments.json", "w") as f:
         json.dump({"workload": bench.workload_name(N, E, 1), "reps": reps, "rows": rows}, f, indent=1)
