@@ -1,0 +1,129 @@
+"""The plain-C post-processing oracle (oracle/postproc_oracle.c) pinned on the CPU: against the outputs of the unmodified reference
+(tests/golden/post_*.npz), against the Python restatement (statement mirror and rounds) on random predicted graphs, against
+networkx's SCC emission order, and on the edge cases the reference meets (no edges, no active edges, one-directional cycles)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import postproc_c as pc
+from oracle import postproc_oracle as po
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+POST_FILES = sorted(glob.glob(os.path.join(GOLDEN, "post_*.npz")))
+FLAG_SETS = (("full", (True, True, True)), ("cut_only", (True, False, False)), ("prune_only", (False, True, False)),
+             ("split_only", (False, False, True)), ("cut_prune", (True, True, False)))
+
+
+@pytest.mark.parametrize("path", POST_FILES, ids=[os.path.basename(p)[:-4] for p in POST_FILES])
+def test_c_oracle_matches_reference_golden(path):
+    g = np.load(path)
+    N, C, _seed = [int(v) for v in g["spec"]]
+    src, dst = g["src"].astype(np.int64), g["dst"].astype(np.int64)
+    prob, pred = g["prob1"], g["pred"].astype(np.int64)
+    lab0, n0 = pc.scc_labels(src, dst, pred, N)
+    assert np.array_equal(lab0, g["labels_initial"]) and n0 == int(lab0.max()) + 1
+    for tag, cfg in FLAG_SETS:
+        lab, act = pc.post_processing(src, dst, pred, prob, C, N, *cfg, numbering="reference")
+        assert np.array_equal(act, g["pred_" + tag]), tag                      # decisions: bit-exact
+        assert np.array_equal(lab, g["labels_" + tag]), tag                    # label integers: bit-exact
+        lab_c, act_c = pc.post_processing(src, dst, pred, prob, C, N, *cfg, numbering="canonical")
+        assert np.array_equal(act_c, act)
+        assert np.array_equal(lab_c, po.scc_partition_canonical(src, dst, act, N))
+
+
+def test_c_oracle_equals_python_oracle_small_dense():
+    for seed in range(12):
+        N, C = 30 + 5 * seed, 3 + seed % 3
+        src, dst, prob, pred, _ = po.planted_prediction_graph(N, C, 1000 + seed, flip_on=0.06, flip_off=0.04, single_dir=0.03,
+                                                              dense=True)
+        lab_s, act_s = po.post_processing_sequential(src, dst, pred, prob, C, N)
+        lab_c, act_c = pc.post_processing(src, dst, pred, prob, C, N, numbering="reference")
+        assert np.array_equal(act_s, act_c) and np.array_equal(lab_s, lab_c)
+
+
+@pytest.mark.parametrize("n_nodes,seed", [(3000, 5), (20000, 6), (200000, 7)])
+def test_c_oracle_equals_python_rounds_sparse(n_nodes, seed):
+    C = 6
+    src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, C, seed, flip_on=0.04, flip_off=0.03, single_dir=0.02)
+    for cfg in ((True, True, True), (False, True, True), (True, False, True)):
+        lab_r, act_r = po.post_processing_rounds(src, dst, pred, prob, C, n_nodes, *cfg, numbering="canonical")
+        lab_c, act_c = pc.post_processing(src, dst, pred, prob, C, n_nodes, *cfg, numbering="canonical")
+        assert np.array_equal(act_r, act_c) and np.array_equal(lab_r, lab_c)
+    if n_nodes <= 20000:                                                        # (the Python Tarjan mirror is interpreter-bound)
+        lab_r, act_r = po.post_processing_rounds(src, dst, pred, prob, C, n_nodes, numbering="reference")
+        lab_c, act_c = pc.post_processing(src, dst, pred, prob, C, n_nodes, numbering="reference")
+        assert np.array_equal(act_r, act_c) and np.array_equal(lab_r, lab_c)
+
+
+def test_c_oracle_stages_equal_python_stages():
+    N, C = 4000, 5
+    src, dst, prob, pred, _ = po.planted_prediction_graph(N, C, 11, flip_on=0.05, flip_off=0.03, single_dir=0.03)
+    rev = po.reverse_edge_map(src, dst, N)
+    assert np.array_equal(pc.reverse_edge_map(src, dst, N), rev)
+    cut_py = po.cut_rounds(pred, rev)
+    assert np.array_equal(pc.cut(src, dst, pred, N), cut_py.astype(np.int64))
+    pr_py, ch_py = po.prune_rounds(src, dst, cut_py, prob, C, N)
+    pr_c, ch_c = pc.prune(src, dst, cut_py, prob, C, N)
+    assert ch_c == ch_py and np.array_equal(pr_c, pr_py.astype(np.int64))
+    sp_py = po.split_rounds(src, dst, pr_py, prob, C, N)
+    assert np.array_equal(pc.split(src, dst, pr_py, prob, C, N), sp_py.astype(np.int64))
+    # unsorted edge order (the reverse map then sorts its keys)
+    perm = np.random.default_rng(0).permutation(src.size)
+    rev_p = pc.reverse_edge_map(src[perm], dst[perm], N)
+    assert np.array_equal(rev_p, po.reverse_edge_map(src[perm], dst[perm], N))
+
+
+def test_c_tarjan_order_matches_networkx():
+    nx = pytest.importorskip("networkx")
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n = int(rng.integers(5, 40))
+        m = int(rng.integers(1, 4 * n))
+        src, dst = rng.integers(0, n, m), rng.integers(0, n, m)
+        keep = src != dst
+        src, dst = src[keep], dst[keep]
+        if src.size == 0:
+            continue
+        G = nx.DiGraph(list(zip(src.tolist(), dst.tolist())))
+        sccs = sorted(nx.strongly_connected_components(G), key=len)            # utils.py:31
+        expect = np.full(n, -1, dtype=np.int64)
+        for k, s in enumerate(sccs):
+            expect[list(s)] = k
+        k = len(sccs)
+        for i in range(n):                                                      # utils.py:34-42
+            if expect[i] < 0:
+                expect[i] = k
+                k += 1
+        lab, n_comp = pc.scc_labels(src, dst, np.ones(src.size, dtype=np.int64), n)
+        assert n_comp == k and np.array_equal(lab, expect)
+
+
+def test_c_oracle_edge_cases():
+    e = np.zeros(0, dtype=np.int64)
+    lab, act = pc.post_processing(e, e, e, np.zeros(0, dtype=np.float32), 4, 5, numbering="reference")
+    assert act.size == 0 and np.array_equal(lab, np.arange(5))
+    src, dst = np.array([0, 1, 2, 3]), np.array([1, 2, 0, 0])                  # a one-directional 3-cycle + a tail
+    prob = np.array([0.9, 0.8, 0.7, 0.6], dtype=np.float32)
+    lab, act = pc.post_processing(src, dst, np.zeros(4, dtype=np.int64), prob, 4, 4, numbering="reference")
+    assert not act.any() and np.array_equal(lab, np.arange(4))                  # nothing active: singletons in index order
+    lab, _ = pc.scc_labels(src, dst, np.ones(4, dtype=np.int64), 4)
+    lab_py, _ = po.scc_labels_reference(src, dst, np.ones(4, dtype=np.int64), 4)
+    assert np.array_equal(lab, lab_py)
+    lab, act = pc.post_processing(src, dst, np.ones(4, dtype=np.int64), prob, 4, 4, cutting=True, pruning=False,
+                                  splitting=False, numbering="reference")
+    assert not act.any()                                                         # no edge has its reverse: CUT removes all
+    with pytest.raises(RuntimeError):
+        pc.post_processing(np.array([0, 9]), np.array([1, 0]), np.ones(2, dtype=np.int64), prob[:2], 4, 4)   # node id out of range
+
+
+def test_c_oracle_pins_the_gpu_case():
+    """The input of tests/test_zz_c_oracle_gpu.py (GPU vs C oracle): here the C oracle against the Python rounds oracle."""
+    from tests.test_zz_c_oracle_gpu import GPU_CASE as c
+    src, dst, prob, pred, _ = po.planted_prediction_graph(c["n_nodes"], c["cams"], c["seed"], n_extra_per_node=c["n_extra_per_node"],
+                                                          flip_on=c["flip_on"], flip_off=c["flip_off"], single_dir=c["single_dir"])
+    lab_r, act_r = po.post_processing_rounds(src, dst, pred, prob, c["cams"], c["n_nodes"], numbering="reference")
+    lab_c, act_c = pc.post_processing(src, dst, pred, prob, c["cams"], c["n_nodes"], numbering="reference")
+    assert np.array_equal(act_r, act_c) and np.array_equal(lab_r, lab_c)
+    assert np.bincount(lab_c).max() <= c["cams"] and int(act_c.sum()) > 0
