@@ -72,6 +72,7 @@ static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / 
 // (griddepcontrol.wait), blocks every thread until the predecessor grid has completed and its writes are visible, so only
 // the launch latency overlaps.  Rule: pdl_wait() is the FIRST statement of every kernel launched through launch(), before any
 // early return (a grid whose blocks all skipped it would let its own successor overtake the predecessor).
+// MPN_PDL=2 additionally triggers the dependent launch at the top of every kernel (see pdl_wait()).
 #ifndef MPN_PDL
 #define MPN_PDL 0
 #endif
@@ -82,6 +83,13 @@ extern int g_fused_distance;         // run-time switch of the fused distance ep
 __device__ __forceinline__ void pdl_wait() {
 #if MPN_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+#if MPN_PDL >= 2
+  // MPN_PDL=2: also release the NEXT kernel right away.  Its blocks become resident as soon as every block of this grid has
+  // started and resources are free, and then sit in their own griddepcontrol.wait (which still waits for this grid to complete
+  // and flush): block launch and prologue leave the critical path.  For the persistent sweeps (all blocks resident from the
+  // start) that is the whole run; for grids launched in waves it is the last wave.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
 

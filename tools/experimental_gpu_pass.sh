@@ -13,8 +13,12 @@ mkdir -p gpurun_out
   MPN_PDL=1 bash ${CSRC}/build.sh
   echo "== experimental parity tests (graph replay, PDL, fused distance epilogue, apply-sweep arrive)"
   MPN_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -k experimental -q 2>&1 | tail -15
-  echo "== A/B table"
-  timeout 600 python tools/gap_experiments.py 30
+  echo "== A/B table (MPN_PDL=1: griddepcontrol.wait only)"
+  timeout 600 python tools/gap_experiments.py 30 pdl1
+  echo "== A/B table (MPN_PDL=2: every kernel also triggers its dependent launch at the top)"
+  MPN_PDL=2 bash ${CSRC}/build.sh
+  MPN_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests -m gpu -k "dependent_launch" -q 2>&1 | tail -3
+  timeout 600 python tools/gap_experiments.py 30 pdl2
   echo "== bench with every switch on (labelled 'experimental' in its line)"
   MPN_PDL_LAUNCH=1 MPN_FUSED_DISTANCE=1 MPN_ATC_ARRIVE=1 timeout 600 python bench.py --steps 20 --warmup 3 | tail -1 > gpurun_out/bench_experimental.json
   echo "== back to the default build"

@@ -12,7 +12,7 @@ Every variant is checked bit for bit against the eager decisions before it is ti
 median of `reps`).  Diagnostic: prints a table and writes gpurun_out/gap_experiments.json.
 
     MPN_PDL=1 bash graph-convolutional-network-for-multi-camera-vehicle-tracking_b200/csrc/build.sh
-    python tools/gap_experiments.py [reps]
+    python tools/gap_experiments.py [reps [tag]]          # MPN_PDL=2 csrc/build.sh: early trigger as well (see common.cuh)
 """
 import json
 import os
@@ -27,6 +27,7 @@ import gcn_mtmc_b200 as m
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+    tag = sys.argv[2] if len(sys.argv) > 2 else ""      # suffix of the output file (e.g. the build variant)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     m._lib.require_device(0)
@@ -154,7 +155,7 @@ def main():
                 lib.mpn_set_pdl(0)
                 os.environ["MPN_ATC_ARRIVE"] = "0"
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/gap_experiments.json", "w") as f:
+    with open("gpurun_out/gap_experiments%s.json" % (("_" + tag) if tag else ""), "w") as f:
         json.dump({"workload": bench.workload_name(N, E, 1), "reps": reps, "rows": rows}, f, indent=1)
 
 
