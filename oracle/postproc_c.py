@@ -34,8 +34,9 @@ def lib():
         l.po_cut.argtypes = [p, p, p, i64, i64]
         l.po_prune.argtypes = [p, p, p, p, i64, i64, i32, C.POINTER(i32)]
         l.po_split.argtypes = [p, p, p, p, i64, i64, i32]
+        l.po_split_sequential.argtypes = [p, p, p, p, i64, i64, i32]
         l.po_post_processing.argtypes = [p, p, p, p, i64, i64, i32, i32, i32, i32, i32, p, p]
-        for f in (l.po_scc_labels, l.po_reverse_map, l.po_cut, l.po_prune, l.po_split, l.po_post_processing):
+        for f in (l.po_scc_labels, l.po_reverse_map, l.po_cut, l.po_prune, l.po_split, l.po_split_sequential, l.po_post_processing):
             f.restype = i32
         _lib = l
     return _lib
@@ -90,6 +91,15 @@ def split(src, dst, act, prob, num_cameras: int, n_nodes: int):
     src, dst, act, prob = _i64(src), _i64(dst), _i64(act).copy(), _f32(prob)
     _check(lib().po_split(src.ctypes.data, dst.ctypes.data, act.ctypes.data, prob.ctypes.data, src.size, n_nodes, num_cameras),
            "po_split")
+    return act
+
+
+def split_sequential(src, dst, act, prob, num_cameras: int, n_nodes: int):
+    """splitting (utils.py:54-123) in the reference's own order, one cluster and one SCC pass per dropped value: the exact
+    semantics under probability ties, for graphs up to ~10^5 active edges."""
+    src, dst, act, prob = _i64(src), _i64(dst), _i64(act).copy(), _f32(prob)
+    _check(lib().po_split_sequential(src.ctypes.data, dst.ctypes.data, act.ctypes.data, prob.ctypes.data, src.size, n_nodes,
+                                     num_cameras), "po_split_sequential")
     return act
 
 

@@ -279,6 +279,53 @@ static int split_rounds(const i64* src, const i64* dst, uint8_t* act, const floa
   return PO_OK;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SPLITTING exactly as the reference orders it (utils.py:54-123), one cluster at a time: l = lowest label with more than C
+ * nodes in the reference numbering; drop (globally, float ==) the minimum-probability value among the active edges touching
+ * cluster l; relabel; continue on l AS RE-READ IN THE NEW NUMBERING (utils.py:112) while that cluster is oversized, else
+ * look for the next oversized cluster.  One SCC pass per dropped value: for graphs up to ~10^5 active edges.  Differs from
+ * split_rounds only under cross-cluster probability ties (oracle/postproc_oracle.py::split_rounds).
+ * ---------------------------------------------------------------------------------------------------------------- */
+static int reference_labels(const i64* src, const i64* dst, const uint8_t* act, i64 E, i64 N, i64* labels, i64* count /*[N]*/) {
+  i64* comp = (i64*)malloc(sizeof(i64) * (size_t)(N > 0 ? N : 1));
+  i64* sizes = NULL;
+  if (!comp) return PO_ERR_ALLOC;
+  const i64 nc = scc_emission_order(src, dst, act, E, N, comp, &sizes);
+  if (nc < 0) { free(comp); return PO_ERR_ALLOC; }
+  i64* cnt = (i64*)calloc((size_t)N + 2, sizeof(i64));
+  i64* rank = (i64*)malloc(sizeof(i64) * (size_t)(nc > 0 ? nc : 1));
+  if (!cnt || !rank) { free(cnt); free(rank); free(comp); free(sizes); return PO_ERR_ALLOC; }
+  for (i64 c = 0; c < nc; ++c) cnt[sizes[c] + 1]++;
+  for (i64 k = 0; k <= N; ++k) cnt[k + 1] += cnt[k];
+  for (i64 c = 0; c < nc; ++c) rank[c] = cnt[sizes[c]]++;
+  i64 total = nc;
+  memset(count, 0, sizeof(i64) * (size_t)N);
+  for (i64 v = 0; v < N; ++v) { labels[v] = comp[v] >= 0 ? rank[comp[v]] : total++; count[labels[v]]++; }
+  free(cnt); free(rank); free(comp); free(sizes);
+  return PO_OK;
+}
+static int split_sequential(const i64* src, const i64* dst, uint8_t* act, const float* prob, i64 E, i64 N, int C) {
+  i64* labels = (i64*)malloc(sizeof(i64) * (size_t)(N > 0 ? N : 1));
+  i64* count = (i64*)malloc(sizeof(i64) * (size_t)(N > 0 ? N : 1));
+  if (!labels || !count) { free(labels); free(count); return PO_ERR_ALLOC; }
+  int rc = reference_labels(src, dst, act, E, N, labels, count);
+  while (rc == PO_OK) {
+    i64 l = -1;
+    for (i64 k = 0; k < N; ++k) if (count[k] > C) { l = k; break; }       /* lowest oversized label (utils.py:60-64) */
+    if (l < 0) break;
+    for (;;) {
+      float m = INFINITY;
+      for (i64 e = 0; e < E; ++e)                                          /* either endpoint in the cluster (utils.py:71) */
+        if (act[e] && (labels[src[e]] == l || labels[dst[e]] == l) && prob[e] < m) m = prob[e];
+      for (i64 e = 0; e < E; ++e) if (prob[e] == m) act[e] = 0;            /* global float equality (utils.py:96-98) */
+      rc = reference_labels(src, dst, act, E, N, labels, count);
+      if (rc != PO_OK || !(count[l] > C)) break;                           /* l re-read in the NEW numbering (utils.py:112) */
+    }
+  }
+  free(labels); free(count);
+  return rc;
+}
+
 /* stage entry points (each takes and returns int64 activity vectors like the reference's `predictions`) */
 int po_cut(const i64* src, const i64* dst, i64* act64, i64 E, i64 N) {
   if (E < 0 || N < 0 || (E > 0 && (!src || !dst || !act64))) return PO_ERR_ARG;
@@ -310,6 +357,17 @@ int po_split(const i64* src, const i64* dst, i64* act64, const float* prob, i64 
   if (!act) return PO_ERR_ALLOC;
   for (i64 e = 0; e < E; ++e) act[e] = act64[e] != 0;
   const int rc = split_rounds(src, dst, act, prob, E, N, num_cameras);
+  if (rc == PO_OK) for (i64 e = 0; e < E; ++e) act64[e] = act[e];
+  free(act);
+  return rc;
+}
+
+int po_split_sequential(const i64* src, const i64* dst, i64* act64, const float* prob, i64 E, i64 N, int num_cameras) {
+  if (E < 0 || N < 0 || (E > 0 && (!src || !dst || !act64 || !prob))) return PO_ERR_ARG;
+  uint8_t* act = (uint8_t*)malloc((size_t)(E > 0 ? E : 1));
+  if (!act) return PO_ERR_ALLOC;
+  for (i64 e = 0; e < E; ++e) act[e] = act64[e] != 0;
+  const int rc = split_sequential(src, dst, act, prob, E, N, num_cameras);
   if (rc == PO_OK) for (i64 e = 0; e < E; ++e) act64[e] = act[e];
   free(act);
   return rc;

@@ -8,6 +8,9 @@ Two restatements of the reference post-processing (integer / index work, bit-exa
   that scales to 1e8 edges; ``tests/test_oracle_postproc.py`` checks both against each other and
   against golden outputs of the real reference (``tests/golden/make_golden.py``).
 
+Under exact probability ties across oversized clusters the rounds formulation of SPLITTING can differ from the reference's
+one-cluster-at-a-time order; see ``split_rounds`` (``report_ties``) and ``oracle/postproc_oracle.c::po_split_sequential``.
+
 Parity status: pinned only by outputs of the reference itself generated in the build container
 ("parity unpinned" by upstream tests: there are none).
 
@@ -247,16 +250,26 @@ def prune_rounds(src, dst, act, prob, num_cameras, n_nodes):
         act[rem] = False
 
 
-def split_rounds(src, dst, act, prob, num_cameras, n_nodes):
+def split_rounds(src, dst, act, prob, num_cameras, n_nodes, report_ties=False):
+    """SPLITTING as rounds: every oversized cluster drops its minimum-probability edge(s) in the same round.
+
+    Equal to the reference's one-cluster-at-a-time loop (``split_sequential``) whenever no round has a *cross-cluster tie*: a
+    minimum m_A of an oversized cluster A that is also the probability of an active edge touching ANOTHER oversized cluster B
+    with m_A > m_B.  The reference compares floats with ``==`` globally (utils.py:96-98), so in its order B may lose that edge
+    while A is processed and no longer need to drop its own minimum, whereas here B drops its minimum in the same round.
+    (Equal minima of two clusters are harmless, and so are ties with edges of clusters that are not oversized.)  Exact fp32
+    ties between different edges' softmax outputs do not occur in generic inputs; ``report_ties=True`` also returns the number
+    of rounds in which the condition above held, i.e. in which the equivalence is not guaranteed."""
     src, dst = np.asarray(src), np.asarray(dst)
     prob = np.asarray(prob)
     act = np.array(act, dtype=bool, copy=True)
+    tie_rounds = 0
     while True:
         lab = scc_partition_canonical(src, dst, act, n_nodes)
         size = np.bincount(lab, minlength=n_nodes)
         big = size > num_cameras
         if not big.any():
-            return act
+            return (act, tie_rounds) if report_ties else act
         a = np.flatnonzero(act)
         m = np.full(n_nodes, np.inf, dtype=np.float64)
         ls, ld = lab[src[a]], lab[dst[a]]
@@ -264,6 +277,11 @@ def split_rounds(src, dst, act, prob, num_cameras, n_nodes):
         np.minimum.at(m, ls[s_ok], prob[a][s_ok])
         np.minimum.at(m, ld[d_ok], prob[a][d_ok])
         vals = np.unique(m[np.isfinite(m)]).astype(prob.dtype)
+        if report_ties and vals.size > 1:
+            pa = prob[a]
+            hit = np.isin(pa, vals)                    # active edges whose probability is some cluster's minimum ...
+            tie = (hit & s_ok & (pa > m[ls])) | (hit & d_ok & (pa > m[ld]))   # ... but not the minimum of an oversized cluster they touch
+            tie_rounds += bool(tie.any())
         act &= ~np.isin(prob, vals)                    # every edge anywhere with prob in {m_l}
 
 

@@ -127,3 +127,44 @@ def test_c_oracle_pins_the_gpu_case():
     lab_c, act_c = pc.post_processing(src, dst, pred, prob, c["cams"], c["n_nodes"], numbering="reference")
     assert np.array_equal(act_r, act_c) and np.array_equal(lab_r, lab_c)
     assert np.bincount(lab_c).max() <= c["cams"] and int(act_c.sum()) > 0
+
+
+def test_c_split_sequential_is_the_statement_mirror_under_ties():
+    """po_split_sequential (the reference's own order, one cluster at a time) against the Python statement mirror on heavily
+    tied probabilities, where the order matters."""
+    rng = np.random.default_rng(5)
+    n_checked = 0
+    for trial in range(300):
+        n, C = int(rng.integers(6, 28)), int(rng.integers(2, 5))
+        cam = np.sort(rng.integers(0, C, n))
+        s, d = np.nonzero(cam[:, None] != cam[None, :])
+        keep = rng.random(s.size) < rng.uniform(0.5, 1.0)
+        s, d = s[keep], d[keep]
+        if s.size == 0:
+            continue
+        prob = (np.round(rng.random(s.size) * 10) / 10).astype(np.float32)
+        pred = (prob > 0.5).astype(np.int64)
+        start = po.cut_sequential(s, d, pred) if trial % 2 else pred
+        assert np.array_equal(pc.split_sequential(s, d, start, prob, C, n), po.split_sequential(s, d, start, prob, C, n))
+        n_checked += 1
+    assert n_checked > 250
+
+
+@pytest.mark.parametrize("n_nodes,cams,seed", [(3000, 6, 1), (20000, 8, 2), (20000, 8, 5)])
+def test_rounds_equal_the_reference_order_on_the_gpu_test_graphs(n_nodes, cams, seed):
+    """The graphs of the GPU parity tests (tests/test_gpu_parity.py, same generator arguments): the rounds formulation the CUDA
+    path implements gives exactly what the reference's one-cluster-at-a-time SPLITTING gives (the exact order is affordable in
+    C at this size), including the graph on which split_rounds reports cross-cluster ties."""
+    src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, cams, seed, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03,
+                                                          single_dir=0.05)
+    if n_nodes == 20000 and seed == 5:                                          # (the sharded test sorts its edges)
+        order = np.lexsort((dst, src))
+        src, dst, prob, pred = src[order], dst[order], prob[order], pred[order]
+    act = pc.cut(src, dst, pred, n_nodes)
+    act, _ = pc.prune(src, dst, act, prob, cams, n_nodes)
+    act = pc.cut(src, dst, act, n_nodes)
+    exact = pc.split_sequential(src, dst, act, prob, cams, n_nodes)
+    rounds = pc.split(src, dst, act, prob, cams, n_nodes)
+    assert np.array_equal(exact, rounds)
+    lab, act_full = pc.post_processing(src, dst, pred, prob, cams, n_nodes, numbering="reference")
+    assert np.array_equal(act_full, exact)

@@ -91,3 +91,35 @@ def test_rounds_equal_sequential_random():
         lab_r, act_r = po.post_processing_rounds(src, dst, pred, prob, C, N, numbering="reference")
         assert np.array_equal(act_s, act_r)
         assert np.array_equal(lab_s, lab_r)
+
+
+def test_split_rounds_equal_sequential_unless_cross_cluster_tie():
+    """Heavily tied probabilities (one decimal): the rounds formulation of SPLITTING (what the CUDA path runs) equals the
+    reference's one-cluster-at-a-time loop in every run without a cross-cluster tie, and ``report_ties`` flags every run in
+    which it does not.  CUT and PRUNE agree under ties as well (first index on equal probabilities)."""
+    rng = np.random.default_rng(123)
+    differ_flagged = ties_seen = 0
+    for trial in range(500):
+        n, C = int(rng.integers(6, 28)), int(rng.integers(2, 5))
+        cam = np.sort(rng.integers(0, C, n))
+        s, d = np.nonzero(cam[:, None] != cam[None, :])
+        keep = rng.random(s.size) < rng.uniform(0.5, 1.0)
+        s, d = s[keep], d[keep]
+        if s.size == 0:
+            continue
+        prob = (np.round(rng.random(s.size) * 10) / 10).astype(np.float32)
+        pred = (prob > 0.5).astype(np.int64)
+        act = po.cut_sequential(s, d, pred)
+        assert np.array_equal(act, po.cut_rounds(pred, po.reverse_edge_map(s, d, n)).astype(np.int64))
+        pr_s = po.prune_sequential(s, d, act, prob, C, n)
+        pr_r, changed = po.prune_rounds(s, d, act, prob, C, n)
+        assert (pr_s is None) == (not changed)
+        assert np.array_equal(act if pr_s is None else pr_s, pr_r.astype(np.int64))
+        start = act if trial % 2 else pred
+        sp_s = po.split_sequential(s, d, start, prob, C, n)
+        sp_r, tie_rounds = po.split_rounds(s, d, start, prob, C, n, report_ties=True)
+        ties_seen += tie_rounds > 0
+        if not np.array_equal(sp_s, sp_r.astype(np.int64)):
+            assert tie_rounds > 0, "rounds differ from the statement mirror without a cross-cluster tie (trial %d)" % trial
+            differ_flagged += 1
+    assert ties_seen > 0 and differ_flagged > 0        # the generator does reach the condition
