@@ -35,8 +35,9 @@ def lib():
         l.po_prune.argtypes = [p, p, p, p, i64, i64, i32, C.POINTER(i32)]
         l.po_split.argtypes = [p, p, p, p, i64, i64, i32]
         l.po_split_sequential.argtypes = [p, p, p, p, i64, i64, i32]
+        l.po_split_hybrid.argtypes = [p, p, p, p, i64, i64, i32, p]
         l.po_post_processing.argtypes = [p, p, p, p, i64, i64, i32, i32, i32, i32, i32, p, p]
-        for f in (l.po_scc_labels, l.po_reverse_map, l.po_cut, l.po_prune, l.po_split, l.po_split_sequential, l.po_post_processing):
+        for f in (l.po_scc_labels, l.po_reverse_map, l.po_cut, l.po_prune, l.po_split, l.po_split_sequential, l.po_split_hybrid, l.po_post_processing):
             f.restype = i32
         _lib = l
     return _lib
@@ -101,6 +102,16 @@ def split_sequential(src, dst, act, prob, num_cameras: int, n_nodes: int):
     _check(lib().po_split_sequential(src.ctypes.data, dst.ctypes.data, act.ctypes.data, prob.ctypes.data, src.size, n_nodes,
                                      num_cameras), "po_split_sequential")
     return act
+
+
+def split_hybrid(src, dst, act, prob, num_cameras: int, n_nodes: int):
+    """SPLITTING in the reference's order where probability ties make the order matter, all clusters per iteration elsewhere
+    (design study, see the C source).  -> (act, {'tie_values', 'iterations', 'tainted_steps'})."""
+    src, dst, act, prob = _i64(src), _i64(dst), _i64(act).copy(), _f32(prob)
+    stats = np.zeros(3, dtype=np.int64)
+    _check(lib().po_split_hybrid(src.ctypes.data, dst.ctypes.data, act.ctypes.data, prob.ctypes.data, src.size, n_nodes,
+                                 num_cameras, stats.ctypes.data), "po_split_hybrid")
+    return act, dict(tie_values=int(stats[0]), iterations=int(stats[1]), tainted_steps=int(stats[2]))
 
 
 def post_processing(src, dst, pred, prob, num_cameras: int, n_nodes: int, cutting=True, pruning=True, splitting=True,

@@ -326,6 +326,83 @@ static int split_sequential(const i64* src, const i64* dst, uint8_t* act, const 
   return rc;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SPLITTING, exact AND scalable (design study for the CUDA path): the reference's order only
+ * matters between clusters that can meet a probability tie.  T = the probability values carried by two or more active edges
+ * that touch oversized clusters when SPLITTING starts (edges never gain clusters and clusters never grow, so no tie outside T
+ * can ever arise).  An oversized cluster is TAINTED while an active edge touching it has a value in T.
+ *   - untainted oversized clusters: all drop their minimum in the same iteration (their values are not in T, so they cannot
+ *     touch another oversized cluster: order-independent, as in split_rounds);
+ *   - tainted oversized clusters: one per iteration, the lowest label of the reference numbering, exactly as the reference
+ *     picks it (utils.py:60-64,112).
+ * Equal to split_sequential (tests/test_c_oracle.py) except for one third-order effect that is not modelled: the emission
+ * order of two tainted clusters of EQUAL size could depend on whether an untainted cluster that connects them through
+ * one-directional edges has already been processed.
+ * ---------------------------------------------------------------------------------------------------------------- */
+static int in_sorted(const float* v, i64 n, float x) {
+  i64 lo = 0, hi = n;
+  while (lo < hi) {
+    const i64 mid = (lo + hi) >> 1;
+    if (v[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && v[lo] == x;
+}
+static int split_hybrid(const i64* src, const i64* dst, uint8_t* act, const float* prob, i64 E, i64 N, int C, i64* stats /*[3]*/) {
+  i64* labels = (i64*)malloc(sizeof(i64) * (size_t)(N > 0 ? N : 1));
+  i64* count = (i64*)malloc(sizeof(i64) * (size_t)(N > 0 ? N : 1));
+  uint8_t* tainted = (uint8_t*)malloc((size_t)(N > 0 ? N : 1));
+  float* mins = (float*)malloc(sizeof(float) * (size_t)(N > 0 ? N : 1));
+  float* tie = NULL;
+  float* vals = (float*)malloc(sizeof(float) * (size_t)(N > 0 ? N : 1));
+  i64 n_tie = 0;
+  if (!labels || !count || !tainted || !mins || !vals) { free(labels); free(count); free(tainted); free(mins); free(vals); return PO_ERR_ALLOC; }
+  int rc = reference_labels(src, dst, act, E, N, labels, count);
+  if (rc == PO_OK) {                                   /* T: duplicated values among the active edges touching oversized clusters */
+    i64 n = 0;
+    for (i64 e = 0; e < E; ++e) n += act[e] && (count[labels[src[e]]] > C || count[labels[dst[e]]] > C);
+    tie = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+    if (!tie) rc = PO_ERR_ALLOC;
+    else {
+      i64 k = 0;
+      for (i64 e = 0; e < E; ++e)
+        if (act[e] && (count[labels[src[e]]] > C || count[labels[dst[e]]] > C)) tie[k++] = prob[e];
+      qsort(tie, (size_t)n, sizeof(float), float_cmp);
+      for (i64 i = 0; i + 1 < n; ++i)
+        if (tie[i] == tie[i + 1] && (n_tie == 0 || tie[n_tie - 1] != tie[i])) tie[n_tie++] = tie[i];
+    }
+  }
+  stats[0] = n_tie; stats[1] = stats[2] = 0;           /* tie values, iterations, tainted steps */
+  i64 cur = -1;                                        /* label the reference's inner loop is on */
+  while (rc == PO_OK) {
+    int any = 0;
+    for (i64 k = 0; k < N; ++k) { tainted[k] = 0; mins[k] = INFINITY; any |= count[k] > C; }
+    if (!any) break;
+    ++stats[1];
+    for (i64 e = 0; e < E; ++e) {
+      if (!act[e]) continue;
+      const i64 ls = labels[src[e]], ld = labels[dst[e]];
+      const int hit = n_tie > 0 && in_sorted(tie, n_tie, prob[e]);
+      if (count[ls] > C) { if (prob[e] < mins[ls]) mins[ls] = prob[e]; tainted[ls] |= hit; }
+      if (count[ld] > C) { if (prob[e] < mins[ld]) mins[ld] = prob[e]; tainted[ld] |= hit; }
+    }
+    i64 nv = 0;
+    /* the reference stays on label l — RE-READ in the new numbering (utils.py:112; nodes that lost every active edge move to
+     * the end of the numbering, so this need not be the lowest oversized label) — while that cluster is oversized */
+    if (!(cur >= 0 && cur < N && count[cur] > C && tainted[cur])) {
+      cur = -1;
+      for (i64 k = 0; k < N; ++k) if (count[k] > C && tainted[k]) { cur = k; break; }
+    }
+    for (i64 k = 0; k < N; ++k)
+      if (count[k] > C && !tainted[k]) vals[nv++] = mins[k];
+    if (cur >= 0) { vals[nv++] = mins[cur]; ++stats[2]; }
+    qsort(vals, (size_t)nv, sizeof(float), float_cmp);
+    for (i64 e = 0; e < E; ++e) if (act[e] && in_sorted(vals, nv, prob[e])) act[e] = 0;
+    rc = reference_labels(src, dst, act, E, N, labels, count);
+  }
+  free(labels); free(count); free(tainted); free(mins); free(tie); free(vals);
+  return rc;
+}
+
 /* stage entry points (each takes and returns int64 activity vectors like the reference's `predictions`) */
 int po_cut(const i64* src, const i64* dst, i64* act64, i64 E, i64 N) {
   if (E < 0 || N < 0 || (E > 0 && (!src || !dst || !act64))) return PO_ERR_ARG;
@@ -368,6 +445,17 @@ int po_split_sequential(const i64* src, const i64* dst, i64* act64, const float*
   if (!act) return PO_ERR_ALLOC;
   for (i64 e = 0; e < E; ++e) act[e] = act64[e] != 0;
   const int rc = split_sequential(src, dst, act, prob, E, N, num_cameras);
+  if (rc == PO_OK) for (i64 e = 0; e < E; ++e) act64[e] = act[e];
+  free(act);
+  return rc;
+}
+
+int po_split_hybrid(const i64* src, const i64* dst, i64* act64, const float* prob, i64 E, i64 N, int num_cameras, i64* stats) {
+  if (E < 0 || N < 0 || !stats || (E > 0 && (!src || !dst || !act64 || !prob))) return PO_ERR_ARG;
+  uint8_t* act = (uint8_t*)malloc((size_t)(E > 0 ? E : 1));
+  if (!act) return PO_ERR_ALLOC;
+  for (i64 e = 0; e < E; ++e) act[e] = act64[e] != 0;
+  const int rc = split_hybrid(src, dst, act, prob, E, N, num_cameras, stats);
   if (rc == PO_OK) for (i64 e = 0; e < E; ++e) act64[e] = act[e];
   free(act);
   return rc;

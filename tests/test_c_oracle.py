@@ -168,3 +168,41 @@ def test_rounds_equal_the_reference_order_on_the_gpu_test_graphs(n_nodes, cams, 
     assert np.array_equal(exact, rounds)
     lab, act_full = pc.post_processing(src, dst, pred, prob, cams, n_nodes, numbering="reference")
     assert np.array_equal(act_full, exact)
+
+
+def test_c_split_hybrid_is_exact_under_ties():
+    """po_split_hybrid — the reference's order only where a probability tie can make the order matter, all clusters per iteration
+    elsewhere — equals the reference-order SPLITTING on tied graphs on which the plain rounds formulation does not."""
+    n_checked = rounds_differ = 0
+    for decimals in (1, 2, 3):
+        rng = np.random.default_rng(7 + decimals)
+        for trial in range(250):
+            n, C = int(rng.integers(8, 40)), int(rng.integers(2, 5))
+            cam = np.sort(rng.integers(0, C, n))
+            s, d = np.nonzero(cam[:, None] != cam[None, :])
+            keep = rng.random(s.size) < rng.uniform(0.4, 1.0)
+            s, d = s[keep], d[keep]
+            if s.size == 0:
+                continue
+            q = 10 ** decimals
+            prob = (np.round(rng.random(s.size) * q) / q).astype(np.float32)
+            pred = (prob > 0.5).astype(np.int64)
+            start = po.cut_sequential(s, d, pred) if trial % 2 else pred
+            exact = pc.split_sequential(s, d, start, prob, C, n)
+            hybrid, stats = pc.split_hybrid(s, d, start, prob, C, n)
+            assert np.array_equal(hybrid, exact), (decimals, trial, stats)
+            rounds_differ += not np.array_equal(pc.split(s, d, start, prob, C, n), exact)
+            n_checked += 1
+    assert n_checked > 600 and rounds_differ > 0
+
+
+def test_c_split_hybrid_on_a_20k_node_graph():
+    n_nodes, cams = 20000, 8
+    src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, cams, 5, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03,
+                                                          single_dir=0.05)
+    act = pc.cut(src, dst, pred, n_nodes)
+    act, _ = pc.prune(src, dst, act, prob, cams, n_nodes)
+    act = pc.cut(src, dst, act, n_nodes)
+    hybrid, stats = pc.split_hybrid(src, dst, act, prob, cams, n_nodes)
+    assert stats["tie_values"] > 0 and stats["tainted_steps"] > 0
+    assert np.array_equal(hybrid, pc.split_sequential(src, dst, act, prob, cams, n_nodes))
