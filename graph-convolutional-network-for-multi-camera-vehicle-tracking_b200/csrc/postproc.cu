@@ -774,6 +774,50 @@ static void labels_reference(const int* src, const int* dst, long long m, int n_
   *n_comp = (int)k;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SPLITTING in the reference's own order on the host (utils.py:54-123), over the ACTIVE edge list only (an inactive edge can
+// neither be a minimum nor be switched off).  One cluster at a time: l = lowest label with more than C nodes in the reference
+// numbering; every active edge whose probability EQUALS (float ==, utils.py:96-98) the minimum over the active edges touching
+// cluster l goes; relabel; stay on l as re-read in the new numbering (utils.py:112) while that cluster is oversized.
+// One sequential Tarjan pass per dropped value: the exact semantics under probability ties, not the fast path.
+// ------------------------------------------------------------------------------------------------
+static long long split_reference(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep) {
+  std::vector<long long> idx(m);                       // surviving edges, in edge order
+  for (long long i = 0; i < m; ++i) { idx[i] = i; keep[i] = 1; }
+  std::vector<int> s(m), d(m);
+  std::vector<long long> labels(n_nodes);
+  std::vector<int> count;
+  long long steps = 0;
+  auto relabel = [&]() {
+    const long long k = (long long)idx.size();
+    for (long long i = 0; i < k; ++i) { s[i] = src[idx[i]]; d[i] = dst[idx[i]]; }
+    int nc = 0;
+    labels_reference(s.data(), d.data(), k, n_nodes, labels.data(), &nc);
+    count.assign(nc, 0);
+    for (int v = 0; v < n_nodes; ++v) count[labels[v]]++;
+  };
+  relabel();
+  for (;;) {
+    long long l = -1;
+    for (size_t k = 0; k < count.size(); ++k) if (count[k] > C) { l = (long long)k; break; }
+    if (l < 0) break;
+    for (;;) {
+      float mn = INFINITY;
+      for (long long i : idx)
+        if ((labels[src[i]] == l || labels[dst[i]] == l) && prob[i] < mn) mn = prob[i];
+      size_t w = 0;
+      for (size_t r = 0; r < idx.size(); ++r) {
+        if (prob[idx[r]] == mn) keep[idx[r]] = 0; else idx[w++] = idx[r];
+      }
+      idx.resize(w);
+      ++steps;
+      relabel();
+      if (!(l < (long long)count.size() && count[l] > C)) break;
+    }
+  }
+  return steps;
+}
+
 __global__ void clear_inactive_kernel(long long n, const int* __restrict__ eid, const uint8_t* __restrict__ keep,
                                       uint8_t* __restrict__ act) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -963,6 +1007,17 @@ int mpn_labels_reference_host(const int32_t* src, const int32_t* dst, int64_t n_
   int nc = 0;
   labels_reference(src, dst, n_active, n_nodes, (long long*)labels_out, &nc);
   if (n_components) *n_components = nc;
+  return MPN_OK;
+}
+
+int mpn_split_reference_host(const int32_t* src, const int32_t* dst, const float* prob, int64_t n_active, int32_t n_nodes,
+                             int32_t num_cameras, uint8_t* keep_out, int64_t* steps_out) {
+  MPN_REQUIRE(n_nodes > 0 && n_active >= 0 && num_cameras >= 1 && (n_active == 0 || (src && dst && prob && keep_out)),
+              "split_reference_host: bad arguments");
+  for (int64_t i = 0; i < n_active; ++i)
+    MPN_REQUIRE(src[i] >= 0 && src[i] < n_nodes && dst[i] >= 0 && dst[i] < n_nodes, "split_reference_host: node id out of range");
+  const long long steps = split_reference(src, dst, prob, n_active, n_nodes, num_cameras, keep_out);
+  if (steps_out) *steps_out = steps;
   return MPN_OK;
 }
 

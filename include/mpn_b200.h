@@ -341,6 +341,14 @@ int mpn_clear_inactive(uint8_t* act_dev, const int32_t* eid_dev, const uint8_t* 
  * assigns them — networkx SCC emission order, stable sort by size, isolated nodes last.  HOST pointers. */
 int mpn_labels_reference_host(const int32_t* src_host, const int32_t* dst_host, int64_t n_active, int32_t n_nodes,
                               int64_t* labels_out_host, int32_t* n_components_host);
+/* Host-side SPLITTING in the reference's own order (utils.py:54-123): one oversized cluster at a time — the lowest label of the
+ * reference numbering, re-read after every relabel as utils.py:112 does — dropping every active edge whose probability equals
+ * (float ==, utils.py:96-98) the minimum among the active edges touching that cluster.  Input: the ACTIVE edges in edge order
+ * (mpn_compact_active) with their probabilities; output keep_out[i] = 0 for the edges SPLITTING switches off; *steps_out = number
+ * of dropped values (one sequential SCC pass each).  The exact semantics under probability ties, where mpn_split's
+ * all-clusters-per-round schedule can differ; not the fast path.  HOST pointers. */
+int mpn_split_reference_host(const int32_t* src_host, const int32_t* dst_host, const float* prob_host, int64_t n_active,
+                             int32_t n_nodes, int32_t num_cameras, uint8_t* keep_out_host, int64_t* steps_out);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM building block (exported for tests and for the roofline bench):

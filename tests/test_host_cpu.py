@@ -122,3 +122,53 @@ def test_stream_and_sharded_post_refuse_cpu():
     g = SimpleNamespace(n_edges=4, perm=None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.CudaPostOps().compact(g, torch.ones(4, dtype=torch.uint8), torch.rand(4))
+
+
+def test_split_reference_host_matches_the_oracle_under_ties():
+    """mpn_split_reference_host (product, C++) against the independent plain-C oracle of the reference's SPLITTING order
+    (oracle/postproc_oracle.c::po_split_sequential, itself pinned against the Python statement mirror), on graphs with heavily
+    tied probabilities and on a 3 k-node planted graph.  Host pointers only: runs without a GPU."""
+    import ctypes as C
+    import numpy as np
+    from oracle import postproc_c as pc
+    from oracle import postproc_oracle as po
+    lib = m._lib.lib()
+
+    def host_split(src, dst, act, prob, cams, n_nodes):
+        a = np.flatnonzero(act)
+        s32, d32 = np.ascontiguousarray(src[a], dtype=np.int32), np.ascontiguousarray(dst[a], dtype=np.int32)
+        p32 = np.ascontiguousarray(prob[a], dtype=np.float32)
+        keep = np.empty(a.size, dtype=np.uint8)
+        steps = C.c_int64(0)
+        m._lib.check(lib.mpn_split_reference_host(s32.ctypes.data, d32.ctypes.data, p32.ctypes.data, a.size, n_nodes, cams,
+                                                  keep.ctypes.data, C.byref(steps)))
+        out = np.array(act, dtype=np.int64, copy=True)
+        out[a[keep == 0]] = 0
+        return out, int(steps.value)
+
+    rng = np.random.default_rng(17)
+    checked = 0
+    for trial in range(200):
+        n, cams = int(rng.integers(8, 40)), int(rng.integers(2, 5))
+        cam = np.sort(rng.integers(0, cams, n))
+        s, d = np.nonzero(cam[:, None] != cam[None, :])
+        keep = rng.random(s.size) < rng.uniform(0.4, 1.0)
+        s, d = s[keep], d[keep]
+        if s.size == 0:
+            continue
+        q = 10 ** (1 + trial % 3)
+        prob = (np.round(rng.random(s.size) * q) / q).astype(np.float32)
+        pred = (prob > 0.5).astype(np.int64)
+        start = po.cut_sequential(s, d, pred) if trial % 2 else pred
+        got, _ = host_split(s, d, start, prob, cams, n)
+        assert np.array_equal(got, pc.split_sequential(s, d, start, prob, cams, n)), trial
+        checked += 1
+    assert checked > 150
+    src, dst, prob, pred, _ = po.planted_prediction_graph(3000, 6, 1, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03, single_dir=0.05)
+    act = pc.cut(src, dst, pred, 3000)
+    act, _ = pc.prune(src, dst, act, prob, 6, 3000)
+    act = pc.cut(src, dst, act, 3000)
+    got, steps = host_split(src, dst, act, prob, 6, 3000)
+    assert steps > 0 and np.array_equal(got, pc.split_sequential(src, dst, act, prob, 6, 3000))
+    with pytest.raises(m._lib.MpnError):
+        m._lib.check(lib.mpn_split_reference_host(None, None, None, 3, 10, 4, None, None))
