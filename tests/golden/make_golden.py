@@ -138,6 +138,60 @@ def run_post_case(ref_utils, ref_inference, name, spec):
                                                        out["labels_full"].max() + 1))
 
 
+def tied_graphs(n_cases=10, seed=9):
+    """Small cross-camera graphs with two-decimal probabilities: exact ties between edges of different clusters, where the ORDER
+    in which the reference's splitting visits clusters decides the result.  Half of the cases are chosen so that the
+    all-clusters-per-round formulation gives different decisions than the statement mirror (search on the CPU, deterministic)."""
+    rng = np.random.default_rng(seed)
+    differ, same = [], []
+    for _ in range(4000):
+        n, C = int(rng.integers(8, 40)), int(rng.integers(2, 5))
+        cam = np.sort(rng.integers(0, C, n))
+        s, d = np.nonzero(cam[:, None] != cam[None, :])
+        keep = rng.random(s.size) < rng.uniform(0.4, 1.0)
+        s, d = s[keep], d[keep]
+        if s.size == 0:
+            continue
+        prob = (np.round(rng.random(s.size) * 100) / 100).astype(np.float32)
+        pred = (prob > 0.5).astype(np.int64)
+        seq = po.split_sequential(s, d, pred, prob, C, n)
+        rnd = po.split_rounds(s, d, pred, prob, C, n).astype(np.int64)
+        bucket = same if np.array_equal(seq, rnd) else differ
+        if len(bucket) < n_cases // 2:
+            bucket.append((s.astype(np.int64), d.astype(np.int64), prob, pred, C, n))
+        if len(differ) >= n_cases // 2 and len(same) >= n_cases // 2:
+            break
+    return differ + same
+
+
+def run_ties_cases(ref_utils, ref_inference):
+    """The unmodified reference on the tied graphs: pins the behaviour under probability ties (utils.py:96-98,112)."""
+    import networkx as nx
+    Data = sys.modules["torch_geometric.data"].Data
+    out = {}
+    cases = tied_graphs()
+    sink = io.StringIO()
+    for i, (src, dst, prob1, pred, C, N) in enumerate(cases):
+        edge_index = torch.from_numpy(np.stack([src, dst]))
+        data = Data(x=torch.zeros(N, 1), edge_index=edge_index)
+        edge_list = edge_index.numpy()
+        preds_prob = torch.from_numpy(np.stack([1 - prob1, prob1], axis=1))
+        out.update({f"k{i}_spec": np.array([N, C], dtype=np.int64), f"k{i}_src": src.astype(np.int32), f"k{i}_dst": dst.astype(np.int32),
+                    f"k{i}_prob1": prob1, f"k{i}_pred": pred.astype(np.int8)})
+        with contextlib.redirect_stdout(sink):
+            for tag, cfg in (("full", (True, True, True)), ("split_only", (False, False, True)), ("prune_split", (False, True, True))):
+                predictions = torch.from_numpy(pred.copy())
+                act_list = [(edge_list[0][p], edge_list[1][p]) for p in torch.where(predictions == 1)[0]]
+                ID0, _ = ref_utils.compute_SCC_and_Clusters(nx.DiGraph(act_list), N)
+                CONFIG = {"CUTTING": cfg[0], "PRUNING": cfg[1], "SPLITTING": cfg[2]}
+                ID, P = ref_inference.post_processing(C, ID0.clone(), act_list, predictions, edge_list, CONFIG, data, preds_prob)
+                out[f"k{i}_labels_{tag}"] = ID.numpy()
+                out[f"k{i}_pred_{tag}"] = P.numpy().astype(np.int8)
+    out["n_cases"] = np.array([len(cases)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "ties_cases.npz"), **out)
+    print("ties_cases", len(cases), "graphs")
+
+
 def run_eval_case(ref_inference):
     """compute_P_R_F of the reference (inference.py:20-66) on CPU tensors; every count is non-zero so that none of its
     `.cuda()` zero constants is reached."""
@@ -167,6 +221,8 @@ def main():
             run_post_case(ref_utils, ref_inference, name, spec)
     if not only or "eval_prf" in only:
         run_eval_case(ref_inference)
+    if not only or "ties_cases" in only:
+        run_ties_cases(ref_utils, ref_inference)
 
 
 if __name__ == "__main__":

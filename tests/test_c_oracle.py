@@ -206,3 +206,51 @@ def test_c_split_hybrid_on_a_20k_node_graph():
     hybrid, stats = pc.split_hybrid(src, dst, act, prob, cams, n_nodes)
     assert stats["tie_values"] > 0 and stats["tainted_steps"] > 0
     assert np.array_equal(hybrid, pc.split_sequential(src, dst, act, prob, cams, n_nodes))
+
+
+def _ties_cases():
+    g = np.load(os.path.join(GOLDEN, "ties_cases.npz"))
+    for i in range(int(g["n_cases"][0])):
+        N, C = [int(v) for v in g[f"k{i}_spec"]]
+        yield (i, g[f"k{i}_src"].astype(np.int64), g[f"k{i}_dst"].astype(np.int64), g[f"k{i}_prob1"], g[f"k{i}_pred"].astype(np.int64),
+               C, N, {k[len(f"k{i}_"):]: g[k] for k in g.files if k.startswith(f"k{i}_labels_") or k.startswith(f"k{i}_pred_")})
+
+
+def test_reference_order_under_ties_matches_the_reference_itself():
+    """tests/golden/ties_cases.npz: outputs of the UNMODIFIED reference on graphs with exact probability ties (two decimals), half of
+    them graphs on which the rounds formulation gives other decisions.  The statement mirror, the C restatement of the reference's
+    order, the hybrid and the product's host SPLITTING must all reproduce the reference bit for bit; the rounds formulation is
+    checked to differ on at least one case (that is what these fixtures are for)."""
+    import ctypes as C_
+    import gcn_mtmc_b200 as m
+    lib = m._lib.lib()
+    rounds_differ = n = 0
+    for i, src, dst, prob, pred, C, N, ref in _ties_cases():
+        for tag, cfg in (("full", (True, True, True)), ("split_only", (False, False, True)), ("prune_split", (False, True, True))):
+            lab_s, act_s = po.post_processing_sequential(src, dst, pred, prob, C, N, *cfg)           # Python statement mirror
+            assert np.array_equal(act_s, ref["pred_" + tag]) and np.array_equal(lab_s, ref["labels_" + tag]), (i, tag)
+            # C: CUT / PRUNE / CUT as rounds (equal to the statements, ties included), SPLITTING in the reference's order
+            act = pred
+            if cfg[0]:
+                act = pc.cut(src, dst, act, N)
+            if cfg[1]:
+                act, _ = pc.prune(src, dst, act, prob, C, N)
+            if cfg[0]:
+                act = pc.cut(src, dst, act, N)
+            exact = pc.split_sequential(src, dst, act, prob, C, N)
+            assert np.array_equal(exact, ref["pred_" + tag]), (i, tag)
+            assert np.array_equal(pc.scc_labels(src, dst, exact, N)[0], ref["labels_" + tag]), (i, tag)
+            assert np.array_equal(pc.split_hybrid(src, dst, act, prob, C, N)[0], exact), (i, tag)
+            a = np.flatnonzero(act)                                                                  # product: host SPLITTING
+            if a.size:
+                s32, d32 = np.ascontiguousarray(src[a], dtype=np.int32), np.ascontiguousarray(dst[a], dtype=np.int32)
+                p32 = np.ascontiguousarray(prob[a], dtype=np.float32)
+                keep = np.empty(a.size, dtype=np.uint8)
+                m._lib.check(lib.mpn_split_reference_host(s32.ctypes.data, d32.ctypes.data, p32.ctypes.data, a.size, N, C,
+                                                          keep.ctypes.data, None))
+                got = act.copy()
+                got[a[keep == 0]] = 0
+                assert np.array_equal(got, ref["pred_" + tag]), (i, tag)
+            rounds_differ += not np.array_equal(pc.split(src, dst, act, prob, C, N), exact)
+            n += 1
+    assert n == 30 and rounds_differ >= 5

@@ -39,48 +39,30 @@ def test_post_processing_200k_nodes_vs_c_oracle(m):
     assert np.array_equal(Pc.cpu().numpy(), act_ref) and same_partition(IDc.numpy(), lab_ref)
 
 
-def _tied_cases(n_cases=4):
-    """Small dense cross-camera graphs with two-decimal probabilities on which the rounds formulation of SPLITTING and the
-    reference's own order give different decisions (found by search on the CPU, deterministic)."""
-    rng = np.random.default_rng(9)
-    out = []
-    for trial in range(2000):
-        n, C = int(rng.integers(8, 40)), int(rng.integers(2, 5))
-        cam = np.sort(rng.integers(0, C, n))
-        s, d = np.nonzero(cam[:, None] != cam[None, :])
-        keep = rng.random(s.size) < rng.uniform(0.4, 1.0)
-        s, d = s[keep], d[keep]
-        if s.size == 0:
-            continue
-        prob = (np.round(rng.random(s.size) * 100) / 100).astype(np.float32)
-        pred = (prob > 0.5).astype(np.int64)
-        exact = pc.split_sequential(s, d, pred, prob, C, n)
-        if not np.array_equal(exact, pc.split(s, d, pred, prob, C, n)):
-            out.append((s, d, prob, pred, C, n, exact))
-            if len(out) == n_cases:
-                break
-    return out
-
-
 def test_split_order_reference_experimental(m):
-    """post_processing(split_order='reference') — SPLITTING on the host in the reference's own order — where it matters (tied
-    probabilities: the default rounds give other decisions) and where it does not (a 20 k-node planted graph)."""
+    """post_processing(split_order='reference') — SPLITTING on the host in the reference's own order — against the outputs of the
+    UNMODIFIED reference on graphs with exact probability ties (tests/golden/ties_cases.npz; on half of them the default rounds give
+    other decisions), and on a 20 k-node planted graph where the two orders agree."""
     import os
     if os.environ.get("MPN_TEST_EXPERIMENTAL") != "1":
         pytest.skip("split_order='reference' was written after the round's GPU time was spent; MPN_TEST_EXPERIMENTAL=1 runs it")
+    from tests.test_c_oracle import _ties_cases
     dev = torch.device("cuda", 0)
-    only_split = {"CUTTING": False, "PRUNING": False, "SPLITTING": True}
-    cases = _tied_cases()
-    assert len(cases) >= 2
-    for s, d, prob, pred, C, n, exact in cases:
+    rounds_differ = 0
+    for i, s, d, prob, pred, C, n, ref in _ties_cases():
         data = Data(x=torch.zeros(n, 1, device=dev), edge_index=torch.from_numpy(np.stack([s, d])).to(dev))
-        args = (C, None, None)
-        ID, P = m.post_processing(*args, torch.from_numpy(pred).to(dev), None, dict(only_split), data, torch.from_numpy(prob).to(dev),
-                                  split_order="reference")
-        assert np.array_equal(P.cpu().numpy(), exact)
-        assert np.array_equal(ID.numpy(), pc.scc_labels(s, d, exact, n)[0])
-        ID, P = m.post_processing(*args, torch.from_numpy(pred).to(dev), None, dict(only_split), data, torch.from_numpy(prob).to(dev))
-        assert np.array_equal(P.cpu().numpy(), pc.split(s, d, pred, prob, C, n))           # the default: rounds
+        for tag, cfg in (("full", (True, True, True)), ("split_only", (False, False, True)), ("prune_split", (False, True, True))):
+            CONFIG = {"CUTTING": cfg[0], "PRUNING": cfg[1], "SPLITTING": cfg[2]}
+            ID, P = m.post_processing(C, None, None, torch.from_numpy(pred).to(dev), None, dict(CONFIG), data,
+                                      torch.from_numpy(prob).to(dev), split_order="reference")
+            assert np.array_equal(P.cpu().numpy(), ref["pred_" + tag]), (i, tag)          # the reference's decisions
+            assert np.array_equal(ID.numpy(), ref["labels_" + tag]), (i, tag)             # and its label integers
+            ID, P = m.post_processing(C, None, None, torch.from_numpy(pred).to(dev), None, dict(CONFIG), data,
+                                      torch.from_numpy(prob).to(dev))                      # the default: rounds
+            lab_r, act_r = pc.post_processing(s, d, pred, prob, C, n, *cfg, numbering="reference")
+            assert np.array_equal(P.cpu().numpy(), act_r) and np.array_equal(ID.numpy(), lab_r), (i, tag)
+            rounds_differ += not np.array_equal(act_r, ref["pred_" + tag])
+    assert rounds_differ >= 5
     n_nodes, cams = 20000, 8
     src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, cams, 2, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03,
                                                           single_dir=0.05)
