@@ -1,14 +1,14 @@
 #!/usr/bin/env bash
 # One GPU call that evaluates the switched-off experimental paths: parity tests first, then the A/B table.
 # Every step runs under its own timeout so that a hang ends the step, not the box.  Outputs land in gpurun_out/.
-#   gpurun --timeout 1500 -- 'bash tools/experimental_gpu_pass.sh'
+#   gpurun --timeout 3300 -- 'bash tools/experimental_gpu_pass.sh'
 set -uo pipefail
 cd "$(dirname "${BASH_SOURCE[0]}")/.."
 CSRC=graph-convolutional-network-for-multi-camera-vehicle-tracking_b200/csrc
 mkdir -p gpurun_out
 {
   echo "== default build: shipped GPU suite (sanity)"
-  bash ${CSRC}/build.sh && timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+  bash ${CSRC}/build.sh && timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
   echo "== PDL build"
   MPN_PDL=1 bash ${CSRC}/build.sh
   echo "== experimental parity tests (graph replay, PDL, fused distance epilogue, apply-sweep arrive)"
