@@ -718,28 +718,28 @@ static int post_begin(PostCtx& c, const mpn_graph* g, const uint8_t* act, void* 
 // reference label numbering on the host (utils.py:30-52 + networkx SCC emission order)
 // ------------------------------------------------------------------------------------------------
 static void labels_reference(const int* src, const int* dst, long long m, int n_nodes, long long* labels, int* n_comp) {
+  // flat arrays throughout (one allocation each, no per-component vectors): this runs once per post_processing call on up to
+  // millions of active edges, and once per dropped value in split_reference
   std::vector<int> order;                 // nodes in first-appearance order (u then v per edge): DiGraph insertion order
-  std::vector<int> pos(n_nodes, -1);
+  order.reserve((size_t)std::min<long long>(2 * m, n_nodes));
+  std::vector<char> seen(n_nodes, 0);
+  std::vector<long long> ptr((size_t)n_nodes + 1, 0);
   for (long long i = 0; i < m; ++i) {
-    if (pos[src[i]] < 0) { pos[src[i]] = (int)order.size(); order.push_back(src[i]); }
-    if (pos[dst[i]] < 0) { pos[dst[i]] = (int)order.size(); order.push_back(dst[i]); }
+    const int u = src[i], v = dst[i];
+    if (!seen[u]) { seen[u] = 1; order.push_back(u); }
+    if (!seen[v]) { seen[v] = 1; order.push_back(v); }
+    ptr[u + 1]++;
   }
-  std::vector<long long> ptr(n_nodes + 1, 0);
-  for (long long i = 0; i < m; ++i) ptr[src[i] + 1]++;
   for (int i = 0; i < n_nodes; ++i) ptr[i + 1] += ptr[i];
-  std::vector<int> adj(m);
-  {
-    std::vector<long long> cur(ptr.begin(), ptr.end() - 1);
-    for (long long i = 0; i < m; ++i) adj[cur[src[i]]++] = dst[i];       // successor order = edge insertion order
-  }
-  std::vector<int> preorder(n_nodes, 0), lowlink(n_nodes, 0);
-  std::vector<char> found(n_nodes, 0);
+  std::vector<int> adj((size_t)m);
   std::vector<long long> cursor(ptr.begin(), ptr.end() - 1);
-  std::vector<int> queue, scc_queue;
-  std::vector<std::vector<int>> sccs;
+  for (long long i = 0; i < m; ++i) adj[cursor[src[i]]++] = dst[i];       // successor order = edge insertion order
+  for (int i = 0; i < n_nodes; ++i) cursor[i] = ptr[i];                   // now the resumable successor iterator of each node
+  std::vector<int> preorder(n_nodes, 0), lowlink(n_nodes, 0), comp(n_nodes, -1);
+  std::vector<int> queue, scc_queue, comp_size;
   int counter = 0;
   for (int source : order) {
-    if (found[source]) continue;
+    if (comp[source] >= 0) continue;
     queue.assign(1, source);
     while (!queue.empty()) {
       const int v = queue.back();
@@ -750,27 +750,32 @@ static void labels_reference(const int* src, const int* dst, long long m, int n_
         if (preorder[w] == 0) { queue.push_back(w); done = false; break; }
       }
       if (!done) continue;
-      lowlink[v] = preorder[v];
+      int low = preorder[v];
       for (long long k = ptr[v]; k < ptr[v + 1]; ++k) {
         const int w = adj[k];
-        if (!found[w]) lowlink[v] = std::min(lowlink[v], preorder[w] > preorder[v] ? lowlink[w] : preorder[w]);
+        if (comp[w] < 0) low = std::min(low, preorder[w] > preorder[v] ? lowlink[w] : preorder[w]);
       }
+      lowlink[v] = low;
       queue.pop_back();
-      if (lowlink[v] == preorder[v]) {
-        std::vector<int> scc(1, v);
-        while (!scc_queue.empty() && preorder[scc_queue.back()] > preorder[v]) { scc.push_back(scc_queue.back()); scc_queue.pop_back(); }
-        for (int w : scc) found[w] = 1;
-        sccs.push_back(std::move(scc));
+      if (low == preorder[v]) {
+        const int c = (int)comp_size.size();                              // emission index of this component
+        int size = 1;
+        comp[v] = c;
+        while (!scc_queue.empty() && preorder[scc_queue.back()] > preorder[v]) { comp[scc_queue.back()] = c; scc_queue.pop_back(); ++size; }
+        comp_size.push_back(size);
       } else {
         scc_queue.push_back(v);
       }
     }
   }
-  std::stable_sort(sccs.begin(), sccs.end(), [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() < b.size(); });
-  for (int i = 0; i < n_nodes; ++i) labels[i] = -1;
-  long long k = 0;
-  for (const auto& s : sccs) { for (int v : s) labels[v] = k; ++k; }
-  for (int i = 0; i < n_nodes; ++i) if (labels[i] < 0) labels[i] = k++;
+  // sorted(key=len), stable: counting sort of the emission indices by component size (utils.py:31)
+  const int nc = (int)comp_size.size();
+  std::vector<int> start((size_t)n_nodes + 2, 0), rank(nc);
+  for (int c = 0; c < nc; ++c) start[comp_size[c] + 1]++;
+  for (int sz = 0; sz <= n_nodes; ++sz) start[sz + 1] += start[sz];
+  for (int c = 0; c < nc; ++c) rank[c] = start[comp_size[c]]++;
+  long long k = nc;
+  for (int i = 0; i < n_nodes; ++i) labels[i] = comp[i] >= 0 ? rank[comp[i]] : k++;   // nodes without an active edge: last, index order
   *n_comp = (int)k;
 }
 
