@@ -717,51 +717,54 @@ static int post_begin(PostCtx& c, const mpn_graph* g, const uint8_t* act, void* 
 // ------------------------------------------------------------------------------------------------
 // reference label numbering on the host (utils.py:30-52 + networkx SCC emission order)
 // ------------------------------------------------------------------------------------------------
+struct TarjanNode {                       // everything the traversal touches about one node, in one cache line
+  int beg, end, cur;                      // successor list [beg, end) in adj, resumable iterator
+  int pre, low, comp;                     // preorder number (0 = unvisited), lowlink, emission index of its component (-1 = open)
+};
 static void labels_reference(const int* src, const int* dst, long long m, int n_nodes, long long* labels, int* n_comp) {
   // flat arrays throughout (one allocation each, no per-component vectors): this runs once per post_processing call on up to
-  // millions of active edges, and once per dropped value in split_reference
+  // millions of active edges (m < 2^31: edge ids are int32 everywhere), and once per dropped value in split_reference
   std::vector<int> order;                 // nodes in first-appearance order (u then v per edge): DiGraph insertion order
   order.reserve((size_t)std::min<long long>(2 * m, n_nodes));
-  std::vector<char> seen(n_nodes, 0);
-  std::vector<long long> ptr((size_t)n_nodes + 1, 0);
+  std::vector<TarjanNode> node((size_t)n_nodes + 1, TarjanNode{0, 0, 0, 0, 0, -2});     // comp -2: not in the digraph yet
   for (long long i = 0; i < m; ++i) {
     const int u = src[i], v = dst[i];
-    if (!seen[u]) { seen[u] = 1; order.push_back(u); }
-    if (!seen[v]) { seen[v] = 1; order.push_back(v); }
-    ptr[u + 1]++;
+    if (node[u].comp == -2) { node[u].comp = -1; order.push_back(u); }
+    if (node[v].comp == -2) { node[v].comp = -1; order.push_back(v); }
+    node[u].end++;                        // out-degree for now
   }
-  for (int i = 0; i < n_nodes; ++i) ptr[i + 1] += ptr[i];
+  int run = 0;
+  for (int i = 0; i < n_nodes; ++i) { const int deg = node[i].end; node[i].beg = node[i].cur = run; run += deg; node[i].end = run; }
   std::vector<int> adj((size_t)m);
-  std::vector<long long> cursor(ptr.begin(), ptr.end() - 1);
-  for (long long i = 0; i < m; ++i) adj[cursor[src[i]]++] = dst[i];       // successor order = edge insertion order
-  for (int i = 0; i < n_nodes; ++i) cursor[i] = ptr[i];                   // now the resumable successor iterator of each node
-  std::vector<int> preorder(n_nodes, 0), lowlink(n_nodes, 0), comp(n_nodes, -1);
+  for (long long i = 0; i < m; ++i) adj[node[src[i]].cur++] = dst[i];     // successor order = edge insertion order
+  for (int i = 0; i < n_nodes; ++i) node[i].cur = node[i].beg;
   std::vector<int> queue, scc_queue, comp_size;
   int counter = 0;
   for (int source : order) {
-    if (comp[source] >= 0) continue;
+    if (node[source].comp >= 0) continue;
     queue.assign(1, source);
     while (!queue.empty()) {
       const int v = queue.back();
-      if (preorder[v] == 0) preorder[v] = ++counter;
+      TarjanNode& nv = node[v];
+      if (nv.pre == 0) nv.pre = ++counter;
       bool done = true;
-      while (cursor[v] < ptr[v + 1]) {
-        const int w = adj[cursor[v]++];
-        if (preorder[w] == 0) { queue.push_back(w); done = false; break; }
+      while (nv.cur < nv.end) {
+        const int w = adj[nv.cur++];
+        if (node[w].pre == 0) { queue.push_back(w); done = false; break; }
       }
       if (!done) continue;
-      int low = preorder[v];
-      for (long long k = ptr[v]; k < ptr[v + 1]; ++k) {
-        const int w = adj[k];
-        if (comp[w] < 0) low = std::min(low, preorder[w] > preorder[v] ? lowlink[w] : preorder[w]);
+      int low = nv.pre;
+      for (int k = nv.beg; k < nv.end; ++k) {
+        const TarjanNode& nw = node[adj[k]];
+        if (nw.comp < 0) low = std::min(low, nw.pre > nv.pre ? nw.low : nw.pre);
       }
-      lowlink[v] = low;
+      nv.low = low;
       queue.pop_back();
-      if (low == preorder[v]) {
+      if (low == nv.pre) {
         const int c = (int)comp_size.size();                              // emission index of this component
         int size = 1;
-        comp[v] = c;
-        while (!scc_queue.empty() && preorder[scc_queue.back()] > preorder[v]) { comp[scc_queue.back()] = c; scc_queue.pop_back(); ++size; }
+        nv.comp = c;
+        while (!scc_queue.empty() && node[scc_queue.back()].pre > nv.pre) { node[scc_queue.back()].comp = c; scc_queue.pop_back(); ++size; }
         comp_size.push_back(size);
       } else {
         scc_queue.push_back(v);
@@ -775,7 +778,7 @@ static void labels_reference(const int* src, const int* dst, long long m, int n_
   for (int sz = 0; sz <= n_nodes; ++sz) start[sz + 1] += start[sz];
   for (int c = 0; c < nc; ++c) rank[c] = start[comp_size[c]]++;
   long long k = nc;
-  for (int i = 0; i < n_nodes; ++i) labels[i] = comp[i] >= 0 ? rank[comp[i]] : k++;   // nodes without an active edge: last, index order
+  for (int i = 0; i < n_nodes; ++i) labels[i] = node[i].comp >= 0 ? rank[node[i].comp] : k++;   // no active edge: last, index order
   *n_comp = (int)k;
 }
 
@@ -1006,7 +1009,8 @@ int mpn_clear_inactive(uint8_t* act, const int32_t* eid, const uint8_t* keep, in
 
 int mpn_labels_reference_host(const int32_t* src, const int32_t* dst, int64_t n_active, int32_t n_nodes, int64_t* labels_out,
                               int32_t* n_components) {
-  MPN_REQUIRE(labels_out && n_nodes > 0 && n_active >= 0 && (n_active == 0 || (src && dst)), "labels_reference_host: bad arguments");
+  MPN_REQUIRE(labels_out && n_nodes > 0 && n_active >= 0 && n_active < (1ll << 31) && (n_active == 0 || (src && dst)),
+              "labels_reference_host: bad arguments");
   for (int64_t i = 0; i < n_active; ++i)
     MPN_REQUIRE(src[i] >= 0 && src[i] < n_nodes && dst[i] >= 0 && dst[i] < n_nodes, "labels_reference_host: node id out of range");
   int nc = 0;
@@ -1017,7 +1021,8 @@ int mpn_labels_reference_host(const int32_t* src, const int32_t* dst, int64_t n_
 
 int mpn_split_reference_host(const int32_t* src, const int32_t* dst, const float* prob, int64_t n_active, int32_t n_nodes,
                              int32_t num_cameras, uint8_t* keep_out, int64_t* steps_out) {
-  MPN_REQUIRE(n_nodes > 0 && n_active >= 0 && num_cameras >= 1 && (n_active == 0 || (src && dst && prob && keep_out)),
+  MPN_REQUIRE(n_nodes > 0 && n_active >= 0 && n_active < (1ll << 31) && num_cameras >= 1 &&
+                  (n_active == 0 || (src && dst && prob && keep_out)),
               "split_reference_host: bad arguments");
   for (int64_t i = 0; i < n_active; ++i)
     MPN_REQUIRE(src[i] >= 0 && src[i] < n_nodes && dst[i] >= 0 && dst[i] < n_nodes, "split_reference_host: node id out of range");
