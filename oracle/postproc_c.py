@@ -20,7 +20,13 @@ def build_library(force: bool = False) -> str:
     """gcc -O2 -shared -fPIC oracle/postproc_oracle.c -> oracle/_build/libpostproc_oracle.so (rebuilt when the source is newer)."""
     if force or not os.path.isfile(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(SOURCE):
         os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-        subprocess.run(["gcc", "-O2", "-std=c99", "-Wall", "-Wextra", "-shared", "-fPIC", SOURCE, "-o", LIB_PATH, "-lm"], check=True)
+        tmp = LIB_PATH + ".tmp%d" % os.getpid()
+        try:
+            subprocess.run(["gcc", "-O2", "-std=c99", "-Wall", "-Wextra", "-shared", "-fPIC", SOURCE, "-o", tmp, "-lm"], check=True)
+            os.replace(tmp, LIB_PATH)                  # atomic: parallel test workers may race here
+        except (OSError, subprocess.CalledProcessError):
+            if force or not os.path.isfile(LIB_PATH):  # no compiler and nothing prebuilt: the caller cannot check anything
+                raise
     return LIB_PATH
 
 
