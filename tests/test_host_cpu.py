@@ -172,3 +172,35 @@ def test_split_reference_host_matches_the_oracle_under_ties():
     assert steps > 0 and np.array_equal(got, pc.split_sequential(src, dst, act, prob, 6, 3000))
     with pytest.raises(m._lib.MpnError):
         m._lib.check(lib.mpn_split_reference_host(None, None, None, 3, 10, 4, None, None))
+
+
+def test_host_numbering_equals_networkx_on_random_digraphs():
+    """mpn_labels_reference_host against the library the reference calls (utils.py:31: sorted(nx.strongly_connected_components(G),
+    key=len), then the nodes without an active edge in index order, utils.py:34-42), on random digraphs of up to 2000 nodes."""
+    import ctypes as C
+    import numpy as np
+    nx = pytest.importorskip("networkx")
+    lib = m._lib.lib()
+    rng = np.random.default_rng(4)
+    for trial in range(25):
+        n = int(rng.integers(50, 2000))
+        e = int(rng.integers(1, 4 * n))
+        s, d = rng.integers(0, n, e), rng.integers(0, n, e)
+        keep = s != d
+        s, d = s[keep], d[keep]
+        if s.size == 0:
+            continue
+        sccs = sorted(nx.strongly_connected_components(nx.DiGraph(list(zip(s.tolist(), d.tolist())))), key=len)
+        expect = np.full(n, -1, dtype=np.int64)
+        for i, c in enumerate(sccs):
+            expect[list(c)] = i
+        k = len(sccs)
+        for i in range(n):
+            if expect[i] < 0:
+                expect[i] = k
+                k += 1
+        s32, d32 = np.ascontiguousarray(s, dtype=np.int32), np.ascontiguousarray(d, dtype=np.int32)
+        lab = np.empty(n, dtype=np.int64)
+        nc = C.c_int32(0)
+        m._lib.check(lib.mpn_labels_reference_host(s32.ctypes.data, d32.ctypes.data, s.size, n, lab.ctypes.data, C.byref(nc)))
+        assert nc.value == k and np.array_equal(lab, expect), trial
