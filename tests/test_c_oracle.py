@@ -254,3 +254,31 @@ def test_reference_order_under_ties_matches_the_reference_itself():
             rounds_differ += not np.array_equal(pc.split(src, dst, act, prob, C, N), exact)
             n += 1
     assert n == 30 and rounds_differ >= 5
+
+
+S02_FLAG_SETS = FLAG_SETS
+
+
+def load_s02_case():
+    g = np.load(os.path.join(GOLDEN, "s02post_n300_c4.npz"))
+    N, C, _seed = [int(v) for v in g["spec"]]
+    return g, N, C, g["src"].astype(np.int64), g["dst"].astype(np.int64), g["prob1"], g["pred"].astype(np.int64)
+
+
+def test_oracles_match_the_reference_at_its_own_problem_size():
+    """tests/golden/s02post_n300_c4.npz: the unmodified reference's post_processing on one S02-shaped predicted graph (BASELINE
+    configs[0]: 300 tracklets, 4 cameras, E = 67,500 directed edges, 3,896 active; 6.6 minutes of reference time for the five flag
+    sets).  The C oracle (rounds and reference order), the numpy rounds and the statement mirror give its decisions and label
+    integers bit for bit."""
+    g, N, C, src, dst, prob, pred = load_s02_case()
+    assert src.size == 67500 and N == 300 and C == 4
+    assert np.array_equal(pc.scc_labels(src, dst, pred, N)[0], g["labels_initial"])
+    for tag, cfg in S02_FLAG_SETS:
+        lab, act = pc.post_processing(src, dst, pred, prob, C, N, *cfg, numbering="reference")
+        assert np.array_equal(act, g["pred_" + tag]) and np.array_equal(lab, g["labels_" + tag]), tag
+        lab, act = po.post_processing_rounds(src, dst, pred, prob, C, N, *cfg, numbering="reference")
+        assert np.array_equal(act, g["pred_" + tag]) and np.array_equal(lab, g["labels_" + tag]), tag
+    lab, act = po.post_processing_sequential(src, dst, pred, prob, C, N)
+    assert np.array_equal(act, g["pred_full"]) and np.array_equal(lab, g["labels_full"])
+    a = pc.cut(src, dst, pc.prune(src, dst, pc.cut(src, dst, pred, N), prob, C, N)[0], N)
+    assert np.array_equal(pc.split_sequential(src, dst, a, prob, C, N), g["pred_full"])

@@ -74,3 +74,17 @@ def test_split_order_reference_experimental(m):
                                   numbering=numbering, split_order="reference")
         assert np.array_equal(P.cpu().numpy(), act_ref)
         assert np.array_equal(ID.numpy(), lab_ref) if numbering == "reference" else same_partition(ID.numpy(), lab_ref)
+
+
+def test_post_processing_matches_the_reference_at_s02_size(m):
+    """The CUDA post-processing against the unmodified reference's outputs on one S02-shaped predicted graph (300 tracklets, 4 cameras,
+    67,500 directed edges: the reference's own problem size; tests/golden/s02post_n300_c4.npz), all five flag sets."""
+    from tests.test_c_oracle import S02_FLAG_SETS, load_s02_case
+    g, N, C, src, dst, prob, pred = load_s02_case()
+    dev = torch.device("cuda", 0)
+    data = Data(x=torch.zeros(N, 1, device=dev), edge_index=torch.from_numpy(np.stack([src, dst])).to(dev))
+    for tag, cfg in S02_FLAG_SETS:
+        CONFIG = {"CUTTING": cfg[0], "PRUNING": cfg[1], "SPLITTING": cfg[2]}
+        ID, P = m.post_processing(C, None, None, torch.from_numpy(pred).to(dev), None, CONFIG, data, torch.from_numpy(prob).to(dev))
+        assert np.array_equal(P.cpu().numpy(), g["pred_" + tag]), tag
+        assert np.array_equal(ID.numpy(), g["labels_" + tag]), tag
