@@ -123,3 +123,20 @@ def test_split_rounds_equal_sequential_unless_cross_cluster_tie():
             assert tie_rounds > 0, "rounds differ from the statement mirror without a cross-cluster tie (trial %d)" % trial
             differ_flagged += 1
     assert ties_seen > 0 and differ_flagged > 0        # the generator does reach the condition
+
+
+def test_mpn_oracle_matches_reference_at_its_own_problem_size():
+    """tests/golden/s02mpn_shipped_L1.npz: the unmodified reference (shipped L=1 configuration, 2048-d features) on one S02-shaped
+    graph of 300 tracklets, 4 cameras, E = 67,500 directed edges (BASELINE configs[0]).  Same tolerances as the small cases."""
+    path = os.path.join(GOLDEN, "s02mpn_shipped_L1.npz")
+    g, params, sd, x, edge_index, _ = load_mpn_case(path)
+    assert edge_index.shape[1] == 67500 and x.shape == (300, 2048)
+    ea = mo.edge_features(x, edge_index)
+    assert np.allclose(ea.numpy(), g["edge_attr"], rtol=2e-6, atol=2e-6)
+    outs, h = mo.mpn_forward(sd, params, "resnet101", x, edge_index, torch.from_numpy(g["edge_attr"]))
+    ref = g["logits0"]
+    assert len(outs) == 1 and np.abs(outs[0].numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.abs(h.numpy() - g["h"]).max() <= 1e-4 * max(1.0, np.abs(g["h"]).max())
+    _, pred = mo.decide(outs[-1])
+    margin = np.abs(ref[:, 1] - ref[:, 0])
+    assert not np.any((pred.numpy() != g["pred"]) & (margin > 1e-4))

@@ -88,3 +88,29 @@ def test_post_processing_matches_the_reference_at_s02_size(m):
         ID, P = m.post_processing(C, None, None, torch.from_numpy(pred).to(dev), None, CONFIG, data, torch.from_numpy(prob).to(dev))
         assert np.array_equal(P.cpu().numpy(), g["pred_" + tag]), tag
         assert np.array_equal(ID.numpy(), g["labels_" + tag]), tag
+
+
+def test_forward_matches_the_reference_at_s02_size(m):
+    """The CUDA edge features, and forward + decisions on the reference's edge features, against the unmodified reference on one S02-shaped graph (300 tracklets, 4
+    cameras, 2048-d features, 67,500 directed edges, shipped L=1 model; tests/golden/s02mpn_shipped_L1.npz): logits within
+    1e-4 * max|logit| (north_star), h within 1e-4, decisions identical outside the 1e-4 margin band, edge features within 1e-5."""
+    import copy
+    import os
+    from tests._util import GOLDEN, load_mpn_case
+    dev = torch.device("cuda", 0)
+    g, params, sd, x, ei, _ = load_mpn_case(os.path.join(GOLDEN, "s02mpn_shipped_L1.npz"))
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    net.fuse_decisions = True
+    feats = m.edge_features(x.to(dev), ei.to(dev))                               # inference.py:453-456 on the CUDA path
+    assert np.allclose(feats.cpu().numpy(), g["edge_attr"], rtol=1e-5, atol=1e-5)
+    data = Data(x=x.to(dev), edge_index=ei.to(dev), edge_attr=torch.from_numpy(g["edge_attr"]).to(dev))   # the reference's own input
+    out, h = net(data)
+    torch.cuda.synchronize()
+    ref = g["logits0"]
+    logits = out["classified_edges"][-1].cpu().numpy()
+    assert len(out["classified_edges"]) == 1 and np.abs(logits - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.abs(h.cpu().numpy() - g["h"]).max() <= 1e-4 * max(1.0, np.abs(g["h"]).max())
+    margin = np.abs(ref[:, 1] - ref[:, 0])
+    assert not np.any((net.last_pred.cpu().numpy() != g["pred"]) & (margin > 1e-4))
