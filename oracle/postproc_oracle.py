@@ -5,7 +5,7 @@ Two restatements of the reference post-processing (integer / index work, bit-exa
 * ``*_sequential`` functions follow the reference statement by statement (same loop order,
   same snapshot semantics, same label numbering); quadratic, for small graphs only.
 * ``*_rounds`` functions are the vectorised "parallel rounds" formulation
-  that scales to 1e8 edges; ``tests/test_oracle_postproc.py`` checks both against each other and
+  that scales to 1e8 edges; ``tests/test_oracle_golden.py (and tests/test_c_oracle.py for the C restatement)`` checks both against each other and
   against golden outputs of the real reference (``tests/golden/make_golden.py``).
 
 Under exact probability ties across oversized clusters the rounds formulation of SPLITTING can differ from the reference's
