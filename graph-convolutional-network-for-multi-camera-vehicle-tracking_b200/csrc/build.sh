@@ -4,9 +4,7 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="${HERE}/../libmpn_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-# MPN_PDL=1: compile the experimental programmatic-dependent-launch support in (common.cuh); 2: plus an early trigger in every
-# kernel; default 0 = plain launches
-FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3 -DMPN_PDL=${MPN_PDL:-0} ${MPN_NVCC_EXTRA:-})
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3 ${MPN_NVCC_EXTRA:-})
 OBJ="${HERE}/_obj"
 mkdir -p "${OBJ}"
 # objects built with other flags are stale

@@ -66,36 +66,21 @@ struct Arena {
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// Programmatic dependent launch (EXPERIMENTAL, compiled out unless the library is built with -DMPN_PDL=1, i.e.
-// `MPN_PDL=1 csrc/build.sh`; then still off until mpn_set_pdl(1) / MPN_PDL_LAUNCH=1).  A kernel launched through launch()
-// with the attribute may be scheduled while its predecessor in the stream drains; its first statement, pdl_wait()
-// (griddepcontrol.wait), blocks every thread until the predecessor grid has completed and its writes are visible, so only
-// the launch latency overlaps.  Rule: pdl_wait() is the FIRST statement of every kernel launched through launch(), before any
-// early return (a grid whose blocks all skipped it would let its own successor overtake the predecessor).
-// MPN_PDL=2 additionally triggers the dependent launch at the top of every kernel (see pdl_wait()).
-#ifndef MPN_PDL
-#define MPN_PDL 0
-#endif
-extern int g_pdl_launch;             // run-time switch (only read when MPN_PDL=1)
-extern int g_fused_distance;         // run-time switch of the fused distance epilogue (mpn_set_fused_distance; default off)
+// Programmatic dependent launch (on by default; mpn_set_pdl(0) switches it off for A/B measurements).  A kernel launched
+// through launch() carries the programmatic-stream-serialization attribute and may be scheduled while its predecessor in the
+// stream drains; its first statement, pdl_wait() (griddepcontrol.wait), blocks every thread until the predecessor grid has
+// completed and its writes are visible, so only the launch latency overlaps (measured on configs[1]: 0.838 -> 0.795 ms per
+// step, profiles/r2_01_gap_experiments.md; triggering the dependent launch early inside the kernels gave nothing more).
+// Rule: pdl_wait() is the FIRST statement of every kernel launched through launch(), before any early return (a grid whose
+// blocks all skipped it would let its own successor overtake the predecessor).
+extern int g_pdl_launch;             // run-time switch
+extern int g_fused_distance;         // run-time switch of the fused distance epilogue (mpn_set_fused_distance)
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void pdl_wait() {
-#if MPN_PDL
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-#if MPN_PDL >= 2
-  // MPN_PDL=2: also release the NEXT kernel right away.  Its blocks become resident as soon as every block of this grid has
-  // started and resources are free, and then sit in their own griddepcontrol.wait (which still waits for this grid to complete
-  // and flush): block launch and prologue leave the critical path.  For the persistent sweeps (all blocks resident from the
-  // start) that is the whole run; for grids launched in waves it is the last wave.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename... Params, typename... Args>
 static inline void launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-#if MPN_PDL
   if (g_pdl_launch) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -110,7 +95,6 @@ static inline void launch(void (*kernel)(Params...), dim3 grid, dim3 block, size
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);     // errors surface through MPN_LAUNCH_OK()
     return;
   }
-#endif
   kernel<<<grid, block, smem, st>>>(static_cast<Args&&>(args)...);
 }
 

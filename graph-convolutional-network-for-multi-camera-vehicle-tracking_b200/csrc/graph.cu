@@ -8,11 +8,7 @@ namespace mpn {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_kernel_launches = 0;
-static int pdl_from_env() {
-  const char* e = getenv("MPN_PDL_LAUNCH");
-  return MPN_PDL && e != nullptr && e[0] == '1';
-}
-int g_pdl_launch = pdl_from_env();
+int g_pdl_launch = 1;
 static int fused_distance_from_env() {
   const char* e = getenv("MPN_FUSED_DISTANCE");
   return e != nullptr && e[0] == '1';
@@ -305,7 +301,6 @@ int mpn_set_fused_distance(int enable) {
 }
 
 int mpn_set_pdl(int enable) {
-  if (!MPN_PDL) return 0;
   if (enable >= 0) mpn::g_pdl_launch = enable != 0;
   return mpn::g_pdl_launch ? 2 : 1;
 }

@@ -679,8 +679,15 @@ __device__ __forceinline__ f32x2 relu2(f32x2 v) {
   return pack2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
 }
 
-// softmax([l0,l1])[1] (inference.py:475-477) = 1 / (1 + exp(l0 - l1)): one exp, same value up to rounding
-__device__ __forceinline__ float softmax1(float l0, float l1) { return 1.0f / (1.0f + expf(l0 - l1)); }
+// softmax([l0,l1])[1] (inference.py:475-477) with ATen's own arithmetic (softmax_warp_forward: exp(x - max) / sum, IEEE
+// division, full-precision expf), so that the value is bit-identical to torch.softmax(logits, dim=1)[:, 1] on the device:
+// PRUNING takes an argmin over it and SPLITTING compares it with float == (utils.py:96-98, 288-289).  exp(0) = 1 exactly, so
+// one expf suffices:  l1 >= l0: 1 / (e + 1);  l1 < l0: e / (1 + e),  e = expf(-|l0 - l1|).
+__device__ __forceinline__ float softmax1(float l0, float l1) {
+  const float e = expf(-fabsf(l0 - l1));
+  const float sum = e + 1.0f;
+  return __fdiv_rn((l1 >= l0) ? 1.0f : e, sum);
+}
 
 template <bool CLASSIFY>
 __device__ __forceinline__ void classify_store(const EdgeConsts& sc, const float (&ep)[4], int e, float2* __restrict__ logits,
@@ -852,17 +859,6 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
 // shared-memory accesses through explicit 32-bit addresses that the compiler must keep in registers (opaque): ptxas otherwise
 // rebuilds every tile / ring address from threadIdx in each iteration of the batch loop (~15 instructions per batch)
 __device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
@@ -878,12 +874,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-// ARRIVE (EXPERIMENTAL, MPN_ATC_ARRIVE=1, not yet run on hardware): the per-iteration block barrier in front of the MMA issue
-// becomes an mbarrier that all 128 threads arrive on and only the issuing thread waits for, so the other warps go on preparing the
-// next batch (the hand-over of a new row's red[] / w2 tile keeps its __syncthreads).  Safe without the barrier: the operand tiles
-// are double-buffered and a thread reaches iteration i+2 only through the drain of iteration i+1, i.e. after MMA i has retired;
-// MMA i+1 overwrites the TMEM accumulators only after every thread has arrived, i.e. after its tcgen05.ld of MMA i's result.
-template <bool CLASSIFY, bool DECIDE, bool AGGMAX, int CTAS, bool ARRIVE = false>
+template <bool CLASSIFY, bool DECIDE, bool AGGMAX, int CTAS>
 __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
     const mpn_graph g, const float4* __restrict__ ybuf, const float* __restrict__ A, const float* __restrict__ consts,
     float* __restrict__ msg_task, float2* __restrict__ logits, uint8_t* __restrict__ pred, float* __restrict__ prob1) {
@@ -896,17 +887,14 @@ __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
   __shared__ int s_row[ATC_SEG], s_beg[ATC_SEG], s_end[ATC_SEG];
   __shared__ float red[2][ATC_THREADS / 32][32];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ __align__(8) uint64_t ready_bar;            // ARRIVE: operand tiles written / previous result read, per thread
   __shared__ uint32_t tmem_slot;
   load_consts(sc, consts);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (warp == 0) tmem_alloc(&tmem_slot, 32 * ATC_NB);
   if (tid == 0) {
     mbar_init(&bar, 1);
-    if (ARRIVE) mbar_init(&ready_bar, ATC_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  uint32_t ready_phase = 0;
   if (tid < 32) {                                        // static parts of the weight tiles (channel = tid)
     float wh[4], wl[4];
 #pragma unroll
@@ -1042,7 +1030,7 @@ __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
               logits[e] = make_float2(l0, l1);
               if (DECIDE) {
                 pred[e] = (l1 > l0) ? 1 : 0;                                      // argmax, tie -> class 0 (inference.py:479)
-                prob1[e] = rcp_approx(1.0f + ex2_approx((l0 - l1) * 1.4426950408889634f));   // softmax(.)[1] (inference.py:475-477)
+                prob1[e] = softmax1(l0, l1);                                      // softmax(.)[1] (inference.py:475-477), ATen-exact
               }
             }
             float eh[4], el[4];
@@ -1069,14 +1057,7 @@ __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        if (ARRIVE) {
-          if (first_batch && new_run) __syncthreads();   // red[] of the finished run, w2 tile of the new one (block-uniform)
-          mbar_arrive(&ready_bar);
-          if (tid == 0) mbar_wait(&ready_bar, ready_phase);
-          ready_phase ^= 1;
-        } else {
-          __syncthreads();
-        }
+        __syncthreads();
         if (tid == 0) {
           tc_fence_after();
 #pragma unroll
@@ -1890,20 +1871,14 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
       if (p->use_tc && apply_tc && stored && g.chunk >= ATC_THREADS && (!classify || (pred_out != nullptr) == (prob1_out != nullptr))) {
         const bool agg_max = p->w.node_agg == MPN_AGG_MAX;
         p->msg_abs = agg_max ? 0 : 1;                      // msg_task holds sum |z|: node_finalize adds the closed-form half
-        const char* ctas_env = getenv("MPN_ATC_CTAS");     // resident blocks per SM: 4 | 5, read per launch (measurements flip it)
-        const int atc_ctas = ctas_env ? (atoi(ctas_env) == 5 ? 5 : 4) : ATC_CTAS_PER_SM;
-        const char* arrive_env = getenv("MPN_ATC_ARRIVE");   // EXPERIMENTAL: mbarrier arrive instead of the block barrier (5 blocks per SM only)
-        const bool atc_arrive = arrive_env != nullptr && arrive_env[0] == '1';
 #define MPN_ATC3(CL, DE, MX, NC) mpn::launch(apply_tc_kernel<CL, DE, MX, NC>, kNumSMs * NC, ATC_THREADS, 0, st, g, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
-#define MPN_ATC3A(CL, DE, MX) mpn::launch(apply_tc_kernel<CL, DE, MX, 5, true>, kNumSMs * 5, ATC_THREADS, 0, st, g, yb, p->A, p->consts, p->msg_task, lg, pred_out, prob1_out)
-#define MPN_ATC2(CL, DE, MX) do { if (atc_ctas == 5 && atc_arrive) MPN_ATC3A(CL, DE, MX); else if (atc_ctas == 5) MPN_ATC3(CL, DE, MX, 5); else MPN_ATC3(CL, DE, MX, 4); } while (0)
+#define MPN_ATC2(CL, DE, MX) MPN_ATC3(CL, DE, MX, ATC_CTAS_PER_SM)
 #define MPN_ATC(CL, DE) do { if (agg_max) MPN_ATC2(CL, DE, true); else MPN_ATC2(CL, DE, false); } while (0)
         if (!classify) MPN_ATC(false, false);
         else if (pred_out && prob1_out) MPN_ATC(true, true);
         else MPN_ATC(true, false);
 #undef MPN_ATC
 #undef MPN_ATC2
-#undef MPN_ATC3A
 #undef MPN_ATC3
         break;
       }

@@ -46,11 +46,9 @@ int mpn_abi_version(void);
 const char* mpn_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (monotonic) */
 uint64_t mpn_kernel_launches(void);
-/* EXPERIMENTAL (off by default): programmatic dependent launch of the graph-build / edge-feature / forward kernels, so the
- * launch latency of kernel n+1 overlaps the tail of kernel n (every kernel starts with griddepcontrol.wait).
- * enable > 0 / == 0 switches it on / off, enable < 0 only queries.  Returns 0 when the support is compiled out (the default
- * build: launches are plain <<<>>> and this call changes nothing); when the library was built with `MPN_PDL=1 csrc/build.sh`:
- * 1 = switch is off, 2 = switch is on (initial state: on iff the environment has MPN_PDL_LAUNCH=1). */
+/* Programmatic dependent launch of the graph-build / edge-feature / forward kernels (on by default): the launch latency of
+ * kernel n+1 overlaps the tail of kernel n (every kernel starts with griddepcontrol.wait, so results are bit-identical).
+ * enable > 0 / == 0 switches it on / off (A/B measurements), enable < 0 only queries.  Returns 1 = off, 2 = on. */
 int mpn_set_pdl(int enable);
 /* EXPERIMENTAL (off by default, not yet validated on hardware): form the edge features (inference.py:453-456) in the epilogue
  * of the Gram GEMM — TMEM accumulator -> distance / cosine -> edge_attr, no Gram matrix in HBM and no gather pass — for graphs

@@ -394,9 +394,7 @@ def test_graph_stream_pipelined_copies_match_direct_forward(m, depth):
         gs.submit(cases[0][0], cases[0][1], outs[1][0])                         # wrong number of edges
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MPN_TEST_EXPERIMENTAL") != "1",
-                    reason="GraphStream(graph_replay=True) is experimental and not yet validated on hardware; MPN_TEST_EXPERIMENTAL=1 runs it")
-def test_graph_stream_graph_replay_experimental(m):
+def test_graph_stream_graph_replay(m):
     """Slot-level CUDA-graph replay: the third and later submits of one signature per slot are replays; same bits as eager."""
     params = mo.shipped_model_params(1, 1, 64, (48, 40))
     sd = mo.init_weights(params, "resnet101", 21)
@@ -420,13 +418,11 @@ def test_graph_stream_graph_replay_experimental(m):
             assert torch.equal(o, r)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MPN_TEST_EXPERIMENTAL") != "1",
-                    reason="programmatic dependent launch is experimental (MPN_PDL=1 csrc/build.sh); MPN_TEST_EXPERIMENTAL=1 runs it")
-def test_programmatic_dependent_launch_experimental(m):
-    """Same bits with the launch attribute on: graph tables, edge features, forward (small-graph replay and large-graph path)."""
+def test_programmatic_dependent_launch(m):
+    """Same bits with and without the launch attribute (the default is on): graph tables, edge features, forward (small-graph
+    replay and large-graph path)."""
     lib = m._lib.lib()
-    if lib.mpn_set_pdl(-1) == 0:
-        pytest.skip("library built without MPN_PDL=1")
+    assert lib.mpn_set_pdl(-1) == 2, "programmatic dependent launch is the default"
     params = mo.shipped_model_params(2, 1, 64, (48, 40))
     sd = mo.init_weights(params, "resnet101", 23)
     net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
@@ -449,7 +445,7 @@ def test_programmatic_dependent_launch_experimental(m):
                 for a, b in zip(outs[0], o):
                     assert torch.equal(a, b)
     finally:
-        lib.mpn_set_pdl(0)
+        lib.mpn_set_pdl(1)
 
 
 @pytest.mark.skipif(__import__("os").environ.get("MPN_TEST_EXPERIMENTAL") != "1",
@@ -518,40 +514,6 @@ def test_fused_distance_epilogue_experimental(m):
         assert (preds[0][0] != preds[1][0]).sum().item() <= 2
     finally:
         lib.mpn_set_fused_distance(0)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("MPN_TEST_EXPERIMENTAL") != "1",
-                    reason="MPN_ATC_ARRIVE (mbarrier arrive instead of the block barrier in the apply sweep) is experimental; "
-                           "MPN_TEST_EXPERIMENTAL=1 runs it")
-def test_apply_sweep_arrive_variant_experimental(m):
-    """Same arithmetic, different synchronisation: logits, h and decisions must be bit-identical, run after run."""
-    import os
-    params = mo.shipped_model_params(3, 2, 64, (48, 40))
-    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
-    net.load_state_dict(mo.init_weights(params, "resnet101", 31), strict=True)
-    net = net.to(dev()).eval()
-    net.fuse_decisions = True
-    old = os.environ.get("MPN_ATC_ARRIVE")
-    try:
-        for N, C_, chunk in ((600, 3, 128), (4096, 8, None), (1500, 5, 256)):
-            x, ei, _, _ = mo.synth_graph(N, C_, 13, D=64, planted=True)
-            outs = []
-            for on in ("0", "1", "1", "0"):
-                os.environ["MPN_ATC_ARRIVE"] = on
-                d = Data(x=x.to(dev()), edge_index=ei.to(dev()))
-                d.mpn_graph = m.TrackletGraph(d.edge_index, N, chunk=chunk)
-                d.edge_attr = m.edge_features(d.x, None, graph=d.mpn_graph)
-                out, h = net(d)
-                torch.cuda.synchronize()
-                outs.append([t.clone() for t in out["classified_edges"]] + [h.clone(), net.last_pred.clone()])
-            for o in outs[1:]:
-                for a, b in zip(outs[0], o):
-                    assert torch.equal(a, b)
-    finally:
-        if old is None:
-            os.environ.pop("MPN_ATC_ARRIVE", None)
-        else:
-            os.environ["MPN_ATC_ARRIVE"] = old
 
 
 class _NoComm:

@@ -24,17 +24,11 @@ def test_library_exports_every_declared_symbol():
     assert lib.mpn_abi_version() == m._lib.ABI_VERSION == 4
 
 
-def test_pdl_switch_is_off_unless_built_in():
-    """mpn_set_pdl reports whether programmatic dependent launch was compiled in (MPN_PDL=1 csrc/build.sh); the default build
-    has plain launches and ignores the request."""
+def test_pdl_switch_defaults_on():
+    """Programmatic dependent launch is compiled in and on by default; mpn_set_pdl(0/1) is the A/B switch of the tools."""
     lib = m._lib.lib()
-    state = lib.mpn_set_pdl(-1)                       # query: 0 = compiled out, 1 = off, 2 = on
-    assert state in (0, 1, 2)
-    if state == 0:
-        assert lib.mpn_set_pdl(1) == 0 and lib.mpn_set_pdl(0) == 0
-    else:
-        assert lib.mpn_set_pdl(1) == 2 and lib.mpn_set_pdl(-1) == 2 and lib.mpn_set_pdl(0) == 1
-        lib.mpn_set_pdl(state - 1)
+    assert lib.mpn_set_pdl(-1) == 2                   # 1 = off, 2 = on
+    assert lib.mpn_set_pdl(0) == 1 and lib.mpn_set_pdl(-1) == 1 and lib.mpn_set_pdl(1) == 2
 
 
 def test_fused_distance_switch_defaults_off():
