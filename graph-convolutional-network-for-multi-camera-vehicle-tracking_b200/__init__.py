@@ -28,10 +28,10 @@ from .pipeline import GraphStream
 from .sharded import (CudaPhases, CudaPostOps, ShardedMPN, partition_rows, shard_edges, sharded_forward,
                       sharded_post_processing)
 from .postprocess import (compute_SCC_and_Clusters, post_processing, pruning, remove_edges_single_direction,
-                          splitting)
+                          split_stats, splitting)
 
 __all__ = ["MOTMPNet", "edge_features", "post_processing", "pruning", "splitting", "remove_edges_single_direction",
-           "compute_SCC_and_Clusters", "TrackletGraph", "graph_for", "ShardedMPN", "CudaPhases", "sharded_forward", "partition_rows",
+           "compute_SCC_and_Clusters", "split_stats", "TrackletGraph", "graph_for", "ShardedMPN", "CudaPhases", "sharded_forward", "partition_rows",
            "shard_edges", "GraphStream", "sharded_post_processing", "CudaPostOps", "_lib", "evaluation", "compute_P_R_F", "clustering_scores", "relabel_detections", "tracking_table",
            "save_mtmc", "edge_labels", "normalize_columns", "pack_reid_features", "pack_reid_features_from_pickles",
            "read_packed_features", "load_packed_features"]

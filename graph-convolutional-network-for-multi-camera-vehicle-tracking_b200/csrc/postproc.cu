@@ -30,6 +30,12 @@ struct PostCtx {
   unsigned long long *mo, *mi;
   unsigned int *mbits, *hash;
   int hash_cap;
+  int *wcc, *wccflag;                                            // SPLIT: weakly connected components and the flagged ones
+  unsigned int* tie_keys;                                        // SPLIT: probability values of the dirty edges ...
+  int* tie_counts;                                               // ... and how many active edges carry each
+  int tie_cap;
+  float* a_prob;                                                 // SPLIT: probabilities in active-list order
+  uint8_t* sel;
   size_t total;
   // host
   int n_active;
@@ -59,7 +65,16 @@ static void post_layout(PostCtx& c, void* ws, size_t ws_bytes) {
   while ((size_t)cap < N) cap <<= 1;
   c.hash_cap = cap;
   c.hash = a.take<unsigned int>(cap);
-  c.counters = a.take<int>(8);
+  c.wcc = a.take<int>(N);
+  c.wccflag = a.take<int>(N);
+  int tcap = 1024;
+  while ((size_t)tcap < E / 4) tcap <<= 1;
+  c.tie_cap = tcap;
+  c.tie_keys = a.take<unsigned int>(tcap);
+  c.tie_counts = a.take<int>(tcap);
+  c.a_prob = a.take<float>(E);
+  c.sel = a.take<uint8_t>(E);
+  c.counters = a.take<int>(16);
   c.total = a.off;
 }
 
@@ -638,14 +653,136 @@ static int scc_dirty(PostCtx& c, const uint8_t* act, int Dn, int De) {
   return MPN_OK;
 }
 
+// ---- probability ties -------------------------------------------------------------------------------------------------
+// The rounds above equal the reference's one-cluster-at-a-time loop exactly when no probability value that an oversized
+// cluster can drop is carried by a second active edge: the reference removes EVERY edge with that value (utils.py:96-98), so
+// a shared value couples two clusters and the order in which the reference visits them (utils.py:60-64,112) decides the
+// outcome.  Ties are detected on the device; a graph that has one goes through the exact order on the host
+// (split_exact.cu), restricted to the weakly connected components that SPLITTING can touch.
+//   table: open addressing over the probability bits of the active edges touching oversized clusters ("dirty" edges);
+//   count: how many active edges of the whole graph carry each of those values.
+__global__ void tie_insert_kernel(int n_list, const int* __restrict__ list, const int* __restrict__ a_eid, const uint8_t* __restrict__ act,
+                                  const float* __restrict__ prob, int pstride, unsigned int* __restrict__ keys, int cap) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_list; k += gridDim.x * blockDim.x) {
+    const int e = a_eid[list[k]];
+    if (!act[e]) continue;
+    const unsigned int key = __float_as_uint(prob[(size_t)e * pstride]);
+    unsigned int slot = hash_u32(key) & (cap - 1);
+    for (;;) {
+      const unsigned int old = atomicCAS(&keys[slot], HASH_EMPTY, key);
+      if (old == HASH_EMPTY || old == key) break;
+      slot = (slot + 1) & (cap - 1);
+    }
+  }
+}
+__device__ __forceinline__ int tie_find(const unsigned int* __restrict__ keys, int cap, unsigned int key) {
+  unsigned int slot = hash_u32(key) & (cap - 1);
+  for (;;) {
+    const unsigned int v = keys[slot];
+    if (v == key) return (int)slot;
+    if (v == HASH_EMPTY) return -1;
+    slot = (slot + 1) & (cap - 1);
+  }
+}
+__global__ void tie_count_kernel(int A, const int* __restrict__ a_eid, const uint8_t* __restrict__ act, const float* __restrict__ prob,
+                                 int pstride, const unsigned int* __restrict__ keys, int* __restrict__ counts, int cap) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    const int e = a_eid[i];
+    if (!act[e]) continue;
+    const int slot = tie_find(keys, cap, __float_as_uint(prob[(size_t)e * pstride]));
+    if (slot >= 0) atomicAdd(&counts[slot], 1);
+  }
+}
+// weakly connected components: union-find over every active edge
+__global__ void union_all_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const int* __restrict__ a_dst,
+                                 const uint8_t* __restrict__ act, int* __restrict__ parent) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x)
+    if (act[a_eid[i]]) uf_union(parent, a_src[i], a_dst[i]);
+}
+// flag the components SPLITTING can touch: those holding an oversized cluster, those holding an edge with a tied value
+__global__ void flag_wcc_nodes_kernel(int n_list, const int* __restrict__ list, const int* __restrict__ wcc, int* __restrict__ flag) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_list; k += gridDim.x * blockDim.x) flag[wcc[list[k]]] = 1;
+}
+__global__ void flag_wcc_ties_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const uint8_t* __restrict__ act,
+                                     const float* __restrict__ prob, int pstride, const unsigned int* __restrict__ keys,
+                                     const int* __restrict__ counts, int cap, const int* __restrict__ wcc, int* __restrict__ flag,
+                                     int* __restrict__ n_tied_edges) {
+  int tied = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    const int e = a_eid[i];
+    if (!act[e]) continue;
+    const int slot = tie_find(keys, cap, __float_as_uint(prob[(size_t)e * pstride]));
+    if (slot >= 0 && counts[slot] >= 2) { flag[wcc[a_src[i]]] = 1; ++tied; }
+  }
+  tied = __reduce_add_sync(0xffffffffu, tied);
+  if ((threadIdx.x & 31) == 0 && tied) atomicAdd(n_tied_edges, tied);
+}
+// per active-list entry: probability (compacted) and whether its component is flagged (activity included)
+__global__ void gather_select_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const uint8_t* __restrict__ act,
+                                     const float* __restrict__ prob, int pstride, const int* __restrict__ wcc, const int* __restrict__ flag,
+                                     float* __restrict__ a_prob, uint8_t* __restrict__ sel) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    const int e = a_eid[i];
+    a_prob[i] = prob[(size_t)e * pstride];
+    sel[i] = (act[e] && flag[wcc[a_src[i]]]) ? 1 : 0;
+  }
+}
+
+static thread_local long long g_split_stats[4] = {0, 0, 0, 0};     // tie values' edges, steps / rounds, off-lowest steps, mode
+
+__global__ void apply_keep_kernel(int A, const int* __restrict__ a_eid, const uint8_t* __restrict__ keep, uint8_t* __restrict__ act) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x)
+    if (!keep[i]) act[a_eid[i]] = 0;
+}
+
+int split_exact_host_impl(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep,
+                          int64_t* stats_out);      // split_exact.cu
+
+// the reference's order on the host for the flagged components (every oversized cluster lives in one of them)
+static int split_in_reference_order(PostCtx& c, uint8_t* act, const float* prob, int pstride, int num_cameras, int* rounds) {
+  const int A = c.n_active, N = c.g.n_nodes;
+  gather_select_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, act, prob, pstride, c.wcc, c.wccflag, c.a_prob, c.sel);
+  MPN_LAUNCH_OK();
+  std::vector<int> hs(A), hd(A);
+  std::vector<float> hp(A);
+  std::vector<uint8_t> hsel(A), keep_all(A, 1);
+  MPN_CUDA_OK(cudaMemcpyAsync(hs.data(), c.a_src, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaMemcpyAsync(hd.data(), c.a_dst, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaMemcpyAsync(hp.data(), c.a_prob, sizeof(float) * A, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaMemcpyAsync(hsel.data(), c.sel, A, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  std::vector<int> pos;                             // active-list positions of the sub-problem, edge order
+  pos.reserve(A / 4 + 16);
+  for (int i = 0; i < A; ++i)
+    if (hsel[i]) pos.push_back(i);
+  const long long m = (long long)pos.size();
+  std::vector<int> ss(m), dd(m);
+  std::vector<float> pp(m);
+  std::vector<uint8_t> keep(m, 1);
+  for (long long k = 0; k < m; ++k) { ss[k] = hs[pos[k]]; dd[k] = hd[pos[k]]; pp[k] = hp[pos[k]]; }
+  int64_t st[4] = {0, 0, 0, 0};
+  if (m > 0) MPN_TRY(split_exact_host_impl(ss.data(), dd.data(), pp.data(), m, N, num_cameras, keep.data(), st));
+  for (long long k = 0; k < m; ++k) keep_all[pos[k]] = keep[k];
+  MPN_CUDA_OK(cudaMemcpyAsync(c.sel, keep_all.data(), A, cudaMemcpyHostToDevice, c.st));
+  apply_keep_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.sel, act);
+  MPN_LAUNCH_OK();
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));        // keep_all must outlive the copy
+  *rounds = (int)st[0];
+  g_split_stats[1] = st[0];
+  g_split_stats[2] = st[1];
+  g_split_stats[3] = 1;
+  return MPN_OK;
+}
+
 static int split_stage(PostCtx& c, uint8_t* act, const float* prob, int pstride, int num_cameras, int* rounds) {
   const int A = c.n_active, N = c.g.n_nodes;
   *rounds = 0;
+  g_split_stats[0] = g_split_stats[1] = g_split_stats[2] = g_split_stats[3] = 0;
   if (A == 0) return MPN_OK;
   // round 0 on the whole graph: components, sizes, dirty lists
   MPN_TRY(scc_stage(c, act, nullptr));
   MPN_CUDA_OK(cudaMemsetAsync(c.size, 0, sizeof(int) * N, c.st));
-  MPN_CUDA_OK(cudaMemsetAsync(c.counters + 5, 0, 2 * sizeof(int), c.st));
+  MPN_CUDA_OK(cudaMemsetAsync(c.counters + 5, 0, 4 * sizeof(int), c.st));
   comp_size_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, c.size);
   MPN_LAUNCH_OK();
   mark_dirty_nodes_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.label, c.size, num_cameras, c.dirty_nodes, c.counters + 5);
@@ -660,13 +797,44 @@ static int split_stage(PostCtx& c, uint8_t* act, const float* prob, int pstride,
   static const bool dbg = getenv("MPN_POST_DEBUG") != nullptr;
   if (dbg) fprintf(stderr, "[split] A=%d N=%d dirty nodes=%d dirty edges=%d\n", A, N, Dn, De);
   if (Dn == 0) return MPN_OK;
-  auto t_prev = std::chrono::steady_clock::now();
-  for (;;) {
-    if (dbg) {
-      auto t_now = std::chrono::steady_clock::now();
-      fprintf(stderr, "[split] round %d: previous round took %.1f us\n", *rounds, std::chrono::duration<double, std::micro>(t_now - t_prev).count());
-      t_prev = t_now;
+  // ---- probability ties among the values an oversized cluster can drop?
+  iota_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.wcc);
+  MPN_LAUNCH_OK();
+  union_all_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, c.wcc);
+  MPN_LAUNCH_OK();
+  flatten_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.wcc, nullptr);
+  MPN_LAUNCH_OK();
+  MPN_CUDA_OK(cudaMemsetAsync(c.wccflag, 0, sizeof(int) * N, c.st));
+  const bool table_fits = (long long)De * 5 <= (long long)c.tie_cap * 3;       // load factor <= 0.6
+  int n_tied = 0;
+  if (table_fits) {
+    MPN_CUDA_OK(cudaMemsetAsync(c.tie_keys, 0xFF, sizeof(unsigned int) * c.tie_cap, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(c.tie_counts, 0, sizeof(int) * c.tie_cap, c.st));
+    if (De > 0) {
+      tie_insert_kernel<<<list_grid(De), 256, 0, c.st>>>(De, c.dirty_edges, c.a_eid, act, prob, pstride, c.tie_keys, c.tie_cap);
+      MPN_LAUNCH_OK();
     }
+    tie_count_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, act, prob, pstride, c.tie_keys, c.tie_counts, c.tie_cap);
+    MPN_LAUNCH_OK();
+    flag_wcc_ties_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, act, prob, pstride, c.tie_keys, c.tie_counts, c.tie_cap,
+                                                         c.wcc, c.wccflag, c.counters + 7);
+    MPN_LAUNCH_OK();
+    MPN_CUDA_OK(cudaMemcpyAsync(&n_tied, c.counters + 7, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  }
+  g_split_stats[0] = table_fits ? n_tied : -1;
+  if (dbg) fprintf(stderr, "[split] active edges carrying a tied value: %d%s\n", n_tied, table_fits ? "" : " (table too small: all active edges go to the host)");
+  if (!table_fits || n_tied > 0) {
+    if (!table_fits) {
+      MPN_CUDA_OK(cudaMemsetAsync(c.wccflag, 0x01, sizeof(int) * N, c.st));   // every component (any non-zero flag)
+    } else {
+      flag_wcc_nodes_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.wcc, c.wccflag);
+      MPN_LAUNCH_OK();
+    }
+    return split_in_reference_order(c, act, prob, pstride, num_cameras, rounds);
+  }
+  // ---- no ties: the clusters are independent, every oversized cluster drops its minimum in the same round
+  for (;;) {
     // per-cluster minimum probability over the active edges touching each oversized cluster
     reset_nodes_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.label, c.size, c.mbits, 4);
     MPN_LAUNCH_OK();
@@ -696,6 +864,7 @@ static int split_stage(PostCtx& c, uint8_t* act, const float* prob, int pstride,
     comp_size_list_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.label, c.size);
     MPN_LAUNCH_OK();
   }
+  g_split_stats[1] = *rounds;
   return MPN_OK;
 }
 
@@ -782,50 +951,6 @@ static void labels_reference(const int* src, const int* dst, long long m, int n_
   *n_comp = (int)k;
 }
 
-// ------------------------------------------------------------------------------------------------
-// SPLITTING in the reference's own order on the host (utils.py:54-123), over the ACTIVE edge list only (an inactive edge can
-// neither be a minimum nor be switched off).  One cluster at a time: l = lowest label with more than C nodes in the reference
-// numbering; every active edge whose probability EQUALS (float ==, utils.py:96-98) the minimum over the active edges touching
-// cluster l goes; relabel; stay on l as re-read in the new numbering (utils.py:112) while that cluster is oversized.
-// One sequential Tarjan pass per dropped value: the exact semantics under probability ties, not the fast path.
-// ------------------------------------------------------------------------------------------------
-static long long split_reference(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep) {
-  std::vector<long long> idx(m);                       // surviving edges, in edge order
-  for (long long i = 0; i < m; ++i) { idx[i] = i; keep[i] = 1; }
-  std::vector<int> s(m), d(m);
-  std::vector<long long> labels(n_nodes);
-  std::vector<int> count;
-  long long steps = 0;
-  auto relabel = [&]() {
-    const long long k = (long long)idx.size();
-    for (long long i = 0; i < k; ++i) { s[i] = src[idx[i]]; d[i] = dst[idx[i]]; }
-    int nc = 0;
-    labels_reference(s.data(), d.data(), k, n_nodes, labels.data(), &nc);
-    count.assign(nc, 0);
-    for (int v = 0; v < n_nodes; ++v) count[labels[v]]++;
-  };
-  relabel();
-  for (;;) {
-    long long l = -1;
-    for (size_t k = 0; k < count.size(); ++k) if (count[k] > C) { l = (long long)k; break; }
-    if (l < 0) break;
-    for (;;) {
-      float mn = INFINITY;
-      for (long long i : idx)
-        if ((labels[src[i]] == l || labels[dst[i]] == l) && prob[i] < mn) mn = prob[i];
-      size_t w = 0;
-      for (size_t r = 0; r < idx.size(); ++r) {
-        if (prob[idx[r]] == mn) keep[idx[r]] = 0; else idx[w++] = idx[r];
-      }
-      idx.resize(w);
-      ++steps;
-      relabel();
-      if (!(l < (long long)count.size() && count[l] > C)) break;
-    }
-  }
-  return steps;
-}
-
 __global__ void clear_inactive_kernel(long long n, const int* __restrict__ eid, const uint8_t* __restrict__ keep,
                                       uint8_t* __restrict__ act) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -893,6 +1018,10 @@ int mpn_split(const mpn_graph* g, uint8_t* act, const float* prob1, int32_t pstr
   MPN_CUDA_OK(cudaStreamSynchronize(c.st));
   if (rounds) *rounds = r;
   return MPN_OK;
+}
+
+void mpn_split_last_stats(int64_t out[4]) {
+  if (out) for (int i = 0; i < 4; ++i) out[i] = g_split_stats[i];
 }
 
 int mpn_scc_labels(const mpn_graph* g, const uint8_t* act, int32_t* labels, int32_t* n_components, void* ws, size_t ws_bytes,
@@ -1016,18 +1145,6 @@ int mpn_labels_reference_host(const int32_t* src, const int32_t* dst, int64_t n_
   int nc = 0;
   labels_reference(src, dst, n_active, n_nodes, (long long*)labels_out, &nc);
   if (n_components) *n_components = nc;
-  return MPN_OK;
-}
-
-int mpn_split_reference_host(const int32_t* src, const int32_t* dst, const float* prob, int64_t n_active, int32_t n_nodes,
-                             int32_t num_cameras, uint8_t* keep_out, int64_t* steps_out) {
-  MPN_REQUIRE(n_nodes > 0 && n_active >= 0 && n_active < (1ll << 31) && num_cameras >= 1 &&
-                  (n_active == 0 || (src && dst && prob && keep_out)),
-              "split_reference_host: bad arguments");
-  for (int64_t i = 0; i < n_active; ++i)
-    MPN_REQUIRE(src[i] >= 0 && src[i] < n_nodes && dst[i] >= 0 && dst[i] < n_nodes, "split_reference_host: node id out of range");
-  const long long steps = split_reference(src, dst, prob, n_active, n_nodes, num_cameras, keep_out);
-  if (steps_out) *steps_out = steps;
   return MPN_OK;
 }
 

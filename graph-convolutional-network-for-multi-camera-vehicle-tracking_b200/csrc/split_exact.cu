@@ -1,0 +1,260 @@
+// SPLITTING (utils.py:54-123) in the reference's own one-cluster-at-a-time order, for the clusters whose outcome depends on
+// that order (probability ties).  Host code: the reference's order is sequential by definition; what this file removes is the
+// cost of following it — the reference recomputes every strongly connected component of the whole graph after each dropped
+// value, here a step only recomputes the weakly connected component(s) it touched.
+//
+// What the reference does (utils.py:54-123, compute_SCC_and_Clusters utils.py:30-52):
+//   labels = position in  sorted(SCCs of the active digraph, key=len)  (stable; networkx emission order within one size), nodes
+//   without an active edge appended last;  l = lowest label with more than C nodes;  loop: m = min probability over the active
+//   edges with an endpoint in cluster l;  every edge of the graph with probability == m is switched off (float ==, :96-98);
+//   relabel;  stay on the INTEGER l (re-read in the new numbering, :112) while that label is oversized, else start over.
+//
+// Facts used (each checked against the unmodified reference's outputs in tests/):
+//   * networkx emits the SCCs source by source (sources in first-appearance order of the nodes in the active edge list, u
+//     before v), each source's DFS in post-order; a DFS never leaves the weakly connected component (WCC) of its source.  So
+//     the emission order is the lexicographic order of (first-appearance key of the emitting source, index within that DFS),
+//     and both parts are functions of the WCC alone: a step only invalidates the keys of the WCCs that lost an edge.
+//   * every small (<= C nodes) cluster sorts before every oversized one, so the label of the i-th oversized cluster is
+//     n_small + i and "label l is still oversized" reads  0 <= l - n_small' < n_big'  after the step: only the CHANGE of the
+//     number of small clusters matters, never its value.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <iterator>
+#include <set>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mpn {
+
+namespace {
+
+struct SplitExact {
+  long long m;
+  const float* prob;
+  int C, n;                                       // camera bound, number of (local) nodes
+  std::vector<int> ls, ld;                        // local endpoints of every edge
+  std::vector<int> out_ptr, out_adj, in_ptr, in_adj;     // incident edge ids per node, ascending (= edge order)
+  std::vector<int> out_first, in_first;           // first entry of the lists that may still be alive
+  std::vector<uint8_t> alive;
+  std::vector<int> by_prob;                       // edge ids sorted by probability
+  std::vector<int> comp, wcc;                     // cluster / WCC id of a node (-1: no active edge)
+  std::vector<int> pre, low, it, mark;            // traversal scratch
+  struct Cluster { int size; long long src_key; int idx; std::vector<int> nodes; };
+  std::vector<Cluster> clusters;
+  std::vector<std::vector<int>> wcc_nodes;
+  typedef std::tuple<int, long long, int, int> BigKey;      // (size, key of the emitting source, index in its DFS, cluster id)
+  std::set<BigKey> big;
+  long long n_small = 0;
+  int mark_gen = 0;
+
+  long long first_key(int v) {                    // first-appearance key of v in the current active edge list: 2*edge + side
+    int& a = out_first[v];
+    while (a < out_ptr[v + 1] && !alive[out_adj[a]]) ++a;
+    int& b = in_first[v];
+    while (b < in_ptr[v + 1] && !alive[in_adj[b]]) ++b;
+    long long k = INT64_MAX;
+    if (a < out_ptr[v + 1]) k = 2ll * out_adj[a];
+    if (b < in_ptr[v + 1]) k = std::min(k, 2ll * in_adj[b] + 1);
+    return k;
+  }
+
+  void unregister_wcc(int w) {
+    for (int v : wcc_nodes[w]) {
+      const int c = comp[v];
+      if (c < 0 || clusters[c].size == 0) continue;
+      if (clusters[c].size > C) big.erase(BigKey(clusters[c].size, clusters[c].src_key, clusters[c].idx, c));
+      else --n_small;
+      clusters[c].size = 0;                       // dead
+      std::vector<int>().swap(clusters[c].nodes);
+    }
+  }
+
+  // nodes: a set closed under the alive edges.  Splits it into WCCs, runs networkx's SCC generator on each, registers clusters.
+  void recompute(const std::vector<int>& nodes) {
+    ++mark_gen;
+    std::vector<int> stack, wn, order, dfs, scc_stack;
+    std::vector<std::pair<long long, int>> keyed;
+    for (int seed : nodes) {
+      if (mark[seed] == mark_gen) continue;
+      mark[seed] = mark_gen;
+      wn.clear();
+      stack.assign(1, seed);
+      while (!stack.empty()) {                    // undirected traversal over the alive edges
+        const int v = stack.back();
+        stack.pop_back();
+        wn.push_back(v);
+        for (int k = out_first[v]; k < out_ptr[v + 1]; ++k) {
+          const int e = out_adj[k];
+          if (alive[e] && mark[ld[e]] != mark_gen) { mark[ld[e]] = mark_gen; stack.push_back(ld[e]); }
+        }
+        for (int k = in_first[v]; k < in_ptr[v + 1]; ++k) {
+          const int e = in_adj[k];
+          if (alive[e] && mark[ls[e]] != mark_gen) { mark[ls[e]] = mark_gen; stack.push_back(ls[e]); }
+        }
+      }
+      if (wn.size() == 1 && first_key(wn[0]) == INT64_MAX) {      // no active edge left: not in the digraph (utils.py:34-42)
+        comp[wn[0]] = -1;
+        wcc[wn[0]] = -1;
+        continue;
+      }
+      const int w = (int)wcc_nodes.size();
+      keyed.clear();
+      for (int v : wn) { keyed.emplace_back(first_key(v), v); wcc[v] = w; comp[v] = -2; pre[v] = 0; it[v] = out_first[v]; }
+      std::sort(keyed.begin(), keyed.end());
+      wcc_nodes.emplace_back(wn);
+      int counter = 0;
+      for (const auto& kv : keyed) {              // sources in node insertion order of nx.DiGraph(active edge list)
+        const int source = kv.second;
+        if (comp[source] != -2) continue;
+        int emitted = 0;
+        dfs.assign(1, source);
+        while (!dfs.empty()) {
+          const int v = dfs.back();
+          if (pre[v] == 0) pre[v] = ++counter;
+          bool done = true;
+          while (it[v] < out_ptr[v + 1]) {
+            const int e = out_adj[it[v]++];
+            if (!alive[e]) continue;
+            const int u = ld[e];
+            if (pre[u] == 0) { dfs.push_back(u); done = false; break; }
+          }
+          if (!done) continue;
+          int lo = pre[v];
+          for (int k = out_first[v]; k < out_ptr[v + 1]; ++k) {
+            const int e = out_adj[k];
+            if (!alive[e]) continue;
+            const int u = ld[e];
+            if (comp[u] == -2) lo = std::min(lo, pre[u] > pre[v] ? low[u] : pre[u]);
+          }
+          low[v] = lo;
+          dfs.pop_back();
+          if (lo == pre[v]) {
+            const int c = (int)clusters.size();
+            clusters.emplace_back();
+            Cluster& cl = clusters.back();
+            cl.nodes.push_back(v);
+            comp[v] = c;
+            while (!scc_stack.empty() && pre[scc_stack.back()] > pre[v]) {
+              comp[scc_stack.back()] = c;
+              cl.nodes.push_back(scc_stack.back());
+              scc_stack.pop_back();
+            }
+            cl.size = (int)cl.nodes.size();
+            cl.src_key = kv.first;
+            cl.idx = emitted++;
+            if (cl.size > C) big.insert(BigKey(cl.size, cl.src_key, cl.idx, c));
+            else ++n_small;
+          } else {
+            scc_stack.push_back(v);
+          }
+        }
+      }
+    }
+  }
+};
+
+}  // namespace
+
+// keep_out[i] = 0 for the edges SPLITTING switches off.  stats_out[4]: dropped values, steps taken on a label that was not the
+// lowest oversized one (utils.py:112 re-reads the integer), clusters examined, 0.
+int split_exact_host_impl(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep,
+                            int64_t* stats_out) {
+  SplitExact S;
+  S.m = m; S.prob = prob; S.C = C;
+  // local node ids in order of first use (only the nodes of the sub-problem get traversal state)
+  std::vector<int> local((size_t)n_nodes, -1);
+  S.ls.resize(m); S.ld.resize(m);
+  int n = 0;
+  for (long long i = 0; i < m; ++i) {
+    if (local[src[i]] < 0) local[src[i]] = n++;
+    if (local[dst[i]] < 0) local[dst[i]] = n++;
+    S.ls[i] = local[src[i]];
+    S.ld[i] = local[dst[i]];
+    keep[i] = 1;
+  }
+  std::vector<int>().swap(local);
+  S.n = n;
+  S.out_ptr.assign(n + 1, 0); S.in_ptr.assign(n + 1, 0);
+  for (long long i = 0; i < m; ++i) { S.out_ptr[S.ls[i] + 1]++; S.in_ptr[S.ld[i] + 1]++; }
+  for (int v = 0; v < n; ++v) { S.out_ptr[v + 1] += S.out_ptr[v]; S.in_ptr[v + 1] += S.in_ptr[v]; }
+  S.out_adj.resize(m); S.in_adj.resize(m);
+  {
+    std::vector<int> oc(S.out_ptr.begin(), S.out_ptr.end() - 1), ic(S.in_ptr.begin(), S.in_ptr.end() - 1);
+    for (long long i = 0; i < m; ++i) { S.out_adj[oc[S.ls[i]]++] = (int)i; S.in_adj[ic[S.ld[i]]++] = (int)i; }
+  }
+  S.out_first.assign(S.out_ptr.begin(), S.out_ptr.end() - 1);
+  S.in_first.assign(S.in_ptr.begin(), S.in_ptr.end() - 1);
+  S.alive.assign(m, 1);
+  S.by_prob.resize(m);
+  for (long long i = 0; i < m; ++i) S.by_prob[i] = (int)i;
+  std::sort(S.by_prob.begin(), S.by_prob.end(), [&](int a, int b) { return prob[a] < prob[b] || (prob[a] == prob[b] && a < b); });
+  S.comp.assign(n, -1); S.wcc.assign(n, -1);
+  S.pre.assign(n, 0); S.low.assign(n, 0); S.it.assign(n, 0); S.mark.assign(n, 0);
+  {
+    std::vector<int> all(n);
+    for (int v = 0; v < n; ++v) all[v] = v;
+    S.recompute(all);
+  }
+  long long steps = 0, off_lowest = 0;
+  long long sticky = -1;                          // index (in the order of `big`) of the cluster the reference's inner loop is on
+  std::vector<int> affected;
+  std::vector<long long> wcc_stamp;
+  while (!S.big.empty()) {
+    const long long idx = (sticky >= 0) ? sticky : 0;
+    if (idx > 0) ++off_lowest;
+    auto itb = S.big.begin();
+    std::advance(itb, idx);
+    const int c = std::get<3>(*itb);
+    const long long small_before = S.n_small;
+    // minimum probability over the active edges with an endpoint in the cluster (utils.py:69-95)
+    float mn = INFINITY;
+    for (int v : S.clusters[c].nodes) {
+      for (int k = S.out_first[v]; k < S.out_ptr[v + 1]; ++k) { const int e = S.out_adj[k]; if (S.alive[e] && prob[e] < mn) mn = prob[e]; }
+      for (int k = S.in_first[v]; k < S.in_ptr[v + 1]; ++k) { const int e = S.in_adj[k]; if (S.alive[e] && prob[e] < mn) mn = prob[e]; }
+    }
+    if (!(mn < INFINITY)) { set_error("split: an oversized cluster without a finite edge probability"); return MPN_ERR_INVALID; }
+    // every edge of the graph with that probability (float ==, utils.py:96-98)
+    auto lo = std::lower_bound(S.by_prob.begin(), S.by_prob.end(), mn, [&](int e, float x) { return prob[e] < x; });
+    affected.clear();
+    for (auto p = lo; p != S.by_prob.end() && prob[*p] == mn; ++p) {
+      const int e = *p;
+      if (!S.alive[e]) continue;
+      S.alive[e] = 0;
+      keep[e] = 0;
+      const int w = S.wcc[S.ls[e]];
+      if ((size_t)w >= wcc_stamp.size()) wcc_stamp.resize(S.wcc_nodes.size(), -1);
+      if (wcc_stamp[w] != steps) { wcc_stamp[w] = steps; affected.push_back(w); }
+    }
+    ++steps;
+    for (int w : affected) S.unregister_wcc(w);
+    for (int w : affected) {
+      std::vector<int> nodes;
+      nodes.swap(S.wcc_nodes[w]);
+      S.recompute(nodes);
+    }
+    // np.bincount(ID_pred)[l] > num_cameras with l the INTEGER of the cluster just handled (utils.py:112)
+    const long long j = idx - (S.n_small - small_before);
+    sticky = (j >= 0 && j < (long long)S.big.size()) ? j : -1;
+  }
+  if (stats_out) { stats_out[0] = steps; stats_out[1] = off_lowest; stats_out[2] = (long long)S.clusters.size(); stats_out[3] = 0; }
+  return MPN_OK;
+}
+
+}  // namespace mpn
+
+extern "C" int mpn_split_exact_host(const int32_t* src, const int32_t* dst, const float* prob, int64_t n_active, int32_t n_nodes,
+                                    int32_t num_cameras, uint8_t* keep_out, int64_t* stats_out) {
+  MPN_REQUIRE(n_nodes > 0 && n_active >= 0 && n_active < (1ll << 31) && num_cameras >= 1 &&
+                  (n_active == 0 || (src && dst && prob && keep_out)),
+              "split_exact_host: bad arguments");
+  for (int64_t i = 0; i < n_active; ++i)
+    MPN_REQUIRE(src[i] >= 0 && src[i] < n_nodes && dst[i] >= 0 && dst[i] < n_nodes, "split_exact_host: node id out of range");
+  if (n_active == 0) {
+    if (stats_out) stats_out[0] = stats_out[1] = stats_out[2] = stats_out[3] = 0;
+    return MPN_OK;
+  }
+  return mpn::split_exact_host_impl(src, dst, prob, n_active, n_nodes, num_cameras, keep_out, stats_out);
+}

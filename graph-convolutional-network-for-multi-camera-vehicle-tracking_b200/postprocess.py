@@ -91,34 +91,6 @@ class _Post:
                                                       C.byref(ncomp)))
         return labels, int(ncomp.value)
 
-    def split_reference(self, num_cameras):
-        """SPLITTING in the reference's own order (utils.py:54-123) on the host over the active edges: the exact semantics under
-        probability ties, one sequential SCC pass per dropped value (mpn_split_reference_host).  Returns the number of dropped values."""
-        g = self.g
-        if g.perm is not None or g.row_offset != 0 or g.n_nodes != g.n_cols or self._prob_keep is None:
-            raise NotImplementedError("split_order='reference' needs an unsharded graph with (row, col)-sorted edges and the "
-                                      "edge probabilities")
-        idx = torch.nonzero(self.act, as_tuple=False).reshape(-1)               # active edge ids, edge order
-        n = int(idx.numel())
-        if n == 0:
-            return 0
-        src = torch.empty(n, dtype=torch.int32, device=self.dev)
-        dst = torch.empty(n, dtype=torch.int32, device=self.dev)
-        n_act = C.c_int64(0)
-        with torch.cuda.device(self.dev):
-            _lib.check(self.lib.mpn_active_edges(g.ref, self.act.data_ptr(), src.data_ptr(), dst.data_ptr(), n, C.byref(n_act),
-                                                 self.ws.data_ptr(), self.ws.numel(), self.stream))
-        if int(n_act.value) != n:
-            raise RuntimeError("active-edge count changed under split_reference")
-        s_h, d_h = src.cpu(), dst.cpu()
-        p_h = self._prob_keep[idx].float().contiguous().cpu()
-        keep = torch.empty(n, dtype=torch.uint8)
-        steps = C.c_int64(0)
-        _lib.check(self.lib.mpn_split_reference_host(s_h.data_ptr(), d_h.data_ptr(), p_h.data_ptr(), n, g.n_nodes, int(num_cameras),
-                                                     keep.data_ptr(), C.byref(steps)))
-        self.act[idx[(keep == 0).to(self.dev)]] = 0
-        return int(steps.value)
-
     def labels_canonical(self):
         lab = torch.empty(self.g.n_nodes, dtype=torch.int32, device=self.dev)
         ncomp = C.c_int32(0)
@@ -182,21 +154,28 @@ def splitting(ID_pred, predictions, preds_prob, edge_list, data_batch, predicted
     return predictions
 
 
+def split_stats():
+    """SPLITTING of this thread's last ``splitting`` / ``post_processing`` call (mpn_split_last_stats): dict with the number of active
+    edges that carried a tied probability value, rounds / dropped values, off-lowest steps and the mode that ran."""
+    out = (C.c_int64 * 4)()
+    _lib.lib().mpn_split_last_stats(C.cast(out, C.c_void_p))
+    return {"tied_edges": int(out[0]), "rounds": int(out[1]), "off_lowest_steps": int(out[2]),
+            "mode": "reference_order_host" if out[3] else "device_rounds"}
+
+
 def post_processing(num_cameras, ID_pred, predicted_active_edges, predictions, edge_list, CONFIG, data, preds_prob,
-                    numbering='reference', verbose=False, split_order='rounds'):
+                    numbering='reference', verbose=False):
     """inference.post_processing (inference.py:70-169): CUT -> PRUNE -> CUT -> SPLIT, then SCC labels.
 
     Returns (ID_pred: int64 CPU tensor [N], predictions: int64 [E] on the device).  ``numbering='reference'``
     reproduces the reference's label integers (host Tarjan over the few active edges); ``'canonical'`` labels each
     cluster with its smallest node id and stays on the device until the final copy.
 
-    ``split_order``: ``'rounds'`` (default) lets every oversized cluster drop its minimum-probability edge in the same round on
-    the device; ``'reference'`` (EXPERIMENTAL, not yet run on hardware) runs SPLITTING on the host in the reference's own
-    one-cluster-at-a-time order, which differs only when different clusters meet an exact probability tie
-    and costs one sequential SCC pass per dropped value.
+    SPLITTING is exact under probability ties (utils.py:96-98 removes every edge with the dropped value, which couples the
+    clusters that share it): ties are detected on the device; without one every oversized cluster drops its minimum in the same
+    round on the device, with one the components SPLITTING can touch follow the reference's own order (csrc/split_exact.cu).
+    ``split_stats()`` tells which ran.
     """
-    if split_order not in ('rounds', 'reference'):
-        raise ValueError("split_order must be 'rounds' or 'reference'")
     for k in ('CUTTING', 'PRUNING', 'SPLITTING'):
         CONFIG[k] = _as_bool(CONFIG[k])                       # same in-place fix-up as inference.py:75-91
     flags = (_lib.POST_CUT if CONFIG['CUTTING'] else 0) | (_lib.POST_PRUNE if CONFIG['PRUNING'] else 0) | \
@@ -206,18 +185,10 @@ def post_processing(num_cameras, ID_pred, predicted_active_edges, predictions, e
     p = _Post(data, predictions, preds_prob)
     lab = torch.empty(p.g.n_nodes, dtype=torch.int32, device=p.dev)
     ncomp, changed = C.c_int32(0), C.c_int32(0)
-    host_split = split_order == 'reference' and (flags & _lib.POST_SPLIT) != 0
-    dev_flags = flags & ~_lib.POST_SPLIT if host_split else flags
-    if dev_flags:
-        with torch.cuda.device(p.dev):
-            _lib.check(p.lib.mpn_post_processing(p.g.ref, p.act.data_ptr(), p.prob_ptr, p.prob_stride, int(num_cameras), dev_flags,
-                                                 lab.data_ptr(), C.byref(ncomp), C.byref(changed), p.ws.data_ptr(),
-                                                 p.ws.numel(), p.stream))
-    if host_split:
-        p.split_reference(num_cameras)
-        if numbering == 'canonical':
-            lab, n_can = p.labels_canonical()
-            ncomp = C.c_int32(n_can)
+    with torch.cuda.device(p.dev):
+        _lib.check(p.lib.mpn_post_processing(p.g.ref, p.act.data_ptr(), p.prob_ptr, p.prob_stride, int(num_cameras), flags,
+                                             lab.data_ptr(), C.byref(ncomp), C.byref(changed), p.ws.data_ptr(),
+                                             p.ws.numel(), p.stream))
     new_pred = p.predictions(predictions).reshape(predictions.shape)
     if flags == _lib.POST_SPLIT:
         predictions.copy_(new_pred)                           # splitting mutates its argument in place (utils.py:98)

@@ -296,7 +296,11 @@ int mpn_decide(const float* logits_dev, int64_t n_edges, uint8_t* pred_out_dev, 
  *   mpn_cut     remove_edges_single_direction      utils.py:125-142
  *   mpn_prune   pruning                            utils.py:144-339 (live 161-188,277-317); *changed_host = 0
  *               is the reference's "return []" case
- *   mpn_split   splitting                          utils.py:54-123
+ *   mpn_split   splitting                          utils.py:54-123.  Exact under probability ties: when no value that an
+ *               oversized cluster can drop is shared with a second active edge, all oversized clusters drop their minimum in
+ *               the same round on the device (the clusters are independent); otherwise the weakly connected components that
+ *               SPLITTING can touch go through the reference's own one-cluster-at-a-time order (mpn_split_exact_host).
+ *               mpn_split_last_stats reports which of the two ran.
  *   mpn_scc_labels  partition of compute_SCC_and_Clusters (utils.py:30-52); labels_dev[n] = smallest node
  *               id of n's strongly connected component ("canonical" numbering)
  *   mpn_post_processing  inference.post_processing inference.py:70-169 (CUT, PRUNE, CUT, SPLIT)
@@ -308,6 +312,11 @@ int mpn_prune(const mpn_graph* g, uint8_t* act_dev, const float* prob1_dev, int3
               int32_t* changed_host, int32_t* rounds_host, void* workspace_dev, size_t workspace_bytes, void* stream);
 int mpn_split(const mpn_graph* g, uint8_t* act_dev, const float* prob1_dev, int32_t prob_stride, int32_t num_cameras,
               int32_t* rounds_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* SPLITTING of the calling thread's last mpn_split / mpn_post_processing: out[0] = active edges carrying a probability value
+ * that is tied with an edge touching an oversized cluster (-1: not counted, every active edge went to the host),
+ * out[1] = rounds (device) or dropped values (host order), out[2] = host-order steps taken on a label other than the lowest
+ * oversized one (utils.py:112), out[3] = 0 device rounds | 1 reference order on the host. */
+void mpn_split_last_stats(int64_t out_host[4]);
 int mpn_scc_labels(const mpn_graph* g, const uint8_t* act_dev, int32_t* labels_dev, int32_t* n_components_host,
                    void* workspace_dev, size_t workspace_bytes, void* stream);
 int mpn_post_processing(const mpn_graph* g, uint8_t* act_dev, const float* prob1_dev, int32_t prob_stride,
@@ -340,13 +349,15 @@ int mpn_clear_inactive(uint8_t* act_dev, const int32_t* eid_dev, const uint8_t* 
 int mpn_labels_reference_host(const int32_t* src_host, const int32_t* dst_host, int64_t n_active, int32_t n_nodes,
                               int64_t* labels_out_host, int32_t* n_components_host);
 /* Host-side SPLITTING in the reference's own order (utils.py:54-123): one oversized cluster at a time — the lowest label of the
- * reference numbering, re-read after every relabel as utils.py:112 does — dropping every active edge whose probability equals
- * (float ==, utils.py:96-98) the minimum among the active edges touching that cluster.  Input: the ACTIVE edges in edge order
- * (mpn_compact_active) with their probabilities; output keep_out[i] = 0 for the edges SPLITTING switches off; *steps_out = number
- * of dropped values (one sequential SCC pass each).  The exact semantics under probability ties, where mpn_split's
- * all-clusters-per-round schedule can differ; not the fast path.  HOST pointers. */
-int mpn_split_reference_host(const int32_t* src_host, const int32_t* dst_host, const float* prob_host, int64_t n_active,
-                             int32_t n_nodes, int32_t num_cameras, uint8_t* keep_out_host, int64_t* steps_out);
+ * reference numbering, the integer label re-read after every relabel as utils.py:112 does — dropping every active edge whose
+ * probability equals (float ==, utils.py:96-98) the minimum among the active edges touching that cluster.  A step recomputes only
+ * the weakly connected components it touched (csrc/split_exact.cu), not the whole graph as the reference does.  Input: active
+ * edges in edge order with their probabilities — all of them, or the weakly connected components that SPLITTING can touch
+ * (mpn_split gathers those: oversized clusters and probability ties).  Output keep_out[i] = 0 for the edges switched off;
+ * stats_out[4] (optional): dropped values, steps taken on a label other than the lowest oversized one, clusters examined, 0.
+ * HOST pointers. */
+int mpn_split_exact_host(const int32_t* src_host, const int32_t* dst_host, const float* prob_host, int64_t n_active,
+                         int32_t n_nodes, int32_t num_cameras, uint8_t* keep_out_host, int64_t* stats_out);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM building block (exported for tests and for the roofline bench):

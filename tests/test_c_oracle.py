@@ -246,8 +246,8 @@ def test_reference_order_under_ties_matches_the_reference_itself():
                 s32, d32 = np.ascontiguousarray(src[a], dtype=np.int32), np.ascontiguousarray(dst[a], dtype=np.int32)
                 p32 = np.ascontiguousarray(prob[a], dtype=np.float32)
                 keep = np.empty(a.size, dtype=np.uint8)
-                m._lib.check(lib.mpn_split_reference_host(s32.ctypes.data, d32.ctypes.data, p32.ctypes.data, a.size, N, C,
-                                                          keep.ctypes.data, None))
+                m._lib.check(lib.mpn_split_exact_host(s32.ctypes.data, d32.ctypes.data, p32.ctypes.data, a.size, N, C,
+                                                      keep.ctypes.data, None))
                 got = act.copy()
                 got[a[keep == 0]] = 0
                 assert np.array_equal(got, ref["pred_" + tag]), (i, tag)

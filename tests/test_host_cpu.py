@@ -118,8 +118,8 @@ def test_stream_and_sharded_post_refuse_cpu():
         m.CudaPostOps().compact(g, torch.ones(4, dtype=torch.uint8), torch.rand(4))
 
 
-def test_split_reference_host_matches_the_oracle_under_ties():
-    """mpn_split_reference_host (product, C++) against the independent plain-C oracle of the reference's SPLITTING order
+def test_split_exact_host_matches_the_oracle_under_ties():
+    """mpn_split_exact_host (product, C++: the reference's order with per-component recomputation) against the independent plain-C oracle of the reference's SPLITTING order
     (oracle/postproc_oracle.c::po_split_sequential, itself pinned against the Python statement mirror), on graphs with heavily
     tied probabilities and on a 3 k-node planted graph.  Host pointers only: runs without a GPU."""
     import ctypes as C
@@ -133,16 +133,16 @@ def test_split_reference_host_matches_the_oracle_under_ties():
         s32, d32 = np.ascontiguousarray(src[a], dtype=np.int32), np.ascontiguousarray(dst[a], dtype=np.int32)
         p32 = np.ascontiguousarray(prob[a], dtype=np.float32)
         keep = np.empty(a.size, dtype=np.uint8)
-        steps = C.c_int64(0)
-        m._lib.check(lib.mpn_split_reference_host(s32.ctypes.data, d32.ctypes.data, p32.ctypes.data, a.size, n_nodes, cams,
-                                                  keep.ctypes.data, C.byref(steps)))
+        stats = (C.c_int64 * 4)()
+        m._lib.check(lib.mpn_split_exact_host(s32.ctypes.data, d32.ctypes.data, p32.ctypes.data, a.size, n_nodes, cams,
+                                              keep.ctypes.data, C.cast(stats, C.c_void_p)))
         out = np.array(act, dtype=np.int64, copy=True)
         out[a[keep == 0]] = 0
-        return out, int(steps.value)
+        return out, int(stats[0])
 
     rng = np.random.default_rng(17)
     checked = 0
-    for trial in range(200):
+    for trial in range(600):
         n, cams = int(rng.integers(8, 40)), int(rng.integers(2, 5))
         cam = np.sort(rng.integers(0, cams, n))
         s, d = np.nonzero(cam[:, None] != cam[None, :])
@@ -157,7 +157,7 @@ def test_split_reference_host_matches_the_oracle_under_ties():
         got, _ = host_split(s, d, start, prob, cams, n)
         assert np.array_equal(got, pc.split_sequential(s, d, start, prob, cams, n)), trial
         checked += 1
-    assert checked > 150
+    assert checked > 450
     src, dst, prob, pred, _ = po.planted_prediction_graph(3000, 6, 1, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03, single_dir=0.05)
     act = pc.cut(src, dst, pred, 3000)
     act, _ = pc.prune(src, dst, act, prob, 6, 3000)
@@ -165,7 +165,43 @@ def test_split_reference_host_matches_the_oracle_under_ties():
     got, steps = host_split(src, dst, act, prob, 6, 3000)
     assert steps > 0 and np.array_equal(got, pc.split_sequential(src, dst, act, prob, 6, 3000))
     with pytest.raises(m._lib.MpnError):
-        m._lib.check(lib.mpn_split_reference_host(None, None, None, 3, 10, 4, None, None))
+        m._lib.check(lib.mpn_split_exact_host(None, None, None, 3, 10, 4, None, None))
+
+
+def test_split_exact_host_200k_nodes_zero_differing_decisions():
+    """mpn_split_exact_host on the 200 k-node graph of tests/test_zz_c_oracle_gpu.py (0.9 M active edges, 1568 tied values, 44
+    steps off the lowest label) against the stored result of the C statement-order oracle (tests/golden/make_split200k.py,
+    11 minutes of po_split_sequential): zero differing decisions, the reference's label integers."""
+    import ctypes as C
+    import hashlib
+    import numpy as np
+    from oracle import postproc_c as pc
+    from oracle import postproc_oracle as po
+    from tests._util import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "split200k_sequential.npz"))
+    n_nodes, cams, seed = [int(v) for v in g["spec"]]
+    src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, cams, seed, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03,
+                                                          single_dir=0.05)
+    act = pc.cut(src, dst, pred, n_nodes)
+    act, _ = pc.prune(src, dst, act, prob, cams, n_nodes)
+    act = pc.cut(src, dst, act, n_nodes)
+    a = np.flatnonzero(act)
+    assert a.size == int(g["n_start_active"][0])
+    ref = np.zeros(src.size, dtype=np.int64)
+    ref[a] = np.unpackbits(g["final_bits"])[:a.size]
+    s32, d32 = np.ascontiguousarray(src[a], dtype=np.int32), np.ascontiguousarray(dst[a], dtype=np.int32)
+    p32 = np.ascontiguousarray(prob[a], dtype=np.float32)
+    keep = np.empty(a.size, dtype=np.uint8)
+    stats = (C.c_int64 * 4)()
+    m._lib.check(m._lib.lib().mpn_split_exact_host(s32.ctypes.data, d32.ctypes.data, p32.ctypes.data, a.size, n_nodes, cams,
+                                                   keep.ctypes.data, C.cast(stats, C.c_void_p)))
+    got = act.copy()
+    got[a[keep == 0]] = 0
+    assert int((got != ref).sum()) == 0
+    assert stats[0] > 8000 and stats[1] > 0                      # dropped values; steps on a label other than the lowest
+    lab, _ = pc.scc_labels(src, dst, got, n_nodes)
+    assert hashlib.sha256(np.ascontiguousarray(lab, dtype=np.int64).tobytes()).digest() == g["labels_sha256"].tobytes()
+    assert int((pc.split(src, dst, act, prob, cams, n_nodes) != ref).sum()) > 0       # all-clusters-per-round differs here
 
 
 def test_host_numbering_equals_networkx_on_random_digraphs():

@@ -23,57 +23,89 @@ def m():
 
 
 def test_post_processing_200k_nodes_vs_c_oracle(m):
+    """200 k nodes, 2.2 M edges, ~0.9 M active when SPLITTING starts, 1568 tied probability values: the default path against the
+    reference's own SPLITTING order (oracle/postproc_oracle.c::po_split_sequential, stored by tests/golden/make_split200k.py —
+    8 minutes of CPU) with ZERO differing decisions, and the reference's label integers; CUT / PRUNE against the C oracle live."""
+    import hashlib
+    import os
+    from tests._util import GOLDEN
     c = GPU_CASE
     dev = torch.device("cuda", 0)
     src, dst, prob, pred, _ = po.planted_prediction_graph(c["n_nodes"], c["cams"], c["seed"], n_extra_per_node=c["n_extra_per_node"],
                                                           flip_on=c["flip_on"], flip_off=c["flip_off"], single_dir=c["single_dir"])
-    lab_ref, act_ref = pc.post_processing(src, dst, pred, prob, c["cams"], c["n_nodes"], numbering="reference")
+    gold = np.load(os.path.join(GOLDEN, "split200k_sequential.npz"))
+    assert list(gold["spec"]) == [c["n_nodes"], c["cams"], c["seed"]] and int(gold["n_edges"][0]) == src.size
+    start = pc.cut(src, dst, pred, c["n_nodes"])
+    start, _ = pc.prune(src, dst, start, prob, c["cams"], c["n_nodes"])
+    start = pc.cut(src, dst, start, c["n_nodes"])
+    start_idx = np.flatnonzero(start)
+    assert start_idx.size == int(gold["n_start_active"][0])
+    act_ref = np.zeros(src.size, dtype=np.int64)
+    act_ref[start_idx] = np.unpackbits(gold["final_bits"])[:start_idx.size]
     data = Data(x=torch.zeros(c["n_nodes"], 1, device=dev), edge_index=torch.from_numpy(np.stack([src, dst])).to(dev))
     cfg = {"CUTTING": True, "PRUNING": True, "SPLITTING": True}
     ID, P = m.post_processing(c["cams"], None, None, torch.from_numpy(pred).to(dev), None, cfg, data, torch.from_numpy(prob).to(dev))
-    assert np.array_equal(P.cpu().numpy(), act_ref)                                # decisions: bit-exact
-    assert np.array_equal(ID.numpy(), lab_ref)                                     # the reference's label integers: bit-exact
+    stats = m.split_stats()
+    assert stats["mode"] == "reference_order_host" and stats["tied_edges"] > 0 and stats["rounds"] > 0
+    assert int((P.cpu().numpy() != act_ref).sum()) == 0                            # decisions: bit-exact, ties included
+    assert hashlib.sha256(np.ascontiguousarray(ID.numpy(), dtype=np.int64).tobytes()).digest() == gold["labels_sha256"].tobytes()
     assert np.bincount(ID.numpy()).max() <= c["cams"]                              # size-independent property
     IDc, Pc = m.post_processing(c["cams"], None, None, torch.from_numpy(pred).to(dev), None, cfg, data, torch.from_numpy(prob).to(dev),
                                 numbering="canonical")
-    assert np.array_equal(Pc.cpu().numpy(), act_ref) and same_partition(IDc.numpy(), lab_ref)
+    assert np.array_equal(Pc.cpu().numpy(), act_ref) and same_partition(IDc.numpy(), ID.numpy())
+    # the rounds formulation (what round 1 shipped) differs on this graph: the fixture does pin the order
+    assert int((pc.split(src, dst, start, prob, c["cams"], c["n_nodes"]) != act_ref).sum()) > 0
 
 
-def test_split_order_reference_experimental(m):
-    """post_processing(split_order='reference') — SPLITTING on the host in the reference's own order — against the outputs of the
-    UNMODIFIED reference on graphs with exact probability ties (tests/golden/ties_cases.npz; on half of them the default rounds give
-    other decisions), and on a 20 k-node planted graph where the two orders agree."""
-    import os
-    if os.environ.get("MPN_TEST_EXPERIMENTAL") != "1":
-        pytest.skip("split_order='reference' was written after the round's GPU time was spent; MPN_TEST_EXPERIMENTAL=1 runs it")
+def test_splitting_under_ties_matches_the_reference(m):
+    """The DEFAULT post_processing against the outputs of the UNMODIFIED reference on graphs with exact probability ties
+    (tests/golden/ties_cases.npz; on half of them all-clusters-per-round gives other decisions), three flag sets each; and graphs
+    without ties take the device rounds."""
     from tests.test_c_oracle import _ties_cases
     dev = torch.device("cuda", 0)
-    rounds_differ = 0
+    host_mode = 0
     for i, s, d, prob, pred, C, n, ref in _ties_cases():
         data = Data(x=torch.zeros(n, 1, device=dev), edge_index=torch.from_numpy(np.stack([s, d])).to(dev))
         for tag, cfg in (("full", (True, True, True)), ("split_only", (False, False, True)), ("prune_split", (False, True, True))):
             CONFIG = {"CUTTING": cfg[0], "PRUNING": cfg[1], "SPLITTING": cfg[2]}
             ID, P = m.post_processing(C, None, None, torch.from_numpy(pred).to(dev), None, dict(CONFIG), data,
-                                      torch.from_numpy(prob).to(dev), split_order="reference")
+                                      torch.from_numpy(prob).to(dev))
+            host_mode += m.split_stats()["mode"] == "reference_order_host"
             assert np.array_equal(P.cpu().numpy(), ref["pred_" + tag]), (i, tag)          # the reference's decisions
             assert np.array_equal(ID.numpy(), ref["labels_" + tag]), (i, tag)             # and its label integers
-            ID, P = m.post_processing(C, None, None, torch.from_numpy(pred).to(dev), None, dict(CONFIG), data,
-                                      torch.from_numpy(prob).to(dev))                      # the default: rounds
-            lab_r, act_r = pc.post_processing(s, d, pred, prob, C, n, *cfg, numbering="reference")
-            assert np.array_equal(P.cpu().numpy(), act_r) and np.array_equal(ID.numpy(), lab_r), (i, tag)
-            rounds_differ += not np.array_equal(act_r, ref["pred_" + tag])
-    assert rounds_differ >= 5
+            if tag == "split_only":                                                       # splitting() mutates its argument (utils.py:98)
+                p2 = torch.from_numpy(pred).to(dev)
+                out = m.splitting(None, p2, torch.from_numpy(prob).to(dev), None, data, None, C)
+                assert out is p2 and np.array_equal(p2.cpu().numpy(), ref["pred_" + tag]), (i, tag)
+    assert host_mode >= 10
     n_nodes, cams = 20000, 8
     src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, cams, 2, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03,
                                                           single_dir=0.05)
-    lab_ref, act_ref = pc.post_processing(src, dst, pred, prob, cams, n_nodes, numbering="reference")
+    start = pc.cut(src, dst, pred, n_nodes)
+    start, _ = pc.prune(src, dst, start, prob, cams, n_nodes)
+    start = pc.cut(src, dst, start, n_nodes)
+    act_ref = pc.split_sequential(src, dst, start, prob, cams, n_nodes)                   # the reference's order (5 s of CPU)
+    lab_ref, _ = pc.scc_labels(src, dst, act_ref, n_nodes)
     data = Data(x=torch.zeros(n_nodes, 1, device=dev), edge_index=torch.from_numpy(np.stack([src, dst])).to(dev))
     for numbering in ("reference", "canonical"):
         ID, P = m.post_processing(cams, None, None, torch.from_numpy(pred).to(dev), None,
                                   {"CUTTING": True, "PRUNING": True, "SPLITTING": True}, data, torch.from_numpy(prob).to(dev),
-                                  numbering=numbering, split_order="reference")
+                                  numbering=numbering)
         assert np.array_equal(P.cpu().numpy(), act_ref)
         assert np.array_equal(ID.numpy(), lab_ref) if numbering == "reference" else same_partition(ID.numpy(), lab_ref)
+    # distinct probabilities -> no tie -> device rounds, same result as the reference's order
+    rng = np.random.default_rng(0)
+    prob_u = rng.permutation(np.linspace(0.55, 0.99, prob.size, dtype=np.float64)).astype(np.float32)
+    prob_u = np.where(pred > 0, prob_u, np.float32(1.0) - prob_u).astype(np.float32)
+    assert np.unique(prob_u[pred > 0]).size == int((pred > 0).sum())
+    ID, P = m.post_processing(cams, None, None, torch.from_numpy(pred).to(dev), None,
+                              {"CUTTING": True, "PRUNING": True, "SPLITTING": True}, data, torch.from_numpy(prob_u).to(dev))
+    st = m.split_stats()
+    assert st["mode"] == "device_rounds" and st["tied_edges"] == 0 and st["rounds"] > 0
+    start = pc.cut(src, dst, pred, n_nodes)
+    start, _ = pc.prune(src, dst, start, prob_u, cams, n_nodes)
+    start = pc.cut(src, dst, start, n_nodes)
+    assert np.array_equal(P.cpu().numpy(), pc.split_sequential(src, dst, start, prob_u, cams, n_nodes))
 
 
 def test_post_processing_matches_the_reference_at_s02_size(m):
