@@ -27,7 +27,7 @@ W_EDGE_W0, W_NODE_W0, W_SMALL_FLOATS = 1592, 1864, 2888
 
 class MpnGraph(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_cols", C.c_int32), ("row_offset", C.c_int32), ("chunk", C.c_int32),
-                ("n_edges", C.c_int64), ("max_tasks", C.c_int32), ("reserved", C.c_int32),
+                ("n_edges", C.c_int64), ("max_tasks", C.c_int32), ("layout_hint", C.c_int32),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("taskptr", C.c_void_p), ("task_row", C.c_void_p),
                 ("n_tasks", C.c_void_p), ("n_graphs", C.c_int32), ("max_graph_nodes", C.c_int32),
                 ("node_gid", C.c_void_p), ("graph_nptr", C.c_void_p)]
@@ -79,13 +79,14 @@ _PROTOS = {
     "mpn_kernel_launches": (C.c_uint64, []),
     "mpn_check_device": (C.c_int, [C.c_int]),
     "mpn_set_pdl": (C.c_int, [C.c_int]),
-    "mpn_set_fused_distance": (C.c_int, [C.c_int]),
     "mpn_graph_build": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p]),
     "mpn_graph_build_i32": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_graph_build_deferred": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_cross_camera_edges": (C.c_int64, [C.c_void_p, C.c_int32]),
     "mpn_cross_camera_block_edges": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "mpn_graph_build_cross_camera": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mpn_profile_gram": (C.c_int, [C.c_int]),
+    "mpn_profile_gram_ms": (C.c_float, []),
     "mpn_edge_features_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph), C.c_int32]),
     "mpn_edge_features": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_forward_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_int32]),

@@ -10,7 +10,7 @@ mkdir -p "${OBJ}"
 # objects built with other flags are stale
 if [ "$(cat "${OBJ}/.flags" 2>/dev/null)" != "${FLAGS[*]}" ]; then rm -f "${OBJ}"/*.o; echo "${FLAGS[*]}" > "${OBJ}/.flags"; fi
 pids=()
-for f in graph gemm_simt gemm_tc gemm_api edge_features mpn_forward postproc split_exact eval; do
+for f in graph gemm_simt gemm_tc gemm_api gram_ef edge_features mpn_forward postproc split_exact eval; do
   if [ ! -f "${OBJ}/${f}.o" ] || [ "${HERE}/${f}.cu" -nt "${OBJ}/${f}.o" ] || [ "${HERE}/common.cuh" -nt "${OBJ}/${f}.o" ] || \
      [ "${HERE}/kernels.h" -nt "${OBJ}/${f}.o" ] || [ "${HERE}/tcgen05.cuh" -nt "${OBJ}/${f}.o" ] || [ "${HERE}/edge_feature_gather.inc" -nt "${OBJ}/${f}.o" ] || [ "${HERE}/../../include/mpn_b200.h" -nt "${OBJ}/${f}.o" ]; then
     "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${OBJ}/${f}.o" &

@@ -74,7 +74,6 @@ static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / 
 // Rule: pdl_wait() is the FIRST statement of every kernel launched through launch(), before any early return (a grid whose
 // blocks all skipped it would let its own successor overtake the predecessor).
 extern int g_pdl_launch;             // run-time switch
-extern int g_fused_distance;         // run-time switch of the fused distance epilogue (mpn_set_fused_distance)
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -44,8 +44,9 @@ __global__ void col_mean_finalize_kernel(const double* __restrict__ part, int n,
 // per edge; the Gram entry they are combined with is itself only fp32-accurate): st[r] = {|a'|^2, sum a', mu.a' + |mu|^2/2, |a|}
 __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu, int n, int D,
                                                           float* __restrict__ xc, float4* __restrict__ st,
-                                                          unsigned int* __restrict__ amax_bits) {
+                                                          unsigned int* __restrict__ amax_bits, const int* __restrict__ run_flag) {
   pdl_wait();
+  if (run_flag != nullptr && *run_flag == 0) return;
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -111,37 +112,34 @@ __global__ void __launch_bounds__(256) gram_blockdiag_simt_kernel(const float* _
   }
 }
 
-// one warp per task (a run of edges of one row): coalesced Gram reads when the row's columns are consecutive
+// one warp per task (a run of edges of one row): coalesced Gram reads when the row's columns are consecutive.
+// run_flag (optional): nothing to do when *run_flag == 0 (the fused kernel of gram_ef.cu wrote the features itself)
 __global__ void __launch_bounds__(256) edge_feature_gather_kernel(const mpn_graph g, int r0, int r1, const float* __restrict__ G,
                                                                   const long long* __restrict__ g_off,
                                                                   const float4* __restrict__ st, int D,
                                                                   float2* __restrict__ edge_attr,
-                                                                  int* __restrict__ refine_list, int* __restrict__ refine_count) {
+                                                                  int* __restrict__ refine_list, int* __restrict__ refine_count,
+                                                                  const int* __restrict__ run_flag) {
   pdl_wait();
-#include "edge_feature_gather.inc"
-}
-// the same pass behind the fused distance epilogue: nothing to do when the GEMM's epilogue wrote the features itself
-__global__ void __launch_bounds__(256) edge_feature_gather_unless_fused_kernel(const mpn_graph g, int r0, int r1, const float* __restrict__ G,
-                                                                               const float4* __restrict__ st, int D,
-                                                                               float2* __restrict__ edge_attr, int* __restrict__ refine_list,
-                                                                               int* __restrict__ refine_count,
-                                                                               const int* __restrict__ not_one_gap) {
-  pdl_wait();
-  if (*not_one_gap == 0) return;
-  const long long* g_off = nullptr;
+  if (run_flag != nullptr && *run_flag == 0) return;
 #include "edge_feature_gather.inc"
 }
 
 // direct recomputation for the flagged pairs (one warp per pair), fp32 elementwise like ATen
+// fixed_sums (optional, with the fused kernel only): the moment sums (a, b, aa, ab, bb) of the recomputed pairs are added as
+// 2^40 fixed point integers, so the total does not depend on the order in which the list was filled
 __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_graph g, const float* __restrict__ x, int D,
                                                                   const int* __restrict__ refine_list,
                                                                   const int* __restrict__ refine_count,
-                                                                  float2* __restrict__ edge_attr) {
+                                                                  float2* __restrict__ edge_attr,
+                                                                  unsigned long long* __restrict__ fixed_sums,
+                                                                  const int* __restrict__ not_one_gap) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n = *refine_count;
+  const bool with_sums = fixed_sums != nullptr && not_one_gap != nullptr && *not_one_gap == 0;
   for (int i = gwarp; i < n; i += nwarps) {
     const int e = refine_list[i];
     int lo = 0, hi = g.n_nodes;                       // row = last r with rowptr[r] <= e
@@ -163,30 +161,18 @@ __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_grap
     d2 = warp_sum(d2); ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
     if (lane == 0) {
       const double denom = fmax(sqrt(aa) * sqrt(bb), (double)COSINE_EPS);
-      edge_attr[e] = make_float2((float)sqrt(d2), (float)(1.0 - ab / denom));
+      const float2 o = make_float2((float)sqrt(d2), (float)(1.0 - ab / denom));
+      edge_attr[e] = o;
+      if (with_sums) {
+        const double fa = o.x, fb = o.y, sc = 1099511627776.0;        // 2^40
+        atomicAdd(fixed_sums + 0, (unsigned long long)__double2ll_rn(fa * sc));
+        atomicAdd(fixed_sums + 1, (unsigned long long)__double2ll_rn(fb * sc));
+        atomicAdd(fixed_sums + 2, (unsigned long long)__double2ll_rn(fa * fa * sc));
+        atomicAdd(fixed_sums + 3, (unsigned long long)__double2ll_rn(fa * fb * sc));
+        atomicAdd(fixed_sums + 4, (unsigned long long)__double2ll_rn(fb * fb * sc));
+      }
     }
   }
-}
-
-// EXPERIMENTAL fused distance epilogue: (first column, length) of the one gap in each row's column list, and the proof that
-// the row has that shape.  Columns are strictly ascending within a row (K0), so col[beg+k] - k is non-decreasing: 0 before
-// the gap, the gap length after it -> binary search for the first k with col[beg+k] != k.  The row is "all columns but
-// [k, k+gl)" iff the entry after the gap is k+gl and the last entry is n_cols-1 (deg-k strictly ascending values in a range
-// of exactly deg-k integers); the prefix is 0..k-1 by the search invariant.  Any other row raises *not_one_gap.
-__global__ void __launch_bounds__(256) gap_table_kernel(const mpn_graph g, int2* __restrict__ gap, int* __restrict__ not_one_gap) {
-  pdl_wait();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= g.n_nodes) return;
-  const int beg = g.rowptr[r], deg = g.rowptr[r + 1] - beg;
-  const int gl = g.n_cols - deg;
-  int lo = 0, hi = deg;                                  // first k with col[beg+k] != k (deg: the gap is at the end)
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (g.col[beg + mid] == mid) lo = mid + 1; else hi = mid;
-  }
-  gap[r] = make_int2(lo, gl);
-  const bool ok = gl >= 0 && (lo == deg || (g.col[beg + lo] == lo + gl && g.col[beg + deg - 1] == g.n_cols - 1));
-  if (!ok) atomicOr(not_one_gap, 1);
 }
 
 struct EfLayout {
@@ -196,12 +182,15 @@ struct EfLayout {
   float* G;
   int *refine_list, *refine_count;
   unsigned int* amax_bits;         // max |x'| over the centred features (float bits): scale of the fp16 operand planes
+  unsigned int* mu_ticket;         // last-block ticket of the column-mean kernel
   long long* g_off;
   void* gemm_ws;
   size_t gemm_ws_bytes;
   int rows_per_block;
-  int2* gap;                       // fused distance epilogue: one-gap table of the rows (last slices: the other offsets do not move)
+  int2* gap;                       // fused distance epilogue: one-gap table of the rows
   int* not_one_gap;
+  GeWorkspace ge;                  // planes / records / tile list of the fused kernel (gram_ef.cu)
+  bool fused_possible;
   size_t total;
 };
 
@@ -210,7 +199,7 @@ static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) 
   Arena a(ws, ws_bytes);
   L.st = a.take<float4>((size_t)g->n_cols);
   L.mu = a.take<float>(D);
-  L.mu_part = a.take<double>((size_t)CM_SPLITS * D);
+  L.mu_part = a.take<double>((size_t)(ge_col_mean_splits() > CM_SPLITS ? ge_col_mean_splits() : CM_SPLITS) * D);
   L.xc = a.take<float>((size_t)g->n_cols * D);
   const bool batched = g->n_graphs > 1 && g->node_gid && g->graph_nptr;
   const size_t budget = (size_t)2 << 30;
@@ -224,12 +213,104 @@ static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) 
   L.refine_list = a.take<int>((size_t)(g->n_edges > 0 ? g->n_edges : 1));
   L.refine_count = a.take<int>(1);
   L.amax_bits = a.take<unsigned int>(1);
+  L.mu_ticket = a.take<unsigned int>(64);                    // one per 128-column tile (D <= 8192)
+  L.not_one_gap = a.take<int>(1);
   L.gemm_ws_bytes = batched ? gemm_tc_workspace_bytes(1, g->n_cols, D) : gemm_tc_workspace_bytes((int)rows, g->n_cols, D);
   L.gemm_ws = L.gemm_ws_bytes ? (void*)a.take<char>(L.gemm_ws_bytes) : nullptr;
   L.gap = a.take<int2>((size_t)(g->n_nodes > 0 ? g->n_nodes : 1));
-  L.not_one_gap = a.take<int>(1);
+  L.fused_possible = !batched && gram_ef_shape_ok(g->n_nodes, g->n_cols, D);
+  memset(&L.ge, 0, sizeof(L.ge));
+  if (L.fused_possible) {
+    ge_workspace_layout(g->n_cols, g->n_nodes, D, &L.ge, ws ? (char*)ws + a.off : nullptr, ws ? (ws_bytes > a.off ? ws_bytes - a.off : 0) : 0);
+    a.off += L.ge.total;
+  }
   L.total = a.off;
   return L;
+}
+
+// moments (optional): the caller wants the first encoder BatchNorm's moment sums taken on the way (mpn_forward_with_edge_features).
+//   partials   [>= 148][MPN_SUMS_DOUBLES] zeroed by the caller; the fused kernel writes one row per CTA
+//   fixed_sums [5] zeroed by the caller; the refine pass adds the recomputed pairs' share as 2^40 fixed point
+//   handled    out: device flag, 0 = the fused kernel produced features AND moments, != 0 = the caller must sweep edge_attr itself;
+//              nullptr when that is already known on the host (known_fused tells which)
+int edge_features_impl(const mpn_graph* g, const float* x, int32_t D, float* edge_attr, int use_tc, void* ws, size_t ws_bytes,
+                       cudaStream_t st, EfMoments* moments) {
+  MPN_REQUIRE(g && x && D > 0 && ws, "edge_features: NULL argument");
+  MPN_REQUIRE(edge_attr || g->n_edges == 0, "edge_features: NULL output");
+  MPN_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  EfLayout L = ef_layout(g, D, ws, ws_bytes);
+  if (L.total > ws_bytes) {
+    set_error("edge_features workspace too small: need %zu bytes, have %zu", L.total, ws_bytes);
+    return MPN_ERR_WORKSPACE;
+  }
+  if (moments) { moments->handled_flag = nullptr; moments->known_fused = 0; }
+  if (g->n_edges == 0) return MPN_OK;
+  MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, 4 * 256, st));        // refine_count, amax_bits, mean ticket, not_one_gap (adjacent slices)
+  if ((D % 4) == 0 && D <= 8192 && (((uintptr_t)x) & 15) == 0) {          // (64 ticket slots: one per 128-column tile)
+    MPN_TRY(ge_col_mean(x, g->n_cols, D, L.mu_part, L.mu_ticket, L.mu, st));
+  } else {
+    mpn::launch(col_mean_partial_kernel, dim3(div_up(D, 32), CM_SPLITS), 256, 0, st, x, g->n_cols, D, div_up(g->n_cols, CM_SPLITS), L.mu_part);
+    MPN_LAUNCH_OK();
+    mpn::launch(col_mean_finalize_kernel, div_up(D, 128), 128, 0, st, L.mu_part, g->n_cols, D, L.mu);
+    MPN_LAUNCH_OK();
+  }
+  if (g->n_graphs > 1 && g->node_gid && g->graph_nptr) {
+    // batched small graphs: block-diagonal Gram (one ng x ng block per graph), gather epilogue
+    mpn::launch(center_rows_kernel, min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st, x, L.mu, g->n_cols, D, L.xc, L.st, L.amax_bits,
+                (const int*)nullptr);
+    MPN_LAUNCH_OK();
+    MPN_REQUIRE(g->row_offset == 0 && g->n_cols == g->n_nodes && g->max_graph_nodes > 0, "batched edge features: bad graph");
+    mpn::launch(gram_offsets_kernel, 1, 32, 0, st, g->graph_nptr, g->n_graphs, L.g_off);
+    MPN_LAUNCH_OK();
+    if (use_tc && gemm_tc_supported(g->n_cols, 64, D) && g->n_graphs <= 65535) {
+      MPN_TRY(gram_blockdiag_tc(L.xc, g->n_cols, D, g->graph_nptr, L.g_off, g->n_graphs, g->max_graph_nodes, L.G, L.gemm_ws,
+                                L.gemm_ws_bytes, st, (const float*)L.amax_bits));
+    } else {
+      mpn::launch(gram_blockdiag_simt_kernel, kNumSMs * 8, 256, 0, st, L.xc, g->n_cols, D, g->node_gid, g->graph_nptr, L.g_off, L.G);
+      MPN_LAUNCH_OK();
+    }
+    mpn::launch(edge_feature_gather_kernel, kNumSMs * 8, 256, 0, st, *g, 0, g->n_nodes, L.G, L.g_off, L.st, D, (float2*)edge_attr, L.refine_list,
+                                                           L.refine_count, (const int*)nullptr);
+    MPN_LAUNCH_OK();
+    mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr,
+                (unsigned long long*)nullptr, (const int*)nullptr);
+    MPN_LAUNCH_OK();
+    return MPN_OK;
+  }
+  // Dense cross-camera graphs (every row = all columns but one gap; verified on the device unless the builder of the graph
+  // vouches for it through g->layout_hint): the features are formed in the epilogue of the Gram GEMM (gram_ef.cu).  Any other
+  // graph: Gram block in HBM + gather.  With an unknown layout both sets of launches are enqueued, each kernel tests the
+  // device flag first and one set returns at once.
+  const bool fused = use_tc && L.fused_possible;
+  const bool known_one_gap = fused && g->layout_hint == MPN_LAYOUT_ONE_GAP;
+  const int* run_gather = nullptr;                   // old path: unconditional
+  if (fused) {
+    int n_rows = 0;
+    MPN_TRY(gram_ef_run(x, L.mu, g, D, L.gap, L.not_one_gap, (float2*)edge_attr, L.refine_list, L.refine_count,
+                        moments ? moments->partials : nullptr, &n_rows, L.ge, st));
+    if (moments) { moments->handled_flag = L.not_one_gap; moments->known_fused = known_one_gap ? 1 : 0; }
+    run_gather = L.not_one_gap;
+  }
+  if (!known_one_gap) {
+    mpn::launch(center_rows_kernel, min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st, x, L.mu, g->n_cols, D, L.xc, L.st, L.amax_bits,
+                run_gather);
+    MPN_LAUNCH_OK();
+    for (int r0 = 0; r0 < g->n_nodes; r0 += L.rows_per_block) {
+      const int r1 = min(r0 + L.rows_per_block, g->n_nodes);
+      const float* Ablk = L.xc + (size_t)(g->row_offset + r0) * D;
+      if (use_tc && gemm_tc_supported(r1 - r0, g->n_cols, D))
+        MPN_TRY(gram_nt_tc(L.xc, g->row_offset + r0, L.G, r1 - r0, g->n_cols, D, (const float*)L.amax_bits, L.gemm_ws, L.gemm_ws_bytes, st, run_gather));
+      else
+        MPN_TRY(gemm_nt_simt(Ablk, L.xc, nullptr, nullptr, nullptr, L.G, r1 - r0, g->n_cols, D, st));
+      mpn::launch(edge_feature_gather_kernel, kNumSMs * 8, 256, 0, st, *g, r0, r1, L.G, (const long long*)nullptr, L.st, D, (float2*)edge_attr,
+                                                             L.refine_list, L.refine_count, run_gather);
+      MPN_LAUNCH_OK();
+    }
+  }
+  mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr,
+              moments ? moments->fixed_sums : (unsigned long long*)nullptr, fused ? (const int*)L.not_one_gap : (const int*)nullptr);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
 }
 
 }  // namespace mpn
@@ -245,78 +326,7 @@ size_t mpn_edge_features_workspace_bytes(const mpn_graph* g, int32_t D) {
 
 int mpn_edge_features(const mpn_graph* g, const float* x, int32_t D, float* edge_attr, int use_tc, void* ws, size_t ws_bytes,
                       void* stream) {
-  MPN_REQUIRE(g && x && D > 0 && ws, "edge_features: NULL argument");
-  MPN_REQUIRE(edge_attr || g->n_edges == 0, "edge_features: NULL output");
-  MPN_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  EfLayout L = ef_layout(g, D, ws, ws_bytes);
-  if (L.total > ws_bytes) {
-    set_error("edge_features workspace too small: need %zu bytes, have %zu", L.total, ws_bytes);
-    return MPN_ERR_WORKSPACE;
-  }
-  if (g->n_edges == 0) return MPN_OK;
-  mpn::launch(col_mean_partial_kernel, dim3(div_up(D, 32), CM_SPLITS), 256, 0, st, x, g->n_cols, D, div_up(g->n_cols, CM_SPLITS), L.mu_part);
-  MPN_LAUNCH_OK();
-  mpn::launch(col_mean_finalize_kernel, div_up(D, 128), 128, 0, st, L.mu_part, g->n_cols, D, L.mu);
-  MPN_LAUNCH_OK();
-  MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, 2 * 256, st));        // refine_count and amax_bits (adjacent 256-byte slices)
-  mpn::launch(center_rows_kernel, min(kNumSMs * 8, div_up((long long)g->n_cols * 32, 256)), 256, 0, st, x, L.mu, g->n_cols, D, L.xc, L.st, L.amax_bits);
-  MPN_LAUNCH_OK();
-  if (g->n_graphs > 1 && g->node_gid && g->graph_nptr) {
-    // batched small graphs: block-diagonal Gram (one ng x ng block per graph), same epilogue
-    MPN_REQUIRE(g->row_offset == 0 && g->n_cols == g->n_nodes && g->max_graph_nodes > 0, "batched edge features: bad graph");
-    mpn::launch(gram_offsets_kernel, 1, 32, 0, st, g->graph_nptr, g->n_graphs, L.g_off);
-    MPN_LAUNCH_OK();
-    if (use_tc && gemm_tc_supported(g->n_cols, 64, D) && g->n_graphs <= 65535) {
-      MPN_TRY(gram_blockdiag_tc(L.xc, g->n_cols, D, g->graph_nptr, L.g_off, g->n_graphs, g->max_graph_nodes, L.G, L.gemm_ws,
-                                L.gemm_ws_bytes, st, (const float*)L.amax_bits));
-    } else {
-      mpn::launch(gram_blockdiag_simt_kernel, kNumSMs * 8, 256, 0, st, L.xc, g->n_cols, D, g->node_gid, g->graph_nptr, L.g_off, L.G);
-      MPN_LAUNCH_OK();
-    }
-    mpn::launch(edge_feature_gather_kernel, kNumSMs * 8, 256, 0, st, *g, 0, g->n_nodes, L.G, L.g_off, L.st, D, (float2*)edge_attr, L.refine_list,
-                                                           L.refine_count);
-    MPN_LAUNCH_OK();
-    mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
-    MPN_LAUNCH_OK();
-    return MPN_OK;
-  }
-  // EXPERIMENTAL (mpn_set_fused_distance, off by default): distances formed by the epilogue warps of the Gram GEMM when every
-  // row of the graph is "all columns but one gap" (decided on the device; otherwise the same launches store the Gram block
-  // and gather from it as below)
-  if (g_fused_distance && use_tc && gram_ef_supported(min(L.rows_per_block, g->n_nodes), g->n_cols, D, (const float*)L.amax_bits)) {
-    MPN_CUDA_OK(cudaMemsetAsync(L.not_one_gap, 0, sizeof(int), st));
-    mpn::launch(gap_table_kernel, div_up(g->n_nodes, 256), 256, 0, st, *g, L.gap, L.not_one_gap);
-    MPN_LAUNCH_OK();
-    for (int r0 = 0; r0 < g->n_nodes; r0 += L.rows_per_block) {
-      const int r1 = min(r0 + L.rows_per_block, g->n_nodes);
-      EfEpilogue ef;
-      ef.st = L.st; ef.rowptr = g->rowptr; ef.gap = L.gap; ef.not_one_gap = L.not_one_gap; ef.edge_attr = (float2*)edge_attr;
-      ef.refine_list = L.refine_list; ef.refine_count = L.refine_count;
-      ef.row_local0 = r0; ef.row_global0 = g->row_offset + r0; ef.D = D;
-      MPN_TRY(gram_nt_tc(L.xc, g->row_offset + r0, L.G, r1 - r0, g->n_cols, D, (const float*)L.amax_bits, L.gemm_ws, L.gemm_ws_bytes, st, &ef));
-      mpn::launch(edge_feature_gather_unless_fused_kernel, kNumSMs * 8, 256, 0, st, *g, r0, r1, L.G, L.st, D, (float2*)edge_attr,
-                  L.refine_list, L.refine_count, L.not_one_gap);
-      MPN_LAUNCH_OK();
-    }
-    mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
-    MPN_LAUNCH_OK();
-    return MPN_OK;
-  }
-  for (int r0 = 0; r0 < g->n_nodes; r0 += L.rows_per_block) {
-    const int r1 = min(r0 + L.rows_per_block, g->n_nodes);
-    const float* Ablk = L.xc + (size_t)(g->row_offset + r0) * D;
-    if (use_tc && gemm_tc_supported(r1 - r0, g->n_cols, D))
-      MPN_TRY(gram_nt_tc(L.xc, g->row_offset + r0, L.G, r1 - r0, g->n_cols, D, (const float*)L.amax_bits, L.gemm_ws, L.gemm_ws_bytes, st));
-    else
-      MPN_TRY(gemm_nt_simt(Ablk, L.xc, nullptr, nullptr, nullptr, L.G, r1 - r0, g->n_cols, D, st));
-    mpn::launch(edge_feature_gather_kernel, kNumSMs * 8, 256, 0, st, *g, r0, r1, L.G, nullptr, L.st, D, (float2*)edge_attr,
-                                                           L.refine_list, L.refine_count);
-    MPN_LAUNCH_OK();
-  }
-  mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr);
-  MPN_LAUNCH_OK();
-  return MPN_OK;
+  return mpn::edge_features_impl(g, x, D, edge_attr, use_tc, ws, ws_bytes, (cudaStream_t)stream, nullptr);
 }
 
 }  // extern "C"

@@ -64,35 +64,16 @@ struct TcCfg {
 };
 
 // SYM: C = A A^T (A == B, M == N): only tiles on or above the diagonal are computed, the epilogue also writes the mirror.
-// distance epilogue of one Gram entry g = a'.b' for the ordered pair (a = aggregated-at node, b = neighbour): the arithmetic
-// of edge_feature_gather_kernel (edge_features.cu), statement for statement
-__device__ __forceinline__ void ef_store(const EfEpilogue& E, int e, const float4 a, const float4 b, float g) {
-  const double eps = (double)PAIRWISE_EPS;
-  const double sa = a.x, xa = a.y, ma = a.z;
-  const double gij = g;
-  double d2 = sa + (double)b.x - 2.0 * gij + 2.0 * eps * (xa - (double)b.y) + E.D * eps * eps;
-  if (d2 < (double)REFINE_FRACTION * (sa + (double)b.x)) {
-    const int slot = atomicAdd(E.refine_count, 1);
-    E.refine_list[slot] = e;
-  }
-  if (d2 < 0.0) d2 = 0.0;
-  const double ab = gij + ma + (double)b.z;
-  const float denom = fmaxf(a.w * b.w, COSINE_EPS);
-  E.edge_attr[e] = make_float2(sqrtf((float)d2), 1.0f - (float)ab / denom);
-}
-
-template <bool EF> struct EfParam { typedef EfNone type; };
-template <> struct EfParam<true> { typedef EfEpilogue type; };
-
-template <int BN, bool SYM, bool F16, bool EF = false>
+// run_flag (optional, device): the grid returns at once when *run_flag == 0.
+template <int BN, bool SYM, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                       const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
                       const int* __restrict__ graph_nptr, const long long* __restrict__ g_off,
-                      const float* __restrict__ out_scale, const typename EfParam<EF>::type ef) {
+                      const float* __restrict__ out_scale, const int* __restrict__ run_flag) {
   pdl_wait();
-  static_assert(!EF || (F16 && BN == TC_BM), "the distance epilogue is written for the fp16 planes and square tiles");
+  if (run_flag != nullptr && *run_flag == 0) return;
   constexpr int BK = F16 ? TC_BK_F16 : TC_BK;            // elements of K per stage (128 bytes either way)
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -117,30 +98,6 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     M = N = ng;
     C += g_off[blockIdx.z];
   }
-  bool ef_on = false;                                    // block-uniform: the graph has the one-gap shape
-  if constexpr (EF) ef_on = *ef.not_one_gap == 0;
-  if constexpr (EF) {
-   if (ef_on) {
-    // a tile without edges (all of its rows have their gap across all of its columns: a same-camera tile) skips the main loop
-    int no_edges = 1;
-    if (threadIdx.x < TC_BM) {
-      const int r = m0 + threadIdx.x;
-      if (r < M) {
-        const int2 gp = ef.gap[ef.row_local0 + r];
-        no_edges = gp.x <= n0 && gp.x + gp.y >= min(n0 + BN, N);
-      }
-      if (SYM && no_edges && n0 >= m0 + TC_BM) {       // the mirrored block: rows n0.., columns m0..
-        const int c = n0 + threadIdx.x;
-        if (c < N) {
-          const int2 gp = ef.gap[c];
-          no_edges = gp.x <= m0 && gp.x + gp.y >= min(m0 + TC_BM, M);
-        }
-      }
-    }
-    if (__syncthreads_and(no_edges)) return;
-   }
-  }
-
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full_bar, 1);
@@ -215,18 +172,6 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     const int row = m0 + q * 32 + lane;
     const bool vec_ok = ((N & 3) == 0) && ((((uintptr_t)C) & 15) == 0);
     const float oscale = (F16 && out_scale) ? *out_scale : 1.f;       // power of two: exact
-    // EF: this thread's row as the aggregated-at node (direct entries) and as the neighbour (mirrored entries)
-    float4 st_row = make_float4(0.f, 0.f, 0.f, 0.f);
-    int rp_row = 0, gap0 = 0, gap1 = 0;
-    if constexpr (EF) {
-      if (ef_on && row < M) {
-        st_row = ef.st[ef.row_global0 + row];
-        rp_row = ef.rowptr[ef.row_local0 + row];
-        const int2 gp = ef.gap[ef.row_local0 + row];
-        gap0 = gp.x;
-        gap1 = gp.x + gp.y;
-      }
-    }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= N) break;                                                  // warp-uniform
@@ -241,32 +186,6 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       tmem_ld32(tq + Cfg::CORR_COL, w);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = F16 ? (v[j] + w[j]) * oscale : v[j] + w[j];
-      if constexpr (EF) {
-       if (ef_on) {
-        if (row < M) {
-          // direct entries (row -> col): 32 consecutive edges of this thread's row, but for the gap
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = n0 + c0 + j;
-            if (col < N && (col < gap0 || col >= gap1))
-              ef_store(ef, rp_row + col - (col >= gap1 ? gap1 - gap0 : 0), st_row, __ldg(ef.st + col), v[j]);
-          }
-          if (SYM && n0 >= m0 + TC_BM) {
-            // mirrored entries (col -> row): the lanes of a warp hold consecutive rows = consecutive edges of node `col`
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = n0 + c0 + j;
-              if (col < N) {                                                    // warp-uniform
-                const int2 gp = __ldg(ef.gap + col);
-                if (row < gp.x || row >= gp.x + gp.y)
-                  ef_store(ef, __ldg(ef.rowptr + col) + row - (row >= gp.x + gp.y ? gp.y : 0), __ldg(ef.st + col), st_row, v[j]);
-              }
-            }
-          }
-        }
-        continue;
-       }
-      }
       if (row < M) {
         float* out = C + (size_t)row * N + n0 + c0;
         if (vec_ok && n0 + c0 + 32 <= N) {
@@ -345,8 +264,10 @@ __device__ __forceinline__ float f16_scale_of(float amax) {
   return ldexpf(1.f, 14 - e);
 }
 __global__ void __launch_bounds__(256) split_f16_kernel(const float4* __restrict__ x, long long n4, const float* __restrict__ amax,
-                                                        uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ out_scale) {
+                                                        uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ out_scale,
+                                                        const int* __restrict__ run_flag) {
   pdl_wait();
+  if (run_flag != nullptr && *run_flag == 0) return;
   const float s = f16_scale_of(*amax);
   if (out_scale && blockIdx.x == 0 && threadIdx.x == 0) *out_scale = (1.f / s) * (1.f / s);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -385,7 +306,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* base, int rows, int K, int box_rows, bool f16 = false) {
+int make_tma_map_2d(CUtensorMap* map, const void* base, int rows, int K, int box_rows, bool f16) {
   EncodeTiledFn enc = get_encode_fn();
   MPN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -415,19 +336,18 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K) {
   return 2 * plane_a + 2 * plane_b + 1024;
 }
 
-template <int BN, bool SYM, bool F16 = false, bool EF = false>
+template <int BN, bool SYM, bool F16 = false>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const float* bias,
                      float* C, int M, int N, int K, cudaStream_t st, const int* graph_nptr = nullptr, const long long* g_off = nullptr,
-                     int n_graphs = 1, int max_ng = 0, const float* out_scale = nullptr,
-                     const typename EfParam<EF>::type& ef = typename EfParam<EF>::type()) {
+                     int n_graphs = 1, int max_ng = 0, const float* out_scale = nullptr, const int* run_flag = nullptr) {
   static bool configured = false;
   if (!configured) {
-    MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN, SYM, F16, EF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+    MPN_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<BN, SYM, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
     configured = true;
   }
   dim3 grid(div_up(N, BN), div_up(M, TC_BM));
   if (graph_nptr) grid = dim3(div_up(max_ng, BN), div_up(max_ng, TC_BM), n_graphs);
-  mpn::launch(gemm_nt_3xtf32_kernel<BN, SYM, F16, EF>, grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st, ah, al, bh, bl, bias, C, M, N, K, graph_nptr, g_off, out_scale, ef);
+  mpn::launch(gemm_nt_3xtf32_kernel<BN, SYM, F16>, grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st, ah, al, bh, bl, bias, C, M, N, K, graph_nptr, g_off, out_scale, run_flag);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -469,10 +389,10 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
   }
   // 128-wide tiles measured both faster (3 stages, more tiles per wave) and more accurate (three accumulators) than 256
   const int BN = (forced_bn == 128 || forced_bn == 256) ? forced_bn : 128;
-  MPN_TRY(make_map(&ah, a_hi, M, K, TC_BM));
-  MPN_TRY(make_map(&al, a_lo, M, K, TC_BM));
-  MPN_TRY(make_map(&bh, b_hi, N, K, BN));
-  MPN_TRY(make_map(&bl, b_lo, N, K, BN));
+  MPN_TRY(make_tma_map_2d(&ah, a_hi, M, K, TC_BM, false));
+  MPN_TRY(make_tma_map_2d(&al, a_lo, M, K, TC_BM, false));
+  MPN_TRY(make_tma_map_2d(&bh, b_hi, N, K, BN, false));
+  MPN_TRY(make_tma_map_2d(&bl, b_lo, N, K, BN, false));
   const bool sym = (A == B) && (M == N) && bias == nullptr;     // Gram matrix: half the tiles
   if (BN == 256) return launch_tc<256, false>(ah, al, bh, bl, bias, C, M, N, K, st);
   if (sym) return launch_tc<128, true>(ah, al, bh, bl, bias, C, M, N, K, st);
@@ -573,10 +493,10 @@ int gemm_nt_tc_f16(const float* A, const float* bias, float* C, int M, int N, in
                                                    b_scale, (uint2*)a_hi, (uint2*)a_lo, out_scale);
   MPN_LAUNCH_OK();
   CUtensorMap ah, al, bh, bl;
-  MPN_TRY(make_map(&ah, a_hi, M, K, TC_BM, true));
-  MPN_TRY(make_map(&al, a_lo, M, K, TC_BM, true));
-  MPN_TRY(make_map(&bh, b_hi16, N, K, 128, true));
-  MPN_TRY(make_map(&bl, b_lo16, N, K, 128, true));
+  MPN_TRY(make_tma_map_2d(&ah, a_hi, M, K, TC_BM, true));
+  MPN_TRY(make_tma_map_2d(&al, a_lo, M, K, TC_BM, true));
+  MPN_TRY(make_tma_map_2d(&bh, b_hi16, N, K, 128, true));
+  MPN_TRY(make_tma_map_2d(&bl, b_lo16, N, K, 128, true));
   return launch_tc<128, false, true>(ah, al, bh, bl, bias, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);
 }
 
@@ -588,16 +508,13 @@ static bool gram_f16_enabled() {
 
 // Gram block C[M,N] = A X^T where A is the row block of X starting at row a_row0 (X: [N,K], amax_dev = max |X| as float bits
 // written by the producer of X).  fp16 planes (3xFP16) when K % 8 == 0, else the TF32 path.  Symmetric tiles when A == X.
-bool gram_ef_supported(int M, int N, int K, const float* amax_dev) {
-  return gram_f16_enabled() && amax_dev != nullptr && (K % 8) == 0 && gemm_tc_supported(M, N, K);
-}
-
 int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const float* amax_dev, void* ws, size_t ws_bytes, cudaStream_t st,
-               const EfEpilogue* ef) {
+               const int* run_flag) {
   const float* A = X + (size_t)a_row0 * K;
-  MPN_REQUIRE(ef == nullptr || gram_ef_supported(M, N, K, amax_dev), "fused distance epilogue: needs the fp16 operand planes");
-  if (!gram_f16_enabled() || amax_dev == nullptr || (K % 8) != 0)
+  if (!gram_f16_enabled() || amax_dev == nullptr || (K % 8) != 0) {
+    MPN_REQUIRE(run_flag == nullptr, "tcgen05 Gram: the TF32 planes have no conditional launch");
     return gemm_nt_tc(A, X, nullptr, C, M, N, K, ws, ws_bytes, st);
+  }
   MPN_REQUIRE(gemm_tc_supported(M, N, K), "tcgen05 Gram: unsupported shape %d x %d x %d", M, N, K);
   MPN_REQUIRE(ws && ws_bytes >= gemm_tc_workspace_bytes(M, N, K), "tcgen05 Gram: workspace too small");
   char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
@@ -605,21 +522,15 @@ int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const 
   __half* hi = (__half*)w;
   __half* lo = (__half*)(w + plane);
   float* out_scale = (float*)(w + 2 * plane);
-  mpn::launch(split_f16_kernel, kNumSMs * 8, 256, 0, st, (const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi, (uint2*)lo, out_scale);
+  mpn::launch(split_f16_kernel, kNumSMs * 8, 256, 0, st, (const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi, (uint2*)lo, out_scale, run_flag);
   MPN_LAUNCH_OK();
   CUtensorMap ah, al, bh, bl;
-  MPN_TRY(make_map(&ah, hi + (size_t)a_row0 * K, M, K, TC_BM, true));
-  MPN_TRY(make_map(&al, lo + (size_t)a_row0 * K, M, K, TC_BM, true));
-  MPN_TRY(make_map(&bh, hi, N, K, 128, true));
-  MPN_TRY(make_map(&bl, lo, N, K, 128, true));
-  if (ef != nullptr) {
-    MPN_REQUIRE(C != nullptr && ef->not_one_gap != nullptr, "fused distance epilogue: the Gram block is the fallback and must exist");
-    if (a_row0 == 0 && M == N && ef->row_local0 == 0 && ef->row_global0 == 0)
-      return launch_tc<128, true, true, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, *ef);
-    return launch_tc<128, false, true, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, *ef);
-  }
-  if (a_row0 == 0 && M == N) return launch_tc<128, true, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);
-  return launch_tc<128, false, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale);
+  MPN_TRY(make_tma_map_2d(&ah, hi + (size_t)a_row0 * K, M, K, TC_BM, true));
+  MPN_TRY(make_tma_map_2d(&al, lo + (size_t)a_row0 * K, M, K, TC_BM, true));
+  MPN_TRY(make_tma_map_2d(&bh, hi, N, K, 128, true));
+  MPN_TRY(make_tma_map_2d(&bl, lo, N, K, 128, true));
+  if (a_row0 == 0 && M == N) return launch_tc<128, true, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, run_flag);
+  return launch_tc<128, false, true>(ah, al, bh, bl, nullptr, C, M, N, K, st, nullptr, nullptr, 1, 0, out_scale, run_flag);
 }
 
 // Block-diagonal Gram matrix of a batch of graphs: for graph i with rows [nptr[i], nptr[i+1]) the ng x ng block
@@ -635,19 +546,19 @@ int gram_blockdiag_tc(const float* X, int N, int K, const int* graph_nptr, const
     const size_t plane16 = (((size_t)N * K * sizeof(__half)) + 255) & ~(size_t)255;
     __half *hi16 = (__half*)w, *lo16 = (__half*)(w + plane16);
     float* out_scale = (float*)(w + 2 * plane16);
-    mpn::launch(split_f16_kernel, kNumSMs * 8, 256, 0, st, (const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi16, (uint2*)lo16, out_scale);
+    mpn::launch(split_f16_kernel, kNumSMs * 8, 256, 0, st, (const float4*)X, (long long)N * K / 4, amax_dev, (uint2*)hi16, (uint2*)lo16, out_scale, (const int*)nullptr);
     MPN_LAUNCH_OK();
     CUtensorMap mh16, ml16;
-    MPN_TRY(make_map(&mh16, hi16, N, K, TC_BM, true));
-    MPN_TRY(make_map(&ml16, lo16, N, K, TC_BM, true));
+    MPN_TRY(make_tma_map_2d(&mh16, hi16, N, K, TC_BM, true));
+    MPN_TRY(make_tma_map_2d(&ml16, lo16, N, K, TC_BM, true));
     return launch_tc<128, true, true>(mh16, ml16, mh16, ml16, nullptr, Gbuf, N, N, K, st, graph_nptr, g_off, n_graphs, max_ng, out_scale);
   }
   float *hi = (float*)w, *lo = (float*)(w + plane);
   mpn::launch(split_tf32_kernel, kNumSMs * 8, 256, 0, st, (const float4*)X, (long long)N * K / 4, K, nullptr, nullptr, nullptr, (float4*)hi, (float4*)lo);
   MPN_LAUNCH_OK();
   CUtensorMap mh, ml;
-  MPN_TRY(make_map(&mh, hi, N, K, TC_BM));
-  MPN_TRY(make_map(&ml, lo, N, K, TC_BM));
+  MPN_TRY(make_tma_map_2d(&mh, hi, N, K, TC_BM, false));
+  MPN_TRY(make_tma_map_2d(&ml, lo, N, K, TC_BM, false));
   return launch_tc<128, true>(mh, ml, mh, ml, nullptr, Gbuf, N, N, K, st, graph_nptr, g_off, n_graphs, max_ng);
 }
 

@@ -9,11 +9,6 @@ namespace mpn {
 static thread_local char g_err[512] = "";
 unsigned long long g_kernel_launches = 0;
 int g_pdl_launch = 1;
-static int fused_distance_from_env() {
-  const char* e = getenv("MPN_FUSED_DISTANCE");
-  return e != nullptr && e[0] == '1';
-}
-int g_fused_distance = fused_distance_from_env();
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -288,17 +283,13 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr, int32_t n
   MPN_LAUNCH_OK();
   mpn::launch(task_fill, min(kNumSMs * 8, div_up(g->n_nodes, 256)), 256, 0, st, g->taskptr, g->n_nodes, g->max_tasks, g->task_row);
   MPN_LAUNCH_OK();
+  g->layout_hint = MPN_LAYOUT_ONE_GAP;         // every row: all nodes but its own camera's range
   return MPN_OK;
 }
 
 int mpn_abi_version(void) { return MPN_B200_ABI_VERSION; }
 const char* mpn_last_error(void) { return mpn::g_err; }
 uint64_t mpn_kernel_launches(void) { return mpn::g_kernel_launches; }
-
-int mpn_set_fused_distance(int enable) {
-  if (enable >= 0) mpn::g_fused_distance = enable != 0;
-  return mpn::g_fused_distance ? 2 : 1;
-}
 
 int mpn_set_pdl(int enable) {
   if (enable >= 0) mpn::g_pdl_launch = enable != 0;

@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared between the translation units of libmpn_b200.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -12,25 +13,37 @@ constexpr float PAIRWISE_EPS = 1e-6f;
 constexpr float COSINE_EPS = 1e-8f;
 constexpr float REFINE_FRACTION = 0.25f;
 
-// EXPERIMENTAL (mpn_set_fused_distance): the distance epilogue inside the Gram GEMM.  For graphs whose rows are "all columns
-// but one contiguous gap" (dense cross-camera graphs: the gap is the node's own camera) the edge id of the ordered pair
-// (i, j) is closed-form, e = rowptr[i] + j - (j past the gap ? gap length : 0), so the epilogue warps turn the accumulator
-// straight into edge_attr rows: no Gram matrix in HBM, no gather pass.  Whether a graph has that shape is decided on the
-// device (gap_table_kernel verifies every row and raises *not_one_gap otherwise): the kernel then falls back to storing the
-// Gram block, and the gather kernel that follows — skipped when the flag is clear — does the work as before.
-struct EfEpilogue {
-  const float4* st;        // [n_cols] per-node statistics of the centred rows (center_rows_kernel), global node ids
-  const int* rowptr;       // [n_rows+1] of the graph (local rows)
-  const int2* gap;         // [n_rows] (first column of the gap, length of the gap) of each local row, global column ids
-  const int* not_one_gap;  // device flag: 0 = every row has the one-gap shape (fused epilogue), else store the Gram block
-  float2* edge_attr;       // [E]
-  int* refine_list;
-  int* refine_count;
-  int row_local0;          // local row / global node id of row 0 of the A block
-  int row_global0;
-  int D;
+// gemm_tc.cu: 2-D tiled tensor map over a row-major [rows, K] plane (fp32: 32-element boxes, fp16: 64-element boxes = 128 bytes)
+int make_tma_map_2d(CUtensorMap* map, const void* base, int rows, int K, int box_rows, bool f16);
+
+// gram_ef.cu: edge features of a dense cross-camera graph in the epilogue of the Gram GEMM (every kernel is a no-op when
+// *not_one_gap != 0).  partials: optional [n_partial_rows][MPN_SUMS_DOUBLES] block partial rows of the first encoder BatchNorm's
+// moment sums (columns 0..4 = sum a, b, aa, ab, bb over the edges that were NOT sent to the refine list).
+struct GeWorkspace {
+  uint16_t *hi, *lo;          // [n_cols, D] fp16 planes of the centred, per-row scaled features
+  float4* rec;                // [n_cols]
+  float* scale_inv;           // [n_cols]
+  int *tiles, *n_tiles;
+  size_t total;
 };
-struct EfNone {};
+int ge_workspace_layout(int n_cols, int M, int D, GeWorkspace* L, void* ws, size_t ws_bytes);
+bool gram_ef_shape_ok(int M, int N, int D);
+// column means of x [n, D] (fp64 partial sums, fixed order): part [ge_col_mean_splits()][D] doubles, *ticket zeroed once
+int ge_col_mean_splits();
+int ge_col_mean(const float* x, int n, int D, double* part, unsigned int* ticket, float* mu, cudaStream_t st);
+// fills gap / *not_one_gap (zeroed by the caller) for the rows of g, then runs the fused kernels
+int gram_ef_run(const float* x, const float* mu, const mpn_graph* g, int D, int2* gap, int* not_one_gap, float2* edge_attr,
+                int* refine_list, int* refine_count, double* partials, int* n_partial_rows, const GeWorkspace& L, cudaStream_t st);
+
+// edge_features.cu
+struct EfMoments {                 // in: partials [>= kNumSMs][MPN_SUMS_DOUBLES] and fixed_sums [5], both zeroed by the caller
+  double* partials;
+  unsigned long long* fixed_sums;
+  const int* handled_flag;         // out: device flag, 0 = features AND moments came from the fused kernel (nullptr: gather path)
+  int known_fused;                 // out: 1 = the host already knows the fused kernel ran (the graph's layout hint)
+};
+int edge_features_impl(const mpn_graph* g, const float* x, int32_t D, float* edge_attr, int use_tc, void* ws, size_t ws_bytes,
+                       cudaStream_t st, EfMoments* moments);
 
 // gemm_simt.cu
 int gemm_nt_simt(const float* A, const float* B, const float* bias, const float* a_scale, const float* a_shift,
@@ -46,9 +59,9 @@ int gemm_nt_tc(const float* A, const float* B, const float* bias, float* C, int 
 int split_tf32(const float* x, long long n, float* hi, float* lo, cudaStream_t st);
 // Gram block of the row block [a_row0, a_row0+M) of X [N,K] against all of X: 3xFP16 planes scaled by max|X| (amax_dev: float
 // bits on the device) when K % 8 == 0, else / when amax_dev is NULL the TF32 path of gemm_nt_tc
+// run_flag (optional, device): the launches return at once when *run_flag == 0
 int gram_nt_tc(const float* X, int a_row0, float* C, int M, int N, int K, const float* amax_dev, void* workspace, size_t workspace_bytes,
-               cudaStream_t st, const EfEpilogue* ef = nullptr);   // ef: fused distance epilogue (fp16 planes only; C = its fallback)
-bool gram_ef_supported(int M, int N, int K, const float* amax_dev);
+               cudaStream_t st, const int* run_flag = nullptr);
 bool gemm_tc_supported(int M, int N, int K);
 // 3xFP16 variant for the node encoder: A is split here into fp16 planes (fused BatchNorm+ReLU; plane scale from a_amax_host, or
 // measured on the device when a_amax_host <= 0), B planes (b_hi16/b_lo16, scaled by b_scale) are cached by the caller

@@ -153,6 +153,8 @@ struct FinArgs {
   unsigned int* counter;      // != nullptr: fuse into the producing kernel's last block
   double* n_total_dev;        // != nullptr: total edge count lives on the device (exchanged with the first all-reduce)
   double local_edges;         // this rank's edge count (sharded runs)
+  const unsigned long long* fixed;   // ENC0, optional: 2^40 fixed-point sums of the edges the fused edge-feature kernel left to the
+                              // refine pass (gram_ef.cu / edge_features.cu), added to columns 0..4
   int re_e;                   // reattach_initial_edges: 0 off, 1 on (y of the current step is recomputed later: keep the folded
                               // step-1 weights), 2 on and y stored (switch to the split weights after the first edge update)
 };
@@ -164,44 +166,42 @@ __device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, i
   const float* small = f.small;
   const int k = threadIdx.x;
   if (do_reduce) {
-    // one warp per column: lanes stride over the partial rows in a fixed pattern, then a fixed shuffle tree
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_partials = f.n_partials, n_partials2 = f.n_partials2;
-    const double* partials = f.partials;
-    const double* partials2 = f.partials2;
-    // The reduction is the serial tail of the sweep's last block.  ENC/EDGE stages have 8 live columns: one per warp.  The NODE
-    // stage has 74: a warp sums 4 columns per pass (4 independent load streams) instead of one.
-    if (stage != MPN_STAGE_NODE) {
-      for (int col = warp; col < SUMS; col += (int)(blockDim.x >> 5)) {
-        double s = 0.0;
-        if (col < 8)
-          for (int p = lane; p < n_partials; p += 32) s += __ldcg(partials + (size_t)p * SUMS + col);
-        s = warp_sum(s);
-        if (lane == 0) sums[col] = s;
+    // The reduction is the serial tail of the sweep's last block: it has to be short.  A thread owns a PAIR of adjacent live columns
+    // (one 16-byte L2 load per partial row) and every `groups`-th row, four loads in flight; the row groups are then added through
+    // shared memory in group order.  Fixed pattern => bit-reproducible.  Live columns: 8 (ENC / EDGE stages), 74 (NODE stage).
+    __shared__ double red[512];
+    const int ncols = (stage == MPN_STAGE_NODE) ? 74 : 8;
+    const int pairs = ncols >> 1;
+    int groups = (int)blockDim.x / pairs;
+    if (groups * ncols > 512) groups = 512 / ncols;
+    const int n_rows = f.n_partials;
+    if (k < groups * pairs) {
+      const int cp = k % pairs, gi = k / pairs;
+      const double* base = f.partials + 2 * cp;
+      double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
+      int p = gi;
+      for (; p + 3 * groups < n_rows; p += 4 * groups) {
+        const double2 v0 = __ldcg(reinterpret_cast<const double2*>(base + (size_t)p * SUMS));
+        const double2 v1 = __ldcg(reinterpret_cast<const double2*>(base + (size_t)(p + groups) * SUMS));
+        const double2 v2 = __ldcg(reinterpret_cast<const double2*>(base + (size_t)(p + 2 * groups) * SUMS));
+        const double2 v3 = __ldcg(reinterpret_cast<const double2*>(base + (size_t)(p + 3 * groups) * SUMS));
+        a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y; a2.x += v2.x; a2.y += v2.y; a3.x += v3.x; a3.y += v3.y;
       }
-    } else {
-      constexpr int CG = 4;
-      constexpr int n_live = 74;
-      for (int col0 = warp * CG; col0 < SUMS; col0 += (int)(blockDim.x >> 5) * CG) {
-        double acc[CG];
-#pragma unroll
-        for (int j = 0; j < CG; ++j) acc[j] = 0.0;
-        if (col0 < n_live) {
-          const bool second = col0 < 64;                 // CG divides 64: a group never straddles the split
-          const double* src = second ? partials2 : partials;
-          const int n = second ? n_partials2 : n_partials;
-          for (int p = lane; p < n; p += 32) {
-#pragma unroll
-            for (int j = 0; j < CG; ++j)
-              if (col0 + j < n_live) acc[j] += __ldcg(src + (size_t)p * SUMS + col0 + j);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < CG; ++j) {
-          const double v = warp_sum(acc[j]);
-          if (lane == 0 && col0 + j < SUMS) sums[col0 + j] = v;
-        }
+      for (; p < n_rows; p += groups) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(base + (size_t)p * SUMS));
+        a0.x += v.x; a0.y += v.y;
       }
+      red[gi * ncols + 2 * cp] = (a0.x + a1.x) + (a2.x + a3.x);
+      red[gi * ncols + 2 * cp + 1] = (a0.y + a1.y) + (a2.y + a3.y);
+    }
+    __syncthreads();
+    if (k < SUMS) {
+      double t = 0.0;
+      if (k < ncols)
+        for (int gi = 0; gi < groups; ++gi) t += red[gi * ncols + k];
+      if (stage == MPN_STAGE_ENC0 && f.fixed != nullptr && k < 5)
+        t += (double)(long long)__ldcg(f.fixed + k) * (1.0 / 1099511627776.0);
+      sums[k] = t;
     }
   }
   __syncthreads();
@@ -370,8 +370,10 @@ template <int STAGE>
 __global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_kernel(const float2* __restrict__ edge_attr, long long E,
                                                                     const float* __restrict__ consts,
                                                                     const float* __restrict__ small,
-                                                                    double* __restrict__ partials, const FinArgs fin) {
+                                                                    double* __restrict__ partials, const FinArgs fin,
+                                                                    const int* __restrict__ run_flag) {
   pdl_wait();
+  if (run_flag != nullptr && *run_flag == 0) return;       // the fused edge-feature kernel has taken these sums already
   __shared__ EdgeConsts sc;
   __shared__ double red[(SWEEP_THREADS / 32) * 8];
   __shared__ float w2raw[20];
@@ -383,6 +385,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_kernel(const float2
   }
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   constexpr int U = 4;                                  // independent loads in flight per thread
+  // Sums run in fp32 over RUN x U edges of this thread, then join the fp64 accumulators: the fp32 -> fp64 conversions and the
+  // double-precision adds per edge were what bounded this sweep (8 of each per edge), not the 8 B/edge it reads.  A run of 32
+  // terms of similar size loses ~1e-7 relative with random sign; over E / 32 runs the totals keep ~1e-9.
+  constexpr int RUN = 8;
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int in_run = 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; e0 < E; e0 += stride * U) {
     float2 eav[U];
@@ -398,17 +406,23 @@ __global__ void __launch_bounds__(SWEEP_THREADS) enc_moments_kernel(const float2
       if (!ok[j]) continue;
       const float2 ea = eav[j];
       if (STAGE == 0) {
-        const double a = ea.x, b = ea.y;
-        acc[0] += a; acc[1] += b; acc[2] += a * a; acc[3] += a * b; acc[4] += b * b;
+        f[0] += ea.x; f[1] += ea.y; f[2] = fmaf(ea.x, ea.x, f[2]); f[3] = fmaf(ea.x, ea.y, f[3]); f[4] = fmaf(ea.y, ea.y, f[4]);
       } else {
         float a1[4], u[4];
         enc_layer1(sc, ea, a1);
         enc_layer2_pre(w2raw, w2raw + 16, a1, u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const double d = u[k]; acc[k] += d; acc[4 + k] += d * d; }
+        for (int k = 0; k < 4; ++k) { f[k] += u[k]; f[4 + k] = fmaf(u[k], u[k], f[4 + k]); }
       }
     }
+    if (++in_run == RUN) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc[k] += (double)f[k]; f[k] = 0.f; }
+      in_run = 0;
+    }
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] += (double)f[k];
   block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
   finalize_in_last_block(fin);
 }
@@ -482,6 +496,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mp
       for (int k = 0; k < 8; ++k) acc[k] = 0.0;
     }
     const float4 ps = Ps[tr.row];
+    float ft[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int base = tr.beg; base < tr.end; base += 32 * U) {
       EdgeLoad<U> L;
       load_edges<U, SRC == 0 || RE_E, true, SRC == 1>(L, g, base, tr.end, lane, edge_attr, Pd, ybuf);
@@ -506,10 +521,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) edge_moments_kernel(const mp
         if (L.ok[j]) {
           if (WRITE_Y) ybuf[L.e[j]] = make_float4(y[0], y[1], y[2], y[3]);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { const double d = y[k]; acc[k] += d; acc[4 + k] += d * d; }
+          for (int k = 0; k < 4; ++k) { ft[k] += y[k]; ft[4 + k] = fmaf(y[k], y[k], ft[4 + k]); }
         }
       }
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += (double)ft[k];      // one task (<= chunk / 32 edges per lane) in fp32, the running sums in fp64
     if (BATCHED) {                                         // per-task partial, reduced per graph in fixed task order
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -1196,6 +1213,7 @@ __global__ void __launch_bounds__(128) graph_finalize_kernel(int stage, const mp
   f.counter = nullptr;
   f.n_total_dev = nullptr;
   f.local_edges = 0.0;
+  f.fixed = nullptr;
   f.re_e = re_e;
   finalize_body(f, 0, 1);
 }
@@ -1526,6 +1544,7 @@ struct mpn_fwd_plan {
   float *h_full, *h0_full, *Ps, *Pd, *A, *consts, *s1_task, *msg_task, *ybuf;
   double *partials, *partials2, *sums;
   unsigned int* fin_counter;
+  unsigned long long* fix_sums;  // [8] fixed-point moment sums of the refined edge features (fused K1)
   unsigned int* col_counter;   // [max_dim/32 + 1] ticket counters of the column-statistics tiles
   int fuse_fin;               // single-GPU: the last block of each moment sweep folds the constants itself
   int n_graphs;               // > 1: batched small graphs, BatchNorm statistics per graph
@@ -1582,6 +1601,7 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.partials2 = nullptr;                 // (the per-node moment part now lives in the sweep's own partial rows)
   p.sums = a.take<double>(G * SUMS);
   p.fin_counter = a.take<unsigned int>(1);
+  p.fix_sums = a.take<unsigned long long>(8);
   p.n_total_dev = a.take<double>(1);
   p.col_counter = a.take<unsigned int>((size_t)(max_dim > 0 ? max_dim : 1) / 32 + 1);
   p.ybuf = stores_y(p) ? a.take<float>((size_t)g.n_edges * 4) : nullptr;
@@ -1664,6 +1684,7 @@ static FinArgs make_fin(const mpn_fwd_plan* p, int stage, bool fused) {
   f.counter = fused ? p->fin_counter : nullptr;
   f.n_total_dev = p->n_total_on_device ? p->n_total_dev : nullptr;
   f.local_edges = (double)p->g.n_edges;
+  f.fixed = nullptr;
   f.re_e = p->w.reattach_edges ? (stores_y(*p) ? 2 : 1) : 0;
   return f;
 }
@@ -1838,10 +1859,12 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
     case MPN_STAGE_ENC0:
       MPN_CUDA_OK(cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st));
       MPN_CUDA_OK(cudaMemsetAsync(p->fin_counter, 0, sizeof(unsigned int), st));
-      mpn::launch(enc_moments_kernel<0>, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused));
+      mpn::launch(enc_moments_kernel<0>, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused),
+                  (const int*)nullptr);
       break;
     case MPN_STAGE_ENC1:
-      mpn::launch(enc_moments_kernel<1>, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused));
+      mpn::launch(enc_moments_kernel<1>, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused),
+                  (const int*)nullptr);
       break;
     case MPN_STAGE_EDGE:
       if (step == 1) {
@@ -1966,8 +1989,39 @@ static int forward_impl(const mpn_graph* g, const mpn_weights* w, const float* x
     const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
     STEP_TRY(mpn_plan_node_encoder(p, x, fork ? ss->stream : st));
     if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
-    if (ef_ws != nullptr) STEP_TRY(mpn_edge_features(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st));
-    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
+    bool enc0_done = false;
+    if (ef_ws != nullptr && p->n_graphs <= 1) {
+      // K1 with the first encoder BatchNorm's moment sums taken in the GEMM epilogue (dense cross-camera graphs): the ENC0 sweep
+      // over edge_attr is replaced by one finalize block; for a graph whose layout is decided on the device the sweep is
+      // enqueued behind a flag test and returns at once when the fused kernel ran
+      if (cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st) != cudaSuccess ||
+          cudaMemsetAsync(p->fin_counter, 0, sizeof(unsigned int), st) != cudaSuccess ||
+          cudaMemsetAsync(p->fix_sums, 0, sizeof(unsigned long long) * 8, st) != cudaSuccess) { set_error("memset failed"); rc = MPN_ERR_CUDA; goto done; }
+      EfMoments mom;
+      mom.partials = p->partials; mom.fixed_sums = p->fix_sums; mom.handled_flag = nullptr; mom.known_fused = 0;
+      STEP_TRY(edge_features_impl(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st, &mom));
+      if (mom.handled_flag != nullptr) {
+        if (!mom.known_fused) {
+          const int flat_grid = (int)min((long long)SWEEP_GRID, (long long)div_up(g->n_edges > 0 ? g->n_edges : 1, SWEEP_THREADS));
+          mpn::launch(enc_moments_kernel<0>, flat_grid, SWEEP_THREADS, 0, st, (const float2*)edge_attr, g->n_edges, p->consts, p->w.small,
+                      p->partials, make_fin(p, MPN_STAGE_ENC0, false), mom.handled_flag);
+          ++mpn::g_kernel_launches;
+        }
+        FinArgs f = make_fin(p, MPN_STAGE_ENC0, false);
+        f.fixed = p->fix_sums;
+        mpn::launch(finalize_kernel, 1, FIN_THREADS, 0, st, f, 1, 1);
+        ++mpn::g_kernel_launches;
+        if (cudaGetLastError() != cudaSuccess) { set_error("ENC0 finalize launch failed"); rc = MPN_ERR_CUDA; goto done; }
+        // the later sweeps reduce SWEEP_GRID partial rows and write only their own grid's: rows the fused kernel may have
+        // written beyond that grid must read zero again (never the case for a dense graph: E / 256 >= tiles)
+        if ((long long)kNumSMs > (long long)div_up(g->n_edges > 0 ? g->n_edges : 1, SWEEP_THREADS) &&
+            cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st) != cudaSuccess) { set_error("memset failed"); rc = MPN_ERR_CUDA; goto done; }
+        enc0_done = true;
+      }
+    } else if (ef_ws != nullptr) {
+      STEP_TRY(mpn_edge_features(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st));
+    }
+    if (!enc0_done) STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
     if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
   }

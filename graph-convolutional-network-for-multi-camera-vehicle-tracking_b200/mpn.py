@@ -54,7 +54,7 @@ class _GraphedForward:
         lib = _lib.lib()
         need = lib.mpn_forward_workspace_bytes(self.g.ref, C.byref(W), L)
         self.ws = torch.empty(need + 4096, dtype=torch.uint8, device=dev)      # private: lives as long as the graph
-        self._last = (None, None, None)
+        self._last = None
         self._stage(g, x, ea)
 
         def launch():
@@ -74,15 +74,17 @@ class _GraphedForward:
                 launch()
 
     def _stage(self, g, x, ea):
-        lg, lx, le = self._last
+        # the graph tables are immutable once built: identity (held through a weak reference) is enough.  The features are
+        # ALWAYS copied: tensor identity + _version would miss writes through .data or by a foreign kernel, and at most 2^21
+        # edges are staged here (a few microseconds)
+        lg = self._last() if self._last is not None else None
         if lg is not g:
             for name in self.tables:
                 getattr(self.g, name).copy_(getattr(g, name), non_blocking=True)
-        if lx is None or lx[0] is not x or lx[1] != x._version:
-            self.x.copy_(x, non_blocking=True)
-        if le is None or le[0] is not ea or le[1] != ea._version:
-            self.ea.copy_(ea, non_blocking=True)
-        self._last = (g, (x, x._version), (ea, ea._version))
+            import weakref
+            self._last = weakref.ref(g)
+        self.x.copy_(x, non_blocking=True)
+        self.ea.copy_(ea, non_blocking=True)
 
     def run(self, g, x, ea):
         self._stage(g, x, ea)
@@ -210,8 +212,10 @@ class MOTMPNet(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def invalidate_weight_cache(self):
-        """Needed only after a Parameter OBJECT is replaced (``module.weight = nn.Parameter(...)``); in-place updates
-        (``load_state_dict``, ``.to()``, ``p.data.copy_``) are detected through the tensors' data pointers and versions."""
+        """The packed weights (and their tensor-core planes) are cached and rebuilt when a parameter's data pointer or version
+        counter changes: ``load_state_dict``, ``.to()``, in-place ops on the Parameter itself.  Call this after anything those
+        two do not see: a Parameter OBJECT replaced (``module.weight = nn.Parameter(...)``), writes through ``p.data`` (``.data``
+        has its own version counter) or by a foreign kernel."""
         self.__dict__.pop("_param_list", None)
         self._packed = None
 
@@ -347,7 +351,8 @@ class MOTMPNet(nn.Module):
         n_out = 1 if L == 0 else n_cls
         fused = bool(self.fuse_decisions) and n_out > 0
         if self.use_cuda_graph and g.n_edges <= self.cuda_graph_max_edges and g.n_edges > 1:
-            key = (dev.index, g.n_nodes, g.n_edges, g.n_graphs, x.shape[1], L, n_cls, bool(self.fuse_decisions), self._packed[0])
+            key = (dev.index, g.n_nodes, g.n_edges, g.n_graphs, g.chunk, g.max_tasks, g.max_graph_nodes, x.shape[1], L, n_cls,
+                   bool(self.fuse_decisions), self._packed[0])
             ent = self._graphs.get(key)
             if ent is None:
                 if len(self._graphs) >= 8:

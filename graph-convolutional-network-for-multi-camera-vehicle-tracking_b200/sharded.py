@@ -267,8 +267,9 @@ class ShardedMPN:
     plus the replicated ``x``; outputs stay sharded (logits of the local edges, h of the local rows).
 
     ``fused=True`` (default): one launch sequence per rank with the collectives inside the kernels over NVLink peer
-    memory (``mpn_forward_sharded``).  If symmetric memory cannot be set up the reason is kept in ``peer_error`` and the
-    NCCL schedule (``sharded_forward``: all-reduce / all-gather between phases) is used instead.
+    memory (``mpn_forward_sharded``).  If symmetric memory cannot be set up the call RAISES (there is no silent change of
+    schedule); ``fused=False`` selects the phase schedule with NCCL collectives between the phases (``sharded_forward``) — the
+    reference schedule the fused kernels are tested against.  ``path`` names the one in use.
     """
 
     def __init__(self, model, group=None, fused: bool = True, shard_node_encoder: bool = True):
@@ -277,7 +278,6 @@ class ShardedMPN:
         self.comm = TorchComm(group)
         self.fused = fused and self.comm.world > 1
         self.peers = None
-        self.peer_error = None
         self._totals = {}
 
     def _total_edges(self, g, dev):
@@ -290,16 +290,19 @@ class ShardedMPN:
             self._totals[key] = (g, int(tot.item()))
         return self._totals[key][1]
 
+    @property
+    def path(self) -> str:
+        return "fused_peer_memory" if self.fused else "nccl_phase_schedule"
+
     def _peer_memory(self, n_cols, dev):
         if self.peers is not None and self.peers.n_cols == n_cols:
             return self.peers
-        if self.peer_error is not None:
-            return None
         try:
             self.peers = PeerMemory(n_cols, dev, self.comm.group)
-        except Exception as e:                          # noqa: BLE001 - any failure -> NCCL schedule, reason recorded
-            self.peer_error = "%s: %s" % (type(e).__name__, e)
+        except Exception as e:                          # noqa: BLE001
             self.peers = None
+            raise RuntimeError("ShardedMPN(fused=True): the NVLink peer-memory exchange buffers could not be set up (%s: %s); "
+                               "pass fused=False for the NCCL phase schedule" % (type(e).__name__, e)) from e
         return self.peers
 
     def post_processing(self, num_cameras, graph, pred, prob1, CONFIG, numbering='reference'):

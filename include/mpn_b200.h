@@ -50,13 +50,6 @@ uint64_t mpn_kernel_launches(void);
  * kernel n+1 overlaps the tail of kernel n (every kernel starts with griddepcontrol.wait, so results are bit-identical).
  * enable > 0 / == 0 switches it on / off (A/B measurements), enable < 0 only queries.  Returns 1 = off, 2 = on. */
 int mpn_set_pdl(int enable);
-/* EXPERIMENTAL (off by default, not yet validated on hardware): form the edge features (inference.py:453-456) in the epilogue
- * of the Gram GEMM — TMEM accumulator -> distance / cosine -> edge_attr, no Gram matrix in HBM and no gather pass — for graphs
- * whose every row is "all columns but one contiguous gap" (dense cross-camera graphs: the gap is the node's own camera), which
- * is checked on the device in the same call; any other graph takes the Gram + gather path inside the same launches.
- * enable > 0 / == 0 switches it on / off, < 0 only queries; returns 1 = off, 2 = on (initial state: on iff the environment has
- * MPN_FUSED_DISTANCE=1). */
-int mpn_set_fused_distance(int enable);
 /* 0 if device `dev` exists and is sm_100; error otherwise.  Never falls back to CPU. */
 int mpn_check_device(int dev);
 
@@ -75,7 +68,9 @@ typedef struct mpn_graph {
   int32_t chunk;            /* edges per task (power of two, 32..4096) */
   int64_t n_edges;
   int32_t max_tasks;        /* capacity of task_row / task_beg */
-  int32_t reserved;
+  int32_t layout_hint;      /* MPN_LAYOUT_UNKNOWN, or MPN_LAYOUT_ONE_GAP when the builder of the tables vouches that every row lists
+                             * all columns but one contiguous gap (mpn_graph_build_cross_camera sets it): mpn_edge_features then
+                             * skips the launches of the Gram + gather path, which an unknown layout enqueues as the alternative */
   int32_t* rowptr;          /* dev [n_nodes+1]  */
   int32_t* col;             /* dev [n_edges]    global column ids */
   int32_t* taskptr;         /* dev [n_nodes+1]  first task of each row */
@@ -90,6 +85,7 @@ typedef struct mpn_graph {
   int32_t* graph_nptr;      /* dev [n_graphs+1]  first node of each graph         */
 } mpn_graph;
 
+enum { MPN_LAYOUT_UNKNOWN = 0, MPN_LAYOUT_ONE_GAP = 1 };
 /* Fills the tables of `g` (pointers and sizes pre-set by the caller).  Synchronises (reads the sorted flag). */
 int mpn_graph_build(mpn_graph* g, const int64_t* edge_index_dev, void* stream);
 /* Same from int32 row/col arrays already split (used for row-block shards). */
@@ -117,10 +113,18 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr_host, int3
 /* ------------------------------------------------------------------------------------------------
  * Edge features (K1).  Replaces inference.py:453-456:
  *   edge_attr[e] = [ ||x_r - x_c + 1e-6||_2 , 1 - cos(x_r, x_c) ]
- * computed from the Gram matrix X X^T (fp32-accurate: 3xTF32 tensor-core GEMM, or the fp32 SIMT GEMM
- * when `use_tensor_cores` is 0) with the distance epilogue applied per edge; the [E,D] gathers of the
- * reference are never materialised.  x: dev [n_cols, D] fp32 row-major.  edge_attr: dev [E,2].
+ * computed from the Gram matrix X X^T of the centred features (fp32-accurate: three fp16-plane products on the tensor
+ * cores, or the fp32 SIMT GEMM when `use_tensor_cores` is 0); the [E,D] gathers of the reference are never materialised.
+ * Dense cross-camera graphs (every row = all columns but one contiguous gap, inference.py:407-413; checked on the device
+ * unless g->layout_hint says so) with D % 64 == 0: ONE persistent tcgen05 kernel whose epilogue turns the TMEM accumulator
+ * straight into edge_attr rows (csrc/gram_ef.cu) — no Gram matrix in HBM, no gather pass.  Any other graph: Gram block in
+ * HBM + a gather pass.  x: dev [n_cols, D] fp32 row-major.  edge_attr: dev [E,2].
  * ---------------------------------------------------------------------------------------------- */
+/* Measurement hook (bench.py): with enable != 0 every later mpn_edge_features call records a CUDA event on its stream before and
+ * after the Gram GEMM + distance epilogue launch (csrc/gram_ef.cu); mpn_profile_gram_ms waits for the second event and returns
+ * the duration of the last such launch in milliseconds (-1 if none).  Off by default: the events break the launch overlap. */
+int mpn_profile_gram(int enable);
+float mpn_profile_gram_ms(void);
 size_t mpn_edge_features_workspace_bytes(const mpn_graph* g, int32_t D);
 int mpn_edge_features(const mpn_graph* g, const float* x_dev, int32_t D, float* edge_attr_dev,
                       int use_tensor_cores, void* workspace_dev, size_t workspace_bytes, void* stream);

@@ -157,7 +157,7 @@ def mlp_forward(sd, prefix: str, layout, x: torch.Tensor) -> torch.Tensor:
 
 def scatter_add_rows(src: torch.Tensor, index: torch.Tensor, dim_size: int) -> torch.Tensor:
     """torch_scatter.scatter_add(src, index, dim=0, dim_size) (models/mpn.py:202): sequential on CPU."""
-    return torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype).index_add_(0, index, src)
+    return torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device).index_add_(0, index, src)
 
 
 def aggregate_rows(src: torch.Tensor, index: torch.Tensor, dim_size: int, how: str) -> torch.Tensor:
@@ -167,10 +167,10 @@ def aggregate_rows(src: torch.Tensor, index: torch.Tensor, dim_size: int, how: s
     if how == "sum":
         return scatter_add_rows(src, index, dim_size)
     if how == "mean":
-        cnt = torch.zeros(dim_size, dtype=src.dtype).index_add_(0, index, torch.ones(index.numel(), dtype=src.dtype))
+        cnt = torch.zeros(dim_size, dtype=src.dtype, device=src.device).index_add_(0, index, torch.ones(index.numel(), dtype=src.dtype, device=src.device))
         return scatter_add_rows(src, index, dim_size) / cnt.clamp_min(1).unsqueeze(1)
     if how == "max":
-        out = torch.full((dim_size,) + tuple(src.shape[1:]), float("-inf"), dtype=src.dtype)
+        out = torch.full((dim_size,) + tuple(src.shape[1:]), float("-inf"), dtype=src.dtype, device=src.device)
         out = out.scatter_reduce(0, index.unsqueeze(1).expand_as(src), src, reduce="amax", include_self=True)
         return torch.where(torch.isinf(out), torch.zeros_like(out), out)
     raise ValueError(how)
@@ -178,8 +178,11 @@ def aggregate_rows(src: torch.Tensor, index: torch.Tensor, dim_size: int, how: s
 
 def mpn_forward(sd, model_params: dict, arch: str, x: torch.Tensor, edge_index: torch.Tensor,
                 edge_attr: torch.Tensor, dtype=torch.float32):
-    """MOTMPNet.forward (models/mpn.py:250-299).  Returns (list of [E,2] logits, h [N,node_out])."""
+    """MOTMPNet.forward (models/mpn.py:250-299).  Returns (list of [E,2] logits, h [N,node_out]).  Plain torch ops: runs on
+    whatever device ``x`` lives on (the fp64 checks at benchmark size run it on the GPU; ``sd`` is moved along)."""
     lay = model_layouts(model_params, arch)
+    if any(v.device != x.device for v in sd.values()):
+        sd = {k: v.to(x.device) for k, v in sd.items()}
     x = x.to(dtype)
     edge_attr = edge_attr.to(dtype)
     row, col = edge_index[0].long(), edge_index[1].long()
@@ -221,7 +224,7 @@ def edge_features(x: torch.Tensor, edge_index: torch.Tensor, chunk: int = 1 << 1
     x = x.to(dtype)
     row, col = edge_index[0].long(), edge_index[1].long()
     E = row.numel()
-    out = torch.empty(E, 2, dtype=dtype)
+    out = torch.empty(E, 2, dtype=dtype, device=x.device)
     for s in range(0, E, chunk):
         a, b = x[row[s:s + chunk]], x[col[s:s + chunk]]
         out[s:s + chunk, 0] = (a - b + PAIRWISE_EPS).norm(dim=1)

@@ -47,8 +47,8 @@ def check_case(rank, world, dev, L, n_cls, N, C, modes, chunk=None, reattach=Fal
         for _rep in range(3):
             out, h_l, pred, prob1 = sh.forward(xd, ei_l, ea[lo:hi].to(dev), blocks, fuse_decisions=True, graph=g)
         torch.cuda.synchronize()
-        if fused and sh.peer_error is not None and rank == 0:
-            print("fused path unavailable:", sh.peer_error)
+        if fused and sh.path != "fused_peer_memory" and rank == 0:
+            print("fused path unavailable")
         mode = "fused" if (fused and sh.peers is not None) else "nccl"
         modes.add(mode)
         results[mode] = out["classified_edges"][-1].clone()

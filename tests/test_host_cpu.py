@@ -31,13 +31,6 @@ def test_pdl_switch_defaults_on():
     assert lib.mpn_set_pdl(0) == 1 and lib.mpn_set_pdl(-1) == 1 and lib.mpn_set_pdl(1) == 2
 
 
-def test_fused_distance_switch_defaults_off():
-    lib = m._lib.lib()
-    if os.environ.get("MPN_FUSED_DISTANCE") != "1":
-        assert lib.mpn_set_fused_distance(-1) == 1             # 1 = off, 2 = on
-    assert lib.mpn_set_fused_distance(1) == 2 and lib.mpn_set_fused_distance(0) == 1
-
-
 def test_no_device_fails_loudly():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

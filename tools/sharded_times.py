@@ -26,7 +26,7 @@ for fused in (True, False):
         a.record(); sh.forward(x, ei, ea, blocks, fuse_decisions=True, graph=g); b.record(); b.synchronize()
         hs.append(1e3 * (time.perf_counter() - t0)); ts.append(a.elapsed_time(b))
     if rank == 0:
-        print("fused=%s peers=%s err=%s" % (fused, sh.peers is not None, sh.peer_error))
+        print("fused=%s peers=%s path=%s" % (fused, sh.peers is not None, sh.path))
         print("  device ms:", " ".join("%.2f" % t for t in ts))
         print("  host   ms:", " ".join("%.2f" % t for t in hs))
 tt = torch.tensor([ei.shape[1]], dtype=torch.float64, device=dev); dist.all_reduce(tt); TOT = int(tt.item())
