@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libmpn_b200.so")
 MPN_OK, MPN_ERR_INVALID, MPN_ERR_CUDA, MPN_ERR_UNSORTED, MPN_ERR_WORKSPACE, MPN_ERR_NO_DEVICE = range(6)
 MPN_DE, MPN_DH, MPN_MAX_NODE_LAYERS = 4, 32, 8
 MPN_SUMS_DOUBLES = 96
-ABI_VERSION = 4             # MPN_B200_ABI_VERSION of include/mpn_b200.h (bumped when a struct or a signature changes)
+ABI_VERSION = 5             # MPN_B200_ABI_VERSION of include/mpn_b200.h (bumped when a struct or a signature changes)
 STAGE_ENC0, STAGE_ENC1, STAGE_EDGE, STAGE_NODE, STAGE_APPLY = range(5)
 POST_CUT, POST_PRUNE, POST_SPLIT = 1, 2, 4
 
@@ -129,6 +129,8 @@ _PROTOS = {
     "mpn_compact_active": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_clear_inactive": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mpn_labels_reference": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
     "mpn_labels_reference_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "mpn_split_exact_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p]),

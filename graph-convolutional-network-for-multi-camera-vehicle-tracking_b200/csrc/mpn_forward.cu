@@ -7,6 +7,7 @@
 //                h' = segment_sum_row(relu(BN(z)))      BN over all E edges        (models/mpn.py:99,202)
 // BatchNorm uses batch statistics, so every BN is a global reduction followed by a second sweep.
 // Moments are accumulated in fp64, block partials are reduced in a fixed order (deterministic).
+#include <mutex>
 #include <new>
 #include <stdlib.h>
 
@@ -1955,8 +1956,10 @@ struct SideStream {
 static SideStream* side_stream() {
   static SideStream table[64];
   static int state[64];                 // 0 = not tried, 1 = ok, -1 = failed
+  static std::mutex init_lock;          // (the library is used by one host thread per device; creation is guarded all the same)
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> hold(init_lock);
   if (state[dev] == 0) {
     SideStream& s = table[dev];
     const bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&

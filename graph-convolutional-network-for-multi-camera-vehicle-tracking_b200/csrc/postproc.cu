@@ -256,30 +256,44 @@ __global__ void prune_remove_kernel(int N, const unsigned long long* __restrict_
   }
 }
 
+__global__ void prune_reset_kernel(int N, int* __restrict__ fo, int* __restrict__ fi, unsigned long long* __restrict__ mo,
+                                   unsigned long long* __restrict__ mi) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    fo[n] = 0; fi[n] = 0; mo[n] = ~0ull; mi[n] = ~0ull;
+  }
+}
+
+// Rounds are enqueued PRUNE_BATCH at a time with one flag word each and the host reads the flags once per batch: a round without
+// a violating node removes nothing, so the rounds enqueued past the fixed point are no-ops (the violation flags of a batch are a
+// prefix of ones).  One host round trip per 8 rounds instead of one per round (the smoke graph needs 87 rounds).
+constexpr int PRUNE_BATCH = 8;
 static int prune_stage(PostCtx& c, uint8_t* act, const float* prob, int pstride, int num_cameras, int* changed, int* rounds) {
   const int A = c.n_active, N = c.g.n_nodes;
   *changed = 0;
   *rounds = 0;
   if (A == 0) return MPN_OK;
+  int* flags = c.counters + 8;                          // PRUNE_BATCH flag words
   for (;;) {
-    MPN_CUDA_OK(cudaMemsetAsync(c.fo, 0, sizeof(int) * N, c.st));
-    MPN_CUDA_OK(cudaMemsetAsync(c.fi, 0, sizeof(int) * N, c.st));
-    MPN_CUDA_OK(cudaMemsetAsync(c.mo, 0xFF, sizeof(unsigned long long) * N, c.st));
-    MPN_CUDA_OK(cudaMemsetAsync(c.mi, 0xFF, sizeof(unsigned long long) * N, c.st));
-    MPN_CUDA_OK(cudaMemsetAsync(c.counters + 1, 0, sizeof(int), c.st));
-    flow_count_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, c.fo, c.fi);
-    MPN_LAUNCH_OK();
-    prune_pick_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, prob, pstride, num_cameras - 1, c.fo,
-                                                      c.fi, c.mo, c.mi, c.counters + 1);
-    MPN_LAUNCH_OK();
-    int viol = 0;
-    MPN_CUDA_OK(cudaMemcpyAsync(&viol, c.counters + 1, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(int) * PRUNE_BATCH, c.st));
+    for (int r = 0; r < PRUNE_BATCH; ++r) {
+      prune_reset_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.fo, c.fi, c.mo, c.mi);
+      MPN_LAUNCH_OK();
+      flow_count_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, c.fo, c.fi);
+      MPN_LAUNCH_OK();
+      prune_pick_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, prob, pstride, num_cameras - 1, c.fo,
+                                                        c.fi, c.mo, c.mi, flags + r);
+      MPN_LAUNCH_OK();
+      prune_remove_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.mo, c.mi, act);
+      MPN_LAUNCH_OK();
+    }
+    int viol[PRUNE_BATCH];
+    MPN_CUDA_OK(cudaMemcpyAsync(viol, flags, sizeof(int) * PRUNE_BATCH, cudaMemcpyDeviceToHost, c.st));
     MPN_CUDA_OK(cudaStreamSynchronize(c.st));
-    if (!viol) break;
-    *changed = 1;
-    ++*rounds;
-    prune_remove_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.mo, c.mi, act);
-    MPN_LAUNCH_OK();
+    int n_viol = 0;
+    while (n_viol < PRUNE_BATCH && viol[n_viol]) ++n_viol;
+    *rounds += n_viol;
+    if (n_viol > 0) *changed = 1;
+    if (n_viol < PRUNE_BATCH) break;
   }
   return MPN_OK;
 }
@@ -951,6 +965,129 @@ static void labels_reference(const int* src, const int* dst, long long m, int n_
   *n_comp = (int)k;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Reference label numbering (utils.py:30-52) without a sequential pass over the active edges.
+// networkx emits the SCCs source by source (sources in first-appearance order of the nodes in the active edge list, u before v),
+// each source's DFS in post-order, and a DFS never leaves its weakly connected component.  So
+//   label = rank of (size, first-appearance key of the emitting source, index within that DFS)   among the SCCs with an edge,
+// then the nodes without an active edge in index order.  For an SCC that is alone in its weakly connected component (no
+// one-directional edge to another SCC — every component after CUTTING, almost every component otherwise) the emitting source is
+// its own earliest node: key = min over its nodes of the first-appearance key, index 0 — an atomicMin per active edge on the
+// device.  Only the components that one-directional edges tie together go through the sequential generator (split_exact.cu),
+// restricted to those components.
+// ------------------------------------------------------------------------------------------------
+__global__ void first_appearance_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const int* __restrict__ a_dst,
+                                        const uint8_t* __restrict__ act, unsigned int* __restrict__ fa) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    if (!act[a_eid[i]]) continue;
+    atomicMin(&fa[a_src[i]], 2u * (unsigned int)i);
+    atomicMin(&fa[a_dst[i]], 2u * (unsigned int)i + 1u);
+  }
+}
+__global__ void inter_scc_flag_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const int* __restrict__ a_dst,
+                                      const uint8_t* __restrict__ act, const int* __restrict__ label, const int* __restrict__ wcc,
+                                      int* __restrict__ wccflag, int* __restrict__ count) {
+  int c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
+    if (!act[a_eid[i]]) continue;
+    if (label[a_src[i]] != label[a_dst[i]]) {
+      ++c;
+      if (wcc != nullptr) wccflag[wcc[a_src[i]]] = 1;
+    }
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+__global__ void select_flagged_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const uint8_t* __restrict__ act,
+                                      const int* __restrict__ wcc, const int* __restrict__ wccflag, uint8_t* __restrict__ sel) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x)
+    sel[i] = (act[a_eid[i]] && wccflag[wcc[a_src[i]]]) ? 1 : 0;
+}
+
+void scc_emission_keys_host(const int* src, const int* dst, long long m, int n_nodes, std::vector<int>& node_out,
+                            std::vector<long long>& key_out, std::vector<int>& idx_out, std::vector<int>& size_out);   // split_exact.cu
+
+static int labels_reference_parallel(PostCtx& c, const uint8_t* act, long long* labels_out, int* n_comp_out) {
+  const int A = c.n_active, N = c.g.n_nodes;
+  MPN_TRY(scc_stage(c, act, nullptr));
+  unsigned int* fa = reinterpret_cast<unsigned int*>(c.fo);
+  MPN_CUDA_OK(cudaMemsetAsync(fa, 0xFF, sizeof(unsigned int) * N, c.st));
+  MPN_CUDA_OK(cudaMemsetAsync(c.counters + 7, 0, sizeof(int), c.st));
+  int n_inter = 0;
+  if (A > 0) {
+    first_appearance_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, fa);
+    MPN_LAUNCH_OK();
+    inter_scc_flag_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, c.label, nullptr, nullptr, c.counters + 7);
+    MPN_LAUNCH_OK();
+  }
+  std::vector<int> h_label(N);
+  std::vector<unsigned int> h_fa(N);
+  MPN_CUDA_OK(cudaMemcpyAsync(h_label.data(), c.label, sizeof(int) * N, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaMemcpyAsync(h_fa.data(), fa, sizeof(unsigned int) * N, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaMemcpyAsync(&n_inter, c.counters + 7, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+  // components that one-directional edges tie together: their emission order comes from the sequential generator
+  std::vector<int> cx_node, cx_idx, cx_size;
+  std::vector<long long> cx_key;
+  std::vector<int> pos;
+  if (n_inter > 0) {
+    iota_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.wcc);
+    MPN_LAUNCH_OK();
+    union_all_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, c.wcc);
+    MPN_LAUNCH_OK();
+    flatten_kernel<<<list_grid(N), 256, 0, c.st>>>(N, c.wcc, nullptr);
+    MPN_LAUNCH_OK();
+    MPN_CUDA_OK(cudaMemsetAsync(c.wccflag, 0, sizeof(int) * N, c.st));
+    MPN_CUDA_OK(cudaMemsetAsync(c.counters + 7, 0, sizeof(int), c.st));
+    inter_scc_flag_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, c.a_dst, act, c.label, c.wcc, c.wccflag, c.counters + 7);
+    MPN_LAUNCH_OK();
+    select_flagged_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, act, c.wcc, c.wccflag, c.sel);
+    MPN_LAUNCH_OK();
+    std::vector<int> hs(A), hd(A);
+    std::vector<uint8_t> hsel(A);
+    MPN_CUDA_OK(cudaMemcpyAsync(hs.data(), c.a_src, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaMemcpyAsync(hd.data(), c.a_dst, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaMemcpyAsync(hsel.data(), c.sel, A, cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaStreamSynchronize(c.st));
+    std::vector<int> ss, dd;
+    for (int i = 0; i < A; ++i)
+      if (hsel[i]) { pos.push_back(i); ss.push_back(hs[i]); dd.push_back(hd[i]); }
+    scc_emission_keys_host(ss.data(), dd.data(), (long long)ss.size(), N, cx_node, cx_key, cx_idx, cx_size);
+  }
+  // per SCC (root = smallest node id): size, key, index; then the rank
+  struct Rep { unsigned int size; unsigned int idx; unsigned long long key; int root; };
+  std::vector<unsigned int> size(N, 0u), idx(N, 0u);
+  std::vector<unsigned long long> key(N, ~0ull);
+  for (int n = 0; n < N; ++n) {
+    if (h_fa[n] == 0xFFFFFFFFu) continue;
+    const int r = h_label[n];
+    ++size[r];
+    if ((unsigned long long)h_fa[n] < key[r]) key[r] = h_fa[n];
+  }
+  for (size_t v = 0; v < cx_node.size(); ++v) {
+    const int r = h_label[cx_node[v]];
+    // local key = 2 * (index in the gathered list) + side  ->  2 * (position in the active list) + side
+    key[r] = 2ull * (unsigned long long)pos[(size_t)(cx_key[v] >> 1)] + (unsigned long long)(cx_key[v] & 1);
+    idx[r] = (unsigned int)cx_idx[v];
+    if ((unsigned int)cx_size[v] != size[r]) { set_error("reference numbering: component sizes disagree (device %u, host %d)", size[r], cx_size[v]); return MPN_ERR_INVALID; }
+  }
+  std::vector<Rep> reps;
+  reps.reserve(N / 2 + 1);
+  for (int r = 0; r < N; ++r)
+    if (size[r] > 0) reps.push_back(Rep{size[r], idx[r], key[r], r});
+  std::sort(reps.begin(), reps.end(), [](const Rep& a, const Rep& b) {
+    if (a.size != b.size) return a.size < b.size;
+    if (a.key != b.key) return a.key < b.key;
+    return a.idx < b.idx;
+  });
+  std::vector<int> rank(N, -1);
+  for (size_t i = 0; i < reps.size(); ++i) rank[reps[i].root] = (int)i;
+  long long next = (long long)reps.size();
+  for (int n = 0; n < N; ++n) labels_out[n] = (h_fa[n] != 0xFFFFFFFFu) ? rank[h_label[n]] : next++;
+  if (n_comp_out) *n_comp_out = (int)next;
+  return MPN_OK;
+}
+
 __global__ void clear_inactive_kernel(long long n, const int* __restrict__ eid, const uint8_t* __restrict__ keep,
                                       uint8_t* __restrict__ act) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -1133,6 +1270,18 @@ int mpn_clear_inactive(uint8_t* act, const int32_t* eid, const uint8_t* keep, in
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs * 8, (n + 255) / 256));
   clear_inactive_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, eid, keep, act);
   MPN_LAUNCH_OK();
+  return MPN_OK;
+}
+
+int mpn_labels_reference(const mpn_graph* g, const uint8_t* act, int64_t* labels_out_host, int32_t* n_components, void* ws,
+                         size_t ws_bytes, void* stream) {
+  PostCtx c;
+  MPN_REQUIRE(labels_out_host, "labels_reference: NULL output");
+  MPN_TRY(post_begin(c, g, act, ws, ws_bytes, stream));
+  MPN_REQUIRE((long long)c.n_active < (1ll << 30), "labels_reference: more than 2^30 active edges");
+  int nc = 0;
+  MPN_TRY(labels_reference_parallel(c, act, (long long*)labels_out_host, &nc));
+  if (n_components) *n_components = nc;
   return MPN_OK;
 }
 

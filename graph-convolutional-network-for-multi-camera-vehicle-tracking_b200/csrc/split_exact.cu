@@ -160,20 +160,18 @@ struct SplitExact {
 
 // keep_out[i] = 0 for the edges SPLITTING switches off.  stats_out[4]: dropped values, steps taken on a label that was not the
 // lowest oversized one (utils.py:112 re-reads the integer), clusters examined, 0.
-int split_exact_host_impl(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep,
-                            int64_t* stats_out) {
-  SplitExact S;
+// builds the adjacency of the sub-problem (local node ids in order of first use) and registers every cluster
+static void split_exact_init(SplitExact& S, const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C,
+                             std::vector<int>* global_of_local) {
   S.m = m; S.prob = prob; S.C = C;
-  // local node ids in order of first use (only the nodes of the sub-problem get traversal state)
   std::vector<int> local((size_t)n_nodes, -1);
   S.ls.resize(m); S.ld.resize(m);
   int n = 0;
   for (long long i = 0; i < m; ++i) {
-    if (local[src[i]] < 0) local[src[i]] = n++;
-    if (local[dst[i]] < 0) local[dst[i]] = n++;
+    if (local[src[i]] < 0) { local[src[i]] = n++; if (global_of_local) global_of_local->push_back(src[i]); }
+    if (local[dst[i]] < 0) { local[dst[i]] = n++; if (global_of_local) global_of_local->push_back(dst[i]); }
     S.ls[i] = local[src[i]];
     S.ld[i] = local[dst[i]];
-    keep[i] = 1;
   }
   std::vector<int>().swap(local);
   S.n = n;
@@ -188,16 +186,37 @@ int split_exact_host_impl(const int* src, const int* dst, const float* prob, lon
   S.out_first.assign(S.out_ptr.begin(), S.out_ptr.end() - 1);
   S.in_first.assign(S.in_ptr.begin(), S.in_ptr.end() - 1);
   S.alive.assign(m, 1);
+  S.comp.assign(n, -1); S.wcc.assign(n, -1);
+  S.pre.assign(n, 0); S.low.assign(n, 0); S.it.assign(n, 0); S.mark.assign(n, 0);
+  std::vector<int> all(n);
+  for (int v = 0; v < n; ++v) all[v] = v;
+  S.recompute(all);
+}
+
+// networkx's emission order for a sub-graph that is a union of whole weakly connected components, given as its active edges in
+// edge order: for every node that appears, the key of its strongly connected component = (first-appearance key of the source
+// whose DFS emitted it, in units of 2 * local edge index + side; index within that DFS; size).  Used by the reference label
+// numbering for the components that one-directional edges tie together (postproc.cu).
+void scc_emission_keys_host(const int* src, const int* dst, long long m, int n_nodes, std::vector<int>& node_out,
+                            std::vector<long long>& key_out, std::vector<int>& idx_out, std::vector<int>& size_out) {
+  SplitExact S;
+  node_out.clear();
+  split_exact_init(S, src, dst, nullptr, m, n_nodes, 0x7fffffff, &node_out);
+  key_out.resize(S.n); idx_out.resize(S.n); size_out.resize(S.n);
+  for (int v = 0; v < S.n; ++v) {
+    const SplitExact::Cluster& c = S.clusters[S.comp[v]];
+    key_out[v] = c.src_key; idx_out[v] = c.idx; size_out[v] = c.size;
+  }
+}
+
+int split_exact_host_impl(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep,
+                          int64_t* stats_out) {
+  SplitExact S;
+  for (long long i = 0; i < m; ++i) keep[i] = 1;
+  split_exact_init(S, src, dst, prob, m, n_nodes, C, nullptr);
   S.by_prob.resize(m);
   for (long long i = 0; i < m; ++i) S.by_prob[i] = (int)i;
   std::sort(S.by_prob.begin(), S.by_prob.end(), [&](int a, int b) { return prob[a] < prob[b] || (prob[a] == prob[b] && a < b); });
-  S.comp.assign(n, -1); S.wcc.assign(n, -1);
-  S.pre.assign(n, 0); S.low.assign(n, 0); S.it.assign(n, 0); S.mark.assign(n, 0);
-  {
-    std::vector<int> all(n);
-    for (int v = 0; v < n; ++v) all[v] = v;
-    S.recompute(all);
-  }
   long long steps = 0, off_lowest = 0;
   long long sticky = -1;                          // index (in the order of `big`) of the cluster the reference's inner loop is on
   std::vector<int> affected;

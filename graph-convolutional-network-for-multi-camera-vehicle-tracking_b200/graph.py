@@ -12,11 +12,33 @@ import torch
 from . import _lib
 
 _WORKSPACES = {}
+_SCOPE = []              # workspace_scope() tags (innermost last)
+
+
+class workspace_scope:
+    """``with workspace_scope(tag):`` gives the calls inside their own scratch buffers (keyed by tag).  A captured CUDA graph bakes
+    the addresses of its scratch memory in, so every capture runs under a tag of its own: buffers that another caller could grow
+    (= free) must never end up inside a graph (GraphStream._capture, _GraphedForward)."""
+
+    def __init__(self, tag: str):
+        self.tag = str(tag)
+
+    def __enter__(self):
+        _SCOPE.append(self.tag)
+        return self
+
+    def __exit__(self, *exc):
+        _SCOPE.pop()
+        return False
 
 
 def workspace(kind: str, device: torch.device, nbytes: int) -> torch.Tensor:
-    """Grow-only uint8 scratch buffer per (kind, device); torch owns the memory, the C ABI only borrows it."""
-    key = (kind, device.index)
+    """Grow-only uint8 scratch buffer per (kind[, scope], device); torch owns the memory, the C ABI only borrows it.
+
+    Contract (also in INTEGRATION.md / include/mpn_b200.h): ONE host thread and ONE CUDA stream per device use the library at a
+    time.  The buffers are shared by consecutive calls; growing one frees the old allocation, which is safe only because the
+    caching allocator defers the reuse of a block to the stream that last used it — the caller's single compute stream."""
+    key = (kind if not _SCOPE else kind + "#" + _SCOPE[-1], device.index)
     buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None
@@ -24,6 +46,12 @@ def workspace(kind: str, device: torch.device, nbytes: int) -> torch.Tensor:
         buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
         _WORKSPACES[key] = buf
     return buf
+
+
+def release_scope(tag: str):
+    """Drops the scratch buffers of a scope (a captured graph that used them has been destroyed)."""
+    for key in [k for k in _WORKSPACES if k[0].endswith("#" + str(tag))]:
+        _WORKSPACES.pop(key, None)
 
 
 def current_stream_ptr(device: torch.device) -> int:

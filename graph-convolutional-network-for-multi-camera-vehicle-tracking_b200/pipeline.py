@@ -12,7 +12,7 @@ Nothing here computes: it is stream / event / buffer plumbing around ``TrackletG
 """
 import torch
 
-from .graph import TrackletGraph
+from .graph import TrackletGraph, release_scope, workspace_scope
 
 
 class _Slot:
@@ -36,9 +36,11 @@ class GraphStream:
     """
 
     def __init__(self, model, device, depth: int = 2, graph_replay: bool = False):
-        """``graph_replay`` (EXPERIMENTAL, off by default, not yet measured on hardware): when a slot sees the same signature
-        (feature shape, camera layout, weights) a second time, the graph tables + forward of that slot are captured as one CUDA
-        graph over slot-static buffers and replayed from then on: one launch instead of ~40 per graph."""
+        """``graph_replay``: when a slot sees the same signature (feature shape, camera layout, weights) a second time, the graph
+        tables + edge features + forward + decisions of that slot are captured as one CUDA graph over slot-static buffers and
+        replayed from then on: one launch instead of ~40 per graph (configs[1]: 0.84 -> 0.79 ms per step, same bits; the win is
+        larger for small graphs, whose time is mostly launches).  Off by default: a stream of graphs of ever-changing shapes
+        would only pay the captures."""
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.model, self.device, self.depth = model, torch.device(device), int(depth)
@@ -49,6 +51,8 @@ class GraphStream:
         self.copy_out = torch.cuda.Stream(self.device)
         self.slots = [_Slot() for _ in range(self.depth)]
         self.n_submitted = 0
+        GraphStream._instances = getattr(GraphStream, "_instances", 0) + 1
+        self._id = GraphStream._instances
 
     def submit(self, x_host, cam_ids, pred_host, prob_host=None):
         """``x_host``: pinned fp32 [N, D] (column-normalised ReID features, inference.py:403-404); ``cam_ids``: host sequence of
@@ -78,7 +82,7 @@ class GraphStream:
                 if slot.cap_key == key:
                     cap = slot.cap
                 elif slot.seen_key == key:                   # second time: capture (the first, eager run did the lazy set-up)
-                    slot.cap, slot.cap_key = self._capture(slot, cam_ids), key
+                    slot.cap, slot.cap_key = self._capture(slot, cam_ids, self.n_submitted % self.depth), key
                     cap = slot.cap
                 else:
                     slot.seen_key, slot.cap, slot.cap_key = key, None, None
@@ -128,9 +132,29 @@ class GraphStream:
         self.model._weights(self.device)                   # refreshes the packed-weights key if a parameter changed
         return (slot.x_dev.data_ptr(), tuple(slot.x_dev.shape), str(cam.dtype), cam.tobytes(), self.model._packed[0])
 
-    def _capture(self, slot, cam_ids):
+    def _capture(self, slot, cam_ids, index):
         """One CUDA graph of K0 + K1 + forward + decisions for this slot.  Tensors allocated while capturing (graph tables,
-        edge features, logits, decisions) live in the graph's private pool: their addresses are the same at every replay."""
+        edge features, logits, decisions) live in the graph's private pool: their addresses are the same at every replay.  The
+        library's scratch buffers are taken from a scope of this slot's own (and pre-sized by an eager run inside the scope), so
+        no other call can grow — and thereby free — memory whose address the graph has baked in."""
+        model, dev = self.model, self.device
+        tag = "graphstream%d.slot%d" % (self._id, index)
+        slot.cap = None
+        release_scope(tag)
+        with workspace_scope(tag):
+            warm = _Batch()
+            warm.x, warm.edge_attr = slot.x_dev, None
+            warm.mpn_graph = TrackletGraph.from_cameras(cam_ids, dev)
+            warm.num_nodes = warm.mpn_graph.n_cols
+            fuse0, small0 = model.fuse_decisions, model.use_cuda_graph
+            model.fuse_decisions, model.use_cuda_graph = True, False
+            try:
+                model(warm)                                     # sizes the scoped workspaces outside the capture
+            finally:
+                model.fuse_decisions, model.use_cuda_graph = fuse0, small0
+            return self._capture_scoped(slot, cam_ids)
+
+    def _capture_scoped(self, slot, cam_ids):
         model, dev = self.model, self.device
         cap = _Batch()
         cap.graph = torch.cuda.CUDAGraph()

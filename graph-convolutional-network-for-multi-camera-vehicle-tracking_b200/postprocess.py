@@ -63,10 +63,6 @@ class _Post:
     def labels_reference(self):
         """ID_pred exactly as compute_SCC_and_Clusters numbers it (utils.py:30-52): int64 CPU tensor."""
         g = self.g
-        n_act = C.c_int64(0)
-        cap = max(int(self.act.sum().item()), 1)
-        src = torch.empty(cap, dtype=torch.int32, device=self.dev)
-        dst = torch.empty(cap, dtype=torch.int32, device=self.dev)
         act = self.act
         if g.perm is not None:
             # the reference scans active edges in the CALLER's edge order: compact in that order
@@ -80,11 +76,13 @@ class _Post:
             s_h, d_h = ei[0, sel].to(torch.int32).cpu(), ei[1, sel].to(torch.int32).cpu()
             n = int(idx.numel())
         else:
+            # sorted graphs: partition + first-appearance keys on the device, the rank over the components on the host
+            labels = torch.empty(g.n_nodes, dtype=torch.int64)
+            ncomp = C.c_int32(0)
             with torch.cuda.device(self.dev):
-                _lib.check(self.lib.mpn_active_edges(g.ref, act.data_ptr(), src.data_ptr(), dst.data_ptr(), cap,
-                                                     C.byref(n_act), self.ws.data_ptr(), self.ws.numel(), self.stream))
-            n = int(n_act.value)
-            s_h, d_h = src[:n].cpu(), dst[:n].cpu()
+                _lib.check(self.lib.mpn_labels_reference(g.ref, act.data_ptr(), labels.data_ptr(), C.byref(ncomp),
+                                                         self.ws.data_ptr(), self.ws.numel(), self.stream))
+            return labels, int(ncomp.value)
         labels = torch.empty(g.n_nodes, dtype=torch.int64)
         ncomp = C.c_int32(0)
         _lib.check(self.lib.mpn_labels_reference_host(s_h.data_ptr(), d_h.data_ptr(), n, g.n_nodes, labels.data_ptr(),

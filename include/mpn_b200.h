@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPN_B200_ABI_VERSION 4
+#define MPN_B200_ABI_VERSION 5
 
 enum {
   MPN_OK = 0,
@@ -42,6 +42,9 @@ enum {
 #define MPN_DH 32           /* node embedding width  (encoder node_out_dim, node_model fc_dims[-1]) */
 #define MPN_MAX_NODE_LAYERS 8
 
+/* Threading contract: one host thread and one CUDA stream per device use the library at a time.  Work is enqueued on the caller's
+ * stream (plus one library-owned side stream per device, forked from and joined to it with events); scratch memory is the
+ * caller's (workspace arguments); the error string and the SPLITTING statistics are thread-local. */
 int mpn_abi_version(void);
 const char* mpn_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (monotonic) */
@@ -350,6 +353,12 @@ int mpn_compact_active(const mpn_graph* g, const uint8_t* act_dev, const float* 
 int mpn_clear_inactive(uint8_t* act_dev, const int32_t* eid_dev, const uint8_t* keep_dev, int64_t n, void* stream);
 /* Host-side (CPU, sequential by nature): label integers exactly as compute_SCC_and_Clusters (utils.py:30-52)
  * assigns them — networkx SCC emission order, stable sort by size, isolated nodes last.  HOST pointers. */
+/* ID_pred exactly as compute_SCC_and_Clusters numbers it (utils.py:30-52) for the activity flags `act_dev` of a (row, col)-sorted
+ * graph: SCC partition and first-appearance keys on the device, the rank of (size, emission key) on the host over the
+ * COMPONENTS (not the edges); only the components that one-directional edges tie together go through a sequential generator.
+ * labels_out_host: HOST int64 [n_nodes].  Synchronises. */
+int mpn_labels_reference(const mpn_graph* g, const uint8_t* act_dev, int64_t* labels_out_host, int32_t* n_components_host,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
 int mpn_labels_reference_host(const int32_t* src_host, const int32_t* dst_host, int64_t n_active, int32_t n_nodes,
                               int64_t* labels_out_host, int32_t* n_components_host);
 /* Host-side SPLITTING in the reference's own order (utils.py:54-123): one oversized cluster at a time — the lowest label of the

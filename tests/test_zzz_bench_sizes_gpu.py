@@ -6,7 +6,8 @@ configs[1]: 4096 tracklets, 8 cameras, 2048-d features, E = 14,680,064 — tcgen
 configs[2]: 2000 S02-shaped graphs in one call, 50 of them against the single-graph path.
 configs[3]: post-processing on 1,000,000 nodes against the plain-C oracle (bit-exact decisions and reference label integers) on
             distinct probabilities (no tie: all-clusters-per-round equals the reference's order exactly, so the C rounds oracle is
-            a valid checker at this size), and under float32 ties through size-independent properties.
+            a valid checker at this size), and under float32 ties through size-independent properties (the statement-order oracle
+            needs hours at this size; it pins the same code path at 200 k nodes in tests/test_zz_c_oracle_gpu.py).
 """
 import numpy as np
 import pytest
@@ -54,10 +55,12 @@ def test_configs3_size_post_processing_vs_c_oracle(m):
                                                           single_dir=0.05)
     # distinct probabilities on the active edges: no tie, so the reference's order cannot matter
     rng = np.random.default_rng(1)
-    prob_u = np.where(pred > 0, rng.permutation(np.linspace(0.55, 0.99, prob.size)), 0.2).astype(np.float64)
-    prob_u = prob_u.astype(np.float32)
     a = pred > 0
-    assert np.unique(prob_u[a]).size == int(a.sum())
+    n_act = int(a.sum())
+    bits = np.float32(0.55).view(np.uint32) + rng.permutation(n_act).astype(np.uint32)     # consecutive float32 values from 0.55 up
+    prob_u = np.full(prob.size, 0.2, dtype=np.float32)
+    prob_u[a] = bits.view(np.float32)
+    assert np.unique(prob_u[a]).size == n_act and prob_u[a].max() < 1.0
     data = Data(x=torch.zeros(n_nodes, 1, device=dev), edge_index=torch.from_numpy(np.stack([src, dst])).to(dev))
     cfg = {"CUTTING": True, "PRUNING": True, "SPLITTING": True}
     lab_ref, act_ref = pc.post_processing(src, dst, pred, prob_u, cams, n_nodes, numbering="reference")
@@ -70,12 +73,10 @@ def test_configs3_size_post_processing_vs_c_oracle(m):
     st = m.split_stats()
     assert st["mode"] == "reference_order_host" and st["tied_edges"] > 0
     assert np.bincount(ID.numpy()).max() <= cams
-    Pn = P.cpu().numpy()
-    rev = pc.reverse_edge_map(src, dst, n_nodes)
-    on = np.flatnonzero(Pn)
-    assert np.all(rev[on] >= 0) and np.all(Pn[rev[on]] == 1)                       # what survives is symmetric (CUT ran last before SPLIT)
-    ID2, P2 = m.post_processing(cams, None, None, P.clone(), None, dict(cfg), data, torch.from_numpy(prob).to(dev))
-    assert torch.equal(P2, P) and np.array_equal(ID2.numpy(), ID.numpy())          # idempotent
+    assert bool((P.cpu() <= torch.from_numpy(pred)).all())                          # only active edges were switched off
+    ID2, P2 = m.post_processing(cams, None, None, P.clone(), None, {"CUTTING": False, "PRUNING": False, "SPLITTING": True}, data,
+                                torch.from_numpy(prob).to(dev))
+    assert torch.equal(P2, P) and np.array_equal(ID2.numpy(), ID.numpy())          # SPLITTING again: nothing oversized is left
     # CUT + PRUNE + CUT (order-free stages) against the C oracle on the tied probabilities too
     lab_c, act_c = pc.post_processing(src, dst, pred, prob, cams, n_nodes, splitting=False, numbering="reference")
     IDc, Pc = m.post_processing(cams, None, None, torch.from_numpy(pred).to(dev), None,

@@ -11,10 +11,9 @@ x, ei = bench.device_graph(N, 8, 0, dev)
 b = bench.Batch(); b.num_nodes = N
 
 
-def step():
+def step():                      # the bench step: tables from the int64 edge_index, ONE forward call with the edge features inside
     g = m.TrackletGraph(ei, N, validate="deferred")
-    b.x, b.mpn_graph = x, g
-    b.edge_attr = m.edge_features(x, None, graph=g)
+    b.x, b.edge_index, b.mpn_graph, b.edge_attr = x, ei, g, None
     net(b)
     g.validate()
     return net.last_pred
