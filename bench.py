@@ -824,9 +824,9 @@ def run_ours(args):
     # Throughput of a STREAM of host-resident graphs (the reference loops over one-graph batches, inference.py:375): GraphStream
     # keeps two graphs in flight so the PCIe copies of neighbouring graphs overlap the kernels.  Every graph still pays its own
     # H2D (features + camera ids) and D2H (decisions) inside the timed region; the region closes after the last D2H.
-    pipe_ms, pipe_depth, n_pipe = None, 2, max(args.steps, 3)
-    if world == 1:
-        gs = m.GraphStream(net, dev, depth=pipe_depth)
+    pipe_ms, pipe_depth, n_pipe = None, 2, max(min(args.steps, 200), 3)
+    if True:
+        gs = m.GraphStream(net, dev, depth=pipe_depth) if world == 1 else m.ShardedGraphStream(sharded, blocks, dev, depth=pipe_depth)
         hpreds = [torch.empty(E_local, dtype=torch.uint8).pin_memory() for _ in range(pipe_depth + 1)]
 
         def run_pipe(k):
@@ -842,7 +842,10 @@ def run_ours(args):
         run_pipe(n_pipe)
         b.record()
         barrier()
-        pipe_ms = a.elapsed_time(b) / n_pipe
+        pipe = torch.tensor([a.elapsed_time(b) / n_pipe], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(pipe, op=dist.ReduceOp.MAX)                        # max over ranks
+        pipe_ms = float(pipe.item())
         gs.drain()
         if not torch.equal(hpreds[(n_pipe - 1) % len(hpreds)], hpred):
             raise RuntimeError("GraphStream decisions differ from the one-at-a-time call")
@@ -865,10 +868,11 @@ def run_ours(args):
                         "d2h_bytes_per_step": d2h, "ms_per_step": pipe_ms or e2e_ms,
                         "inputs": "host node features f32 (N = 1: [N,2048]; N > 1: each rank its own rows, all-gathered over NVLink) + "
                                   "camera ids; graph tables built on the device; decisions (u8 per edge) copied back",
-                        "how": ("GraphStream(depth=%d): %d graphs submitted back to back from pinned host memory, timed from the first "
-                                "H2D to the last D2H (CUDA events); the H2D / D2H of neighbouring graphs overlap the kernels, every "
-                                "graph pays its own copies; no L2 flush (each graph's ~600 MB of edge arrays exceed L2)"
-                                % (pipe_depth, n_pipe)) if pipe_ms else
+                        "how": ("%s(depth=%d): %d graphs submitted back to back from pinned host memory, timed from the first "
+                                "H2D to the last D2H (CUDA events, max over ranks); the H2D / D2H%s of neighbouring graphs overlap the "
+                                "kernels, every graph pays its own copies; no L2 flush (each graph's ~600 MB of edge arrays exceed L2)"
+                                % ("GraphStream" if world == 1 else "ShardedGraphStream", pipe_depth, n_pipe,
+                                   "" if world == 1 else " / NVLink all-gather of the feature rows")) if pipe_ms else
                                "one graph at a time: H2D, kernels, D2H serial; median over the timed calls, max over ranks",
                         "one_at_a_time": {"value": E_total / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
                                           "how": "H2D, kernels, D2H serial per call, barrier + L2 flush between calls; median"}},

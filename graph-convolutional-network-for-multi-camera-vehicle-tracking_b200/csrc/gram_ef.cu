@@ -136,30 +136,36 @@ __global__ void __launch_bounds__(256) ge_col_mean_kernel(const float* __restric
 }
 
 // ---- pre-pass 2: centred rows -> per-row scaled fp16 planes + node records, and the one-gap table of the graph's own rows.
-// One warp per row.  rec[r] = {|a'|^2, 2 eps sum a', mu.a' + |mu|^2/2, 1/|a|}, scale_inv[r] = 2^-k_r with max|a'| 2^k_r in
+// One warp per row (four fp32 terms, then fp64: the row statistics stay accurate to ~1e-7 relative, like the Gram entry they meet).  rec[r] = {|a'|^2, 2 eps sum a', mu.a' + |mu|^2/2, 1/|a|}, scale_inv[r] = 2^-k_r with max|a'| 2^k_r in
 // [2^13, 2^14).  A row whose norm is too small for the reciprocal (the reference clamps |a||b| at 1e-8) poisons its |a'|^2 with
 // NaN: every pair it takes part in then fails the cancellation test and is recomputed exactly.
-// REGS > 0: the row (REGS x 128 floats) is held in registers between the statistics and the split (one read of x); 0: two passes.
+// STAGE: the row is copied once into shared memory with cp.async (no registers held across the gap search and the statistics, so
+// every warp of the grid is resident in one wave) and both passes read it from there; !STAGE (rows that do not fit): two passes
+// over global memory.
 // Gap table (rows of the graph block only): columns are strictly ascending within a row, so col[beg+k] - k is non-decreasing: 0
 // before the gap, the gap length after it -> 32-ary search for the first k with col[beg+k] != k.  The row is "all columns but
 // [k, k+gl)" iff the entry after the gap is k+gl and the last entry is n_cols-1; any other row raises *not_one_gap.
-template <int REGS>
-__global__ void __launch_bounds__(128) ge_center_split_kernel(const float* __restrict__ x, const float* __restrict__ mu, int n, int D,
+constexpr int GE_CS_WARPS = 4;
+template <bool STAGE>
+__global__ void __launch_bounds__(32 * GE_CS_WARPS) ge_center_split_kernel(const float* __restrict__ x, const float* __restrict__ mu, int n, int D,
                                                               uint2* __restrict__ hi, uint2* __restrict__ lo, float4* __restrict__ rec,
                                                               float* __restrict__ scale_inv, const mpn_graph g, int2* __restrict__ gap,
                                                               int* __restrict__ not_one_gap) {
   pdl_wait();
-  const int lane = threadIdx.x & 31;
+  extern __shared__ float4 cs_rows[];                        // STAGE: [GE_CS_WARPS][D / 4]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int D4 = D >> 2;
   const float4* mu4 = reinterpret_cast<const float4*>(mu);
+  float4* mine = cs_rows + (size_t)warp * D4;
   for (int r = gwarp; r < n; r += nwarps) {
     const float4* p = reinterpret_cast<const float4*>(x + (size_t)r * D);
-    float4 buf[REGS > 0 ? REGS : 1];
-    if (REGS > 0) {                                          // the row's loads are in flight while the gap search runs
-#pragma unroll
-      for (int t = 0; t < REGS; ++t) buf[t] = p[lane + 32 * t];
+    if (STAGE) {                                             // the row's bytes are in flight while the gap search runs
+      __syncwarp();
+      for (int k = lane; k < D4; k += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(mine + k)), "l"(p + k) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     const int lr = r - g.row_offset;
     if (lr >= 0 && lr < g.n_nodes) {                         // gap of local row lr (warp-uniform branch)
@@ -184,25 +190,25 @@ __global__ void __launch_bounds__(128) ge_center_split_kernel(const float* __res
         if (!ok) atomicOr(not_one_gap, 1);
       }
     }
+    if (STAGE) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
     double sq = 0.0, sx = 0.0, md = 0.0, mm = 0.0;
     float amax = 0.f;
-    for (int t = 0; t * 32 + lane < D4; ++t) {
-      const int k = t * 32 + lane;
-      float4 v;
-      if (REGS > 0) v = buf[t]; else v = p[k];
+    for (int k = lane; k < D4; k += 32) {
+      const float4 v = STAGE ? mine[k] : p[k];
       const float4 m = __ldg(mu4 + k);
       const float c[4] = {v.x - m.x, v.y - m.y, v.z - m.z, v.w - m.w};
       const float mv[4] = {m.x, m.y, m.z, m.w};
-      if (REGS > 0) buf[t] = make_float4(c[0], c[1], c[2], c[3]);
+      if (STAGE) mine[k] = make_float4(c[0], c[1], c[2], c[3]);
+      float q = 0.f, s1 = 0.f, d1 = 0.f, m2 = 0.f;           // four terms in fp32, then one conversion each
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         amax = fmaxf(amax, fabsf(c[j]));
-        sq += (double)c[j] * c[j];
-        sx += (double)c[j];
-        md += (double)mv[j] * c[j];
-        mm += (double)mv[j] * mv[j];
+        q = fmaf(c[j], c[j], q); s1 += c[j]; d1 = fmaf(mv[j], c[j], d1); m2 = fmaf(mv[j], mv[j], m2);
       }
-      if (REGS > 0 && t + 1 == REGS) break;
+      sq += (double)q; sx += (double)s1; md += (double)d1; mm += (double)m2;
     }
     sq = warp_sum(sq); sx = warp_sum(sx); md = warp_sum(md); mm = warp_sum(mm);
 #pragma unroll
@@ -222,11 +228,11 @@ __global__ void __launch_bounds__(128) ge_center_split_kernel(const float* __res
     }
     uint2* oh = hi + (size_t)r * D4;
     uint2* ol = lo + (size_t)r * D4;
-    for (int t = 0; t * 32 + lane < D4; ++t) {
-      const int k = t * 32 + lane;
+    for (int k = lane; k < D4; k += 32) {
       float c[4];
-      if (REGS > 0) {
-        c[0] = buf[t].x * s; c[1] = buf[t].y * s; c[2] = buf[t].z * s; c[3] = buf[t].w * s;
+      if (STAGE) {
+        const float4 cv = mine[k];
+        c[0] = cv.x * s; c[1] = cv.y * s; c[2] = cv.z * s; c[3] = cv.w * s;
       } else {
         const float4 v = p[k], m = __ldg(mu4 + k);
         c[0] = (v.x - m.x) * s; c[1] = (v.y - m.y) * s; c[2] = (v.z - m.z) * s; c[3] = (v.w - m.w) * s;
@@ -244,7 +250,6 @@ __global__ void __launch_bounds__(128) ge_center_split_kernel(const float* __res
       pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
       oh[k] = ph;
       ol[k] = pl;
-      if (REGS > 0 && t + 1 == REGS) break;
     }
   }
 }
@@ -611,17 +616,15 @@ int gram_ef_run(const float* x, const float* mu, const mpn_graph* g, int D, int2
                 int* refine_list, int* refine_count, double* partials, int* n_partial_rows, const GeWorkspace& L, cudaStream_t st) {
   const int N = g->n_cols, M = g->n_nodes;
   MPN_REQUIRE(gram_ef_shape_ok(M, N, D), "fused edge features: unsupported shape M=%d N=%d D=%d", M, N, D);
-  const int cs_grid = min(kNumSMs * 16, div_up((long long)N * 32, 128));
-#define GE_CS(R) mpn::launch(ge_center_split_kernel<R>, cs_grid, 128, 0, st, x, mu, N, D, (uint2*)L.hi, (uint2*)L.lo, L.rec, L.scale_inv, *g, gap, not_one_gap)
-  switch ((D % 128) == 0 ? D / 128 : 0) {                  // rows of up to 2048 floats stay in registers between the two passes
-    case 1: GE_CS(1); break;
-    case 2: GE_CS(2); break;
-    case 4: GE_CS(4); break;
-    case 8: GE_CS(8); break;
-    case 16: GE_CS(16); break;
-    default: GE_CS(0); break;
+  const int cs_grid = min(kNumSMs * 16, div_up((long long)N, GE_CS_WARPS));
+  const size_t cs_smem = (size_t)GE_CS_WARPS * D * sizeof(float);
+  if (cs_smem <= 48 * 1024) {                              // rows of up to 3072 floats are staged in shared memory
+    mpn::launch(ge_center_split_kernel<true>, cs_grid, 32 * GE_CS_WARPS, cs_smem, st, x, mu, N, D, (uint2*)L.hi, (uint2*)L.lo, L.rec, L.scale_inv, *g,
+                gap, not_one_gap);
+  } else {
+    mpn::launch(ge_center_split_kernel<false>, cs_grid, 32 * GE_CS_WARPS, 0, st, x, mu, N, D, (uint2*)L.hi, (uint2*)L.lo, L.rec, L.scale_inv, *g,
+                gap, not_one_gap);
   }
-#undef GE_CS
   MPN_LAUNCH_OK();
   const int sym = (g->row_offset == 0 && M == N) ? 1 : 0;
   mpn::launch(ge_tile_list_kernel, 1, 1024, 0, st, gap, M, N, g->row_offset, sym, L.tiles, L.n_tiles, not_one_gap);

@@ -68,10 +68,11 @@ class GraphStream:
         slot = self.slots[self.n_submitted % self.depth]
         ticket = self.n_submitted
         with torch.cuda.device(dev):
-            if slot.x_dev is None or slot.x_dev.shape != x_host.shape:
+            full_shape = self._device_feature_shape(x_host, cam_ids)
+            if slot.x_dev is None or tuple(slot.x_dev.shape) != tuple(full_shape):
                 if slot.busy:
                     slot.compute_done.synchronize()
-                slot.x_dev = torch.empty(x_host.shape, dtype=torch.float32, device=dev)
+                slot.x_dev = torch.empty(full_shape, dtype=torch.float32, device=dev)
                 self.copy_in.wait_stream(compute)          # the allocator may hand out memory this stream still uses
             if slot.busy:
                 compute.wait_event(slot.out_done)            # the previous occupant's outputs have left the device: free them
@@ -87,33 +88,25 @@ class GraphStream:
                 else:
                     slot.seen_key, slot.cap, slot.cap_key = key, None, None
             # K0 on the device (does not need x): only the camera layout crosses PCIe
-            g = cap.g if cap is not None else TrackletGraph.from_cameras(cam_ids, dev)
+            g = cap.g if cap is not None else self._tables(cam_ids)
             if pred_host.numel() != g.n_edges or pred_host.dtype != torch.uint8:
                 raise ValueError("pred_host must be uint8 with one entry per edge (%d)" % g.n_edges)
             if prob_host is not None and (prob_host.numel() != g.n_edges or prob_host.dtype != torch.float32
                                           or not prob_host.is_pinned()):
                 raise ValueError("prob_host must be pinned float32 with one entry per edge")
-            if g.n_cols != x_host.shape[0]:
-                raise ValueError("cam_ids has %d entries, x_host %d rows" % (g.n_cols, x_host.shape[0]))
+            if g.n_cols != slot.x_dev.shape[0]:
+                raise ValueError("cam_ids has %d entries, the features %d rows" % (g.n_cols, slot.x_dev.shape[0]))
             if slot.busy:
                 self.copy_in.wait_event(slot.compute_done)   # the previous occupant's kernels have read x_dev
             with torch.cuda.stream(self.copy_in):
-                slot.x_dev.copy_(x_host, non_blocking=True)
+                self._copy_in(slot, x_host)
                 slot.in_done.record(self.copy_in)
             compute.wait_event(slot.in_done)
             if cap is not None:
                 cap.graph.replay()                           # tables + edge features + forward + decisions: one launch
                 data, pred, prob1 = cap.data, cap.pred, cap.prob1
             else:
-                data = _Batch()
-                data.x, data.mpn_graph, data.edge_attr, data.num_nodes = slot.x_dev, g, None, g.n_cols
-                fuse = self.model.fuse_decisions
-                self.model.fuse_decisions = True
-                try:
-                    self.model(data)
-                finally:
-                    self.model.fuse_decisions = fuse
-                pred, prob1 = self.model.last_pred, self.model.last_prob1
+                data, pred, prob1 = self._compute(slot, g)
             slot.compute_done.record(compute)
             self.copy_out.wait_event(slot.compute_done)
             with torch.cuda.stream(self.copy_out):
@@ -125,6 +118,27 @@ class GraphStream:
             slot.busy = True
         self.n_submitted += 1
         return ticket
+
+    # ---- hooks (ShardedGraphStream overrides them)
+    def _device_feature_shape(self, x_host, cam_ids):
+        return tuple(x_host.shape)
+
+    def _tables(self, cam_ids):
+        return TrackletGraph.from_cameras(cam_ids, self.device)          # K0 on the device: only the camera layout crosses PCIe
+
+    def _copy_in(self, slot, x_host):
+        slot.x_dev.copy_(x_host, non_blocking=True)
+
+    def _compute(self, slot, g):
+        data = _Batch()
+        data.x, data.mpn_graph, data.edge_attr, data.num_nodes = slot.x_dev, g, None, g.n_cols
+        fuse = self.model.fuse_decisions
+        self.model.fuse_decisions = True
+        try:
+            self.model(data)
+        finally:
+            self.model.fuse_decisions = fuse
+        return data, self.model.last_pred, self.model.last_prob1
 
     def _signature(self, slot, cam_ids):
         import numpy as np
@@ -194,3 +208,47 @@ class GraphStream:
 
 class _Batch:
     """Attribute bag standing in for torch_geometric.data.Data (inference.py:458)."""
+
+
+class ShardedGraphStream(GraphStream):
+    """The same pipeline for a row-block sharded graph (one process per GPU, ``ShardedMPN``): every rank copies only ITS rows of
+    the features from its pinned host buffer, the ranks all-gather them over NVLink on the copy-in stream (NCCL), each rank runs
+    its shard (tables of its row block, edge features of its rows, sharded forward) and copies its shard's decisions back.  One
+    graph computes at a time (the peer-memory exchange buffers of ``ShardedMPN`` are single-buffered); the copies and the
+    all-gather of graph i+1 overlap the kernels of graph i.  ``submit(x_rows_host, cam_ids, pred_host)``: ``x_rows_host`` =
+    rows ``blocks[rank]`` of the feature matrix."""
+
+    def __init__(self, sharded, blocks, device, depth: int = 2):
+        super().__init__(sharded.model, device, depth=depth, graph_replay=False)
+        self.sharded, self.blocks = sharded, [tuple(b) for b in blocks]
+        self.rank = sharded.comm.rank
+        n0, n1 = self.blocks[self.rank]
+        if any(b[1] - b[0] != n1 - n0 for b in self.blocks):
+            raise ValueError("ShardedGraphStream needs equal row blocks (NCCL all-gather of the feature rows)")
+
+    def _device_feature_shape(self, x_host, cam_ids):
+        n0, n1 = self.blocks[self.rank]
+        if x_host.shape[0] != n1 - n0:
+            raise ValueError("x_host must hold this rank's %d rows" % (n1 - n0))
+        return (self.blocks[-1][1], x_host.shape[1])
+
+    def _tables(self, cam_ids):
+        import numpy as np
+        cam = np.asarray(cam_ids.cpu() if isinstance(cam_ids, torch.Tensor) else cam_ids).reshape(-1)
+        sizes = np.bincount(cam - cam.min()).astype(np.int64)
+        self._total_edges = int((sizes * (cam.size - sizes)).sum())       # of the WHOLE graph: no all-reduce / host sync per submit
+        return TrackletGraph.from_cameras(cam_ids, self.device, row_block=self.blocks[self.rank])
+
+    def _copy_in(self, slot, x_host):
+        import torch.distributed as dist
+        n0, n1 = self.blocks[self.rank]
+        mine = slot.x_dev[n0:n1]
+        mine.copy_(x_host, non_blocking=True)
+        dist.all_gather_into_tensor(slot.x_dev, mine, group=self.sharded.comm.group)      # in place: rank r's rows sit at offset r
+
+    def _compute(self, slot, g):
+        from .edge_features import edge_features
+        ea = edge_features(slot.x_dev, None, graph=g)
+        out, h, pred, prob1 = self.sharded.forward(slot.x_dev, None, ea, self.blocks, fuse_decisions=True, graph=g,
+                                                   total_edges=self._total_edges)
+        return (out, h, ea), pred, prob1

@@ -101,6 +101,37 @@ def check_post(rank, world, dev, n_nodes=20000, cams=8):
     return ev0.elapsed_time(ev1)
 
 
+def check_stream(rank, world, dev):
+    """ShardedGraphStream (each rank copies its own feature rows, NVLink all-gather, shard forward, decisions back; two graphs in
+    flight) against the direct sharded call, bit for bit, over several graphs of two shapes."""
+    params = mo.shipped_model_params(2, 1, 64, (48, 40))
+    sd = mo.init_weights(params, "resnet101", 3)
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    sh = m.ShardedMPN(net)
+    for N, C in ((64 * world * 3, 3), (128 * world * 4, 4)):
+        per = N // world
+        blocks = [(r * per, (r + 1) * per) for r in range(world)]
+        cam = (np.arange(N) * C // N)
+        xs, refs = [], []
+        for seed in range(5):
+            x, _, _, _ = mo.synth_graph(N, C, seed, D=64, planted=True)
+            xd = x.to(dev)
+            g = m.TrackletGraph.from_cameras(cam, dev, row_block=blocks[rank])
+            ea = m.edge_features(xd, None, graph=g)
+            pred = sh.forward(xd, None, ea, blocks, fuse_decisions=True, graph=g)[2]
+            xs.append(x[blocks[rank][0]:blocks[rank][1]].contiguous().pin_memory())
+            refs.append(pred.cpu())
+        gs = m.ShardedGraphStream(sh, blocks, dev, depth=2)
+        outs = [torch.zeros(refs[0].numel(), dtype=torch.uint8).pin_memory() for _ in xs]
+        for xr, o in zip(xs, outs):
+            gs.submit(xr, cam, o)
+        gs.drain()
+        for o, r in zip(outs, refs):
+            assert torch.equal(o, r), "ShardedGraphStream decisions differ from the direct sharded call"
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
@@ -111,6 +142,7 @@ def main():
                                               (1, 1, 600, 3, 256, False), (3, 1, 600, 3, 128, True)]:
         worst = max(worst, check_case(rank, world, dev, L, n_cls, N, C, modes, chunk, reattach))
     post_ms = check_post(rank, world, dev)
+    check_stream(rank, world, dev)
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
