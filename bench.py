@@ -628,8 +628,7 @@ def big_graph_step(m, dev, world, rank, sharded_cls, n_nodes=32768, L=4, steps=3
             net(batch)
             return net.last_pred
         gr = m.TrackletGraph.from_cameras(cam_host, dev, row_block=blocks[rank])
-        ea = m.edge_features(x, None, graph=gr)
-        return sharded.forward(x, None, ea, blocks, fuse_decisions=True, graph=gr, total_edges=E_total)[2]
+        return sharded.forward(x, None, None, blocks, fuse_decisions=True, graph=gr, total_edges=E_total)[2]
 
     def barrier():
         if world > 1:
@@ -717,8 +716,7 @@ def run_ours(args):
             return net.last_pred
         n0, n1 = blocks[rank]
         g = m.TrackletGraph(ei, n_nodes, row_offset=n0, n_rows=n1 - n0, validate="deferred")
-        ea = m.edge_features(x, ei, graph=g)
-        out, h, pred, prob1 = sharded.forward(x, ei, ea, blocks, fuse_decisions=True, graph=g)
+        out, h, pred, prob1 = sharded.forward(x, ei, None, blocks, fuse_decisions=True, graph=g)     # edge features inside the call
         g.validate()
         return pred
 
@@ -800,8 +798,7 @@ def run_ours(args):
         mine.copy_(hx, non_blocking=True)
         dist.all_gather_into_tensor(dx, mine)
         g = m.TrackletGraph.from_cameras(cam_host, dev, row_block=blocks[rank])
-        ea = m.edge_features(dx, None, graph=g)
-        return sharded.forward(dx, None, ea, blocks, fuse_decisions=True, graph=g)[2]
+        return sharded.forward(dx, None, None, blocks, fuse_decisions=True, graph=g)[2]
 
     samples = []
     for i in range(n_e2e + 1):
@@ -825,7 +822,7 @@ def run_ours(args):
     # keeps two graphs in flight so the PCIe copies of neighbouring graphs overlap the kernels.  Every graph still pays its own
     # H2D (features + camera ids) and D2H (decisions) inside the timed region; the region closes after the last D2H.
     pipe_ms, pipe_depth, n_pipe = None, 2, max(min(args.steps, 200), 3)
-    if True:
+    if world >= 1:
         gs = m.GraphStream(net, dev, depth=pipe_depth) if world == 1 else m.ShardedGraphStream(sharded, blocks, dev, depth=pipe_depth)
         hpreds = [torch.empty(E_local, dtype=torch.uint8).pin_memory() for _ in range(pipe_depth + 1)]
 

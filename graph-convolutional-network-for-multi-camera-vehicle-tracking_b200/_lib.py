@@ -111,6 +111,9 @@ _PROTOS = {
     "mpn_forward_sharded": (C.c_int, [C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(MpnPeerCtx),
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mpn_forward_sharded_with_edge_features": (C.c_int, [C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_void_p, C.c_void_p, C.c_int32,
+                                                         C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                         C.POINTER(MpnPeerCtx), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_decide": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_post_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph)]),
     "mpn_cut": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -2071,9 +2071,12 @@ int mpn_forward_with_edge_features(const mpn_graph* g, const mpn_weights* w, con
                       ef_ws_bytes, stream);
 }
 
-int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x, const float* edge_attr, int32_t L, int32_t n_cls,
-                        int64_t total_edges, float* logits_out, float* h_out, uint8_t* pred_out, float* prob1_out, int use_tc,
-                        const mpn_peer_ctx* peers, void* ws, size_t ws_bytes, void* stream) {
+// ef_ws != NULL: edge_attr is an OUTPUT, produced here by the fused edge-feature kernel on the caller's stream (it overlaps the
+// node encoder on the side stream and hands over the first encoder BatchNorm's moment sums: no ENC0 sweep)
+static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const float* x, float* edge_attr_rw, int32_t L, int32_t n_cls,
+                                int64_t total_edges, float* logits_out, float* h_out, uint8_t* pred_out, float* prob1_out, int use_tc,
+                                const mpn_peer_ctx* peers, void* ws, size_t ws_bytes, void* ef_ws, size_t ef_ws_bytes, void* stream) {
+  const float* edge_attr = edge_attr_rw;
   MPN_REQUIRE(g && x && edge_attr && logits_out && peers, "forward_sharded: NULL argument");
   MPN_REQUIRE(peers->world >= 1 && peers->world <= MPN_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world, "forward_sharded: bad rank/world");
   MPN_REQUIRE(g->n_graphs <= 1, "forward_sharded: batched graphs cannot be row-sharded");
@@ -2104,23 +2107,51 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
 #define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
 #define PEER_FINALIZE(stage) do { mpn::launch(finalize_peer_kernel, 1, FIN_THREADS, 0, st, make_fin(p, stage, false), P, ++seq_m); \
     ++mpn::g_kernel_launches; if (cudaGetLastError() != cudaSuccess) { set_error("finalize_peer launch failed"); rc = MPN_ERR_CUDA; goto done; } } while (0)
+  // first encoder BatchNorm: a sweep over edge_attr, or (features computed here by the fused kernel) the partial rows of its epilogue
+#define ENC0_STAGE() do { \
+    bool enc0_done_ = false; \
+    if (ef_ws != nullptr) { \
+      if (cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st) != cudaSuccess || \
+          cudaMemsetAsync(p->fix_sums, 0, sizeof(unsigned long long) * 8, st) != cudaSuccess) { set_error("memset failed"); rc = MPN_ERR_CUDA; goto done; } \
+      EfMoments mom_; \
+      mom_.partials = p->partials; mom_.fixed_sums = p->fix_sums; mom_.handled_flag = nullptr; mom_.known_fused = 0; \
+      STEP_TRY(edge_features_impl(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st, &mom_)); \
+      if (mom_.handled_flag != nullptr && mom_.known_fused) { \
+        FinArgs f_ = make_fin(p, MPN_STAGE_ENC0, false); \
+        f_.fixed = p->fix_sums; \
+        mpn::launch(finalize_peer_kernel, 1, FIN_THREADS, 0, st, f_, P, ++seq_m); \
+        ++mpn::g_kernel_launches; \
+        if (cudaGetLastError() != cudaSuccess) { set_error("finalize_peer launch failed"); rc = MPN_ERR_CUDA; goto done; } \
+        enc0_done_ = true; \
+      } \
+    } \
+    if (!enc0_done_) { \
+      STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st)); \
+      PEER_FINALIZE(MPN_STAGE_ENC0); \
+    } } while (0)
   if (shard_enc) {
-    // every rank encodes its own rows; column statistics and the encoded rows travel over NVLink inside the kernels
-    STEP_TRY(node_encoder_sharded(p, x, P, seq_c, st));
-    mpn::launch(peer_publish_h_kernel, 1, 32, 0, st, P, ++seq_h);
+    // every rank encodes its own rows; column statistics and the encoded rows travel over NVLink inside the kernels.  The
+    // encoder chain (GEMMs + column-statistics exchanges, flag word 2, then the h publish, flag word 1) runs on the side stream
+    // while the caller's stream does the two encoder sweeps over edge_attr and their moment exchanges (flag word 0): the two
+    // chains touch different exchange slots and meet again before the first node tables.
+    SideStream* ss = side_stream();
+    const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
+    cudaStream_t es = fork ? ss->stream : st;
+    STEP_TRY(node_encoder_sharded(p, x, P, seq_c, es));
+    mpn::launch(peer_publish_h_kernel, 1, 32, 0, es, P, ++seq_h);
     ++mpn::g_kernel_launches;
     h_pending = true;
-    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
-    PEER_FINALIZE(MPN_STAGE_ENC0);
+    if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
+    ENC0_STAGE();
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
     PEER_FINALIZE(MPN_STAGE_ENC1);
+    if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
   } else {
     SideStream* ss = side_stream();
     const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
     STEP_TRY(mpn_plan_node_encoder(p, x, fork ? ss->stream : st));
     if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
-    STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
-    PEER_FINALIZE(MPN_STAGE_ENC0);
+    ENC0_STAGE();
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
     PEER_FINALIZE(MPN_STAGE_ENC1);
     if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
@@ -2162,11 +2193,28 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
                                     cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) { set_error("h copy failed: %s", cudaGetErrorString(e)); rc = MPN_ERR_CUDA; }
   }
+#undef ENC0_STAGE
 #undef PEER_FINALIZE
 #undef STEP_TRY
 done:
   mpn_plan_destroy(p);
   return rc;
+}
+
+int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x, const float* edge_attr, int32_t L, int32_t n_cls,
+                        int64_t total_edges, float* logits_out, float* h_out, uint8_t* pred_out, float* prob1_out, int use_tc,
+                        const mpn_peer_ctx* peers, void* ws, size_t ws_bytes, void* stream) {
+  return forward_sharded_impl(g, w, x, const_cast<float*>(edge_attr), L, n_cls, total_edges, logits_out, h_out, pred_out, prob1_out, use_tc,
+                              peers, ws, ws_bytes, nullptr, 0, stream);
+}
+
+int mpn_forward_sharded_with_edge_features(const mpn_graph* g, const mpn_weights* w, const float* x, float* edge_attr_out, int32_t L,
+                                           int32_t n_cls, int64_t total_edges, float* logits_out, float* h_out, uint8_t* pred_out,
+                                           float* prob1_out, int use_tc, const mpn_peer_ctx* peers, void* ws, size_t ws_bytes,
+                                           void* ef_ws, size_t ef_ws_bytes, void* stream) {
+  MPN_REQUIRE(ef_ws != nullptr && edge_attr_out != nullptr, "forward_sharded_with_edge_features: NULL edge-feature buffer / workspace");
+  return forward_sharded_impl(g, w, x, edge_attr_out, L, n_cls, total_edges, logits_out, h_out, pred_out, prob1_out, use_tc, peers, ws,
+                              ws_bytes, ef_ws, ef_ws_bytes, stream);
 }
 
 int mpn_decide(const float* logits, int64_t E, uint8_t* pred, float* prob1, void* stream) {

@@ -247,8 +247,6 @@ class ShardedGraphStream(GraphStream):
         dist.all_gather_into_tensor(slot.x_dev, mine, group=self.sharded.comm.group)      # in place: rank r's rows sit at offset r
 
     def _compute(self, slot, g):
-        from .edge_features import edge_features
-        ea = edge_features(slot.x_dev, None, graph=g)
-        out, h, pred, prob1 = self.sharded.forward(slot.x_dev, None, ea, self.blocks, fuse_decisions=True, graph=g,
+        out, h, pred, prob1 = self.sharded.forward(slot.x_dev, None, None, self.blocks, fuse_decisions=True, graph=g,
                                                    total_edges=self._total_edges)
-        return (out, h, ea), pred, prob1
+        return (out, h, self.sharded.last_edge_attr), pred, prob1

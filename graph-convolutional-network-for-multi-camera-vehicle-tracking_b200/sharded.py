@@ -312,7 +312,9 @@ class ShardedMPN:
 
     @torch.no_grad()
     def forward(self, x, local_edge_index, local_edge_attr, blocks, fuse_decisions=False, graph=None, total_edges=None):
-        """``total_edges``: number of edges of the WHOLE graph if the caller knows it (saves one all-reduce + host sync)."""
+        """``total_edges``: number of edges of the WHOLE graph if the caller knows it (saves one all-reduce + host sync).
+        ``local_edge_attr=None``: the edge features of this rank's rows (inference.py:453-456) are computed inside the call — they
+        overlap the node encoder and hand the first BatchNorm's moment sums over — and kept in ``self.last_edge_attr``."""
         from .mpn import USE_TENSOR_CORES
         m, comm = self.model, self.comm
         dev = x.device
@@ -324,11 +326,19 @@ class ShardedMPN:
         L, n_cls = int(m.num_enc_steps), int(m.num_class_steps)
         n_out = 1 if L == 0 else n_cls
         x = x.contiguous().float()
-        ea = local_edge_attr.contiguous().float()
+        make_features = local_edge_attr is None          # edge features of this rank's rows computed inside the call
         logits = torch.empty(max(n_out, 1), g.n_edges, 2, dtype=torch.float32, device=dev)
         pred = torch.empty(g.n_edges, dtype=torch.uint8, device=dev) if fuse_decisions else None
         prob1 = torch.empty(g.n_edges, dtype=torch.float32, device=dev) if fuse_decisions else None
         peers = self._peer_memory(x.shape[0], dev) if (self.fused and L >= 1) else None
+        if make_features and peers is None:
+            from .edge_features import edge_features
+            ea = edge_features(x, None, graph=g)
+        elif make_features:
+            ea = torch.empty(g.n_edges, 2, dtype=torch.float32, device=dev)
+        else:
+            ea = local_edge_attr.contiguous().float()
+        self.last_edge_attr = ea
         if peers is not None:
             total = int(total_edges) if total_edges is not None else -1      # -1: summed on the device, no host collective
             lib = _lib.lib()
@@ -339,12 +349,20 @@ class ShardedMPN:
             shard_enc = self.shard_node_encoder and max(W.node_dims[1:n_layers + 1]) <= _lib.MPN_PEER_CSTAT_COLS
             ctx = peers.ctx(shard_enc)
             with torch.cuda.device(dev):
-                _lib.check(lib.mpn_forward_sharded(g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, total,
-                                                   logits.data_ptr(), h_local.data_ptr(),
-                                                   pred.data_ptr() if pred is not None else None,
-                                                   prob1.data_ptr() if prob1 is not None else None,
-                                                   int(bool(USE_TENSOR_CORES)), C.byref(ctx), ws.data_ptr(), ws.numel(),
-                                                   current_stream_ptr(dev)))
+                if make_features:
+                    ef_ws = workspace("edge_features", dev, lib.mpn_edge_features_workspace_bytes(g.ref, x.shape[1]))
+                    _lib.check(lib.mpn_forward_sharded_with_edge_features(
+                        g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, total, logits.data_ptr(), h_local.data_ptr(),
+                        pred.data_ptr() if pred is not None else None, prob1.data_ptr() if prob1 is not None else None,
+                        int(bool(USE_TENSOR_CORES)), C.byref(ctx), ws.data_ptr(), ws.numel(), ef_ws.data_ptr(), ef_ws.numel(),
+                        current_stream_ptr(dev)))
+                else:
+                    _lib.check(lib.mpn_forward_sharded(g.ref, C.byref(W), x.data_ptr(), ea.data_ptr(), L, n_cls, total,
+                                                       logits.data_ptr(), h_local.data_ptr(),
+                                                       pred.data_ptr() if pred is not None else None,
+                                                       prob1.data_ptr() if prob1 is not None else None,
+                                                       int(bool(USE_TENSOR_CORES)), C.byref(ctx), ws.data_ptr(), ws.numel(),
+                                                       current_stream_ptr(dev)))
             peers.advance(L, shard_enc, n_layers)
             return {'classified_edges': [logits[i] for i in range(n_out)]}, h_local, pred, prob1
         total = int(total_edges) if total_edges is not None else self._total_edges(g, dev)

@@ -290,6 +290,15 @@ int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x
                         int32_t num_enc_steps, int32_t num_class_steps, int64_t total_edges, float* logits_out_dev,
                         float* h_out_dev /* [g->n_nodes,32] local rows */, uint8_t* pred_out_dev, float* prob1_out_dev,
                         int use_tensor_cores, const mpn_peer_ctx* peers, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* K1 + the sharded forward in one call (the row-block variant of mpn_forward_with_edge_features): edge_attr_out_dev [E_local,2] is
+ * PRODUCED here by the fused edge-feature kernel (this rank's rows of the Gram matrix) on `stream` while the node encoder runs on
+ * the side stream; the first encoder BatchNorm's moment sums come from that kernel's epilogue (no sweep over edge_attr), the
+ * ranks' sums still meet in the same peer-memory exchange.  ef_workspace: mpn_edge_features_workspace_bytes(g, node_dims[0]). */
+int mpn_forward_sharded_with_edge_features(const mpn_graph* g, const mpn_weights* w, const float* x_dev, float* edge_attr_out_dev,
+                                           int32_t num_enc_steps, int32_t num_class_steps, int64_t total_edges, float* logits_out_dev,
+                                           float* h_out_dev, uint8_t* pred_out_dev, float* prob1_out_dev, int use_tensor_cores,
+                                           const mpn_peer_ctx* peers, void* workspace_dev, size_t workspace_bytes,
+                                           void* ef_workspace_dev, size_t ef_workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Decisions.  Replaces inference.py:475-479 when the caller owns the logits.

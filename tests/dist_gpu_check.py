@@ -46,6 +46,11 @@ def check_case(rank, world, dev, L, n_cls, N, C, modes, chunk=None, reattach=Fal
         sh = m.ShardedMPN(net, fused=fused)
         for _rep in range(3):
             out, h_l, pred, prob1 = sh.forward(xd, ei_l, ea[lo:hi].to(dev), blocks, fuse_decisions=True, graph=g)
+        if fused:                                      # edge features inside the call (fused kernel + its moment sums): same logits
+            out_f, h_f, pred_f, _ = sh.forward(xd, ei_l, None, blocks, fuse_decisions=True, graph=g)
+            assert torch.allclose(sh.last_edge_attr.cpu(), ea[lo:hi], rtol=1e-5, atol=1e-5)
+            scale = ref[-1].abs().max().item()
+            assert (out_f["classified_edges"][-1] - out["classified_edges"][-1]).abs().max().item() <= 1e-5 * scale
         torch.cuda.synchronize()
         if fused and sh.path != "fused_peer_memory" and rank == 0:
             print("fused path unavailable")
@@ -119,8 +124,7 @@ def check_stream(rank, world, dev):
             x, _, _, _ = mo.synth_graph(N, C, seed, D=64, planted=True)
             xd = x.to(dev)
             g = m.TrackletGraph.from_cameras(cam, dev, row_block=blocks[rank])
-            ea = m.edge_features(xd, None, graph=g)
-            pred = sh.forward(xd, None, ea, blocks, fuse_decisions=True, graph=g)[2]
+            pred = sh.forward(xd, None, None, blocks, fuse_decisions=True, graph=g)[2]      # the call the stream makes
             xs.append(x[blocks[rank][0]:blocks[rank][1]].contiguous().pin_memory())
             refs.append(pred.cpu())
         gs = m.ShardedGraphStream(sh, blocks, dev, depth=2)
