@@ -141,6 +141,7 @@ struct TaskPrefetch {
 // produced the partials (single-GPU: saves a launch per BatchNorm).  Partials written by other blocks of the same kernel
 // are read with ld.global.cg (L2), never through the non-coherent path.
 // ------------------------------------------------------------------------------------------------
+struct PeerArgs;
 struct FinArgs {
   int stage;
   const double* partials;
@@ -156,6 +157,8 @@ struct FinArgs {
   double local_edges;         // this rank's edge count (sharded runs)
   const unsigned long long* fixed;   // ENC0, optional: 2^40 fixed-point sums of the edges the fused edge-feature kernel left to the
                               // refine pass (gram_ef.cu / edge_features.cu), added to columns 0..4
+  const struct PeerArgs* peers;      // sharded runs with the finalize fused into the sweep's last block: device copy of the peer
+  unsigned long long seq;            // table and this exchange's sequence number (peers == nullptr: single GPU)
   int re_e;                   // reattach_initial_edges: 0 off, 1 on (y of the current step is recomputed later: keep the folded
                               // step-1 weights), 2 on and y stored (switch to the split weights after the first edge update)
 };
@@ -170,11 +173,11 @@ __device__ __forceinline__ void finalize_body(const FinArgs& f, int do_reduce, i
     // The reduction is the serial tail of the sweep's last block: it has to be short.  A thread owns a PAIR of adjacent live columns
     // (one 16-byte L2 load per partial row) and every `groups`-th row, four loads in flight; the row groups are then added through
     // shared memory in group order.  Fixed pattern => bit-reproducible.  Live columns: 8 (ENC / EDGE stages), 74 (NODE stage).
-    __shared__ double red[512];
+    __shared__ double red[2048];
     const int ncols = (stage == MPN_STAGE_NODE) ? 74 : 8;
     const int pairs = ncols >> 1;
     int groups = (int)blockDim.x / pairs;
-    if (groups * ncols > 512) groups = 512 / ncols;
+    if (groups * ncols > 2048) groups = 2048 / ncols;
     const int n_rows = f.n_partials;
     if (k < groups * pairs) {
       const int cp = k % pairs, gi = k / pairs;
@@ -305,10 +308,10 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned 
   }
 }
 
-// moment all-reduce + constant folding in one kernel: local partials -> my slot -> flag; wait for every rank; add the
-// slots in rank order (the same order on every rank => bit-identical totals); fold.
-__global__ void __launch_bounds__(1024) finalize_peer_kernel(const FinArgs f, const PeerArgs P, unsigned long long seq) {
-  pdl_wait();
+// moment all-reduce + constant folding: local partials -> my slot -> flag; wait for every rank; add the slots in rank order (the
+// same order on every rank => bit-identical totals); fold.  Runs as its own one-block kernel, or inside the last block of the
+// sweep that produced the partials (FinArgs::peers): no extra launch, and the partial rows are still hot in L2.
+__device__ __forceinline__ void finalize_peer_body(const FinArgs& f, const PeerArgs& P, unsigned long long seq) {
   finalize_body(f, 1, 0);                                   // local block partials -> f.sums
   __syncthreads();
   const int k = threadIdx.x;
@@ -335,6 +338,10 @@ __global__ void __launch_bounds__(1024) finalize_peer_kernel(const FinArgs f, co
   __syncthreads();
   finalize_body(f, 0, 1);
 }
+__global__ void __launch_bounds__(1024) finalize_peer_kernel(const FinArgs f, const PeerArgs P, unsigned long long seq) {
+  pdl_wait();
+  finalize_peer_body(f, P, seq);
+}
 
 // h all-gather: publish / wait on the second flag word
 __global__ void peer_publish_h_kernel(const PeerArgs P, unsigned long long seq) {
@@ -359,7 +366,8 @@ __device__ __forceinline__ void finalize_in_last_block(const FinArgs& f) {
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
-  finalize_body(f, 1, 1);
+  if (f.peers != nullptr) finalize_peer_body(f, *f.peers, f.seq);
+  else finalize_body(f, 1, 1);
   if (threadIdx.x == 0) *f.counter = 0u;             // ready for the next sweep
 }
 
@@ -1215,6 +1223,8 @@ __global__ void __launch_bounds__(128) graph_finalize_kernel(int stage, const mp
   f.n_total_dev = nullptr;
   f.local_edges = 0.0;
   f.fixed = nullptr;
+  f.peers = nullptr;
+  f.seq = 0;
   f.re_e = re_e;
   finalize_body(f, 0, 1);
 }
@@ -1546,6 +1556,9 @@ struct mpn_fwd_plan {
   double *partials, *partials2, *sums;
   unsigned int* fin_counter;
   unsigned long long* fix_sums;  // [8] fixed-point moment sums of the refined edge features (fused K1)
+  int seq_m_active;              // sharded runs: the sweeps' last blocks do the peer exchange
+  PeerArgs* peers_dev;           // sharded runs: device copy of the peer table (exchange fused into the sweeps' last blocks)
+  unsigned long long seq_m;      // sharded runs: last moment-exchange sequence number used
   unsigned int* col_counter;   // [max_dim/32 + 1] ticket counters of the column-statistics tiles
   int fuse_fin;               // single-GPU: the last block of each moment sweep folds the constants itself
   int n_graphs;               // > 1: batched small graphs, BatchNorm statistics per graph
@@ -1603,6 +1616,7 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.sums = a.take<double>(G * SUMS);
   p.fin_counter = a.take<unsigned int>(1);
   p.fix_sums = a.take<unsigned long long>(8);
+  p.peers_dev = a.take<PeerArgs>(1);
   p.n_total_dev = a.take<double>(1);
   p.col_counter = a.take<unsigned int>((size_t)(max_dim > 0 ? max_dim : 1) / 32 + 1);
   p.ybuf = stores_y(p) ? a.take<float>((size_t)g.n_edges * 4) : nullptr;
@@ -1686,6 +1700,9 @@ static FinArgs make_fin(const mpn_fwd_plan* p, int stage, bool fused) {
   f.n_total_dev = p->n_total_on_device ? p->n_total_dev : nullptr;
   f.local_edges = (double)p->g.n_edges;
   f.fixed = nullptr;
+  f.peers = nullptr;
+  f.seq = 0;
+  if (fused && p->seq_m_active) { f.peers = p->peers_dev; f.seq = ++const_cast<mpn_fwd_plan*>(p)->seq_m; }
   f.re_e = p->w.reattach_edges ? (stores_y(*p) ? 2 : 1) : 0;
   return f;
 }
@@ -2099,9 +2116,19 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
   MPN_TRY(mpn_plan_create(&p, g, w, L, n_cls, total_edges > 0 ? total_edges : (int64_t)1 << 40, use_tc, ws, ws_bytes));
   p->n_total_on_device = total_edges > 0 ? 0 : 1;
   if (L > 1 || shard_enc) p->h_full = peers->h[peers->rank];            // node tables read the peer-visible buffer
-  p->fuse_fin = 0;
+  // the moment exchange of every BatchNorm runs in the last block of the sweep that produced the partial sums
+  p->fuse_fin = 1;
+  p->seq_m_active = 1;
+  p->seq_m = peers->seq_moments;
   int rc = MPN_OK;
-  unsigned long long seq_m = peers->seq_moments, seq_h = peers->seq_h, seq_c = peers->seq_c;
+  unsigned long long& seq_m = p->seq_m;
+  unsigned long long seq_h = peers->seq_h, seq_c = peers->seq_c;
+  if (cudaMemcpyAsync(p->peers_dev, &P, sizeof(PeerArgs), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemsetAsync(p->fin_counter, 0, sizeof(unsigned int), st) != cudaSuccess) {
+    set_error("peer table upload failed");
+    mpn_plan_destroy(p);
+    return MPN_ERR_CUDA;
+  }
   bool h_pending = false;                                   // an h exchange has been published and not yet awaited
   const size_t lstride = (size_t)g->n_edges * 2;
 #define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
@@ -2125,10 +2152,8 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
         enc0_done_ = true; \
       } \
     } \
-    if (!enc0_done_) { \
-      STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st)); \
-      PEER_FINALIZE(MPN_STAGE_ENC0); \
-    } } while (0)
+    if (!enc0_done_) STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st)); \
+    } while (0)
   if (shard_enc) {
     // every rank encodes its own rows; column statistics and the encoded rows travel over NVLink inside the kernels.  The
     // encoder chain (GEMMs + column-statistics exchanges, flag word 2, then the h publish, flag word 1) runs on the side stream
@@ -2144,7 +2169,6 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
     if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
     ENC0_STAGE();
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
-    PEER_FINALIZE(MPN_STAGE_ENC1);
     if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
   } else {
     SideStream* ss = side_stream();
@@ -2153,7 +2177,6 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
     if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
     ENC0_STAGE();
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
-    PEER_FINALIZE(MPN_STAGE_ENC1);
     if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
   }
   {
@@ -2167,9 +2190,7 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
       }
       STEP_TRY(mpn_plan_node_tables(p, step, st));
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_EDGE, edge_attr, nullptr, nullptr, nullptr, st));
-      PEER_FINALIZE(MPN_STAGE_EDGE);
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_NODE, edge_attr, nullptr, nullptr, nullptr, st));
-      PEER_FINALIZE(MPN_STAGE_NODE);
       const bool cls = step >= first_class_step;
       const bool last = step == L;
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_APPLY, edge_attr, cls ? logits_out + lstride * k : nullptr,
