@@ -319,17 +319,23 @@ __device__ __forceinline__ void finalize_peer_body(const FinArgs& f, const PeerA
   // the first all-reduce of a forward also carries the edge counts (last, otherwise unused, slot entry)
   if (k == SUMS - 1 && f.stage == MPN_STAGE_ENC0 && f.n_total_dev) f.sums[SUMS - 1] = f.local_edges;
   __syncthreads();
-  if (k < SUMS) P.sums[P.rank][slot * SUMS + k] = f.sums[k];
+  // PUSH: every rank stores its sums into each peer's memory (slot of this exchange, row = my rank), then raises my flag word IN
+  // THE PEER'S memory; a rank polls and reads only its own memory (remote loads cost a NVLink round trip each, remote stores
+  // are fire-and-forget).  Double-buffered by the parity of seq: a rank can be at most one exchange ahead of a peer.
+  if (k < SUMS) {
+    const double v = f.sums[k];
+    for (int r = 0; r < P.world; ++r) P.sums[r][((size_t)slot * KPEERS + P.rank) * SUMS + k] = v;
+  }
   __threadfence_system();
   __syncthreads();
-  if (k == 0) st_release_sys(P.flags[P.rank], seq);
-  if (k < P.world) wait_flag(P.flags[k], seq);
+  if (k < P.world) st_release_sys(P.flags[k] + P.rank, seq);               // flag word [0][my rank] of peer k
+  if (k < P.world) wait_flag(P.flags[P.rank] + k, seq);                    // my own memory: word [0][k] raised by rank k
   __syncthreads();
   if (k < SUMS) {
     double t = 0.0;
-    for (int r = 0; r < P.world; ++r) {
+    for (int r = 0; r < P.world; ++r) {                                     // rank order: the same on every rank
       double v;
-      asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(P.sums[r] + slot * SUMS + k));
+      asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(P.sums[P.rank] + ((size_t)slot * KPEERS + r) * SUMS + k));
       t += v;
     }
     f.sums[k] = t;
@@ -346,14 +352,14 @@ __global__ void __launch_bounds__(1024) finalize_peer_kernel(const FinArgs f, co
 // h all-gather: publish / wait on the second flag word
 __global__ void peer_publish_h_kernel(const PeerArgs P, unsigned long long seq) {
   pdl_wait();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x < P.world) {                         // flag word [1][my rank] of every peer (pushed)
     __threadfence_system();
-    st_release_sys(P.flags[P.rank] + 1, seq);
+    st_release_sys(P.flags[threadIdx.x] + KPEERS + P.rank, seq);
   }
 }
 __global__ void peer_wait_h_kernel(const PeerArgs P, unsigned long long seq) {
   pdl_wait();
-  if (blockIdx.x == 0 && threadIdx.x < P.world) wait_flag(P.flags[threadIdx.x] + 1, seq);
+  if (blockIdx.x == 0 && threadIdx.x < P.world) wait_flag(P.flags[P.rank] + KPEERS + threadIdx.x, seq);     // own memory
 }
 
 // called by every block at the end of a sweep kernel, after its partial row has been written
@@ -1373,8 +1379,8 @@ __global__ void __launch_bounds__(1024) colstats_peer_kernel(const double* __res
   }
   __threadfence_system();
   __syncthreads();
-  if (col == 0) st_release_sys(P.flags[P.rank] + 2, seq);
-  if (col < P.world) wait_flag(P.flags[col] + 2, seq);
+  if (col == 0) st_release_sys(P.flags[P.rank] + 2 * KPEERS, seq);
+  if (col < P.world) wait_flag(P.flags[col] + 2 * KPEERS, seq);
   __syncthreads();
   if (col < Nc) {
     double s = 0.0, q = 0.0;

@@ -217,9 +217,9 @@ class CudaPhases:
         return self._h
 
 
-SUMS_BYTES = 2 * _lib.MPN_SUMS_DOUBLES * 8          # two slots of 96 fp64 moment sums
-FLAGS_OFFSET = SUMS_BYTES                            # three uint64 sequence flags (moments, h, column stats)
-CSTATS_OFFSET = 2048                                 # two slots of [1024][2] fp64 column sums (sharded node encoder)
+SUMS_BYTES = 2 * _lib.MPN_MAX_PEERS * _lib.MPN_SUMS_DOUBLES * 8      # two slots x 16 source ranks x 96 fp64 moment sums (pushed by the sources)
+FLAGS_OFFSET = SUMS_BYTES                            # 3 x 16 uint64 sequence flags: [moments][src], [h][src], [column stats][0]
+CSTATS_OFFSET = FLAGS_OFFSET + 512                   # two slots of [1024][2] fp64 column sums (sharded node encoder)
 H_OFFSET = CSTATS_OFFSET + 2 * _lib.MPN_PEER_CSTAT_COLS * 2 * 8        # h buffer [n_cols, 32] fp32 starts here
 
 

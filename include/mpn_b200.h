@@ -262,8 +262,10 @@ float* mpn_plan_h_full(mpn_fwd_plan* plan);     /* dev [n_cols,32]: row block [r
  * 96 fp64 sums in a peer-mapped slot, raises a sequence flag with st.release.sys, then adds all ranks' slots in rank
  * order — bit-identical totals on every rank), and for L > 1 the node-finalize kernel stores its rows of h straight into
  * every peer's h buffer (the all-gather).  `sums[r]`, `flags[r]`, `h[r]` are rank r's buffers as mapped into THIS
- * process (e.g. torch.distributed._symmetric_memory); layout per rank: sums = 2 slots x 96 doubles, flags = 2 uint64
- * (moment sequence, h sequence, column-stat sequence; zero-initialised, monotonic across calls), h = [n_cols,32] fp32,
+ * process (e.g. torch.distributed._symmetric_memory); layout per rank: sums = 2 slots x MPN_MAX_PEERS rows x 96 doubles (row s of
+ * a slot is WRITTEN BY rank s: the exchange pushes, every rank polls and reads only its own memory), flags = 3 x MPN_MAX_PEERS
+ * uint64 (word [0][s]: moment sequence raised by rank s, [1][s]: h sequence raised by rank s, [2][0]: this rank's column-stat
+ * sequence; zero-initialised, monotonic across calls), h = [n_cols,32] fp32,
  * cstats = 2 slots x MPN_PEER_CSTAT_COLS x 2 doubles.  With shard_node_encoder != 0 every rank encodes only its own row
  * block of x: the per-column BatchNorm sums of each encoder layer are all-reduced through `cstats` inside a kernel and
  * the encoded rows are stored into every peer's h buffer (needs h != NULL and encoder widths <= MPN_PEER_CSTAT_COLS).
