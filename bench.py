@@ -524,8 +524,10 @@ def extra_batched_graphs(m, dev, n_graphs=2000, n=300, cams=4):
 
 def planted_prediction_device(n_nodes, cams, e_target, dev, seed=7):
     """Predicted graph of BASELINE configs[3] generated on the device: planted clusters of <= cams nodes (one per camera), their
-    directed edges active with p in U(0.55,1) (2 % flipped off), plus random inter-cluster edges up to ``e_target`` of which 2 %
-    are flipped on (p in U(0.5,0.6)); ~1 % of the active edges lose their reverse.  Edges are (row, col)-sorted and unique."""
+    directed edges active with p in U(0.55,1) (2 % flipped off), plus random inter-cluster pairs (both directions) up to
+    ``e_target`` edges, each direction flipped on with 2 % (p in U(0.5,0.6)) — ~4e-4 of the pairs end up mutual and merge
+    clusters, which is what PRUNING and SPLITTING then undo; ~1 % of the active edges lose their reverse.  Edges are (row, col)-
+    sorted and unique."""
     g = torch.Generator(device=dev).manual_seed(seed)
     # nodes are laid out cluster by cluster; node k of a cluster sits in camera k
     sizes = torch.randint(1, cams + 1, (int(n_nodes * 2 / (cams + 1)) + cams,), generator=g, device=dev)
@@ -546,13 +548,13 @@ def planted_prediction_device(n_nodes, cams, e_target, dev, seed=7):
         parts_s += [a, a + k]
         parts_d += [a + k, a]
     s_in, d_in = torch.cat(parts_s), torch.cat(parts_d)
-    n_rand = max(0, e_target - s_in.numel())
+    n_rand = max(0, (e_target - s_in.numel()) // 2)                          # random inter-cluster PAIRS, both directions present
     s_r = torch.randint(0, n_nodes, (n_rand,), generator=g, device=dev)
     d_r = torch.randint(0, n_nodes, (n_rand,), generator=g, device=dev)
-    keep = cluster[s_r] != cluster[d_r]
+    keep = (cluster[s_r] != cluster[d_r]) & (pos[s_r] != pos[d_r])          # different identities, different cameras
     s_r, d_r = s_r[keep], d_r[keep]
-    key = torch.cat([s_in * n_nodes + d_in, s_r * n_nodes + d_r])
-    intra = torch.cat([torch.ones(s_in.numel(), dtype=torch.bool, device=dev), torch.zeros(s_r.numel(), dtype=torch.bool, device=dev)])
+    key = torch.cat([s_in * n_nodes + d_in, s_r * n_nodes + d_r, d_r * n_nodes + s_r])
+    intra = torch.cat([torch.ones(s_in.numel(), dtype=torch.bool, device=dev), torch.zeros(2 * s_r.numel(), dtype=torch.bool, device=dev)])
     key, order = torch.sort(key)
     intra = intra[order]
     uniq = torch.ones_like(intra)

@@ -711,6 +711,85 @@ __device__ __forceinline__ f32x2 relu2(f32x2 v) {
   return pack2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
 }
 
+// ENC1 moments on packed fp32: the sweep over edge_attr for the second encoder BatchNorm is issue bound (ncu: 2.1 warp
+// instructions per edge, issue slots 64 % busy, DRAM 28 %), so a thread takes TWO edges per 16-byte load and runs both through the
+// 2 -> 4 -> 4 edge encoder with fma.rn.f32x2 (one instruction per channel for both edges); the folded weights sit in registers as
+// broadcast pairs.  Sums in fp32 runs (RUN x U x 2 edges), then fp64, as enc_moments_kernel<1>.
+__global__ void __launch_bounds__(SWEEP_THREADS, 2) enc_moments1_packed_kernel(const float4* __restrict__ edge_attr2, long long n_pairs,
+                                                                             const float2* __restrict__ edge_attr, long long E,
+                                                                             const float* __restrict__ consts, const float* __restrict__ small,
+                                                                             double* __restrict__ partials, const FinArgs fin) {
+  pdl_wait();
+  __shared__ EdgeConsts sc;
+  __shared__ double red[(SWEEP_THREADS / 32) * 8];
+  load_consts(sc, consts);
+  f32x2 w1x[4], w1y[4], c1[4], w2[16], c2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    w1x[j] = pack2(sc.v[FC_ENC1_W + 2 * j], sc.v[FC_ENC1_W + 2 * j]);
+    w1y[j] = pack2(sc.v[FC_ENC1_W + 2 * j + 1], sc.v[FC_ENC1_W + 2 * j + 1]);
+    c1[j] = pack2(sc.v[FC_ENC1_C + j], sc.v[FC_ENC1_C + j]);
+    const float b = small[MPN_W_ENC2_B + j];
+    c2[j] = pack2(b, b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float w = small[MPN_W_ENC2_W + 4 * j + k]; w2[4 * j + k] = pack2(w, w); }
+  }
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  f32x2 f[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] = 0ull;
+  constexpr int U = 4, RUN = 4;
+  int in_run = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_pairs; i0 += stride * U) {
+    float4 v[U];
+    bool ok[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const long long i = i0 + stride * j;
+      ok[j] = i < n_pairs;
+      v[j] = ldg_stream4(edge_attr2 + (ok[j] ? i : n_pairs - 1));
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (!ok[j]) continue;
+      const f32x2 x2 = pack2(v[j].x, v[j].z), y2 = pack2(v[j].y, v[j].w);
+      f32x2 a1[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a1[c] = relu2(fma2(w1x[c], x2, fma2(w1y[c], y2, c1[c])));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        f32x2 u = c2[c];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u = fma2(w2[4 * c + k], a1[k], u);
+        f[c] = add2(f[c], u);
+        f[4 + c] = fma2(u, u, f[4 + c]);
+      }
+    }
+    if (++in_run == RUN) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { float lo, hi; unpack2(f[k], lo, hi); acc[k] += (double)lo + (double)hi; f[k] = 0ull; }
+      in_run = 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { float lo, hi; unpack2(f[k], lo, hi); acc[k] += (double)lo + (double)hi; }
+  if ((E & 1) && blockIdx.x == 0 && threadIdx.x == 0) {          // odd edge count: the last edge on its own
+    float a1[4], u[4];
+    enc_layer1(sc, edge_attr[E - 1], a1);
+    float w2raw[20];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w2raw[k] = small[MPN_W_ENC2_W + k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w2raw[16 + k] = small[MPN_W_ENC2_B + k];
+    enc_layer2_pre(w2raw, w2raw + 16, a1, u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { acc[k] += (double)u[k]; acc[4 + k] += (double)u[k] * (double)u[k]; }
+  }
+  block_sum_doubles<8, SWEEP_THREADS>(acc, red, partials + (size_t)blockIdx.x * SUMS);
+  finalize_in_last_block(fin);
+}
+
 // softmax([l0,l1])[1] (inference.py:475-477) with ATen's own arithmetic (softmax_warp_forward: exp(x - max) / sum, IEEE
 // division, full-precision expf), so that the value is bit-identical to torch.softmax(logits, dim=1)[:, 1] on the device:
 // PRUNING takes an argmin over it and SPLITTING compares it with float == (utils.py:96-98, 288-289).  exp(0) = 1 exactly, so
@@ -1887,8 +1966,19 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
                   (const int*)nullptr);
       break;
     case MPN_STAGE_ENC1:
-      mpn::launch(enc_moments_kernel<1>, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused),
-                  (const int*)nullptr);
+      if ((((uintptr_t)ea) & 15) == 0 && g.n_edges >= 2) {
+        const long long n_pairs = g.n_edges >> 1;
+        const int pgrid = (int)min((long long)kNumSMs * 2, (long long)div_up(n_pairs, SWEEP_THREADS));
+        FinArgs pf = make_fin(p, stage, fused);
+        pf.n_partials = pf.n_partials2 = pgrid;             // rows beyond this grid still hold the previous stage's partial sums:
+        if (!fused && pgrid < SWEEP_GRID)                   // a separate reduce (phase API) adds SWEEP_GRID rows -> clear them
+          MPN_CUDA_OK(cudaMemsetAsync(p->partials + (size_t)pgrid * SUMS, 0, sizeof(double) * (size_t)(SWEEP_GRID - pgrid) * SUMS, st));
+        mpn::launch(enc_moments1_packed_kernel, pgrid, SWEEP_THREADS, 0, st, (const float4*)ea, n_pairs, ea, g.n_edges, p->consts, p->w.small,
+                    p->partials, pf);
+      } else {
+        mpn::launch(enc_moments_kernel<1>, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused),
+                    (const int*)nullptr);
+      }
       break;
     case MPN_STAGE_EDGE:
       if (step == 1) {

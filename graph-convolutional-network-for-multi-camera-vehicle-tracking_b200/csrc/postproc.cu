@@ -35,7 +35,7 @@ struct PostCtx {
   int* tie_counts;                                               // ... and how many active edges carry each
   int tie_cap;
   float* a_prob;                                                 // SPLIT: probabilities in active-list order
-  uint8_t* sel;
+  uint8_t *sel, *tiedb;                                          // SPLIT: entry selected for the host; value carried by >= 2 active edges
   size_t total;
   // host
   int n_active;
@@ -74,6 +74,7 @@ static void post_layout(PostCtx& c, void* ws, size_t ws_bytes) {
   c.tie_counts = a.take<int>(tcap);
   c.a_prob = a.take<float>(E);
   c.sel = a.take<uint8_t>(E);
+  c.tiedb = a.take<uint8_t>(E);
   c.counters = a.take<int>(16);
   c.total = a.off;
 }
@@ -720,13 +721,16 @@ __global__ void flag_wcc_nodes_kernel(int n_list, const int* __restrict__ list, 
 __global__ void flag_wcc_ties_kernel(int A, const int* __restrict__ a_eid, const int* __restrict__ a_src, const uint8_t* __restrict__ act,
                                      const float* __restrict__ prob, int pstride, const unsigned int* __restrict__ keys,
                                      const int* __restrict__ counts, int cap, const int* __restrict__ wcc, int* __restrict__ flag,
-                                     int* __restrict__ n_tied_edges) {
+                                     uint8_t* __restrict__ tiedb, int* __restrict__ n_tied_edges) {
   int tied = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A; i += gridDim.x * blockDim.x) {
     const int e = a_eid[i];
-    if (!act[e]) continue;
-    const int slot = tie_find(keys, cap, __float_as_uint(prob[(size_t)e * pstride]));
-    if (slot >= 0 && counts[slot] >= 2) { flag[wcc[a_src[i]]] = 1; ++tied; }
+    uint8_t t = 0;
+    if (act[e]) {
+      const int slot = tie_find(keys, cap, __float_as_uint(prob[(size_t)e * pstride]));
+      if (slot >= 0 && counts[slot] >= 2) { flag[wcc[a_src[i]]] = 1; ++tied; t = 1; }
+    }
+    tiedb[i] = t;
   }
   tied = __reduce_add_sync(0xffffffffu, tied);
   if ((threadIdx.x & 31) == 0 && tied) atomicAdd(n_tied_edges, tied);
@@ -750,16 +754,20 @@ __global__ void apply_keep_kernel(int A, const int* __restrict__ a_eid, const ui
 }
 
 int split_exact_host_impl(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep,
-                          int64_t* stats_out);      // split_exact.cu
+                          int64_t* stats_out, const uint8_t* tied, const int* seeds, long long n_seeds);      // split_exact.cu
 
 // the reference's order on the host for the flagged components (every oversized cluster lives in one of them)
-static int split_in_reference_order(PostCtx& c, uint8_t* act, const float* prob, int pstride, int num_cameras, int* rounds) {
+static int split_in_reference_order(PostCtx& c, uint8_t* act, const float* prob, int pstride, int num_cameras, int Dn, bool have_ties,
+                                    int* rounds) {
   const int A = c.n_active, N = c.g.n_nodes;
   gather_select_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, act, prob, pstride, c.wcc, c.wccflag, c.a_prob, c.sel);
   MPN_LAUNCH_OK();
   std::vector<int> hs(A), hd(A);
   std::vector<float> hp(A);
-  std::vector<uint8_t> hsel(A), keep_all(A, 1);
+  std::vector<uint8_t> hsel(A), keep_all(A, 1), htied(have_ties ? A : 0);
+  std::vector<int> seeds(Dn);
+  MPN_CUDA_OK(cudaMemcpyAsync(seeds.data(), c.dirty_nodes, sizeof(int) * Dn, cudaMemcpyDeviceToHost, c.st));
+  if (have_ties) MPN_CUDA_OK(cudaMemcpyAsync(htied.data(), c.tiedb, A, cudaMemcpyDeviceToHost, c.st));
   MPN_CUDA_OK(cudaMemcpyAsync(hs.data(), c.a_src, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
   MPN_CUDA_OK(cudaMemcpyAsync(hd.data(), c.a_dst, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
   MPN_CUDA_OK(cudaMemcpyAsync(hp.data(), c.a_prob, sizeof(float) * A, cudaMemcpyDeviceToHost, c.st));
@@ -772,10 +780,11 @@ static int split_in_reference_order(PostCtx& c, uint8_t* act, const float* prob,
   const long long m = (long long)pos.size();
   std::vector<int> ss(m), dd(m);
   std::vector<float> pp(m);
-  std::vector<uint8_t> keep(m, 1);
-  for (long long k = 0; k < m; ++k) { ss[k] = hs[pos[k]]; dd[k] = hd[pos[k]]; pp[k] = hp[pos[k]]; }
+  std::vector<uint8_t> keep(m, 1), tt(have_ties ? m : 0);
+  for (long long k = 0; k < m; ++k) { ss[k] = hs[pos[k]]; dd[k] = hd[pos[k]]; pp[k] = hp[pos[k]]; if (have_ties) tt[k] = htied[pos[k]]; }
   int64_t st[4] = {0, 0, 0, 0};
-  if (m > 0) MPN_TRY(split_exact_host_impl(ss.data(), dd.data(), pp.data(), m, N, num_cameras, keep.data(), st));
+  if (m > 0) MPN_TRY(split_exact_host_impl(ss.data(), dd.data(), pp.data(), m, N, num_cameras, keep.data(), st, have_ties ? tt.data() : nullptr,
+                                           seeds.data(), (long long)seeds.size()));
   for (long long k = 0; k < m; ++k) keep_all[pos[k]] = keep[k];
   MPN_CUDA_OK(cudaMemcpyAsync(c.sel, keep_all.data(), A, cudaMemcpyHostToDevice, c.st));
   apply_keep_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.sel, act);
@@ -831,7 +840,7 @@ static int split_stage(PostCtx& c, uint8_t* act, const float* prob, int pstride,
     tie_count_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, act, prob, pstride, c.tie_keys, c.tie_counts, c.tie_cap);
     MPN_LAUNCH_OK();
     flag_wcc_ties_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, act, prob, pstride, c.tie_keys, c.tie_counts, c.tie_cap,
-                                                         c.wcc, c.wccflag, c.counters + 7);
+                                                         c.wcc, c.wccflag, c.tiedb, c.counters + 7);
     MPN_LAUNCH_OK();
     MPN_CUDA_OK(cudaMemcpyAsync(&n_tied, c.counters + 7, sizeof(int), cudaMemcpyDeviceToHost, c.st));
     MPN_CUDA_OK(cudaStreamSynchronize(c.st));
@@ -845,7 +854,7 @@ static int split_stage(PostCtx& c, uint8_t* act, const float* prob, int pstride,
       flag_wcc_nodes_kernel<<<list_grid(Dn), 256, 0, c.st>>>(Dn, c.dirty_nodes, c.wcc, c.wccflag);
       MPN_LAUNCH_OK();
     }
-    return split_in_reference_order(c, act, prob, pstride, num_cameras, rounds);
+    return split_in_reference_order(c, act, prob, pstride, num_cameras, Dn, table_fits, rounds);
   }
   // ---- no ties: the clusters are independent, every oversized cluster drops its minimum in the same round
   for (;;) {

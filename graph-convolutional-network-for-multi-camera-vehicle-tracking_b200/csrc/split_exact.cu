@@ -23,7 +23,10 @@
 #include <iterator>
 #include <set>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
+
+#include <cstring>
 
 #include "common.cuh"
 
@@ -73,12 +76,12 @@ struct SplitExact {
   }
 
   // nodes: a set closed under the alive edges.  Splits it into WCCs, runs networkx's SCC generator on each, registers clusters.
-  void recompute(const std::vector<int>& nodes) {
+  void recompute(const std::vector<int>& nodes, bool lazy_only = false) {
     ++mark_gen;
     std::vector<int> stack, wn, order, dfs, scc_stack;
     std::vector<std::pair<long long, int>> keyed;
     for (int seed : nodes) {
-      if (mark[seed] == mark_gen) continue;
+      if (mark[seed] == mark_gen || (lazy_only && wcc[seed] != -2)) continue;
       mark[seed] = mark_gen;
       wn.clear();
       stack.assign(1, seed);
@@ -162,9 +165,10 @@ struct SplitExact {
 // lowest oversized one (utils.py:112 re-reads the integer), clusters examined, 0.
 // builds the adjacency of the sub-problem (local node ids in order of first use) and registers every cluster
 static void split_exact_init(SplitExact& S, const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C,
-                             std::vector<int>* global_of_local) {
+                             std::vector<int>* global_of_local, const int* seeds = nullptr, long long n_seeds = 0) {
   S.m = m; S.prob = prob; S.C = C;
   std::vector<int> local((size_t)n_nodes, -1);
+  std::vector<int>& local_of = local;
   S.ls.resize(m); S.ld.resize(m);
   int n = 0;
   for (long long i = 0; i < m; ++i) {
@@ -173,7 +177,6 @@ static void split_exact_init(SplitExact& S, const int* src, const int* dst, cons
     S.ls[i] = local[src[i]];
     S.ld[i] = local[dst[i]];
   }
-  std::vector<int>().swap(local);
   S.n = n;
   S.out_ptr.assign(n + 1, 0); S.in_ptr.assign(n + 1, 0);
   for (long long i = 0; i < m; ++i) { S.out_ptr[S.ls[i] + 1]++; S.in_ptr[S.ld[i] + 1]++; }
@@ -186,11 +189,23 @@ static void split_exact_init(SplitExact& S, const int* src, const int* dst, cons
   S.out_first.assign(S.out_ptr.begin(), S.out_ptr.end() - 1);
   S.in_first.assign(S.in_ptr.begin(), S.in_ptr.end() - 1);
   S.alive.assign(m, 1);
-  S.comp.assign(n, -1); S.wcc.assign(n, -1);
+  S.comp.assign(n, -1); S.wcc.assign(n, -2);               // -2: component not examined yet (registered on first use)
   S.pre.assign(n, 0); S.low.assign(n, 0); S.it.assign(n, 0); S.mark.assign(n, 0);
-  std::vector<int> all(n);
-  for (int v = 0; v < n; ++v) all[v] = v;
-  S.recompute(all);
+  if (seeds == nullptr) {
+    std::vector<int> all(n);
+    for (int v = 0; v < n; ++v) all[v] = v;
+    S.recompute(all);
+  } else {
+    // only the weakly connected components that hold an oversized cluster are examined now; a component that merely carries a
+    // tied probability value is examined when (if) that value is dropped
+    std::vector<int> start;
+    start.reserve((size_t)n_seeds);
+    for (long long i = 0; i < n_seeds; ++i) {
+      const int v = seeds[i] >= 0 && seeds[i] < n_nodes ? local_of[(size_t)seeds[i]] : -1;
+      if (v >= 0) start.push_back(v);
+    }
+    S.recompute(start);
+  }
 }
 
 // networkx's emission order for a sub-graph that is a union of whole weakly connected components, given as its active edges in
@@ -209,17 +224,37 @@ void scc_emission_keys_host(const int* src, const int* dst, long long m, int n_n
   }
 }
 
+// tied (optional, [m]): 1 for an edge whose probability value is carried by at least two active edges of the graph (only those can
+// be switched off by another cluster's step); nullptr: found here by sorting.  seeds (optional): global ids of the nodes of the
+// oversized clusters; nullptr: every component is examined up front.
 int split_exact_host_impl(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep,
-                          int64_t* stats_out) {
+                          int64_t* stats_out, const uint8_t* tied, const int* seeds, long long n_seeds) {
   SplitExact S;
   for (long long i = 0; i < m; ++i) keep[i] = 1;
-  split_exact_init(S, src, dst, prob, m, n_nodes, C, nullptr);
-  S.by_prob.resize(m);
-  for (long long i = 0; i < m; ++i) S.by_prob[i] = (int)i;
-  std::sort(S.by_prob.begin(), S.by_prob.end(), [&](int a, int b) { return prob[a] < prob[b] || (prob[a] == prob[b] && a < b); });
+  split_exact_init(S, src, dst, prob, m, n_nodes, C, nullptr, seeds, n_seeds);
+  // probability value (bits) -> the edges that carry it, for the values carried by more than one edge
+  std::unordered_map<uint32_t, std::vector<int>> ties;
+  auto bits_of = [&](int e) { uint32_t b; float f = prob[e] == 0.0f ? 0.0f : prob[e]; memcpy(&b, &f, 4); return b; };
+  if (tied != nullptr) {
+    for (long long i = 0; i < m; ++i)
+      if (tied[i]) ties[bits_of((int)i)].push_back((int)i);
+  } else {
+    std::vector<int> order(m);
+    for (long long i = 0; i < m; ++i) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return prob[a] < prob[b] || (prob[a] == prob[b] && a < b); });
+    for (long long i = 0; i < m;) {
+      long long j = i + 1;
+      while (j < m && prob[order[j]] == prob[order[i]]) ++j;
+      if (j - i > 1) {
+        std::vector<int>& v = ties[bits_of(order[i])];
+        for (long long k = i; k < j; ++k) v.push_back(order[k]);
+      }
+      i = j;
+    }
+  }
   long long steps = 0, off_lowest = 0;
   long long sticky = -1;                          // index (in the order of `big`) of the cluster the reference's inner loop is on
-  std::vector<int> affected;
+  std::vector<int> affected, kill, lazy;
   std::vector<long long> wcc_stamp;
   while (!S.big.empty()) {
     const long long idx = (sticky >= 0) ? sticky : 0;
@@ -227,20 +262,34 @@ int split_exact_host_impl(const int* src, const int* dst, const float* prob, lon
     auto itb = S.big.begin();
     std::advance(itb, idx);
     const int c = std::get<3>(*itb);
-    const long long small_before = S.n_small;
     // minimum probability over the active edges with an endpoint in the cluster (utils.py:69-95)
     float mn = INFINITY;
+    int e_min = -1;
     for (int v : S.clusters[c].nodes) {
-      for (int k = S.out_first[v]; k < S.out_ptr[v + 1]; ++k) { const int e = S.out_adj[k]; if (S.alive[e] && prob[e] < mn) mn = prob[e]; }
-      for (int k = S.in_first[v]; k < S.in_ptr[v + 1]; ++k) { const int e = S.in_adj[k]; if (S.alive[e] && prob[e] < mn) mn = prob[e]; }
+      for (int k = S.out_first[v]; k < S.out_ptr[v + 1]; ++k) { const int e = S.out_adj[k]; if (S.alive[e] && prob[e] < mn) { mn = prob[e]; e_min = e; } }
+      for (int k = S.in_first[v]; k < S.in_ptr[v + 1]; ++k) { const int e = S.in_adj[k]; if (S.alive[e] && prob[e] < mn) { mn = prob[e]; e_min = e; } }
     }
-    if (!(mn < INFINITY)) { set_error("split: an oversized cluster without a finite edge probability"); return MPN_ERR_INVALID; }
-    // every edge of the graph with that probability (float ==, utils.py:96-98)
-    auto lo = std::lower_bound(S.by_prob.begin(), S.by_prob.end(), mn, [&](int e, float x) { return prob[e] < x; });
+    if (e_min < 0) { set_error("split: an oversized cluster without a finite edge probability"); return MPN_ERR_INVALID; }
+    // every edge of the graph with that probability (float ==, utils.py:96-98): the minimum edge itself and, when the value is
+    // carried by more than one edge, the others
+    kill.clear();
+    kill.push_back(e_min);
+    {
+      auto it = ties.find(bits_of(e_min));
+      if (it != ties.end())
+        for (int e : it->second)
+          if (e != e_min && S.alive[e]) kill.push_back(e);
+    }
+    // components that have not been examined yet (they hold no oversized cluster) enter the books before the step is counted
+    lazy.clear();
+    for (int e : kill) {
+      if (S.wcc[S.ls[e]] == -2) lazy.push_back(S.ls[e]);
+      if (S.wcc[S.ld[e]] == -2) lazy.push_back(S.ld[e]);
+    }
+    if (!lazy.empty()) S.recompute(lazy, true);
+    const long long small_before = S.n_small;
     affected.clear();
-    for (auto p = lo; p != S.by_prob.end() && prob[*p] == mn; ++p) {
-      const int e = *p;
-      if (!S.alive[e]) continue;
+    for (int e : kill) {
       S.alive[e] = 0;
       keep[e] = 0;
       const int w = S.wcc[S.ls[e]];
@@ -275,5 +324,5 @@ extern "C" int mpn_split_exact_host(const int32_t* src, const int32_t* dst, cons
     if (stats_out) stats_out[0] = stats_out[1] = stats_out[2] = stats_out[3] = 0;
     return MPN_OK;
   }
-  return mpn::split_exact_host_impl(src, dst, prob, n_active, n_nodes, num_cameras, keep_out, stats_out);
+  return mpn::split_exact_host_impl(src, dst, prob, n_active, n_nodes, num_cameras, keep_out, stats_out, nullptr, nullptr, 0);
 }
