@@ -680,6 +680,34 @@ def big_graph_step(m, dev, world, rank, sharded_cls, n_nodes=32768, L=4, steps=3
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+def step_timeline(lib, step_fn, flush, barrier, dev, world, reps=5):
+    """Where inside ONE step the time goes (mpn_profile_timeline: CUDA events at the phase boundaries of the step's forward call;
+    each entry = ms since the forward began, median over ``reps`` steps, max over ranks).  Measured after the timed region: the
+    events end the programmatic overlap between neighbouring kernels, so this step is a few percent slower than the timed ones."""
+    import ctypes
+    buf, names = (ctypes.c_float * 32)(), ctypes.create_string_buffer(2048)
+    rows = []
+    lib.mpn_profile_timeline(1)
+    try:
+        for r in range(reps):
+            flush.fill_(r)
+            barrier()
+            step_fn()
+            torch.cuda.synchronize(dev)
+            n = lib.mpn_profile_timeline_read(buf, names, 2048)
+            if n <= 0:
+                return None
+            rows.append([buf[i] for i in range(n)])
+    finally:
+        lib.mpn_profile_timeline(0)
+    keys = names.value.decode().split("|")
+    t = torch.tensor(rows, dtype=torch.float64, device=dev).median(dim=0).values
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {k: round(float(v), 4) for k, v in zip(keys, t.tolist())}
+
+
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -778,6 +806,7 @@ def run_ours(args):
     clk = clocks.stop() if clocks else None
     ms_per_step = total_ms / args.steps
     value = E_total / (ms_per_step * 1e-3)
+    timeline = step_timeline(lib, lambda: step(x, ei), flush, barrier, dev, world)
 
     # ---- e2e: the public API with HOST buffers (pinned), copies inside the timed region.  What the reference driver holds on
     # the host before it builds the graph (inference.py:383-414): the node features and the per-node camera ids; the graph tables
@@ -935,6 +964,7 @@ def run_ours(args):
         line["roofline"] = dict(roof[dominant], kernel=dominant, peak_source=peaks["source"], traffic_source=traffic.get("_source"))
         line["roofline_all"] = roof
         line["phase_ms"] = ph
+        line["step_timeline_ms"] = timeline
         line["s02_latency"] = s02_latency(m, dev)
         if not args.no_extras:
             extras = {}
@@ -987,6 +1017,7 @@ def run_ours(args):
                 c5 = {"error": "%s: %s" % (type(exc).__name__, exc)}
         if rank == 0:
             line["phase_ms"] = phs
+            line["step_timeline_ms"] = timeline
             line["c5_strong"] = c5
     if rank == 0:
         emit(line)

@@ -87,6 +87,8 @@ _PROTOS = {
     "mpn_graph_build_cross_camera": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mpn_profile_gram": (C.c_int, [C.c_int]),
     "mpn_profile_gram_ms": (C.c_float, []),
+    "mpn_profile_timeline": (C.c_int, [C.c_int]),
+    "mpn_profile_timeline_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "mpn_edge_features_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph), C.c_int32]),
     "mpn_edge_features": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_forward_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph), C.POINTER(MpnWeights), C.c_int32]),

@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tcgen05.cuh"
@@ -311,6 +313,7 @@ struct GeArgs {
   float2* edge_attr;
   int* refine_list;
   int* refine_count;
+  int balance;                // 1: blocks beyond ceil(T / rounds) take no tiles
   double* partials;           // [gridDim.x][MPN_SUMS_DOUBLES] moment partial rows (columns 0..4) or nullptr
   int M, N, K;                // rows of the block, columns (= nodes of the graph), feature width
   int row_global0;            // global node id of local row 0
@@ -331,6 +334,11 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = *A.n_tiles;
   const int num_kb = (A.K + GE_BK - 1) / GE_BK;
+  // Balanced rounds: T tiles take ceil(T / grid) rounds whatever happens, so only ceil(T / rounds) blocks work and the others leave
+  // their SM to the kernels of the other stream (the node encoder runs beside this kernel): 448 tiles -> 112 blocks x 4 tiles.
+  const int n_rounds = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t_stride = (A.balance && n_rounds > 0) ? (n_tiles + n_rounds - 1) / n_rounds : (int)gridDim.x;
+  const int t_first = (int)blockIdx.x < t_stride ? (int)blockIdx.x : n_tiles;
   if (threadIdx.x == 0) {
     for (int s = 0; s < GE_STAGES; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], 1); }
     mbar_init(&S.tmem_full_bar, 1);
@@ -352,7 +360,7 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = t_first; t < n_tiles; t += t_stride) {
         const int tile = A.tiles[t];
         const int m0 = (tile >> 16) * GE_BM, n0 = (tile & 0xffff) * GE_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -379,7 +387,7 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      for (int t = t_first; t < n_tiles; t += t_stride, ++it) {
         if (it > 0) {                                     // the epilogue has read the previous tile's accumulators
           mbar_wait(&S.tmem_empty_bar, tphase);
           tphase ^= 1;
@@ -413,7 +421,7 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint32_t fphase = 0;
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     float2 (*tb)[GE_TPITCH] = S.tbuf[ew];
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    for (int t = t_first; t < n_tiles; t += t_stride) {
       const int tile = A.tiles[t];
       const int m0 = (tile >> 16) * GE_BM, n0 = (tile & 0xffff) * GE_BN;
       const bool mirror = A.sym && n0 >= m0 + A.row_global0 + GE_BM;     // off-diagonal block of the whole graph
@@ -644,6 +652,9 @@ int gram_ef_run(const float* x, const float* mu, const mpn_graph* g, int D, int2
   A.not_one_gap = not_one_gap; A.edge_attr = edge_attr; A.refine_list = refine_list; A.refine_count = refine_count;
   A.partials = partials; A.M = M; A.N = N; A.K = D; A.row_global0 = g->row_offset; A.sym = sym;
   A.d_eps2 = (float)((double)D * (double)PAIRWISE_EPS * (double)PAIRWISE_EPS);
+  static int balance = -1;                               // MPN_GRAM_BALANCE=0: every block strides by the grid (diagnostics)
+  if (balance < 0) { const char* e = getenv("MPN_GRAM_BALANCE"); balance = e ? atoi(e) : 1; }
+  A.balance = balance;
   const int tm = (M + GE_BM - 1) / GE_BM, tn = (N + GE_BN - 1) / GE_BN;
   const int grid = (int)min((long long)kNumSMs, (long long)tm * tn);
   if (n_partial_rows) *n_partial_rows = grid;

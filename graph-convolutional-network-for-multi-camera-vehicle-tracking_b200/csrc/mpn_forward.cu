@@ -10,6 +10,7 @@
 #include <mutex>
 #include <new>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -1696,10 +1697,10 @@ static int plan_layout(mpn_fwd_plan& p, void* ws, size_t ws_bytes, size_t* need)
   p.task_part = (G > 1) ? a.take<double>((size_t)g.max_tasks * TASK_PART) : nullptr;
   p.s1_task = a.take<float>((size_t)g.max_tasks * 4);
   p.msg_task = a.take<float>((size_t)g.max_tasks * MPN_DH);
-  p.partials = a.take<double>((size_t)SWEEP_GRID * SUMS);
-  p.partials2 = nullptr;                 // (the per-node moment part now lives in the sweep's own partial rows)
   p.sums = a.take<double>(G * SUMS);
-  p.fin_counter = a.take<unsigned int>(1);
+  p.partials = a.take<double>((size_t)SWEEP_GRID * SUMS);      // partials | fin_counter | fix_sums are adjacent: one memset clears
+  p.partials2 = nullptr;                                       // them (clear_moment_state); the per-node moment part lives in the
+  p.fin_counter = a.take<unsigned int>(1);                     // sweep's own partial rows
   p.fix_sums = a.take<unsigned long long>(8);
   p.peers_dev = a.take<PeerArgs>(1);
   p.n_total_dev = a.take<double>(1);
@@ -1770,6 +1771,12 @@ void mpn_plan_destroy(mpn_fwd_plan* plan) { delete plan; }
 double* mpn_plan_sums(mpn_fwd_plan* plan) { return plan ? plan->sums : nullptr; }
 float* mpn_plan_h_full(mpn_fwd_plan* plan) { return plan ? plan->h_full : nullptr; }
 
+// partial rows, the last-block ticket and the fixed-point sums of the fused edge-feature kernel in one memset (every driver call
+// before the first long kernel of a step is on the host's critical path)
+static cudaError_t clear_moment_state(const mpn_fwd_plan* p, cudaStream_t st) {
+  return cudaMemsetAsync(p->partials, 0, (size_t)((const char*)(p->fix_sums + 8) - (const char*)p->partials), st);
+}
+
 static FinArgs make_fin(const mpn_fwd_plan* p, int stage, bool fused) {
   FinArgs f;
   f.stage = stage;
@@ -1806,16 +1813,17 @@ static float encoder_input_bound(const mpn_fwd_plan* p, int l, int M_total) {
   return b > 0.f ? b * 1.0001f : 1.f;
 }
 
-int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
+// layers [l_begin, l_end) of the node encoder; l_end == n_node_layers also writes h.  The pieces of one forward are enqueued in
+// order on one stream (layer l reads the activations, column scale and shift that layer l-1 left in the plan's buffers).
+static int node_encoder_layers(mpn_fwd_plan* p, const float* x, int l_begin, int l_end, cudaStream_t st) {
   MPN_REQUIRE(p && x, "node_encoder: NULL argument");
-  cudaStream_t st = (cudaStream_t)stream;
   const int M = p->g.n_cols;
   const bool batched = p->n_graphs > 1;
-  MPN_CUDA_OK(cudaMemsetAsync(p->col_counter, 0, sizeof(unsigned int) * ((size_t)p->max_dim / 32 + 1), st));
-  const float* in = x;
+  if (l_begin == 0) MPN_CUDA_OK(cudaMemsetAsync(p->col_counter, 0, sizeof(unsigned int) * ((size_t)p->max_dim / 32 + 1), st));
   float* bufs[2] = {p->act0, p->act1};
-  const float *sc = nullptr, *sh = nullptr;
-  for (int l = 0; l < p->w.n_node_layers; ++l) {
+  const float* in = l_begin == 0 ? x : bufs[(l_begin - 1) & 1];
+  const float *sc = l_begin == 0 ? nullptr : p->colscale, *sh = l_begin == 0 ? nullptr : p->colshift;
+  for (int l = l_begin; l < l_end; ++l) {
     const int K = p->w.node_dims[l], Nc = p->w.node_dims[l + 1];
     float* out = bufs[l & 1];
     bool done = false;
@@ -1846,9 +1854,15 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
     sc = p->colscale;
     sh = p->colshift;
   }
+  if (l_end < p->w.n_node_layers) return MPN_OK;
   mpn::launch(bn_relu_apply_kernel, min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st, in, (long long)M * MPN_DH, MPN_DH, sc, sh, batched ? p->g.node_gid : nullptr, p->h_full);
   MPN_LAUNCH_OK();
   return MPN_OK;
+}
+
+int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
+  MPN_REQUIRE(p && x, "node_encoder: NULL argument");
+  return node_encoder_layers(p, x, 0, p->w.n_node_layers, (cudaStream_t)stream);
 }
 
 // node encoder over this rank's row block only; BatchNorm column sums all-reduced through peer memory per layer;
@@ -1960,8 +1974,7 @@ int mpn_plan_sweep(mpn_fwd_plan* p, int32_t step, int32_t stage, const float* ed
   }
   switch (stage) {
     case MPN_STAGE_ENC0:
-      MPN_CUDA_OK(cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st));
-      MPN_CUDA_OK(cudaMemsetAsync(p->fin_counter, 0, sizeof(unsigned int), st));
+      MPN_CUDA_OK(clear_moment_state(p, st));
       mpn::launch(enc_moments_kernel<0>, flat_grid, SWEEP_THREADS, 0, st, ea, g.n_edges, p->consts, p->w.small, p->partials, make_fin(p, stage, fused),
                   (const int*)nullptr);
       break;
@@ -2083,6 +2096,22 @@ static SideStream* side_stream() {
   return state[dev] == 1 ? &table[dev] : nullptr;
 }
 
+// Timeline of one forward (bench.py / tools): events at the phase boundaries of the caller's stream and at the end of the
+// side-stream encoder.  Off by default (an event record between two kernels ends their programmatic overlap).
+constexpr int TL_MAX = 24;
+static bool g_tl_on = false;
+static cudaEvent_t g_tl_ev[TL_MAX];
+static const char* g_tl_name[TL_MAX];
+static int g_tl_n = 0;
+static void tl_mark(const char* name, cudaStream_t st, bool first = false) {
+  if (!g_tl_on) return;
+  if (first) g_tl_n = 0;
+  if (g_tl_n >= TL_MAX) return;
+  if (!g_tl_ev[g_tl_n] && cudaEventCreate(&g_tl_ev[g_tl_n]) != cudaSuccess) return;
+  if (cudaEventRecord(g_tl_ev[g_tl_n], st) != cudaSuccess) return;
+  g_tl_name[g_tl_n++] = name;
+}
+
 // ef_ws != NULL: edge_attr is an OUTPUT, produced here by mpn_edge_features on the main stream while the node encoder runs on
 // the side stream (both only read x)
 static int forward_impl(const mpn_graph* g, const mpn_weights* w, const float* x, float* edge_attr_rw, int32_t L, int32_t n_cls,
@@ -2102,20 +2131,34 @@ static int forward_impl(const mpn_graph* g, const mpn_weights* w, const float* x
     // the node encoder (tensor-core GEMM chain) depends neither on the edge features nor on the edge-encoder sweeps: it runs
     // on a side stream while the caller's stream does the edge chain
     SideStream* ss = side_stream();
+    tl_mark("start", st, true);
     const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
-    STEP_TRY(mpn_plan_node_encoder(p, x, fork ? ss->stream : st));
-    if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
+    // Enqueue order (measured, profiles/r2_05_enqueue_order.md): first encoder layer (the big GEMM, on the idle device), then the
+    // edge-feature kernels (they head the critical path), then the small later encoder layers, which fit beside the Gram kernel
+    // (it leaves SMs free, gram_ef.cu) and are wanted only at the join after the second sweep.  Without a side stream (or without
+    // fused features) the whole encoder is enqueued first, as stream order then demands.
+    bool encoder_enqueued = false;
+    int enc_done_layers = 0;
+#define ENQUEUE_ENCODER() do { if (!encoder_enqueued) { encoder_enqueued = true; \
+      STEP_TRY(node_encoder_layers(p, x, enc_done_layers, p->w.n_node_layers, fork ? ss->stream : st)); \
+      tl_mark("node_encoder_end(side stream)", fork ? ss->stream : st); \
+      if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; } } } while (0)
+    if (!fork || ef_ws == nullptr) ENQUEUE_ENCODER();
+    else if (p->w.n_node_layers > 1) {
+      // the first (largest) encoder layer starts on the idle device; the later, small ones fit beside the Gram kernel
+      STEP_TRY(node_encoder_layers(p, x, 0, 1, ss->stream));
+      enc_done_layers = 1;
+    }
     bool enc0_done = false;
     if (ef_ws != nullptr && p->n_graphs <= 1) {
       // K1 with the first encoder BatchNorm's moment sums taken in the GEMM epilogue (dense cross-camera graphs): the ENC0 sweep
       // over edge_attr is replaced by one finalize block; for a graph whose layout is decided on the device the sweep is
       // enqueued behind a flag test and returns at once when the fused kernel ran
-      if (cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st) != cudaSuccess ||
-          cudaMemsetAsync(p->fin_counter, 0, sizeof(unsigned int), st) != cudaSuccess ||
-          cudaMemsetAsync(p->fix_sums, 0, sizeof(unsigned long long) * 8, st) != cudaSuccess) { set_error("memset failed"); rc = MPN_ERR_CUDA; goto done; }
+      if (clear_moment_state(p, st) != cudaSuccess) { set_error("memset failed"); rc = MPN_ERR_CUDA; goto done; }
       EfMoments mom;
       mom.partials = p->partials; mom.fixed_sums = p->fix_sums; mom.handled_flag = nullptr; mom.known_fused = 0;
       STEP_TRY(edge_features_impl(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st, &mom));
+      ENQUEUE_ENCODER();
       if (mom.handled_flag != nullptr) {
         if (!mom.known_fused) {
           const int flat_grid = (int)min((long long)SWEEP_GRID, (long long)div_up(g->n_edges > 0 ? g->n_edges : 1, SWEEP_THREADS));
@@ -2137,9 +2180,14 @@ static int forward_impl(const mpn_graph* g, const mpn_weights* w, const float* x
     } else if (ef_ws != nullptr) {
       STEP_TRY(mpn_edge_features(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st));
     }
+    ENQUEUE_ENCODER();
+#undef ENQUEUE_ENCODER
     if (!enc0_done) STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC0, edge_attr, nullptr, nullptr, nullptr, st));
+    tl_mark("edge_features+enc0_end", st);
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
+    tl_mark("enc1_end", st);
     if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
+    tl_mark("joined", st);
   }
   if (L == 0) {
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_APPLY, edge_attr, logits_out, pred_out, prob1_out, st));
@@ -2149,14 +2197,19 @@ static int forward_impl(const mpn_graph* g, const mpn_weights* w, const float* x
     int k = 0;
     for (int step = 1; step <= L; ++step) {
       STEP_TRY(mpn_plan_node_tables(p, step, st));
+      tl_mark("node_tables_end", st);
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_EDGE, edge_attr, nullptr, nullptr, nullptr, st));
+      tl_mark("edge_update_end", st);
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_NODE, edge_attr, nullptr, nullptr, nullptr, st));
+      tl_mark("node_moments_end", st);
       const bool cls = step >= first_class_step;
       const bool last = step == L;
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_APPLY, edge_attr, cls ? logits_out + lstride * k : nullptr,
                               (cls && last) ? pred_out : nullptr, (cls && last) ? prob1_out : nullptr, st));
       if (cls) ++k;
+      tl_mark("node_apply_end", st);
       STEP_TRY(mpn_plan_node_finalize(p, step, st));
+      tl_mark("node_finalize_end", st);
     }
   }
   if (h_out) {
@@ -2234,8 +2287,7 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
 #define ENC0_STAGE() do { \
     bool enc0_done_ = false; \
     if (ef_ws != nullptr) { \
-      if (cudaMemsetAsync(p->partials, 0, sizeof(double) * SWEEP_GRID * SUMS, st) != cudaSuccess || \
-          cudaMemsetAsync(p->fix_sums, 0, sizeof(unsigned long long) * 8, st) != cudaSuccess) { set_error("memset failed"); rc = MPN_ERR_CUDA; goto done; } \
+      if (clear_moment_state(p, st) != cudaSuccess) { set_error("memset failed"); rc = MPN_ERR_CUDA; goto done; } \
       EfMoments mom_; \
       mom_.partials = p->partials; mom_.fixed_sums = p->fix_sums; mom_.handled_flag = nullptr; mom_.known_fused = 0; \
       STEP_TRY(edge_features_impl(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st, &mom_)); \
@@ -2256,16 +2308,21 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
     // while the caller's stream does the two encoder sweeps over edge_attr and their moment exchanges (flag word 0): the two
     // chains touch different exchange slots and meet again before the first node tables.
     SideStream* ss = side_stream();
+    tl_mark("start", st, true);
     const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
     cudaStream_t es = fork ? ss->stream : st;
     STEP_TRY(node_encoder_sharded(p, x, P, seq_c, es));
     mpn::launch(peer_publish_h_kernel, 1, 32, 0, es, P, ++seq_h);
     ++mpn::g_kernel_launches;
     h_pending = true;
+    tl_mark("node_encoder_end(side stream)", es);
     if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
     ENC0_STAGE();
+    tl_mark("edge_features+enc0_end", st);
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
+    tl_mark("enc1_end", st);
     if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }
+    tl_mark("joined", st);
   } else {
     SideStream* ss = side_stream();
     const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
@@ -2283,15 +2340,20 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
         mpn::launch(peer_wait_h_kernel, 1, 32, 0, st, P, seq_h);
         ++mpn::g_kernel_launches;
         h_pending = false;
+        tl_mark("h_arrived", st);
       }
       STEP_TRY(mpn_plan_node_tables(p, step, st));
+      tl_mark("node_tables_end", st);
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_EDGE, edge_attr, nullptr, nullptr, nullptr, st));
+      tl_mark("edge_update_end", st);
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_NODE, edge_attr, nullptr, nullptr, nullptr, st));
+      tl_mark("node_moments_end", st);
       const bool cls = step >= first_class_step;
       const bool last = step == L;
       STEP_TRY(mpn_plan_sweep(p, step, MPN_STAGE_APPLY, edge_attr, cls ? logits_out + lstride * k : nullptr,
                               (cls && last) ? pred_out : nullptr, (cls && last) ? prob1_out : nullptr, st));
       if (cls) ++k;
+      tl_mark("node_apply_end", st);
       const int grid = min(kNumSMs * 8, div_up((long long)g->n_nodes * 32, 256));
       if (!last) {
         mpn::launch(node_finalize_kernel<true>, grid, 256, 0, st, p->g, p->msg_task, p->h_full, P, abs_fix(p));
@@ -2303,6 +2365,7 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
         ++mpn::g_kernel_launches;
       }
       if (cudaGetLastError() != cudaSuccess) { set_error("node_finalize launch failed"); rc = MPN_ERR_CUDA; goto done; }
+      tl_mark("node_finalize_end", st);
     }
   }
   if (h_out) {
@@ -2332,6 +2395,34 @@ int mpn_forward_sharded_with_edge_features(const mpn_graph* g, const mpn_weights
   MPN_REQUIRE(ef_ws != nullptr && edge_attr_out != nullptr, "forward_sharded_with_edge_features: NULL edge-feature buffer / workspace");
   return forward_sharded_impl(g, w, x, edge_attr_out, L, n_cls, total_edges, logits_out, h_out, pred_out, prob1_out, use_tc, peers, ws,
                               ws_bytes, ef_ws, ef_ws_bytes, stream);
+}
+
+int mpn_profile_timeline(int enable) {
+  g_tl_on = enable != 0;
+  g_tl_n = 0;
+  return g_tl_on;
+}
+
+int mpn_profile_timeline_read(float* ms_out, char* names_out, int names_bytes) {
+
+  if (g_tl_n == 0) return 0;
+  for (int i = 0; i < g_tl_n; ++i)
+    if (cudaEventSynchronize(g_tl_ev[i]) != cudaSuccess) return -1;
+  int used = 0;
+  for (int i = 0; i < g_tl_n; ++i) {
+    float ms = 0.f;
+    if (i > 0 && cudaEventElapsedTime(&ms, g_tl_ev[0], g_tl_ev[i]) != cudaSuccess) return -1;
+    if (ms_out) ms_out[i] = ms;
+    if (names_out) {
+      const int len = (int)strlen(g_tl_name[i]);
+      if (used + len + 2 > names_bytes) return -1;
+      memcpy(names_out + used, g_tl_name[i], len);
+      used += len;
+      names_out[used++] = i + 1 < g_tl_n ? '|' : '\0';
+    }
+  }
+  if (names_out && used == 0 && names_bytes > 0) names_out[0] = '\0';
+  return g_tl_n;
 }
 
 int mpn_decide(const float* logits, int64_t E, uint8_t* pred, float* prob1, void* stream) {

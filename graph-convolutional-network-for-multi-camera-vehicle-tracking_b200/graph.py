@@ -58,6 +58,22 @@ def current_stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _NoContext:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_CONTEXT = _NoContext()
+
+
+def _on_device(dev):
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already current (the guard costs several microseconds per call)."""
+    return _NO_CONTEXT if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+
 _FLAG_SLOTS = {}
 
 
@@ -105,12 +121,7 @@ class TrackletGraph:
         self.n_edges = int(edge_index.shape[1])
         self.chunk = int(chunk or choose_chunk(self.n_edges))
         self.max_tasks = self.n_edges // self.chunk + self.n_nodes
-        i32 = dict(dtype=torch.int32, device=dev)
-        self.rowptr = torch.empty(self.n_nodes + 1, **i32)
-        self.col = torch.empty(max(self.n_edges, 1), **i32)
-        self.taskptr = torch.empty(self.n_nodes + 1, **i32)
-        self.task_row = torch.empty(max(self.max_tasks, 1), **i32)
-        self.n_tasks = torch.zeros(1, **i32)
+        ptrs = self._alloc_tables(dev)
         self.perm = None
         # batched small graphs: ptr = node offsets [G+1] (PyG ``Batch.ptr``); BatchNorm statistics are then per graph
         self.n_graphs, self.node_gid, self.graph_nptr, self.max_graph_nodes = 1, None, None, 0
@@ -133,8 +144,7 @@ class TrackletGraph:
                 raise ValueError("every graph of a batch needs at least 2 nodes and 2 edges (BatchNorm over one value "
                                  "raises in the reference)")
         self.struct = _lib.MpnGraph(self.n_nodes, self.n_cols, self.row_offset, self.chunk, self.n_edges, self.max_tasks, 0,
-                                    self.rowptr.data_ptr(), self.col.data_ptr(), self.taskptr.data_ptr(),
-                                    self.task_row.data_ptr(), self.n_tasks.data_ptr(), self.n_graphs, self.max_graph_nodes,
+                                    ptrs[0], ptrs[4], ptrs[1], ptrs[3], ptrs[2], self.n_graphs, self.max_graph_nodes,
                                     self.node_gid.data_ptr() if self.node_gid is not None else None,
                                     self.graph_nptr.data_ptr() if self.graph_nptr is not None else None)
         ei = edge_index
@@ -147,7 +157,7 @@ class TrackletGraph:
             raise ValueError("validate must be 'sync' or 'deferred'")
         if validate == "deferred":
             slot = _flag_slot(dev)
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 _lib.check(_lib.lib().mpn_graph_build_deferred(C.byref(self.struct), ei.data_ptr(), slot[0].data_ptr(),
                                                                slot[1].data_ptr(), stream))
             ev = torch.cuda.Event()
@@ -168,6 +178,32 @@ class TrackletGraph:
                 ei = ei[:, perm].contiguous()
                 _lib.check(_lib.lib().mpn_graph_build(C.byref(self.struct), ei.data_ptr(), stream))
         self._keepalive = ei
+
+    # The five int32 tables live in ONE allocation (building a graph is on the host's critical path of every step: one
+    # torch.empty instead of five, no fill kernel); .rowptr / .taskptr / .n_tasks / .task_row / .col are views made on first use.
+    _SECTIONS = {"rowptr": 0, "taskptr": 1, "n_tasks": 2, "task_row": 3, "col": 4}
+
+    def _alloc_tables(self, dev):
+        n1 = self.n_nodes + 1
+        sizes = (n1, n1, 1, max(self.max_tasks, 1), max(self.n_edges, 1))
+        offs, o = [], 0
+        for n in sizes:
+            offs.append(o)
+            o += (n + 3) & ~3                                   # 16-byte aligned sections
+        self._tables = torch.empty(o, dtype=torch.int32, device=dev)
+        self._sections = tuple(zip(offs, sizes))
+        base = self._tables.data_ptr()
+        return tuple(base + 4 * off for off in offs)
+
+    def __getattr__(self, name):                                # only reached when the attribute is not set
+        idx = TrackletGraph._SECTIONS.get(name)
+        sections = self.__dict__.get("_sections")
+        if idx is None or sections is None:
+            raise AttributeError(name)
+        off, n = sections[idx]
+        view = self._tables[off:off + n]
+        self.__dict__[name] = view
+        return view
 
     def validate(self):
         """Deferred validation: wait for the build, then raise what ``validate='sync'`` would have raised.  No-op otherwise."""
@@ -211,19 +247,13 @@ class TrackletGraph:
             raise ValueError("bad row block")
         self.chunk = int(chunk or choose_chunk(self.n_edges))
         self.max_tasks = self.n_edges // self.chunk + self.n_nodes
-        i32 = dict(dtype=torch.int32, device=dev)
-        self.rowptr = torch.empty(self.n_nodes + 1, **i32)
-        self.col = torch.empty(max(self.n_edges, 1), **i32)
-        self.taskptr = torch.empty(self.n_nodes + 1, **i32)
-        self.task_row = torch.empty(max(self.max_tasks, 1), **i32)
-        self.n_tasks = torch.zeros(1, **i32)
+        ptrs = self._alloc_tables(dev)
         self.perm = None
         self.n_graphs, self.node_gid, self.graph_nptr, self.max_graph_nodes = 1, None, None, 0
         self.edge_index = torch.empty(2, self.n_edges, dtype=torch.int64, device=dev) if materialize_edge_index else None
         self.struct = _lib.MpnGraph(self.n_nodes, self.n_cols, self.row_offset, self.chunk, self.n_edges, self.max_tasks, 0,
-                                    self.rowptr.data_ptr(), self.col.data_ptr(), self.taskptr.data_ptr(),
-                                    self.task_row.data_ptr(), self.n_tasks.data_ptr(), 1, 0, None, None)
-        with torch.cuda.device(dev):
+                                    ptrs[0], ptrs[4], ptrs[1], ptrs[3], ptrs[2], 1, 0, None, None)
+        with _on_device(dev):
             _lib.check(L.mpn_graph_build_cross_camera(C.byref(self.struct), cam_ptr.ctypes.data, n_cams,
                                                       self.edge_index.data_ptr() if materialize_edge_index else None,
                                                       current_stream_ptr(dev)))

@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .graph import current_stream_ptr, graph_for, workspace
+from .graph import _on_device, current_stream_ptr, graph_for, workspace
 
 USE_TENSOR_CORES = True
 
@@ -367,7 +367,7 @@ class MOTMPNet(nn.Module):
             lib = _lib.lib()
             need = lib.mpn_forward_workspace_bytes(g.ref, C.byref(W), L)
             ws = workspace("forward", dev, need)
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 if fused_features:
                     ef_ws = workspace("edge_features", dev, lib.mpn_edge_features_workspace_bytes(g.ref, x.shape[1]))
                     _lib.check(lib.mpn_forward_with_edge_features(

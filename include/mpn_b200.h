@@ -128,6 +128,14 @@ int mpn_graph_build_cross_camera(mpn_graph* g, const int32_t* cam_ptr_host, int3
  * the duration of the last such launch in milliseconds (-1 if none).  Off by default: the events break the launch overlap. */
 int mpn_profile_gram(int enable);
 float mpn_profile_gram_ms(void);
+/* Measurement hook (bench.py, tools/): while enabled, mpn_forward / mpn_forward_with_edge_features / mpn_forward_sharded* record a CUDA
+ * event at every phase boundary of the caller's stream (edge features + first BatchNorm, second encoder sweep, join with the
+ * side-stream node encoder, arrival of the peers' rows, node tables, the three sweeps of every step, node finalize) and one at the
+ * end of the side-stream encoder.  mpn_profile_timeline_read waits for the last forward's events and returns their number n;
+ * ms_out[i] = time from the first event to event i, names_out = the n names joined by '|'.  Off by default: an event between
+ * two kernels ends their programmatic overlap.  Not thread safe. */
+int mpn_profile_timeline(int enable);
+int mpn_profile_timeline_read(float* ms_out, char* names_out, int names_bytes);
 size_t mpn_edge_features_workspace_bytes(const mpn_graph* g, int32_t D);
 int mpn_edge_features(const mpn_graph* g, const float* x_dev, int32_t D, float* edge_attr_dev,
                       int use_tensor_cores, void* workspace_dev, size_t workspace_bytes, void* stream);
