@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libmpn_b200.so")
 MPN_OK, MPN_ERR_INVALID, MPN_ERR_CUDA, MPN_ERR_UNSORTED, MPN_ERR_WORKSPACE, MPN_ERR_NO_DEVICE = range(6)
 MPN_DE, MPN_DH, MPN_MAX_NODE_LAYERS = 4, 32, 8
 MPN_SUMS_DOUBLES = 96
-ABI_VERSION = 5             # MPN_B200_ABI_VERSION of include/mpn_b200.h (bumped when a struct or a signature changes)
+ABI_VERSION = 6             # MPN_B200_ABI_VERSION of include/mpn_b200.h (bumped when a struct or a signature changes)
 STAGE_ENC0, STAGE_ENC1, STAGE_EDGE, STAGE_NODE, STAGE_APPLY = range(5)
 POST_CUT, POST_PRUNE, POST_SPLIT = 1, 2, 4
 
@@ -56,7 +56,9 @@ class MpnPeerCtx(C.Structure):
                 ("flags", C.c_void_p * MPN_MAX_PEERS), ("h", C.c_void_p * MPN_MAX_PEERS),
                 ("cstats", C.c_void_p * MPN_MAX_PEERS),
                 ("seq_moments", C.c_uint64), ("seq_h", C.c_uint64), ("seq_c", C.c_uint64),
-                ("shard_node_encoder", C.c_int32), ("reserved", C.c_int32)]
+                ("shard_node_encoder", C.c_int32), ("reserved", C.c_int32),
+                ("edge_attr", C.c_void_p * MPN_MAX_PEERS), ("node_tables", C.c_void_p * MPN_MAX_PEERS),
+                ("block_start", C.c_int32 * (MPN_MAX_PEERS + 1)), ("reserved2", C.c_int32), ("seq_t", C.c_uint64)]
 MPN_PEER_CSTAT_COLS = 1024
 
 
@@ -87,6 +89,7 @@ _PROTOS = {
     "mpn_graph_build_cross_camera": (C.c_int, [C.POINTER(MpnGraph), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mpn_profile_gram": (C.c_int, [C.c_int]),
     "mpn_profile_gram_ms": (C.c_float, []),
+    "mpn_shared_gram_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_profile_timeline": (C.c_int, [C.c_int]),
     "mpn_profile_timeline_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "mpn_edge_features_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph), C.c_int32]),

@@ -145,4 +145,25 @@ __device__ __forceinline__ int ldg_stream_i32(const int* p) {
 }
 #endif
 
+// ---- sequence flags in NVLink peer memory (sharded runs) ----
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// wait until *p >= seq; a protocol bug or a dead peer must surface as a trap, never as a hung GPU
+__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long seq) {
+  if (ld_acquire_sys(p) >= seq) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (ld_acquire_sys(p) < seq) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) __trap();
+  }
+}
+
+
 }  // namespace mpn

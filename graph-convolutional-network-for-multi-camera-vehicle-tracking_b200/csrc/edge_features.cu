@@ -7,6 +7,8 @@
 // The reference gathers two [E,D] copies (8 KB per edge each); here the only per-edge traffic is one Gram read and
 // one 8-byte write.  Pairs whose squared distance still cancels (d^2 < 25% of |a'|^2+|b'|^2: same-identity pairs)
 // are recomputed directly from the rows, exactly as the reference sums them.
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -133,13 +135,15 @@ __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_grap
                                                                   const int* __restrict__ refine_count,
                                                                   float2* __restrict__ edge_attr,
                                                                   unsigned long long* __restrict__ fixed_sums,
-                                                                  const int* __restrict__ not_one_gap) {
+                                                                  const int* __restrict__ not_one_gap, const GeShare sh) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n = *refine_count;
   const bool with_sums = fixed_sums != nullptr && not_one_gap != nullptr && *not_one_gap == 0;
+  // shared Gram (kernels.h): a listed pair is one this rank computed for both directions; the mirrored entry goes to the owner
+  const bool shared = sh.mode != nullptr && *sh.mode == 2 && not_one_gap != nullptr && *not_one_gap == 0;
   for (int i = gwarp; i < n; i += nwarps) {
     const int e = refine_list[i];
     int lo = 0, hi = g.n_nodes;                       // row = last r with rowptr[r] <= e
@@ -147,29 +151,50 @@ __global__ void __launch_bounds__(256) edge_feature_refine_kernel(const mpn_grap
       const int mid = (lo + hi) >> 1;
       if (g.rowptr[mid] <= e) lo = mid; else hi = mid;
     }
+    const int cnode = g.col[e];
     const float* a = x + (size_t)(lo + g.row_offset) * D;
-    const float* b = x + (size_t)g.col[e] * D;
-    double d2 = 0.0, ab = 0.0, aa = 0.0, bb = 0.0;
+    const float* b = x + (size_t)cnode * D;
+    double d2 = 0.0, d2m = 0.0, ab = 0.0, aa = 0.0, bb = 0.0;
     for (int k = lane; k < D; k += 32) {
       const float av = a[k], bv = b[k];
       const float df = av - bv + PAIRWISE_EPS;
+      const float dfm = bv - av + PAIRWISE_EPS;
       d2 += (double)df * df;
+      d2m += (double)dfm * dfm;
       ab += (double)av * bv;
       aa += (double)av * av;
       bb += (double)bv * bv;
     }
     d2 = warp_sum(d2); ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
+    if (shared) d2m = warp_sum(d2m);
     if (lane == 0) {
       const double denom = fmax(sqrt(aa) * sqrt(bb), (double)COSINE_EPS);
       const float2 o = make_float2((float)sqrt(d2), (float)(1.0 - ab / denom));
       edge_attr[e] = o;
+      const double sc = 1099511627776.0;                              // 2^40
       if (with_sums) {
-        const double fa = o.x, fb = o.y, sc = 1099511627776.0;        // 2^40
+        const double fa = o.x, fb = o.y;
         atomicAdd(fixed_sums + 0, (unsigned long long)__double2ll_rn(fa * sc));
         atomicAdd(fixed_sums + 1, (unsigned long long)__double2ll_rn(fb * sc));
         atomicAdd(fixed_sums + 2, (unsigned long long)__double2ll_rn(fa * fa * sc));
         atomicAdd(fixed_sums + 3, (unsigned long long)__double2ll_rn(fa * fb * sc));
         atomicAdd(fixed_sums + 4, (unsigned long long)__double2ll_rn(fb * fb * sc));
+      }
+      if (shared) {                                                   // (cnode -> row) in the shard of cnode's owner
+        int owner = 0;
+        while (owner + 1 < sh.world && cnode >= sh.blk[owner + 1]) ++owner;
+        const int4 te = sh.tab[sh.rank][cnode];                       // (edge base, gap start, gap length) of row cnode
+        const int rnode = lo + g.row_offset;
+        const float2 om = make_float2((float)sqrt(d2m), o.y);
+        sh.ea[owner][te.x + rnode - (rnode >= te.y + te.z ? te.z : 0)] = om;
+        if (with_sums) {
+          const double fa = om.x, fb = om.y;
+          atomicAdd(fixed_sums + 0, (unsigned long long)__double2ll_rn(fa * sc));
+          atomicAdd(fixed_sums + 1, (unsigned long long)__double2ll_rn(fb * sc));
+          atomicAdd(fixed_sums + 2, (unsigned long long)__double2ll_rn(fa * fa * sc));
+          atomicAdd(fixed_sums + 3, (unsigned long long)__double2ll_rn(fa * fb * sc));
+          atomicAdd(fixed_sums + 4, (unsigned long long)__double2ll_rn(fb * fb * sc));
+        }
       }
     }
   }
@@ -189,6 +214,7 @@ struct EfLayout {
   int rows_per_block;
   int2* gap;                       // fused distance epilogue: one-gap table of the rows
   int* not_one_gap;
+  int* share_mode;
   GeWorkspace ge;                  // planes / records / tile list of the fused kernel (gram_ef.cu)
   bool fused_possible;
   size_t total;
@@ -215,6 +241,7 @@ static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) 
   L.amax_bits = a.take<unsigned int>(1);
   L.mu_ticket = a.take<unsigned int>(64);                    // one per 128-column tile (D <= 8192)
   L.not_one_gap = a.take<int>(1);
+  L.share_mode = a.take<int>(1);                             // GeShare::mode (adjacent: cleared by the same memset)
   L.gemm_ws_bytes = batched ? gemm_tc_workspace_bytes(1, g->n_cols, D) : gemm_tc_workspace_bytes((int)rows, g->n_cols, D);
   L.gemm_ws = L.gemm_ws_bytes ? (void*)a.take<char>(L.gemm_ws_bytes) : nullptr;
   L.gap = a.take<int2>((size_t)(g->n_nodes > 0 ? g->n_nodes : 1));
@@ -234,7 +261,7 @@ static EfLayout ef_layout(const mpn_graph* g, int D, void* ws, size_t ws_bytes) 
 //   handled    out: device flag, 0 = the fused kernel produced features AND moments, != 0 = the caller must sweep edge_attr itself;
 //              nullptr when that is already known on the host (known_fused tells which)
 int edge_features_impl(const mpn_graph* g, const float* x, int32_t D, float* edge_attr, int use_tc, void* ws, size_t ws_bytes,
-                       cudaStream_t st, EfMoments* moments) {
+                       cudaStream_t st, EfMoments* moments, const GeShare* share) {
   MPN_REQUIRE(g && x && D > 0 && ws, "edge_features: NULL argument");
   MPN_REQUIRE(edge_attr || g->n_edges == 0, "edge_features: NULL output");
   MPN_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
@@ -245,7 +272,7 @@ int edge_features_impl(const mpn_graph* g, const float* x, int32_t D, float* edg
   }
   if (moments) { moments->handled_flag = nullptr; moments->known_fused = 0; }
   if (g->n_edges == 0) return MPN_OK;
-  MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, 4 * 256, st));        // refine_count, amax_bits, mean ticket, not_one_gap (adjacent slices)
+  MPN_CUDA_OK(cudaMemsetAsync(L.refine_count, 0, 5 * 256, st));        // refine_count, amax_bits, mean ticket, not_one_gap, share mode (adjacent slices)
   if ((D % 4) == 0 && D <= 8192 && (((uintptr_t)x) & 15) == 0) {          // (64 ticket slots: one per 128-column tile)
     MPN_TRY(ge_col_mean(x, g->n_cols, D, L.mu_part, L.mu_ticket, L.mu, st));
   } else {
@@ -273,7 +300,7 @@ int edge_features_impl(const mpn_graph* g, const float* x, int32_t D, float* edg
                                                            L.refine_count, (const int*)nullptr);
     MPN_LAUNCH_OK();
     mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr,
-                (unsigned long long*)nullptr, (const int*)nullptr);
+                (unsigned long long*)nullptr, (const int*)nullptr, GeShare{});
     MPN_LAUNCH_OK();
     return MPN_OK;
   }
@@ -283,11 +310,18 @@ int edge_features_impl(const mpn_graph* g, const float* x, int32_t D, float* edg
   // device flag first and one set returns at once.
   const bool fused = use_tc && L.fused_possible;
   const bool known_one_gap = fused && g->layout_hint == MPN_LAYOUT_ONE_GAP;
+  GeShare sh;
+  memset(&sh, 0, sizeof(sh));
+  if (share != nullptr) {
+    MPN_REQUIRE(fused, "shared Gram needs the fused edge-feature path (tensor cores, D a multiple of 64)");
+    sh = *share;
+    sh.mode = L.share_mode;
+  }
   const int* run_gather = nullptr;                   // old path: unconditional
   if (fused) {
     int n_rows = 0;
     MPN_TRY(gram_ef_run(x, L.mu, g, D, L.gap, L.not_one_gap, (float2*)edge_attr, L.refine_list, L.refine_count,
-                        moments ? moments->partials : nullptr, &n_rows, L.ge, st));
+                        moments ? moments->partials : nullptr, &n_rows, L.ge, st, share ? &sh : nullptr));
     if (moments) { moments->handled_flag = L.not_one_gap; moments->known_fused = known_one_gap ? 1 : 0; }
     run_gather = L.not_one_gap;
   }
@@ -308,7 +342,7 @@ int edge_features_impl(const mpn_graph* g, const float* x, int32_t D, float* edg
     }
   }
   mpn::launch(edge_feature_refine_kernel, kNumSMs * 4, 256, 0, st, *g, x, D, L.refine_list, L.refine_count, (float2*)edge_attr,
-              moments ? moments->fixed_sums : (unsigned long long*)nullptr, fused ? (const int*)L.not_one_gap : (const int*)nullptr);
+              moments ? moments->fixed_sums : (unsigned long long*)nullptr, fused ? (const int*)L.not_one_gap : (const int*)nullptr, sh);
   MPN_LAUNCH_OK();
   return MPN_OK;
 }
@@ -318,6 +352,18 @@ int edge_features_impl(const mpn_graph* g, const float* x, int32_t D, float* edg
 using namespace mpn;
 
 extern "C" {
+
+// tests / bench: which way the last mpn_forward_sharded_with_edge_features on this workspace went (synchronises the stream):
+// 2 = shared symmetric Gram, 0 = every rank its own rows, -1 = error
+int mpn_shared_gram_mode(const mpn_graph* g, int32_t D, const void* ws, size_t ws_bytes, void* stream) {
+  if (g == nullptr || ws == nullptr) return -1;
+  mpn::EfLayout L = mpn::ef_layout(g, D, const_cast<void*>(ws), ws_bytes);
+  if (L.total > ws_bytes) return -1;
+  int mode = -1;
+  if (cudaMemcpyAsync(&mode, L.share_mode, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -1;
+  return mode;
+}
 
 size_t mpn_edge_features_workspace_bytes(const mpn_graph* g, int32_t D) {
   if (!g || D <= 0) return 0;

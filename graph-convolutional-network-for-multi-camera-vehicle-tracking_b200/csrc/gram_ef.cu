@@ -26,6 +26,7 @@
 #include <cuda_fp16.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -53,6 +54,9 @@ struct GeSmem {
   float4 cs_a[GE_BN];
   int4 cs_b[GE_BN];
   int4 rowinfo[GE_BM];                                       // rows of the tile: (edge base before the gap, after the gap, gap end, valid)
+  // shared Gram (GeShare): edge_attr of the column's owner, and the rows [lo, hi) (global ids) whose pair with the column is this rank's
+  float2* cs_ptr[GE_BN];
+  int2 cs_lohi[GE_BN];
   float2 tbuf[GE_EPI_WARPS][32][GE_TPITCH];
 };
 constexpr int GE_SMEM_BYTES = GE_STAGES * GE_STAGE_BYTES + 1024 + (int)sizeof(GeSmem);
@@ -256,14 +260,65 @@ __global__ void __launch_bounds__(32 * GE_CS_WARPS) ge_center_split_kernel(const
   }
 }
 
+
+// ---- shared Gram: which rank computes a pair (kernels.h, GeShare) ----
+__device__ __forceinline__ int ge_owner(const GeShare& sh, int c) {
+  int s = 0;
+  while (s + 1 < sh.world && c >= sh.blk[s + 1]) ++s;
+  return s;
+}
+// rows [lo, hi) (global ids) of THIS rank that compute their pair with column c (owned by rank s); hi == 0: none
+__device__ __forceinline__ int2 ge_row_range(const GeShare& sh, int s, int c) {
+  const int R = sh.rank, W = sh.world;
+  if (s == R) return make_int2(0, c);                                      // own block: r < c
+  const int d = (s - R + W) % W;
+  if (2 * d < W) return make_int2(0, 0x7fffffff);
+  if (2 * d > W) return make_int2(0, 0);
+  if (R < s) return (c < ((sh.blk[s] + sh.blk[s + 1]) >> 1)) ? make_int2(0, 0x7fffffff) : make_int2(0, 0);
+  return make_int2((sh.blk[R] + sh.blk[R + 1]) >> 1, 0x7fffffff);
+}
+
+// one block: push (edge base, gap start, gap length, not_one_gap) of my rows into every rank's node table, raise my flag on every
+// rank, wait for every rank's flag in my own memory, then *mode = 2 iff every rank reported dense cross-camera rows
+__global__ void __launch_bounds__(1024) ge_share_exchange_kernel(const GeShare sh, const int* __restrict__ rowptr, const int2* __restrict__ gap,
+                                                                 int M, const int* __restrict__ not_one_gap) {
+  pdl_wait();
+  const int bad = *not_one_gap;
+  const int g0 = sh.blk[sh.rank];
+  for (int r = threadIdx.x; r < M; r += blockDim.x) {
+    const int2 gp = bad ? make_int2(0, 0) : gap[r];
+    const int4 e = make_int4(rowptr[r], gp.x, gp.y, bad);
+    for (int p = 0; p < sh.world; ++p) sh.tab[p][g0 + r] = e;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < sh.world) {
+    st_release_sys(sh.flags[threadIdx.x] + 3 * MPN_MAX_PEERS + sh.rank, sh.seq);
+    wait_flag(sh.flags[sh.rank] + 3 * MPN_MAX_PEERS + threadIdx.x, sh.seq);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int any_bad = 0;
+    for (int p = 0; p < sh.world; ++p) {
+      if (sh.blk[p + 1] <= sh.blk[p]) { any_bad = 1; continue; }          // a rank without rows: no shared mode
+      int4 e;
+      asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(sh.tab[sh.rank] + sh.blk[p]));
+      any_bad |= e.w;
+    }
+    *sh.mode = any_bad ? 0 : 2;
+  }
+}
+
 // ---- tile list: the 128 x 128 blocks that hold at least one edge, in a fixed order (one block, ordered compaction)
 // sym: the row block is the whole graph -> blocks on or above the diagonal only (the epilogue writes both directions).
 // A block is empty iff all of its rows belong to ONE camera whose node range covers all of its columns.
+// shared (GeShare::mode == 2): the blocks that hold at least one pair this rank computes.
 __global__ void __launch_bounds__(1024) ge_tile_list_kernel(const int2* __restrict__ gap, int M, int N, int row_global0, int sym,
                                                             int* __restrict__ tiles, int* __restrict__ n_tiles,
-                                                            const int* __restrict__ not_one_gap) {
+                                                            const int* __restrict__ not_one_gap, const GeShare sh) {
   pdl_wait();
   if (*not_one_gap != 0) { if (threadIdx.x == 0) *n_tiles = 0; return; }
+  const bool shared = sh.mode != nullptr && *sh.mode == 2;
   __shared__ int warp_cnt[32];
   __shared__ int base;
   const int tm = (M + GE_BM - 1) / GE_BM, tn = (N + GE_BN - 1) / GE_BN;
@@ -278,6 +333,17 @@ __global__ void __launch_bounds__(1024) ge_tile_list_kernel(const int2* __restri
       ti = t / tn; tj = t % tn;
       const int m0 = ti * GE_BM, n0 = tj * GE_BN;
       keep = !(sym && n0 + GE_BN <= m0 + row_global0);             // strictly below the diagonal: written by the mirror
+      if (shared) {
+        keep = false;
+        const int r_lo = row_global0 + m0, r_hi = row_global0 + min(m0 + GE_BM, M);      // global rows [r_lo, r_hi)
+        const int c_hi = min(n0 + GE_BN, N);
+        for (int p = 0; p < sh.world && !keep; ++p) {
+          const int a = max(n0, sh.blk[p]), b = min(c_hi, sh.blk[p + 1]);                 // this block's columns owned by rank p
+          if (a >= b) continue;
+          const int2 first = ge_row_range(sh, p, a), last = ge_row_range(sh, p, b - 1);   // the range is monotone in c within a block
+          keep = (r_lo < first.y && r_hi > first.x) || (r_lo < last.y && r_hi > last.x);
+        }
+      }
       if (keep) {
         const int2 ga = gap[m0], gb = gap[min(m0 + GE_BM, M) - 1];
         const bool one_cam = ga.x == gb.x && ga.y == gb.y;
@@ -319,13 +385,17 @@ struct GeArgs {
   int row_global0;            // global node id of local row 0
   int sym;
   float d_eps2;               // D * eps^2
+  GeShare sh;                 // SHARED kernel only
+  const int4* node_tab;       // SHARED: this rank's copy of the node table [N]
 };
 
+template <bool SHARED>
 __global__ void __launch_bounds__(GE_THREADS, 1)
 gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GeArgs A) {
   pdl_wait();
   if (*A.not_one_gap != 0) return;
+  if (A.sh.mode != nullptr && (*A.sh.mode == 2) != SHARED) return;       // sharded runs enqueue both variants: the exchange decides
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzled tiles, computed on the shared-space address so that the pointers keep their state space
   // (a round trip through uintptr_t makes every later access a generic LD/ST)
@@ -424,7 +494,7 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     for (int t = t_first; t < n_tiles; t += t_stride) {
       const int tile = A.tiles[t];
       const int m0 = (tile >> 16) * GE_BM, n0 = (tile & 0xffff) * GE_BN;
-      const bool mirror = A.sym && n0 >= m0 + A.row_global0 + GE_BM;     // off-diagonal block of the whole graph
+      const bool mirror = SHARED || (A.sym && n0 >= m0 + A.row_global0 + GE_BM);     // off-diagonal block of the whole graph
       // stage the per-column and per-row tables of this tile (the previous tile's epilogue has passed the named barrier below)
       if (et < GE_BN) {
         const int c = n0 + et;
@@ -434,11 +504,23 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           ca = __ldg(A.rec + c);
           cb.x = __float_as_int(__ldg(A.scale_inv + c));
           const int lc = c - A.row_global0;                // the column as a row of this block (mirrored entries)
-          if (mirror && lc >= 0 && lc < A.M) {
+          if (SHARED) {
+            const int owner = ge_owner(A.sh, c);
+            const int2 range = ge_row_range(A.sh, owner, c);
+            if (range.y > 0) {
+              const int4 te = __ldg(A.node_tab + c);       // (edge base, gap start, gap length) of row c in its owner's shard
+              cb.y = te.x; cb.z = te.x - te.z; cb.w = te.y + te.z;
+            }
+            S.cs_ptr[et] = A.sh.ea[owner];
+            S.cs_lohi[et] = range;
+          } else if (mirror && lc >= 0 && lc < A.M) {
             const int2 gp = __ldg(A.gap + lc);
             const int rp = __ldg(A.rowptr + lc);
             cb.y = rp; cb.z = rp - gp.y; cb.w = gp.x + gp.y;
           }
+        } else if (SHARED) {
+          S.cs_ptr[et] = A.edge_attr;
+          S.cs_lohi[et] = make_int2(0, 0);
         }
         S.cs_a[et] = ca;
         S.cs_b[et] = cb;
@@ -512,7 +594,11 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const float u = fmaf(-2.f, g, tsum) + A.d_eps2;
             const float wv = ea - ca.y;
             const float d2d = u + wv, d2m = u - wv;
-            const bool cross = (cmask >> j) & 1u;
+            bool cross = (cmask >> j) & 1u;
+            if (SHARED) {                                   // pairs of this column that another rank computes are not mine
+              const int2 range = S.cs_lohi[c0 + j];
+              cross = cross && grow >= range.x && grow < range.y;
+            }
             const bool cancel = !(fminf(d2d, d2m) >= REFINE_FRACTION * tsum);          // also true for NaN (degenerate rows)
             const float rs = rsqrt_approx(fmaxf(d2d, 1e-30f));
             const float dd = d2d * rs;
@@ -526,8 +612,10 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const float sd = dds + dms;
               s_a += sd; s_aa = fmaf(dds, dds, fmaf(dms, dms, s_aa)); s_b = fmaf(2.f, coss, s_b); s_bb = fmaf(2.f * coss, coss, s_bb);
               s_ab = fmaf(coss, sd, s_ab);
-              if (cross && cb.y >= 0)                       // (j -> i): consecutive lanes = consecutive edges of row j
-                A.edge_attr[grow + (grow >= cb.w ? cb.z : cb.y)] = make_float2(dm, cosv);
+              if (cross && cb.y >= 0) {                     // (j -> i): consecutive lanes = consecutive edges of row j
+                float2* dst = SHARED ? S.cs_ptr[c0 + j] : A.edge_attr;     // SHARED: the owner of row j, over NVLink if it is a peer
+                dst[grow + (grow >= cb.w ? cb.z : cb.y)] = make_float2(dm, cosv);
+              }
             } else {
               s_a += dds; s_aa = fmaf(dds, dds, s_aa); s_b += coss; s_bb = fmaf(coss, coss, s_bb); s_ab = fmaf(coss, dds, s_ab);
             }
@@ -554,7 +642,7 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             flagged &= flagged - 1;
             const int col = cbase + j;
             const int4 cb = S.cs_b[c0 + j];
-            const bool mir = mirror && cb.y >= 0;
+            const bool mir = !SHARED && mirror && cb.y >= 0;      // SHARED: edge_feature_refine writes both directions itself
             const int slot = atomicAdd(A.refine_count, mir ? 2 : 1);
             A.refine_list[slot] = col + (col >= gap1 ? rp_row - (gap1 - gap0) : rp_row);
             if (mir) A.refine_list[slot + 1] = grow + (grow >= cb.w ? cb.z : cb.y);
@@ -621,7 +709,8 @@ int ge_col_mean(const float* x, int n, int D, double* part, unsigned int* ticket
 }
 
 int gram_ef_run(const float* x, const float* mu, const mpn_graph* g, int D, int2* gap, int* not_one_gap, float2* edge_attr,
-                int* refine_list, int* refine_count, double* partials, int* n_partial_rows, const GeWorkspace& L, cudaStream_t st) {
+                int* refine_list, int* refine_count, double* partials, int* n_partial_rows, const GeWorkspace& L, cudaStream_t st,
+                const GeShare* share) {
   const int N = g->n_cols, M = g->n_nodes;
   MPN_REQUIRE(gram_ef_shape_ok(M, N, D), "fused edge features: unsupported shape M=%d N=%d D=%d", M, N, D);
   const int cs_grid = min(kNumSMs * 16, div_up((long long)N, GE_CS_WARPS));
@@ -634,8 +723,20 @@ int gram_ef_run(const float* x, const float* mu, const mpn_graph* g, int D, int2
                 gap, not_one_gap);
   }
   MPN_LAUNCH_OK();
+  GeShare sh;
+  memset(&sh, 0, sizeof(sh));
+  if (share != nullptr) {
+    sh = *share;
+    MPN_REQUIRE(sh.world >= 2 && sh.world <= MPN_MAX_PEERS && sh.rank >= 0 && sh.rank < sh.world && sh.mode != nullptr, "shared Gram: bad rank/world");
+    MPN_REQUIRE(sh.blk[sh.rank] == g->row_offset && sh.blk[sh.rank + 1] == g->row_offset + M && sh.blk[0] == 0 && sh.blk[sh.world] == N,
+                "shared Gram: the row blocks do not match the graph (block [%d,%d), graph rows [%d,%d) of %d)", sh.blk[sh.rank],
+                sh.blk[sh.rank + 1], g->row_offset, g->row_offset + M, N);
+    MPN_REQUIRE((float2*)sh.ea[sh.rank] == edge_attr, "shared Gram: edge_attr must be this rank's peer-visible buffer");
+    mpn::launch(ge_share_exchange_kernel, 1, 1024, 0, st, sh, g->rowptr, (const int2*)gap, M, (const int*)not_one_gap);
+    MPN_LAUNCH_OK();
+  }
   const int sym = (g->row_offset == 0 && M == N) ? 1 : 0;
-  mpn::launch(ge_tile_list_kernel, 1, 1024, 0, st, gap, M, N, g->row_offset, sym, L.tiles, L.n_tiles, not_one_gap);
+  mpn::launch(ge_tile_list_kernel, 1, 1024, 0, st, gap, M, N, g->row_offset, sym, L.tiles, L.n_tiles, not_one_gap, sh);
   MPN_LAUNCH_OK();
   CUtensorMap ah, al, bh, bl;
   MPN_TRY(make_tma_map_2d(&ah, L.hi + (size_t)g->row_offset * D, M, D, GE_BM, true));
@@ -644,7 +745,8 @@ int gram_ef_run(const float* x, const float* mu, const mpn_graph* g, int D, int2
   MPN_TRY(make_tma_map_2d(&bl, L.lo, N, D, GE_BN, true));
   static bool configured = false;
   if (!configured) {
-    MPN_CUDA_OK(cudaFuncSetAttribute(gram_ef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GE_SMEM_BYTES));
+    MPN_CUDA_OK(cudaFuncSetAttribute(gram_ef_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GE_SMEM_BYTES));
+    MPN_CUDA_OK(cudaFuncSetAttribute(gram_ef_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GE_SMEM_BYTES));
     configured = true;
   }
   GeArgs A;
@@ -652,18 +754,24 @@ int gram_ef_run(const float* x, const float* mu, const mpn_graph* g, int D, int2
   A.not_one_gap = not_one_gap; A.edge_attr = edge_attr; A.refine_list = refine_list; A.refine_count = refine_count;
   A.partials = partials; A.M = M; A.N = N; A.K = D; A.row_global0 = g->row_offset; A.sym = sym;
   A.d_eps2 = (float)((double)D * (double)PAIRWISE_EPS * (double)PAIRWISE_EPS);
+  A.sh = sh;
+  A.node_tab = share ? sh.tab[sh.rank] : nullptr;
   static int balance = -1;                               // MPN_GRAM_BALANCE=0: every block strides by the grid (diagnostics)
   if (balance < 0) { const char* e = getenv("MPN_GRAM_BALANCE"); balance = e ? atoi(e) : 1; }
   A.balance = balance;
   const int tm = (M + GE_BM - 1) / GE_BM, tn = (N + GE_BN - 1) / GE_BN;
   const int grid = (int)min((long long)kNumSMs, (long long)tm * tn);
   if (n_partial_rows) *n_partial_rows = grid;
-  if (g_profile_gram) {                                  // bench.py: duration of this one launch (events on the launching stream)
+  if (g_profile_gram) {                                  // bench.py: duration of the Gram launch(es) (events on the launching stream)
     if (!g_prof_ev[0]) { MPN_CUDA_OK(cudaEventCreate(&g_prof_ev[0])); MPN_CUDA_OK(cudaEventCreate(&g_prof_ev[1])); }
     MPN_CUDA_OK(cudaEventRecord(g_prof_ev[0], st));
   }
-  mpn::launch(gram_ef_kernel, grid, GE_THREADS, GE_SMEM_BYTES, st, ah, al, bh, bl, A);
+  mpn::launch(gram_ef_kernel<false>, grid, GE_THREADS, GE_SMEM_BYTES, st, ah, al, bh, bl, A);
   MPN_LAUNCH_OK();
+  if (share != nullptr) {                                // exactly one of the two runs (GeShare::mode, decided on the device)
+    mpn::launch(gram_ef_kernel<true>, grid, GE_THREADS, GE_SMEM_BYTES, st, ah, al, bh, bl, A);
+    MPN_LAUNCH_OK();
+  }
   if (g_profile_gram) MPN_CUDA_OK(cudaEventRecord(g_prof_ev[1], st));
   return MPN_OK;
 }

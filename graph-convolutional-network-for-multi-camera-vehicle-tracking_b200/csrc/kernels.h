@@ -26,6 +26,21 @@ struct GeWorkspace {
   int *tiles, *n_tiles;
   size_t total;
 };
+// Row-block shards that share ONE symmetric Gram (sharded forward, N > 1): every unordered pair of nodes is computed by exactly one
+// rank, which stores the direct entry into its own edge_attr and the mirrored entry into the OWNER's edge_attr over NVLink.
+// Pair (r in block R, c in block S) is computed by R iff  S == R: r < c;  else with d = (S - R) mod W:  2d < W: always,
+// 2d > W: never, 2d == W (antipodal blocks): R < S ? c < mid(S) : r >= mid(R)   (mid = middle of the block: both ranks do half).
+// Each rank first pushes (edge base, gap start, gap length, its not_one_gap flag) of its rows into every rank's node table; the
+// shared mode is used only if every rank's rows are dense cross-camera rows, otherwise every rank falls back to its own rows.
+struct GeShare {
+  int rank, world;
+  int blk[MPN_MAX_PEERS + 1];                 // row blocks: rank r owns nodes [blk[r], blk[r+1])
+  float2* ea[MPN_MAX_PEERS];                  // peer-visible edge_attr of every rank ([E_r] float2)
+  int4* tab[MPN_MAX_PEERS];                   // peer-visible node table [n_cols] of every rank (each rank holds a full copy)
+  unsigned long long* flags[MPN_MAX_PEERS];   // flag block of every rank; word [3][src] = node-table sequence
+  unsigned long long seq;                     // this call's sequence number
+  int* mode;                                  // device word in the caller's workspace: 2 = shared, 0 = every rank its own rows
+};
 int ge_workspace_layout(int n_cols, int M, int D, GeWorkspace* L, void* ws, size_t ws_bytes);
 bool gram_ef_shape_ok(int M, int N, int D);
 // column means of x [n, D] (fp64 partial sums, fixed order): part [ge_col_mean_splits()][D] doubles, *ticket zeroed once
@@ -33,7 +48,8 @@ int ge_col_mean_splits();
 int ge_col_mean(const float* x, int n, int D, double* part, unsigned int* ticket, float* mu, cudaStream_t st);
 // fills gap / *not_one_gap (zeroed by the caller) for the rows of g, then runs the fused kernels
 int gram_ef_run(const float* x, const float* mu, const mpn_graph* g, int D, int2* gap, int* not_one_gap, float2* edge_attr,
-                int* refine_list, int* refine_count, double* partials, int* n_partial_rows, const GeWorkspace& L, cudaStream_t st);
+                int* refine_list, int* refine_count, double* partials, int* n_partial_rows, const GeWorkspace& L, cudaStream_t st,
+                const GeShare* share = nullptr);
 
 // edge_features.cu
 struct EfMoments {                 // in: partials [>= kNumSMs][MPN_SUMS_DOUBLES] and fixed_sums [5], both zeroed by the caller
@@ -43,7 +59,7 @@ struct EfMoments {                 // in: partials [>= kNumSMs][MPN_SUMS_DOUBLES
   int known_fused;                 // out: 1 = the host already knows the fused kernel ran (the graph's layout hint)
 };
 int edge_features_impl(const mpn_graph* g, const float* x, int32_t D, float* edge_attr, int use_tc, void* ws, size_t ws_bytes,
-                       cudaStream_t st, EfMoments* moments);
+                       cudaStream_t st, EfMoments* moments, const GeShare* share = nullptr);   // share->mode is set here
 
 // gemm_simt.cu
 int gemm_nt_simt(const float* A, const float* B, const float* bias, const float* a_scale, const float* a_shift,

@@ -290,25 +290,6 @@ struct PeerArgs {
   float* h[KPEERS];
   double* cstats[KPEERS];
 };
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-// wait until *p >= seq; a protocol bug or a dead peer must surface as a trap, never as a hung GPU
-__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long seq) {
-  if (ld_acquire_sys(p) >= seq) return;
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  while (ld_acquire_sys(p) < seq) {
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 10000000000ull) __trap();
-  }
-}
-
 // moment all-reduce + constant folding: local partials -> my slot -> flag; wait for every rank; add the slots in rank order (the
 // same order on every rank => bit-identical totals); fold.  Runs as its own one-block kernel, or inside the last block of the
 // sweep that produced the partials (FinArgs::peers): no extra launch, and the partial rows are still hot in L2.
@@ -2280,6 +2261,22 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
   }
   bool h_pending = false;                                   // an h exchange has been published and not yet awaited
   const size_t lstride = (size_t)g->n_edges * 2;
+  // shared symmetric Gram: every pair of nodes computed by one rank, the mirrored entry stored into its owner's edge_attr
+  GeShare share;
+  const GeShare* share_ptr = nullptr;
+  if (ef_ws != nullptr && peers->world >= 2 && peers->edge_attr[0] != nullptr) {
+    memset(&share, 0, sizeof(share));
+    share.rank = peers->rank; share.world = peers->world; share.seq = peers->seq_t + 1;
+    for (int r = 0; r < peers->world; ++r) {
+      if (!(peers->edge_attr[r] && peers->node_tables[r])) { set_error("forward_sharded: NULL shared-Gram buffer for rank %d", r); mpn_plan_destroy(p); return MPN_ERR_INVALID; }
+      share.ea[r] = (float2*)peers->edge_attr[r];
+      share.tab[r] = (int4*)peers->node_tables[r];
+      share.flags[r] = (unsigned long long*)peers->flags[r];
+      share.blk[r] = peers->block_start[r];
+    }
+    share.blk[peers->world] = peers->block_start[peers->world];
+    share_ptr = &share;
+  }
 #define STEP_TRY(expr) do { rc = (expr); if (rc != MPN_OK) goto done; } while (0)
 #define PEER_FINALIZE(stage) do { mpn::launch(finalize_peer_kernel, 1, FIN_THREADS, 0, st, make_fin(p, stage, false), P, ++seq_m); \
     ++mpn::g_kernel_launches; if (cudaGetLastError() != cudaSuccess) { set_error("finalize_peer launch failed"); rc = MPN_ERR_CUDA; goto done; } } while (0)
@@ -2290,8 +2287,14 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
       if (clear_moment_state(p, st) != cudaSuccess) { set_error("memset failed"); rc = MPN_ERR_CUDA; goto done; } \
       EfMoments mom_; \
       mom_.partials = p->partials; mom_.fixed_sums = p->fix_sums; mom_.handled_flag = nullptr; mom_.known_fused = 0; \
-      STEP_TRY(edge_features_impl(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st, &mom_)); \
-      if (mom_.handled_flag != nullptr && mom_.known_fused) { \
+      STEP_TRY(edge_features_impl(g, x, w->node_dims[0], edge_attr_rw, use_tc, ef_ws, ef_ws_bytes, st, &mom_, share_ptr)); \
+      if (mom_.handled_flag != nullptr) { \
+        if (!mom_.known_fused) {   /* layout decided on the device: the sweep runs only if the fused kernel did not */ \
+          const int fg_ = (int)min((long long)SWEEP_GRID, (long long)div_up(g->n_edges > 0 ? g->n_edges : 1, SWEEP_THREADS)); \
+          mpn::launch(enc_moments_kernel<0>, fg_, SWEEP_THREADS, 0, st, (const float2*)edge_attr, g->n_edges, p->consts, p->w.small, \
+                      p->partials, make_fin(p, MPN_STAGE_ENC0, false), mom_.handled_flag); \
+          ++mpn::g_kernel_launches; \
+        } \
         FinArgs f_ = make_fin(p, MPN_STAGE_ENC0, false); \
         f_.fixed = p->fix_sums; \
         mpn::launch(finalize_peer_kernel, 1, FIN_THREADS, 0, st, f_, P, ++seq_m); \

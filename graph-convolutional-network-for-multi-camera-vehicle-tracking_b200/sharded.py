@@ -218,9 +218,10 @@ class CudaPhases:
 
 
 SUMS_BYTES = 2 * _lib.MPN_MAX_PEERS * _lib.MPN_SUMS_DOUBLES * 8      # two slots x 16 source ranks x 96 fp64 moment sums (pushed by the sources)
-FLAGS_OFFSET = SUMS_BYTES                            # 3 x 16 uint64 sequence flags: [moments][src], [h][src], [column stats][0]
+FLAGS_OFFSET = SUMS_BYTES                            # 4 x 16 uint64 sequence flags: [moments][src], [h][src], [column stats][0], [node tables][src]
 CSTATS_OFFSET = FLAGS_OFFSET + 512                   # two slots of [1024][2] fp64 column sums (sharded node encoder)
-H_OFFSET = CSTATS_OFFSET + 2 * _lib.MPN_PEER_CSTAT_COLS * 2 * 8        # h buffer [n_cols, 32] fp32 starts here
+H_OFFSET = CSTATS_OFFSET + 2 * _lib.MPN_PEER_CSTAT_COLS * 2 * 8        # h buffer [n_cols, 32] fp32 starts here; the node table
+                                                                       # [n_cols, 4] int32 of the shared Gram follows it
 
 
 class PeerMemory:
@@ -231,7 +232,8 @@ class PeerMemory:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
-        nbytes = H_OFFSET + n_cols * _lib.MPN_DH * 4
+        self.tables_offset = H_OFFSET + n_cols * _lib.MPN_DH * 4
+        nbytes = self.tables_offset + n_cols * 16
         self.n_cols = n_cols
         self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
         self.buf.zero_()
@@ -242,9 +244,38 @@ class PeerMemory:
         if self.world > _lib.MPN_MAX_PEERS:
             raise RuntimeError("at most %d peers" % _lib.MPN_MAX_PEERS)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        self.seq_moments = self.seq_h = self.seq_c = 0
+        self.seq_moments = self.seq_h = self.seq_c = self.seq_t = 0
+        self.ea_buf = self.ea_hdl = self.ea_ptrs = None         # peer-visible edge_attr (shared symmetric Gram), made on first use
+        self.ea_edges = 0
 
-    def ctx(self, shard_encoder: bool) -> "_lib.MpnPeerCtx":
+    def reserve_edge_attr(self, max_edges_per_rank: int, device):
+        """COLLECTIVE: (re)allocates the peer-visible edge_attr buffers, ``max_edges_per_rank`` edges on every rank."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        cap = int(max_edges_per_rank)
+        self.ea_buf = symm_mem.empty(cap * 8, dtype=torch.uint8, device=device)
+        self.ea_hdl = symm_mem.rendezvous(self.ea_buf, self.group)
+        self.ea_ptrs = [int(p) for p in self.ea_hdl.buffer_ptrs]
+        self.ea_edges = cap
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)
+
+    def edge_attr_buffer(self, n_edges: int, device):
+        """This rank's peer-visible edge_attr [n_edges, 2] for the shared symmetric Gram (every pair of nodes is computed by one
+        rank, which stores the mirrored entry into the owner's buffer over NVLink).  The first call allocates collectively
+        (1.25 x the largest shard of the group); a shard that outgrows the buffers raises (see reserve_edge_attr)."""
+        import torch.distributed as dist
+        if self.ea_buf is None:                         # first use: collective (every rank is in its first fused forward)
+            need = torch.tensor([n_edges], dtype=torch.int64, device=device)
+            dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+            self.reserve_edge_attr(int(int(need.item()) * 1.25) + 1024, device)
+        if n_edges > self.ea_edges:
+            raise RuntimeError("this rank's shard has %d edges, the peer-visible edge_attr buffers hold %d: call "
+                               "ShardedMPN.reserve_edge_attr(max_edges_per_rank) on EVERY rank before a larger graph "
+                               "(the allocation is a collective)" % (n_edges, self.ea_edges))
+        return self.ea_buf[:n_edges * 8].view(torch.float32).view(n_edges, 2)
+
+    def ctx(self, shard_encoder: bool, blocks=None) -> "_lib.MpnPeerCtx":
         c = _lib.MpnPeerCtx()
         c.rank, c.world = self.rank, self.world
         for r, base in enumerate(self.ptrs):
@@ -254,9 +285,18 @@ class PeerMemory:
             c.h[r] = base + H_OFFSET
         c.seq_moments, c.seq_h, c.seq_c = self.seq_moments, self.seq_h, self.seq_c
         c.shard_node_encoder = int(shard_encoder)
+        if blocks is not None and self.ea_ptrs is not None:      # shared symmetric Gram
+            for r, base in enumerate(self.ptrs):
+                c.edge_attr[r] = self.ea_ptrs[r]
+                c.node_tables[r] = base + self.tables_offset
+            for r, (b0, b1) in enumerate(blocks):
+                c.block_start[r] = int(b0)
+            c.block_start[len(blocks)] = int(blocks[-1][1])
+            c.seq_t = self.seq_t
         return c
 
-    def advance(self, L: int, shard_encoder: bool, n_layers: int):
+    def advance(self, L: int, shard_encoder: bool, n_layers: int, shared_gram: bool = False):
+        self.seq_t += 1 if shared_gram else 0
         self.seq_moments += 2 + 2 * L
         self.seq_h += max(L - 1, 0) + (1 if shard_encoder else 0)
         self.seq_c += n_layers if shard_encoder else 0
@@ -272,8 +312,13 @@ class ShardedMPN:
     reference schedule the fused kernels are tested against.  ``path`` names the one in use.
     """
 
-    def __init__(self, model, group=None, fused: bool = True, shard_node_encoder: bool = True):
+    def __init__(self, model, group=None, fused: bool = True, shard_node_encoder: bool = True, shared_gram: bool = True):
+        """``shared_gram`` (fused path, edge features computed inside the call): the ranks share ONE symmetric Gram — every pair of
+        nodes is computed by one rank only, the mirrored entry goes into its owner's edge_attr over NVLink (half the tensor-core
+        work per rank).  Needs contiguous row blocks that cover all nodes in rank order; ``last_edge_attr`` is then a view of a
+        peer-visible buffer that the next call overwrites."""
         self.model = model
+        self.shared_gram = bool(shared_gram)
         self.shard_node_encoder = shard_node_encoder
         self.comm = TorchComm(group)
         self.fused = fused and self.comm.world > 1
@@ -289,6 +334,20 @@ class ShardedMPN:
                 self._totals.clear()
             self._totals[key] = (g, int(tot.item()))
         return self._totals[key][1]
+
+    def reserve_edge_attr(self, max_edges_per_rank: int, n_cols: int, device):
+        """COLLECTIVE: size the peer-visible edge_attr buffers of the shared symmetric Gram for shards of up to
+        ``max_edges_per_rank`` edges (graphs of ``n_cols`` nodes).  Only needed before a graph larger than 1.25 x the first one."""
+        self._peer_memory(n_cols, device).reserve_edge_attr(max_edges_per_rank, device)
+
+    def shared_gram_used(self) -> bool:
+        """True when the last fused forward with ``local_edge_attr=None`` took the shared symmetric Gram (every rank's rows dense
+        cross-camera); synchronises the stream.  Tests / bench."""
+        last = getattr(self, "_last_ef", None)
+        if last is None:
+            return False
+        g, D, ef_ws = last
+        return _lib.lib().mpn_shared_gram_mode(g.ref, D, ef_ws.data_ptr(), ef_ws.numel(), current_stream_ptr(g.device)) == 2
 
     @property
     def path(self) -> str:
@@ -335,7 +394,11 @@ class ShardedMPN:
             from .edge_features import edge_features
             ea = edge_features(x, None, graph=g)
         elif make_features:
-            ea = torch.empty(g.n_edges, 2, dtype=torch.float32, device=dev)
+            contiguous_blocks = (len(blocks) == peers.world and blocks[0][0] == 0 and blocks[-1][1] == x.shape[0] and
+                                 all(blocks[i][1] == blocks[i + 1][0] for i in range(len(blocks) - 1)) and
+                                 all(b1 > b0 for b0, b1 in blocks))
+            shared = self.shared_gram and contiguous_blocks and g.n_edges > 0
+            ea = peers.edge_attr_buffer(g.n_edges, dev) if shared else torch.empty(g.n_edges, 2, dtype=torch.float32, device=dev)
         else:
             ea = local_edge_attr.contiguous().float()
         self.last_edge_attr = ea
@@ -347,7 +410,8 @@ class ShardedMPN:
             h_local = torch.empty(g.n_nodes, _lib.MPN_DH, dtype=torch.float32, device=dev)
             n_layers = int(W.n_node_layers)
             shard_enc = self.shard_node_encoder and max(W.node_dims[1:n_layers + 1]) <= _lib.MPN_PEER_CSTAT_COLS
-            ctx = peers.ctx(shard_enc)
+            shared = make_features and self.shared_gram and ea.data_ptr() == (peers.ea_ptrs[peers.rank] if peers.ea_ptrs else -1)
+            ctx = peers.ctx(shard_enc, blocks if shared else None)
             with torch.cuda.device(dev):
                 if make_features:
                     ef_ws = workspace("edge_features", dev, lib.mpn_edge_features_workspace_bytes(g.ref, x.shape[1]))
@@ -363,7 +427,8 @@ class ShardedMPN:
                                                        prob1.data_ptr() if prob1 is not None else None,
                                                        int(bool(USE_TENSOR_CORES)), C.byref(ctx), ws.data_ptr(), ws.numel(),
                                                        current_stream_ptr(dev)))
-            peers.advance(L, shard_enc, n_layers)
+            peers.advance(L, shard_enc, n_layers, shared_gram=shared)
+            self._last_ef = (g, int(x.shape[1]), ef_ws) if make_features else None
             return {'classified_edges': [logits[i] for i in range(n_out)]}, h_local, pred, prob1
         total = int(total_edges) if total_edges is not None else self._total_edges(g, dev)
         with torch.cuda.device(dev):

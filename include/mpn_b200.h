@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPN_B200_ABI_VERSION 5
+#define MPN_B200_ABI_VERSION 6
 
 enum {
   MPN_OK = 0,
@@ -134,6 +134,9 @@ float mpn_profile_gram_ms(void);
  * end of the side-stream encoder.  mpn_profile_timeline_read waits for the last forward's events and returns their number n;
  * ms_out[i] = time from the first event to event i, names_out = the n names joined by '|'.  Off by default: an event between
  * two kernels ends their programmatic overlap.  Not thread safe. */
+/* Tests / bench: how the last mpn_forward_sharded_with_edge_features that used `ef_workspace_dev` computed the edge features
+ * (synchronises the stream): 2 = shared symmetric Gram (mpn_peer_ctx.edge_attr), 0 = every rank its own rows, -1 = error. */
+int mpn_shared_gram_mode(const mpn_graph* g, int32_t feature_dim, const void* ef_workspace_dev, size_t ef_workspace_bytes, void* stream);
 int mpn_profile_timeline(int enable);
 int mpn_profile_timeline_read(float* ms_out, char* names_out, int names_bytes);
 size_t mpn_edge_features_workspace_bytes(const mpn_graph* g, int32_t D);
@@ -294,6 +297,17 @@ typedef struct mpn_peer_ctx {
   uint64_t seq_c;           /* last column-stat sequence number already used */
   int32_t shard_node_encoder;
   int32_t reserved;
+  /* Shared symmetric Gram of mpn_forward_sharded_with_edge_features (optional: edge_attr[0] == NULL -> every rank computes all
+   * pairs of its own rows).  edge_attr[r]: rank r's peer-visible edge_attr buffer ([E_r,2] fp32; edge_attr[rank] must be the
+   * edge_attr_out_dev of the call); node_tables[r]: rank r's peer-visible [n_cols][4] int32 table (filled by the call);
+   * block_start: rank r owns nodes [block_start[r], block_start[r+1]).  Every unordered pair of nodes is then computed by one
+   * rank only, which stores the mirrored entry into the owner's edge_attr over NVLink (csrc/kernels.h GeShare for the rule);
+   * flag word [3][src] of `flags` carries seq_t.  If any rank's rows are not dense cross-camera rows, all ranks fall back. */
+  float* edge_attr[MPN_MAX_PEERS];
+  int32_t* node_tables[MPN_MAX_PEERS];
+  int32_t block_start[MPN_MAX_PEERS + 1];
+  int32_t reserved2;
+  uint64_t seq_t;           /* last node-table sequence number already used */
 } mpn_peer_ctx;
 #define MPN_PEER_CSTAT_COLS 1024
 int mpn_forward_sharded(const mpn_graph* g, const mpn_weights* w, const float* x_dev, const float* edge_attr_dev,

@@ -49,8 +49,17 @@ def check_case(rank, world, dev, L, n_cls, N, C, modes, chunk=None, reattach=Fal
         if fused:                                      # edge features inside the call (fused kernel + its moment sums): same logits
             out_f, h_f, pred_f, _ = sh.forward(xd, ei_l, None, blocks, fuse_decisions=True, graph=g)
             assert torch.allclose(sh.last_edge_attr.cpu(), ea[lo:hi], rtol=1e-5, atol=1e-5)
+            assert sh.shared_gram_used(), "the shared symmetric Gram did not run (dense cross-camera rows on every rank)"
             scale = ref[-1].abs().max().item()
             assert (out_f["classified_edges"][-1] - out["classified_edges"][-1]).abs().max().item() <= 1e-5 * scale
+            for _rep in range(2):                      # sequence numbers of the node-table exchange, buffer reuse
+                out_g, _, pred_g, _ = sh.forward(xd, ei_l, None, blocks, fuse_decisions=True, graph=g)
+                assert torch.equal(out_g["classified_edges"][-1], out_f["classified_edges"][-1]) and torch.equal(pred_g, pred_f)
+            sh_own = m.ShardedMPN(net, fused=True, shared_gram=False)      # every rank all pairs of its own rows
+            out_o, _, pred_o, _ = sh_own.forward(xd, ei_l, None, blocks, fuse_decisions=True, graph=g)
+            assert not sh_own.shared_gram_used()
+            assert torch.allclose(sh_own.last_edge_attr.cpu(), ea[lo:hi], rtol=1e-5, atol=1e-5)
+            assert (out_o["classified_edges"][-1] - out_f["classified_edges"][-1]).abs().max().item() <= 1e-5 * scale
         torch.cuda.synchronize()
         if fused and sh.path != "fused_peer_memory" and rank == 0:
             print("fused path unavailable")

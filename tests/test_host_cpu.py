@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "symbol %s declared in include/mpn_b200.h is not exported" % name
     assert set(m._lib.EXPORTED_SYMBOLS) == declared
-    assert lib.mpn_abi_version() == m._lib.ABI_VERSION == 5
+    assert lib.mpn_abi_version() == m._lib.ABI_VERSION == 6
 
 
 def test_pdl_switch_defaults_on():
