@@ -1848,12 +1848,13 @@ int mpn_plan_node_encoder(mpn_fwd_plan* p, const float* x, void* stream) {
 
 // node encoder over this rank's row block only; BatchNorm column sums all-reduced through peer memory per layer;
 // the encoded rows land in every rank's h buffer (publish of the h flag is left to the caller)
-static int node_encoder_sharded(mpn_fwd_plan* p, const float* x, const PeerArgs& P, unsigned long long& seq_c, cudaStream_t st) {
+static int node_encoder_sharded(mpn_fwd_plan* p, const float* x, const PeerArgs& P, unsigned long long& seq_c, cudaStream_t st,
+                                int l_begin, int l_end) {                 // layers [l_begin, l_end), as node_encoder_layers
   const int M = p->g.n_nodes, off = p->g.row_offset;
-  const float* in = x + (size_t)off * p->w.node_dims[0];
   float* bufs[2] = {p->act0, p->act1};
-  const float *sc = nullptr, *sh = nullptr;
-  for (int l = 0; l < p->w.n_node_layers; ++l) {
+  const float* in = l_begin == 0 ? x + (size_t)off * p->w.node_dims[0] : bufs[(l_begin - 1) & 1];
+  const float *sc = l_begin == 0 ? nullptr : p->colscale, *sh = l_begin == 0 ? nullptr : p->colshift;
+  for (int l = l_begin; l < l_end; ++l) {
     const int K = p->w.node_dims[l], Nc = p->w.node_dims[l + 1];
     MPN_REQUIRE(Nc <= MPN_PEER_CSTAT_COLS, "sharded node encoder: layer width %d > %d", Nc, MPN_PEER_CSTAT_COLS);
     float* out = bufs[l & 1];
@@ -1878,6 +1879,7 @@ static int node_encoder_sharded(mpn_fwd_plan* p, const float* x, const PeerArgs&
     sc = p->colscale;
     sh = p->colshift;
   }
+  if (l_end < p->w.n_node_layers) return MPN_OK;
   mpn::launch(bn_relu_apply_peer_kernel, min(kNumSMs * 4, div_up((long long)M * MPN_DH, 256)), 256, 0, st, in, M, off, sc, sh, P);
   MPN_LAUNCH_OK();
   return MPN_OK;
@@ -2314,14 +2316,23 @@ static int forward_sharded_impl(const mpn_graph* g, const mpn_weights* w, const 
     tl_mark("start", st, true);
     const bool fork = ss != nullptr && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess;
     cudaStream_t es = fork ? ss->stream : st;
-    STEP_TRY(node_encoder_sharded(p, x, P, seq_c, es));
+    // enqueue order as in forward_impl: first encoder layer, edge features (they head the critical path), later layers
+    const int n_first = (fork && ef_ws != nullptr && p->w.n_node_layers > 1) ? 1 : p->w.n_node_layers;
+    STEP_TRY(node_encoder_sharded(p, x, P, seq_c, es, 0, n_first));
+    if (n_first < p->w.n_node_layers) {
+      ENC0_STAGE();
+      tl_mark("edge_features+enc0_end", st);
+      STEP_TRY(node_encoder_sharded(p, x, P, seq_c, es, n_first, p->w.n_node_layers));
+    }
     mpn::launch(peer_publish_h_kernel, 1, 32, 0, es, P, ++seq_h);
     ++mpn::g_kernel_launches;
     h_pending = true;
     tl_mark("node_encoder_end(side stream)", es);
     if (fork && cudaEventRecord(ss->join, ss->stream) != cudaSuccess) { set_error("event record failed"); rc = MPN_ERR_CUDA; goto done; }
-    ENC0_STAGE();
-    tl_mark("edge_features+enc0_end", st);
+    if (n_first == p->w.n_node_layers) {
+      ENC0_STAGE();
+      tl_mark("edge_features+enc0_end", st);
+    }
     STEP_TRY(mpn_plan_sweep(p, 0, MPN_STAGE_ENC1, edge_attr, nullptr, nullptr, nullptr, st));
     tl_mark("enc1_end", st);
     if (fork && cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess) { set_error("stream wait failed"); rc = MPN_ERR_CUDA; goto done; }

@@ -276,23 +276,31 @@ class PeerMemory:
         return self.ea_buf[:n_edges * 8].view(torch.float32).view(n_edges, 2)
 
     def ctx(self, shard_encoder: bool, blocks=None) -> "_lib.MpnPeerCtx":
-        c = _lib.MpnPeerCtx()
-        c.rank, c.world = self.rank, self.world
-        for r, base in enumerate(self.ptrs):
-            c.sums[r] = base
-            c.flags[r] = base + FLAGS_OFFSET
-            c.cstats[r] = base + CSTATS_OFFSET
-            c.h[r] = base + H_OFFSET
-        c.seq_moments, c.seq_h, c.seq_c = self.seq_moments, self.seq_h, self.seq_c
-        c.shard_node_encoder = int(shard_encoder)
-        if blocks is not None and self.ea_ptrs is not None:      # shared symmetric Gram
+        """The peer table of one call.  The pointer part is built once per (encoder mode, row blocks) — ~100 ctypes stores cost
+        tens of microseconds on the host's critical path of every step — only the sequence numbers change per call."""
+        shared = blocks is not None and self.ea_ptrs is not None
+        key = (bool(shard_encoder), tuple(map(tuple, blocks)) if shared else None, self.ea_ptrs[0] if shared else 0)
+        cache = self.__dict__.setdefault("_ctx_cache", {})
+        c = cache.get(key)
+        if c is None:
+            if len(cache) > 8:
+                cache.clear()
+            c = cache[key] = _lib.MpnPeerCtx()
+            c.rank, c.world = self.rank, self.world
             for r, base in enumerate(self.ptrs):
-                c.edge_attr[r] = self.ea_ptrs[r]
-                c.node_tables[r] = base + self.tables_offset
-            for r, (b0, b1) in enumerate(blocks):
-                c.block_start[r] = int(b0)
-            c.block_start[len(blocks)] = int(blocks[-1][1])
-            c.seq_t = self.seq_t
+                c.sums[r] = base
+                c.flags[r] = base + FLAGS_OFFSET
+                c.cstats[r] = base + CSTATS_OFFSET
+                c.h[r] = base + H_OFFSET
+            c.shard_node_encoder = int(shard_encoder)
+            if shared:                                         # shared symmetric Gram
+                for r, base in enumerate(self.ptrs):
+                    c.edge_attr[r] = self.ea_ptrs[r]
+                    c.node_tables[r] = base + self.tables_offset
+                for r, (b0, b1) in enumerate(blocks):
+                    c.block_start[r] = int(b0)
+                c.block_start[len(blocks)] = int(blocks[-1][1])
+        c.seq_moments, c.seq_h, c.seq_c, c.seq_t = self.seq_moments, self.seq_h, self.seq_c, self.seq_t
         return c
 
     def advance(self, L: int, shard_encoder: bool, n_layers: int, shared_gram: bool = False):
