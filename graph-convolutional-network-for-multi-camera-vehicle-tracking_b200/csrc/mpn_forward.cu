@@ -926,6 +926,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) apply_kernel(const mpn_graph
 constexpr int ATC_THREADS = 128;
 constexpr int ATC_CTAS_PER_SM = 5;                       // 40.6 KB shared memory, 89 registers, 64 TMEM columns per block
 constexpr int ATC_SEG = 128;                             // task ranges staged in shared memory per segment
+constexpr int ATC_BATCHES = 512;                         // 128-edge batches per segment (the segment is shortened to fit)
 constexpr int ATC_NB = 2;                                // 128-edge batches per iteration (one barrier / fence / commit for both)
 constexpr int ATC_D = 4;                                 // y runs D batches ahead
 constexpr int ATC_RL = ATC_D + 1;                        // ring slots
@@ -978,6 +979,7 @@ __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
   __shared__ __align__(128) float w2[32 * 8];
   __shared__ __align__(16) float4 ring[ATC_RL][ATC_THREADS];
   __shared__ int s_row[ATC_SEG], s_beg[ATC_SEG], s_end[ATC_SEG];
+  __shared__ int s_bstart[ATC_BATCHES], s_nbatch;
   __shared__ float red[2][ATC_THREADS / 32][32];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -1027,24 +1029,33 @@ __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
   const float t3[4] = {sc.v[FC_BN3_T], sc.v[FC_BN3_T + 1], sc.v[FC_BN3_T + 2], sc.v[FC_BN3_T + 3]};
   int flushes = 0;
 
-  for (int s0 = t_first; s0 < t_last; s0 += ATC_SEG) {
-    const int ns = min(ATC_SEG, t_last - s0);
+  const int seg_tasks = min(ATC_SEG, ATC_BATCHES / max(1, g.chunk / ATC_THREADS));   // a task has at most chunk / 128 batches
+  for (int s0 = t_first; s0 < t_last; s0 += seg_tasks) {
+    const int ns = min(seg_tasks, t_last - s0);
     __syncthreads();                                     // the previous segment's ranges are no longer read
     for (int i = tid; i < ns; i += ATC_THREADS) {
       const TaskRange tr = task_range(g, s0 + i);
       s_row[i] = tr.row; s_beg[i] = tr.beg; s_end[i] = tr.end;
     }
     __syncthreads();
-    // stream iterator (block-uniform): the batch whose y is copied next
-    int st_ti = 0, st_pos = s_beg[0], st_end = s_end[0], st_off = 0;
+    // first edge of every 128-edge batch of the segment, in processing order (a task's batches restart at the task's first edge):
+    // the stream iterator below is then one shared-memory load per batch instead of a walk over the task ranges
+    for (int i = tid; i < ns; i += ATC_THREADS) {
+      int first = 0;
+      for (int k = 0; k < i; ++k) first += (s_end[k] - s_beg[k] + ATC_THREADS - 1) / ATC_THREADS;
+      const int nb_i = (s_end[i] - s_beg[i] + ATC_THREADS - 1) / ATC_THREADS;
+      for (int k = 0; k < nb_i; ++k) s_bstart[first + k] = s_beg[i] + k * ATC_THREADS;
+      if (i == ns - 1) s_nbatch = first + nb_i;
+    }
+    __syncthreads();
+    // stream iterator (block-uniform): the batch whose y is copied next.  A lane past the end of its task reads on into the next
+    // task's edges (clamped to the segment's last edge): valid memory, and a masked lane's result is never added.
+    const int n_batch = s_nbatch, seg_last = s_end[ns - 1] - 1;
+    int st_j = 0, st_off = 0;
     auto issue_stream = [&]() {
-      if (st_ti < ns) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring_addr + (uint32_t)st_off), "l"(ybuf + min(st_pos + tid, st_end - 1)) : "memory");
-        st_pos += ATC_THREADS;
-        if (st_pos >= st_end) {
-          ++st_ti;
-          if (st_ti < ns) { st_pos = s_beg[st_ti]; st_end = s_end[st_ti]; }
-        }
+      if (st_j < n_batch) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring_addr + (uint32_t)st_off), "l"(ybuf + min(s_bstart[st_j] + tid, seg_last)) : "memory");
+        ++st_j;
         st_off = (st_off == (ATC_RL - 1) * ATC_SLOT_BYTES) ? 0 : st_off + ATC_SLOT_BYTES;
       }
       cp_async_commit();
