@@ -746,6 +746,23 @@ __global__ void gather_select_kernel(int A, const int* __restrict__ a_eid, const
   }
 }
 
+// grow-only pinned host buffer of the calling thread (never freed: no CUDA calls from static destructors)
+struct PinnedScratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t n) {
+    if (n > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr; cap = 0;
+      const size_t want = n + n / 4 + 4096;
+      if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; cudaGetLastError(); return nullptr; }
+      cap = want;
+    }
+    return p;
+  }
+};
+static thread_local PinnedScratch g_split_pin;
+
 static thread_local long long g_split_stats[4] = {0, 0, 0, 0};     // tie values' edges, steps / rounds, off-lowest steps, mode
 
 __global__ void apply_keep_kernel(int A, const int* __restrict__ a_eid, const uint8_t* __restrict__ keep, uint8_t* __restrict__ act) {
@@ -754,42 +771,50 @@ __global__ void apply_keep_kernel(int A, const int* __restrict__ a_eid, const ui
 }
 
 int split_exact_host_impl(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep,
-                          int64_t* stats_out, const uint8_t* tied, const int* seeds, long long n_seeds);      // split_exact.cu
+                          int64_t* stats_out, const uint8_t* tied, const int* seeds, long long n_seeds, const uint8_t* sel);      // split_exact.cu
 
 // the reference's order on the host for the flagged components (every oversized cluster lives in one of them)
 static int split_in_reference_order(PostCtx& c, uint8_t* act, const float* prob, int pstride, int num_cameras, int Dn, bool have_ties,
                                     int* rounds) {
   const int A = c.n_active, N = c.g.n_nodes;
+  static const bool dbg = getenv("MPN_POST_DEBUG") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   gather_select_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, act, prob, pstride, c.wcc, c.wccflag, c.a_prob, c.sel);
   MPN_LAUNCH_OK();
-  std::vector<int> hs(A), hd(A);
-  std::vector<float> hp(A);
-  std::vector<uint8_t> hsel(A), keep_all(A, 1), htied(have_ties ? A : 0);
+  // pinned staging (grow-only, per host thread): pageable destinations would be staged by the driver at a few GB/s
+  const size_t Au = (size_t)A, A16 = (Au + 15) & ~(size_t)15;
+  char* pin = (char*)g_split_pin.get(12 * A16 + 3 * A16 + 64);
+  MPN_REQUIRE(pin != nullptr, "split: out of pinned host memory (%zu bytes)", 15 * A16 + 64);
+  int* hs = (int*)pin;
+  int* hd = (int*)(pin + 4 * A16);
+  float* hp = (float*)(pin + 8 * A16);
+  uint8_t* hsel = (uint8_t*)(pin + 12 * A16);
+  uint8_t* htied = hsel + A16;
+  uint8_t* keep_all = htied + A16;
   std::vector<int> seeds(Dn);
   MPN_CUDA_OK(cudaMemcpyAsync(seeds.data(), c.dirty_nodes, sizeof(int) * Dn, cudaMemcpyDeviceToHost, c.st));
-  if (have_ties) MPN_CUDA_OK(cudaMemcpyAsync(htied.data(), c.tiedb, A, cudaMemcpyDeviceToHost, c.st));
-  MPN_CUDA_OK(cudaMemcpyAsync(hs.data(), c.a_src, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
-  MPN_CUDA_OK(cudaMemcpyAsync(hd.data(), c.a_dst, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
-  MPN_CUDA_OK(cudaMemcpyAsync(hp.data(), c.a_prob, sizeof(float) * A, cudaMemcpyDeviceToHost, c.st));
-  MPN_CUDA_OK(cudaMemcpyAsync(hsel.data(), c.sel, A, cudaMemcpyDeviceToHost, c.st));
+  if (have_ties) MPN_CUDA_OK(cudaMemcpyAsync(htied, c.tiedb, Au, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaMemcpyAsync(hsel, c.sel, Au, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaMemcpyAsync(hs, c.a_src, sizeof(int) * Au, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaMemcpyAsync(hd, c.a_dst, sizeof(int) * Au, cudaMemcpyDeviceToHost, c.st));
+  MPN_CUDA_OK(cudaMemcpyAsync(hp, c.a_prob, sizeof(float) * Au, cudaMemcpyDeviceToHost, c.st));
   MPN_CUDA_OK(cudaStreamSynchronize(c.st));
-  std::vector<int> pos;                             // active-list positions of the sub-problem, edge order
-  pos.reserve(A / 4 + 16);
-  for (int i = 0; i < A; ++i)
-    if (hsel[i]) pos.push_back(i);
-  const long long m = (long long)pos.size();
-  std::vector<int> ss(m), dd(m);
-  std::vector<float> pp(m);
-  std::vector<uint8_t> keep(m, 1), tt(have_ties ? m : 0);
-  for (long long k = 0; k < m; ++k) { ss[k] = hs[pos[k]]; dd[k] = hd[pos[k]]; pp[k] = hp[pos[k]]; if (have_ties) tt[k] = htied[pos[k]]; }
+  long long m = 0;                                  // the sub-problem: selected entries (they keep their position as edge id)
+  for (int i = 0; i < A; ++i) m += hsel[i];
+  const double t1 = now();
   int64_t st[4] = {0, 0, 0, 0};
-  if (m > 0) MPN_TRY(split_exact_host_impl(ss.data(), dd.data(), pp.data(), m, N, num_cameras, keep.data(), st, have_ties ? tt.data() : nullptr,
-                                           seeds.data(), (long long)seeds.size()));
-  for (long long k = 0; k < m; ++k) keep_all[pos[k]] = keep[k];
-  MPN_CUDA_OK(cudaMemcpyAsync(c.sel, keep_all.data(), A, cudaMemcpyHostToDevice, c.st));
+  const double t2 = now();
+  if (m > 0) MPN_TRY(split_exact_host_impl(hs, hd, hp, A, N, num_cameras, keep_all, st, have_ties ? htied : nullptr, seeds.data(),
+                                           (long long)seeds.size(), hsel));
+  else memset(keep_all, 1, Au);
+  const double t3 = now();
+  MPN_CUDA_OK(cudaMemcpyAsync(c.sel, keep_all, Au, cudaMemcpyHostToDevice, c.st));
   apply_keep_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.sel, act);
   MPN_LAUNCH_OK();
-  MPN_CUDA_OK(cudaStreamSynchronize(c.st));        // keep_all must outlive the copy
+  MPN_CUDA_OK(cudaStreamSynchronize(c.st));        // the staging buffer is reused by the next call
+  if (dbg) fprintf(stderr, "[split host] A=%d m=%lld seeds=%d: D2H+select %.2f ms, gather %.2f ms, engine %.2f ms, write-back %.2f ms\n", A, m, Dn,
+                   t1 - t0, t2 - t1, t3 - t2, now() - t3);
   *rounds = (int)st[0];
   g_split_stats[1] = st[0];
   g_split_stats[2] = st[1];

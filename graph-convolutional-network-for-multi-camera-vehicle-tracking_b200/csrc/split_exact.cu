@@ -18,12 +18,14 @@
 //     n_small + i and "label l is still oversized" reads  0 <= l - n_small' < n_big'  after the step: only the CHANGE of the
 //     number of small clusters matters, never its value.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <iterator>
 #include <set>
 #include <tuple>
-#include <unordered_map>
 #include <vector>
 
 #include <cstring>
@@ -38,11 +40,11 @@ struct SplitExact {
   long long m;
   const float* prob;
   int C, n;                                       // camera bound, number of (local) nodes
-  std::vector<int> ls, ld;                        // local endpoints of every edge
+  const int *ls = nullptr, *ld = nullptr;         // endpoints of every edge: the caller's arrays (global ids) or ls_own / ld_own
+  std::vector<int> ls_own, ld_own;                // (ids relabelled in order of first use, scc_emission_keys_host)
   std::vector<int> out_ptr, out_adj, in_ptr, in_adj;     // incident edge ids per node, ascending (= edge order)
   std::vector<int> out_first, in_first;           // first entry of the lists that may still be alive
   std::vector<uint8_t> alive;
-  std::vector<int> by_prob;                       // edge ids sorted by probability
   std::vector<int> comp, wcc;                     // cluster / WCC id of a node (-1: no active edge)
   std::vector<int> pre, low, it, mark;            // traversal scratch
   struct Cluster { int size; long long src_key; int idx; std::vector<int> nodes; };
@@ -52,6 +54,8 @@ struct SplitExact {
   std::set<BigKey> big;
   long long n_small = 0;
   int mark_gen = 0;
+  std::vector<int> sc_stack, sc_wn, sc_dfs, sc_scc;          // recompute() scratch (a step recomputes a handful of nodes: no
+  std::vector<std::pair<long long, int>> sc_keyed;           // allocation per call)
 
   long long first_key(int v) {                    // first-appearance key of v in the current active edge list: 2*edge + side
     int& a = out_first[v];
@@ -78,8 +82,9 @@ struct SplitExact {
   // nodes: a set closed under the alive edges.  Splits it into WCCs, runs networkx's SCC generator on each, registers clusters.
   void recompute(const std::vector<int>& nodes, bool lazy_only = false) {
     ++mark_gen;
-    std::vector<int> stack, wn, order, dfs, scc_stack;
-    std::vector<std::pair<long long, int>> keyed;
+    std::vector<int>&stack = sc_stack, &wn = sc_wn, &dfs = sc_dfs, &scc_stack = sc_scc;
+    std::vector<std::pair<long long, int>>& keyed = sc_keyed;
+    scc_stack.clear();
     for (int seed : nodes) {
       if (mark[seed] == mark_gen || (lazy_only && wcc[seed] != -2)) continue;
       mark[seed] = mark_gen;
@@ -164,31 +169,47 @@ struct SplitExact {
 // keep_out[i] = 0 for the edges SPLITTING switches off.  stats_out[4]: dropped values, steps taken on a label that was not the
 // lowest oversized one (utils.py:112 re-reads the integer), clusters examined, 0.
 // builds the adjacency of the sub-problem (local node ids in order of first use) and registers every cluster
+// sel (optional): entries with sel[i] == 0 are not part of the sub-problem (they keep their edge id: ids only need to be ordered)
 static void split_exact_init(SplitExact& S, const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C,
-                             std::vector<int>* global_of_local, const int* seeds = nullptr, long long n_seeds = 0) {
+                             std::vector<int>* global_of_local, const int* seeds = nullptr, long long n_seeds = 0,
+                             const uint8_t* sel = nullptr) {
   S.m = m; S.prob = prob; S.C = C;
-  std::vector<int> local((size_t)n_nodes, -1);
-  std::vector<int>& local_of = local;
-  S.ls.resize(m); S.ld.resize(m);
+  std::vector<int> local;
   int n = 0;
-  for (long long i = 0; i < m; ++i) {
-    if (local[src[i]] < 0) { local[src[i]] = n++; if (global_of_local) global_of_local->push_back(src[i]); }
-    if (local[dst[i]] < 0) { local[dst[i]] = n++; if (global_of_local) global_of_local->push_back(dst[i]); }
-    S.ls[i] = local[src[i]];
-    S.ld[i] = local[dst[i]];
+  if (global_of_local != nullptr) {               // relabel in order of first use (the caller wants the list of nodes that appear)
+    local.assign((size_t)n_nodes, -1);
+    S.ls_own.resize(m); S.ld_own.resize(m);
+    for (long long i = 0; i < m; ++i) {
+      if (sel && !sel[i]) continue;
+      if (local[src[i]] < 0) { local[src[i]] = n++; global_of_local->push_back(src[i]); }
+      if (local[dst[i]] < 0) { local[dst[i]] = n++; global_of_local->push_back(dst[i]); }
+      S.ls_own[i] = local[src[i]];
+      S.ld_own[i] = local[dst[i]];
+    }
+    S.ls = S.ls_own.data(); S.ld = S.ld_own.data();
+  } else {                                        // global ids as they are: no pass over the edges, no copy
+    S.ls = src; S.ld = dst;
+    n = n_nodes;
   }
   S.n = n;
   S.out_ptr.assign(n + 1, 0); S.in_ptr.assign(n + 1, 0);
-  for (long long i = 0; i < m; ++i) { S.out_ptr[S.ls[i] + 1]++; S.in_ptr[S.ld[i] + 1]++; }
+  long long m_sel = 0;
+  for (long long i = 0; i < m; ++i) {
+    if (sel && !sel[i]) continue;
+    S.out_ptr[S.ls[i] + 1]++; S.in_ptr[S.ld[i] + 1]++; ++m_sel;
+  }
   for (int v = 0; v < n; ++v) { S.out_ptr[v + 1] += S.out_ptr[v]; S.in_ptr[v + 1] += S.in_ptr[v]; }
-  S.out_adj.resize(m); S.in_adj.resize(m);
+  S.out_adj.resize(m_sel); S.in_adj.resize(m_sel);
   {
     std::vector<int> oc(S.out_ptr.begin(), S.out_ptr.end() - 1), ic(S.in_ptr.begin(), S.in_ptr.end() - 1);
-    for (long long i = 0; i < m; ++i) { S.out_adj[oc[S.ls[i]]++] = (int)i; S.in_adj[ic[S.ld[i]]++] = (int)i; }
+    for (long long i = 0; i < m; ++i) {
+      if (sel && !sel[i]) continue;
+      S.out_adj[oc[S.ls[i]]++] = (int)i; S.in_adj[ic[S.ld[i]]++] = (int)i;
+    }
   }
   S.out_first.assign(S.out_ptr.begin(), S.out_ptr.end() - 1);
   S.in_first.assign(S.in_ptr.begin(), S.in_ptr.end() - 1);
-  S.alive.assign(m, 1);
+  if (sel) S.alive.assign(sel, sel + m); else S.alive.assign(m, 1);
   S.comp.assign(n, -1); S.wcc.assign(n, -2);               // -2: component not examined yet (registered on first use)
   S.pre.assign(n, 0); S.low.assign(n, 0); S.it.assign(n, 0); S.mark.assign(n, 0);
   if (seeds == nullptr) {
@@ -201,7 +222,8 @@ static void split_exact_init(SplitExact& S, const int* src, const int* dst, cons
     std::vector<int> start;
     start.reserve((size_t)n_seeds);
     for (long long i = 0; i < n_seeds; ++i) {
-      const int v = seeds[i] >= 0 && seeds[i] < n_nodes ? local_of[(size_t)seeds[i]] : -1;
+      int v = seeds[i] >= 0 && seeds[i] < n_nodes ? seeds[i] : -1;
+      if (v >= 0 && !local.empty()) v = local[(size_t)v];
       if (v >= 0) start.push_back(v);
     }
     S.recompute(start);
@@ -228,30 +250,57 @@ void scc_emission_keys_host(const int* src, const int* dst, long long m, int n_n
 // be switched off by another cluster's step); nullptr: found here by sorting.  seeds (optional): global ids of the nodes of the
 // oversized clusters; nullptr: every component is examined up front.
 int split_exact_host_impl(const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C, uint8_t* keep,
-                          int64_t* stats_out, const uint8_t* tied, const int* seeds, long long n_seeds) {
+                          int64_t* stats_out, const uint8_t* tied, const int* seeds, long long n_seeds, const uint8_t* sel) {
   SplitExact S;
+  static const bool dbg = getenv("MPN_POST_DEBUG") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   for (long long i = 0; i < m; ++i) keep[i] = 1;
-  split_exact_init(S, src, dst, prob, m, n_nodes, C, nullptr, seeds, n_seeds);
-  // probability value (bits) -> the edges that carry it, for the values carried by more than one edge
-  std::unordered_map<uint32_t, std::vector<int>> ties;
+  split_exact_init(S, src, dst, prob, m, n_nodes, C, nullptr, seeds, n_seeds, sel);
+  const double t1 = now();
+  // probability value (bits) -> the edges that carry it, for the values carried by more than one edge: open-addressing table of
+  // chain heads over the list of tied edges (no allocation per value; built in one pass)
   auto bits_of = [&](int e) { uint32_t b; float f = prob[e] == 0.0f ? 0.0f : prob[e]; memcpy(&b, &f, 4); return b; };
-  if (tied != nullptr) {
+  std::vector<uint8_t> tied_local;
+  if (tied == nullptr) {                          // stand-alone call: find the shared values by sorting
+    std::vector<int> order;
+    order.reserve(m);
     for (long long i = 0; i < m; ++i)
-      if (tied[i]) ties[bits_of((int)i)].push_back((int)i);
-  } else {
-    std::vector<int> order(m);
-    for (long long i = 0; i < m; ++i) order[i] = (int)i;
+      if (!sel || sel[i]) order.push_back((int)i);
     std::sort(order.begin(), order.end(), [&](int a, int b) { return prob[a] < prob[b] || (prob[a] == prob[b] && a < b); });
-    for (long long i = 0; i < m;) {
+    tied_local.assign(m, 0);
+    const long long mo = (long long)order.size();
+    for (long long i = 0; i < mo;) {
       long long j = i + 1;
-      while (j < m && prob[order[j]] == prob[order[i]]) ++j;
-      if (j - i > 1) {
-        std::vector<int>& v = ties[bits_of(order[i])];
-        for (long long k = i; k < j; ++k) v.push_back(order[k]);
-      }
+      while (j < mo && prob[order[j]] == prob[order[i]]) ++j;
+      if (j - i > 1)
+        for (long long k = i; k < j; ++k) tied_local[order[k]] = 1;
       i = j;
     }
+    tied = tied_local.data();
   }
+  std::vector<int> tied_ids;
+  for (long long i = 0; i < m; ++i)
+    if (tied[i] && (!sel || sel[i])) tied_ids.push_back((int)i);
+  size_t tcap = 16;
+  while (tcap < 2 * tied_ids.size() + 2) tcap <<= 1;
+  const uint32_t TIE_EMPTY = 0xFFFFFFFFu;
+  std::vector<uint32_t> tkeys(tcap, TIE_EMPTY);
+  std::vector<int> thead(tcap, -1), tnext(tied_ids.size(), -1);
+  auto tie_slot = [&](uint32_t b) {
+    size_t h = ((size_t)b * 2654435761u) & (tcap - 1);
+    while (tkeys[h] != TIE_EMPTY && tkeys[h] != b) h = (h + 1) & (tcap - 1);
+    return h;
+  };
+  for (size_t t = 0; t < tied_ids.size(); ++t) {
+    const uint32_t b = bits_of(tied_ids[t]);
+    if (b == TIE_EMPTY) continue;                 // (a NaN pattern: never equal to anything)
+    const size_t h = tie_slot(b);
+    tkeys[h] = b;
+    tnext[t] = thead[h];
+    thead[h] = (int)t;
+  }
+  const double t2 = now();
   long long steps = 0, off_lowest = 0;
   long long sticky = -1;                          // index (in the order of `big`) of the cluster the reference's inner loop is on
   std::vector<int> affected, kill, lazy;
@@ -274,11 +323,13 @@ int split_exact_host_impl(const int* src, const int* dst, const float* prob, lon
     // carried by more than one edge, the others
     kill.clear();
     kill.push_back(e_min);
-    {
-      auto it = ties.find(bits_of(e_min));
-      if (it != ties.end())
-        for (int e : it->second)
+    if (tied[e_min]) {
+      const uint32_t b = bits_of(e_min);
+      if (b != TIE_EMPTY)
+        for (int t = thead[tie_slot(b)]; t >= 0; t = tnext[t]) {
+          const int e = tied_ids[t];
           if (e != e_min && S.alive[e]) kill.push_back(e);
+        }
     }
     // components that have not been examined yet (they hold no oversized cluster) enter the books before the step is counted
     lazy.clear();
@@ -307,6 +358,7 @@ int split_exact_host_impl(const int* src, const int* dst, const float* prob, lon
     const long long j = idx - (S.n_small - small_before);
     sticky = (j >= 0 && j < (long long)S.big.size()) ? j : -1;
   }
+  if (dbg) fprintf(stderr, "[split engine] m=%lld: init %.2f ms, tie map %.2f ms, %lld steps %.2f ms\n", m, t1 - t0, t2 - t1, steps, now() - t2);
   if (stats_out) { stats_out[0] = steps; stats_out[1] = off_lowest; stats_out[2] = (long long)S.clusters.size(); stats_out[3] = 0; }
   return MPN_OK;
 }
@@ -324,5 +376,5 @@ extern "C" int mpn_split_exact_host(const int32_t* src, const int32_t* dst, cons
     if (stats_out) stats_out[0] = stats_out[1] = stats_out[2] = stats_out[3] = 0;
     return MPN_OK;
   }
-  return mpn::split_exact_host_impl(src, dst, prob, n_active, n_nodes, num_cameras, keep_out, stats_out, nullptr, nullptr, 0);
+  return mpn::split_exact_host_impl(src, dst, prob, n_active, n_nodes, num_cameras, keep_out, stats_out, nullptr, nullptr, 0, nullptr);
 }
