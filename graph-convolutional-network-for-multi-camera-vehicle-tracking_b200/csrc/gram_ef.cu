@@ -40,14 +40,14 @@ constexpr int GE_PLANE_BYTES = GE_BM * GE_BK * 2;           // 16 KB
 constexpr int GE_STAGE_BYTES = 4 * GE_PLANE_BYTES;          // 64 KB
 constexpr int GE_EPI_WARPS = 8;                             // two per TMEM lane quarter (each takes half of the columns)
 constexpr int GE_THREADS = 64 + 32 * GE_EPI_WARPS;
-constexpr int GE_TMEM_COLS = 512;                           // [hh0 | corr0 | hh1 | corr1], 128 columns each
+constexpr int GE_TMEM_COLS = 512;                           // two accumulator sets [hh | corr] (128 columns each), one per tile in flight
 constexpr int GE_SUB = 8;                                   // columns per shared-memory transpose step
 constexpr int GE_TPITCH = GE_SUB + 1;                       // float2 per row of the 32 x 8 transpose buffer (+1: conflict-free writes)
 constexpr uint32_t GE_IDESC_N256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(GE_BM >> 4) << 24);   // f16 x f16 -> f32
 constexpr uint32_t GE_IDESC_N128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(GE_BM >> 4) << 24);
 
 struct GeSmem {
-  uint64_t full_bar[GE_STAGES], empty_bar[GE_STAGES], tmem_full_bar, tmem_empty_bar;
+  uint64_t full_bar[GE_STAGES], empty_bar[GE_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   uint32_t tmem_slot, pad;
   // per column j of the current tile: {|b'|^2, 2 eps sum b', mu.b' + |mu|^2/2, 1/|b|} and {2^-k_b (float bits), and the column's own
   // row of the graph for the mirrored entries: edge base before the gap, edge base after the gap, end of the gap} (base < 0: none)
@@ -411,8 +411,7 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int t_first = (int)blockIdx.x < t_stride ? (int)blockIdx.x : n_tiles;
   if (threadIdx.x == 0) {
     for (int s = 0; s < GE_STAGES; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], 1); }
-    mbar_init(&S.tmem_full_bar, 1);
-    mbar_init(&S.tmem_empty_bar, 32 * GE_EPI_WARPS);
+    for (int a = 0; a < 2; ++a) { mbar_init(&S.tmem_full_bar[a], 1); mbar_init(&S.tmem_empty_bar[a], 32 * GE_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&S.tmem_slot, GE_TMEM_COLS);
@@ -451,18 +450,20 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===== MMA issuer =====
     // per k-slice (16 fp16):  a_hi x [b_hi ; b_lo]^T  (N = 256)  ->  [hh_s | corr_s]      hi.hi and hi.lo in one instruction
     //                         a_lo x  b_hi^T          (N = 128)  ->        corr_s          lo.hi
-    // s = slice & 1: two accumulator sets alternate (halves the truncation bias of the tensor core's fp32 accumulate); the shared
-    // A_hi / B_hi operands are read from shared memory twice instead of three times (the main loop is shared-memory bound)
+    // Two accumulator sets [hh | corr] (2 x 256 TMEM columns) alternate from TILE to tile: while the epilogue warps drain set s
+    // the issuer already fills set s ^ 1 with the next tile, so the tensor pipe does not wait for the epilogue.  The shared
+    // A_hi / B_hi operands are read from shared memory twice instead of three times (the main loop is shared-memory bound).
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0, tphase = 0;
+      uint32_t phase = 0;
       int it = 0;
       for (int t = t_first; t < n_tiles; t += t_stride, ++it) {
-        if (it > 0) {                                     // the epilogue has read the previous tile's accumulators
-          mbar_wait(&S.tmem_empty_bar, tphase);
-          tphase ^= 1;
+        const int as = it & 1;
+        if (it >= 2) {                                    // the epilogue has read this set's previous tile (two tiles ago)
+          mbar_wait(&S.tmem_empty_bar[as], (uint32_t)(((it >> 1) - 1) & 1));
           tc_fence_after();
         }
+        const uint32_t set = tmem_base + (uint32_t)as * 256u;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&S.full_bar[stage], phase);
           tc_fence_after();
@@ -472,15 +473,13 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
           for (int kk = 0; kk < GE_BK / 16; ++kk) {
             const uint64_t adv = (uint64_t)((kk * 32) >> 4);          // 16 fp16 = 32 bytes of K per instruction
-            const int slice = kb * (GE_BK / 16) + kk;
-            const uint32_t set = tmem_base + (uint32_t)(slice & 1) * 256u;
-            umma_f16(set, a_hi + adv, b_hi + adv, GE_IDESC_N256, slice >= 2);
+            umma_f16(set, a_hi + adv, b_hi + adv, GE_IDESC_N256, (kb | kk) != 0);
             umma_f16(set + 128u, a_lo + adv, b_hi + adv, GE_IDESC_N128, 1);
           }
           umma_commit(&S.empty_bar[stage]);
           if (++stage == GE_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&S.tmem_full_bar);
+        umma_commit(&S.tmem_full_bar[as]);
       }
     }
   } else {
@@ -488,10 +487,11 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int ew = warp - 2;
     const int q = warp & 3, half = ew >> 2;
     const int et = threadIdx.x - 64;                      // 0..255 among the epilogue threads
-    uint32_t fphase = 0;
+    int it = 0;
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     float2 (*tb)[GE_TPITCH] = S.tbuf[ew];
-    for (int t = t_first; t < n_tiles; t += t_stride) {
+    for (int t = t_first; t < n_tiles; t += t_stride, ++it) {
+      const int as = it & 1;                                // accumulator set of this tile
       const int tile = A.tiles[t];
       const int m0 = (tile >> 16) * GE_BM, n0 = (tile & 0xffff) * GE_BN;
       const bool mirror = SHARED || (A.sym && n0 >= m0 + A.row_global0 + GE_BM);     // off-diagonal block of the whole graph
@@ -549,8 +549,7 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       const float rn_a = ra.w, ma = ra.z, sa = ra.x, ea = ra.y;
       const int grow = A.row_global0 + row;                // global id of this thread's node (position in the mirrored rows)
-      mbar_wait(&S.tmem_full_bar, fphase);
-      fphase ^= 1;
+      mbar_wait(&S.tmem_full_bar[as], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
@@ -566,17 +565,9 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (hi > lo) cmask &= ~((hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u));
         }
         float v[32], w[32];
-        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        tmem_ld32_issue(tq, v);                             // hh0
-        tmem_ld32_issue(tq + 256u, w);                      // hh1
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w[j];
-        tmem_ld32_issue(tq + 128u, w);                      // corr0
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w[j];
-        tmem_ld32_issue(tq + 384u, w);                      // corr1
+        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + c0);
+        tmem_ld32_issue(tq, v);                             // hh
+        tmem_ld32_issue(tq + 128u, w);                      // corr
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += w[j];
@@ -651,7 +642,7 @@ gram_ef_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         acc[0] += (double)s_a; acc[1] += (double)s_b; acc[2] += (double)s_aa; acc[3] += (double)s_ab; acc[4] += (double)s_bb;
       }
       tc_fence_before();
-      mbar_arrive(&S.tmem_empty_bar);                       // this thread's tcgen05.ld of the tile have completed
+      mbar_arrive(&S.tmem_empty_bar[as]);                   // this thread's tcgen05.ld of the tile have completed
       asm volatile("bar.sync 1, 256;" ::: "memory");       // everyone is done with cs / rowinfo before the next tile restages them
     }
     if (A.partials != nullptr) {
