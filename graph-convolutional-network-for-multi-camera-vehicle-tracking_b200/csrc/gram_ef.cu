@@ -262,13 +262,13 @@ __global__ void __launch_bounds__(32 * GE_CS_WARPS) ge_center_split_kernel(const
 
 
 // ---- shared Gram: which rank computes a pair (kernels.h, GeShare) ----
-__device__ __forceinline__ int ge_owner(const GeShare& sh, int c) {
+__host__ __device__ __forceinline__ int ge_owner(const GeShare& sh, int c) {
   int s = 0;
   while (s + 1 < sh.world && c >= sh.blk[s + 1]) ++s;
   return s;
 }
 // rows [lo, hi) (global ids) of THIS rank that compute their pair with column c (owned by rank s); hi == 0: none
-__device__ __forceinline__ int2 ge_row_range(const GeShare& sh, int s, int c) {
+__host__ __device__ __forceinline__ int2 ge_row_range(const GeShare& sh, int s, int c) {
   const int R = sh.rank, W = sh.world;
   if (s == R) return make_int2(0, c);                                      // own block: r < c
   const int d = (s - R + W) % W;
@@ -768,6 +768,21 @@ int gram_ef_run(const float* x, const float* mu, const mpn_graph* g, int D, int2
 }
 
 }  // namespace mpn
+
+// tests: the pair-ownership rule of the shared Gram as the kernels evaluate it (same functions, compiled for the host): the rows
+// [out[0], out[1]) of rank `rank` compute their pair with column c; returns the owner of c, or -1 on bad arguments
+extern "C" int mpn_shared_gram_row_range(int32_t rank, int32_t world, const int32_t* block_start, int32_t c, int32_t* out) {
+  if (world < 1 || world > MPN_MAX_PEERS || rank < 0 || rank >= world || block_start == nullptr || out == nullptr) return -1;
+  mpn::GeShare sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.rank = rank; sh.world = world;
+  for (int r = 0; r <= world; ++r) sh.blk[r] = block_start[r];
+  if (c < sh.blk[0] || c >= sh.blk[world]) return -1;
+  const int owner = mpn::ge_owner(sh, c);
+  const int2 range = mpn::ge_row_range(sh, owner, c);
+  out[0] = range.x; out[1] = range.y;
+  return owner;
+}
 
 extern "C" int mpn_profile_gram(int enable) {
   mpn::g_profile_gram = enable != 0;

@@ -1077,11 +1077,14 @@ static int labels_reference_parallel(PostCtx& c, const uint8_t* act, long long* 
     MPN_LAUNCH_OK();
     select_flagged_kernel<<<list_grid(A), 256, 0, c.st>>>(A, c.a_eid, c.a_src, act, c.wcc, c.wccflag, c.sel);
     MPN_LAUNCH_OK();
-    std::vector<int> hs(A), hd(A);
-    std::vector<uint8_t> hsel(A);
-    MPN_CUDA_OK(cudaMemcpyAsync(hs.data(), c.a_src, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
-    MPN_CUDA_OK(cudaMemcpyAsync(hd.data(), c.a_dst, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
-    MPN_CUDA_OK(cudaMemcpyAsync(hsel.data(), c.sel, A, cudaMemcpyDeviceToHost, c.st));
+    const size_t A16 = ((size_t)A + 15) & ~(size_t)15;
+    char* pin = (char*)g_split_pin.get(9 * A16 + 64);          // pinned staging (see split_in_reference_order)
+    MPN_REQUIRE(pin != nullptr, "reference numbering: out of pinned host memory");
+    int *hs = (int*)pin, *hd = (int*)(pin + 4 * A16);
+    uint8_t* hsel = (uint8_t*)(pin + 8 * A16);
+    MPN_CUDA_OK(cudaMemcpyAsync(hs, c.a_src, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaMemcpyAsync(hd, c.a_dst, sizeof(int) * A, cudaMemcpyDeviceToHost, c.st));
+    MPN_CUDA_OK(cudaMemcpyAsync(hsel, c.sel, A, cudaMemcpyDeviceToHost, c.st));
     MPN_CUDA_OK(cudaStreamSynchronize(c.st));
     std::vector<int> ss, dd;
     for (int i = 0; i < A; ++i)
@@ -1105,15 +1108,41 @@ static int labels_reference_parallel(PostCtx& c, const uint8_t* act, long long* 
     idx[r] = (unsigned int)cx_idx[v];
     if ((unsigned int)cx_size[v] != size[r]) { set_error("reference numbering: component sizes disagree (device %u, host %d)", size[r], cx_size[v]); return MPN_ERR_INVALID; }
   }
+  // rank of a component = its position in the order (size, key, idx).  Keys are positions in the active list (< 2A + 2): one
+  // bucket pass puts the components in (key, idx) order — several components share a key only when one DFS source of the
+  // sequential generator emitted them, those few are sorted by idx — and a stable counting sort by size finishes the order.
   std::vector<Rep> reps;
-  reps.reserve(N / 2 + 1);
-  for (int r = 0; r < N; ++r)
-    if (size[r] > 0) reps.push_back(Rep{size[r], idx[r], key[r], r});
-  std::sort(reps.begin(), reps.end(), [](const Rep& a, const Rep& b) {
-    if (a.size != b.size) return a.size < b.size;
-    if (a.key != b.key) return a.key < b.key;
-    return a.idx < b.idx;
-  });
+  {
+    const size_t n_keys = 2 * (size_t)A + 2;
+    std::vector<int> head(n_keys, -1), nxt((size_t)N, -1);
+    unsigned int max_size = 0;
+    size_t n_reps = 0;
+    for (int r = N - 1; r >= 0; --r) {
+      if (size[r] == 0) continue;
+      if (key[r] >= n_keys) { set_error("reference numbering: first-appearance key out of range"); return MPN_ERR_INVALID; }
+      nxt[r] = head[key[r]];
+      head[key[r]] = r;
+      max_size = std::max(max_size, size[r]);
+      ++n_reps;
+    }
+    std::vector<int> by_key;
+    by_key.reserve(n_reps);
+    std::vector<int> same;
+    for (size_t k = 0; k < n_keys; ++k) {
+      int r = head[k];
+      if (r < 0) continue;
+      if (nxt[r] < 0) { by_key.push_back(r); continue; }
+      same.clear();
+      for (; r >= 0; r = nxt[r]) same.push_back(r);
+      std::sort(same.begin(), same.end(), [&](int a, int b) { return idx[a] < idx[b]; });
+      by_key.insert(by_key.end(), same.begin(), same.end());
+    }
+    std::vector<size_t> first((size_t)max_size + 2, 0);
+    for (int r : by_key) ++first[size[r] + 1];
+    for (size_t z = 1; z < first.size(); ++z) first[z] += first[z - 1];
+    reps.resize(n_reps);
+    for (int r : by_key) reps[first[size[r]]++] = Rep{size[r], idx[r], key[r], r};
+  }
   std::vector<int> rank(N, -1);
   for (size_t i = 0; i < reps.size(); ++i) rank[reps[i].root] = (int)i;
   long long next = (long long)reps.size();

@@ -137,6 +137,10 @@ float mpn_profile_gram_ms(void);
 /* Tests / bench: how the last mpn_forward_sharded_with_edge_features that used `ef_workspace_dev` computed the edge features
  * (synchronises the stream): 2 = shared symmetric Gram (mpn_peer_ctx.edge_attr), 0 = every rank its own rows, -1 = error. */
 int mpn_shared_gram_mode(const mpn_graph* g, int32_t feature_dim, const void* ef_workspace_dev, size_t ef_workspace_bytes, void* stream);
+/* Tests: the pair-ownership rule of the shared Gram exactly as the kernels evaluate it.  Rows [out[0], out[1]) (global node ids,
+ * intersected with rank's own block by the caller) of rank `rank` compute their pair with column c; returns the owner rank of
+ * node c, or -1 on bad arguments.  Host only. */
+int mpn_shared_gram_row_range(int32_t rank, int32_t world, const int32_t* block_start, int32_t c, int32_t* out_host);
 int mpn_profile_timeline(int enable);
 int mpn_profile_timeline_read(float* ms_out, char* names_out, int names_bytes);
 size_t mpn_edge_features_workspace_bytes(const mpn_graph* g, int32_t D);

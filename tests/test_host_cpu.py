@@ -227,3 +227,36 @@ def test_host_numbering_equals_networkx_on_random_digraphs():
         nc = C.c_int32(0)
         m._lib.check(lib.mpn_labels_reference_host(s32.ctypes.data, d32.ctypes.data, s.size, n, lab.ctypes.data, C.byref(nc)))
         assert nc.value == k and np.array_equal(lab, expect), trial
+
+
+def test_shared_gram_every_pair_computed_exactly_once():
+    """The pair-ownership rule of the shared symmetric Gram (csrc/kernels.h GeShare; the kernels' own functions compiled for the
+    host): for every world size and ragged row blocks, each unordered pair of nodes is computed by exactly one rank, a rank only
+    claims pairs whose row it owns, and the ranks' shares of the cross-block pairs are balanced."""
+    import ctypes as C
+    import numpy as np
+    lib = m._lib.lib()
+    rng = np.random.default_rng(11)
+    for world in range(2, 9):
+        for trial in range(4):
+            n = int(rng.integers(world * 3, 90))
+            cuts = np.sort(rng.choice(np.arange(1, n), size=world - 1, replace=False)) if trial else np.arange(1, world) * (n // world)
+            blk = np.r_[0, cuts, n].astype(np.int32)
+            owner = np.searchsorted(blk, np.arange(n), side="right") - 1
+            claimed = np.zeros((n, n), dtype=np.int32)            # claimed[r, c]: ranks that compute pair {r, c} as (row r, column c)
+            out = (C.c_int32 * 2)()
+            for rank in range(world):
+                for c in range(n):
+                    got = lib.mpn_shared_gram_row_range(rank, world, blk.ctypes.data, c, out)
+                    assert got == owner[c]
+                    lo, hi = max(out[0], blk[rank]), min(out[1], blk[rank + 1])
+                    if hi > lo:
+                        claimed[lo:hi, c] += 1
+            both = claimed + claimed.T                            # pair {r, c} computed as (r, c) or as (c, r)
+            off = ~np.eye(n, dtype=bool)
+            assert np.all(both[off] == 1), (world, blk)
+            assert np.all(np.diag(claimed) == 0)
+            work = np.array([claimed[blk[r]:blk[r + 1]].sum() for r in range(world)])
+            if trial == 0 and n % world == 0:                     # equal blocks: equal shares (antipodal blocks are split in half)
+                assert work.max() - work.min() <= n, (world, work)
+    assert lib.mpn_shared_gram_row_range(0, 0, None, 0, None) == -1
