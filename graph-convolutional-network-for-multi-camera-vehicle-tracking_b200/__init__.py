@@ -24,7 +24,7 @@ from .graph_inputs import (edge_labels, load_packed_features, normalize_columns,
 from .edge_features import edge_features
 from .graph import TrackletGraph, graph_for
 from .mpn import MOTMPNet
-from .pipeline import GraphStream, ShardedGraphStream
+from .pipeline import GraphStream, ShardedGraphStream, unpack_decisions
 from .sharded import (CudaPhases, CudaPostOps, ShardedMPN, partition_rows, shard_edges, sharded_forward,
                       sharded_post_processing)
 from .postprocess import (compute_SCC_and_Clusters, post_processing, pruning, remove_edges_single_direction,
@@ -32,6 +32,6 @@ from .postprocess import (compute_SCC_and_Clusters, post_processing, pruning, re
 
 __all__ = ["MOTMPNet", "edge_features", "post_processing", "pruning", "splitting", "remove_edges_single_direction",
            "compute_SCC_and_Clusters", "split_stats", "TrackletGraph", "graph_for", "ShardedMPN", "CudaPhases", "sharded_forward", "partition_rows",
-           "shard_edges", "GraphStream", "ShardedGraphStream", "sharded_post_processing", "CudaPostOps", "_lib", "evaluation", "compute_P_R_F", "clustering_scores", "relabel_detections", "tracking_table",
+           "shard_edges", "GraphStream", "ShardedGraphStream", "unpack_decisions", "sharded_post_processing", "CudaPostOps", "_lib", "evaluation", "compute_P_R_F", "clustering_scores", "relabel_detections", "tracking_table",
            "save_mtmc", "edge_labels", "normalize_columns", "pack_reid_features", "pack_reid_features_from_pickles",
            "read_packed_features", "load_packed_features"]

@@ -91,6 +91,7 @@ _PROTOS = {
     "mpn_profile_gram_ms": (C.c_float, []),
     "mpn_shared_gram_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpn_shared_gram_row_range": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mpn_pack_decisions": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "mpn_profile_timeline": (C.c_int, [C.c_int]),
     "mpn_profile_timeline_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "mpn_edge_features_workspace_bytes": (C.c_size_t, [C.POINTER(MpnGraph), C.c_int32]),

@@ -1363,6 +1363,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS) classify_encoded_kernel(const f
   }
 }
 
+// decisions as a bit mask: bit (e & 31) of word e >> 5 (= np.unpackbits(bytes, bitorder="little")); 1/8 of the D2H bytes
+__global__ void __launch_bounds__(256) pack_decisions_kernel(const uint8_t* __restrict__ pred, long long E, uint32_t* __restrict__ words) {
+  pdl_wait();
+  const long long n_words = (E + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = warp0; w < n_words; w += nwarps) {
+    const long long e = (w << 5) + lane;
+    const unsigned int bits = __ballot_sync(0xffffffffu, e < E && pred[e] != 0);
+    if (lane == 0) words[w] = bits;
+  }
+}
+
 __global__ void decide_kernel(const float2* __restrict__ logits, long long E, uint8_t* __restrict__ pred, float* __restrict__ prob1) {
   pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -2420,6 +2433,16 @@ int mpn_forward_sharded_with_edge_features(const mpn_graph* g, const mpn_weights
   MPN_REQUIRE(ef_ws != nullptr && edge_attr_out != nullptr, "forward_sharded_with_edge_features: NULL edge-feature buffer / workspace");
   return forward_sharded_impl(g, w, x, edge_attr_out, L, n_cls, total_edges, logits_out, h_out, pred_out, prob1_out, use_tc, peers, ws,
                               ws_bytes, ef_ws, ef_ws_bytes, stream);
+}
+
+int mpn_pack_decisions(const uint8_t* pred, int64_t E, uint32_t* words_out, void* stream) {
+  MPN_REQUIRE((pred && words_out) || E == 0, "pack_decisions: NULL argument");
+  if (E == 0) return MPN_OK;
+  const long long n_words = (E + 31) >> 5;
+  mpn::launch(pack_decisions_kernel, (int)min((long long)kNumSMs * 8, (long long)div_up(n_words * 32, 256)), 256, 0, (cudaStream_t)stream, pred,
+              (long long)E, words_out);
+  MPN_LAUNCH_OK();
+  return MPN_OK;
 }
 
 int mpn_profile_timeline(int enable) {

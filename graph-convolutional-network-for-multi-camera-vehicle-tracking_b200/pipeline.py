@@ -12,7 +12,8 @@ Nothing here computes: it is stream / event / buffer plumbing around ``TrackletG
 """
 import torch
 
-from .graph import TrackletGraph, release_scope, workspace_scope
+from . import _lib
+from .graph import TrackletGraph, current_stream_ptr, release_scope, workspace_scope
 
 
 class _Slot:
@@ -35,12 +36,16 @@ class GraphStream:
     ``pred_host`` buffer before passing the same buffer to a submit ``depth`` calls later (or simply use ``depth + 1`` buffers).
     """
 
-    def __init__(self, model, device, depth: int = 2, graph_replay: bool = False):
+    def __init__(self, model, device, depth: int = 2, graph_replay: bool = False, packed_decisions: bool = False):
         """``graph_replay``: when a slot sees the same signature (feature shape, camera layout, weights) a second time, the graph
         tables + edge features + forward + decisions of that slot are captured as one CUDA graph over slot-static buffers and
         replayed from then on: one launch instead of ~40 per graph (configs[1]: 0.84 -> 0.79 ms per step, same bits; the win is
         larger for small graphs, whose time is mostly launches).  Off by default: a stream of graphs of ever-changing shapes
-        would only pay the captures."""
+        would only pay the captures.
+        ``packed_decisions``: the decisions travel to the host as a bit mask (``mpn_pack_decisions``: 1 bit per edge, 1/8 of the
+        D2H bytes — on a multi-GPU box the host's memory system, shared by all GPUs, bounds the stream); ``pred_host`` is then
+        pinned uint8 [4 * ceil(E / 32)], ``unpack_decisions(pred_host, E)`` gives the 0/1 array back."""
+        self.packed = bool(packed_decisions)
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.model, self.device, self.depth = model, torch.device(device), int(depth)
@@ -89,8 +94,10 @@ class GraphStream:
                     slot.seen_key, slot.cap, slot.cap_key = key, None, None
             # K0 on the device (does not need x): only the camera layout crosses PCIe
             g = cap.g if cap is not None else self._tables(cam_ids)
-            if pred_host.numel() != g.n_edges or pred_host.dtype != torch.uint8:
-                raise ValueError("pred_host must be uint8 with one entry per edge (%d)" % g.n_edges)
+            n_out = 4 * ((g.n_edges + 31) // 32) if self.packed else g.n_edges
+            if pred_host.numel() != n_out or pred_host.dtype != torch.uint8:
+                raise ValueError("pred_host must be uint8 with %d entries (%s)" % (n_out, "bit mask, 4 * ceil(E / 32) bytes" if self.packed
+                                                                                  else "one per edge"))
             if prob_host is not None and (prob_host.numel() != g.n_edges or prob_host.dtype != torch.float32
                                           or not prob_host.is_pinned()):
                 raise ValueError("prob_host must be pinned float32 with one entry per edge")
@@ -105,19 +112,27 @@ class GraphStream:
             if cap is not None:
                 cap.graph.replay()                           # tables + edge features + forward + decisions: one launch
                 data, pred, prob1 = cap.data, cap.pred, cap.prob1
+                out = cap.bits if self.packed else pred
             else:
                 data, pred, prob1 = self._compute(slot, g)
+                out = self._pack(pred) if self.packed else pred
             slot.compute_done.record(compute)
             self.copy_out.wait_event(slot.compute_done)
             with torch.cuda.stream(self.copy_out):
-                pred_host.copy_(pred, non_blocking=True)
+                pred_host.copy_(out, non_blocking=True)
                 if prob_host is not None:
                     prob_host.copy_(prob1, non_blocking=True)
                 slot.out_done.record(self.copy_out)
-            slot.keep = (g, pred, prob1, data)
+            slot.keep = (g, pred, prob1, data, out)
             slot.busy = True
         self.n_submitted += 1
         return ticket
+
+    def _pack(self, pred):
+        """uint8 [E] decisions -> uint8 [4 * ceil(E / 32)] bit mask, on the current stream."""
+        bits = torch.empty(4 * ((pred.numel() + 31) // 32), dtype=torch.uint8, device=pred.device)
+        _lib.check(_lib.lib().mpn_pack_decisions(pred.data_ptr(), pred.numel(), bits.data_ptr(), current_stream_ptr(pred.device)))
+        return bits
 
     # ---- hooks (ShardedGraphStream overrides them)
     def _device_feature_shape(self, x_host, cam_ids):
@@ -181,6 +196,7 @@ class GraphStream:
                 cap.data.x, cap.data.mpn_graph, cap.data.edge_attr, cap.data.num_nodes = slot.x_dev, cap.g, None, cap.g.n_cols
                 model(cap.data)
                 cap.pred, cap.prob1 = model.last_pred, model.last_prob1
+                cap.bits = self._pack(cap.pred) if self.packed else None
         finally:
             model.fuse_decisions, model.use_cuda_graph = fuse, small
         return cap
@@ -206,6 +222,13 @@ class GraphStream:
                     slot.keep = None
 
 
+def unpack_decisions(bits_host, n_edges: int):
+    """The 0/1 decisions (numpy uint8 [n_edges]) of a ``GraphStream(packed_decisions=True)`` output buffer."""
+    import numpy as np
+    arr = bits_host.numpy() if isinstance(bits_host, torch.Tensor) else np.asarray(bits_host)
+    return np.unpackbits(arr.reshape(-1).view(np.uint8), bitorder="little")[:int(n_edges)]
+
+
 class _Batch:
     """Attribute bag standing in for torch_geometric.data.Data (inference.py:458)."""
 
@@ -218,8 +241,8 @@ class ShardedGraphStream(GraphStream):
     all-gather of graph i+1 overlap the kernels of graph i.  ``submit(x_rows_host, cam_ids, pred_host)``: ``x_rows_host`` =
     rows ``blocks[rank]`` of the feature matrix."""
 
-    def __init__(self, sharded, blocks, device, depth: int = 2):
-        super().__init__(sharded.model, device, depth=depth, graph_replay=False)
+    def __init__(self, sharded, blocks, device, depth: int = 2, packed_decisions: bool = False):
+        super().__init__(sharded.model, device, depth=depth, graph_replay=False, packed_decisions=packed_decisions)
         self.sharded, self.blocks = sharded, [tuple(b) for b in blocks]
         self.rank = sharded.comm.rank
         n0, n1 = self.blocks[self.rank]

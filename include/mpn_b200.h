@@ -332,6 +332,9 @@ int mpn_forward_sharded_with_edge_features(const mpn_graph* g, const mpn_weights
  * Decisions.  Replaces inference.py:475-479 when the caller owns the logits.
  * ---------------------------------------------------------------------------------------------- */
 int mpn_decide(const float* logits_dev, int64_t n_edges, uint8_t* pred_out_dev, float* prob1_out_dev, void* stream);
+/* The decisions (inference.py:479) as a bit mask for the trip to the host: bit (e & 31) of words_out_dev[e >> 5] = pred[e] != 0,
+ * ceil(n_edges / 32) uint32 words (bytes in np.unpackbits(..., bitorder="little") order); 1/8 of the D2H bytes of pred. */
+int mpn_pack_decisions(const uint8_t* pred_dev, int64_t n_edges, uint32_t* words_out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Post-processing (K5).  `act` is dev uint8 [E] (1 = active edge), updated in place; `prob1` dev fp32

@@ -851,3 +851,35 @@ def test_multi_gpu_fused_collectives_torchrun(m):
            "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(root, "tests", "dist_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     assert r.returncode == 0 and "dist_gpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_graph_stream_packed_decisions(m):
+    """GraphStream(packed_decisions=True): the bit mask that crosses PCIe unpacks to exactly the per-edge decisions (ragged E: not
+    a multiple of 32), eager and replayed as a CUDA graph; mpn_pack_decisions on its own for E = 1, 31, 32, 33."""
+    d0 = dev()
+    lib = m._lib.lib()
+    for E in (1, 31, 32, 33, 1000):
+        pred = (torch.rand(E, device=d0) < 0.3).to(torch.uint8)
+        words = torch.zeros(4 * ((E + 31) // 32), dtype=torch.uint8, device=d0)
+        m._lib.check(lib.mpn_pack_decisions(pred.data_ptr(), E, words.data_ptr(), torch.cuda.current_stream(d0).cuda_stream))
+        assert np.array_equal(m.unpack_decisions(words.cpu(), E), pred.cpu().numpy())
+    params = mo.shipped_model_params(1, 1, 64, (32,))
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101").to(d0).eval()
+    n, cams = 45, 3
+    cam = (np.arange(n) * cams // n)
+    x = torch.randn(n, 64).pin_memory()
+    ref_stream = m.GraphStream(net, d0, depth=1)
+    E = int(sum((cam != c).sum() for c in cam))
+    want = torch.empty(E, dtype=torch.uint8).pin_memory()
+    ref_stream.submit(x, cam, want)
+    ref_stream.drain()
+    for replay in (False, True):
+        gs = m.GraphStream(net, d0, depth=2, graph_replay=replay, packed_decisions=True)
+        bufs = [torch.zeros(4 * ((E + 31) // 32), dtype=torch.uint8).pin_memory() for _ in range(3)]
+        for i in range(5):
+            gs.submit(x, cam, bufs[i % 3])
+        gs.drain()
+        for bts in bufs:
+            assert np.array_equal(m.unpack_decisions(bts, E), want.numpy())
+        with pytest.raises(ValueError):
+            gs.submit(x, cam, want)                       # a per-edge buffer where the bit mask is expected
