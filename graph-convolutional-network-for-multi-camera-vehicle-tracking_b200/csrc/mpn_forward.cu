@@ -1067,7 +1067,7 @@ __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
     for (int c = 0; c < 32; ++c) acc[c] = 0.f;
     int pending = 0;                                     // batches of the MMA group in flight whose result has not been accumulated
     int run_first = 0;                                   // first task (segment index) of the current run of one row
-    int c_off = 0, buf = 0;
+    int c_off = 0, buf = 0, issuer = 0;
     bool ok_prev[ATC_NB];
 #pragma unroll
     for (int h = 0; h < ATC_NB; ++h) ok_prev[h] = false;
@@ -1162,8 +1162,8 @@ __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
+        if (tid == issuer) {                             // the issuing duty (~75 instructions) rotates over the four warps: no warp is
+          tc_fence_after();                              // the one the block barrier always waits for
 #pragma unroll
           for (int h = 0; h < ATC_NB; ++h) {
             if (h < nb) {
@@ -1173,6 +1173,7 @@ __global__ void __launch_bounds__(ATC_THREADS, CTAS) apply_tc_kernel(
           }
           umma_commit(&bar);
         }
+        issuer = (issuer + 32) & (ATC_THREADS - 1);
         pending = nb;
         buf ^= 1;
         if (flushed) {

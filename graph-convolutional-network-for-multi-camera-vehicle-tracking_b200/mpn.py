@@ -348,6 +348,8 @@ class MOTMPNet(nn.Module):
         if ea.shape != (g.n_edges, 2):
             raise ValueError("data.edge_attr must be [E,2]")
         L, n_cls = int(self.num_enc_steps), int(self.num_class_steps)
+        if L > 0:
+            n_cls = min(n_cls, L)         # first_class_step <= 0 classifies every step: L outputs (models/mpn.py:281,290)
         n_out = 1 if L == 0 else n_cls
         fused = bool(self.fuse_decisions) and n_out > 0
         if self.use_cuda_graph and g.n_edges <= self.cuda_graph_max_edges and g.n_edges > 1:

@@ -391,6 +391,8 @@ class ShardedMPN:
             raise ValueError("sharded forward needs (row, col)-sorted local edges")
         W = m._weights(dev)
         L, n_cls = int(m.num_enc_steps), int(m.num_class_steps)
+        if L > 0:
+            n_cls = min(n_cls, L)         # as MOTMPNet.forward (models/mpn.py:281,290)
         n_out = 1 if L == 0 else n_cls
         x = x.contiguous().float()
         make_features = local_edge_attr is None          # edge features of this rank's rows computed inside the call

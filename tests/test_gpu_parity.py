@@ -883,3 +883,22 @@ def test_graph_stream_packed_decisions(m):
             assert np.array_equal(m.unpack_decisions(bts, E), want.numpy())
         with pytest.raises(ValueError):
             gs.submit(x, cam, want)                       # a per-edge buffer where the bit mask is expected
+
+
+def test_more_class_steps_than_enc_steps(m):
+    """num_class_steps > num_enc_steps: first_class_step <= 0, the reference classifies at every step and returns L outputs
+    (models/mpn.py:281,290); so does this forward."""
+    params = mo.shipped_model_params(2, 3, 64, (32,))
+    x, ei, cam, _ = mo.synth_graph(60, 3, 5, D=64)
+    sd = mo.init_weights(params, "resnet101", 4)
+    ea = mo.edge_features(x, ei)
+    ref, href = mo.mpn_forward(sd, params, "resnet101", x, ei, ea, dtype=torch.float64)
+    assert len(ref) == 2
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev()).eval()
+    out, h = net(Data(x=x.to(dev()), edge_index=ei.to(dev()), edge_attr=ea.to(dev())))
+    assert len(out["classified_edges"]) == 2
+    for got, want in zip(out["classified_edges"], ref):
+        scale = max(1.0, want.abs().max().item())
+        assert (got.cpu().double() - want).abs().max().item() <= 2e-5 * scale
