@@ -91,6 +91,48 @@ def check_case(rank, world, dev, L, n_cls, N, C, modes, chunk=None, reattach=Fal
     return worst
 
 
+def check_shared_fallback(rank, world, dev, N=360, C=4):
+    """One row of the LAST rank's block lacks an edge (not a dense cross-camera row): that rank's rows go through the Gram + gather
+    path, and every other rank must notice — through the node-table exchange, on the device — and compute all pairs of its own rows
+    instead of waiting for mirrored entries that never come.  Features and logits against the oracle of the modified graph."""
+    params = mo.shipped_model_params(1, 1, 128, (96, 64))
+    x, ei, cam, _ = mo.synth_graph(N, C, 7, D=128, planted=True)
+    victim = N - 2                                               # a row of the last block: drop one of its middle edges
+    rows = np.flatnonzero(ei[0].numpy() == victim)
+    keep = np.ones(ei.shape[1], dtype=bool)
+    keep[rows[len(rows) // 2]] = False
+    ei = ei[:, torch.from_numpy(keep)]
+    sd = mo.init_weights(params, "resnet101", 5)
+    ea = mo.edge_features(x, ei)
+    ref, _ = mo.mpn_forward(sd, params, "resnet101", x, ei, ea, dtype=torch.float64)
+    net = m.MOTMPNet(copy.deepcopy(params), None, "resnet101")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    rowptr = torch.searchsorted(ei[0].contiguous(), torch.arange(N + 1))
+    blocks = m.partition_rows(rowptr, world)
+    n0, n1 = blocks[rank]
+    assert blocks[-1][0] <= victim
+    lo, hi = m.shard_edges(ei, n0, n1)
+    ei_l = ei[:, lo:hi].to(dev)
+    g = m.TrackletGraph(ei_l, N, row_offset=n0, n_rows=n1 - n0)
+    sh = m.ShardedMPN(net)
+    for _rep in range(2):
+        out, _, pred, _ = sh.forward(x.to(dev), ei_l, None, blocks, fuse_decisions=True, graph=g)
+        assert not sh.shared_gram_used(), "a rank used the shared Gram although one rank's rows are not dense cross-camera rows"
+        assert torch.allclose(sh.last_edge_attr.cpu(), ea[lo:hi], rtol=1e-5, atol=1e-5)
+        err = (out["classified_edges"][-1].cpu().double() - ref[-1][lo:hi]).abs().max().item()
+        assert err <= 1e-4 * ref[-1].abs().max().item(), err
+    # and the shared mode comes back for the next dense graph on the same ShardedMPN / exchange buffers
+    x2, ei2, _, _ = mo.synth_graph(N, C, 8, D=128, planted=True)
+    rowptr2 = torch.searchsorted(ei2[0].contiguous(), torch.arange(N + 1))
+    blocks2 = m.partition_rows(rowptr2, world)
+    lo2, hi2 = m.shard_edges(ei2, *blocks2[rank])
+    g2 = m.TrackletGraph(ei2[:, lo2:hi2].to(dev), N, row_offset=blocks2[rank][0], n_rows=blocks2[rank][1] - blocks2[rank][0])
+    sh.forward(x2.to(dev), ei2[:, lo2:hi2].to(dev), None, blocks2, fuse_decisions=True, graph=g2)
+    assert sh.shared_gram_used()
+    assert torch.allclose(sh.last_edge_attr.cpu(), mo.edge_features(x2, ei2)[lo2:hi2], rtol=1e-5, atol=1e-5)
+
+
 def check_post(rank, world, dev, n_nodes=20000, cams=8):
     """Sparse predicted graph (planted clusters + noise), sharded by row block: decisions and reference label integers."""
     src, dst, prob, pred, _ = po.planted_prediction_graph(n_nodes, cams, 9, n_extra_per_node=6.0, flip_on=0.05, flip_off=0.03,
@@ -154,6 +196,7 @@ def main():
     for (L, n_cls, N, C, chunk, reattach) in [(1, 1, 240, 4, None, False), (4, 2, 200, 5, None, False), (2, 1, 600, 3, 128, False),
                                               (1, 1, 600, 3, 256, False), (3, 1, 600, 3, 128, True)]:
         worst = max(worst, check_case(rank, world, dev, L, n_cls, N, C, modes, chunk, reattach))
+    check_shared_fallback(rank, world, dev)
     post_ms = check_post(rank, world, dev)
     check_stream(rank, world, dev)
     t = torch.tensor([worst], device=dev)
