@@ -13,7 +13,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .graph import TrackletGraph, current_stream_ptr, workspace
+from .graph import TrackletGraph, _on_device, current_stream_ptr, workspace
 
 
 def partition_rows(rowptr: torch.Tensor, world: int):
@@ -348,6 +348,18 @@ class ShardedMPN:
         ``max_edges_per_rank`` edges (graphs of ``n_cols`` nodes).  Only needed before a graph larger than 1.25 x the first one."""
         self._peer_memory(n_cols, device).reserve_edge_attr(max_edges_per_rank, device)
 
+    def _blocks_cover(self, blocks, world, n_nodes) -> bool:
+        """Contiguous non-empty row blocks in rank order that cover all nodes (what the shared Gram needs); cached per block list
+        (the check is on the host's critical path of every step)."""
+        key = (tuple(map(tuple, blocks)), int(world), int(n_nodes))
+        hit = self.__dict__.get("_cover_cache")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        ok = (len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == n_nodes and
+              all(blocks[i][1] == blocks[i + 1][0] for i in range(len(blocks) - 1)) and all(b1 > b0 for b0, b1 in blocks))
+        self._cover_cache = (key, ok)
+        return ok
+
     def shared_gram_used(self) -> bool:
         """True when the last fused forward with ``local_edge_attr=None`` took the shared symmetric Gram (every rank's rows dense
         cross-camera); synchronises the stream.  Tests / bench."""
@@ -404,10 +416,7 @@ class ShardedMPN:
             from .edge_features import edge_features
             ea = edge_features(x, None, graph=g)
         elif make_features:
-            contiguous_blocks = (len(blocks) == peers.world and blocks[0][0] == 0 and blocks[-1][1] == x.shape[0] and
-                                 all(blocks[i][1] == blocks[i + 1][0] for i in range(len(blocks) - 1)) and
-                                 all(b1 > b0 for b0, b1 in blocks))
-            shared = self.shared_gram and contiguous_blocks and g.n_edges > 0
+            shared = self.shared_gram and g.n_edges > 0 and self._blocks_cover(blocks, peers.world, x.shape[0])
             ea = peers.edge_attr_buffer(g.n_edges, dev) if shared else torch.empty(g.n_edges, 2, dtype=torch.float32, device=dev)
         else:
             ea = local_edge_attr.contiguous().float()
@@ -418,11 +427,14 @@ class ShardedMPN:
             need = lib.mpn_forward_workspace_bytes(g.ref, C.byref(W), L)
             ws = workspace("forward_sharded", dev, need)
             h_local = torch.empty(g.n_nodes, _lib.MPN_DH, dtype=torch.float32, device=dev)
-            n_layers = int(W.n_node_layers)
-            shard_enc = self.shard_node_encoder and max(W.node_dims[1:n_layers + 1]) <= _lib.MPN_PEER_CSTAT_COLS
+            enc = self.__dict__.get("_enc_mode")                   # (weights struct, layers, sharded encoder?): per weight version
+            if enc is None or enc[0] is not W:
+                nl = int(W.n_node_layers)
+                enc = self._enc_mode = (W, nl, self.shard_node_encoder and max(W.node_dims[1:nl + 1]) <= _lib.MPN_PEER_CSTAT_COLS)
+            n_layers, shard_enc = enc[1], enc[2]
             shared = make_features and self.shared_gram and ea.data_ptr() == (peers.ea_ptrs[peers.rank] if peers.ea_ptrs else -1)
             ctx = peers.ctx(shard_enc, blocks if shared else None)
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 if make_features:
                     ef_ws = workspace("edge_features", dev, lib.mpn_edge_features_workspace_bytes(g.ref, x.shape[1]))
                     _lib.check(lib.mpn_forward_sharded_with_edge_features(
