@@ -173,6 +173,7 @@ struct SplitExact {
 static void split_exact_init(SplitExact& S, const int* src, const int* dst, const float* prob, long long m, int n_nodes, int C,
                              std::vector<int>* global_of_local, const int* seeds = nullptr, long long n_seeds = 0,
                              const uint8_t* sel = nullptr) {
+  const auto t_init0 = std::chrono::steady_clock::now();
   S.m = m; S.prob = prob; S.C = C;
   std::vector<int> local;
   int n = 0;
@@ -212,6 +213,9 @@ static void split_exact_init(SplitExact& S, const int* src, const int* dst, cons
   if (sel) S.alive.assign(sel, sel + m); else S.alive.assign(m, 1);
   S.comp.assign(n, -1); S.wcc.assign(n, -2);               // -2: component not examined yet (registered on first use)
   S.pre.assign(n, 0); S.low.assign(n, 0); S.it.assign(n, 0); S.mark.assign(n, 0);
+  if (getenv("MPN_POST_DEBUG") != nullptr)
+    fprintf(stderr, "[split engine] adjacency of %lld edges / %d nodes built at +%.2f ms\n", m_sel, n,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_init0).count());
   if (seeds == nullptr) {
     std::vector<int> all(n);
     for (int v = 0; v < n; ++v) all[v] = v;
