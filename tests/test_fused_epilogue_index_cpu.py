@@ -1,10 +1,14 @@
-"""CPU check of the index arithmetic behind the (experimental) fused distance epilogue of the Gram GEMM.
+"""CPU check of the index arithmetic behind the fused distance epilogue of the Gram GEMM (csrc/gram_ef.cu).
 
-The kernel (csrc/gemm_tc.cu, EF = true) never looks an edge id up: for graphs whose rows are "all columns but one contiguous
-gap" it computes e = rowptr[i] + j - (j past the gap ? gap length : 0), walks only the tiles on or above the diagonal (symmetric
-Gram), writes the mirrored entries from the same accumulator and skips tiles without edges.  This test replays exactly that walk
-in numpy — gap table by binary search (gap_table_kernel), tile skip vote, direct and mirrored entries — on the reference's
-edge order (inference.py:407-413) and checks that every edge is written exactly once with the right (row, col) pair."""
+The kernel never looks an edge id up: for graphs whose rows are "all columns but one contiguous gap" it computes
+e = rowptr[i] + j - (j past the gap ? gap length : 0), walks only the tiles on or above the diagonal when the row block is the
+whole graph, writes the mirrored entries from the same accumulator and does not list tiles without edges.  This test replays that
+walk in numpy — the gap table and its two end-point checks (the gap search of ge_center_split_kernel; a binary search here, a
+32-ary one there: same answer), the tile list (ge_tile_list_kernel), direct and mirrored entries (the epilogue of
+gram_ef_kernel<false>) — on the reference's edge order (inference.py:407-413) and checks that every edge is written exactly once
+with the right (row, col) pair.  The shipped kernels themselves are checked against the reference's values on the GPU
+(tests/test_gpu_parity.py); the pair-ownership rule of the sharded variant is checked through the library itself
+(tests/test_host_cpu.py::test_shared_gram_every_pair_computed_exactly_once)."""
 import numpy as np
 import pytest
 
@@ -14,7 +18,7 @@ BM = BN = 128
 
 
 def gap_table(rowptr, col, n_cols, with_flag=False):
-    """gap_table_kernel: first k with col[beg+k] != k (binary search on the non-decreasing col[beg+k] - k), gap length, and
+    """The gap search of ge_center_split_kernel: first k with col[beg+k] != k (binary search on the non-decreasing col[beg+k] - k), gap length, and
     the two end-point checks that prove the row is 'all columns but that gap' (else the not_one_gap flag is raised)."""
     gap = np.zeros((rowptr.size - 1, 2), dtype=np.int64)
     not_one_gap = 0
