@@ -260,3 +260,24 @@ def test_shared_gram_every_pair_computed_exactly_once():
             if trial == 0 and n % world == 0:                     # equal blocks: equal shares (antipodal blocks are split in half)
                 assert work.max() - work.min() <= n, (world, work)
     assert lib.mpn_shared_gram_row_range(0, 0, None, 0, None) == -1
+
+
+def test_unpack_decisions_and_block_cover_host_logic():
+    """Host-only pieces of the multi-GPU / stream paths: the bit-mask decisions unpack in np.packbits(bitorder='little') order
+    (what mpn_pack_decisions writes: bit e & 31 of word e >> 5), and the row-block check that gates the shared symmetric Gram."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 32, 33, 1000):
+        pred = (rng.random(n) < 0.4).astype(np.uint8)
+        words = np.zeros(4 * ((n + 31) // 32), dtype=np.uint8)
+        packed = np.packbits(pred, bitorder="little")
+        words[:packed.size] = packed
+        assert np.array_equal(m.unpack_decisions(words, n), pred)
+        assert np.array_equal(m.unpack_decisions(torch.from_numpy(words), n), pred)
+    sh = m.ShardedMPN(None, fused=False)
+    assert sh._blocks_cover([(0, 5), (5, 9)], 2, 9)
+    assert sh._blocks_cover([(0, 5), (5, 9)], 2, 9)               # cached answer
+    assert not sh._blocks_cover([(0, 5), (6, 9)], 2, 9)           # hole
+    assert not sh._blocks_cover([(0, 5), (5, 9)], 2, 10)          # does not reach the last node
+    assert not sh._blocks_cover([(0, 5), (5, 5), (5, 9)], 3, 9)   # empty block
+    assert not sh._blocks_cover([(0, 9)], 2, 9)                   # one block per rank
