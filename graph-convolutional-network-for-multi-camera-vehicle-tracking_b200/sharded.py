@@ -412,6 +412,11 @@ class ShardedMPN:
         pred = torch.empty(g.n_edges, dtype=torch.uint8, device=dev) if fuse_decisions else None
         prob1 = torch.empty(g.n_edges, dtype=torch.float32, device=dev) if fuse_decisions else None
         peers = self._peer_memory(x.shape[0], dev) if (self.fused and L >= 1) else None
+        if peers is not None and g.n_edges == 0:
+            # every rank takes part in every exchange of the fused schedule; a block without edges cannot (its peers would wait
+            # for it until the 10 s trap of the flag wait)
+            raise ValueError("fused sharded forward: this rank's row block [%d, %d) has no edges; balance the blocks by degree "
+                             "(partition_rows) or use ShardedMPN(fused=False)" % (n0, n1))
         if make_features and peers is None:
             from .edge_features import edge_features
             ea = edge_features(x, None, graph=g)
